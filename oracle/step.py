@@ -1,0 +1,73 @@
+"""Oracle: one `feed_data` + `optimize_parameters` iteration (TEST INFRASTRUCTURE).
+
+Restates image.closure (neosr/models/image.py:427-625) and
+image.optimize_parameters (627-662) for the generator-only configurations
+(C1: L1; C3: L1 + VGG perceptual), accumulate = 1, AMP off, no SAM/ECO.
+Autograd supplies the backward pass, exactly as in the reference.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+from torch import Tensor
+
+from . import losses as L
+from .optim import AdanSFState, EMAState, adan_sf_step, clip_grad_norm
+from .swinir import SwinIRConfig, swinir_forward
+
+
+class OracleTrainer:
+    """Holds what `image.__init__`/`init_training_settings` hold: net_g params, the loss
+    configuration, optimizer_g (adan_sf), EMA.  `net_fn(params, lq)` is the generator."""
+
+    def __init__(self, params: dict, net_fn, *, pixel_weight: float | None = 1.0,
+                 percep_weight: float | None = None, vgg_params: dict | None = None,
+                 layer_weights: dict | None = None, optim: dict | None = None,
+                 ema: float = 0.999, grad_clip: bool = True):
+        self.names = list(params)
+        self.params = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        self.net_fn = net_fn
+        self.pixel_weight, self.percep_weight = pixel_weight, percep_weight
+        self.vgg_params, self.layer_weights = vgg_params, layer_weights
+        self.grad_clip = grad_clip
+        self.opt = AdanSFState([self.params[k] for k in self.names], **(optim or {}))
+        self.ema = EMAState([self.params[k] for k in self.names], ema) if ema and ema > 0 else None
+        self.log_dict: OrderedDict = OrderedDict()
+        self.last_grads: dict = {}
+
+    def feed_data(self, data: dict) -> None:  # image.py:374-391 (no augmentation)
+        self.lq, self.gt = data["lq"], data["gt"]
+
+    def optimize_parameters(self, current_iter: int = 0) -> None:
+        out = self.net_fn(self.params, self.lq)
+        self.output = out
+        total = torch.zeros(1)
+        log = OrderedDict()
+        if self.pixel_weight is not None:  # image.py:473-476
+            l_pix = L.l1_loss(out, self.gt, self.pixel_weight)
+            total = total + l_pix
+            log["l_g_pix"] = l_pix
+        if self.percep_weight is not None:  # image.py:491-494
+            l_per = L.vgg_perceptual_loss(self.vgg_params, out, self.gt, self.percep_weight, self.layer_weights)
+            total = total + l_per
+            log["l_g_percep"] = l_per
+        log["l_g_total"] = total
+        plist = [self.params[k] for k in self.names]
+        grads = torch.autograd.grad(total, plist, allow_unused=True)
+        grads = [torch.zeros_like(p) if g is None else g.contiguous().clone() for g, p in zip(grads, plist)]
+        self.grad_norm = clip_grad_norm(grads, 1.0) if self.grad_clip else None  # image.py:533-544
+        self.last_grads = dict(zip(self.names, [g.clone() for g in grads]))
+        if torch.isnan(total).any():  # image.py:611-619
+            raise ValueError("NaN found, aborting training.")
+        self.log_dict = OrderedDict((k, float(v.detach().mean())) for k, v in log.items())
+        adan_sf_step(self.opt, grads)  # image.py:642
+        if self.ema is not None:  # image.py:661-662
+            self.ema.update(plist)
+
+    def get_current_log(self):
+        return self.log_dict
+
+
+def make_swinir_trainer(params: dict, cfg: SwinIRConfig, **kw) -> OracleTrainer:
+    return OracleTrainer(params, lambda p, x: swinir_forward(p, cfg, x), **kw)

@@ -1,0 +1,96 @@
+"""Pin the oracle against the LIVE reference modules (build container only).
+
+Skipped wherever /root/reference is absent (e.g. the GPU box); the committed
+fixtures in tests/golden/ carry the same check there (test_oracle_golden.py).
+"""
+import pytest
+import torch
+
+from oracle import losses as OL
+from oracle import ref_shim
+from oracle.step import make_swinir_trainer
+from oracle.swinir import SwinIRConfig, swinir_forward, swinir_medium_config, swinir_param_shapes, synth_params
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_shim.available(), reason="live reference not mounted")]
+
+TINY = dict(img_size=16, embed_dim=36, depths=(2, 2), num_heads=(3, 3), window_size=8, mlp_ratio=2.0,
+            upsampler="pixelshuffle", resi_connection="1conv", upscale=4)
+
+
+def _ref_swinir(cfgkw, params):
+    ref_shim.activate(4)
+    from neosr.archs.swinir_arch import swinir
+    kw = dict(cfgkw)
+    net = swinir(drop_path_rate=0.0, **kw)
+    missing = net.load_state_dict(params, strict=False)
+    assert not missing.unexpected_keys
+    assert all(("relative_position_index" in k or "attn_mask" in k) for k in missing.missing_keys)
+    return net.train()
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("hw", [(16, 16), (24, 32)])
+def test_swinir_tiny_forward_backward(hw):
+    cfg = SwinIRConfig(**TINY)
+    p = synth_params(swinir_param_shapes(cfg), seed=1)
+    net = _ref_swinir(TINY, p)
+    assert set(swinir_param_shapes(cfg)) == {k for k, _ in net.named_parameters()}
+    x = torch.rand(2, 3, *hw, generator=torch.Generator().manual_seed(2))
+    y_ref = net(x)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y = swinir_forward(pr, cfg, x)
+    assert _rel(y, y_ref) < 1e-5
+    gt = torch.rand_like(y_ref)
+    (y_ref - gt).abs().mean().backward()
+    g = torch.autograd.grad((y - gt).abs().mean(), list(pr.values()))
+    ref_g = dict((k, v.grad) for k, v in net.named_parameters())
+    for k, gi in zip(pr, g):
+        assert _rel(gi, ref_g[k]) < 2e-4, k
+
+
+def test_swinir_medium_forward():
+    cfg = swinir_medium_config(4)
+    p = synth_params(swinir_param_shapes(cfg), seed=0)
+    ref_shim.activate(4)
+    net = ref_shim.build_network({"type": "swinir_medium", "drop_path_rate": 0.0})
+    assert {k: tuple(v.shape) for k, v in net.named_parameters()} == swinir_param_shapes(cfg)
+    net.load_state_dict(p, strict=False)
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        assert _rel(swinir_forward(p, cfg, x), net(x)) < 1e-5
+
+
+def test_perceptual_and_step():
+    """3 iterations of the reference's REAL optimize_parameters vs the oracle trainer."""
+    cfg = SwinIRConfig(**TINY)
+    p = synth_params(swinir_param_shapes(cfg), seed=4)
+    vgg_p = synth_params(OL.vgg19_conv_shapes(), seed=5)
+    ref_shim.activate(4)
+    from neosr.losses.basic_loss import L1Loss
+    net = _ref_swinir(TINY, p)
+    cri_p = ref_shim.build_vgg_perceptual(vgg_p, loss_weight=0.5)
+    okw = dict(lr=1e-3, betas=(0.98, 0.92, 0.987), weight_decay=0.02, schedule_free=True, warmup_steps=1600)
+    model = ref_shim.make_image_model(net, cri_pix=L1Loss(1.0), cri_perceptual=cri_p, optim_kw=okw)
+    tr = make_swinir_trainer(p, cfg, pixel_weight=1.0, percep_weight=0.5, vgg_params=vgg_p, optim=okw, ema=0.999)
+    g = torch.Generator().manual_seed(6)
+    for it in range(3):
+        lq, gt = torch.rand(2, 3, 16, 16, generator=g), torch.rand(2, 3, 64, 64, generator=g)
+        model.feed_data({"lq": lq, "gt": gt})
+        model.optimize_parameters(it)
+        tr.feed_data({"lq": lq, "gt": gt})
+        tr.optimize_parameters(it)
+        ref_log = model.get_current_log()
+        for k, v in tr.get_current_log().items():
+            assert abs(v - ref_log[k]) <= 1e-5 * max(1.0, abs(ref_log[k])), (it, k, v, ref_log[k])
+    ref_params = dict(net.named_parameters())
+    ema_params = dict(model.net_g_ema.module.named_parameters())
+    for i, k in enumerate(tr.names):
+        assert _rel(tr.params[k].detach(), ref_params[k].detach()) < 1e-4, k
+        assert _rel(tr.ema.avg[i], ema_params[k].detach()) < 1e-4, k
+    sd = model.optimizer_g.state_dict()
+    assert set(sd["state"][0]) == {"exp_avg", "exp_avg_sq", "exp_avg_diff", "z", "neg_pre_grad"}
+    assert abs(sd["param_groups"][0]["weight_sum"] - tr.opt.weight_sum) < 1e-12
