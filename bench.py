@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Headline benchmark: LR-crops/s through one full training step (feed_data +
+optimize_parameters) of SwinIR-medium x4, 64->256 RGB crops, L1 + VGG19-perceptual,
+adan_sf + EMA, batch 32 per GPU (BASELINE.json configs[2], "C3").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (B200 kernels, C ABI)
+    python bench.py --impl reference --gpus N ...             # reference arm: the oracle's CPU
+                                                              # restatement of the same step
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# algorithmic work per LR crop for C3 (SURVEY.md §8d / BASELINE.md §3): G fwd+bwd + VGG fwd(x)+fwd(gt)+dgrad(x)
+GFLOP_PER_CROP_C3 = 321.30 + 152.88
+METRIC = "LR-crops/sec (SwinIR-M 4x, 64->256, full training step)"
+
+
+def peaks() -> dict:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+def make_opt(batch: int, dist: bool, rank: int, world: int) -> dict:
+    return {"name": "bench_c3", "model_type": "image", "scale": 4, "is_train": True, "dist": dist, "rank": rank,
+            "world_size": world, "num_gpu": world,
+            "network_g": {"type": "swinir_medium", "drop_path_rate": 0.0, "upscale": 4},
+            "datasets": {"train": {"patch_size": 64, "batch_size": batch}},
+            "train": {"ema": 0.999,
+                      "optim_g": {"type": "adan_sf", "lr": 1e-3, "betas": [0.98, 0.92, 0.987], "weight_decay": 0.02,
+                                  "schedule_free": True, "warmup_steps": 1600},
+                      "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0},
+                      "perceptual_opt": {"type": "vgg_perceptual_loss", "loss_weight": 0.5, "criterion": "chc",
+                                         "allow_random_init": True}},
+            "path": {}}
+
+
+def synth_batches(n: int, batch: int, seed: int, lq_size: int = 64, scale: int = 4):
+    """SURVEY.md §8d synthetic inputs: gt = rand quantised to 8 bit; lq = antialiased bicubic
+    downsample, clamped, quantised.  Returned in pinned host memory."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = []
+    for _ in range(n):
+        gt = torch.rand(batch, 3, lq_size * scale, lq_size * scale, generator=g)
+        gt = torch.round(gt * 255) / 255
+        lq = F.interpolate(gt, scale_factor=1 / scale, mode="bicubic", antialias=True).clamp(0, 1)
+        lq = torch.round(lq * 255) / 255
+        out.append({"lq": lq.contiguous().pin_memory() if torch.cuda.is_available() else lq,
+                    "gt": gt.contiguous().pin_memory() if torch.cuda.is_available() else gt})
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.index)], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------- reference arm
+def cpu_oracle_run(batch: int, steps: int, warmup: int, budget_s: float) -> dict:
+    """Time the oracle's CPU restatement of the same step (bounded sample of the workload)."""
+    import torch
+
+    from oracle import losses as OL
+    from oracle.step import make_swinir_trainer
+    from oracle.swinir import swinir_medium_config, swinir_param_shapes, synth_params
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = swinir_medium_config(4)
+    p = synth_params(swinir_param_shapes(cfg), seed=0)
+    vgg_p = synth_params(OL.vgg19_conv_shapes(), seed=5)
+    tr = make_swinir_trainer(p, cfg, pixel_weight=1.0, percep_weight=0.5, vgg_params=vgg_p, ema=0.999,
+                             optim=dict(lr=1e-3, betas=(0.98, 0.92, 0.987), weight_decay=0.02, schedule_free=True,
+                                        warmup_steps=1600))
+    data = synth_batches(2, batch, seed=1024)
+    t_start = time.perf_counter()
+    for i in range(warmup):
+        tr.feed_data(data[i % 2])
+        tr.optimize_parameters(i)
+    times = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        tr.feed_data(data[i % 2])
+        tr.optimize_parameters(warmup + i)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+    mean = sum(times) / len(times)
+    return {"value": batch / mean, "unit": "crops/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} timed + {warmup} warm-up step(s) of the full C3 step at batch {batch} (crops/s is "
+                      f"batch-normalised), torch CPU fp32, {cores} threads", "ms_per_step": mean * 1e3,
+            "steps": len(times)}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = 1
+    r = cpu_oracle_run(b, max(1, min(args.steps, 6)), min(args.warmup, 1), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "crops/s", "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3 swinir_medium x4 64->256 L1+perceptual adan_sf+EMA (CPU oracle port, "
+                                   "bounded sample)", "batch_per_step": b},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------- our arm
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    from neosr_b200 import ops
+    from neosr_b200.models import build_model
+    B = args.batch
+    model = build_model(make_opt(B, world > 1, rank, world))
+    if world > 1:  # identical replicas: broadcast rank-0 initial weights (what DDP does at wrap time)
+        for p in model.net_g.parameters():
+            dist.broadcast(p.data, 0)
+    pool = synth_batches(args.pool, B, seed=1024 + rank)
+    dev_pool = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in pool]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(loop, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loop(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    it = [0]
+
+    def step_resident(i):
+        model.feed_data(dev_pool[i % len(dev_pool)])
+        model.optimize_parameters(it[0])
+        it[0] += 1
+
+    losses = []
+
+    def step_e2e(i):
+        model.feed_data(pool[i % len(pool)])       # pinned host -> device inside the timed region
+        model.optimize_parameters(it[0])
+        it[0] += 1
+        losses.append(model.get_current_log()["l_g_total"])  # device -> host read of the step's loss
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.LAUNCHES
+    ms = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES - l0
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    # one extra step with per-launch CUDA events: which kernel dominates, and its roofline
+    ops.PROFILE = []
+    step_resident(0)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    agg: dict = {}
+    for name, key, flops, nbytes, a, b in prof:
+        r = agg.setdefault((name, key), {"ms": 0.0, "n": 0, "flops": flops, "bytes": nbytes})
+        r["ms"] += a.elapsed_time(b)
+        r["n"] += 1
+    step_ms_prof = sum(r["ms"] for r in agg.values())
+    fam: dict = {}
+    for (name, key), r in agg.items():
+        f = fam.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+        f["ms"] += r["ms"]; f["n"] += r["n"]; f["flops"] += r["flops"] * r["n"]; f["bytes"] += r["bytes"] * r["n"]
+    pk = peaks()
+    (dname, dkey), drec = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    avg_ms = drec["ms"] / drec["n"]
+    is_tensor = drec["flops"] > 0
+    if is_tensor:
+        ach = drec["flops"] / (avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_sustained"], "traffic": None}
+    else:
+        ach = drec["bytes"] / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": None}
+    roof.update({"kernel": dname, "shape": list(dkey), "avg_launch_ms": avg_ms, "launches_per_step": drec["n"],
+                 "share_of_step": drec["ms"] / step_ms_prof, "peak_source": pk["source"],
+                 "engine": os.environ.get("NSR_ENGINE", "auto")})
+
+    if rank == 0:
+        crops = B * world * args.steps
+        value = crops / (ms * 1e-3)
+        step_tflops = value / world * GFLOP_PER_CROP_C3 / 1e3
+        out_dir = ROOT / "gpurun_out"
+        try:
+            out_dir.mkdir(exist_ok=True)
+            table = sorted(({"kernel": n, "shape": list(k), **r} for (n, k), r in agg.items()), key=lambda r: -r["ms"])
+            (out_dir / f"kernel_table_n{world}.json").write_text(json.dumps(
+                {"step_ms_sum_of_kernels": step_ms_prof, "families": fam, "kernels": table}, indent=1))
+        except OSError:
+            pass
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_oracle_run(1, 2, 1, budget_s=60.0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        bytes_in = sum(v.numel() * 4 for v in pool[0].values())
+        line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded rand, 8-bit quantised; VGG19 weights "
+                                                               "seeded-random: no pretrained weights offline)",
+                "config": {"workload": "C3: swinir_medium x4, 64x64->256x256 RGB, L1(1.0)+vgg19 perceptual(0.5, chc), "
+                                       "adan_sf + EMA 0.999, grad-clip 1.0, drop_path 0", "batch_per_gpu": B,
+                           "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": "per-step working set (activations > 40 GB at B=32) >> 126 MB L2; pool of "
+                                 f"{len(pool)} distinct batches cycled"},
+                "clocks": sampler.summary(),
+                "e2e": {"value": crops / (ms_e2e * 1e-3), "unit": "crops/s", "h2d_bytes_per_step": bytes_in,
+                        "d2h_bytes_per_step": 4 * 3, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches,
+                "roofline": roof,
+                "step_roofline": {"bound": "tensor", "achieved": step_tflops, "unit": "TFLOP/s",
+                                  "peak": pk["bf16_sustained"], "frac": step_tflops / pk["bf16_sustained"],
+                                  "gflop_per_crop": GFLOP_PER_CROP_C3,
+                                  "note": "whole step vs sustained bf16 peak; the fp32-parity engines are exact-fp32 "
+                                          "SIMT or 3xBF16-split tcgen05 (ceiling = peak/3)"},
+                "cpu_baseline": cpu, "final_loss": losses[-1] if losses else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="LR crops per GPU per step (C3: 32)")
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,268 @@
+/*
+ * neosr_b200 — C ABI of the B200-native neosr training-step kernels.
+ *
+ * The reference (muslll/neosr) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md §0 fact 1, §8b).  Each entry point below therefore cites the
+ * reference ATen/cuDNN call site (file:line under /root/reference) that it
+ * replaces.  Conventions for every function:
+ *
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers to
+ *     fp32 (unless stated) buffers owned by the caller, borrowed for the call;
+ *   - activations are NHWC ("tokens": [batch*h*w, channels]), weights are either
+ *     the reference's own layout (OIHW / [out,in]) or an opaque packed buffer
+ *     produced by nsr_pack_weight();
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), never
+ *     synchronised; entry points are re-entrant (no global mutable state);
+ *   - return 0 on success, a negative NSR_E_* code otherwise; nsr_last_error()
+ *     returns a thread-local message.  Nothing throws or exits.
+ */
+#ifndef NEOSR_B200_H
+#define NEOSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSR_OK 0
+#define NSR_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define NSR_E_CUDA (-2)      /* CUDA runtime error (message in nsr_last_error) */
+#define NSR_E_WORKSPACE (-3) /* workspace too small */
+
+/* activation codes for the fused GEMM/conv epilogues */
+#define NSR_ACT_NONE 0
+#define NSR_ACT_RELU 1
+#define NSR_ACT_LRELU 2 /* slope = act_slope */
+#define NSR_ACT_GELU 3  /* exact erf GELU (torch.nn.GELU default) */
+#define NSR_ACT_PRELU 4 /* per-output-channel slope vector */
+
+/* engine selection for the contraction kernels */
+#define NSR_ENGINE_AUTO 0
+#define NSR_ENGINE_SIMT 1    /* exact-fp32 CUDA-core implicit GEMM */
+#define NSR_ENGINE_TCGEN05 2 /* tcgen05 (UMMA) 3xBF16-split, fp32 accumulate in TMEM */
+
+const char* nsr_last_error(void);
+int nsr_version(void);
+/* 1 when the current device is sm_100 and the tcgen05 kernels may be used. */
+int nsr_device_supports_tcgen05(void);
+
+/* ------------------------------------------------------------------ contraction ---- */
+/*
+ * One descriptor drives Linear and Conv2d (stride 1) as an implicit GEMM over NHWC:
+ *   y[p, co] = epilogue( sum_{r,s,ci} x[p shifted by (r-pad, s-pad), ci] * w[co, r, s, ci] )
+ * Replaces: nn.Linear (swinir_arch.py:27-29,139,143 — qkv/proj/fc1/fc2), nn.Conv2d
+ * (swinir_arch.py:889,630,964,978-982,782; compact_arch.py:48-72; esrgan_arch.py:97-106;
+ * vgg_arch.py:134 features) and their autograd dgrad (same call with the dgrad-packed
+ * weight).  Epilogue, in order:
+ *   v = acc + bias[co]                       (bias may be NULL)
+ *   if (y_pre) y_pre[p,co] = v               (pre-activation copy, e.g. GELU input)
+ *   v = act(v)                               (NSR_ACT_*)
+ *   if (mul_actgrad) v *= act'(aux[p,co])    (chain rule through the producer's
+ *                                             activation; aux = its saved output /
+ *                                             pre-activation, code in actgrad)
+ *   if (row_scale) v *= row_scale[p / (h*w)] (per-sample DropPath factor, arch_util.py:118-131)
+ *   if (residual) v += residual[p,co]
+ *   y[p,co] = v
+ */
+typedef struct NsrConv {
+  int32_t batch, h, w;   /* input == output spatial size (stride 1, "same" padding) */
+  int32_t cin, cout;
+  int32_t kh, kw, pad;
+  int32_t x_ld;          /* floats between consecutive pixels of x   (>= cin)  */
+  int32_t y_ld;          /* floats between consecutive pixels of y/y_pre/residual/aux (>= cout) */
+  int32_t act;           /* NSR_ACT_* applied to the output */
+  float act_slope;
+  int32_t actgrad;       /* NSR_ACT_* whose derivative multiplies the output (0 = none) */
+  float actgrad_slope;
+  int32_t engine;        /* NSR_ENGINE_* */
+  const float* x;
+  const void* w_packed;  /* from nsr_pack_weight (fprop or dgrad flavour) */
+  const float* bias;
+  const float* prelu;    /* [cout] slopes for NSR_ACT_PRELU (act or actgrad) */
+  const float* aux;
+  const float* row_scale;
+  const float* residual;
+  float* y_pre;
+  float* y;
+} NsrConv;
+
+int nsr_conv_fprop(const NsrConv* d, void* stream);
+
+/* Packed-weight buffers. `flavour` 0 = fprop  (w[co][r][s][ci]),
+ *                         1 = dgrad  (w'[ci][kh-1-r][kw-1-s][co], i.e. the transposed,
+ *                                     180deg-rotated filter so that dgrad is an fprop).
+ * Source is the reference layout OIHW ([cout, cin, kh, kw]; Linear = kh=kw=1).
+ * The buffer holds an fp32 copy (SIMT engine) followed by the bf16 hi/lo tile images the
+ * tcgen05 engine streams with bulk copies. */
+size_t nsr_packed_weight_bytes(int cout, int cin, int kh, int kw, int flavour);
+int nsr_pack_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int flavour,
+                    void* packed, void* stream);
+
+/*
+ * Weight gradient of the same contraction (autograd of nn.Linear / nn.Conv2d weights):
+ *   dw[co, ci, r, s] = sum_p dy[p, co] * x[p shifted by (r-pad, s-pad), ci]      (OIHW out)
+ *   dbias[co]        = sum_p dy[p, co]                                            (optional)
+ * Deterministic split-K: partials go to `workspace`, a second pass reduces them in a
+ * fixed order.  nsr_conv_wgrad_workspace() gives the size needed.
+ */
+typedef struct NsrWgrad {
+  int32_t batch, h, w;
+  int32_t cin, cout;
+  int32_t kh, kw, pad;
+  int32_t x_ld, dy_ld;
+  int32_t engine;
+  const float* x;
+  const float* dy;
+  float* dw;     /* [cout, cin, kh, kw] fp32, overwritten */
+  float* dbias;  /* [cout] or NULL, overwritten */
+  void* workspace;
+  size_t workspace_bytes;
+} NsrWgrad;
+
+size_t nsr_conv_wgrad_workspace(const NsrWgrad* d);
+int nsr_conv_wgrad(const NsrWgrad* d, void* stream);
+
+/* ------------------------------------------------------------------ layout / elementwise */
+/* y_nhwc[b,h,w,c] = x_nchw[b,c,h,w] * scale[c] + shift[c]
+ * Replaces `(x - self.mean) * self.img_range` (swinir_arch.py:1041-1042) and the VGG input
+ * normalisation (vgg_arch.py:189-190) fused with the NCHW->NHWC transpose. */
+int nsr_nchw_to_nhwc_affine(const float* x, float* y, int batch, int c, int h, int w,
+                            const float* scale, const float* shift, void* stream);
+/* y_nchw[b,c,h,w] = x_nhwc[b,h,w,c] * scale[c] + shift[c]   (swinir_arch.py:1077 and the
+ * backward of the above: pass shift = NULL). */
+int nsr_nhwc_to_nchw_affine(const float* x, float* y, int batch, int c, int h, int w,
+                            const float* scale, const float* shift, void* stream);
+
+/* nn.PixelShuffle(r) on NHWC (swinir_arch.py:783,786,810; compact_arch.py:73):
+ *   y[b, h*r+i, w*r+j, c] = x[b, h, w, c*r*r + i*r + j]          (bit-exact index map)
+ * inverse != 0 runs the map backwards (autograd of pixel_shuffle == pixel_unshuffle). */
+int nsr_pixel_shuffle_nhwc(const float* x, float* y, int batch, int h, int w, int c_out, int r,
+                           int inverse, void* stream);
+
+/* nn.MaxPool2d(2,2) on NHWC (vgg_arch.py:143) and its backward fused with the ReLU mask of
+ * the pooled tensor and an optional extra gradient term:
+ *   dx[i] = (x[i] > 0 ? routed(dy) : 0) + (dextra ? dextra[i] : 0) */
+int nsr_maxpool2_nhwc(const float* x, float* y, int batch, int h, int w, int c, void* stream);
+int nsr_maxpool2_relu_bwd_nhwc(const float* x, const float* dy, const float* dextra, float* dx,
+                               int batch, int h, int w, int c, void* stream);
+
+/* y = a * alpha + b * beta (b may be NULL). Gradient accumulation glue. */
+int nsr_axpby(const float* a, float alpha, const float* b, float beta, float* y, size_t n, void* stream);
+/* dx = dy * act'(aux) + (dextra ? dextra : 0) */
+int nsr_actgrad_mul(const float* dy, const float* aux, const float* dextra, float* dx, size_t n,
+                    int act, float slope, void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm ---------- */
+/* nn.LayerNorm(c, eps) over the last dim of [rows, c] (swinir_arch.py:284,297,708,960). */
+int nsr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                      float* mean, float* rstd, int rows, int c, float eps, void* stream);
+/* dx = LN'(dy) + (dres ? dres : 0); dgamma/dbeta reduced deterministically via workspace
+ * (>= nsr_layernorm_bwd_workspace(c) bytes). */
+size_t nsr_layernorm_bwd_workspace(int c);
+int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                      const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                      int rows, int c, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ window attention --- */
+/*
+ * Fused (shifted-)window multi-head self-attention core on token-major qkv:
+ *   cyclic shift + window_partition (swinir_arch.py:353-364), q*scale, q@k^T, +relative-
+ *   position bias table[index] (185-195), +shift mask (197-202, calculate_mask 313-341 as a
+ *   function of token coordinates), softmax, @v, window_reverse + un-shift (376-386).
+ * qkv:  [batch*h*w, 3*c]  (output of the qkv Linear in natural token order)
+ * out:  [batch*h*w, c]    (input of the proj Linear, natural token order)
+ * bias_table: [(2*ws-1)^2, heads].  use_mask != 0 adds the {0,-100} mask for `shift`.
+ * Supported: ws*ws <= 64, head_dim <= 32 (SwinIR S/M/L at window 8).
+ */
+int nsr_window_attn_fwd(const float* qkv, const float* bias_table, float* out, int batch, int h,
+                        int w, int c, int heads, int ws, int shift, int use_mask, float scale,
+                        void* stream);
+size_t nsr_window_attn_bwd_workspace(int heads, int ws);
+int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv,
+                        float* dbias_table, int batch, int h, int w, int c, int heads, int ws,
+                        int shift, int use_mask, float scale, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ losses ------------- */
+/* All loss kernels ADD weight*loss into *loss_accum (device scalar) and write d(loss)/d(pred)
+ * (already multiplied by weight and upstream 1.0) into dpred; reductions are two-pass and
+ * deterministic.  workspace >= nsr_loss_workspace() bytes. */
+size_t nsr_loss_workspace(void);
+/* L1Loss (basic_loss.py:45-53): weight * mean|pred - target|. */
+int nsr_l1_loss(const float* pred, const float* target, float* dpred, size_t n, float weight,
+                float* loss_accum, float* loss_value, void* workspace, void* stream);
+/* chc_loss(huber, lambda=0, clip [cmin,cmax]) on pre-scaled inputs (basic_loss.py:180-219 as
+ * used by vgg_perceptual_loss.py:145,232-236): weight * mean(clamp(sqrt((s*(a-b))^2+1e-12))). */
+int nsr_charbonnier_loss(const float* a, const float* b, float* da, size_t n, float in_scale,
+                         float clip_min, float clip_max, float weight, float* loss_accum,
+                         float* loss_value, void* workspace, void* stream);
+/* BCEWithLogits vs a constant label (gan_loss.py:62-82). */
+int nsr_bce_logits_loss(const float* logits, float* dlogits, size_t n, float label, float weight,
+                        float* loss_accum, float* loss_value, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ optimizer ---------- */
+/* Multi-tensor table: one entry per parameter tensor (device pointers).  The table itself
+ * lives in device memory; `chunk_base` is the running count of NSR_OPT_CHUNK-element chunks
+ * before this tensor (host-computed prefix sum) so a CTA can binary-search its tensor. */
+#define NSR_OPT_CHUNK 4096
+typedef struct NsrParamEntry {
+  float* p;
+  float* g;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* exp_avg_diff;
+  float* z;
+  float* neg_pre_grad;
+  float* ema;          /* may be NULL */
+  int64_t n;
+  int64_t chunk_base;
+} NsrParamEntry;
+
+/* sum of squares of all gradients -> *sumsq (device float, overwritten); deterministic
+ * (fixed chunk->CTA assignment, fixed-order final reduce). */
+size_t nsr_grad_sumsq_workspace(void);
+int nsr_grad_sumsq(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
+                   float* sumsq, void* workspace, void* stream);
+
+/* Scalars of one adan_sf step, derived on the host in double precision exactly where the
+ * reference derives them (adan_sf.py:176-211, 289-330) and rounded to fp32 once. */
+typedef struct NsrAdanSF {
+  float beta1, one_minus_beta1;
+  float beta2, one_minus_beta2;
+  float beta3, one_minus_beta3;
+  float bias_correction3_sqrt, eps;
+  float decay;            /* 1 - lr * weight_decay */
+  float ckp1;             /* schedule-free interpolation weight (lerp params -> z) */
+  float step_size;        /* lr * (bias_correction1 * (1 - ckp1))        [sf]  | lr / bc1        */
+  float step_size_diff;   /* lr * (beta2 / bias_correction2 * (1 - ckp1)) [sf] | lr * beta2 / bc2 */
+  float lr;               /* z -= lr * g */
+  int32_t schedule_free;
+  int32_t first_step;     /* neg_pre_grad := -g before the update (adan_sf.py:226-227) */
+  float max_norm;         /* clip_grad_norm_ threshold (image.py:540-544); <= 0 disables */
+  float ema_lerp;         /* 1 - decay of AveragedModel EMA; <= 0 disables */
+  int32_t ema_first;      /* first EMA update copies (n_averaged == 0) */
+} NsrAdanSF;
+/* Fused clip_grad_norm_ + adan_sf._multi_tensor_adan + EMA lerp (image.py:540-544,642,661-662;
+ * adan_sf.py:264-330).  `sumsq` is the device scalar from nsr_grad_sumsq (may be NULL when
+ * max_norm <= 0).  Gradient buffers are left holding the clipped gradient, as in the reference. */
+int nsr_adan_sf_step(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
+                     const NsrAdanSF* hp, const float* sumsq, void* stream);
+
+typedef struct NsrAdamW {
+  float beta1, one_minus_beta1, beta2, one_minus_beta2;
+  float eps, decay;       /* decay = 1 - lr * weight_decay */
+  float step_size;        /* lr / bias_correction1 */
+  float bias_correction2_sqrt;
+  float max_norm, ema_lerp;
+  int32_t ema_first;
+} NsrAdamW;
+/* torch.optim.AdamW (base.py:154-155) with the same clip + EMA fusion; uses exp_avg/exp_avg_sq. */
+int nsr_adamw_step(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
+                   const NsrAdamW* hp, const float* sumsq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEOSR_B200_H */

@@ -1,0 +1,410 @@
+"""SwinIR generator on the B200 kernels — drop-in for neosr/archs/swinir_arch.py.
+
+Same registry names (`swinir_small`, `swinir_medium`, `swinir_large`), constructor keywords,
+parameter/buffer names and shapes (``state_dict()`` interchanges with the reference key for
+key), and `forward(x[B,3,h,w] in [0,1]) -> [B,3,s*h,s*w]`.  The implementation is not a port:
+there is no per-op autograd graph.  One explicit forward and one explicit backward drive the
+C-ABI kernels over NHWC token tensors:
+
+  * roll / window_partition / window_reverse / attention mask (swinir_arch.py:41-78, 313-386)
+    are index math inside `nsr_window_attn_{fwd,bwd}` — nothing is materialised;
+  * Linear and Conv2d are one implicit-GEMM family with fused bias / GELU / LeakyReLU /
+    residual epilogues (`nsr_conv_fprop`), dgrad is the same kernel on the rotated filter,
+    wgrad is a deterministic split-K kernel;
+  * PatchEmbed/PatchUnEmbed transposes (712-716, 757-761) vanish because everything stays NHWC.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import Tensor, nn
+from torch.nn.init import trunc_normal_
+
+from .. import ops
+from ..engine import ParamSet
+from ..registry import ARCH_REGISTRY
+from .arch_util import net_opt
+
+
+def _rel_pos_index(ws: int) -> Tensor:
+    """Buffer `relative_position_index` (swinir_arch.py:120-137); the kernels recompute it
+    arithmetically, the buffer exists for state_dict compatibility."""
+    ar = torch.arange(ws)
+    cy, cx = torch.meshgrid(ar, ar, indexing="ij")
+    cy, cx = cy.reshape(-1), cx.reshape(-1)
+    return (cy[:, None] - cy[None, :] + ws - 1) * (2 * ws - 1) + (cx[:, None] - cx[None, :] + ws - 1)
+
+
+def _shift_mask(h: int, w: int, ws: int, shift: int) -> Tensor:
+    """Buffer `attn_mask` (swinir_arch.py:313-341) as a closed form of token coordinates."""
+    def region(n):
+        i = torch.arange(n)
+        return (i >= n - ws).long() + (i >= n - shift).long()
+    ids = (region(h)[:, None] * 3 + region(w)[None, :]).float()
+    ids = ids.view(h // ws, ws, w // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    diff = ids[:, None, :] - ids[:, :, None]
+    return torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
+
+
+class _Attn(nn.Module):
+    def __init__(self, dim: int, ws: int, heads: int, qkv_bias: bool):
+        super().__init__()
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) ** 2, heads))
+        self.register_buffer("relative_position_index", _rel_pos_index(ws))
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, res, heads, ws, shift, mlp_ratio, qkv_bias, drop_path):
+        super().__init__()
+        if min(res) <= ws:
+            raise ValueError("img_size must exceed window_size (the reference then disables windows; unsupported)")
+        self.shift_size, self.window_size, self.drop_prob = shift, ws, float(drop_path)
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = _Attn(dim, ws, heads, qkv_bias)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+        self.register_buffer("attn_mask", _shift_mask(res[0], res[1], ws, shift) if shift > 0 else None)
+
+
+class _Group(nn.Module):
+    def __init__(self, blocks):
+        super().__init__()
+        self.blocks = nn.ModuleList(blocks)
+
+
+def _resi_conv(dim: int, kind: str) -> nn.Module:
+    if kind == "1conv":
+        return nn.Conv2d(dim, dim, 3, 1, 1)
+    return nn.Sequential(nn.Conv2d(dim, dim // 4, 3, 1, 1), nn.LeakyReLU(0.2, True),
+                         nn.Conv2d(dim // 4, dim // 4, 1, 1, 0), nn.LeakyReLU(0.2, True),
+                         nn.Conv2d(dim // 4, dim, 3, 1, 1))
+
+
+class _RSTB(nn.Module):
+    def __init__(self, blocks, dim, resi):
+        super().__init__()
+        self.residual_group = _Group(blocks)
+        self.conv = _resi_conv(dim, resi)
+
+
+class _Norm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+
+
+class swinir(nn.Module):
+    """Constructor mirrors neosr/archs/swinir_arch.py:849-874."""
+
+    def __init__(self, img_size=32, patch_size=1, in_chans=3, embed_dim=60, depths=(6, 6, 6, 6),
+                 num_heads=(6, 6, 6, 6), flash_attn=False, window_size=8, mlp_ratio=2.0, qkv_bias=True,
+                 qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=nn.LayerNorm,
+                 ape=False, patch_norm=True, use_checkpoint=False, upscale=None, img_range=1.0,
+                 upsampler="pixelshuffle", resi_connection="1conv", **kwargs):
+        super().__init__()
+        if upscale is None:
+            upscale = net_opt()[0]
+        if patch_size != 1 or ape or flash_attn or drop_rate or attn_drop_rate or norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("neosr_b200.swinir: patch_size!=1 / ape / flash_attn / dropout are not "
+                                      "part of the B200 hot path (reference defaults only)")
+        if upsampler not in ("pixelshuffle", "pixelshuffledirect") or resi_connection != "1conv":
+            raise NotImplementedError(f"neosr_b200.swinir: upsampler={upsampler!r}/resi={resi_connection!r} "
+                                      "not built yet (pixelshuffle[direct] + 1conv are)")
+        nf = 64
+        self.img_range, self.upscale, self.upsampler = img_range, upscale, upsampler
+        self.embed_dim, self.window_size, self.num_heads = embed_dim, window_size, tuple(num_heads)
+        self.depths, self.patch_norm, self.qk_scale = tuple(depths), patch_norm, qk_scale
+        self.in_chans, self.num_feat, self.mlp_ratio = in_chans, nf, mlp_ratio
+        self.mean = torch.full((1, 3, 1, 1), 0.5) if in_chans == 3 else torch.zeros(1, 1, 1, 1)
+        res = (img_size, img_size)
+
+        self.conv_first = nn.Conv2d(in_chans, embed_dim, 3, 1, 1)
+        self.patch_embed = _Norm(embed_dim) if patch_norm else nn.Module()
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        self.layers = nn.ModuleList()
+        k = 0
+        for li, depth in enumerate(depths):
+            blocks = [_Block(embed_dim, res, num_heads[li], window_size, 0 if i % 2 == 0 else window_size // 2,
+                             mlp_ratio, qkv_bias, dpr[k + i]) for i in range(depth)]
+            k += depth
+            self.layers.append(_RSTB(blocks, embed_dim, resi_connection))
+        self.norm = nn.LayerNorm(embed_dim)
+        self.conv_after_body = _resi_conv(embed_dim, resi_connection)
+        if upsampler == "pixelshuffle":
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, nf, 3, 1, 1), nn.LeakyReLU(inplace=True))
+            ups = []
+            if (upscale & (upscale - 1)) == 0:
+                for _ in range(int(math.log2(upscale))):
+                    ups += [nn.Conv2d(nf, 4 * nf, 3, 1, 1), nn.PixelShuffle(2)]
+            elif upscale == 3:
+                ups += [nn.Conv2d(nf, 9 * nf, 3, 1, 1), nn.PixelShuffle(3)]
+            else:
+                raise ValueError(f"scale {upscale} is not supported. Supported scales: 2^n and 3.")
+            self.upsample = nn.Sequential(*ups)
+            self.conv_last = nn.Conv2d(nf, in_chans, 3, 1, 1)
+        else:
+            self.upsample = nn.Sequential(nn.Conv2d(embed_dim, upscale ** 2 * in_chans, 3, 1, 1),
+                                          nn.PixelShuffle(upscale))
+        self.apply(self._init_weights)
+        self._ps: ParamSet | None = None
+        self._affine: dict = {}
+
+    @staticmethod
+    def _init_weights(m):  # swinir_arch.py:1008-1015
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def param_set(self) -> ParamSet:
+        if self._ps is None or any(self._ps._params[n] is not p for n, p in self.named_parameters()):
+            self._ps = ParamSet(self)
+        return self._ps
+
+    def _consts(self, device):
+        c = self._affine.get(device)
+        if c is None:
+            m = self.mean.to(device).flatten().expand(self.in_chans).contiguous()
+            r = float(self.img_range)
+            c = {"in_scale": torch.full((self.in_chans,), r, device=device),
+                 "in_shift": (-m * r).contiguous(),
+                 "out_scale": torch.full((self.in_chans,), 1.0 / r, device=device),
+                 "out_shift": m.clone()}
+            self._affine[device] = c
+        return c
+
+    def _drop_scales(self, batch: int, device):
+        """Per-sample DropPath factors drawn exactly like arch_util.drop_path (118-131)."""
+        out = []
+        for layer in self.layers:
+            for blk in layer.residual_group.blocks:
+                if blk.drop_prob == 0.0 or not self.training:
+                    out.append(None)
+                    continue
+                keep = 1.0 - blk.drop_prob
+                pair = []
+                for _ in range(2):
+                    t = torch.empty(batch, device=device).bernoulli_(keep)
+                    if keep > 0.0:
+                        t.div_(keep)
+                    pair.append(t)
+                out.append(tuple(pair))
+        return out
+
+    # ------------------------------------------------------------------ explicit forward
+    def engine_forward(self, x: Tensor, save: bool):
+        """x: [B,C,h,w] CUDA fp32.  Returns (y [B,C,s*h,s*w], saved-activations dict or None)."""
+        if not x.is_cuda:
+            raise RuntimeError("neosr_b200.swinir runs on CUDA (sm_100a) only; there is no CPU path")
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        ws = self.window_size
+        if H % ws or W % ws:
+            raise ValueError(f"input {H}x{W} must be a multiple of window_size {ws}")
+        ps = self.param_set()
+        k = self._consts(x.device)
+        S: dict = {"shape": (B, H, W)} if save else None
+        drops = self._drop_scales(B, x.device)
+
+        def lin(name, t, **kw):
+            return ops.conv_fprop(t, ps.pw(name + ".weight"), ps.p(name + ".bias") if ps.has(name + ".bias") else None, **kw)
+
+        xin = ops.nchw_to_nhwc_affine(x, k["in_scale"], k["in_shift"])
+        f0 = lin("conv_first", xin)
+        if self.patch_norm:
+            t, mu, rs = ops.layernorm_fwd(f0, ps.p("patch_embed.norm.weight"), ps.p("patch_embed.norm.bias"))
+            if save:
+                S["pe"] = (mu, rs)
+        else:
+            t = f0
+        if save:
+            S["xin"], S["f0"], S["blocks"], S["layers"] = xin, f0, [], []
+        bi_glob = 0
+        for li, layer in enumerate(self.layers):
+            inp = t
+            heads = self.num_heads[li]
+            scale = self.qk_scale or (self.embed_dim // heads) ** -0.5
+            for bi, blk in enumerate(layer.residual_group.blocks):
+                pre = f"layers.{li}.residual_group.blocks.{bi}."
+                ds = drops[bi_glob]
+                bi_glob += 1
+                ln1, mu1, rs1 = ops.layernorm_fwd(t, ps.p(pre + "norm1.weight"), ps.p(pre + "norm1.bias"))
+                qkv = lin(pre + "attn.qkv", ln1)
+                att = ops.window_attn_fwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), heads, ws,
+                                          blk.shift_size, scale)
+                x1 = lin(pre + "attn.proj", att, residual=t, row_scale=ds[0] if ds else None)
+                ln2, mu2, rs2 = ops.layernorm_fwd(x1, ps.p(pre + "norm2.weight"), ps.p(pre + "norm2.bias"))
+                a, hpre = lin(pre + "mlp.fc1", ln2, act="gelu", want_pre=True)
+                x2 = lin(pre + "mlp.fc2", a, residual=x1, row_scale=ds[1] if ds else None)
+                if save:
+                    S["blocks"].append((t, mu1, rs1, ln1, qkv, att, x1, mu2, rs2, ln2, hpre, a, ds))
+                t = x2
+            y = lin(f"layers.{li}.conv", t, residual=inp)
+            if save:
+                S["layers"].append(t)
+            t = y
+        xn, mun, rsn = ops.layernorm_fwd(t, ps.p("norm.weight"), ps.p("norm.bias"))
+        body = lin("conv_after_body", xn, residual=f0)
+        if save:
+            S["final"] = (t, mun, rsn, xn, body)
+        if self.upsampler == "pixelshuffle":
+            u0 = lin("conv_before_upsample.0", body, act="lrelu", act_slope=0.01)
+            cur, ups = u0, []
+            n_up = len(self.upsample) // 2
+            for i in range(n_up):
+                r = self.upsample[2 * i + 1].upscale_factor
+                c = lin(f"upsample.{2 * i}", cur)
+                nxt = ops.pixel_shuffle(c, r)
+                ups.append((cur, r))
+                cur = nxt
+            out = lin("conv_last", cur)
+            if save:
+                S["tail"] = (u0, ups, cur)
+        else:
+            c = lin("upsample.0", body)
+            out = ops.pixel_shuffle(c, self.upscale)
+        y = ops.nhwc_to_nchw_affine(out, k["out_scale"], k["out_shift"])
+        return y, S
+
+    # ------------------------------------------------------------------ explicit backward
+    def engine_backward(self, S: dict, dy: Tensor) -> None:
+        """Writes d(loss)/d(param) for every parameter into the ParamSet's flat gradient buffer
+        (overwrite semantics).  dy: [B,C,s*h,s*w]."""
+        ps = self.param_set()
+        ps.ensure_grads(dy.device)
+        k = self._consts(dy.device)
+        ws = self.window_size
+
+        def bwd(name, x_in, g, need_dx=True, **epi):
+            w = ps.p(name + ".weight")
+            kh = w.shape[2] if w.dim() == 4 else 1
+            has_b = ps.has(name + ".bias")
+            ops.conv_wgrad(x_in, g, ps.g(name + ".weight"), ps.g(name + ".bias") if has_b else None, kh, kh)
+            if need_dx:
+                return ops.conv_fprop(g, ps.pw(name + ".weight"), None, dgrad=True, **epi)
+            return None
+
+        def scaled(g, s):  # DropPath: branch gradient = s[b] * g
+            if s is None:
+                return g
+            B = g.shape[0]
+            return (g.view(B, -1) * s.view(B, 1)).view_as(g).contiguous()
+
+        g = ops.nchw_to_nhwc_affine(dy.contiguous().float(), k["out_scale"], None)
+        if self.upsampler == "pixelshuffle":
+            u0, ups, last_in = S["tail"]
+            g = bwd("conv_last", last_in, g)
+            for i in reversed(range(len(ups))):
+                src, r = ups[i]
+                g = ops.pixel_unshuffle(g, r)
+                if i == 0:
+                    g = bwd(f"upsample.{2 * i}", src, g, actgrad="lrelu", actgrad_slope=0.01, aux=u0)
+                else:
+                    g = bwd(f"upsample.{2 * i}", src, g)
+            t_last, mun, rsn, xn, body = S["final"]
+            g = bwd("conv_before_upsample.0", body, g)
+        else:
+            t_last, mun, rsn, xn, body = S["final"]
+            g = ops.pixel_unshuffle(g, self.upscale)
+            g = bwd("upsample.0", body, g)
+        df0 = g  # through the `+ x` skip of conv_after_body (swinir_arch.py:1047)
+        g = bwd("conv_after_body", xn, g)
+        g = ops.layernorm_bwd(g, t_last, ps.p("norm.weight"), mun, rsn, ps.g("norm.weight"), ps.g("norm.bias"))
+        nblk = len(S["blocks"])
+        bi_glob = nblk
+        for li in reversed(range(len(self.layers))):
+            heads = self.num_heads[li]
+            scale = self.qk_scale or (self.embed_dim // heads) ** -0.5
+            dinp = g
+            g = bwd(f"layers.{li}.conv", S["layers"][li], g)
+            depth = len(self.layers[li].residual_group.blocks)
+            for bi in reversed(range(depth)):
+                bi_glob -= 1
+                pre = f"layers.{li}.residual_group.blocks.{bi}."
+                t0, mu1, rs1, ln1, qkv, att, x1, mu2, rs2, ln2, hpre, a, ds = S["blocks"][bi_glob]
+                shift = self.layers[li].residual_group.blocks[bi].shift_size
+                gb = scaled(g, ds[1] if ds else None)
+                dh = bwd(pre + "mlp.fc2", a, gb, actgrad="gelu", aux=hpre)
+                dln2 = bwd(pre + "mlp.fc1", ln2, dh)
+                g1 = ops.layernorm_bwd(dln2, x1, ps.p(pre + "norm2.weight"), mu2, rs2, ps.g(pre + "norm2.weight"),
+                                       ps.g(pre + "norm2.bias"), dres=g)
+                gb = scaled(g1, ds[0] if ds else None)
+                datt = bwd(pre + "attn.proj", att, gb)
+                dqkv = ops.window_attn_bwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
+                                           ps.g(pre + "attn.relative_position_bias_table"), heads, ws, shift, scale)
+                dln1 = bwd(pre + "attn.qkv", ln1, dqkv)
+                g = ops.layernorm_bwd(dln1, t0, ps.p(pre + "norm1.weight"), mu1, rs1, ps.g(pre + "norm1.weight"),
+                                      ps.g(pre + "norm1.bias"), dres=g1)
+            g = ops.axpby(g, 1.0, dinp, 1.0)
+        if self.patch_norm:
+            mu, rs = S["pe"]
+            g = ops.layernorm_bwd(g, S["f0"], ps.p("patch_embed.norm.weight"), mu, rs,
+                                  ps.g("patch_embed.norm.weight"), ps.g("patch_embed.norm.bias"), dres=df0)
+        else:
+            g = ops.axpby(g, 1.0, df0, 1.0)
+        bwd("conv_first", S["xin"], g, need_dx=False)
+
+    # ------------------------------------------------------------------ nn.Module surface
+    def train(self, mode: bool = True):
+        if self._ps is not None:
+            self._ps.invalidate_packed()
+        return super().train(mode)
+
+    def forward(self, x: Tensor) -> Tensor:
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not need_grad:
+            return self.engine_forward(x, save=False)[0]
+        return _SwinIRFn.apply(x, self, *self.parameters())
+
+
+class _SwinIRFn(torch.autograd.Function):
+    """Makes the explicit engine a single autograd node so the module also works under the
+    reference's own `closure` (loss.backward(), image.py:531)."""
+
+    @staticmethod
+    def forward(ctx, x, net, *params):
+        y, saved = net.engine_forward(x, save=True)
+        ctx.net, ctx.saved = net, saved
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        net = ctx.net
+        net.engine_backward(ctx.saved, dy)
+        ctx.saved = None
+        ps = net.param_set()
+        grads = [ps.g(n) if p.requires_grad else None for n, p in net.named_parameters()]
+        return (None, None, *grads)
+
+
+@ARCH_REGISTRY.register()
+def swinir_small(**kwargs):
+    return swinir(img_size=64, depths=[6, 6, 6, 6], embed_dim=60, num_heads=[6, 6, 6, 6],
+                  upsampler="pixelshuffledirect", resi_connection="1conv", **kwargs)
+
+
+@ARCH_REGISTRY.register()
+def swinir_medium(**kwargs):
+    return swinir(img_size=48, depths=[6, 6, 6, 6, 6, 6], embed_dim=180, num_heads=[6, 6, 6, 6, 6, 6],
+                  upsampler="pixelshuffle", resi_connection="1conv", **kwargs)
+
+
+@ARCH_REGISTRY.register()
+def swinir_large(**kwargs):
+    return swinir(img_size=64, embed_dim=240, depths=[6] * 9, num_heads=[8] * 9, upsampler="nearest+conv",
+                  resi_connection="3conv", **kwargs)

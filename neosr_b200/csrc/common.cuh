@@ -1,0 +1,98 @@
+// Shared helpers for the neosr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/neosr_b200.h"
+
+namespace nsr {
+
+void set_error(const char* fmt, ...);
+
+#define NSR_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      nsr::set_error(__VA_ARGS__);          \
+      return NSR_E_INVALID;                 \
+    }                                       \
+  } while (0)
+
+#define NSR_CHECK_LAUNCH(name)                                                    \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      nsr::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));     \
+      return NSR_E_CUDA;                                                          \
+    }                                                                             \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- activation math shared by every epilogue -------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case NSR_ACT_RELU: return v > 0.f ? v : 0.f;
+    case NSR_ACT_LRELU:
+    case NSR_ACT_PRELU: return v > 0.f ? v : v * slope;
+    case NSR_ACT_GELU: return gelu_erf(v);
+    default: return v;
+  }
+}
+// derivative of act evaluated from `aux`: for (L)ReLU aux may be the activation OUTPUT
+// (sign is preserved for slope > 0); for GELU / PReLU aux is the PRE-activation.
+__device__ __forceinline__ float act_grad(float aux, int act, float slope) {
+  switch (act) {
+    case NSR_ACT_RELU: return aux > 0.f ? 1.f : 0.f;
+    case NSR_ACT_LRELU:
+    case NSR_ACT_PRELU: return aux > 0.f ? 1.f : slope;
+    case NSR_ACT_GELU: return gelu_erf_grad(aux);
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// packed-weight buffer geometry (see nsr_pack_weight in include/neosr_b200.h)
+struct PackedGeom {
+  int n, taps, c;        // GEMM view W[n][tap][c]
+  int n_pad64;           // n rounded up to 64
+  int cblks;             // ceil(c / 64)
+  size_t f32_bytes;      // fp32 region (1024-aligned)
+  size_t bf16_bytes;     // hi/lo tile images
+};
+static inline PackedGeom packed_geom(int cout, int cin, int kh, int kw, int flavour) {
+  PackedGeom g;
+  g.n = flavour == 0 ? cout : cin;
+  g.c = flavour == 0 ? cin : cout;
+  g.taps = kh * kw;
+  g.n_pad64 = (g.n + 63) / 64 * 64;
+  g.cblks = (g.c + 63) / 64;
+  g.f32_bytes = align_up((size_t)g.n * g.taps * g.c * sizeof(float), 1024);
+  g.bf16_bytes = (size_t)g.taps * g.cblks * 2 * g.n_pad64 * 128;
+  return g;
+}
+
+}  // namespace nsr

@@ -1,0 +1,167 @@
+// C-ABI entry points for the contraction family (Linear / Conv2d fprop, dgrad, wgrad) and
+// the weight packer.  Engine dispatch lives here.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace nsr {
+int conv_fprop_simt(const NsrConv& d, cudaStream_t st);
+int conv_wgrad_simt(const NsrWgrad& d, cudaStream_t st);
+size_t conv_wgrad_workspace_simt(const NsrWgrad& d);
+// tcgen05 engine (igemm_tc.cu)
+bool conv_fprop_tc_supported(const NsrConv& d);
+int conv_fprop_tc(const NsrConv& d, cudaStream_t st);
+bool conv_wgrad_tc_supported(const NsrWgrad& d);
+size_t conv_wgrad_workspace_tc(const NsrWgrad& d);
+int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st);
+
+static int forced_engine() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("NSR_ENGINE");
+    cached = NSR_ENGINE_AUTO;
+    if (e && (!strcmp(e, "simt") || !strcmp(e, "1"))) cached = NSR_ENGINE_SIMT;
+    if (e && (!strcmp(e, "tcgen05") || !strcmp(e, "2"))) cached = NSR_ENGINE_TCGEN05;
+  }
+  return cached;
+}
+
+// ---- weight packing ---------------------------------------------------------------------
+// fp32 region: W[n][tap][c]; flavour 0: n=co, c=ci, tap=(r,s); flavour 1: n=ci, c=co, tap flipped.
+__global__ void pack_weight_f32(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int kh,
+                                int kw, int flavour) {
+  const int taps = kh * kw;
+  const int N = flavour == 0 ? cout : cin, C = flavour == 0 ? cin : cout;
+  const size_t total = (size_t)N * taps * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t r = i / C;
+    const int tap = (int)(r % taps);
+    const int n = (int)(r / taps);
+    const int co = flavour == 0 ? n : c, ci = flavour == 0 ? c : n;
+    const int src_tap = flavour == 0 ? tap : taps - 1 - tap;  // 180-degree rotation
+    out[i] = w[((size_t)co * cin + ci) * taps + src_tap];
+  }
+}
+
+// bf16 hi/lo tile images (see common.cuh PackedGeom and igemm_tc.cu): for k-block kb=(tap,cblk),
+// half h, 64-row block j: 8 KiB tile, row r = 128 B, 16-byte chunk ch stored at ch ^ (r & 7).
+__global__ void pack_weight_bf16(const float* __restrict__ wf32, uint8_t* __restrict__ img, PackedGeom g) {
+  const int nblk = g.n_pad64 / 64;
+  const size_t total = (size_t)g.taps * g.cblks * g.n_pad64 * 8;  // one thread per (kb, n, chunk)
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i & 7);
+    size_t r = i >> 3;
+    const int n = (int)(r % g.n_pad64);
+    const int kb = (int)(r / g.n_pad64);
+    const int tap = kb / g.cblks, cblk = kb - tap * g.cblks;
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cblk * 64 + ch * 8 + e;
+      float v = 0.f;
+      if (n < g.n && c < g.c) v = wf32[((size_t)n * g.taps + tap) * g.c + c];
+      hi[e] = __float2bfloat16_rn(v);
+      lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
+    }
+    const int j = n >> 6, row = n & 63;
+    const size_t tile_hi = ((size_t)(kb * 2 + 0) * nblk + j) * 8192;
+    const size_t tile_lo = ((size_t)(kb * 2 + 1) * nblk + j) * 8192;
+    const size_t off = (size_t)row * 128 + (size_t)((ch ^ (row & 7)) * 16);
+    *reinterpret_cast<uint4*>(img + tile_hi + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(img + tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+}  // namespace nsr
+
+using namespace nsr;
+
+extern "C" size_t nsr_packed_weight_bytes(int cout, int cin, int kh, int kw, int flavour) {
+  PackedGeom g = packed_geom(cout, cin, kh, kw, flavour);
+  return g.f32_bytes + g.bf16_bytes;
+}
+
+extern "C" int nsr_pack_weight(const float* w, int cout, int cin, int kh, int kw, int flavour, void* packed,
+                               void* stream) {
+  NSR_CHECK_ARG(w && packed && cout > 0 && cin > 0 && kh > 0 && kw > 0 && (flavour == 0 || flavour == 1),
+                "nsr_pack_weight: bad arguments");
+  NSR_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 1023) == 0 || (reinterpret_cast<uintptr_t>(packed) & 255) == 0,
+                "nsr_pack_weight: packed buffer must be 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PackedGeom g = packed_geom(cout, cin, kh, kw, flavour);
+  const size_t total = (size_t)g.n * g.taps * g.c;
+  int blocks = ceil_div(total, 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  pack_weight_f32<<<blocks, 256, 0, st>>>(w, reinterpret_cast<float*>(packed), cout, cin, kh, kw, flavour);
+  NSR_CHECK_LAUNCH("pack_weight_f32");
+  const size_t t2 = (size_t)g.taps * g.cblks * g.n_pad64 * 8;
+  blocks = ceil_div(t2, 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  pack_weight_bf16<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(packed),
+                                          reinterpret_cast<uint8_t*>(packed) + g.f32_bytes, g);
+  NSR_CHECK_LAUNCH("pack_weight_bf16");
+  return NSR_OK;
+}
+
+static int check_conv(const NsrConv* d) {
+  NSR_CHECK_ARG(d, "nsr_conv_fprop: null descriptor");
+  NSR_CHECK_ARG(d->batch > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "nsr_conv_fprop: bad geometry");
+  NSR_CHECK_ARG(d->kh > 0 && d->kw > 0 && d->kh == 2 * d->pad + 1 && d->kw == 2 * d->pad + 1,
+                "nsr_conv_fprop: only stride-1 'same' convolutions (k = 2*pad+1) are supported");
+  NSR_CHECK_ARG(d->x_ld >= d->cin && d->y_ld >= d->cout, "nsr_conv_fprop: leading dims too small");
+  NSR_CHECK_ARG(d->x && d->w_packed && d->y, "nsr_conv_fprop: null x / w / y");
+  NSR_CHECK_ARG(!(d->actgrad) || d->aux, "nsr_conv_fprop: actgrad needs aux");
+  NSR_CHECK_ARG(!(d->act == NSR_ACT_PRELU || d->actgrad == NSR_ACT_PRELU) || d->prelu, "nsr_conv_fprop: prelu slopes missing");
+  NSR_CHECK_ARG(d->act >= 0 && d->act <= NSR_ACT_PRELU && d->actgrad >= 0 && d->actgrad <= NSR_ACT_PRELU,
+                "nsr_conv_fprop: bad activation code");
+  return NSR_OK;
+}
+
+extern "C" int nsr_conv_fprop(const NsrConv* d, void* stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int eng = d->engine;
+  if (eng == NSR_ENGINE_AUTO) eng = forced_engine();
+  if (eng == NSR_ENGINE_TCGEN05) {
+    NSR_CHECK_ARG(conv_fprop_tc_supported(*d), "nsr_conv_fprop: shape not supported by the tcgen05 engine");
+    return conv_fprop_tc(*d, st);
+  }
+  if (eng == NSR_ENGINE_AUTO && conv_fprop_tc_supported(*d)) return conv_fprop_tc(*d, st);
+  return conv_fprop_simt(*d, st);
+}
+
+static int check_wgrad(const NsrWgrad* d) {
+  NSR_CHECK_ARG(d, "nsr_conv_wgrad: null descriptor");
+  NSR_CHECK_ARG(d->batch > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "nsr_conv_wgrad: bad geometry");
+  NSR_CHECK_ARG(d->kh == 2 * d->pad + 1 && d->kw == 2 * d->pad + 1, "nsr_conv_wgrad: only stride-1 'same' convolutions");
+  NSR_CHECK_ARG(d->x_ld >= d->cin && d->dy_ld >= d->cout, "nsr_conv_wgrad: leading dims too small");
+  NSR_CHECK_ARG(d->x && d->dy && d->dw, "nsr_conv_wgrad: null x / dy / dw");
+  return NSR_OK;
+}
+
+static bool wgrad_use_tc(const NsrWgrad* d) {
+  int eng = d->engine;
+  if (eng == NSR_ENGINE_AUTO) eng = forced_engine();
+  if (eng == NSR_ENGINE_SIMT) return false;
+  return conv_wgrad_tc_supported(*d);
+}
+
+extern "C" size_t nsr_conv_wgrad_workspace(const NsrWgrad* d) {
+  if (!d) return 0;
+  size_t a = conv_wgrad_workspace_simt(*d);
+  size_t b = conv_wgrad_tc_supported(*d) ? conv_wgrad_workspace_tc(*d) : 0;
+  return a > b ? a : b;
+}
+
+extern "C" int nsr_conv_wgrad(const NsrWgrad* d, void* stream) {
+  int rc = check_wgrad(d);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int eng = d->engine == NSR_ENGINE_AUTO ? forced_engine() : d->engine;
+  if (eng == NSR_ENGINE_TCGEN05)
+    NSR_CHECK_ARG(conv_wgrad_tc_supported(*d), "nsr_conv_wgrad: shape not supported by the tcgen05 engine");
+  if (wgrad_use_tc(d)) return conv_wgrad_tc(*d, st);
+  return conv_wgrad_simt(*d, st);
+}

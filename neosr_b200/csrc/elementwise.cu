@@ -1,0 +1,211 @@
+// Layout / elementwise kernels: NCHW<->NHWC affine, pixel (un)shuffle, 2x2 max-pool fwd/bwd,
+// axpby, activation-gradient multiply.  All HBM-bound; 64-bit indexing, grid-stride loops
+// sized to a multiple of the SM count.
+#include "common.cuh"
+
+namespace nsr {
+
+static inline int ew_blocks(size_t n, int threads = 256) {
+  size_t b = (n + threads - 1) / threads;
+  const size_t cap = (size_t)kNumSMs * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+// NCHW -> NHWC with per-channel affine. Tiled transpose through smem: tile = 32 pixels x C<=32
+// channels would be wasteful for C=3, so the C<=4 image case is handled per pixel (reads are
+// coalesced per channel plane, writes are 12-byte contiguous per pixel).
+__global__ void nchw_to_nhwc_small(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW,
+                                   const float* __restrict__ scale, const float* __restrict__ shift) {
+  const size_t total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / HW, p = i - b * HW;
+    for (int c = 0; c < C; ++c) {
+      float v = x[(b * C + c) * HW + p];
+      v = v * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f);
+      y[i * C + c] = v;
+    }
+  }
+}
+__global__ void nhwc_to_nchw_small(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW,
+                                   const float* __restrict__ scale, const float* __restrict__ shift) {
+  const size_t total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / HW, p = i - b * HW;
+    for (int c = 0; c < C; ++c) {
+      float v = x[i * C + c];
+      v = v * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f);
+      y[(b * C + c) * HW + p] = v;
+    }
+  }
+}
+// general C: 32x32 smem tile transpose over (pixel, channel)
+__global__ void transpose_affine_tile(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int to_nhwc,
+                                      const float* __restrict__ scale, const float* __restrict__ shift) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (to_nhwc) {  // read x[b][c][p] (p fastest), write y[b][p][c] (c fastest)
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j, p = p0 + tx;
+      tile[j][tx] = (c < C && p < HW) ? x[((size_t)b * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int p = p0 + j, c = c0 + tx;
+      if (c < C && p < HW) y[((size_t)b * HW + p) * C + c] = tile[tx][j] * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f);
+    }
+  } else {  // read x[b][p][c], write y[b][c][p]
+    for (int j = ty; j < 32; j += 8) {
+      const int p = p0 + j, c = c0 + tx;
+      tile[j][tx] = (c < C && p < HW) ? x[((size_t)b * HW + p) * C + c] * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j, p = p0 + tx;
+      if (c < C && p < HW) y[((size_t)b * C + c) * HW + p] = tile[tx][j];
+    }
+  }
+}
+
+// y[b, h*r+i, w*r+j, c] = x[b, h, w, c*r*r + i*r + j]; one thread per OUTPUT element group.
+__global__ void pixel_shuffle_nhwc(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int Co,
+                                   int r, int inverse) {
+  const size_t total = (size_t)B * H * r * W * r * Co;
+  const int Ci = Co * r * r;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(o % Co);
+    size_t q = o / Co;
+    const int ow = (int)(q % ((size_t)W * r));
+    q /= (size_t)W * r;
+    const int oh = (int)(q % ((size_t)H * r));
+    const size_t b = q / ((size_t)H * r);
+    const int hh = oh / r, i = oh - hh * r, ww = ow / r, j = ow - ww * r;
+    const size_t xi = ((b * H + hh) * W + ww) * Ci + (size_t)c * r * r + i * r + j;
+    y[inverse ? xi : o] = x[inverse ? o : xi];
+  }
+}
+
+__global__ void maxpool2_nhwc(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)B * Ho * Wo * C;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(o % C);
+    size_t q = o / C;
+    const int ow = (int)(q % Wo);
+    q /= Wo;
+    const int oh = (int)(q % Ho);
+    const size_t b = q / Ho;
+    const float* p = x + ((b * H + oh * 2) * W + ow * 2) * C + c;
+    const float v0 = p[0], v1 = p[C], v2 = p[(size_t)W * C], v3 = p[(size_t)W * C + C];
+    y[o] = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+  }
+}
+// dx for every input element: routed gradient (first max in scan order wins, like ATen) times
+// the ReLU mask of x, plus optional extra term.
+__global__ void maxpool2_relu_bwd_nhwc(const float* __restrict__ x, const float* __restrict__ dy,
+                                       const float* __restrict__ dextra, float* __restrict__ dx, int B, int H, int W,
+                                       int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)B * H * W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t q = i / C;
+    const int w = (int)(q % W);
+    q /= W;
+    const int h = (int)(q % H);
+    const size_t b = q / H;
+    float g = 0.f;
+    const int oh = h >> 1, ow = w >> 1;
+    if (oh < Ho && ow < Wo) {
+      const float* p = x + ((b * H + oh * 2) * W + ow * 2) * C + c;
+      const float v[4] = {p[0], p[C], p[(size_t)W * C], p[(size_t)W * C + C]};
+      int am = 0;
+      float best = v[0];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k] > best) { best = v[k]; am = k; }
+      const int me = (h & 1) * 2 + (w & 1);
+      if (me == am && x[i] > 0.f) g = dy[((b * Ho + oh) * Wo + ow) * C + c];
+    }
+    dx[i] = g + (dextra ? dextra[i] : 0.f);
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta,
+                             float* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = a[i] * alpha + (b ? b[i] * beta : 0.f);
+}
+__global__ void actgrad_mul_kernel(const float* __restrict__ dy, const float* __restrict__ aux,
+                                   const float* __restrict__ dextra, float* __restrict__ dx, size_t n, int act,
+                                   float slope) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * act_grad(aux[i], act, slope) + (dextra ? dextra[i] : 0.f);
+}
+
+}  // namespace nsr
+using namespace nsr;
+
+static int layout_affine(const float* x, float* y, int B, int C, int H, int W, const float* scale, const float* shift,
+                         int to_nhwc, cudaStream_t st) {
+  NSR_CHECK_ARG(x && y && B > 0 && C > 0 && H > 0 && W > 0, "nsr_layout_affine: bad arguments");
+  const int HW = H * W;
+  if (C <= 4) {
+    const size_t n = (size_t)B * HW;
+    if (to_nhwc) nchw_to_nhwc_small<<<ew_blocks(n), 256, 0, st>>>(x, y, B, C, HW, scale, shift);
+    else nhwc_to_nchw_small<<<ew_blocks(n), 256, 0, st>>>(x, y, B, C, HW, scale, shift);
+  } else {
+    dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
+    transpose_affine_tile<<<grid, block, 0, st>>>(x, y, C, HW, to_nhwc, scale, shift);
+  }
+  NSR_CHECK_LAUNCH("layout_affine");
+  return NSR_OK;
+}
+extern "C" int nsr_nchw_to_nhwc_affine(const float* x, float* y, int B, int C, int H, int W, const float* scale,
+                                        const float* shift, void* stream) {
+  return layout_affine(x, y, B, C, H, W, scale, shift, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int nsr_nhwc_to_nchw_affine(const float* x, float* y, int B, int C, int H, int W, const float* scale,
+                                        const float* shift, void* stream) {
+  return layout_affine(x, y, B, C, H, W, scale, shift, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int nsr_pixel_shuffle_nhwc(const float* x, float* y, int B, int H, int W, int Co, int r, int inverse,
+                                       void* stream) {
+  NSR_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && Co > 0 && r > 0, "nsr_pixel_shuffle_nhwc: bad arguments");
+  const size_t n = (size_t)B * H * r * W * r * Co;
+  // forward: x = [B,H,W,Co*r*r] -> y = [B,H*r,W*r,Co]; inverse: x = [B,H*r,W*r,Co] -> y = [B,H,W,Co*r*r]
+  pixel_shuffle_nhwc<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, H, W, Co, r, inverse);
+  NSR_CHECK_LAUNCH("pixel_shuffle_nhwc");
+  return NSR_OK;
+}
+extern "C" int nsr_maxpool2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  NSR_CHECK_ARG(x && y && B > 0 && H > 1 && W > 1 && C > 0, "nsr_maxpool2_nhwc: bad arguments");
+  const size_t n = (size_t)B * (H / 2) * (W / 2) * C;
+  maxpool2_nhwc<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, H, W, C);
+  NSR_CHECK_LAUNCH("maxpool2_nhwc");
+  return NSR_OK;
+}
+extern "C" int nsr_maxpool2_relu_bwd_nhwc(const float* x, const float* dy, const float* dextra, float* dx, int B, int H,
+                                           int W, int C, void* stream) {
+  NSR_CHECK_ARG(x && dy && dx && B > 0 && H > 1 && W > 1 && C > 0, "nsr_maxpool2_relu_bwd_nhwc: bad arguments");
+  const size_t n = (size_t)B * H * W * C;
+  maxpool2_relu_bwd_nhwc<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, dy, dextra, dx, B, H, W, C);
+  NSR_CHECK_LAUNCH("maxpool2_relu_bwd_nhwc");
+  return NSR_OK;
+}
+extern "C" int nsr_axpby(const float* a, float alpha, const float* b, float beta, float* y, size_t n, void* stream) {
+  NSR_CHECK_ARG(a && y, "nsr_axpby: null");
+  if (n == 0) return NSR_OK;
+  axpby_kernel<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, alpha, b, beta, y, n);
+  NSR_CHECK_LAUNCH("axpby");
+  return NSR_OK;
+}
+extern "C" int nsr_actgrad_mul(const float* dy, const float* aux, const float* dextra, float* dx, size_t n, int act,
+                                float slope, void* stream) {
+  NSR_CHECK_ARG(dy && aux && dx, "nsr_actgrad_mul: null");
+  if (n == 0) return NSR_OK;
+  actgrad_mul_kernel<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, aux, dextra, dx, n, act, slope);
+  NSR_CHECK_LAUNCH("actgrad_mul");
+  return NSR_OK;
+}

@@ -1,0 +1,297 @@
+// Fused (shifted-)window attention core, fp32 CUDA-core version.
+//
+// One CTA = one (window, head).  The cyclic shift, window partition/reverse and the {0,-100}
+// shift mask are pure index math on token coordinates (nothing is materialised); the relative
+// position index is computed arithmetically ((iy-jy+ws-1)*(2ws-1) + (ix-jx+ws-1), identical to
+// the reference's registered buffer, swinir_arch.py:120-137).  Softmax uses warp shuffles.
+// Backward recomputes P, and reduces the bias-table gradient deterministically.
+#include "common.cuh"
+
+namespace nsr {
+
+constexpr int WA_N = 64;    // max tokens per window
+constexpr int WA_D = 32;    // max head dim
+constexpr int WA_LD = 33;   // padded row stride for [N][D] tiles
+constexpr int WA_PLD = 65;  // padded row stride for [N][N] tiles
+constexpr int WA_THREADS = 128;
+
+struct WinGeom {
+  int B, H, W, C, heads, ws, shift, use_mask, N, D, nwh, nww;
+  float scale;
+};
+
+__device__ __forceinline__ void win_token_map(const WinGeom& g, int wi, int n, int& tok, int& rid) {
+  const int per = g.nwh * g.nww;
+  const int b = wi / per, rem = wi - b * per;
+  const int wy = rem / g.nww, wx = rem - wy * g.nww;
+  const int iy = n / g.ws, ix = n - iy * g.ws;
+  const int hs = wy * g.ws + iy, wsx = wx * g.ws + ix;  // coordinates in the SHIFTED image
+  int ho = hs + g.shift, wo = wsx + g.shift;            // torch.roll(x, -shift): shifted[i] = x[(i+shift) % n]
+  if (ho >= g.H) ho -= g.H;
+  if (wo >= g.W) wo -= g.W;
+  tok = (b * g.H + ho) * g.W + wo;
+  const int rh = hs < g.H - g.ws ? 0 : (hs < g.H - g.shift ? 1 : 2);  // calculate_mask slices
+  const int rw = wsx < g.W - g.ws ? 0 : (wsx < g.W - g.shift ? 1 : 2);
+  rid = rh * 3 + rw;
+}
+
+__device__ __forceinline__ int rel_index(int ws, int i, int j) {
+  const int iy = i / ws, ix = i - iy * ws, jy = j / ws, jx = j - jy * ws;
+  return (iy - jy + ws - 1) * (2 * ws - 1) + (ix - jx + ws - 1);
+}
+
+// scores for rows [wp*16, wp*16+16) x cols {lane, lane+32}: acc = A[i][:] . Bm[j][:]
+__device__ __forceinline__ void rows_dot(const float* __restrict__ A, const float* __restrict__ Bm, int N, int D,
+                                         int wp, int lane, float (&acc)[16][2]) {
+#pragma unroll
+  for (int r = 0; r < 16; ++r) acc[r][0] = acc[r][1] = 0.f;
+  const bool has1 = lane + 32 < N;
+  const bool has0 = lane < N;
+  for (int d = 0; d < D; ++d) {
+    const float b0 = has0 ? Bm[lane * WA_LD + d] : 0.f;
+    const float b1 = has1 ? Bm[(lane + 32) * WA_LD + d] : 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float a = A[(wp * 16 + r) * WA_LD + d];
+      acc[r][0] = fmaf(a, b0, acc[r][0]);
+      acc[r][1] = fmaf(a, b1, acc[r][1]);
+    }
+  }
+}
+
+// softmax over the 2-per-lane row fragments, in place; masked-out columns (>= N) get 0.
+__device__ __forceinline__ void rows_bias_softmax(const WinGeom& g, const float* __restrict__ bias_s,
+                                                  const int* __restrict__ rid, int wp, int lane,
+                                                  float (&acc)[16][2]) {
+  const bool masked = g.use_mask && g.shift > 0;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int i = wp * 16 + r;
+    if (i >= g.N) { acc[r][0] = acc[r][1] = 0.f; continue; }  // warp-uniform
+    float s[2];
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int j = lane + 32 * cc;
+      if (j < g.N) {
+        float v = acc[r][cc] + bias_s[rel_index(g.ws, i, j)];
+        if (masked && rid[i] != rid[j]) v += -100.0f;
+        s[cc] = v;
+      } else {
+        s[cc] = -INFINITY;
+      }
+    }
+    const float m = warp_max(fmaxf(s[0], s[1]));
+    const float e0 = s[0] == -INFINITY ? 0.f : expf(s[0] - m);
+    const float e1 = s[1] == -INFINITY ? 0.f : expf(s[1] - m);
+    const float inv = 1.f / warp_sum(e0 + e1);
+    acc[r][0] = e0 * inv;
+    acc[r][1] = e1 * inv;
+  }
+}
+
+__global__ void __launch_bounds__(WA_THREADS) window_attn_fwd_kernel(const float* __restrict__ qkv,
+                                                                    const float* __restrict__ table,
+                                                                    float* __restrict__ out, WinGeom g) {
+  __shared__ float Qs[WA_N * WA_LD], Ks[WA_N * WA_LD], Vs[WA_N * WA_LD], Ps[WA_N * WA_PLD];
+  __shared__ float bias_s[(2 * 8 - 1) * (2 * 8 - 1)];
+  __shared__ int tok[WA_N], rid[WA_N];
+  const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
+  const int wi = blockIdx.x, head = blockIdx.y;
+  if (t < g.N) win_token_map(g, wi, t, tok[t], rid[t]);
+  for (int i = t; i < (2 * g.ws - 1) * (2 * g.ws - 1); i += WA_THREADS) bias_s[i] = table[i * g.heads + head];
+  for (int i = t; i < WA_N * WA_LD; i += WA_THREADS) { Qs[i] = 0.f; Ks[i] = 0.f; Vs[i] = 0.f; }
+  __syncthreads();
+  for (int idx = t; idx < g.N * g.D; idx += WA_THREADS) {
+    const int n = idx / g.D, d = idx - n * g.D;
+    const float* p = qkv + (size_t)tok[n] * 3 * g.C + head * g.D + d;
+    Qs[n * WA_LD + d] = p[0] * g.scale;
+    Ks[n * WA_LD + d] = p[g.C];
+    Vs[n * WA_LD + d] = p[2 * g.C];
+  }
+  __syncthreads();
+  float acc[16][2];
+  rows_dot(Qs, Ks, g.N, g.D, wp, lane, acc);
+  rows_bias_softmax(g, bias_s, rid, wp, lane, acc);
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    Ps[(wp * 16 + r) * WA_PLD + lane] = acc[r][0];
+    Ps[(wp * 16 + r) * WA_PLD + lane + 32] = acc[r][1];
+  }
+  __syncwarp();
+  if (lane < g.D) {
+    for (int r = 0; r < 16; ++r) {
+      const int i = wp * 16 + r;
+      if (i >= g.N) break;
+      float o = 0.f;
+      for (int j = 0; j < g.N; ++j) o = fmaf(Ps[i * WA_PLD + j], Vs[j * WA_LD + lane], o);
+      out[(size_t)tok[i] * g.C + head * g.D + lane] = o;
+    }
+  }
+}
+
+constexpr size_t WA_BWD_SMEM = (size_t)(4 * WA_N * WA_LD + 2 * WA_N * WA_PLD + WA_N * WA_N) * sizeof(float);
+
+__global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const float* __restrict__ qkv,
+                                                                    const float* __restrict__ table,
+                                                                    const float* __restrict__ dout,
+                                                                    float* __restrict__ dqkv,
+                                                                    float* __restrict__ partial, WinGeom g, int nwin) {
+  extern __shared__ float sm[];
+  float* Qs = sm;
+  float* Ks = Qs + WA_N * WA_LD;
+  float* Vs = Ks + WA_N * WA_LD;
+  float* Os = Vs + WA_N * WA_LD;   // dO
+  float* Ps = Os + WA_N * WA_LD;
+  float* Ss = Ps + WA_N * WA_PLD;  // dS
+  float* Acc = Ss + WA_N * WA_PLD; // sum over this CTA's windows of dS, [N][N] (stride WA_N)
+  __shared__ float bias_s[(2 * 8 - 1) * (2 * 8 - 1)];
+  __shared__ int tok[WA_N], rid[WA_N];
+  const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
+  const int head = blockIdx.y;
+  for (int i = t; i < (2 * g.ws - 1) * (2 * g.ws - 1); i += WA_THREADS) bias_s[i] = table[i * g.heads + head];
+  for (int i = t; i < WA_N * WA_N; i += WA_THREADS) Acc[i] = 0.f;
+  for (int i = t; i < 4 * WA_N * WA_LD; i += WA_THREADS) sm[i] = 0.f;
+
+  for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
+    __syncthreads();
+    if (t < g.N) win_token_map(g, wi, t, tok[t], rid[t]);
+    __syncthreads();
+    for (int idx = t; idx < g.N * g.D; idx += WA_THREADS) {
+      const int n = idx / g.D, d = idx - n * g.D;
+      const float* p = qkv + (size_t)tok[n] * 3 * g.C + head * g.D + d;
+      Qs[n * WA_LD + d] = p[0] * g.scale;
+      Ks[n * WA_LD + d] = p[g.C];
+      Vs[n * WA_LD + d] = p[2 * g.C];
+      Os[n * WA_LD + d] = dout[(size_t)tok[n] * g.C + head * g.D + d];
+    }
+    __syncthreads();
+    float pr[16][2], dp[16][2];
+    rows_dot(Qs, Ks, g.N, g.D, wp, lane, pr);
+    rows_bias_softmax(g, bias_s, rid, wp, lane, pr);
+    rows_dot(Os, Vs, g.N, g.D, wp, lane, dp);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int i = wp * 16 + r;
+      const float delta = warp_sum(pr[r][0] * dp[r][0] + pr[r][1] * dp[r][1]);
+      const float s0 = pr[r][0] * (dp[r][0] - delta), s1 = pr[r][1] * (dp[r][1] - delta);
+      Ps[i * WA_PLD + lane] = pr[r][0];
+      Ps[i * WA_PLD + lane + 32] = pr[r][1];
+      Ss[i * WA_PLD + lane] = s0;
+      Ss[i * WA_PLD + lane + 32] = s1;
+      Acc[i * WA_N + lane] += s0;
+      Acc[i * WA_N + lane + 32] += s1;
+    }
+    __syncthreads();
+    if (lane < g.D) {
+      for (int r = 0; r < 16; ++r) {
+        const int n = wp * 16 + r;  // row index for dQ, column index for dK/dV
+        if (n >= g.N) break;
+        float dq = 0.f, dk = 0.f, dv = 0.f;
+        for (int m = 0; m < g.N; ++m) {
+          dq = fmaf(Ss[n * WA_PLD + m], Ks[m * WA_LD + lane], dq);
+          dk = fmaf(Ss[m * WA_PLD + n], Qs[m * WA_LD + lane], dk);
+          dv = fmaf(Ps[m * WA_PLD + n], Os[m * WA_LD + lane], dv);
+        }
+        float* o = dqkv + (size_t)tok[n] * 3 * g.C + head * g.D + lane;
+        o[0] = dq * g.scale;
+        o[g.C] = dk;
+        o[2 * g.C] = dv;
+      }
+    }
+  }
+  __syncthreads();
+  float* outp = partial + ((size_t)blockIdx.x * g.heads + head) * WA_N * WA_N;
+  for (int i = t; i < WA_N * WA_N; i += WA_THREADS) outp[i] = Acc[i];
+}
+
+// dtable[tidx, head] = sum over CTA partials and over (i,j) with rel_index(i,j) == tidx.
+__global__ void window_attn_dbias_kernel(const float* __restrict__ partial, float* __restrict__ dtable, int gx,
+                                         int heads, int ws) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int span = 2 * ws - 1;
+  if (id >= span * span * heads) return;
+  const int head = id % heads, tidx = id / heads;
+  const int dy = tidx / span - (ws - 1), dx = tidx % span - (ws - 1);
+  float s = 0.f;
+  for (int jy = 0; jy < ws; ++jy) {
+    const int iy = jy + dy;
+    if (iy < 0 || iy >= ws) continue;
+    for (int jx = 0; jx < ws; ++jx) {
+      const int ix = jx + dx;
+      if (ix < 0 || ix >= ws) continue;
+      const int i = iy * ws + ix, j = jy * ws + jx;
+      for (int b = 0; b < gx; ++b) s += partial[((size_t)b * heads + head) * WA_N * WA_N + i * WA_N + j];
+    }
+  }
+  dtable[tidx * heads + head] = s;
+}
+
+static int bwd_gx(int nwin, int heads) {
+  int gx = (2 * kNumSMs) / heads;
+  if (gx < 1) gx = 1;
+  return gx > nwin ? nwin : gx;
+}
+static int make_geom(WinGeom& g, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
+                     float scale, const char* who) {
+  NSR_CHECK_ARG(batch > 0 && h > 0 && w > 0 && c > 0 && heads > 0 && ws > 0, "%s: bad geometry", who);
+  NSR_CHECK_ARG(c % heads == 0 && c / heads <= WA_D, "%s: head_dim must be <= %d", who, WA_D);
+  NSR_CHECK_ARG(ws * ws <= WA_N && ws <= 8, "%s: window %d not supported (ws*ws <= %d)", who, ws, WA_N);
+  NSR_CHECK_ARG(h % ws == 0 && w % ws == 0, "%s: h, w must be multiples of the window size", who);
+  NSR_CHECK_ARG(shift >= 0 && shift < ws, "%s: shift must be in [0, ws)", who);
+  g = WinGeom{batch, h, w, c, heads, ws, shift, use_mask, ws * ws, c / heads, h / ws, w / ws, scale};
+  return NSR_OK;
+}
+}  // namespace nsr
+using namespace nsr;
+
+extern "C" int nsr_window_attn_fwd(const float* qkv, const float* bias_table, float* out, int batch, int h, int w,
+                                   int c, int heads, int ws, int shift, int use_mask, float scale, void* stream) {
+  NSR_CHECK_ARG(qkv && bias_table && out, "nsr_window_attn_fwd: null pointer");
+  WinGeom g;
+  int rc = make_geom(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_fwd");
+  if (rc) return rc;
+  dim3 grid(batch * g.nwh * g.nww, heads);
+  window_attn_fwd_kernel<<<grid, WA_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(qkv, bias_table, out, g);
+  NSR_CHECK_LAUNCH("window_attn_fwd");
+  return NSR_OK;
+}
+
+extern "C" size_t nsr_window_attn_bwd_workspace(int heads, int ws) {
+  (void)ws;
+  return (size_t)(2 * kNumSMs) * (heads > 0 ? 1 : 1) * WA_N * WA_N * sizeof(float) + (size_t)heads * WA_N * WA_N * sizeof(float);
+}
+
+extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv,
+                                   float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int shift,
+                                   int use_mask, float scale, void* workspace, size_t workspace_bytes, void* stream) {
+  NSR_CHECK_ARG(qkv && bias_table && dout && dqkv && dbias_table, "nsr_window_attn_bwd: null pointer");
+  WinGeom g;
+  int rc = make_geom(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_bwd");
+  if (rc) return rc;
+  const int nwin = batch * g.nwh * g.nww;
+  const int gx = bwd_gx(nwin, heads);
+  const size_t need = (size_t)gx * heads * WA_N * WA_N * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_error("nsr_window_attn_bwd: workspace %zu < %zu", workspace_bytes, need);
+    return NSR_E_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)WA_BWD_SMEM);
+    if (e != cudaSuccess) {
+      set_error("nsr_window_attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return NSR_E_CUDA;
+    }
+    attr_set = true;
+  }
+  float* partial = reinterpret_cast<float*>(workspace);
+  dim3 grid(gx, heads);
+  window_attn_bwd_kernel<<<grid, WA_THREADS, WA_BWD_SMEM, st>>>(qkv, bias_table, dout, dqkv, partial, g, nwin);
+  NSR_CHECK_LAUNCH("window_attn_bwd");
+  const int n = (2 * ws - 1) * (2 * ws - 1) * heads;
+  window_attn_dbias_kernel<<<ceil_div(n, 128), 128, 0, st>>>(partial, dbias_table, gx, heads, ws);
+  NSR_CHECK_LAUNCH("window_attn_dbias");
+  return NSR_OK;
+}

@@ -1,0 +1,252 @@
+"""`image` model: the training step on the B200 kernels — drop-in for neosr/models/image.py.
+
+train.py calls, per iteration, `feed_data(batch)` -> `optimize_parameters(it)` ->
+`update_learning_rate(it, warmup_iter=)`, and on cadence `get_current_log()`,
+`get_current_learning_rate()`, `save(epoch, it)` (train.py:264-332).  This class keeps those
+methods, the option keys they read (image.py:73-230) and the log keys they produce
+(`l_g_pix`, `l_g_percep`, `l_g_total`, ...), but runs ONE explicit pipeline instead of an
+autograd graph:
+
+    G fprop (saving activations) -> fused loss value+grad kernels -> G backward straight into
+    one flat fp32 gradient buffer -> [NCCL all-reduce of that buffer, DDP-style] ->
+    one fused kernel: clip_grad_norm_(1.0) + adan_sf/AdamW + EMA.
+
+Differences from the reference that are deliberate:
+  * multi-GPU works (the reference's DDP path cannot start); gradients are averaged across
+    ranks exactly as DDP would, and the loss log is averaged over ranks only when read;
+  * the loss log and the NaN check are materialised lazily (at `get_current_log()`), which
+    removes the >= 2 host syncs per iteration (image.py:611, base.py:522-524).
+"""
+from __future__ import annotations
+
+import copy
+import os
+import time
+from collections import OrderedDict
+from pathlib import Path
+from typing import Any
+
+import torch
+from torch import Tensor
+from torch.optim.swa_utils import AveragedModel, get_ema_multi_avg_fn
+
+from .. import ops
+from ..archs import build_network
+from ..archs.arch_util import set_default_scale
+from ..losses import build_loss
+from ..optimizers import AdamW, adan_sf
+from ..registry import MODEL_REGISTRY
+
+
+@MODEL_REGISTRY.register()
+class image:
+    def __init__(self, opt: dict[str, Any]) -> None:
+        self.opt = opt
+        if not torch.cuda.is_available():
+            raise RuntimeError("neosr_b200.image: a CUDA device (B200, sm_100a) is required; there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.is_train = opt.get("is_train", True)
+        self.optimizers: list = []
+        self.schedulers: list = []
+        self.log_dict: dict = {}
+        set_default_scale(opt.get("scale", 4), self.is_train)
+
+        self.net_g = build_network(opt["network_g"]).to(self.device)
+        if opt.get("network_d") is not None:
+            raise NotImplementedError("neosr_b200.image: discriminator / GAN branch (image.py:516-608) not built yet")
+        self.net_d = None
+        path = opt.get("path", {}) or {}
+        if path.get("pretrain_network_g"):
+            self.load_network(self.net_g, path["pretrain_network_g"], path.get("param_key_g"),
+                              path.get("strict_load_g", True))
+        self.dist = bool(opt.get("dist", False))
+        self.world_size = int(opt.get("world_size", 1))
+        if self.is_train:
+            self.init_training_settings()
+
+    # ------------------------------------------------------------------ setup (image.py:73-372)
+    def init_training_settings(self) -> None:
+        train_opt = self.opt["train"]
+        self.ema = train_opt.get("ema", -1)
+        if self.ema > 0:
+            self.net_g_ema = AveragedModel(self.net_g, multi_avg_fn=get_ema_multi_avg_fn(self.ema), device=self.device)
+        for k in ("sam", "eco", "wavelet_guided", "match_lq_colors"):
+            if train_opt.get(k):
+                raise NotImplementedError(f"neosr_b200.image: train.{k} is outside the built hot path (SURVEY.md §8f.4)")
+        if self.opt.get("use_amp", False):
+            raise NotImplementedError("neosr_b200.image: AMP is opt-in in the reference and not built (fp32 path)")
+        ds = self.opt.get("datasets", {}).get("train", {})
+        self.accum_iters = ds.get("accumulate", 1) or 1
+        if self.accum_iters != 1:
+            raise NotImplementedError("neosr_b200.image: accumulate != 1 (ill-defined in the reference, SURVEY.md §3.2)")
+        aug = ds.get("augmentation")
+        if aug is not None and not (len(aug) == 1 and "none" in aug):
+            raise NotImplementedError("neosr_b200.image: apply_augment (augmentations.py:219-310) not built yet")
+        self.n_accumulated = 0
+        self._ema_updates = 0  # host mirror of net_g_ema.n_averaged (avoids a device read per step)
+        self.scale = self.opt.get("scale", 4)
+        self.patch_size = ds.get("patch_size")
+        self.gradclip = train_opt.get("grad_clip", True)
+
+        def mk(key):
+            o = train_opt.get(key)
+            if not o:
+                return None
+            o = dict(o)
+            if key == "perceptual_opt" and "allow_random_init" not in o and self.opt.get("vgg_random_init"):
+                o["allow_random_init"] = True
+            return build_loss(o).to(self.device)
+
+        self.cri_pix = mk("pixel_opt")
+        self.cri_perceptual = mk("perceptual_opt")
+        for k in ("mssim_opt", "consistency_opt", "dists_opt", "gan_opt", "ldl_opt", "ff_opt", "gw_opt"):
+            if train_opt.get(k):
+                raise NotImplementedError(f"neosr_b200.image: train.{k} not built yet")
+        if self.cri_pix is None and self.cri_perceptual is None:
+            raise ValueError("Both pixel/mssim and perceptual losses are None. Please enable at least one.")
+        self.setup_optimizers()
+        self.net_g.train()
+        if self.sf_optim_g:
+            self.optimizer_g.train()
+
+    def setup_optimizers(self) -> None:
+        o = dict(self.opt["train"]["optim_g"])
+        optim_type = o.pop("type")
+        self.sf_optim_g = o.get("schedule_free", False)
+        params = [p for p in self.net_g.parameters() if p.requires_grad]
+        if optim_type in {"Adan_SF", "adan_sf"}:
+            if "schedule_free" not in o:
+                raise ValueError("The option 'schedule_free' must be in the config file.")
+            self.optimizer_g = adan_sf(params, **o)
+        elif optim_type in {"AdamW", "adamw"}:
+            self.optimizer_g = AdamW(params, **o)
+        else:
+            raise NotImplementedError(f"neosr_b200.image: optimizer {optim_type} not built (adan_sf, AdamW are)")
+        self.optimizers.append(self.optimizer_g)
+
+    # ------------------------------------------------------------------ the hot path
+    @torch.no_grad()
+    def feed_data(self, data: dict) -> None:  # image.py:374-391
+        self.lq = data["lq"].to(self.device, non_blocking=True)
+        if "gt" in data:
+            self.gt = data["gt"].to(self.device, non_blocking=True)
+
+    @torch.no_grad()
+    def optimize_parameters(self, current_iter: int) -> None:  # image.py:427-662
+        net = self.net_g
+        ps = net.param_set()
+        ps.ensure_grads(self.device)
+        out, saved = net.engine_forward(self.lq, save=True)
+        self.output = out
+        total = torch.zeros(1, dtype=torch.float32, device=self.device)
+        logs = OrderedDict()
+        dout = None
+        if self.cri_pix is not None:
+            v, g = self.cri_pix.value_and_grad(out, self.gt, True, total)
+            logs["l_g_pix"] = v
+            dout = g
+        if self.cri_perceptual is not None:
+            v, g = self.cri_perceptual.value_and_grad(out, self.gt, True, total)
+            logs["l_g_percep"] = v
+            dout = g if dout is None else ops.axpby(dout, 1.0, g, 1.0, out=dout)
+        logs["l_g_total"] = total
+        net.engine_backward(saved, dout)
+        if self.dist and self.world_size > 1:
+            torch.distributed.all_reduce(ps.flat_grad, op=torch.distributed.ReduceOp.AVG)
+        ps.attach_grads()
+        ema = None
+        if self.ema > 0:
+            ema_params = [e.detach() for e, p in zip(self.net_g_ema.module.parameters(), net.parameters())
+                          if p.requires_grad]
+            ema = (ema_params, self.ema, self._ema_updates == 0)
+        self.optimizer_g.step(clip_max_norm=1.0 if self.gradclip else None, ema=ema)
+        if self.ema > 0:
+            self.net_g_ema.n_averaged += 1
+            self._ema_updates += 1
+        self._pending_logs = logs
+
+    def update_learning_rate(self, current_iter: int, warmup_iter: int = -1) -> None:  # base.py:229-254
+        if current_iter > 0 and self.n_accumulated == 0:
+            for s in self.schedulers:
+                s.step()
+        if current_iter < warmup_iter:
+            for opt in self.optimizers:
+                for g in opt.param_groups:
+                    g["lr"] = g.get("initial_lr", g["lr"]) / warmup_iter * current_iter
+
+    def get_current_learning_rate(self):
+        return [g["lr"] for g in self.optimizers[0].param_groups]
+
+    def get_current_log(self) -> dict:
+        """Materialise the (device-resident) loss scalars; average over ranks if distributed
+        (what base.reduce_loss_dict intends, base.py:498-526)."""
+        logs = getattr(self, "_pending_logs", None)
+        if logs:
+            keys = list(logs)
+            vec = torch.cat([logs[k].view(1) for k in keys])
+            if self.dist and self.world_size > 1:
+                torch.distributed.all_reduce(vec, op=torch.distributed.ReduceOp.AVG)
+            vals = vec.tolist()
+            if any(v != v for v in vals):
+                raise ValueError("NaN found, aborting training. Make sure you're using a proper learning rate.")
+            self.log_dict = OrderedDict(zip(keys, vals))
+        return self.log_dict
+
+    # ------------------------------------------------------------------ checkpoints (base.py:281-496)
+    def get_bare_model(self, net):
+        return net
+
+    def save_network(self, net, net_label: str, current_iter, param_key: str = "params") -> None:
+        current_iter = "latest" if current_iter == -1 else current_iter
+        models_dir = Path(self.opt["path"]["models"])
+        models_dir.mkdir(parents=True, exist_ok=True)
+        sd = OrderedDict()
+        for k, v in net.state_dict().items():
+            if k == "n_averaged":
+                continue
+            k = k[7:] if k.startswith("module.") else k
+            sd[k] = v.detach().cpu()
+        if self.sf_optim_g and self.is_train:
+            self.optimizer_g.eval()
+        torch.save({param_key: sd}, models_dir / f"{net_label}_{current_iter}.pth")
+        if self.sf_optim_g and self.is_train:
+            self.optimizer_g.train()
+
+    def save_training_state(self, epoch: int, current_iter: int) -> None:
+        if current_iter == -1:
+            return
+        d = Path(self.opt["path"]["training_states"])
+        d.mkdir(parents=True, exist_ok=True)
+        state = {"epoch": epoch, "iter": current_iter, "optimizers": [o.state_dict() for o in self.optimizers],
+                 "schedulers": [s.state_dict() for s in self.schedulers]}
+        torch.save(state, d / f"{current_iter}.state")
+
+    def save(self, epoch: int, current_iter: int) -> None:  # image.py:932-942
+        if self.opt.get("rank", 0) != 0:
+            return
+        if self.ema > 0:
+            self.save_network(self.net_g_ema, "net_g", current_iter)
+        else:
+            self.save_network(self.net_g, "net_g", current_iter)
+        self.save_training_state(epoch, current_iter)
+
+    def load_network(self, net, load_path, param_key: str | None = None, strict: bool = True) -> None:
+        load_net = torch.load(load_path, map_location="cpu", weights_only=True)
+        if param_key is None:
+            for k in ("params-ema", "params_ema", "params"):
+                if k in load_net:
+                    param_key = k
+                    break
+        if param_key in load_net:
+            load_net = load_net[param_key]
+        load_net = OrderedDict((k[7:] if k.startswith("module.") else k, v) for k, v in load_net.items())
+        net.load_state_dict(load_net, strict=strict)
+
+    def resume_training(self, resume_state: dict) -> None:  # base.py:477-496
+        for i, o in enumerate(resume_state["optimizers"]):
+            self.optimizers[i].load_state_dict(o)
+        for i, s in enumerate(resume_state["schedulers"]):
+            self.schedulers[i].load_state_dict(s)
+
+    def validation(self, dataloader, current_iter, tb_logger, save_img: bool = True) -> None:
+        raise NotImplementedError("neosr_b200.image.validation: SURVEY.md §8f.1 (next after the training step)")

@@ -1,0 +1,364 @@
+"""Tensor-level wrappers over the C ABI (include/neosr_b200.h).
+
+Everything here takes/returns CUDA fp32 torch tensors only as *memory*: the wrappers pull
+`data_ptr()` and the current CUDA stream and call into libneosr_b200.so.  No torch math runs
+on the hot path.  Activations are NHWC ("tokens"): a tensor of shape [B, H, W, C] (contiguous).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import ACT, ENGINE, NsrConv, NsrWgrad, check
+
+
+LAUNCHES = 0          # kernels launched through this module (claim reported by bench.py)
+PROFILE: list | None = None  # when a list: (kernel, shape-key, flops, bytes, start_evt, end_evt) per call
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _prof:
+    """Context manager: CUDA events around one C-ABI call when ops.PROFILE is a list."""
+
+    def __init__(self, name, key, flops=0.0, nbytes=0.0):
+        self.on = PROFILE is not None
+        if self.on:
+            self.rec = [name, key, flops, nbytes, torch.cuda.Event(enable_timing=True),
+                        torch.cuda.Event(enable_timing=True)]
+
+    def __enter__(self):
+        if self.on:
+            self.rec[4].record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.rec[5].record()
+            PROFILE.append(tuple(self.rec))
+
+
+def _p(t: Tensor | None):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Tensor | None, name: str):
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous CUDA fp32 tensor, got {t.dtype} {t.device} "
+                         f"contiguous={t.is_contiguous()}")
+
+
+class Scratch:
+    """One growing device scratch buffer shared by all kernels that need workspace.
+    Safe because every launch is stream-ordered on the same stream."""
+
+    def __init__(self):
+        self.buf: Tensor | None = None
+
+    def get(self, nbytes: int, device) -> Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_scratch: dict = {}
+
+
+def scratch(nbytes: int, device) -> Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    s = _scratch.get(key)
+    if s is None:
+        s = _scratch[key] = Scratch()
+    return s.get(nbytes, device)
+
+
+# ----------------------------------------------------------------------------- weights
+class PackedWeight:
+    """fprop- and dgrad-flavoured packed copies of one Conv2d/Linear weight
+    (reference layout [cout, cin, kh, kw] or [cout, cin])."""
+
+    def __init__(self, weight: Tensor, need_dgrad: bool = True):
+        self.weight = weight
+        self.cout, self.cin = weight.shape[0], weight.shape[1]
+        self.kh = weight.shape[2] if weight.dim() == 4 else 1
+        self.kw = weight.shape[3] if weight.dim() == 4 else 1
+        L = _lib.lib()
+        dev = weight.device
+        self.fprop = torch.empty(L.nsr_packed_weight_bytes(self.cout, self.cin, self.kh, self.kw, 0),
+                                 dtype=torch.uint8, device=dev)
+        self.dgrad = torch.empty(L.nsr_packed_weight_bytes(self.cout, self.cin, self.kh, self.kw, 1),
+                                 dtype=torch.uint8, device=dev) if need_dgrad else None
+        self._version = None
+
+    def refresh(self, force: bool = False) -> "PackedWeight":
+        """Re-pack if the parameter changed since the last pack (tracked by tensor version)."""
+        w = self.weight
+        ver = (w.data_ptr(), w._version)
+        if not force and ver == self._version:
+            return self
+        _chk(w, "weight")
+        L = _lib.lib()
+        st = _stream()
+        check(L.nsr_pack_weight(w.data_ptr(), self.cout, self.cin, self.kh, self.kw, 0, self.fprop.data_ptr(), st),
+              "nsr_pack_weight")
+        if self.dgrad is not None:
+            check(L.nsr_pack_weight(w.data_ptr(), self.cout, self.cin, self.kh, self.kw, 1, self.dgrad.data_ptr(), st),
+                  "nsr_pack_weight")
+        _count(4 if self.dgrad is not None else 2)
+        self._version = ver
+        return self
+
+
+# ----------------------------------------------------------------------------- contraction
+def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad: bool = False,
+               act: str = "none", act_slope: float = 0.0, actgrad: str = "none", actgrad_slope: float = 0.0,
+               aux: Tensor | None = None, prelu: Tensor | None = None, row_scale: Tensor | None = None,
+               residual: Tensor | None = None, want_pre: bool = False, out: Tensor | None = None,
+               engine: str = "auto"):
+    """y = epilogue(conv(x, w)); x is [B,H,W,Cin] NHWC.  With dgrad=True the dgrad-packed
+    filter is used and the roles of cin/cout swap (x is then dY [B,H,W,Cout])."""
+    _chk(x, "x")
+    B, H, W, cx = x.shape
+    cin, cout = (pw.cout, pw.cin) if dgrad else (pw.cin, pw.cout)
+    if cx != cin:
+        raise ValueError(f"conv_fprop: x has {cx} channels, weight expects {cin}")
+    for t, n in ((bias, "bias"), (aux, "aux"), (prelu, "prelu"), (row_scale, "row_scale"), (residual, "residual")):
+        _chk(t, n)
+    y = out if out is not None else torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device)
+    y_pre = torch.empty_like(y) if want_pre else None
+    d = NsrConv(batch=B, h=H, w=W, cin=cin, cout=cout, kh=pw.kh, kw=pw.kw, pad=pw.kh // 2,
+                x_ld=cin, y_ld=cout, act=ACT[act], act_slope=act_slope, actgrad=ACT[actgrad],
+                actgrad_slope=actgrad_slope, engine=ENGINE[engine],
+                x=x.data_ptr(), w_packed=(pw.dgrad if dgrad else pw.fprop).data_ptr(), bias=_p(bias),
+                prelu=_p(prelu), aux=_p(aux), row_scale=_p(row_scale), residual=_p(residual),
+                y_pre=_p(y_pre), y=y.data_ptr())
+    M = B * H * W
+    with _prof("conv_dgrad" if dgrad else "conv_fprop", (M, cin, cout, pw.kh),
+               2.0 * M * cin * cout * pw.kh * pw.kw, 4.0 * M * (cin + cout)):
+        check(_lib.lib().nsr_conv_fprop(C.byref(d), _stream()), "nsr_conv_fprop")
+    _count(1)
+    return (y, y_pre) if want_pre else y
+
+
+def conv_wgrad(x: Tensor, dy: Tensor, dw: Tensor, dbias: Tensor | None, kh: int, kw: int, engine: str = "auto"):
+    """dw[cout,cin,kh,kw] (+ dbias) from x [B,H,W,Cin] and dy [B,H,W,Cout]; overwrites dw/dbias."""
+    _chk(x, "x"), _chk(dy, "dy"), _chk(dw, "dw"), _chk(dbias, "dbias")
+    B, H, W, cin = x.shape
+    cout = dy.shape[-1]
+    if dy.shape[:3] != x.shape[:3] or dw.numel() != cout * cin * kh * kw:
+        raise ValueError(f"conv_wgrad: shape mismatch x{tuple(x.shape)} dy{tuple(dy.shape)} dw{tuple(dw.shape)}")
+    d = NsrWgrad(batch=B, h=H, w=W, cin=cin, cout=cout, kh=kh, kw=kw, pad=kh // 2, x_ld=cin, dy_ld=cout,
+                 engine=ENGINE[engine], x=x.data_ptr(), dy=dy.data_ptr(), dw=dw.data_ptr(), dbias=_p(dbias),
+                 workspace=None, workspace_bytes=0)
+    L = _lib.lib()
+    need = L.nsr_conv_wgrad_workspace(C.byref(d))
+    ws = scratch(need, x.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    M = B * H * W
+    with _prof("conv_wgrad", (M, cin, cout, kh), 2.0 * M * cin * cout * kh * kw, 4.0 * M * (cin + cout)):
+        check(L.nsr_conv_wgrad(C.byref(d), _stream()), "nsr_conv_wgrad")
+    _count(4 if dbias is not None else 2)
+
+
+# ----------------------------------------------------------------------------- layout
+def nchw_to_nhwc_affine(x: Tensor, scale: Tensor | None, shift: Tensor | None) -> Tensor:
+    _chk(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, H, W, Cc), dtype=torch.float32, device=x.device)
+    with _prof("nsr_nchw_to_nhwc_affine", (x.numel(),), 0.0, 8.0 * x.numel()):
+        check(_lib.lib().nsr_nchw_to_nhwc_affine(x.data_ptr(), y.data_ptr(), B, Cc, H, W, _p(scale), _p(shift), _stream()),
+              "nsr_nchw_to_nhwc_affine")
+    _count(1)
+    return y
+
+
+def nhwc_to_nchw_affine(x: Tensor, scale: Tensor | None, shift: Tensor | None) -> Tensor:
+    _chk(x, "x")
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    with _prof("nsr_nhwc_to_nchw_affine", (x.numel(),), 0.0, 8.0 * x.numel()):
+        check(_lib.lib().nsr_nhwc_to_nchw_affine(x.data_ptr(), y.data_ptr(), B, Cc, H, W, _p(scale), _p(shift), _stream()),
+              "nsr_nhwc_to_nchw_affine")
+    _count(1)
+    return y
+
+
+def pixel_shuffle(x: Tensor, r: int) -> Tensor:
+    """[B,H,W,C*r*r] -> [B,H*r,W*r,C]."""
+    _chk(x, "x")
+    B, H, W, Ci = x.shape
+    Co = Ci // (r * r)
+    y = torch.empty((B, H * r, W * r, Co), dtype=torch.float32, device=x.device)
+    with _prof("nsr_pixel_shuffle_nhwc", (x.numel(),), 0.0, 8.0 * x.numel()):
+        check(_lib.lib().nsr_pixel_shuffle_nhwc(x.data_ptr(), y.data_ptr(), B, H, W, Co, r, 0, _stream()),
+              "nsr_pixel_shuffle_nhwc")
+    _count(1)
+    return y
+
+
+def pixel_unshuffle(dy: Tensor, r: int) -> Tensor:
+    """[B,H*r,W*r,C] -> [B,H,W,C*r*r] (autograd of pixel_shuffle)."""
+    _chk(dy, "dy")
+    B, Hr, Wr, Co = dy.shape
+    H, W = Hr // r, Wr // r
+    y = torch.empty((B, H, W, Co * r * r), dtype=torch.float32, device=dy.device)
+    with _prof("nsr_pixel_unshuffle_nhwc", (dy.numel(),), 0.0, 8.0 * dy.numel()):
+        check(_lib.lib().nsr_pixel_shuffle_nhwc(dy.data_ptr(), y.data_ptr(), B, H, W, Co, r, 1, _stream()),
+              "nsr_pixel_shuffle_nhwc")
+    _count(1)
+    return y
+
+
+def maxpool2(x: Tensor) -> Tensor:
+    _chk(x, "x")
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float32, device=x.device)
+    with _prof("nsr_maxpool2_nhwc", (x.numel(),), 0.0, 5.0 * x.numel()):
+        check(_lib.lib().nsr_maxpool2_nhwc(x.data_ptr(), y.data_ptr(), B, H, W, Cc, _stream()), "nsr_maxpool2_nhwc")
+    _count(1)
+    return y
+
+
+def maxpool2_relu_bwd(x: Tensor, dy: Tensor, dextra: Tensor | None = None) -> Tensor:
+    _chk(x, "x"), _chk(dy, "dy"), _chk(dextra, "dextra")
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    with _prof("nsr_maxpool2_relu_bwd_nhwc", (x.numel(),), 0.0, 9.0 * x.numel()):
+        check(_lib.lib().nsr_maxpool2_relu_bwd_nhwc(x.data_ptr(), dy.data_ptr(), _p(dextra), dx.data_ptr(), B, H, W, Cc,
+                                                    _stream()), "nsr_maxpool2_relu_bwd_nhwc")
+    _count(1)
+    return dx
+
+
+def axpby(a: Tensor, alpha: float, b: Tensor | None, beta: float, out: Tensor | None = None) -> Tensor:
+    _chk(a, "a"), _chk(b, "b")
+    y = out if out is not None else torch.empty_like(a)
+    with _prof("nsr_axpby", (a.numel(),), 0.0, 12.0 * a.numel()):
+        check(_lib.lib().nsr_axpby(a.data_ptr(), alpha, _p(b), beta, y.data_ptr(), a.numel(), _stream()), "nsr_axpby")
+    _count(1)
+    return y
+
+
+def actgrad_mul(dy: Tensor, aux: Tensor, act: str, slope: float = 0.0, dextra: Tensor | None = None) -> Tensor:
+    _chk(dy, "dy"), _chk(aux, "aux"), _chk(dextra, "dextra")
+    dx = torch.empty_like(dy)
+    with _prof("nsr_actgrad_mul", (dy.numel(),), 0.0, 12.0 * dy.numel()):
+        check(_lib.lib().nsr_actgrad_mul(dy.data_ptr(), aux.data_ptr(), _p(dextra), dx.data_ptr(), dy.numel(), ACT[act],
+                                         slope, _stream()), "nsr_actgrad_mul")
+    _count(1)
+    return dx
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5):
+    _chk(x, "x"), _chk(gamma, "gamma"), _chk(beta, "beta")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    with _prof("nsr_layernorm_fwd", (rows, c), 0.0, 8.0 * x.numel()):
+        check(_lib.lib().nsr_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                           rstd.data_ptr(), rows, c, eps, _stream()), "nsr_layernorm_fwd")
+    _count(1)
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dgamma: Tensor, dbeta: Tensor,
+                  dres: Tensor | None = None) -> Tensor:
+    for t, n in ((dy, "dy"), (x, "x"), (gamma, "gamma"), (mean, "mean"), (rstd, "rstd"), (dgamma, "dgamma"),
+                 (dbeta, "dbeta"), (dres, "dres")):
+        _chk(t, n)
+    c = x.shape[-1]
+    rows = x.numel() // c
+    dx = torch.empty_like(x)
+    L = _lib.lib()
+    ws = scratch(L.nsr_layernorm_bwd_workspace(c), x.device)
+    with _prof("nsr_layernorm_bwd", (rows, c), 0.0, (16.0 if dres is not None else 12.0) * x.numel()):
+        check(L.nsr_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(dres),
+                                  dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, c, ws.data_ptr(), ws.numel(),
+                                  _stream()), "nsr_layernorm_bwd")
+    _count(2)
+    return dx
+
+
+# ----------------------------------------------------------------------------- attention
+def window_attn_fwd(qkv: Tensor, table: Tensor, heads: int, ws: int, shift: int, scale: float) -> Tensor:
+    """qkv [B,H,W,3C] -> [B,H,W,C]; shift/partition/mask/bias/softmax/PV fused."""
+    _chk(qkv, "qkv"), _chk(table, "table")
+    B, H, W, c3 = qkv.shape
+    c = c3 // 3
+    out = torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device)
+    with _prof("nsr_window_attn_fwd", (B * H * W, c, heads, ws), 0.0, 4.0 * (qkv.numel() + out.numel())):
+        check(_lib.lib().nsr_window_attn_fwd(qkv.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, c, heads, ws, shift,
+                                             1 if shift > 0 else 0, scale, _stream()), "nsr_window_attn_fwd")
+    _count(1)
+    return out
+
+
+def window_attn_bwd(qkv: Tensor, table: Tensor, dout: Tensor, dtable: Tensor, heads: int, ws: int, shift: int,
+                    scale: float) -> Tensor:
+    _chk(qkv, "qkv"), _chk(table, "table"), _chk(dout, "dout"), _chk(dtable, "dtable")
+    B, H, W, c3 = qkv.shape
+    c = c3 // 3
+    dqkv = torch.empty_like(qkv)
+    L = _lib.lib()
+    wsb = scratch(L.nsr_window_attn_bwd_workspace(heads, ws), qkv.device)
+    with _prof("nsr_window_attn_bwd", (B * H * W, c, heads, ws), 0.0, 4.0 * (2 * qkv.numel() + dout.numel())):
+        check(L.nsr_window_attn_bwd(qkv.data_ptr(), table.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), dtable.data_ptr(),
+                                    B, H, W, c, heads, ws, shift, 1 if shift > 0 else 0, scale, wsb.data_ptr(), wsb.numel(),
+                                    _stream()), "nsr_window_attn_bwd")
+    _count(2)
+    return dqkv
+
+
+# ----------------------------------------------------------------------------- losses
+def _loss_ws(device) -> Tensor:
+    return scratch(_lib.lib().nsr_loss_workspace(), device)
+
+
+def l1_loss(pred: Tensor, target: Tensor, weight: float, loss_accum: Tensor | None, want_grad: bool = True):
+    _chk(pred, "pred"), _chk(target, "target")
+    dpred = torch.empty_like(pred) if want_grad else None
+    val = torch.empty(1, dtype=torch.float32, device=pred.device)
+    with _prof("nsr_l1_loss", (pred.numel(),), 0.0, 12.0 * pred.numel()):
+        check(_lib.lib().nsr_l1_loss(pred.data_ptr(), target.data_ptr(), _p(dpred), pred.numel(), weight, _p(loss_accum),
+                                     val.data_ptr(), _loss_ws(pred.device).data_ptr(), _stream()), "nsr_l1_loss")
+    _count(2)
+    return val, dpred
+
+
+def charbonnier_loss(a: Tensor, b: Tensor, weight: float, loss_accum: Tensor | None, in_scale: float = 1.0,
+                     clip_min: float = 0.0, clip_max: float = 1.0, want_grad: bool = True):
+    _chk(a, "a"), _chk(b, "b")
+    da = torch.empty_like(a) if want_grad else None
+    val = torch.empty(1, dtype=torch.float32, device=a.device)
+    with _prof("nsr_charbonnier_loss", (a.numel(),), 0.0, 12.0 * a.numel()):
+        check(_lib.lib().nsr_charbonnier_loss(a.data_ptr(), b.data_ptr(), _p(da), a.numel(), in_scale, clip_min, clip_max,
+                                              weight, _p(loss_accum), val.data_ptr(), _loss_ws(a.device).data_ptr(),
+                                              _stream()), "nsr_charbonnier_loss")
+    _count(2)
+    return val, da
+
+
+def bce_logits_loss(logits: Tensor, label: float, weight: float, loss_accum: Tensor | None, want_grad: bool = True):
+    _chk(logits, "logits")
+    dl = torch.empty_like(logits) if want_grad else None
+    val = torch.empty(1, dtype=torch.float32, device=logits.device)
+    with _prof("nsr_bce_logits_loss", (logits.numel(),), 0.0, 8.0 * logits.numel()):
+        check(_lib.lib().nsr_bce_logits_loss(logits.data_ptr(), _p(dl), logits.numel(), label, weight, _p(loss_accum),
+                                             val.data_ptr(), _loss_ws(logits.device).data_ptr(), _stream()),
+              "nsr_bce_logits_loss")
+    _count(2)
+    return val, dl

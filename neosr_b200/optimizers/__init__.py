@@ -1,0 +1,2 @@
+from .adan_sf import adan_sf  # noqa: F401
+from .adamw import AdamW  # noqa: F401

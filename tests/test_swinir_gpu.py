@@ -1,0 +1,109 @@
+"""Whole-network and whole-step parity on the GPU, through the C ABI, against the committed
+golden fixtures (reference outputs) and the oracle.  Tolerance: 1e-3 relative fp32 (north_star)
+— asserted tighter where the exact-fp32 engine is used."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).parent / "golden"
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _tiny_net(seed):
+    from neosr_b200.archs.swinir_arch import swinir
+    from oracle.make_golden import TINY
+    from oracle.swinir import SwinIRConfig, swinir_param_shapes, synth_params
+    cfg = SwinIRConfig(**TINY)
+    p = synth_params(swinir_param_shapes(cfg), seed=seed)
+    net = swinir(drop_path_rate=0.0, **TINY)
+    missing = net.load_state_dict(p, strict=False)
+    assert not missing.unexpected_keys
+    return net.cuda().train(), cfg, p
+
+
+@pytest.mark.parametrize("tag,hw", [("a", (16, 16)), ("b", (24, 32))])
+def test_tiny_forward_backward_vs_golden(tag, hw):
+    z = np.load(G / "swinir_tiny_fwd_bwd.npz")
+    net, cfg, p = _tiny_net(1)
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 3, *hw, generator=g)
+    y = net(x.cuda())
+    gt = torch.rand(y.shape, generator=g).cuda()
+    assert rel(y.detach(), z[f"{tag}.y"]) < 1e-4
+    (y - gt).abs().mean().backward()
+    worst = max(rel(v.grad, z[f"{tag}.grad.{k}"]) for k, v in net.named_parameters())
+    assert worst < 1e-3, worst
+
+
+def test_medium_forward_and_losses_vs_golden():
+    from neosr_b200.archs import build_network
+    from neosr_b200.losses import build_loss
+    from oracle import losses as OL
+    from oracle.swinir import swinir_medium_config, swinir_param_shapes, synth_params
+    z = np.load(G / "swinir_medium_fwd_loss.npz")
+    cfg = swinir_medium_config(4)
+    net = build_network({"type": "swinir_medium", "drop_path_rate": 0.0, "upscale": 4})
+    net.load_state_dict(synth_params(swinir_param_shapes(cfg), seed=0), strict=False)
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 3, 64, 64, generator=g).cuda()
+    gt = torch.rand(1, 3, 256, 256, generator=g).cuda()
+    y = net(x)
+    assert rel(y.detach(), z["y"]) < 1e-3
+    l1 = build_loss({"type": "L1Loss", "loss_weight": 1.0})
+    per = build_loss({"type": "vgg_perceptual_loss", "loss_weight": 0.5, "criterion": "chc", "allow_random_init": True})
+    per.vgg.load_state_dict(synth_params(OL.vgg19_conv_shapes(), seed=5), strict=False)
+    per = per.cuda()
+    l_pix, l_per = l1(y, gt), per(y, gt)
+    assert abs(float(l_pix) - float(z["l_g_pix"])) < 1e-5
+    assert abs(float(l_per) - float(z["l_g_percep"])) < 1e-3 * abs(float(z["l_g_percep"]))
+    (l_pix + l_per).backward()
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in net.parameters()))
+    assert abs(float(gn) - float(z["grad_norm"])) < 1e-3 * float(z["grad_norm"])
+    for k in [k[5:] for k in z.files if k.startswith("grad.")]:
+        assert rel(dict(net.named_parameters())[k].grad, z[f"grad.{k}"]) < 1e-3, k
+
+
+def test_tiny_step3_vs_golden():
+    """Three iterations of feed_data + optimize_parameters through the `image` model."""
+    from neosr_b200.models import build_model
+    from oracle import losses as OL
+    from oracle.make_golden import OPTIM, TINY
+    from oracle.swinir import SwinIRConfig, swinir_param_shapes, synth_params
+    z = np.load(G / "swinir_tiny_step3.npz")
+    opt = {"model_type": "image", "scale": 4, "is_train": True, "dist": False, "rank": 0, "world_size": 1,
+           "network_g": {"type": "swinir", "drop_path_rate": 0.0, **TINY},
+           "datasets": {"train": {"patch_size": 16}},
+           "train": {"ema": 0.999, "optim_g": {"type": "adan_sf", **OPTIM},
+                     "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0},
+                     "perceptual_opt": {"type": "vgg_perceptual_loss", "loss_weight": 0.5, "criterion": "chc",
+                                        "allow_random_init": True}},
+           "path": {}}
+    from neosr_b200.archs.swinir_arch import swinir
+    from neosr_b200.registry import ARCH_REGISTRY
+    if "swinir" not in ARCH_REGISTRY:
+        ARCH_REGISTRY.register(swinir)
+    model = build_model(opt)
+    cfg = SwinIRConfig(**TINY)
+    model.net_g.load_state_dict(synth_params(swinir_param_shapes(cfg), seed=4), strict=False)
+    model.cri_perceptual.vgg.load_state_dict(synth_params(OL.vgg19_conv_shapes(), seed=5), strict=False)
+    g = torch.Generator().manual_seed(6)
+    for it in range(3):
+        lq, gt = torch.rand(2, 3, 16, 16, generator=g), torch.rand(2, 3, 64, 64, generator=g)
+        model.feed_data({"lq": lq, "gt": gt})
+        model.optimize_parameters(it)
+        log = model.get_current_log()
+        for k, v in log.items():
+            ref = float(z[f"log{it}.{k}"])
+            assert abs(v - ref) <= 1e-3 * max(1e-3, abs(ref)), (it, k, v, ref)
+    for k, v in model.net_g.named_parameters():
+        assert rel(v.detach(), z[f"param.{k}"]) < 1e-3, k
+    for k, v in model.net_g_ema.module.named_parameters():
+        assert rel(v.detach(), z[f"ema.{k}"]) < 1e-3, k
