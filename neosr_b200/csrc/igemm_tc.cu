@@ -1,10 +1,341 @@
-// tcgen05 (UMMA) engine — placeholder until the kernels land; reports "unsupported" so that
-// NSR_ENGINE_AUTO routes everything to the exact-fp32 engine.
-#include "common.cuh"
+// tcgen05 (UMMA) implicit-GEMM engine: 3xBF16-split operands, fp32 accumulation in TMEM.
+//
+//   y[p, n] = epilogue( sum_{tap, c} x[p @ tap, c] * w[n, tap, c] )        (NHWC activations)
+//
+// fp32 parity needs more mantissa than one bf16/tf32 pass gives (SURVEY.md §7 hard part 1), so
+// every operand is split x ~= hi + lo (two bf16) and each k-block issues three MMA groups
+// hi*hi + hi*lo + lo*hi into the same TMEM accumulator (error ~2^-16 relative, fp32 accumulate).
+//
+// Persistent, warp-specialised CTA (1 per SM, 448 threads):
+//   warps 0-7  A producers : gather the im2col tile (zero padding / channel tail by predication)
+//                            straight from fp32 HBM, split to bf16 hi/lo in registers, store into
+//                            the SWIZZLE_128B K-major smem image the tensor core reads;
+//   warp  8    B loader    : weights are pre-split and pre-swizzled by nsr_pack_weight, so one
+//                            bulk copy (cp.async.bulk -> UBLKCP) per operand half fills a stage;
+//   warp  9    MMA issuer  : one elected thread issues tcgen05.mma (M=128, N=BN, K=16) and
+//                            tcgen05.commit to recycle smem stages / publish the accumulator;
+//   warps 10-13 epilogue   : tcgen05.ld TMEM -> registers, bias/activation/act-grad/row-scale/
+//                            residual, fp32 stores.  TMEM is double-buffered (2 x BN columns) so
+//                            the epilogue of tile i overlaps the main loop of tile i+1.
+#include "tc_common.cuh"
+
 namespace nsr {
-bool conv_fprop_tc_supported(const NsrConv&) { return false; }
-int conv_fprop_tc(const NsrConv&, cudaStream_t) { set_error("tcgen05 engine not built"); return NSR_E_INVALID; }
+using namespace tc;
+
+constexpr int TC_BM = 128;          // pixels per tile (UMMA M)
+constexpr int TC_BK = 64;           // bf16 elements per k-block (one 128-byte swizzle row)
+constexpr int TC_PROD_WARPS = 8;
+constexpr int TC_THREADS = (TC_PROD_WARPS + 2 + 4) * 32;  // 448
+constexpr int TC_A_BYTES = TC_BM * 128;                   // one half (hi or lo) of an A stage
+
+template <int BN>
+struct TcCfg {
+  static constexpr int b_bytes = BN * 128;  // one half of a B stage
+  static constexpr int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+  static constexpr int stages = (200 * 1024) / stage_bytes > 4 ? 4 : (200 * 1024) / stage_bytes;
+  static constexpr int smem_bytes = stages * stage_bytes + 1024 /* align slack */ + 256 /* barriers */;
+};
+
+struct TcGeom {
+  int n_tiles, m_tiles, num_tiles, cblks, nk, n_pad64;
+  long long M;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeom g, const uint8_t* __restrict__ wimg) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::stages * Cfg::stage_bytes);
+  uint64_t* full = bars;                      // [stages]  producers + B loader -> MMA
+  uint64_t* empty = bars + Cfg::stages;       // [stages]  MMA -> producers / B loader
+  uint64_t* tfull = bars + 2 * Cfg::stages;   // [2]       MMA -> epilogue
+  uint64_t* tempty = tfull + 2;               // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::stages; ++s) {
+      mbar_init(&full[s], TC_PROD_WARPS * 32 + 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == TC_PROD_WARPS + 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int hw = d.h * d.w;
+  const int taps = d.kh * d.kw;
+
+  if (warp < TC_PROD_WARPS) {
+    // ================================ A producers =========================================
+    const int t = threadIdx.x;        // 0..255
+    const int chunk = t & 7;          // 8-float chunk within the 64-channel k-block
+    const int row0 = t >> 3;          // rows row0 + 32*i, i = 0..3
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const long long m0 = (long long)(tile / g.n_tiles) * TC_BM;
+      int oh[4], ow[4];
+      long long pix[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long p = m0 + row0 + 32 * i;
+        if (p < g.M) {
+          const long long b = p / hw;
+          const int rem = (int)(p - b * hw);
+          oh[i] = rem / d.w;
+          ow[i] = rem - oh[i] * d.w;
+          pix[i] = p;
+        } else {
+          oh[i] = -100000;  // every tap lands out of bounds -> zero rows
+          ow[i] = 0;
+          pix[i] = 0;
+        }
+      }
+      for (int kb = 0; kb < g.nk; ++kb) {
+        const int tap = kb / g.cblks, cblk = kb - tap * g.cblks;
+        const int r = tap / d.kw, s = tap - r * d.kw;
+        const int dh = r - d.pad, dw = s - d.pad;
+        const int c = cblk * TC_BK + chunk * 8;
+        float4 f[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ih = oh[i] + dh, iw = ow[i] + dw;
+          const bool ok = ih >= 0 && ih < d.h && iw >= 0 && iw < d.w;
+          const float* src = d.x + (pix[i] + (long long)dh * d.w + dw) * d.x_ld + c;
+          f[i][0] = (ok && c < d.cin) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[i][1] = (ok && c + 4 < d.cin) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* a_hi = smem + stage * Cfg::stage_bytes;
+        uint8_t* a_lo = a_hi + TC_A_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = row0 + 32 * i;
+          uint4 hi, lo;
+          split8(f[i][0], f[i][1], hi, lo);
+          const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi;
+          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full[stage]);
+        if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == TC_PROD_WARPS) {
+    // ================================ B loader ============================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nblk = g.n_pad64 / 64;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % g.n_tiles) * BN;
+        int rows = g.n_pad64 - n0;
+        if (rows > BN) rows = BN;
+        const uint32_t bytes = (uint32_t)rows * 128;
+        for (int kb = 0; kb < g.nk; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* b_hi = smem + stage * Cfg::stage_bytes + 2 * TC_A_BYTES;
+          uint8_t* b_lo = b_hi + Cfg::b_bytes;
+          const uint8_t* src_hi = wimg + ((size_t)(kb * 2 + 0) * nblk + (n0 >> 6)) * 8192;
+          const uint8_t* src_lo = wimg + ((size_t)(kb * 2 + 1) * nblk + (n0 >> 6)) * 8192;
+          mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+          bulk_g2s(b_hi, src_hi, bytes, &full[stage]);
+          bulk_g2s(b_lo, src_lo, bytes, &full[stage]);
+          if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == TC_PROD_WARPS + 1) {
+    // ================================ MMA issuer ==========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        const uint32_t bphase = (local >> 1) & 1;
+        mbar_wait(&tempty[buf], bphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < g.nk; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
+          const uint64_t a_hi = umma_desc_sw128(sa, 1, 64);
+          const uint64_t a_lo = umma_desc_sw128(sa + TC_A_BYTES, 1, 64);
+          const uint64_t b_hi = umma_desc_sw128(sa + 2 * TC_A_BYTES, 1, 64);
+          const uint64_t b_lo = umma_desc_sw128(sa + 2 * TC_A_BYTES + Cfg::b_bytes, 1, 64);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (2 x 16 B units) per K=16 step
+            umma_bf16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+          umma_commit(&empty[stage]);  // smem stage reusable once these MMAs retire
+          if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[buf]);      // accumulator complete
+      }
+    }
+  } else {
+    // ================================ epilogue ============================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const uint32_t bphase = (local >> 1) & 1;
+      const long long p = (long long)(tile / g.n_tiles) * TC_BM + q * 32 + lane;
+      const int n0 = (tile % g.n_tiles) * BN;
+      mbar_wait(&tfull[buf], bphase);
+      tc_fence_after();
+      const bool prow = p < g.M;
+      const float rs = (d.row_scale && prow) ? d.row_scale[p / hw] : 1.f;
+      const long long obase = p * d.y_ld;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= d.cout) break;  // warp-uniform
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
+        if (prow) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            if (n >= d.cout) break;
+            float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+            if (d.bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(d.bias + n));
+              o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+            }
+            if (d.y_pre) *reinterpret_cast<float4*>(d.y_pre + obase + n) = make_float4(o[0], o[1], o[2], o[3]);
+            if (d.act) {
+              if (d.act == NSR_ACT_PRELU) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
+                o[0] = apply_act(o[0], d.act, s4.x); o[1] = apply_act(o[1], d.act, s4.y);
+                o[2] = apply_act(o[2], d.act, s4.z); o[3] = apply_act(o[3], d.act, s4.w);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = apply_act(o[e], d.act, d.act_slope);
+              }
+            }
+            if (d.actgrad) {
+              const float4 a4 = *reinterpret_cast<const float4*>(d.aux + obase + n);
+              if (d.actgrad == NSR_ACT_PRELU) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
+                o[0] *= act_grad(a4.x, d.actgrad, s4.x); o[1] *= act_grad(a4.y, d.actgrad, s4.y);
+                o[2] *= act_grad(a4.z, d.actgrad, s4.z); o[3] *= act_grad(a4.w, d.actgrad, s4.w);
+              } else {
+                o[0] *= act_grad(a4.x, d.actgrad, d.actgrad_slope); o[1] *= act_grad(a4.y, d.actgrad, d.actgrad_slope);
+                o[2] *= act_grad(a4.z, d.actgrad, d.actgrad_slope); o[3] *= act_grad(a4.w, d.actgrad, d.actgrad_slope);
+              }
+            }
+            if (d.row_scale) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] *= rs;
+            }
+            if (d.residual) {
+              const float4 r4 = *reinterpret_cast<const float4*>(d.residual + obase + n);
+              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+            }
+            *reinterpret_cast<float4*>(d.y + obase + n) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_PROD_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int pick_bn(int cout) {
+  // smallest tile count first, then least padding waste
+  int best = 64, best_cost = 1 << 30;
+  const int cands[4] = {64, 128, 192, 256};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const int tiles = (cout + bn - 1) / bn;
+    const int cost = tiles * bn;  // total padded N; ties -> bigger tile (fewer A re-reads)
+    if (cost < best_cost || (cost == best_cost && bn > best)) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+bool conv_fprop_tc_supported(const NsrConv& d) {
+  static int ok_dev = -1;
+  if (ok_dev < 0) ok_dev = nsr_device_supports_tcgen05();
+  if (!ok_dev) return false;
+  if (d.cin % 4 || d.x_ld % 4 || d.cout % 4 || d.y_ld % 4) return false;
+  if (d.cin < 16 || d.cout < 16) return false;  // image-side 3-channel convs stay on the SIMT engine
+  if (!aligned16(d.x) || !aligned16(d.y) || !aligned16(d.bias) || !aligned16(d.aux) || !aligned16(d.residual) ||
+      !aligned16(d.y_pre) || !aligned16(d.prelu) || !aligned16(d.w_packed))
+    return false;
+  return true;
+}
+
+template <int BN>
+static int launch_fprop_tc(const NsrConv& d, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes);
+    if (e != cudaSuccess) {
+      set_error("igemm_fprop_tc<%d>: cudaFuncSetAttribute(%d): %s", BN, Cfg::smem_bytes, cudaGetErrorString(e));
+      return NSR_E_CUDA;
+    }
+    attr = true;
+  }
+  // which packed flavour this is does not matter: the GEMM view is W[n = d.cout][tap][c = d.cin]
+  PackedGeom pg = packed_geom(d.cout, d.cin, d.kh, d.kw, 0);
+  TcGeom g;
+  g.M = (long long)d.batch * d.h * d.w;
+  g.m_tiles = ceil_div(g.M, TC_BM);
+  g.n_tiles = ceil_div(d.cout, BN);
+  g.num_tiles = g.m_tiles * g.n_tiles;
+  g.cblks = pg.cblks;
+  g.nk = pg.taps * pg.cblks;
+  g.n_pad64 = pg.n_pad64;
+  const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + pg.f32_bytes;
+  const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  igemm_fprop_tc<BN><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, g, wimg);
+  NSR_CHECK_LAUNCH("igemm_fprop_tc");
+  return NSR_OK;
+}
+
+int conv_fprop_tc(const NsrConv& d, cudaStream_t st) {
+  switch (pick_bn(d.cout)) {
+    case 64: return launch_fprop_tc<64>(d, st);
+    case 128: return launch_fprop_tc<128>(d, st);
+    case 192: return launch_fprop_tc<192>(d, st);
+    default: return launch_fprop_tc<256>(d, st);
+  }
+}
+
+// wgrad on tcgen05: not built yet -> SIMT engine
 bool conv_wgrad_tc_supported(const NsrWgrad&) { return false; }
 size_t conv_wgrad_workspace_tc(const NsrWgrad&) { return 0; }
-int conv_wgrad_tc(const NsrWgrad&, cudaStream_t) { set_error("tcgen05 engine not built"); return NSR_E_INVALID; }
+int conv_wgrad_tc(const NsrWgrad&, cudaStream_t) {
+  set_error("tcgen05 wgrad not built");
+  return NSR_E_INVALID;
+}
+
 }  // namespace nsr

