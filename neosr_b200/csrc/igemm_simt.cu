@@ -281,6 +281,15 @@ __global__ void colsum_final(const float* __restrict__ partial, float* __restric
   out[c] = s;
 }
 
+int launch_wgrad_reduce(const float* partial, float* dw, int splitk, int cout, int taps, int cin, cudaStream_t st) {
+  const size_t n = (size_t)cout * taps * cin;
+  int blocks = ceil_div(n, 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  wgrad_reduce<<<blocks, 256, 0, st>>>(partial, dw, splitk, cout, taps, cin);
+  NSR_CHECK_LAUNCH("wgrad_reduce");
+  return NSR_OK;
+}
+
 size_t conv_wgrad_workspace_simt(const NsrWgrad& d) {
   WgradPlan p = wgrad_plan(d);
   return (p.dw_partial_floats + p.bias_partial_floats) * sizeof(float);
@@ -307,10 +316,8 @@ int conv_wgrad_simt(const NsrWgrad& d, cudaStream_t st) {
   dim3 grid((unsigned)p.tiles, (unsigned)p.splitk);
   igemm_wgrad_simt<<<grid, WTHREADS, 0, st>>>(d, p, partial);
   NSR_CHECK_LAUNCH("igemm_wgrad_simt");
-  const size_t n = (size_t)d.cout * p.taps * d.cin;
-  wgrad_reduce<<<ceil_div(n, 256) > 1184 ? 1184 : ceil_div(n, 256), 256, 0, st>>>(partial, d.dw, p.splitk, d.cout,
-                                                                                     p.taps, d.cin);
-  NSR_CHECK_LAUNCH("wgrad_reduce");
+  int rc = launch_wgrad_reduce(partial, d.dw, p.splitk, d.cout, p.taps, d.cin, st);
+  if (rc) return rc;
   if (d.dbias) return conv_bias_grad(d, partial + p.dw_partial_floats, p.bias_blocks, st);
   return NSR_OK;
 }

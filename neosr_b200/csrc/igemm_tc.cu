@@ -71,8 +71,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int hw = d.h * d.w;
-  const int taps = d.kh * d.kw;
-
   if (warp < TC_PROD_WARPS) {
     // ================================ A producers =========================================
     const int t = threadIdx.x;        // 0..255
@@ -330,12 +328,349 @@ int conv_fprop_tc(const NsrConv& d, cudaStream_t st) {
   }
 }
 
-// wgrad on tcgen05: not built yet -> SIMT engine
-bool conv_wgrad_tc_supported(const NsrWgrad&) { return false; }
-size_t conv_wgrad_workspace_tc(const NsrWgrad&) { return 0; }
-int conv_wgrad_tc(const NsrWgrad&, cudaStream_t) {
-  set_error("tcgen05 wgrad not built");
-  return NSR_E_INVALID;
+// ==========================================================================================
+// wgrad:  dw[co, tap, ci] = sum_p dy[p, co] * x[p @ tap, ci]
+//
+// The reduction runs over pixels, so both UMMA operands are "MN-major": a smem row is one pixel
+// (the K index) holding 64 consecutive channels (128 B, SWIZZLE_128B) — byte-for-byte the tile
+// the fprop producers build, only the descriptor says MN-major.  P (rows of D, 128 channels =
+// two 64-channel panels) and Q (columns of D, BN channels) are dy and x in whichever orientation
+// wastes less padding.  Pixels are split across CTAs (deterministic split-K: per-split partials
+// go to the workspace, wgrad_reduce sums them in a fixed order).
+constexpr int WG_KPIX = 64;  // pixels per k-block
+
+template <int BN>
+struct WgCfg {
+  static constexpr int p_bytes = 2 * WG_KPIX * 128;       // one half (hi or lo): 2 panels
+  static constexpr int q_bytes = (BN / 64) * WG_KPIX * 128;
+  static constexpr int stage_bytes = 2 * p_bytes + 2 * q_bytes;
+  static constexpr int stages = (200 * 1024) / stage_bytes > 4 ? 4 : (200 * 1024) / stage_bytes;
+  static constexpr int smem_bytes = stages * stage_bytes + 1024 + 256;
+};
+
+struct WgGeom {
+  int swap;            // 0: P = dy (rows = cout), Q = x (cols = cin); 1: P = x, Q = dy
+  int pc, qc;          // channel counts of P and Q
+  int p_ld, q_ld;
+  int m_tiles, n_tiles, taps, splitk, num_items;
+  long long M, rows_per_split;
+  const float* p_ptr;
+  const float* q_ptr;
+};
+
+int launch_wgrad_reduce(const float* partial, float* dw, int splitk, int cout, int taps, int cin, cudaStream_t st);
+int conv_bias_grad(const NsrWgrad& d, float* bias_partial, int bias_blocks, cudaStream_t st);
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) igemm_wgrad_tc(NsrWgrad d, WgGeom g, float* __restrict__ partial) {
+  using Cfg = WgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::stages * Cfg::stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::stages;
+  uint64_t* tfull = bars + 2 * Cfg::stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::stages; ++s) {
+      mbar_init(&full[s], TC_PROD_WARPS * 32);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == TC_PROD_WARPS + 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int hw = d.h * d.w;
+
+  // item -> (m_tile, n_tile, tap, split)
+  auto decode = [&](int item, int& mt, int& nt, int& tap, int& split) {
+    split = item % g.splitk;
+    item /= g.splitk;
+    tap = item % g.taps;
+    item /= g.taps;
+    nt = item % g.n_tiles;
+    mt = item / g.n_tiles;
+  };
+
+  if (warp < TC_PROD_WARPS) {
+    // ================================ producers ===========================================
+    constexpr int P_ITEMS = WG_KPIX * 16;                // (row, chunk) pairs in the P tile
+    constexpr int ITEMS = WG_KPIX * (128 + BN) / 8;      // P then Q
+    constexpr int PER_THREAD = ITEMS / (TC_PROD_WARPS * 32);
+    static_assert(ITEMS % (TC_PROD_WARPS * 32) == 0, "tile items must divide evenly");
+    const int t = threadIdx.x;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < g.num_items; item += gridDim.x) {
+      int mt, nt, tap, split;
+      decode(item, mt, nt, tap, split);
+      const int r = tap / d.kw, s = tap - r * d.kw;
+      const int dh = r - d.pad, dwc = s - d.pad;
+      const int pdh = g.swap ? dh : 0, pdw = g.swap ? dwc : 0;   // the x operand carries the tap shift
+      const int qdh = g.swap ? 0 : dh, qdw = g.swap ? 0 : dwc;
+      const long long p_begin = (long long)split * g.rows_per_split;
+      long long p_end = p_begin + g.rows_per_split;
+      if (p_end > g.M) p_end = g.M;
+      const int nkb = (int)((p_end - p_begin + WG_KPIX - 1) / WG_KPIX);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const long long pk = p_begin + (long long)kb * WG_KPIX;
+        uint8_t* st_base = smem + stage * Cfg::stage_bytes;
+        bool waited = false;
+#pragma unroll 1
+        for (int i0 = 0; i0 < PER_THREAD; i0 += 2) {
+          float4 f[2][2];
+          int offs[2];
+          uint8_t* dst_hi[2];
+          uint8_t* dst_lo[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int idx = t + (i0 + u) * (TC_PROD_WARPS * 32);
+            const bool isP = idx < P_ITEMS;
+            const int li = isP ? idx : idx - P_ITEMS;
+            const int chunks = isP ? 16 : BN / 8;
+            const int row = li / chunks, chunk = li - row * chunks;   // row = pixel within the k-block
+            const int c0 = (isP ? mt * 128 : nt * BN) + chunk * 8;
+            const int cmax = isP ? g.pc : g.qc;
+            const int ld = isP ? g.p_ld : g.q_ld;
+            const float* base = isP ? g.p_ptr : g.q_ptr;
+            const int sh = isP ? pdh : qdh, sw = isP ? pdw : qdw;
+            const long long p = pk + row;
+            bool ok = p < p_end;
+            long long sp = p;
+            if (ok && (sh | sw)) {
+              const long long b = p / hw;
+              const int rem = (int)(p - b * hw);
+              const int oh = rem / d.w, ow = rem - oh * d.w;
+              const int ih = oh + sh, iw = ow + sw;
+              ok = ih >= 0 && ih < d.h && iw >= 0 && iw < d.w;
+              sp = p + (long long)sh * d.w + sw;
+            }
+            const float* src = base + sp * ld + c0;
+            f[u][0] = (ok && c0 < cmax) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            f[u][1] = (ok && c0 + 4 < cmax) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // panel = 64-channel group; inside a panel: row * 128 B, 16-byte chunk swizzled by row
+            const int panel = chunk >> 3, cc = chunk & 7;
+            offs[u] = panel * (WG_KPIX * 128) + row * 128 + ((cc ^ (row & 7)) << 4);
+            dst_hi[u] = st_base + (isP ? 0 : 2 * Cfg::p_bytes);
+            dst_lo[u] = dst_hi[u] + (isP ? Cfg::p_bytes : Cfg::q_bytes);
+          }
+          if (!waited) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            waited = true;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint4 hi, lo;
+            split8(f[u][0], f[u][1], hi, lo);
+            *reinterpret_cast<uint4*>(dst_hi[u] + offs[u]) = hi;
+            *reinterpret_cast<uint4*>(dst_lo[u] + offs[u]) = lo;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full[stage]);
+        if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == TC_PROD_WARPS + 1) {
+    // ================================ MMA issuer ==========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN, 1, 1);  // both operands MN-major
+      constexpr uint32_t LBO = (WG_KPIX * 128) >> 4;         // next 64-channel panel
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int item = blockIdx.x; item < g.num_items; item += gridDim.x, ++local) {
+        int mt, nt, tap, split;
+        decode(item, mt, nt, tap, split);
+        const long long p_begin = (long long)split * g.rows_per_split;
+        long long p_end = p_begin + g.rows_per_split;
+        if (p_end > g.M) p_end = g.M;
+        const int nkb = (int)((p_end - p_begin + WG_KPIX - 1) / WG_KPIX);
+        const int buf = local & 1;
+        const uint32_t bphase = (local >> 1) & 1;
+        mbar_wait(&tempty[buf], bphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
+          const uint64_t p_hi = umma_desc_sw128(sa, LBO, 64);
+          const uint64_t p_lo = umma_desc_sw128(sa + Cfg::p_bytes, LBO, 64);
+          const uint64_t q_hi = umma_desc_sw128(sa + 2 * Cfg::p_bytes, LBO, 64);
+          const uint64_t q_lo = umma_desc_sw128(sa + 2 * Cfg::p_bytes + Cfg::q_bytes, LBO, 64);
+          // K = 16 pixels per MMA = two 8-row swizzle atoms = 2048 B = 128 x 16 B units
+#pragma unroll
+          for (int k = 0; k < WG_KPIX / 16; ++k) umma_bf16(tmem_d, p_hi + 128 * k, q_hi + 128 * k, idesc, (kb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < WG_KPIX / 16; ++k) umma_bf16(tmem_d, p_hi + 128 * k, q_lo + 128 * k, idesc, 1);
+#pragma unroll
+          for (int k = 0; k < WG_KPIX / 16; ++k) umma_bf16(tmem_d, p_lo + 128 * k, q_hi + 128 * k, idesc, 1);
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= TC_PROD_WARPS + 2) {
+    // ================================ epilogue: TMEM -> split-K partial ====================
+    const int q = warp & 3;
+    int local = 0;
+    const size_t per_split = (size_t)d.cout * g.taps * d.cin;
+    for (int item = blockIdx.x; item < g.num_items; item += gridDim.x, ++local) {
+      int mt, nt, tap, split;
+      decode(item, mt, nt, tap, split);
+      const int buf = local & 1;
+      const uint32_t bphase = (local >> 1) & 1;
+      mbar_wait(&tfull[buf], bphase);
+      tc_fence_after();
+      float* out = partial + (size_t)split * per_split;
+      const int m = mt * 128 + q * 32 + lane;  // P-channel of this thread's accumulator row
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (nt * BN + c0 >= g.qc) break;
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
+        if (m < g.pc) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nt * BN + c0 + j;
+            if (n < g.qc) {
+              const int co = g.swap ? n : m, ci = g.swap ? m : n;
+              out[((size_t)co * g.taps + tap) * d.cin + ci] = v[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_PROD_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct WgPlan {
+  WgGeom g;
+  int bn;
+  int bias_blocks;
+  size_t dw_partial_floats, bias_partial_floats;
+};
+
+static int wg_pick_bn(int qc, int& cost) {
+  int best = 64;
+  cost = 1 << 30;
+  const int cands[4] = {64, 128, 192, 256};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const int c = ((qc + bn - 1) / bn) * bn;
+    if (c < cost || (c == cost && bn > best)) { best = bn; cost = c; }
+  }
+  return best;
+}
+
+static WgPlan wg_plan(const NsrWgrad& d) {
+  WgPlan p;
+  WgGeom& g = p.g;
+  g.M = (long long)d.batch * d.h * d.w;
+  g.taps = d.kh * d.kw;
+  // orientation: rows (P, tiles of 128) x cols (Q, tiles of BN); minimise padded area
+  int cost_a, cost_b;
+  const int bn_a = wg_pick_bn(d.cin, cost_a);   // P = dy (cout), Q = x (cin)
+  const int bn_b = wg_pick_bn(d.cout, cost_b);  // P = x (cin),  Q = dy (cout)
+  const long long area_a = (long long)((d.cout + 127) / 128 * 128) * cost_a;
+  const long long area_b = (long long)((d.cin + 127) / 128 * 128) * cost_b;
+  g.swap = area_b < area_a ? 1 : 0;
+  p.bn = g.swap ? bn_b : bn_a;
+  g.pc = g.swap ? d.cin : d.cout;
+  g.qc = g.swap ? d.cout : d.cin;
+  g.p_ld = g.swap ? d.x_ld : d.dy_ld;
+  g.q_ld = g.swap ? d.dy_ld : d.x_ld;
+  g.p_ptr = g.swap ? d.x : d.dy;
+  g.q_ptr = g.swap ? d.dy : d.x;
+  g.m_tiles = (g.pc + 127) / 128;
+  g.n_tiles = (g.qc + p.bn - 1) / p.bn;
+  const int tiles = g.m_tiles * g.n_tiles * g.taps;
+  int want = (kNumSMs + tiles - 1) / tiles;
+  const int maxs = (int)((g.M + 1023) / 1024);
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  long long rps = (g.M + want - 1) / want;
+  g.rows_per_split = (rps + WG_KPIX - 1) / WG_KPIX * WG_KPIX;
+  g.splitk = (int)((g.M + g.rows_per_split - 1) / g.rows_per_split);
+  g.num_items = tiles * g.splitk;
+  p.dw_partial_floats = (size_t)g.splitk * d.cout * g.taps * d.cin;
+  p.bias_blocks = (int)((g.M + 1023) / 1024);
+  if (p.bias_blocks > kNumSMs * 4) p.bias_blocks = kNumSMs * 4;
+  p.bias_partial_floats = (size_t)p.bias_blocks * d.cout;
+  return p;
+}
+
+bool conv_wgrad_tc_supported(const NsrWgrad& d) {
+  static int ok_dev = -1;
+  if (ok_dev < 0) ok_dev = nsr_device_supports_tcgen05();
+  if (!ok_dev) return false;
+  if (d.cin % 4 || d.cout % 4 || d.x_ld % 4 || d.dy_ld % 4) return false;
+  if (d.cin < 16 || d.cout < 16) return false;
+  if (!aligned16(d.x) || !aligned16(d.dy)) return false;
+  return true;
+}
+size_t conv_wgrad_workspace_tc(const NsrWgrad& d) {
+  WgPlan p = wg_plan(d);
+  return (p.dw_partial_floats + p.bias_partial_floats) * sizeof(float);
+}
+
+template <int BN>
+static int launch_wgrad_tc(const NsrWgrad& d, const WgPlan& p, float* partial, cudaStream_t st) {
+  using Cfg = WgCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes);
+    if (e != cudaSuccess) {
+      set_error("igemm_wgrad_tc<%d>: cudaFuncSetAttribute: %s", BN, cudaGetErrorString(e));
+      return NSR_E_CUDA;
+    }
+    attr = true;
+  }
+  const int grid = p.g.num_items < kNumSMs ? p.g.num_items : kNumSMs;
+  igemm_wgrad_tc<BN><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, p.g, partial);
+  NSR_CHECK_LAUNCH("igemm_wgrad_tc");
+  return NSR_OK;
+}
+
+int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st) {
+  WgPlan p = wg_plan(d);
+  const size_t need = (p.dw_partial_floats + p.bias_partial_floats) * sizeof(float);
+  if (d.workspace_bytes < need || d.workspace == nullptr) {
+    set_error("nsr_conv_wgrad(tcgen05): workspace %zu < %zu", d.workspace_bytes, need);
+    return NSR_E_WORKSPACE;
+  }
+  float* partial = reinterpret_cast<float*>(d.workspace);
+  int rc;
+  switch (p.bn) {
+    case 64: rc = launch_wgrad_tc<64>(d, p, partial, st); break;
+    case 128: rc = launch_wgrad_tc<128>(d, p, partial, st); break;
+    case 192: rc = launch_wgrad_tc<192>(d, p, partial, st); break;
+    default: rc = launch_wgrad_tc<256>(d, p, partial, st); break;
+  }
+  if (rc) return rc;
+  rc = launch_wgrad_reduce(partial, d.dw, p.g.splitk, d.cout, p.g.taps, d.cin, st);
+  if (rc) return rc;
+  if (d.dbias) return conv_bias_grad(d, partial + p.dw_partial_floats, p.bias_blocks, st);
+  return NSR_OK;
 }
 
 }  // namespace nsr

@@ -57,7 +57,7 @@ def test_conv_fprop_dgrad_wgrad(engine, B, H, W, cin, cout, k):
     dx = ops.conv_fprop(nhwc(dy), pw, None, dgrad=True, engine=engine)
     assert rel(nchw(dx), x.grad) < 1e-4
     dw, db = torch.empty_like(w), torch.empty_like(b)
-    ops.conv_wgrad(nhwc(x.detach()), nhwc(dy), dw, db, k, k, engine="auto")
+    ops.conv_wgrad(nhwc(x.detach()), nhwc(dy), dw, db, k, k, engine=engine)
     assert rel(dw, w.grad) < 1e-4
     assert rel(db, b.grad) < 1e-4
 
@@ -106,6 +106,18 @@ def test_tcgen05_large_vs_torch(M, K, N, k):
     assert rel(y, ref) < 2e-5
     y2 = ops.conv_fprop(x, pw, b, residual=res, engine="tcgen05")
     assert torch.equal(y, y2)  # run-to-run deterministic
+    # wgrad: dw = dy^T x over all pixels (split-K, MN-major operands)
+    dy = rnd(B, H, W, N, seed=15)
+    xg = nchw(x).requires_grad_(True)
+    wg = w.clone().requires_grad_(True)
+    F.conv2d(xg, wg, None, 1, k // 2).backward(nchw(dy))
+    dw, db = torch.empty_like(w), torch.empty_like(b)
+    ops.conv_wgrad(x, dy, dw, db, k, k, engine="tcgen05")
+    assert rel(dw, wg.grad) < 2e-5
+    assert rel(db, dy.sum((0, 1, 2))) < 1e-5
+    dw2 = torch.empty_like(w)
+    ops.conv_wgrad(x, dy, dw2, None, k, k, engine="tcgen05")
+    assert torch.equal(dw, dw2)
 
 
 def test_layout_pixelshuffle_maxpool_bitexact():
