@@ -43,6 +43,49 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// Fast exact-form GELU for the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, below fp32 resolution of the O(1) activations it feeds), sharing one
+// exp(-x^2/2) between the cdf and the pdf.  ~15 instructions instead of ~45 for erff + expf.
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float e = __expf(-z * z);                       // = exp(-x^2 / 2)
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;            // erf(|x| / sqrt 2)
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  pdf = 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float c, p;
+  gelu_terms(x, c, p);
+  return x * c;
+}
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  float c, p;
+  gelu_terms(x, c, p);
+  return fmaf(x, p, c);
+}
+__device__ __forceinline__ float apply_act_fast(float v, int act, float slope) {
+  switch (act) {
+    case NSR_ACT_RELU: return v > 0.f ? v : 0.f;
+    case NSR_ACT_LRELU:
+    case NSR_ACT_PRELU: return v > 0.f ? v : v * slope;
+    case NSR_ACT_GELU: return gelu_fast(v);
+    default: return v;
+  }
+}
+__device__ __forceinline__ float act_grad_fast(float aux, int act, float slope) {
+  switch (act) {
+    case NSR_ACT_RELU: return aux > 0.f ? 1.f : 0.f;
+    case NSR_ACT_LRELU:
+    case NSR_ACT_PRELU: return aux > 0.f ? 1.f : slope;
+    case NSR_ACT_GELU: return gelu_fast_grad(aux);
+    default: return 1.f;
+  }
+}
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   switch (act) {
     case NSR_ACT_RELU: return v > 0.f ? v : 0.f;

@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import ACT, ENGINE, NsrConv, NsrWgrad, check
 
 
+DEFAULT_ENGINE = "auto"  # what engine="auto" resolves to ("auto" | "simt" | "tcgen05"); tests flip it
 LAUNCHES = 0          # kernels launched through this module (claim reported by bench.py)
 PROFILE: list | None = None  # when a list: (kernel, shape-key, flops, bytes, start_evt, end_evt) per call
 
@@ -139,7 +140,7 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
     y_pre = torch.empty_like(y) if want_pre else None
     d = NsrConv(batch=B, h=H, w=W, cin=cin, cout=cout, kh=pw.kh, kw=pw.kw, pad=pw.kh // 2,
                 x_ld=cin, y_ld=cout, act=ACT[act], act_slope=act_slope, actgrad=ACT[actgrad],
-                actgrad_slope=actgrad_slope, engine=ENGINE[engine],
+                actgrad_slope=actgrad_slope, engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
                 x=x.data_ptr(), w_packed=(pw.dgrad if dgrad else pw.fprop).data_ptr(), bias=_p(bias),
                 prelu=_p(prelu), aux=_p(aux), row_scale=_p(row_scale), residual=_p(residual),
                 y_pre=_p(y_pre), y=y.data_ptr())
@@ -159,7 +160,7 @@ def conv_wgrad(x: Tensor, dy: Tensor, dw: Tensor, dbias: Tensor | None, kh: int,
     if dy.shape[:3] != x.shape[:3] or dw.numel() != cout * cin * kh * kw:
         raise ValueError(f"conv_wgrad: shape mismatch x{tuple(x.shape)} dy{tuple(dy.shape)} dw{tuple(dw.shape)}")
     d = NsrWgrad(batch=B, h=H, w=W, cin=cin, cout=cout, kh=kh, kw=kw, pad=kh // 2, x_ld=cin, dy_ld=cout,
-                 engine=ENGINE[engine], x=x.data_ptr(), dy=dy.data_ptr(), dw=dw.data_ptr(), dbias=_p(dbias),
+                 engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine], x=x.data_ptr(), dy=dy.data_ptr(), dw=dw.data_ptr(), dbias=_p(dbias),
                  workspace=None, workspace_bytes=0)
     L = _lib.lib()
     need = L.nsr_conv_wgrad_workspace(C.byref(d))

@@ -108,13 +108,12 @@ def test_tcgen05_large_vs_torch(M, K, N, k):
     assert torch.equal(y, y2)  # run-to-run deterministic
     # wgrad: dw = dy^T x over all pixels (split-K, MN-major operands)
     dy = rnd(B, H, W, N, seed=15)
-    xg = nchw(x).requires_grad_(True)
-    wg = w.clone().requires_grad_(True)
-    F.conv2d(xg, wg, None, 1, k // 2).backward(nchw(dy))
+    wg = w.double().requires_grad_(True)  # fp64 reference: the reduction runs over up to 131072 pixels
+    F.conv2d(nchw(x).double(), wg, None, 1, k // 2).backward(nchw(dy).double())
     dw, db = torch.empty_like(w), torch.empty_like(b)
     ops.conv_wgrad(x, dy, dw, db, k, k, engine="tcgen05")
-    assert rel(dw, wg.grad) < 2e-5
-    assert rel(db, dy.sum((0, 1, 2))) < 1e-5
+    assert rel(dw.double(), wg.grad) < 3e-5
+    assert rel(db.double(), dy.double().sum((0, 1, 2))) < 1e-5
     dw2 = torch.empty_like(w)
     ops.conv_wgrad(x, dy, dw2, None, k, k, engine="tcgen05")
     assert torch.equal(dw, dw2)

@@ -32,6 +32,9 @@ def test_tiny_fwd_bwd(tag, hw):
     grads = torch.autograd.grad((y - gt).abs().mean(), list(p.values()))
     for k, gi in zip(p, grads):
         assert _rel(gi, z[f"{tag}.grad.{k}"]) < 2e-4, k
+    grads = torch.autograd.grad(((swinir_forward(p, cfg, x) - gt) ** 2).mean(), list(p.values()))
+    for k, gi in zip(p, grads):
+        assert _rel(gi, z[f"{tag}.mse_grad.{k}"]) < 2e-4, k
 
 
 def test_tiny_step3():

@@ -37,9 +37,24 @@ def test_tiny_forward_backward_vs_golden(tag, hw):
     y = net(x.cuda())
     gt = torch.rand(y.shape, generator=g).cuda()
     assert rel(y.detach(), z[f"{tag}.y"]) < 1e-4
-    (y - gt).abs().mean().backward()
-    worst = max(rel(v.grad, z[f"{tag}.grad.{k}"]) for k, v in net.named_parameters())
-    assert worst < 1e-3, worst
+    # smooth (MSE) loss: every parameter gradient within 1e-3 relative on the default engine mix
+    ((y - gt) ** 2).mean().backward()
+    errs = {k: rel(v.grad, z[f"{tag}.mse_grad.{k}"]) for k, v in net.named_parameters()}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 1e-3, (worst, errs[worst])
+    # L1 loss (sign() of y - gt): exact-fp32 engine reproduces the reference gradients to 1e-3;
+    # the split-precision engine may flip sign() where |y - gt| < 1e-6, so it is held to 1e-2 there
+    from neosr_b200 import ops
+    for engine, tol in (("simt", 1e-3), ("auto", 1e-2)):
+        ops.DEFAULT_ENGINE = engine
+        try:
+            net.zero_grad()
+            (net(x.cuda()) - gt).abs().mean().backward()
+        finally:
+            ops.DEFAULT_ENGINE = "auto"
+        errs = {k: rel(v.grad, z[f"{tag}.grad.{k}"]) for k, v in net.named_parameters()}
+        worst = max(errs, key=errs.get)
+        assert errs[worst] < tol, (engine, worst, errs[worst])
 
 
 def test_medium_forward_and_losses_vs_golden():
