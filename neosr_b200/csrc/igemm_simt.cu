@@ -261,16 +261,57 @@ __global__ void wgrad_reduce(const float* __restrict__ partial, float* __restric
   }
 }
 
-// column sums of dy[M, cout] (row stride ld): phase 1 -> partial[block][cout]
-__global__ void colsum_partial(const float* __restrict__ dy, float* __restrict__ partial, long long M, int cout, int ld) {
-  const long long rows_per = (M + gridDim.x - 1) / gridDim.x;
-  const long long r0 = (long long)blockIdx.x * rows_per;
+// column sums of dy[M, cout] (row stride ld): phase 1 -> partial[blockIdx.y][cout].
+// blockDim = (64 column quads, 4 row lanes); each thread keeps 8 independent 16-byte loads in
+// flight (rows r, r+4, ...), so the pass streams at HBM rate instead of one load per round trip.
+__global__ void __launch_bounds__(256) colsum_partial(const float* __restrict__ dy, float* __restrict__ partial,
+                                                      long long M, int cout, int ld, int vec) {
+  __shared__ float4 red[4][64];
+  const int cq = blockIdx.x * 64 + threadIdx.x;       // column quad
+  const int c = cq * 4;
+  const long long rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * rows_per;
   long long r1 = r0 + rows_per;
   if (r1 > M) r1 = M;
-  for (int c = threadIdx.x; c < cout; c += blockDim.x) {
-    float s = 0.f;
-    for (long long r = r0; r < r1; ++r) s += dy[r * ld + c];
-    partial[(size_t)blockIdx.x * cout + c] = s;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cout) {
+    long long r = r0 + threadIdx.y;
+    if (vec && c + 3 < cout) {
+      for (; r + 28 < r1; r += 32) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(dy + (r + 4 * u) * ld + c));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+      }
+      for (; r < r1; r += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dy + r * ld + c));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    } else {
+      for (; r < r1; r += 4) {
+        const float* p = dy + r * ld + c;
+        acc.x += p[0];
+        if (c + 1 < cout) acc.y += p[1];
+        if (c + 2 < cout) acc.z += p[2];
+        if (c + 3 < cout) acc.w += p[3];
+      }
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cout) {
+    float4 s = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float4 o = red[k][threadIdx.x];
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    float* out = partial + (size_t)blockIdx.y * cout + c;
+    out[0] = s.x;
+    if (c + 1 < cout) out[1] = s.y;
+    if (c + 2 < cout) out[2] = s.z;
+    if (c + 3 < cout) out[3] = s.w;
   }
 }
 __global__ void colsum_final(const float* __restrict__ partial, float* __restrict__ out, int blocks, int cout) {
@@ -297,8 +338,9 @@ size_t conv_wgrad_workspace_simt(const NsrWgrad& d) {
 
 int conv_bias_grad(const NsrWgrad& d, float* bias_partial, int bias_blocks, cudaStream_t st) {
   const long long M = (long long)d.batch * d.h * d.w;
-  const int th = d.cout >= 256 ? 256 : (d.cout + 31) / 32 * 32;
-  colsum_partial<<<bias_blocks, th, 0, st>>>(d.dy, bias_partial, M, d.cout, d.dy_ld);
+  const int vec = (d.dy_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.dy) & 15) == 0);
+  dim3 grid((unsigned)ceil_div(d.cout, 256), (unsigned)bias_blocks), block(64, 4);
+  colsum_partial<<<grid, block, 0, st>>>(d.dy, bias_partial, M, d.cout, d.dy_ld, vec);
   NSR_CHECK_LAUNCH("colsum_partial");
   colsum_final<<<ceil_div(d.cout, 128), 128, 0, st>>>(bias_partial, d.dbias, bias_blocks, d.cout);
   NSR_CHECK_LAUNCH("colsum_final");

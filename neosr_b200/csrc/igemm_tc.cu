@@ -27,13 +27,15 @@ constexpr int TC_BK = 64;           // bf16 elements per k-block (one 128-byte s
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_PROD_WARPS + 2 + 4) * 32;  // 448
 constexpr int TC_A_BYTES = TC_BM * 128;                   // one half (hi or lo) of an A stage
+constexpr int EPI_LD = 36;                                // padded row stride (floats) of the epilogue staging tile
 
 template <int BN>
 struct TcCfg {
   static constexpr int b_bytes = BN * 128;  // one half of a B stage
   static constexpr int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
   static constexpr int stages = (200 * 1024) / stage_bytes > 4 ? 4 : (200 * 1024) / stage_bytes;
-  static constexpr int smem_bytes = stages * stage_bytes + 1024 /* align slack */ + 256 /* barriers */;
+  static constexpr int smem_bytes = stages * stage_bytes + 1024 /* align slack */ + 256 /* barriers */ +
+                                    4 * 32 * EPI_LD * 4 /* epilogue transpose staging */;
 };
 
 struct TcGeom {
@@ -207,65 +209,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
     }
   } else {
     // ================================ epilogue ============================================
+    // TMEM hands each thread one accumulator ROW (32 consecutive columns).  A per-warp smem
+    // transpose turns that into row-contiguous global traffic: every warp instruction reads
+    // (aux / residual) or writes (y, y_pre) 4 rows x 128 contiguous bytes.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(smem + Cfg::stages * Cfg::stage_bytes + 256) + q * (32 * EPI_LD);
+    const int er = lane >> 3, ec = (lane & 7) * 4;   // (row-in-group, column) of this lane's float4
     int local = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
       const uint32_t bphase = (local >> 1) & 1;
-      const long long p = (long long)(tile / g.n_tiles) * TC_BM + q * 32 + lane;
+      const long long p0 = (long long)(tile / g.n_tiles) * TC_BM + q * 32;   // first row of this warp
       const int n0 = (tile % g.n_tiles) * BN;
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
-      const bool prow = p < g.M;
-      const float rs = (d.row_scale && prow) ? d.row_scale[p / hw] : 1.f;
-      const long long obase = p * d.y_ld;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (n0 + c0 >= d.cout) break;  // warp-uniform
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
-        if (prow) {
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + c0 + j;
-            if (n >= d.cout) break;
-            float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-            if (d.bias) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(d.bias + n));
-              o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
-            }
-            if (d.y_pre) *reinterpret_cast<float4*>(d.y_pre + obase + n) = make_float4(o[0], o[1], o[2], o[3]);
-            if (d.act) {
-              if (d.act == NSR_ACT_PRELU) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
-                o[0] = apply_act_fast(o[0], d.act, s4.x); o[1] = apply_act_fast(o[1], d.act, s4.y);
-                o[2] = apply_act_fast(o[2], d.act, s4.z); o[3] = apply_act_fast(o[3], d.act, s4.w);
-              } else {
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int n = n0 + c0 + ec;
+        const bool ncol = n < d.cout;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
+        if (ncol && d.bias) b4 = __ldg(reinterpret_cast<const float4*>(d.bias + n));
+        if (ncol && d.prelu) s4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
+        float4 aux4[8], res4[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = apply_act_fast(o[e], d.act, d.act_slope);
-              }
-            }
-            if (d.actgrad) {
-              const float4 a4 = *reinterpret_cast<const float4*>(d.aux + obase + n);
-              if (d.actgrad == NSR_ACT_PRELU) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
-                o[0] *= act_grad_fast(a4.x, d.actgrad, s4.x); o[1] *= act_grad_fast(a4.y, d.actgrad, s4.y);
-                o[2] *= act_grad_fast(a4.z, d.actgrad, s4.z); o[3] *= act_grad_fast(a4.w, d.actgrad, s4.w);
-              } else {
-                o[0] *= act_grad_fast(a4.x, d.actgrad, d.actgrad_slope); o[1] *= act_grad_fast(a4.y, d.actgrad, d.actgrad_slope);
-                o[2] *= act_grad_fast(a4.z, d.actgrad, d.actgrad_slope); o[3] *= act_grad_fast(a4.w, d.actgrad, d.actgrad_slope);
-              }
-            }
-            if (d.row_scale) {
+        for (int i = 0; i < 8; ++i) {
+          const long long p = p0 + i * 4 + er;
+          const bool ok = ncol && p < g.M;
+          const long long o = p * d.y_ld + n;
+          aux4[i] = (ok && d.actgrad) ? *reinterpret_cast<const float4*>(d.aux + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          res4[i] = (ok && d.residual) ? *reinterpret_cast<const float4*>(d.residual + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] *= rs;
+        for (int i = 0; i < 8; ++i) {
+          const long long p = p0 + i * 4 + er;
+          if (!(ncol && p < g.M)) continue;
+          const long long o = p * d.y_ld + n;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + (i * 4 + er) * EPI_LD + ec);
+          float ov[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
+          if (d.y_pre) *reinterpret_cast<float4*>(d.y_pre + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+          if (d.act) {
+            if (d.act == NSR_ACT_PRELU) {
+              ov[0] = apply_act_fast(ov[0], d.act, s4.x); ov[1] = apply_act_fast(ov[1], d.act, s4.y);
+              ov[2] = apply_act_fast(ov[2], d.act, s4.z); ov[3] = apply_act_fast(ov[3], d.act, s4.w);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ov[e] = apply_act_fast(ov[e], d.act, d.act_slope);
             }
-            if (d.residual) {
-              const float4 r4 = *reinterpret_cast<const float4*>(d.residual + obase + n);
-              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-            }
-            *reinterpret_cast<float4*>(d.y + obase + n) = make_float4(o[0], o[1], o[2], o[3]);
           }
+          if (d.actgrad) {
+            if (d.actgrad == NSR_ACT_PRELU) {
+              ov[0] *= act_grad_fast(aux4[i].x, d.actgrad, s4.x); ov[1] *= act_grad_fast(aux4[i].y, d.actgrad, s4.y);
+              ov[2] *= act_grad_fast(aux4[i].z, d.actgrad, s4.z); ov[3] *= act_grad_fast(aux4[i].w, d.actgrad, s4.w);
+            } else {
+              ov[0] *= act_grad_fast(aux4[i].x, d.actgrad, d.actgrad_slope);
+              ov[1] *= act_grad_fast(aux4[i].y, d.actgrad, d.actgrad_slope);
+              ov[2] *= act_grad_fast(aux4[i].z, d.actgrad, d.actgrad_slope);
+              ov[3] *= act_grad_fast(aux4[i].w, d.actgrad, d.actgrad_slope);
+            }
+          }
+          if (d.row_scale) {
+            const float rs = d.row_scale[p / hw];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ov[e] *= rs;
+          }
+          if (d.residual) { ov[0] += res4[i].x; ov[1] += res4[i].y; ov[2] += res4[i].z; ov[3] += res4[i].w; }
+          *reinterpret_cast<float4*>(d.y + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
         }
       }
       tc_fence_before();
