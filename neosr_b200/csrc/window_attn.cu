@@ -5,6 +5,8 @@
 // position index is computed arithmetically ((iy-jy+ws-1)*(2ws-1) + (ix-jx+ws-1), identical to
 // the reference's registered buffer, swinir_arch.py:120-137).  Softmax uses warp shuffles.
 // Backward recomputes P, and reduces the bias-table gradient deterministically.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nsr {
@@ -226,8 +228,23 @@ __global__ void window_attn_dbias_kernel(const float* __restrict__ partial, floa
   dtable[tidx * heads + head] = s;
 }
 
-static int bwd_gx(int nwin, int heads) {
-  int gx = (2 * kNumSMs) / heads;
+bool window_attn_mma_supported(int c, int heads, int ws);
+int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, int batch, int h, int w, int c,
+                               int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
+int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float* dout, float* dqkv, float* partial,
+                               int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
+                               float scale, cudaStream_t st);
+static bool use_mma(int c, int heads, int ws) {
+  static int simt_forced = -1;
+  if (simt_forced < 0) {
+    const char* e = getenv("NSR_ATTN");
+    simt_forced = (e && !strcmp(e, "simt")) ? 1 : 0;
+  }
+  return !simt_forced && window_attn_mma_supported(c, heads, ws);
+}
+
+static int bwd_gx(int nwin, int heads, bool mma) {
+  int gx = ((mma ? 3 : 2) * kNumSMs) / heads;
   if (gx < 1) gx = 1;
   return gx > nwin ? nwin : gx;
 }
@@ -250,6 +267,9 @@ extern "C" int nsr_window_attn_fwd(const float* qkv, const float* bias_table, fl
   WinGeom g;
   int rc = make_geom(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_fwd");
   if (rc) return rc;
+  if (use_mma(c, heads, ws))
+    return window_attn_fwd_mma_launch(qkv, bias_table, out, batch, h, w, c, heads, ws, shift, use_mask, scale,
+                                      reinterpret_cast<cudaStream_t>(stream));
   dim3 grid(batch * g.nwh * g.nww, heads);
   window_attn_fwd_kernel<<<grid, WA_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(qkv, bias_table, out, g);
   NSR_CHECK_LAUNCH("window_attn_fwd");
@@ -258,7 +278,7 @@ extern "C" int nsr_window_attn_fwd(const float* qkv, const float* bias_table, fl
 
 extern "C" size_t nsr_window_attn_bwd_workspace(int heads, int ws) {
   (void)ws;
-  return (size_t)(2 * kNumSMs) * (heads > 0 ? 1 : 1) * WA_N * WA_N * sizeof(float) + (size_t)heads * WA_N * WA_N * sizeof(float);
+  return (size_t)(3 * kNumSMs + (heads > 0 ? heads : 1)) * WA_N * WA_N * sizeof(float);
 }
 
 extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv,
@@ -269,7 +289,8 @@ extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, co
   int rc = make_geom(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_bwd");
   if (rc) return rc;
   const int nwin = batch * g.nwh * g.nww;
-  const int gx = bwd_gx(nwin, heads);
+  const bool mma = use_mma(c, heads, ws);
+  const int gx = bwd_gx(nwin, heads, mma);
   const size_t need = (size_t)gx * heads * WA_N * WA_N * sizeof(float);
   if (!workspace || workspace_bytes < need) {
     set_error("nsr_window_attn_bwd: workspace %zu < %zu", workspace_bytes, need);
@@ -287,9 +308,15 @@ extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, co
     attr_set = true;
   }
   float* partial = reinterpret_cast<float*>(workspace);
-  dim3 grid(gx, heads);
-  window_attn_bwd_kernel<<<grid, WA_THREADS, WA_BWD_SMEM, st>>>(qkv, bias_table, dout, dqkv, partial, g, nwin);
-  NSR_CHECK_LAUNCH("window_attn_bwd");
+  if (mma) {
+    rc = window_attn_bwd_mma_launch(qkv, bias_table, dout, dqkv, partial, gx, batch, h, w, c, heads, ws, shift,
+                                    use_mask, scale, st);
+    if (rc) return rc;
+  } else {
+    dim3 grid(gx, heads);
+    window_attn_bwd_kernel<<<grid, WA_THREADS, WA_BWD_SMEM, st>>>(qkv, bias_table, dout, dqkv, partial, g, nwin);
+    NSR_CHECK_LAUNCH("window_attn_bwd");
+  }
   const int n = (2 * ws - 1) * (2 * ws - 1) * heads;
   window_attn_dbias_kernel<<<ceil_div(n, 128), 128, 0, st>>>(partial, dbias_table, gx, heads, ws);
   NSR_CHECK_LAUNCH("window_attn_dbias");

@@ -1,0 +1,427 @@
+// Fused (shifted-)window attention core on the tensor cores (warp-level mma.sync m16n8k16,
+// bf16 operands split hi/lo in three passes, fp32 accumulate) for 8x8 windows, head_dim <= 32.
+//
+// One CTA iteration = one (window, head): 64 tokens, 4 warps x 16 query rows.  The 64x64x32
+// micro-GEMMs are far too small for a tcgen05/TMEM pipeline to pay off (a 128-row UMMA would
+// need two windows with different K/V); the register-resident mma.sync form keeps S, P, dP, dS in
+// registers between the GEMMs (the accumulator layout of one MMA is the A-operand layout of the
+// next), so nothing but Q/K/V/dO tiles ever touches shared memory in the forward pass.
+// Shift / window partition / mask / relative-position bias are index math, as in window_attn.cu.
+#include "common.cuh"
+
+namespace nsr {
+
+constexpr int AM_N = 64, AM_THREADS = 128;
+constexpr int AM_LD = 40;   // bf16 row stride of [token][d] tiles (80 B: conflict-free fragment loads)
+constexpr int AM_LDT = 72;  // bf16 row stride of [d][token] and [token][token] tiles (144 B)
+
+struct AttnGeom {
+  int B, H, W, C, heads, ws, shift, use_mask, D, nwh, nww;
+  float scale;
+};
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += (a_hi + a_lo) * (b_hi + b_lo) without the lo*lo term
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                     uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_bf16(c, ah, bh0, bh1);
+  mma_bf16(c, ah, bl0, bl1);
+  mma_bf16(c, al, bh0, bh1);
+}
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+// A fragment (16 rows x 16 k) from a row-major [row][k] bf16 tile
+__device__ __forceinline__ void load_a(const __nv_bfloat16* base, int ld, int row0, int k0, int g, int tid,
+                                       uint32_t (&a)[4]) {
+  const __nv_bfloat16* p = base + (row0 + g) * ld + k0 + tid * 2;
+  a[0] = lds32(p);
+  a[1] = lds32(p + 8 * ld);
+  a[2] = lds32(p + 8);
+  a[3] = lds32(p + 8 * ld + 8);
+}
+// B fragment (16 k x 8 n) from an [n][k] bf16 tile (k contiguous)
+__device__ __forceinline__ void load_b(const __nv_bfloat16* base, int ld, int n0, int k0, int g, int tid, uint32_t& b0,
+                                       uint32_t& b1) {
+  const __nv_bfloat16* p = base + (n0 + g) * ld + k0 + tid * 2;
+  b0 = lds32(p);
+  b1 = lds32(p + 8);
+}
+
+__device__ __forceinline__ void attn_token_map(const AttnGeom& g, int wi, int n, int& tok, int& rid) {
+  const int per = g.nwh * g.nww;
+  const int b = wi / per, rem = wi - b * per;
+  const int wy = rem / g.nww, wx = rem - wy * g.nww;
+  const int iy = n / g.ws, ix = n - iy * g.ws;
+  const int hs = wy * g.ws + iy, wsx = wx * g.ws + ix;
+  int ho = hs + g.shift, wo = wsx + g.shift;
+  if (ho >= g.H) ho -= g.H;
+  if (wo >= g.W) wo -= g.W;
+  tok = (b * g.H + ho) * g.W + wo;
+  const int rh = hs < g.H - g.ws ? 0 : (hs < g.H - g.shift ? 1 : 2);
+  const int rw = wsx < g.W - g.ws ? 0 : (wsx < g.W - g.shift ? 1 : 2);
+  rid = rh * 3 + rw;
+}
+
+// S = Qs K^T for this warp's 16 rows: acc[nt] covers columns 8nt..8nt+7
+__device__ __forceinline__ void qk_scores(const __nv_bfloat16* Ah, const __nv_bfloat16* Al, const __nv_bfloat16* Bh,
+                                          const __nv_bfloat16* Bl, int row0, int g, int tid, float (&acc)[8][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    uint32_t ah[4], al[4];
+    load_a(Ah, AM_LD, row0, kk * 16, g, tid, ah);
+    load_a(Al, AM_LD, row0, kk * 16, g, tid, al);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      uint32_t bh0, bh1, bl0, bl1;
+      load_b(Bh, AM_LD, nt * 8, kk * 16, g, tid, bh0, bh1);
+      load_b(Bl, AM_LD, nt * 8, kk * 16, g, tid, bl0, bl1);
+      mma3(acc[nt], ah, al, bh0, bh1, bl0, bl1);
+    }
+  }
+}
+
+// bias + mask + softmax on the accumulator layout (rows row0+g and row0+g+8), in place -> P
+__device__ __forceinline__ void bias_mask_softmax(const AttnGeom& gm, const float* bias_s, const int* rid, int row0,
+                                                  int g, int tid, float (&acc)[8][4]) {
+  const bool masked = gm.use_mask && gm.shift > 0;
+  const int span = 2 * gm.ws - 1;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = row0 + g + 8 * h;
+    const int iy = i / gm.ws, ix = i - iy * gm.ws;
+    const int ri = rid[i];
+    float m = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + tid * 2 + e;
+        const int jy = j / gm.ws, jx = j - jy * gm.ws;
+        float v = acc[nt][2 * h + e] + bias_s[(iy - jy + gm.ws - 1) * span + (ix - jx + gm.ws - 1)];
+        if (masked && ri != rid[j]) v += -100.0f;
+        acc[nt][2 * h + e] = v;
+        m = fmaxf(m, v);
+      }
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float s = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float ev = expf(acc[nt][2 * h + e] - m);
+        acc[nt][2 * h + e] = ev;
+        s += ev;
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      acc[nt][2 * h] *= inv;
+      acc[nt][2 * h + 1] *= inv;
+    }
+  }
+}
+
+// out[16 x 32] = X[16 x 64] (accumulator layout, as A operand) * Bt, Bt = [n = d][k = token] tiles
+__device__ __forceinline__ void acc_times(const float (&x)[8][4], const __nv_bfloat16* Bh, const __nv_bfloat16* Bl,
+                                          int g, int tid, float (&o)[4][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t ah[4], al[4];
+    split_pair(x[2 * kk][0], x[2 * kk][1], ah[0], al[0]);
+    split_pair(x[2 * kk][2], x[2 * kk][3], ah[1], al[1]);
+    split_pair(x[2 * kk + 1][0], x[2 * kk + 1][1], ah[2], al[2]);
+    split_pair(x[2 * kk + 1][2], x[2 * kk + 1][3], ah[3], al[3]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t bh0, bh1, bl0, bl1;
+      load_b(Bh, AM_LDT, nt * 8, kk * 16, g, tid, bh0, bh1);
+      load_b(Bl, AM_LDT, nt * 8, kk * 16, g, tid, bl0, bl1);
+      mma3(o[nt], ah, al, bh0, bh1, bl0, bl1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* __restrict__ qkv,
+                                                                 const float* __restrict__ table,
+                                                                 float* __restrict__ out, AttnGeom gm) {
+  __shared__ __align__(16) __nv_bfloat16 Qh[AM_N * AM_LD], Ql[AM_N * AM_LD], Kh[AM_N * AM_LD], Kl[AM_N * AM_LD];
+  __shared__ __align__(16) __nv_bfloat16 Vth[32 * AM_LDT], Vtl[32 * AM_LDT];
+  __shared__ float bias_s[225];
+  __shared__ int tok[AM_N], rid[AM_N];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
+  const int wi = blockIdx.x, head = blockIdx.y;
+  if (t < AM_N) attn_token_map(gm, wi, t, tok[t], rid[t]);
+  for (int i = t; i < (2 * gm.ws - 1) * (2 * gm.ws - 1); i += AM_THREADS) bias_s[i] = table[i * gm.heads + head];
+  // zero the d-padding (columns D..31) once
+  for (int i = t; i < AM_N * AM_LD / 2; i += AM_THREADS) {
+    reinterpret_cast<uint32_t*>(Qh)[i] = 0; reinterpret_cast<uint32_t*>(Ql)[i] = 0;
+    reinterpret_cast<uint32_t*>(Kh)[i] = 0; reinterpret_cast<uint32_t*>(Kl)[i] = 0;
+  }
+  for (int i = t; i < 32 * AM_LDT / 2; i += AM_THREADS) {
+    reinterpret_cast<uint32_t*>(Vth)[i] = 0; reinterpret_cast<uint32_t*>(Vtl)[i] = 0;
+  }
+  __syncthreads();
+  const int hp = gm.D / 2;  // float2 pairs per token
+  for (int idx = t; idx < AM_N * hp; idx += AM_THREADS) {
+    const int n = idx / hp, pr = idx - n * hp;
+    const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
+    const float2 q = *reinterpret_cast<const float2*>(p);
+    const float2 k = *reinterpret_cast<const float2*>(p + gm.C);
+    const float2 v = *reinterpret_cast<const float2*>(p + 2 * gm.C);
+    uint32_t hi, lo;
+    split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
+    *reinterpret_cast<uint32_t*>(&Qh[n * AM_LD + 2 * pr]) = hi;
+    *reinterpret_cast<uint32_t*>(&Ql[n * AM_LD + 2 * pr]) = lo;
+    split_pair(k.x, k.y, hi, lo);
+    *reinterpret_cast<uint32_t*>(&Kh[n * AM_LD + 2 * pr]) = hi;
+    *reinterpret_cast<uint32_t*>(&Kl[n * AM_LD + 2 * pr]) = lo;
+    split_pair(v.x, v.y, hi, lo);
+    reinterpret_cast<uint16_t*>(Vth)[(2 * pr) * AM_LDT + n] = (uint16_t)(hi & 0xFFFF);
+    reinterpret_cast<uint16_t*>(Vth)[(2 * pr + 1) * AM_LDT + n] = (uint16_t)(hi >> 16);
+    reinterpret_cast<uint16_t*>(Vtl)[(2 * pr) * AM_LDT + n] = (uint16_t)(lo & 0xFFFF);
+    reinterpret_cast<uint16_t*>(Vtl)[(2 * pr + 1) * AM_LDT + n] = (uint16_t)(lo >> 16);
+  }
+  __syncthreads();
+  const int row0 = warp * 16;
+  float acc[8][4];
+  qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, acc);
+  bias_mask_softmax(gm, bias_s, rid, row0, g, tid, acc);
+  float o[4][4];
+  acc_times(acc, Vth, Vtl, g, tid, o);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = row0 + g + 8 * h;
+    float* dst = out + (size_t)tok[i] * gm.C + head * gm.D;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = nt * 8 + tid * 2;
+      if (c < gm.D) *reinterpret_cast<float2*>(dst + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward
+// smem map (bf16 elements). Phase-1 tiles [token][d]; phase-2 tiles alias them.
+constexpr int BW_TILE = AM_N * AM_LD;      // 2560
+constexpr int BW_TT = 32 * AM_LDT;         // 2304   [d][token]
+constexpr int BW_PT = AM_N * AM_LDT;       // 4608   [token][token]
+constexpr int BW_PHASE1 = 8 * BW_TILE;     // Q,K,V,dO hi+lo = 20480 elements
+static_assert(4 * BW_PT <= BW_PHASE1, "Pt/dSt (hi+lo) must fit in the phase-1 region");
+constexpr size_t BW_SMEM = (size_t)(BW_PHASE1 + 6 * BW_TT) * sizeof(__nv_bfloat16);
+
+__global__ void __launch_bounds__(AM_THREADS) window_attn_bwd_mma(const float* __restrict__ qkv,
+                                                                 const float* __restrict__ table,
+                                                                 const float* __restrict__ dout,
+                                                                 float* __restrict__ dqkv,
+                                                                 float* __restrict__ partial, AttnGeom gm, int nwin) {
+  extern __shared__ __align__(16) __nv_bfloat16 sm[];
+  __nv_bfloat16* Qh = sm;                 __nv_bfloat16* Ql = Qh + BW_TILE;
+  __nv_bfloat16* Kh = Ql + BW_TILE;       __nv_bfloat16* Kl = Kh + BW_TILE;
+  __nv_bfloat16* Vh = Kl + BW_TILE;       __nv_bfloat16* Vl = Vh + BW_TILE;
+  __nv_bfloat16* Oh = Vl + BW_TILE;       __nv_bfloat16* Ol = Oh + BW_TILE;    // dO
+  __nv_bfloat16* Pth = sm;                __nv_bfloat16* Ptl = Pth + BW_PT;    // alias phase-1 region
+  __nv_bfloat16* Sth = Ptl + BW_PT;       __nv_bfloat16* Stl = Sth + BW_PT;
+  __nv_bfloat16* Qth = sm + BW_PHASE1;    __nv_bfloat16* Qtl = Qth + BW_TT;    // [d][token]
+  __nv_bfloat16* Kth = Qtl + BW_TT;       __nv_bfloat16* Ktl = Kth + BW_TT;
+  __nv_bfloat16* Oth = Ktl + BW_TT;       __nv_bfloat16* Otl = Oth + BW_TT;
+  __shared__ float bias_s[225];
+  __shared__ int tok[AM_N], rid[AM_N];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
+  const int head = blockIdx.y;
+  const int row0 = warp * 16;
+  for (int i = t; i < (2 * gm.ws - 1) * (2 * gm.ws - 1); i += AM_THREADS) bias_s[i] = table[i * gm.heads + head];
+  for (int i = t; i < 6 * BW_TT / 2; i += AM_THREADS) reinterpret_cast<uint32_t*>(Qth)[i] = 0;  // d padding rows
+  float dacc[8][4];  // sum over this CTA's windows of dS, accumulator layout (fixed (i,j) per thread)
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) dacc[nt][0] = dacc[nt][1] = dacc[nt][2] = dacc[nt][3] = 0.f;
+  const int hp = gm.D / 2;
+
+  for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
+    __syncthreads();  // previous window's phase-2 reads are done
+    if (t < AM_N) attn_token_map(gm, wi, t, tok[t], rid[t]);
+    // zero the k-padding (columns D..31) of the eight [token][d] tiles (phase 2 aliased over them)
+    for (int i = t; i < 8 * AM_N * ((32 - gm.D) / 2); i += AM_THREADS) {
+      const int per_row = (32 - gm.D) / 2;
+      const int cpair = i % per_row, rowt = i / per_row;  // rowt = tile * 64 + row
+      *reinterpret_cast<uint32_t*>(&sm[rowt * AM_LD + gm.D + 2 * cpair]) = 0;
+    }
+    __syncthreads();
+    for (int idx = t; idx < AM_N * hp; idx += AM_THREADS) {
+      const int n = idx / hp, pr = idx - n * hp;
+      const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
+      const float2 q = *reinterpret_cast<const float2*>(p);
+      const float2 k = *reinterpret_cast<const float2*>(p + gm.C);
+      const float2 v = *reinterpret_cast<const float2*>(p + 2 * gm.C);
+      const float2 dy = *reinterpret_cast<const float2*>(dout + (size_t)tok[n] * gm.C + head * gm.D + 2 * pr);
+      uint32_t hi, lo;
+      const int o1 = n * AM_LD + 2 * pr, t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
+      split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
+      *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
+      reinterpret_cast<uint16_t*>(Qth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Qth)[t1] = (uint16_t)(hi >> 16);
+      reinterpret_cast<uint16_t*>(Qtl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Qtl)[t1] = (uint16_t)(lo >> 16);
+      split_pair(k.x, k.y, hi, lo);
+      *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
+      reinterpret_cast<uint16_t*>(Kth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Kth)[t1] = (uint16_t)(hi >> 16);
+      reinterpret_cast<uint16_t*>(Ktl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ktl)[t1] = (uint16_t)(lo >> 16);
+      split_pair(v.x, v.y, hi, lo);
+      *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
+      split_pair(dy.x, dy.y, hi, lo);
+      *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
+      reinterpret_cast<uint16_t*>(Oth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Oth)[t1] = (uint16_t)(hi >> 16);
+      reinterpret_cast<uint16_t*>(Otl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Otl)[t1] = (uint16_t)(lo >> 16);
+    }
+    __syncthreads();
+    // ---- phase 1: P = softmax(Qs K^T + bias + mask); dP = dO V^T; dS = P o (dP - rowsum(P o dP))
+    float pr_[8][4], ds[8][4];
+    qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, pr_);
+    bias_mask_softmax(gm, bias_s, rid, row0, g, tid, pr_);
+    qk_scores(Oh, Ol, Vh, Vl, row0, g, tid, ds);  // dP[i][j] = sum_d dO[i][d] V[j][d]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float delta = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) delta += pr_[nt][2 * h] * ds[nt][2 * h] + pr_[nt][2 * h + 1] * ds[nt][2 * h + 1];
+      delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+      delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float v = pr_[nt][2 * h + e] * (ds[nt][2 * h + e] - delta);
+          ds[nt][2 * h + e] = v;
+          dacc[nt][2 * h + e] += v;
+        }
+      }
+    }
+    __syncthreads();  // every warp is done reading the phase-1 tiles; they become Pt / dSt
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = row0 + g + 8 * h;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + tid * 2 + e;
+          const float pv = pr_[nt][2 * h + e], sv = ds[nt][2 * h + e];
+          const __nv_bfloat16 ph = __float2bfloat16_rn(pv), sh = __float2bfloat16_rn(sv);
+          Pth[j * AM_LDT + i] = ph;
+          Ptl[j * AM_LDT + i] = __float2bfloat16_rn(pv - __bfloat162float(ph));
+          Sth[j * AM_LDT + i] = sh;
+          Stl[j * AM_LDT + i] = __float2bfloat16_rn(sv - __bfloat162float(sh));
+        }
+      }
+    }
+    // ---- phase 2a: dQ[i][d] = scale * sum_j dS[i][j] K[j][d]   (A = dS from registers, B = Kt)
+    float o[4][4];
+    acc_times(ds, Kth, Ktl, g, tid, o);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* dst = dqkv + (size_t)tok[row0 + g + 8 * h] * 3 * gm.C + head * gm.D;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = nt * 8 + tid * 2;
+        if (c < gm.D) *reinterpret_cast<float2*>(dst + c) = make_float2(o[nt][2 * h] * gm.scale, o[nt][2 * h + 1] * gm.scale);
+      }
+    }
+    __syncthreads();  // Pt / dSt complete
+    // ---- phase 2b: dK[j][d] = sum_i dS[i][j] Qs[i][d];  dV[j][d] = sum_i P[i][j] dO[i][d]   (rows j = this warp's 16)
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const __nv_bfloat16* Ah = which == 0 ? Sth : Pth;
+      const __nv_bfloat16* Al = which == 0 ? Stl : Ptl;
+      const __nv_bfloat16* Bh = which == 0 ? Qth : Oth;
+      const __nv_bfloat16* Bl = which == 0 ? Qtl : Otl;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t ah[4], al[4];
+        load_a(Ah, AM_LDT, row0, kk * 16, g, tid, ah);
+        load_a(Al, AM_LDT, row0, kk * 16, g, tid, al);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          uint32_t bh0, bh1, bl0, bl1;
+          load_b(Bh, AM_LDT, nt * 8, kk * 16, g, tid, bh0, bh1);
+          load_b(Bl, AM_LDT, nt * 8, kk * 16, g, tid, bl0, bl1);
+          mma3(o[nt], ah, al, bh0, bh1, bl0, bl1);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float* dst = dqkv + (size_t)tok[row0 + g + 8 * h] * 3 * gm.C + (which == 0 ? gm.C : 2 * gm.C) + head * gm.D;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int c = nt * 8 + tid * 2;
+          if (c < gm.D) *reinterpret_cast<float2*>(dst + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
+        }
+      }
+    }
+  }
+  // bias-table gradient partial: [blockIdx.x][head][i][j]
+  float* outp = partial + ((size_t)blockIdx.x * gm.heads + head) * AM_N * AM_N;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = row0 + g + 8 * h;
+      *reinterpret_cast<float2*>(outp + i * AM_N + nt * 8 + tid * 2) = make_float2(dacc[nt][2 * h], dacc[nt][2 * h + 1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+bool window_attn_mma_supported(int c, int heads, int ws) {
+  const int d = c / heads;
+  return ws == 8 && d <= 32 && d % 2 == 0 && (c % 2 == 0);
+}
+
+int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, int batch, int h, int w, int c,
+                               int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st) {
+  AttnGeom g{batch, h, w, c, heads, ws, shift, use_mask, c / heads, h / ws, w / ws, scale};
+  dim3 grid(batch * g.nwh * g.nww, heads);
+  window_attn_fwd_mma<<<grid, AM_THREADS, 0, st>>>(qkv, table, out, g);
+  NSR_CHECK_LAUNCH("window_attn_fwd_mma");
+  return NSR_OK;
+}
+
+int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float* dout, float* dqkv, float* partial,
+                               int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
+                               float scale, cudaStream_t st) {
+  AttnGeom g{batch, h, w, c, heads, ws, shift, use_mask, c / heads, h / ws, w / ws, scale};
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(window_attn_bwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SMEM);
+    if (e != cudaSuccess) {
+      set_error("window_attn_bwd_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return NSR_E_CUDA;
+    }
+    attr = true;
+  }
+  dim3 grid(gx, heads);
+  window_attn_bwd_mma<<<grid, AM_THREADS, BW_SMEM, st>>>(qkv, table, dout, dqkv, partial, g, batch * g.nwh * g.nww);
+  NSR_CHECK_LAUNCH("window_attn_bwd_mma");
+  return NSR_OK;
+}
+
+}  // namespace nsr

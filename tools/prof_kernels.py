@@ -1,0 +1,74 @@
+"""Launch single hot kernels at their C3 shapes (for ncu captures and micro-timing).
+
+    python tools/prof_kernels.py linear_qkv [reps]
+"""
+import math
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from neosr_b200 import ops  # noqa: E402
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "linear_qkv"
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    B, H, W, C = 32, 64, 64, 180
+    if what.startswith("linear_") or what.startswith("wgrad_") or what.startswith("dgrad_"):
+        kind, name = what.split("_", 1)
+        cin, cout, k, extra = {"qkv": (180, 540, 1, {}), "proj": (180, 180, 1, {"res": 1}),
+                               "fc1": (180, 360, 1, {"gelu": 1}), "fc2": (360, 180, 1, {"res": 1}),
+                               "conv": (180, 180, 3, {"res": 1})}[name]
+        x = rnd(B, H, W, cin, seed=1)
+        w = rnd(cout, cin, k, k, seed=2, scale=1 / math.sqrt(cin * k * k))
+        b = rnd(cout, seed=3, scale=0.1)
+        res = rnd(B, H, W, cout, seed=4)
+        pw = ops.PackedWeight(w).refresh()
+        dy = rnd(B, H, W, cout, seed=5)
+        dw, db = torch.empty_like(w), torch.empty_like(b)
+
+        def run():
+            if kind == "linear":
+                if extra.get("gelu"):
+                    ops.conv_fprop(x, pw, b, act="gelu", want_pre=True)
+                else:
+                    ops.conv_fprop(x, pw, b, residual=res if extra.get("res") else None)
+            elif kind == "dgrad":
+                ops.conv_fprop(dy, pw, None, dgrad=True, actgrad="gelu" if name == "fc2" else "none",
+                               aux=x if name == "fc2" else None)
+            else:
+                ops.conv_wgrad(x, dy, dw, db, k, k)
+    elif what.startswith("attn"):
+        qkv = rnd(B, H, W, 3 * C, seed=1)
+        table = rnd(225, 6, seed=2, scale=0.5)
+        dout = rnd(B, H, W, C, seed=3)
+        dtable = torch.empty_like(table)
+
+        def run():
+            if what == "attn_fwd":
+                ops.window_attn_fwd(qkv, table, 6, 8, 4, 30 ** -0.5)
+            else:
+                ops.window_attn_bwd(qkv, table, dout, dtable, 6, 8, 4, 30 ** -0.5)
+    else:
+        raise SystemExit(f"unknown kernel {what}")
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{what}: {e0.elapsed_time(e1) / reps:.4f} ms per call over {reps} reps")
+
+
+if __name__ == "__main__":
+    main()
