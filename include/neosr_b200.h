@@ -85,10 +85,29 @@ typedef struct NsrConv {
   const float* row_scale;
   const float* residual;
   float* y_pre;
-  float* y;
+  float* y;              /* may be NULL when y_sti is given */
+  /* Split-tile-image (STI) operands, see nsr_sti_bytes(): x_sti replaces x as the A operand of a
+   * 1x1 contraction (bulk-copied, no conversion in the kernel); y_sti receives the final output
+   * value pre-split to bf16 hi/lo in the layout the next contraction bulk-copies. */
+  const void* x_sti;
+  void* y_sti;
 } NsrConv;
 
 int nsr_conv_fprop(const NsrConv* d, void* stream);
+
+/*
+ * Split tile image (STI) of a token tensor [rows, c] (fp32 semantics): the tensor is stored as
+ * bf16 hi + bf16 lo (x ~= hi + lo, the 3xBF16 operand split) in 128-row x 64-channel blocks,
+ * each block = 16 KiB hi image + 16 KiB lo image, a row = 128 bytes, 16-byte chunk `ch` of row
+ * `r` stored at chunk position ch ^ (r & 7) (the SWIZZLE_128B pattern tcgen05 reads).  Block
+ * (mt, kb) lives at ((mt * ceil(c/64)) + kb) * 32 KiB.  Same bytes as fp32; a contraction
+ * bulk-copies blocks straight into shared memory (fprop/dgrad: K-major A tile; wgrad: MN-major
+ * panels).  Rows >= `rows` and channels >= `c` must read as zero.
+ */
+size_t nsr_sti_bytes(long long rows, int c);
+/* fp32 [rows, c] (row stride ld) -> STI (utility / tests; producers normally emit STI directly) */
+int nsr_sti_from_f32(const float* x, int ld, long long rows, int c, void* sti, void* stream);
+int nsr_sti_to_f32(const void* sti, long long rows, int c, float* y, int ld, void* stream);
 
 /* Packed-weight buffers. `flavour` 0 = fprop  (w[co][r][s][ci]),
  *                         1 = dgrad  (w'[ci][kh-1-r][kw-1-s][co], i.e. the transposed,
@@ -119,6 +138,8 @@ typedef struct NsrWgrad {
   float* dbias;  /* [cout] or NULL, overwritten */
   void* workspace;
   size_t workspace_bytes;
+  const void* x_sti;   /* optional STI copies of x / dy (1x1 only): operands arrive by bulk copy */
+  const void* dy_sti;
 } NsrWgrad;
 
 size_t nsr_conv_wgrad_workspace(const NsrWgrad* d);
@@ -157,13 +178,14 @@ int nsr_actgrad_mul(const float* dy, const float* aux, const float* dextra, floa
 /* ------------------------------------------------------------------ LayerNorm ---------- */
 /* nn.LayerNorm(c, eps) over the last dim of [rows, c] (swinir_arch.py:284,297,708,960). */
 int nsr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
-                      float* mean, float* rstd, int rows, int c, float eps, void* stream);
+                      float* mean, float* rstd, int rows, int c, float eps, void* y_sti, void* stream);
+/* y (fp32) and y_sti (split tile image, see nsr_sti_bytes) are both optional outputs. */
 /* dx = LN'(dy) + (dres ? dres : 0); dgamma/dbeta reduced deterministically via workspace
  * (>= nsr_layernorm_bwd_workspace(c) bytes). */
 size_t nsr_layernorm_bwd_workspace(int c);
 int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
                       const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
-                      int rows, int c, void* workspace, size_t workspace_bytes, void* stream);
+                      int rows, int c, void* workspace, size_t workspace_bytes, void* dx_sti, void* stream);
 
 /* ------------------------------------------------------------------ window attention --- */
 /*
@@ -178,12 +200,13 @@ int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
  */
 int nsr_window_attn_fwd(const float* qkv, const float* bias_table, float* out, int batch, int h,
                         int w, int c, int heads, int ws, int shift, int use_mask, float scale,
-                        void* stream);
+                        void* out_sti, void* stream);
+/* out (fp32) may be NULL when out_sti is given; likewise dqkv / dqkv_sti below. */
 size_t nsr_window_attn_bwd_workspace(int heads, int ws);
 int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv,
                         float* dbias_table, int batch, int h, int w, int c, int heads, int ws,
                         int shift, int use_mask, float scale, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        size_t workspace_bytes, void* dqkv_sti, void* stream);
 
 /* ------------------------------------------------------------------ losses ------------- */
 /* All loss kernels ADD weight*loss into *loss_accum (device scalar) and write d(loss)/d(pred)

@@ -29,7 +29,7 @@ class NsrConv(C.Structure):
         ("engine", C.c_int32),
         ("x", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("prelu", C.c_void_p),
         ("aux", C.c_void_p), ("row_scale", C.c_void_p), ("residual", C.c_void_p),
-        ("y_pre", C.c_void_p), ("y", C.c_void_p),
+        ("y_pre", C.c_void_p), ("y", C.c_void_p), ("x_sti", C.c_void_p), ("y_sti", C.c_void_p),
     ]
 
 
@@ -40,7 +40,7 @@ class NsrWgrad(C.Structure):
         ("kh", C.c_int32), ("kw", C.c_int32), ("pad", C.c_int32),
         ("x_ld", C.c_int32), ("dy_ld", C.c_int32), ("engine", C.c_int32),
         ("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p), ("dbias", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("x_sti", C.c_void_p), ("dy_sti", C.c_void_p),
     ]
 
 
@@ -86,12 +86,15 @@ SIGNATURES = {
     "nsr_maxpool2_relu_bwd_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "nsr_axpby": (_i, [_p, _f, _p, _f, _p, _z, _p]),
     "nsr_actgrad_mul": (_i, [_p, _p, _p, _p, _z, _i, _f, _p]),
-    "nsr_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _f, _p]),
+    "nsr_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _p]),
+    "nsr_sti_bytes": (_z, [C.c_longlong, _i]),
+    "nsr_sti_from_f32": (_i, [_p, _i, C.c_longlong, _i, _p, _p]),
+    "nsr_sti_to_f32": (_i, [_p, C.c_longlong, _i, _p, _i, _p]),
     "nsr_layernorm_bwd_workspace": (_z, [_i]),
-    "nsr_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _z, _p]),
-    "nsr_window_attn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "nsr_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _z, _p, _p]),
+    "nsr_window_attn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p]),
     "nsr_window_attn_bwd_workspace": (_z, [_i, _i]),
-    "nsr_window_attn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _z, _p]),
+    "nsr_window_attn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _z, _p, _p]),
     "nsr_loss_workspace": (_z, []),
     "nsr_l1_loss": (_i, [_p, _p, _p, _z, _f, _p, _p, _p, _p]),
     "nsr_charbonnier_loss": (_i, [_p, _p, _p, _z, _f, _f, _f, _f, _p, _p, _p, _p]),

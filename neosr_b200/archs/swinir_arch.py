@@ -220,6 +220,7 @@ class swinir(nn.Module):
         k = self._consts(x.device)
         S: dict = {"shape": (B, H, W)} if save else None
         drops = self._drop_scales(B, x.device)
+        sti = ops.sti_enabled()  # GEMM operands as split tile images (bulk-copied, no conversion warps)
 
         def lin(name, t, **kw):
             return ops.conv_fprop(t, ps.pw(name + ".weight"), ps.p(name + ".bias") if ps.has(name + ".bias") else None, **kw)
@@ -243,13 +244,15 @@ class swinir(nn.Module):
                 pre = f"layers.{li}.residual_group.blocks.{bi}."
                 ds = drops[bi_glob]
                 bi_glob += 1
-                ln1, mu1, rs1 = ops.layernorm_fwd(t, ps.p(pre + "norm1.weight"), ps.p(pre + "norm1.bias"))
+                ln1, mu1, rs1 = ops.layernorm_fwd(t, ps.p(pre + "norm1.weight"), ps.p(pre + "norm1.bias"),
+                                                  sti_out=sti, f32_out=not sti)
                 qkv = lin(pre + "attn.qkv", ln1)
                 att = ops.window_attn_fwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), heads, ws,
-                                          blk.shift_size, scale)
+                                          blk.shift_size, scale, sti_out=sti)
                 x1 = lin(pre + "attn.proj", att, residual=t, row_scale=ds[0] if ds else None)
-                ln2, mu2, rs2 = ops.layernorm_fwd(x1, ps.p(pre + "norm2.weight"), ps.p(pre + "norm2.bias"))
-                a, hpre = lin(pre + "mlp.fc1", ln2, act="gelu", want_pre=True)
+                ln2, mu2, rs2 = ops.layernorm_fwd(x1, ps.p(pre + "norm2.weight"), ps.p(pre + "norm2.bias"),
+                                                  sti_out=sti, f32_out=not sti)
+                a, hpre = lin(pre + "mlp.fc1", ln2, act="gelu", want_pre=True, sti_out=sti, f32_out=not sti)
                 x2 = lin(pre + "mlp.fc2", a, residual=x1, row_scale=ds[1] if ds else None)
                 if save:
                     S["blocks"].append((t, mu1, rs1, ln1, qkv, att, x1, mu2, rs2, ln2, hpre, a, ds))
@@ -290,20 +293,37 @@ class swinir(nn.Module):
         k = self._consts(dy.device)
         ws = self.window_size
 
+        sti = ops.sti_enabled() and bool(S["blocks"]) and isinstance(S["blocks"][0][3], ops.STI)
+
+        def split(v):  # (fp32, STI) pair or a single tensor -> (fp32 | None, STI | None)
+            if isinstance(v, tuple):
+                return v
+            return (None, v) if isinstance(v, ops.STI) else (v, None)
+
         def bwd(name, x_in, g, need_dx=True, **epi):
+            """wgrad (+ bias grad) of layer `name`, then dgrad.  x_in / g may be fp32 tensors, STIs or
+            (fp32, STI) pairs; STI copies feed the tcgen05 bulk-copy kernels when both exist."""
             w = ps.p(name + ".weight")
             kh = w.shape[2] if w.dim() == 4 else 1
             has_b = ps.has(name + ".bias")
-            ops.conv_wgrad(x_in, g, ps.g(name + ".weight"), ps.g(name + ".bias") if has_b else None, kh, kh)
+            xf, xs = split(x_in)
+            gf, gs = split(g)
+            use_sti = kh == 1 and xs is not None and gs is not None
+            ops.conv_wgrad(None if use_sti else xf, gf if (gf is not None and (has_b or not use_sti)) else None,
+                           ps.g(name + ".weight"), ps.g(name + ".bias") if has_b else None, kh, kh,
+                           x_sti=xs if use_sti else None, dy_sti=gs if use_sti else None)
             if need_dx:
-                return ops.conv_fprop(g, ps.pw(name + ".weight"), None, dgrad=True, **epi)
+                src = gs if (kh == 1 and gs is not None) else gf
+                return ops.conv_fprop(src, ps.pw(name + ".weight"), None, dgrad=True, **epi)
             return None
 
         def scaled(g, s):  # DropPath: branch gradient = s[b] * g
             if s is None:
                 return g
-            B = g.shape[0]
-            return (g.view(B, -1) * s.view(B, 1)).view_as(g).contiguous()
+            gf, _ = split(g)
+            B = gf.shape[0]
+            gf = (gf.view(B, -1) * s.view(B, 1)).view_as(gf).contiguous()
+            return (gf, ops.STI.from_f32(gf)) if sti else gf
 
         g = ops.nchw_to_nhwc_affine(dy.contiguous().float(), k["out_scale"], None)
         if self.upsampler == "pixelshuffle":
@@ -331,26 +351,30 @@ class swinir(nn.Module):
             heads = self.num_heads[li]
             scale = self.qk_scale or (self.embed_dim // heads) ** -0.5
             dinp = g
-            g = bwd(f"layers.{li}.conv", S["layers"][li], g)
+            # grad w.r.t. the last block's output: fp32 for the LayerNorm backward, STI for fc2's dgrad/wgrad
+            g = bwd(f"layers.{li}.conv", S["layers"][li], g, sti_out=sti)
             depth = len(self.layers[li].residual_group.blocks)
             for bi in reversed(range(depth)):
                 bi_glob -= 1
                 pre = f"layers.{li}.residual_group.blocks.{bi}."
                 t0, mu1, rs1, ln1, qkv, att, x1, mu2, rs2, ln2, hpre, a, ds = S["blocks"][bi_glob]
                 shift = self.layers[li].residual_group.blocks[bi].shift_size
+                gf = split(g)[0]
                 gb = scaled(g, ds[1] if ds else None)
-                dh = bwd(pre + "mlp.fc2", a, gb, actgrad="gelu", aux=hpre)
+                dh = bwd(pre + "mlp.fc2", a, gb, actgrad="gelu", aux=hpre, sti_out=sti, f32_out=not sti)
                 dln2 = bwd(pre + "mlp.fc1", ln2, dh)
                 g1 = ops.layernorm_bwd(dln2, x1, ps.p(pre + "norm2.weight"), mu2, rs2, ps.g(pre + "norm2.weight"),
-                                       ps.g(pre + "norm2.bias"), dres=g)
+                                       ps.g(pre + "norm2.bias"), dres=gf, sti_out=sti)
+                g1f = split(g1)[0]
                 gb = scaled(g1, ds[0] if ds else None)
                 datt = bwd(pre + "attn.proj", att, gb)
                 dqkv = ops.window_attn_bwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
-                                           ps.g(pre + "attn.relative_position_bias_table"), heads, ws, shift, scale)
+                                           ps.g(pre + "attn.relative_position_bias_table"), heads, ws, shift, scale,
+                                           sti_out=sti)
                 dln1 = bwd(pre + "attn.qkv", ln1, dqkv)
                 g = ops.layernorm_bwd(dln1, t0, ps.p(pre + "norm1.weight"), mu1, rs1, ps.g(pre + "norm1.weight"),
-                                      ps.g(pre + "norm1.bias"), dres=g1)
-            g = ops.axpby(g, 1.0, dinp, 1.0)
+                                      ps.g(pre + "norm1.bias"), dres=g1f, sti_out=sti and bi > 0)
+            g = ops.axpby(split(g)[0], 1.0, dinp, 1.0)
         if self.patch_norm:
             mu, rs = S["pe"]
             g = ops.layernorm_bwd(g, S["f0"], ps.p("patch_embed.norm.weight"), mu, rs,

@@ -73,9 +73,74 @@ __global__ void pack_weight_bf16(const float* __restrict__ wf32, uint8_t* __rest
   }
 }
 
+// ---- split tile image <-> fp32 (utility; producers emit STI directly on the hot path) -------
+__global__ void sti_from_f32_kernel(const float* __restrict__ x, int ld, long long rows, int c, uint8_t* __restrict__ sti) {
+  const int kbs = (c + 63) / 64;
+  const long long mts = (rows + 127) / 128;
+  const long long total = mts * 128 * kbs * 8;  // one thread per (row, 16-byte chunk)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % (kbs * 8));
+    const long long p = i / (kbs * 8);
+    const int c0 = ch * 8;
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+      if (p < rows && c0 + e < c) v = x[p * ld + c0 + e];
+      hi[e] = __float2bfloat16_rn(v);
+      lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
+    }
+    const long long mt = p >> 7;
+    const int r = (int)(p & 127), kb = ch >> 3, cc = ch & 7;
+    uint8_t* dst = sti + ((size_t)(mt * kbs + kb) << 15) + r * 128 + ((cc ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+__global__ void sti_to_f32_kernel(const uint8_t* __restrict__ sti, long long rows, int c, float* __restrict__ y, int ld) {
+  const int kbs = (c + 63) / 64;
+  const long long total = rows * kbs * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % (kbs * 8));
+    const long long p = i / (kbs * 8);
+    const long long mt = p >> 7;
+    const int r = (int)(p & 127), kb = ch >> 3, cc = ch & 7;
+    const uint8_t* src = sti + ((size_t)(mt * kbs + kb) << 15) + r * 128 + ((cc ^ (r & 7)) << 4);
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(src);
+    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(src + 16384);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (ch * 8 + e < c) y[p * ld + ch * 8 + e] = __bfloat162float(hi[e]) + __bfloat162float(lo[e]);
+  }
+}
+
 }  // namespace nsr
 
 using namespace nsr;
+
+extern "C" size_t nsr_sti_bytes(long long rows, int c) {
+  if (rows <= 0 || c <= 0) return 0;
+  return (size_t)((rows + 127) / 128) * (size_t)((c + 63) / 64) * 32768;
+}
+extern "C" int nsr_sti_from_f32(const float* x, int ld, long long rows, int c, void* sti, void* stream) {
+  NSR_CHECK_ARG(x && sti && rows > 0 && c > 0 && ld >= c, "nsr_sti_from_f32: bad arguments");
+  const long long total = ((rows + 127) / 128) * 128 * ((c + 63) / 64) * 8;
+  int blocks = ceil_div(total, 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  sti_from_f32_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ld, rows, c, reinterpret_cast<uint8_t*>(sti));
+  NSR_CHECK_LAUNCH("sti_from_f32");
+  return NSR_OK;
+}
+extern "C" int nsr_sti_to_f32(const void* sti, long long rows, int c, float* y, int ld, void* stream) {
+  NSR_CHECK_ARG(y && sti && rows > 0 && c > 0 && ld >= c, "nsr_sti_to_f32: bad arguments");
+  const long long total = rows * ((c + 63) / 64) * 8;
+  int blocks = ceil_div(total, 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  sti_to_f32_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint8_t*>(sti), rows, c, y, ld);
+  NSR_CHECK_LAUNCH("sti_to_f32");
+  return NSR_OK;
+}
 
 extern "C" size_t nsr_packed_weight_bytes(int cout, int cin, int kh, int kw, int flavour) {
   PackedGeom g = packed_geom(cout, cin, kh, kw, flavour);
@@ -110,7 +175,7 @@ static int check_conv(const NsrConv* d) {
   NSR_CHECK_ARG(d->kh > 0 && d->kw > 0 && d->kh == 2 * d->pad + 1 && d->kw == 2 * d->pad + 1,
                 "nsr_conv_fprop: only stride-1 'same' convolutions (k = 2*pad+1) are supported");
   NSR_CHECK_ARG(d->x_ld >= d->cin && d->y_ld >= d->cout, "nsr_conv_fprop: leading dims too small");
-  NSR_CHECK_ARG(d->x && d->w_packed && d->y, "nsr_conv_fprop: null x / w / y");
+  NSR_CHECK_ARG((d->x || d->x_sti) && d->w_packed && (d->y || d->y_sti), "nsr_conv_fprop: null x / w / y");
   NSR_CHECK_ARG(!(d->actgrad) || d->aux, "nsr_conv_fprop: actgrad needs aux");
   NSR_CHECK_ARG(!(d->act == NSR_ACT_PRELU || d->actgrad == NSR_ACT_PRELU) || d->prelu, "nsr_conv_fprop: prelu slopes missing");
   NSR_CHECK_ARG(d->act >= 0 && d->act <= NSR_ACT_PRELU && d->actgrad >= 0 && d->actgrad <= NSR_ACT_PRELU,
@@ -129,6 +194,7 @@ extern "C" int nsr_conv_fprop(const NsrConv* d, void* stream) {
     return conv_fprop_tc(*d, st);
   }
   if (eng == NSR_ENGINE_AUTO && conv_fprop_tc_supported(*d)) return conv_fprop_tc(*d, st);
+  NSR_CHECK_ARG(d->x && d->y && !d->y_sti, "nsr_conv_fprop: split-tile-image operands need the tcgen05 engine");
   return conv_fprop_simt(*d, st);
 }
 
@@ -137,7 +203,7 @@ static int check_wgrad(const NsrWgrad* d) {
   NSR_CHECK_ARG(d->batch > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "nsr_conv_wgrad: bad geometry");
   NSR_CHECK_ARG(d->kh == 2 * d->pad + 1 && d->kw == 2 * d->pad + 1, "nsr_conv_wgrad: only stride-1 'same' convolutions");
   NSR_CHECK_ARG(d->x_ld >= d->cin && d->dy_ld >= d->cout, "nsr_conv_wgrad: leading dims too small");
-  NSR_CHECK_ARG(d->x && d->dy && d->dw, "nsr_conv_wgrad: null x / dy / dw");
+  NSR_CHECK_ARG(((d->x && d->dy) || (d->x_sti && d->dy_sti)) && d->dw, "nsr_conv_wgrad: null x / dy / dw");
   return NSR_OK;
 }
 
@@ -163,5 +229,6 @@ extern "C" int nsr_conv_wgrad(const NsrWgrad* d, void* stream) {
   if (eng == NSR_ENGINE_TCGEN05)
     NSR_CHECK_ARG(conv_wgrad_tc_supported(*d), "nsr_conv_wgrad: shape not supported by the tcgen05 engine");
   if (wgrad_use_tc(d)) return conv_wgrad_tc(*d, st);
+  NSR_CHECK_ARG(d->x && d->dy, "nsr_conv_wgrad: split-tile-image operands need the tcgen05 engine");
   return conv_wgrad_simt(*d, st);
 }

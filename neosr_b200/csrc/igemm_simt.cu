@@ -314,6 +314,42 @@ __global__ void __launch_bounds__(256) colsum_partial(const float* __restrict__ 
     if (c + 3 < cout) out[3] = s.w;
   }
 }
+// same reduction when dy only exists as a split tile image: thread = (16-byte chunk, row lane)
+__global__ void __launch_bounds__(256) colsum_sti_partial(const uint8_t* __restrict__ sti, float* __restrict__ partial,
+                                                          long long M, int cout) {
+  __shared__ float red[32][65];
+  const int kbs = (cout + 63) / 64;
+  const int kb = blockIdx.x;
+  const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const long long rows_per = ((M + gridDim.y - 1) / gridDim.y + 127) / 128 * 128;
+  const long long r0 = (long long)blockIdx.y * rows_per;
+  long long r1 = r0 + rows_per;
+  if (r1 > M) r1 = M;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long p = r0 + rl; p < r1; p += 32) {
+    const int r = (int)(p & 127);
+    const uint8_t* src = sti + ((size_t)((p >> 7) * kbs + kb) << 15) + r * 128 + ((cl ^ (r & 7)) << 4);
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(src + 16384));
+    const uint32_t hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[2 * e] += __uint_as_float(hv[e] << 16) + __uint_as_float(lv[e] << 16);
+      acc[2 * e + 1] += __uint_as_float(hv[e] & 0xFFFF0000u) + __uint_as_float(lv[e] & 0xFFFF0000u);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][cl * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float sum = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) sum += red[k][threadIdx.x];
+    const int c = kb * 64 + threadIdx.x;
+    if (c < cout) partial[(size_t)blockIdx.y * cout + c] = sum;
+  }
+}
+
 __global__ void colsum_final(const float* __restrict__ partial, float* __restrict__ out, int blocks, int cout) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cout) return;
@@ -338,10 +374,17 @@ size_t conv_wgrad_workspace_simt(const NsrWgrad& d) {
 
 int conv_bias_grad(const NsrWgrad& d, float* bias_partial, int bias_blocks, cudaStream_t st) {
   const long long M = (long long)d.batch * d.h * d.w;
-  const int vec = (d.dy_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.dy) & 15) == 0);
-  dim3 grid((unsigned)ceil_div(d.cout, 256), (unsigned)bias_blocks), block(64, 4);
-  colsum_partial<<<grid, block, 0, st>>>(d.dy, bias_partial, M, d.cout, d.dy_ld, vec);
-  NSR_CHECK_LAUNCH("colsum_partial");
+  if (d.dy == nullptr) {  // only the split tile image of dy exists
+    if (bias_blocks > (int)((M + 127) / 128)) bias_blocks = (int)((M + 127) / 128);
+    dim3 grid((unsigned)((d.cout + 63) / 64), (unsigned)bias_blocks);
+    colsum_sti_partial<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(d.dy_sti), bias_partial, M, d.cout);
+    NSR_CHECK_LAUNCH("colsum_sti_partial");
+  } else {
+    const int vec = (d.dy_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.dy) & 15) == 0);
+    dim3 grid((unsigned)ceil_div(d.cout, 256), (unsigned)bias_blocks), block(64, 4);
+    colsum_partial<<<grid, block, 0, st>>>(d.dy, bias_partial, M, d.cout, d.dy_ld, vec);
+    NSR_CHECK_LAUNCH("colsum_partial");
+  }
   colsum_final<<<ceil_div(d.cout, 128), 128, 0, st>>>(bias_partial, d.dbias, bias_blocks, d.cout);
   NSR_CHECK_LAUNCH("colsum_final");
   return NSR_OK;

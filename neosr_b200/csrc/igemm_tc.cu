@@ -17,7 +17,7 @@
 //   warps 10-13 epilogue   : tcgen05.ld TMEM -> registers, bias/activation/act-grad/row-scale/
 //                            residual, fp32 stores.  TMEM is double-buffered (2 x BN columns) so
 //                            the epilogue of tile i overlaps the main loop of tile i+1.
-#include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace nsr {
 using namespace tc;
@@ -27,15 +27,18 @@ constexpr int TC_BK = 64;           // bf16 elements per k-block (one 128-byte s
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_PROD_WARPS + 2 + 4) * 32;  // 448
 constexpr int TC_A_BYTES = TC_BM * 128;                   // one half (hi or lo) of an A stage
-constexpr int EPI_LD = 36;                                // padded row stride (floats) of the epilogue staging tile
 
-template <int BN>
+// STI = the A operand arrives as a split tile image (bulk copy, no conversion warps); the eight
+// producer warps then serve as extra epilogue warps (12 instead of 4).
+template <int BN, bool STI>
 struct TcCfg {
   static constexpr int b_bytes = BN * 128;  // one half of a B stage
   static constexpr int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
-  static constexpr int stages = (200 * 1024) / stage_bytes > 4 ? 4 : (200 * 1024) / stage_bytes;
-  static constexpr int smem_bytes = stages * stage_bytes + 1024 /* align slack */ + 256 /* barriers */ +
-                                    4 * 32 * EPI_LD * 4 /* epilogue transpose staging */;
+  static constexpr int epi_warps = STI ? 12 : 4;
+  static constexpr int epi_bytes = epi_warps * 32 * EPI_LD * 4;  // per-warp transpose tiles
+  static constexpr int budget = 227 * 1024 - 1024 - 256 - epi_bytes;
+  static constexpr int stages = budget / stage_bytes > 4 ? 4 : budget / stage_bytes;
+  static constexpr int smem_bytes = stages * stage_bytes + 1024 /* align slack */ + 256 /* barriers */ + epi_bytes;
 };
 
 struct TcGeom {
@@ -43,9 +46,9 @@ struct TcGeom {
   long long M;
 };
 
-template <int BN>
+template <int BN, bool STI>
 __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeom g, const uint8_t* __restrict__ wimg) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, STI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::stages * Cfg::stage_bytes);
@@ -58,12 +61,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::stages; ++s) {
-      mbar_init(&full[s], TC_PROD_WARPS * 32 + 1);
+      mbar_init(&full[s], STI ? 1 : TC_PROD_WARPS * 32 + 1);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 128);
+      mbar_init(&tempty[b], Cfg::epi_warps * 32);
     }
     fence_mbar_init();
   }
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int hw = d.h * d.w;
-  if (warp < TC_PROD_WARPS) {
+  if (!STI && warp < TC_PROD_WARPS) {
     // ================================ A producers =========================================
     // Software pipelined over the flattened (tile, k-block) sequence: the loads of step i+1 are in
     // flight (8 x LDG.128 per thread = one whole A k-block per CTA) while step i is split to
@@ -160,13 +163,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
         int rows = g.n_pad64 - n0;
         if (rows > BN) rows = BN;
         const uint32_t bytes = (uint32_t)rows * 128;
+        const size_t mt = (size_t)(tile / g.n_tiles);
         for (int kb = 0; kb < g.nk; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* b_hi = smem + stage * Cfg::stage_bytes + 2 * TC_A_BYTES;
           uint8_t* b_lo = b_hi + Cfg::b_bytes;
           const uint8_t* src_hi = wimg + ((size_t)(kb * 2 + 0) * nblk + (n0 >> 6)) * 8192;
           const uint8_t* src_lo = wimg + ((size_t)(kb * 2 + 1) * nblk + (n0 >> 6)) * 8192;
-          mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+          mbar_arrive_expect_tx(&full[stage], 2 * bytes + (STI ? 2 * TC_A_BYTES : 0));
+          if (STI)  // A tile = one 32 KiB block (hi image + lo image) of the split tile image
+            bulk_g2s(smem + stage * Cfg::stage_bytes,
+                     reinterpret_cast<const uint8_t*>(d.x_sti) + ((mt * g.nk + kb) << 15), 2 * TC_A_BYTES, &full[stage]);
           bulk_g2s(b_hi, src_hi, bytes, &full[stage]);
           bulk_g2s(b_lo, src_lo, bytes, &full[stage]);
           if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
@@ -207,14 +214,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
         umma_commit(&tfull[buf]);      // accumulator complete
       }
     }
-  } else {
+  } else if (warp >= TC_PROD_WARPS + 2 || (STI && warp < TC_PROD_WARPS)) {
     // ================================ epilogue ============================================
     // TMEM hands each thread one accumulator ROW (32 consecutive columns).  A per-warp smem
     // transpose turns that into row-contiguous global traffic: every warp instruction reads
     // (aux / residual) or writes (y, y_pre) 4 rows x 128 contiguous bytes.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem + Cfg::stages * Cfg::stage_bytes + 256) + q * (32 * EPI_LD);
-    const int er = lane >> 3, ec = (lane & 7) * 4;   // (row-in-group, column) of this lane's float4
+    constexpr int NSLOT = STI ? 3 : 1;                                   // warps sharing a lane quarter
+    const int slot = STI ? (warp < TC_PROD_WARPS ? (warp >> 2) : 2) : 0;  // they interleave 32-col chunks
+    float* stg = reinterpret_cast<float*>(smem + Cfg::stages * Cfg::stage_bytes + 256) + (slot * 4 + q) * (32 * EPI_LD);
+    const int kbs_out = d.y_sti ? (d.cout + 63) / 64 : 0;
+    const int ncols = kbs_out ? kbs_out * 64 : d.cout;
     int local = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
@@ -224,65 +234,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= d.cout) break;  // warp-uniform
-        float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        const int n = n0 + c0 + ec;
-        const bool ncol = n < d.cout;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
-        if (ncol && d.bias) b4 = __ldg(reinterpret_cast<const float4*>(d.bias + n));
-        if (ncol && d.prelu) s4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
-        float4 aux4[8], res4[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long p = p0 + i * 4 + er;
-          const bool ok = ncol && p < g.M;
-          const long long o = p * d.y_ld + n;
-          aux4[i] = (ok && d.actgrad) ? *reinterpret_cast<const float4*>(d.aux + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-          res4[i] = (ok && d.residual) ? *reinterpret_cast<const float4*>(d.residual + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long p = p0 + i * 4 + er;
-          if (!(ncol && p < g.M)) continue;
-          const long long o = p * d.y_ld + n;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + (i * 4 + er) * EPI_LD + ec);
-          float ov[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
-          if (d.y_pre) *reinterpret_cast<float4*>(d.y_pre + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-          if (d.act) {
-            if (d.act == NSR_ACT_PRELU) {
-              ov[0] = apply_act_fast(ov[0], d.act, s4.x); ov[1] = apply_act_fast(ov[1], d.act, s4.y);
-              ov[2] = apply_act_fast(ov[2], d.act, s4.z); ov[3] = apply_act_fast(ov[3], d.act, s4.w);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ov[e] = apply_act_fast(ov[e], d.act, d.act_slope);
-            }
-          }
-          if (d.actgrad) {
-            if (d.actgrad == NSR_ACT_PRELU) {
-              ov[0] *= act_grad_fast(aux4[i].x, d.actgrad, s4.x); ov[1] *= act_grad_fast(aux4[i].y, d.actgrad, s4.y);
-              ov[2] *= act_grad_fast(aux4[i].z, d.actgrad, s4.z); ov[3] *= act_grad_fast(aux4[i].w, d.actgrad, s4.w);
-            } else {
-              ov[0] *= act_grad_fast(aux4[i].x, d.actgrad, d.actgrad_slope);
-              ov[1] *= act_grad_fast(aux4[i].y, d.actgrad, d.actgrad_slope);
-              ov[2] *= act_grad_fast(aux4[i].z, d.actgrad, d.actgrad_slope);
-              ov[3] *= act_grad_fast(aux4[i].w, d.actgrad, d.actgrad_slope);
-            }
-          }
-          if (d.row_scale) {
-            const float rs = d.row_scale[p / hw];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) ov[e] *= rs;
-          }
-          if (d.residual) { ov[0] += res4[i].x; ov[1] += res4[i].y; ov[2] += res4[i].z; ov[3] += res4[i].w; }
-          *reinterpret_cast<float4*>(d.y + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        }
+      for (int c0 = slot * 32; c0 < BN; c0 += 32 * NSLOT) {
+        if (n0 + c0 >= ncols) break;  // warp-uniform
+        epi_chunk(d, stg, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, p0, n0 + c0, g.M, hw, lane, kbs_out);
       }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
@@ -319,18 +273,25 @@ bool conv_fprop_tc_supported(const NsrConv& d) {
   if (!ok_dev) return false;
   if (d.cin % 4 || d.x_ld % 4 || d.cout % 4 || d.y_ld % 4) return false;
   if (d.cin < 16 || d.cout < 16) return false;  // image-side 3-channel convs stay on the SIMT engine
-  if (!aligned16(d.x) || !aligned16(d.y) || !aligned16(d.bias) || !aligned16(d.aux) || !aligned16(d.residual) ||
+  if (d.x_sti != nullptr) {
+    if (d.kh != 1 || d.kw != 1) return false;  // tile images carry no halo: 1x1 contractions only
+    if (!aligned16(d.x_sti)) return false;
+  } else if (d.x == nullptr) {
+    return false;
+  }
+  if (d.y == nullptr && d.y_sti == nullptr) return false;
+  if (!aligned16(d.x) || !aligned16(d.y) || !aligned16(d.y_sti) || !aligned16(d.bias) || !aligned16(d.aux) || !aligned16(d.residual) ||
       !aligned16(d.y_pre) || !aligned16(d.prelu) || !aligned16(d.w_packed))
     return false;
   return true;
 }
 
-template <int BN>
+template <int BN, bool STI>
 static int launch_fprop_tc(const NsrConv& d, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, STI>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_tc<BN, STI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes);
     if (e != cudaSuccess) {
       set_error("igemm_fprop_tc<%d>: cudaFuncSetAttribute(%d): %s", BN, Cfg::smem_bytes, cudaGetErrorString(e));
       return NSR_E_CUDA;
@@ -349,17 +310,26 @@ static int launch_fprop_tc(const NsrConv& d, cudaStream_t st) {
   g.n_pad64 = pg.n_pad64;
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + pg.f32_bytes;
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  igemm_fprop_tc<BN><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, g, wimg);
+  igemm_fprop_tc<BN, STI><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, g, wimg);
   NSR_CHECK_LAUNCH("igemm_fprop_tc");
   return NSR_OK;
 }
 
 int conv_fprop_tc(const NsrConv& d, cudaStream_t st) {
+  if (d.x_sti != nullptr) {
+    int bn = pick_bn(d.cout);
+    if (bn == 256) bn = 128;  // the 12-warp epilogue staging leaves no room for BN=256 stages
+    switch (bn) {
+      case 64: return launch_fprop_tc<64, true>(d, st);
+      case 128: return launch_fprop_tc<128, true>(d, st);
+      default: return launch_fprop_tc<192, true>(d, st);
+    }
+  }
   switch (pick_bn(d.cout)) {
-    case 64: return launch_fprop_tc<64>(d, st);
-    case 128: return launch_fprop_tc<128>(d, st);
-    case 192: return launch_fprop_tc<192>(d, st);
-    default: return launch_fprop_tc<256>(d, st);
+    case 64: return launch_fprop_tc<64, false>(d, st);
+    case 128: return launch_fprop_tc<128, false>(d, st);
+    case 192: return launch_fprop_tc<192, false>(d, st);
+    default: return launch_fprop_tc<256, false>(d, st);
   }
 }
 
@@ -392,12 +362,14 @@ struct WgGeom {
   long long M, rows_per_split;
   const float* p_ptr;
   const float* q_ptr;
+  const void* p_sti;
+  const void* q_sti;
 };
 
 int launch_wgrad_reduce(const float* partial, float* dw, int splitk, int cout, int taps, int cin, cudaStream_t st);
 int conv_bias_grad(const NsrWgrad& d, float* bias_partial, int bias_blocks, cudaStream_t st);
 
-template <int BN>
+template <int BN, bool STI>
 __global__ void __launch_bounds__(TC_THREADS, 1) igemm_wgrad_tc(NsrWgrad d, WgGeom g, float* __restrict__ partial) {
   using Cfg = WgCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -411,7 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_wgrad_tc(NsrWgrad d, WgGe
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::stages; ++s) {
-      mbar_init(&full[s], TC_PROD_WARPS * 32);
+      mbar_init(&full[s], STI ? 1 : TC_PROD_WARPS * 32);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -437,7 +409,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_wgrad_tc(NsrWgrad d, WgGe
     mt = item / g.n_tiles;
   };
 
-  if (warp < TC_PROD_WARPS) {
+  if (STI && warp == TC_PROD_WARPS) {
+    // ================================ bulk loader (operands are split tile images) ==========
+    // A k-block = 64 pixels = rows [r0, r0+64) of the 128-row blocks: 8 KiB per 64-channel panel
+    // and half, contiguous in the image, so each panel half is one bulk copy.
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int kbp = (g.pc + 63) / 64, kbq = (g.qc + 63) / 64;
+      const uint8_t* psti = reinterpret_cast<const uint8_t*>(g.p_sti);
+      const uint8_t* qsti = reinterpret_cast<const uint8_t*>(g.q_sti);
+      for (int item = blockIdx.x; item < g.num_items; item += gridDim.x) {
+        int mt, nt, tap, split;
+        decode(item, mt, nt, tap, split);
+        const long long p_begin = (long long)split * g.rows_per_split;
+        long long p_end = p_begin + g.rows_per_split;
+        if (p_end > g.M) p_end = g.M;
+        const int nkb = (int)((p_end - p_begin + WG_KPIX - 1) / WG_KPIX);
+        int np = kbp - mt * 2;
+        np = np > 2 ? 2 : np;
+        int nq = kbq - nt * (BN / 64);
+        nq = nq > BN / 64 ? BN / 64 : nq;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const long long pk = p_begin + (long long)kb * WG_KPIX;
+          const size_t pm = (size_t)(pk >> 7);
+          const uint32_t roff = (uint32_t)(pk & 127) * 128;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sb = smem + stage * Cfg::stage_bytes;
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(np + nq) * 2 * (WG_KPIX * 128));
+          for (int j = 0; j < np; ++j) {
+            const uint8_t* src = psti + ((pm * kbp + (size_t)(mt * 2 + j)) << 15) + roff;
+            bulk_g2s(sb + j * (WG_KPIX * 128), src, WG_KPIX * 128, &full[stage]);
+            bulk_g2s(sb + Cfg::p_bytes + j * (WG_KPIX * 128), src + 16384, WG_KPIX * 128, &full[stage]);
+          }
+          for (int j = 0; j < nq; ++j) {
+            const uint8_t* src = qsti + ((pm * kbq + (size_t)(nt * (BN / 64) + j)) << 15) + roff;
+            bulk_g2s(sb + 2 * Cfg::p_bytes + j * (WG_KPIX * 128), src, WG_KPIX * 128, &full[stage]);
+            bulk_g2s(sb + 2 * Cfg::p_bytes + Cfg::q_bytes + j * (WG_KPIX * 128), src + 16384, WG_KPIX * 128, &full[stage]);
+          }
+          if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (!STI && warp < TC_PROD_WARPS) {
     // ================================ producers ===========================================
     // Each k-block needs (128 + BN) / 32 (row, 8-channel chunk) items per thread; they are
     // processed in groups of G with the loads of the next group (possibly of the next k-block or
@@ -670,6 +684,8 @@ static WgPlan wg_plan(const NsrWgrad& d) {
   g.q_ld = g.swap ? d.dy_ld : d.x_ld;
   g.p_ptr = g.swap ? d.x : d.dy;
   g.q_ptr = g.swap ? d.dy : d.x;
+  g.p_sti = g.swap ? d.x_sti : d.dy_sti;
+  g.q_sti = g.swap ? d.dy_sti : d.x_sti;
   g.m_tiles = (g.pc + 127) / 128;
   g.n_tiles = (g.qc + p.bn - 1) / p.bn;
   const int tiles = g.m_tiles * g.n_tiles * g.taps;
@@ -698,7 +714,9 @@ bool conv_wgrad_tc_supported(const NsrWgrad& d) {
   if (!ok_dev) return false;
   if (d.cin % 4 || d.cout % 4 || d.x_ld % 4 || d.dy_ld % 4) return false;
   if (d.cin < 16 || d.cout < 16) return false;
-  if (!aligned16(d.x) || !aligned16(d.dy)) return false;
+  const bool sti = d.x_sti != nullptr && d.dy_sti != nullptr && d.kh == 1 && d.kw == 1;
+  if (!sti && (d.x == nullptr || d.dy == nullptr)) return false;
+  if (!aligned16(d.x) || !aligned16(d.dy) || !aligned16(d.x_sti) || !aligned16(d.dy_sti)) return false;
   return true;
 }
 size_t conv_wgrad_workspace_tc(const NsrWgrad& d) {
@@ -706,12 +724,12 @@ size_t conv_wgrad_workspace_tc(const NsrWgrad& d) {
   return (p.dw_partial_floats + p.bias_partial_floats) * sizeof(float);
 }
 
-template <int BN>
+template <int BN, bool STI>
 static int launch_wgrad_tc(const NsrWgrad& d, const WgPlan& p, float* partial, cudaStream_t st) {
   using Cfg = WgCfg<BN>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_tc<BN, STI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes);
     if (e != cudaSuccess) {
       set_error("igemm_wgrad_tc<%d>: cudaFuncSetAttribute: %s", BN, cudaGetErrorString(e));
       return NSR_E_CUDA;
@@ -719,7 +737,7 @@ static int launch_wgrad_tc(const NsrWgrad& d, const WgPlan& p, float* partial, c
     attr = true;
   }
   const int grid = p.g.num_items < kNumSMs ? p.g.num_items : kNumSMs;
-  igemm_wgrad_tc<BN><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, p.g, partial);
+  igemm_wgrad_tc<BN, STI><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, p.g, partial);
   NSR_CHECK_LAUNCH("igemm_wgrad_tc");
   return NSR_OK;
 }
@@ -733,11 +751,21 @@ int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st) {
   }
   float* partial = reinterpret_cast<float*>(d.workspace);
   int rc;
-  switch (p.bn) {
-    case 64: rc = launch_wgrad_tc<64>(d, p, partial, st); break;
-    case 128: rc = launch_wgrad_tc<128>(d, p, partial, st); break;
-    case 192: rc = launch_wgrad_tc<192>(d, p, partial, st); break;
-    default: rc = launch_wgrad_tc<256>(d, p, partial, st); break;
+  const bool sti = d.x_sti != nullptr && d.dy_sti != nullptr && d.kh == 1 && d.kw == 1;
+  if (sti) {
+    switch (p.bn) {
+      case 64: rc = launch_wgrad_tc<64, true>(d, p, partial, st); break;
+      case 128: rc = launch_wgrad_tc<128, true>(d, p, partial, st); break;
+      case 192: rc = launch_wgrad_tc<192, true>(d, p, partial, st); break;
+      default: rc = launch_wgrad_tc<256, true>(d, p, partial, st); break;
+    }
+  } else {
+    switch (p.bn) {
+      case 64: rc = launch_wgrad_tc<64, false>(d, p, partial, st); break;
+      case 128: rc = launch_wgrad_tc<128, false>(d, p, partial, st); break;
+      case 192: rc = launch_wgrad_tc<192, false>(d, p, partial, st); break;
+      default: rc = launch_wgrad_tc<256, false>(d, p, partial, st); break;
+    }
   }
   if (rc) return rc;
   rc = launch_wgrad_reduce(partial, d.dw, p.g.splitk, d.cout, p.g.taps, d.cin, st);

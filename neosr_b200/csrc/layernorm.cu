@@ -1,6 +1,6 @@
 // LayerNorm over the channel dim of [rows, C] tokens: warp-per-row, shuffle reductions,
 // deterministic two-pass dgamma/dbeta.  HBM-bound (fwd: read x, write y; bwd: read x,dy(,dres), write dx).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace nsr {
 
@@ -89,6 +89,172 @@ __global__ void layernorm_bwd_final(const float* __restrict__ partial, float* __
   else if (dbeta) dbeta[c - C] = s;
 }
 
+// ---- v2: 16-byte-chunk-per-lane kernels (C % 4 == 0, C <= 768) with optional split-tile-image output.
+// Each lane owns NCH chunks of 8 channels for every row its warp processes: gamma/beta and the
+// dgamma/dbeta partial sums live in registers, rows stream through as 128-bit loads/stores, and the
+// normalised row can be emitted directly as bf16 hi/lo in the layout the next contraction bulk-copies.
+template <int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_v2(const float* __restrict__ x,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float* __restrict__ y,
+                                                                 float* __restrict__ mean, float* __restrict__ rstd,
+                                                                 uint8_t* __restrict__ y_sti, int rows, int C, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kbs = (C + 63) / 64;
+  const float invC = 1.f / (float)C;
+  float gm[NCH][8], bt[NCH][8];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (lane + 32 * k) * 8 + e;
+      gm[k][e] = c < C ? gamma[c] : 0.f;
+      bt[k][e] = c < C ? beta[c] : 0.f;
+    }
+  for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows; r += (long long)gridDim.x * LN_WARPS) {
+    const float* xr = x + r * C;
+    float v[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (lane + 32 * k) * 8;
+      const float4 a = c0 < C ? *reinterpret_cast<const float4*>(xr + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b = c0 + 4 < C ? *reinterpret_cast<const float4*>(xr + c0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w;
+      v[k][4] = b.x; v[k][5] = b.y; v[k][6] = b.z; v[k][7] = b.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[k][e];
+    }
+    const float mu = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dlt = ((lane + 32 * k) * 8 + e < C) ? v[k][e] - mu : 0.f;
+        q = fmaf(dlt, dlt, q);
+      }
+    const float rs = rsqrtf(warp_sum(q) * invC + eps);
+    if (lane == 0) {
+      if (mean) mean[r] = mu;
+      if (rstd) rstd[r] = rs;
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int ch = lane + 32 * k, c0 = ch * 8;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (c0 + e < C) ? (v[k][e] - mu) * rs * gm[k][e] + bt[k][e] : 0.f;
+      if (y) {
+        if (c0 < C) *reinterpret_cast<float4*>(y + r * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        if (c0 + 4 < C) *reinterpret_cast<float4*>(y + r * C + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (y_sti && ch < kbs * 8) {
+        uint4 hi, lo;
+        tc::split8(make_float4(o[0], o[1], o[2], o[3]), make_float4(o[4], o[5], o[6], o[7]), hi, lo);
+        const int rr = (int)(r & 127), kb = ch >> 3, cc = ch & 7;
+        uint8_t* dst = y_sti + ((size_t)((r >> 7) * kbs + kb) << 15) + rr * 128 + ((cc ^ (rr & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + 16384) = lo;
+      }
+    }
+  }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_v2(
+    const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+    float* __restrict__ dx, uint8_t* __restrict__ dx_sti, float* __restrict__ partial, int rows, int C) {
+  extern __shared__ float sm[];  // [LN_WARPS][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kbs = (C + 63) / 64;
+  const float invC = 1.f / (float)C;
+  float gm[NCH][8], dg[NCH][8], db[NCH][8];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (lane + 32 * k) * 8 + e;
+      gm[k][e] = c < C ? gamma[c] : 0.f;
+      dg[k][e] = 0.f;
+      db[k][e] = 0.f;
+    }
+  for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows; r += (long long)gridDim.x * LN_WARPS) {
+    const float mu = mean[r], rs = rstd[r];
+    float xh[NCH][8], g[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (lane + 32 * k) * 8;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xa = c0 < C ? *reinterpret_cast<const float4*>(x + r * C + c0) : z;
+      const float4 xb = c0 + 4 < C ? *reinterpret_cast<const float4*>(x + r * C + c0 + 4) : z;
+      const float4 ga = c0 < C ? *reinterpret_cast<const float4*>(dy + r * C + c0) : z;
+      const float4 gb = c0 + 4 < C ? *reinterpret_cast<const float4*>(dy + r * C + c0 + 4) : z;
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool ok = c0 + e < C;
+        xh[k][e] = ok ? (xv[e] - mu) * rs : 0.f;
+        g[k][e] = gv[e];
+        const float gg = gv[e] * gm[k][e];
+        s1 += gg;
+        s2 = fmaf(gg, xh[k][e], s2);
+        dg[k][e] = fmaf(gv[e], xh[k][e], dg[k][e]);
+        db[k][e] += gv[e];
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int ch = lane + 32 * k, c0 = ch * 8;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (c0 + e < C) ? rs * (g[k][e] * gm[k][e] - s1 - xh[k][e] * s2) : 0.f;
+      if (dres) {
+        if (c0 < C) {
+          const float4 ra = *reinterpret_cast<const float4*>(dres + r * C + c0);
+          o[0] += ra.x; o[1] += ra.y; o[2] += ra.z; o[3] += ra.w;
+        }
+        if (c0 + 4 < C) {
+          const float4 rb = *reinterpret_cast<const float4*>(dres + r * C + c0 + 4);
+          o[4] += rb.x; o[5] += rb.y; o[6] += rb.z; o[7] += rb.w;
+        }
+      }
+      if (dx) {
+        if (c0 < C) *reinterpret_cast<float4*>(dx + r * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        if (c0 + 4 < C) *reinterpret_cast<float4*>(dx + r * C + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (dx_sti && ch < kbs * 8) {
+        uint4 hi, lo;
+        tc::split8(make_float4(o[0], o[1], o[2], o[3]), make_float4(o[4], o[5], o[6], o[7]), hi, lo);
+        const int rr = (int)(r & 127), kb = ch >> 3, cc = ch & 7;
+        uint8_t* dst = dx_sti + ((size_t)((r >> 7) * kbs + kb) << 15) + rr * 128 + ((cc ^ (rr & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + 16384) = lo;
+      }
+    }
+  }
+  float* wg = sm + (size_t)warp * 2 * C;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (lane + 32 * k) * 8 + e;
+      if (c < C) { wg[c] = dg[k][e]; wg[C + c] = db[k][e]; }
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) s += sm[(size_t)w * 2 * C + c];
+    partial[(size_t)blockIdx.x * 2 * C + c] = s;
+  }
+}
+
 static int ln_blocks(int rows) {
   int b = ceil_div(rows, LN_WARPS);
   return b > LN_MAX_BLOCKS ? LN_MAX_BLOCKS : (b < 1 ? 1 : b);
@@ -96,19 +262,32 @@ static int ln_blocks(int rows) {
 }  // namespace nsr
 using namespace nsr;
 
+static bool ln_v2_ok(const void* a, const void* b, const void* c, const void* d, int C) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return C % 4 == 0 && C <= 768 && al(a) && al(b) && al(c) && al(d);
+}
+
 extern "C" int nsr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
-                                 float* rstd, int rows, int c, float eps, void* stream) {
-  NSR_CHECK_ARG(x && gamma && beta && y && rows > 0 && c > 0, "nsr_layernorm_fwd: bad arguments");
-  layernorm_fwd_kernel<<<ln_blocks(rows), LN_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, gamma, beta, y, mean, rstd, rows, c, eps);
+                                 float* rstd, int rows, int c, float eps, void* y_sti, void* stream) {
+  NSR_CHECK_ARG(x && gamma && beta && (y || y_sti) && rows > 0 && c > 0, "nsr_layernorm_fwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ln_v2_ok(x, y, y_sti, nullptr, c)) {
+    uint8_t* sti = reinterpret_cast<uint8_t*>(y_sti);
+    if (c <= 256) layernorm_fwd_v2<1><<<ln_blocks(rows), LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, sti, rows, c, eps);
+    else if (c <= 512) layernorm_fwd_v2<2><<<ln_blocks(rows), LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, sti, rows, c, eps);
+    else layernorm_fwd_v2<3><<<ln_blocks(rows), LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, sti, rows, c, eps);
+  } else {
+    NSR_CHECK_ARG(y && !y_sti, "nsr_layernorm_fwd: split-tile-image output needs C % 4 == 0, C <= 768, 16-byte alignment");
+    layernorm_fwd_kernel<<<ln_blocks(rows), LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, c, eps);
+  }
   NSR_CHECK_LAUNCH("layernorm_fwd");
   return NSR_OK;
 }
 extern "C" size_t nsr_layernorm_bwd_workspace(int c) { return (size_t)LN_MAX_BLOCKS * 2 * c * sizeof(float); }
 extern "C" int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
                                  const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta, int rows,
-                                 int c, void* workspace, size_t workspace_bytes, void* stream) {
-  NSR_CHECK_ARG(dy && x && gamma && mean && rstd && dx && rows > 0 && c > 0, "nsr_layernorm_bwd: bad arguments");
+                                 int c, void* workspace, size_t workspace_bytes, void* dx_sti, void* stream) {
+  NSR_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_sti) && rows > 0 && c > 0, "nsr_layernorm_bwd: bad arguments");
   NSR_CHECK_ARG(c <= 704, "nsr_layernorm_bwd: C > 704 not supported");
   if (!workspace || workspace_bytes < nsr_layernorm_bwd_workspace(c)) {
     set_error("nsr_layernorm_bwd: workspace too small");
@@ -118,7 +297,15 @@ extern "C" int nsr_layernorm_bwd(const float* dy, const float* x, const float* g
   const int blocks = ln_blocks(rows);
   const size_t smem = (size_t)LN_WARPS * 2 * c * sizeof(float);
   float* partial = reinterpret_cast<float*>(workspace);
-  layernorm_bwd_kernel<<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, partial, rows, c);
+  if (ln_v2_ok(x, dy, dres, dx, c) && (reinterpret_cast<uintptr_t>(dx_sti) & 15) == 0) {
+    uint8_t* sti = reinterpret_cast<uint8_t*>(dx_sti);
+    if (c <= 256) layernorm_bwd_v2<1><<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, sti, partial, rows, c);
+    else if (c <= 512) layernorm_bwd_v2<2><<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, sti, partial, rows, c);
+    else layernorm_bwd_v2<3><<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, sti, partial, rows, c);
+  } else {
+    NSR_CHECK_ARG(dx && !dx_sti, "nsr_layernorm_bwd: split-tile-image output needs C % 4 == 0 and 16-byte alignment");
+    layernorm_bwd_kernel<<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, partial, rows, c);
+  }
   NSR_CHECK_LAUNCH("layernorm_bwd");
   layernorm_bwd_final<<<ceil_div(2 * c, 128), 128, 0, st>>>(partial, dgamma, dbeta, blocks, c);
   NSR_CHECK_LAUNCH("layernorm_bwd_final");

@@ -1,0 +1,98 @@
+// Shared epilogue of the tcgen05 contraction kernels: one 32-column chunk of this warp's 32
+// accumulator rows, TMEM -> registers -> per-warp smem transpose -> row-contiguous global traffic.
+#pragma once
+#include "tc_common.cuh"
+
+namespace nsr {
+namespace tc {
+
+constexpr int EPI_LD = 36;  // padded row stride (floats) of the per-warp transpose tile [32][EPI_LD]
+
+// byte offset (hi image) of the 8-byte half-chunk holding channels col..col+3 (col % 4 == 0) of row p
+__device__ __forceinline__ size_t sti_offset(long long p, int col, int kbs) {
+  const long long mt = p >> 7;
+  const int r = (int)(p & 127);
+  const int kb = col >> 6, cc = col & 63;
+  return ((size_t)(mt * kbs + kb) << 15) + (size_t)(r * 128 + (((cc >> 3) ^ (r & 7)) << 4) + ((cc >> 2) & 1) * 8);
+}
+
+// d: contraction descriptor (epilogue fields), stg: this warp's [32][EPI_LD] fp32 tile,
+// taddr: TMEM address of (lane quarter, first column of the chunk), p0: first row of this warp,
+// nc0: first output channel of the chunk, kbs_out: 64-channel blocks of the STI output (0 if none)
+__device__ __forceinline__ void epi_chunk(const NsrConv& d, float* stg, uint32_t taddr, long long p0, int nc0,
+                                          long long M, int hw, int lane, int kbs_out) {
+  const int er = lane >> 3, ec = (lane & 7) * 4;
+  float v[32];
+  tmem_ld_32x32(taddr, v);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  __syncwarp();
+  const int n = nc0 + ec;
+  const bool ncol = n < d.cout;
+  const bool nsti = d.y_sti != nullptr && n < kbs_out * 64;
+  if (!ncol && !nsti) return;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
+  if (ncol && d.bias) b4 = __ldg(reinterpret_cast<const float4*>(d.bias + n));
+  if (ncol && d.prelu) s4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
+  float4 aux4[8], res4[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long p = p0 + i * 4 + er;
+    const bool ok = ncol && p < M;
+    const long long o = p * d.y_ld + n;
+    aux4[i] = (ok && d.actgrad) ? *reinterpret_cast<const float4*>(d.aux + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    res4[i] = (ok && d.residual) ? *reinterpret_cast<const float4*>(d.residual + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long p = p0 + i * 4 + er;
+    if (p >= M) continue;
+    float ov[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ncol) {
+      const long long o = p * d.y_ld + n;
+      const float4 a4 = *reinterpret_cast<const float4*>(stg + (i * 4 + er) * EPI_LD + ec);
+      ov[0] = a4.x + b4.x; ov[1] = a4.y + b4.y; ov[2] = a4.z + b4.z; ov[3] = a4.w + b4.w;
+      if (d.y_pre) *reinterpret_cast<float4*>(d.y_pre + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      if (d.act) {
+        if (d.act == NSR_ACT_PRELU) {
+          ov[0] = apply_act_fast(ov[0], d.act, s4.x); ov[1] = apply_act_fast(ov[1], d.act, s4.y);
+          ov[2] = apply_act_fast(ov[2], d.act, s4.z); ov[3] = apply_act_fast(ov[3], d.act, s4.w);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ov[e] = apply_act_fast(ov[e], d.act, d.act_slope);
+        }
+      }
+      if (d.actgrad) {
+        if (d.actgrad == NSR_ACT_PRELU) {
+          ov[0] *= act_grad_fast(aux4[i].x, d.actgrad, s4.x); ov[1] *= act_grad_fast(aux4[i].y, d.actgrad, s4.y);
+          ov[2] *= act_grad_fast(aux4[i].z, d.actgrad, s4.z); ov[3] *= act_grad_fast(aux4[i].w, d.actgrad, s4.w);
+        } else {
+          ov[0] *= act_grad_fast(aux4[i].x, d.actgrad, d.actgrad_slope);
+          ov[1] *= act_grad_fast(aux4[i].y, d.actgrad, d.actgrad_slope);
+          ov[2] *= act_grad_fast(aux4[i].z, d.actgrad, d.actgrad_slope);
+          ov[3] *= act_grad_fast(aux4[i].w, d.actgrad, d.actgrad_slope);
+        }
+      }
+      if (d.row_scale) {
+        const float rs = d.row_scale[p / hw];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ov[e] *= rs;
+      }
+      if (d.residual) { ov[0] += res4[i].x; ov[1] += res4[i].y; ov[2] += res4[i].z; ov[3] += res4[i].w; }
+      if (d.y) *reinterpret_cast<float4*>(d.y + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    }
+    if (nsti) {  // channels in [cout, kbs_out*64) are written as zeros (K padding of the next contraction)
+      uint2 hi, lo;
+      split2(ov[0], ov[1], hi.x, lo.x);
+      split2(ov[2], ov[3], hi.y, lo.y);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(d.y_sti) + sti_offset(p, n, kbs_out);
+      *reinterpret_cast<uint2*>(dst) = hi;
+      *reinterpret_cast<uint2*>(dst + 16384) = lo;
+    }
+  }
+}
+
+}  // namespace tc
+}  // namespace nsr

@@ -229,10 +229,10 @@ __global__ void window_attn_dbias_kernel(const float* __restrict__ partial, floa
 }
 
 bool window_attn_mma_supported(int c, int heads, int ws);
-int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, int batch, int h, int w, int c,
-                               int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
-int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float* dout, float* dqkv, float* partial,
-                               int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
+int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w,
+                               int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
+int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float* dout, float* dqkv, void* dqkv_sti,
+                               float* partial, int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
                                float scale, cudaStream_t st);
 static bool use_mma(int c, int heads, int ws) {
   static int simt_forced = -1;
@@ -262,17 +262,20 @@ static int make_geom(WinGeom& g, int batch, int h, int w, int c, int heads, int 
 using namespace nsr;
 
 extern "C" int nsr_window_attn_fwd(const float* qkv, const float* bias_table, float* out, int batch, int h, int w,
-                                   int c, int heads, int ws, int shift, int use_mask, float scale, void* stream) {
-  NSR_CHECK_ARG(qkv && bias_table && out, "nsr_window_attn_fwd: null pointer");
+                                   int c, int heads, int ws, int shift, int use_mask, float scale, void* out_sti,
+                                   void* stream) {
+  NSR_CHECK_ARG(qkv && bias_table && (out || out_sti), "nsr_window_attn_fwd: null pointer");
   WinGeom g;
   int rc = make_geom(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_fwd");
   if (rc) return rc;
   if (use_mma(c, heads, ws))
-    return window_attn_fwd_mma_launch(qkv, bias_table, out, batch, h, w, c, heads, ws, shift, use_mask, scale,
+    return window_attn_fwd_mma_launch(qkv, bias_table, out, out_sti, batch, h, w, c, heads, ws, shift, use_mask, scale,
                                       reinterpret_cast<cudaStream_t>(stream));
+  NSR_CHECK_ARG(out, "nsr_window_attn_fwd: this shape runs on the fp32 kernel, which needs the fp32 output buffer");
   dim3 grid(batch * g.nwh * g.nww, heads);
   window_attn_fwd_kernel<<<grid, WA_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(qkv, bias_table, out, g);
   NSR_CHECK_LAUNCH("window_attn_fwd");
+  if (out_sti) return nsr_sti_from_f32(out, c, (long long)batch * h * w, c, out_sti, stream);
   return NSR_OK;
 }
 
@@ -283,8 +286,9 @@ extern "C" size_t nsr_window_attn_bwd_workspace(int heads, int ws) {
 
 extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv,
                                    float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int shift,
-                                   int use_mask, float scale, void* workspace, size_t workspace_bytes, void* stream) {
-  NSR_CHECK_ARG(qkv && bias_table && dout && dqkv && dbias_table, "nsr_window_attn_bwd: null pointer");
+                                   int use_mask, float scale, void* workspace, size_t workspace_bytes, void* dqkv_sti,
+                                   void* stream) {
+  NSR_CHECK_ARG(qkv && bias_table && dout && (dqkv || dqkv_sti) && dbias_table, "nsr_window_attn_bwd: null pointer");
   WinGeom g;
   int rc = make_geom(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_bwd");
   if (rc) return rc;
@@ -309,13 +313,18 @@ extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, co
   }
   float* partial = reinterpret_cast<float*>(workspace);
   if (mma) {
-    rc = window_attn_bwd_mma_launch(qkv, bias_table, dout, dqkv, partial, gx, batch, h, w, c, heads, ws, shift,
+    rc = window_attn_bwd_mma_launch(qkv, bias_table, dout, dqkv, dqkv_sti, partial, gx, batch, h, w, c, heads, ws, shift,
                                     use_mask, scale, st);
     if (rc) return rc;
   } else {
+    NSR_CHECK_ARG(dqkv, "nsr_window_attn_bwd: this shape runs on the fp32 kernel, which needs the fp32 dqkv buffer");
     dim3 grid(gx, heads);
     window_attn_bwd_kernel<<<grid, WA_THREADS, WA_BWD_SMEM, st>>>(qkv, bias_table, dout, dqkv, partial, g, nwin);
     NSR_CHECK_LAUNCH("window_attn_bwd");
+    if (dqkv_sti) {
+      rc = nsr_sti_from_f32(dqkv, 3 * c, (long long)batch * h * w, 3 * c, dqkv_sti, stream);
+      if (rc) return rc;
+    }
   }
   const int n = (2 * ws - 1) * (2 * ws - 1) * heads;
   window_attn_dbias_kernel<<<ceil_div(n, 128), 128, 0, st>>>(partial, dbias_table, gx, heads, ws);

@@ -73,6 +73,24 @@ __device__ __forceinline__ void attn_token_map(const AttnGeom& g, int wi, int n,
   rid = rh * 3 + rw;
 }
 
+// store the pair (v0, v1) for channels (cidx, cidx+1) of token row p into a split tile image
+__device__ __forceinline__ void sti_store_pair(uint8_t* sti, int kbs, long long p, int cidx, float v0, float v1) {
+  uint32_t hi, lo;
+  split_pair(v0, v1, hi, lo);
+  const int r = (int)(p & 127), kb = cidx >> 6, cc = cidx & 63;
+  uint8_t* dst = sti + ((size_t)((p >> 7) * kbs + kb) << 15) + r * 128 + (((cc >> 3) ^ (r & 7)) << 4) + (cc & 7) * 2;
+  *reinterpret_cast<uint32_t*>(dst) = hi;
+  *reinterpret_cast<uint32_t*>(dst + 16384) = lo;
+}
+// zero the channel padding [cfirst, kbs*64) of this window's 64 tokens (done by the last head's CTA)
+__device__ __forceinline__ void sti_zero_padding(uint8_t* sti, int kbs, const int* tok, int cfirst, int t) {
+  const int pairs = (kbs * 64 - cfirst) / 2;
+  for (int i = t; i < AM_N * pairs; i += AM_THREADS) {
+    const int n = i / pairs, pr = i - n * pairs;
+    sti_store_pair(sti, kbs, tok[n], cfirst + 2 * pr, 0.f, 0.f);
+  }
+}
+
 // S = Qs K^T for this warp's 16 rows: acc[nt] covers columns 8nt..8nt+7
 __device__ __forceinline__ void qk_scores(const __nv_bfloat16* Ah, const __nv_bfloat16* Al, const __nv_bfloat16* Bh,
                                           const __nv_bfloat16* Bl, int row0, int g, int tid, float (&acc)[8][4]) {
@@ -164,7 +182,8 @@ __device__ __forceinline__ void acc_times(const float (&x)[8][4], const __nv_bfl
 // ------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* __restrict__ qkv,
                                                                  const float* __restrict__ table,
-                                                                 float* __restrict__ out, AttnGeom gm) {
+                                                                 float* __restrict__ out, uint8_t* __restrict__ out_sti,
+                                                                 AttnGeom gm) {
   __shared__ __align__(16) __nv_bfloat16 Qh[AM_N * AM_LD], Ql[AM_N * AM_LD], Kh[AM_N * AM_LD], Kl[AM_N * AM_LD];
   __shared__ __align__(16) __nv_bfloat16 Vth[32 * AM_LDT], Vtl[32 * AM_LDT];
   __shared__ float bias_s[225];
@@ -212,13 +231,16 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int i = row0 + g + 8 * h;
-    float* dst = out + (size_t)tok[i] * gm.C + head * gm.D;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int c = nt * 8 + tid * 2;
-      if (c < gm.D) *reinterpret_cast<float2*>(dst + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
+      if (c < gm.D) {
+        if (out) *reinterpret_cast<float2*>(out + (size_t)tok[i] * gm.C + head * gm.D + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
+        if (out_sti) sti_store_pair(out_sti, (gm.C + 63) / 64, tok[i], head * gm.D + c, o[nt][2 * h], o[nt][2 * h + 1]);
+      }
     }
   }
+  if (out_sti && head == gm.heads - 1) sti_zero_padding(out_sti, (gm.C + 63) / 64, tok, gm.C, t);
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -230,10 +252,11 @@ constexpr int BW_PHASE1 = 8 * BW_TILE;     // Q,K,V,dO hi+lo = 20480 elements
 static_assert(4 * BW_PT <= BW_PHASE1, "Pt/dSt (hi+lo) must fit in the phase-1 region");
 constexpr size_t BW_SMEM = (size_t)(BW_PHASE1 + 6 * BW_TT) * sizeof(__nv_bfloat16);
 
-__global__ void __launch_bounds__(AM_THREADS) window_attn_bwd_mma(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float* __restrict__ qkv,
                                                                  const float* __restrict__ table,
                                                                  const float* __restrict__ dout,
                                                                  float* __restrict__ dqkv,
+                                                                 uint8_t* __restrict__ dqkv_sti,
                                                                  float* __restrict__ partial, AttnGeom gm, int nwin) {
   extern __shared__ __align__(16) __nv_bfloat16 sm[];
   __nv_bfloat16* Qh = sm;                 __nv_bfloat16* Ql = Qh + BW_TILE;
@@ -335,13 +358,18 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_bwd_mma(const float* _
     // ---- phase 2a: dQ[i][d] = scale * sum_j dS[i][j] K[j][d]   (A = dS from registers, B = Kt)
     float o[4][4];
     acc_times(ds, Kth, Ktl, g, tid, o);
+    const int kbs3 = (3 * gm.C + 63) / 64;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float* dst = dqkv + (size_t)tok[row0 + g + 8 * h] * 3 * gm.C + head * gm.D;
+      const long long tk = tok[row0 + g + 8 * h];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int c = nt * 8 + tid * 2;
-        if (c < gm.D) *reinterpret_cast<float2*>(dst + c) = make_float2(o[nt][2 * h] * gm.scale, o[nt][2 * h + 1] * gm.scale);
+        if (c < gm.D) {
+          const float v0 = o[nt][2 * h] * gm.scale, v1 = o[nt][2 * h + 1] * gm.scale;
+          if (dqkv) *reinterpret_cast<float2*>(dqkv + tk * 3 * gm.C + head * gm.D + c) = make_float2(v0, v1);
+          if (dqkv_sti) sti_store_pair(dqkv_sti, kbs3, tk, head * gm.D + c, v0, v1);
+        }
       }
     }
     __syncthreads();  // Pt / dSt complete
@@ -369,14 +397,19 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_bwd_mma(const float* _
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float* dst = dqkv + (size_t)tok[row0 + g + 8 * h] * 3 * gm.C + (which == 0 ? gm.C : 2 * gm.C) + head * gm.D;
+        const long long tk = tok[row0 + g + 8 * h];
+        const int cbase = (which == 0 ? gm.C : 2 * gm.C) + head * gm.D;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int c = nt * 8 + tid * 2;
-          if (c < gm.D) *reinterpret_cast<float2*>(dst + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
+          if (c < gm.D) {
+            if (dqkv) *reinterpret_cast<float2*>(dqkv + tk * 3 * gm.C + cbase + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
+            if (dqkv_sti) sti_store_pair(dqkv_sti, kbs3, tk, cbase + c, o[nt][2 * h], o[nt][2 * h + 1]);
+          }
         }
       }
     }
+    if (dqkv_sti && head == gm.heads - 1) sti_zero_padding(dqkv_sti, kbs3, tok, 3 * gm.C, t);
   }
   // bias-table gradient partial: [blockIdx.x][head][i][j]
   float* outp = partial + ((size_t)blockIdx.x * gm.heads + head) * AM_N * AM_N;
@@ -396,17 +429,17 @@ bool window_attn_mma_supported(int c, int heads, int ws) {
   return ws == 8 && d <= 32 && d % 2 == 0 && (c % 2 == 0);
 }
 
-int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, int batch, int h, int w, int c,
-                               int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st) {
+int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w,
+                               int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st) {
   AttnGeom g{batch, h, w, c, heads, ws, shift, use_mask, c / heads, h / ws, w / ws, scale};
   dim3 grid(batch * g.nwh * g.nww, heads);
-  window_attn_fwd_mma<<<grid, AM_THREADS, 0, st>>>(qkv, table, out, g);
+  window_attn_fwd_mma<<<grid, AM_THREADS, 0, st>>>(qkv, table, out, reinterpret_cast<uint8_t*>(out_sti), g);
   NSR_CHECK_LAUNCH("window_attn_fwd_mma");
   return NSR_OK;
 }
 
-int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float* dout, float* dqkv, float* partial,
-                               int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
+int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float* dout, float* dqkv, void* dqkv_sti,
+                               float* partial, int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
                                float scale, cudaStream_t st) {
   AttnGeom g{batch, h, w, c, heads, ws, shift, use_mask, c / heads, h / ws, w / ws, scale};
   static bool attr = false;
@@ -419,7 +452,8 @@ int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float
     attr = true;
   }
   dim3 grid(gx, heads);
-  window_attn_bwd_mma<<<grid, AM_THREADS, BW_SMEM, st>>>(qkv, table, dout, dqkv, partial, g, batch * g.nwh * g.nww);
+  window_attn_bwd_mma<<<grid, AM_THREADS, BW_SMEM, st>>>(qkv, table, dout, dqkv, reinterpret_cast<uint8_t*>(dqkv_sti), partial,
+                                                         g, batch * g.nwh * g.nww);
   NSR_CHECK_LAUNCH("window_attn_bwd_mma");
   return NSR_OK;
 }

@@ -84,6 +84,46 @@ def scratch(nbytes: int, device) -> Tensor:
     return s.get(nbytes, device)
 
 
+# ----------------------------------------------------------------------------- split tile images
+class STI:
+    """A token tensor [B,H,W,C] stored as a split tile image (see nsr_sti_bytes in the header):
+    bf16 hi + bf16 lo in 128-row x 64-channel swizzled blocks, the layout tcgen05 contractions
+    bulk-copy straight into shared memory.  Same bytes as fp32."""
+
+    def __init__(self, shape, device):
+        self.shape = tuple(shape)
+        B, H, W, Cc = self.shape
+        self.rows, self.c = B * H * W, Cc
+        n = _lib.lib().nsr_sti_bytes(self.rows, Cc)
+        # rows beyond `rows` must read as zero (they enter the wgrad reduction): zero-fill when padded
+        alloc = torch.zeros if self.rows % 128 else torch.empty
+        self.buf = alloc(n, dtype=torch.uint8, device=device)
+        self.device = device
+
+    def data_ptr(self):
+        return self.buf.data_ptr()
+
+    @staticmethod
+    def from_f32(x: Tensor) -> "STI":
+        _chk(x, "x")
+        s = STI(x.shape, x.device)
+        check(_lib.lib().nsr_sti_from_f32(x.data_ptr(), s.c, s.rows, s.c, s.data_ptr(), _stream()), "nsr_sti_from_f32")
+        _count(1)
+        return s
+
+    def to_f32(self) -> Tensor:
+        y = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+        check(_lib.lib().nsr_sti_to_f32(self.data_ptr(), self.rows, self.c, y.data_ptr(), self.c, _stream()), "nsr_sti_to_f32")
+        _count(1)
+        return y
+
+
+def sti_enabled() -> bool:
+    """Split-tile-image operands need the tcgen05 engine (sm_100) and are skipped when a test
+    forces the exact-fp32 engine."""
+    return DEFAULT_ENGINE != "simt" and bool(_lib.lib().nsr_device_supports_tcgen05())
+
+
 # ----------------------------------------------------------------------------- weights
 class PackedWeight:
     """fprop- and dgrad-flavoured packed copies of one Conv2d/Linear weight
@@ -126,48 +166,64 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
                act: str = "none", act_slope: float = 0.0, actgrad: str = "none", actgrad_slope: float = 0.0,
                aux: Tensor | None = None, prelu: Tensor | None = None, row_scale: Tensor | None = None,
                residual: Tensor | None = None, want_pre: bool = False, out: Tensor | None = None,
-               engine: str = "auto"):
-    """y = epilogue(conv(x, w)); x is [B,H,W,Cin] NHWC.  With dgrad=True the dgrad-packed
-    filter is used and the roles of cin/cout swap (x is then dY [B,H,W,Cout])."""
-    _chk(x, "x")
+               engine: str = "auto", sti_out: bool = False, f32_out: bool = True):
+    """y = epilogue(conv(x, w)); x is [B,H,W,Cin] NHWC fp32 or an STI (1x1 only).  With dgrad=True
+    the dgrad-packed filter is used and the roles of cin/cout swap (x is then dY [B,H,W,Cout]).
+    sti_out / f32_out select the output formats: returns y (fp32), or the STI, or (y, sti)."""
+    x_is_sti = isinstance(x, STI)
+    if not x_is_sti:
+        _chk(x, "x")
     B, H, W, cx = x.shape
     cin, cout = (pw.cout, pw.cin) if dgrad else (pw.cin, pw.cout)
     if cx != cin:
         raise ValueError(f"conv_fprop: x has {cx} channels, weight expects {cin}")
     for t, n in ((bias, "bias"), (aux, "aux"), (prelu, "prelu"), (row_scale, "row_scale"), (residual, "residual")):
         _chk(t, n)
-    y = out if out is not None else torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device)
-    y_pre = torch.empty_like(y) if want_pre else None
+    y = None
+    if f32_out:
+        y = out if out is not None else torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device)
+    y_sti = STI((B, H, W, cout), x.device) if sti_out else None
+    if y is None and y_sti is None:
+        raise ValueError("conv_fprop: no output format selected")
+    y_pre = torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device) if want_pre else None
     d = NsrConv(batch=B, h=H, w=W, cin=cin, cout=cout, kh=pw.kh, kw=pw.kw, pad=pw.kh // 2,
                 x_ld=cin, y_ld=cout, act=ACT[act], act_slope=act_slope, actgrad=ACT[actgrad],
                 actgrad_slope=actgrad_slope, engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
-                x=x.data_ptr(), w_packed=(pw.dgrad if dgrad else pw.fprop).data_ptr(), bias=_p(bias),
-                prelu=_p(prelu), aux=_p(aux), row_scale=_p(row_scale), residual=_p(residual),
-                y_pre=_p(y_pre), y=y.data_ptr())
+                x=None if x_is_sti else x.data_ptr(), w_packed=(pw.dgrad if dgrad else pw.fprop).data_ptr(),
+                bias=_p(bias), prelu=_p(prelu), aux=_p(aux), row_scale=_p(row_scale), residual=_p(residual),
+                y_pre=_p(y_pre), y=_p(y), x_sti=x.data_ptr() if x_is_sti else None, y_sti=_p(y_sti))
     M = B * H * W
-    with _prof("conv_dgrad" if dgrad else "conv_fprop", (M, cin, cout, pw.kh),
+    with _prof(("conv_dgrad" if dgrad else "conv_fprop") + ("_sti" if x_is_sti else ""), (M, cin, cout, pw.kh),
                2.0 * M * cin * cout * pw.kh * pw.kw, 4.0 * M * (cin + cout)):
         check(_lib.lib().nsr_conv_fprop(C.byref(d), _stream()), "nsr_conv_fprop")
     _count(1)
-    return (y, y_pre) if want_pre else y
+    res = y if y_sti is None else (y_sti if y is None else (y, y_sti))
+    return (res, y_pre) if want_pre else res
 
 
-def conv_wgrad(x: Tensor, dy: Tensor, dw: Tensor, dbias: Tensor | None, kh: int, kw: int, engine: str = "auto"):
-    """dw[cout,cin,kh,kw] (+ dbias) from x [B,H,W,Cin] and dy [B,H,W,Cout]; overwrites dw/dbias."""
+def conv_wgrad(x, dy, dw: Tensor, dbias: Tensor | None, kh: int, kw: int, engine: str = "auto",
+               x_sti: STI | None = None, dy_sti: STI | None = None):
+    """dw[cout,cin,kh,kw] (+ dbias) from x [B,H,W,Cin] and dy [B,H,W,Cout]; overwrites dw/dbias.
+    x / dy may be None when their split tile images are given (1x1 contractions)."""
     _chk(x, "x"), _chk(dy, "dy"), _chk(dw, "dw"), _chk(dbias, "dbias")
-    B, H, W, cin = x.shape
-    cout = dy.shape[-1]
+    xs, ds = (x if x is not None else x_sti), (dy if dy is not None else dy_sti)
+    B, H, W, cin = xs.shape
+    cout = ds.shape[-1]
+    x, dy = (x if x is not None else xs), (dy if dy is not None else ds)
     if dy.shape[:3] != x.shape[:3] or dw.numel() != cout * cin * kh * kw:
         raise ValueError(f"conv_wgrad: shape mismatch x{tuple(x.shape)} dy{tuple(dy.shape)} dw{tuple(dw.shape)}")
     d = NsrWgrad(batch=B, h=H, w=W, cin=cin, cout=cout, kh=kh, kw=kw, pad=kh // 2, x_ld=cin, dy_ld=cout,
-                 engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine], x=x.data_ptr(), dy=dy.data_ptr(), dw=dw.data_ptr(), dbias=_p(dbias),
-                 workspace=None, workspace_bytes=0)
+                 engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
+                 x=None if isinstance(x, STI) else x.data_ptr(), dy=None if isinstance(dy, STI) else dy.data_ptr(),
+                 dw=dw.data_ptr(), dbias=_p(dbias), workspace=None, workspace_bytes=0,
+                 x_sti=_p(x_sti), dy_sti=_p(dy_sti))
     L = _lib.lib()
     need = L.nsr_conv_wgrad_workspace(C.byref(d))
     ws = scratch(need, x.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     M = B * H * W
-    with _prof("conv_wgrad", (M, cin, cout, kh), 2.0 * M * cin * cout * kh * kw, 4.0 * M * (cin + cout)):
+    with _prof("conv_wgrad" + ("_sti" if x_sti is not None and dy_sti is not None else ""), (M, cin, cout, kh),
+               2.0 * M * cin * cout * kh * kw, 4.0 * M * (cin + cout)):
         check(L.nsr_conv_wgrad(C.byref(d), _stream()), "nsr_conv_wgrad")
     _count(4 if dbias is not None else 2)
 
@@ -262,66 +318,80 @@ def actgrad_mul(dy: Tensor, aux: Tensor, act: str, slope: float = 0.0, dextra: T
 
 
 # ----------------------------------------------------------------------------- LayerNorm
-def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5):
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, sti_out: bool = False,
+                  f32_out: bool = True):
+    """Returns (y, mean, rstd); y is fp32, an STI, or (fp32, STI) per sti_out / f32_out."""
     _chk(x, "x"), _chk(gamma, "gamma"), _chk(beta, "beta")
     c = x.shape[-1]
     rows = x.numel() // c
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if f32_out else None
+    y_sti = STI(x.shape, x.device) if sti_out else None
     mean = torch.empty(rows, dtype=torch.float32, device=x.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
     with _prof("nsr_layernorm_fwd", (rows, c), 0.0, 8.0 * x.numel()):
-        check(_lib.lib().nsr_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
-                                           rstd.data_ptr(), rows, c, eps, _stream()), "nsr_layernorm_fwd")
+        check(_lib.lib().nsr_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(y), mean.data_ptr(),
+                                           rstd.data_ptr(), rows, c, eps, _p(y_sti), _stream()), "nsr_layernorm_fwd")
     _count(1)
-    return y, mean, rstd
+    return (y if y_sti is None else (y_sti if y is None else (y, y_sti))), mean, rstd
 
 
 def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dgamma: Tensor, dbeta: Tensor,
-                  dres: Tensor | None = None) -> Tensor:
+                  dres: Tensor | None = None, sti_out: bool = False):
+    """dx (fp32) [, dx as STI when sti_out]."""
     for t, n in ((dy, "dy"), (x, "x"), (gamma, "gamma"), (mean, "mean"), (rstd, "rstd"), (dgamma, "dgamma"),
                  (dbeta, "dbeta"), (dres, "dres")):
         _chk(t, n)
     c = x.shape[-1]
     rows = x.numel() // c
     dx = torch.empty_like(x)
+    dx_sti = STI(x.shape, x.device) if sti_out else None
     L = _lib.lib()
     ws = scratch(L.nsr_layernorm_bwd_workspace(c), x.device)
     with _prof("nsr_layernorm_bwd", (rows, c), 0.0, (16.0 if dres is not None else 12.0) * x.numel()):
         check(L.nsr_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(dres),
                                   dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, c, ws.data_ptr(), ws.numel(),
-                                  _stream()), "nsr_layernorm_bwd")
+                                  _p(dx_sti), _stream()), "nsr_layernorm_bwd")
     _count(2)
-    return dx
+    return (dx, dx_sti) if sti_out else dx
 
 
 # ----------------------------------------------------------------------------- attention
-def window_attn_fwd(qkv: Tensor, table: Tensor, heads: int, ws: int, shift: int, scale: float) -> Tensor:
-    """qkv [B,H,W,3C] -> [B,H,W,C]; shift/partition/mask/bias/softmax/PV fused."""
+def _attn_mma_ok(c: int, heads: int, ws: int) -> bool:
+    d = c // heads
+    return ws == 8 and d <= 32 and d % 2 == 0
+
+
+def window_attn_fwd(qkv: Tensor, table: Tensor, heads: int, ws: int, shift: int, scale: float, sti_out: bool = False):
+    """qkv [B,H,W,3C] -> [B,H,W,C] (fp32, or an STI when sti_out); shift/partition/mask/bias/softmax/PV fused."""
     _chk(qkv, "qkv"), _chk(table, "table")
     B, H, W, c3 = qkv.shape
     c = c3 // 3
-    out = torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device)
-    with _prof("nsr_window_attn_fwd", (B * H * W, c, heads, ws), 0.0, 4.0 * (qkv.numel() + out.numel())):
-        check(_lib.lib().nsr_window_attn_fwd(qkv.data_ptr(), table.data_ptr(), out.data_ptr(), B, H, W, c, heads, ws, shift,
-                                             1 if shift > 0 else 0, scale, _stream()), "nsr_window_attn_fwd")
+    out_sti = STI((B, H, W, c), qkv.device) if sti_out else None
+    need_f32 = (not sti_out) or not _attn_mma_ok(c, heads, ws)
+    out = torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device) if need_f32 else None
+    with _prof("nsr_window_attn_fwd", (B * H * W, c, heads, ws), 0.0, 4.0 * (qkv.numel() + B * H * W * c)):
+        check(_lib.lib().nsr_window_attn_fwd(qkv.data_ptr(), table.data_ptr(), _p(out), B, H, W, c, heads, ws, shift,
+                                             1 if shift > 0 else 0, scale, _p(out_sti), _stream()), "nsr_window_attn_fwd")
     _count(1)
-    return out
+    return out_sti if sti_out else out
 
 
 def window_attn_bwd(qkv: Tensor, table: Tensor, dout: Tensor, dtable: Tensor, heads: int, ws: int, shift: int,
-                    scale: float) -> Tensor:
+                    scale: float, sti_out: bool = False):
     _chk(qkv, "qkv"), _chk(table, "table"), _chk(dout, "dout"), _chk(dtable, "dtable")
     B, H, W, c3 = qkv.shape
     c = c3 // 3
-    dqkv = torch.empty_like(qkv)
+    dqkv_sti = STI(qkv.shape, qkv.device) if sti_out else None
+    need_f32 = (not sti_out) or not _attn_mma_ok(c, heads, ws)
+    dqkv = torch.empty_like(qkv) if need_f32 else None
     L = _lib.lib()
     wsb = scratch(L.nsr_window_attn_bwd_workspace(heads, ws), qkv.device)
     with _prof("nsr_window_attn_bwd", (B * H * W, c, heads, ws), 0.0, 4.0 * (2 * qkv.numel() + dout.numel())):
-        check(L.nsr_window_attn_bwd(qkv.data_ptr(), table.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), dtable.data_ptr(),
+        check(L.nsr_window_attn_bwd(qkv.data_ptr(), table.data_ptr(), dout.data_ptr(), _p(dqkv), dtable.data_ptr(),
                                     B, H, W, c, heads, ws, shift, 1 if shift > 0 else 0, scale, wsb.data_ptr(), wsb.numel(),
-                                    _stream()), "nsr_window_attn_bwd")
+                                    _p(dqkv_sti), _stream()), "nsr_window_attn_bwd")
     _count(2)
-    return dqkv
+    return dqkv_sti if sti_out else dqkv
 
 
 # ----------------------------------------------------------------------------- losses

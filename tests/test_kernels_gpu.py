@@ -252,3 +252,76 @@ def test_fused_adan_sf_clip_ema_vs_oracle():
         assert rel(s["neg_pre_grad"].cpu(), st.neg_pre_grad[i]) < 1e-5
     g = opt.param_groups[0]
     assert g["step"] == 3 and abs(g["weight_sum"] - st.weight_sum) < 1e-15
+
+
+# ----------------------------------------------------------------------------- split tile images
+@pytest.mark.parametrize("B,H,W,C", [(1, 8, 24, 180), (2, 16, 16, 36), (1, 64, 64, 540)])
+def test_sti_roundtrip(B, H, W, C):
+    from neosr_b200 import ops
+    x = rnd(B, H, W, C, seed=1)
+    s = ops.STI.from_f32(x)
+    assert rel(s.to_f32(), x) < 1e-5  # hi + lo carries ~17 mantissa bits
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 8, 24, 180, 540), (2, 32, 64, 180, 360), (2, 32, 64, 360, 180),
+                                            (1, 16, 16, 36, 72), (32, 64, 64, 180, 180)])
+def test_sti_linear_fprop_dgrad_wgrad(B, H, W, cin, cout):
+    """1x1 contractions whose operands arrive / leave as split tile images (bulk-copy kernels)."""
+    from neosr_b200 import ops
+    x = rnd(B, H, W, cin, seed=1)
+    w = rnd(cout, cin, seed=2, scale=1 / math.sqrt(cin))
+    b = rnd(cout, seed=3, scale=0.1)
+    res = rnd(B, H, W, cout, seed=4)
+    dy = rnd(B, H, W, cout, seed=5)
+    pw = ops.PackedWeight(w).refresh()
+    xs, dys = ops.STI.from_f32(x), ops.STI.from_f32(dy)
+    lin = F.linear(x.double(), w.double(), b.double())
+    y = ops.conv_fprop(xs, pw, b, residual=res)
+    assert rel(y.double(), lin + res.double()) < 2e-5
+    (ys, pre) = ops.conv_fprop(xs, pw, b, act="gelu", want_pre=True, sti_out=True, f32_out=False)
+    assert rel(pre.double(), lin) < 2e-5
+    assert rel(ys.to_f32().double(), F.gelu(lin)) < 3e-5
+    yf, ys2 = ops.conv_fprop(x, pw, b, sti_out=True)  # fp32-A kernel emitting both formats
+    assert rel(ys2.to_f32(), yf) < 1e-5
+    dx = ops.conv_fprop(dys, pw, None, dgrad=True)
+    assert rel(dx.double(), dy.double() @ w.double()) < 2e-5
+    aux = rnd(B, H, W, cin, seed=7)
+    dxs = ops.conv_fprop(dys, pw, None, dgrad=True, actgrad="gelu", aux=aux, sti_out=True, f32_out=False)
+    ag = aux.double().requires_grad_(True)
+    F.gelu(ag).sum().backward()
+    assert rel(dxs.to_f32().double(), (dy.double() @ w.double()) * ag.grad) < 3e-5
+    dw, db = torch.empty_like(w), torch.empty_like(b)
+    ops.conv_wgrad(None, None, dw, db, 1, 1, x_sti=xs, dy_sti=dys)
+    ref_dw = dy.double().reshape(-1, cout).t() @ x.double().reshape(-1, cin)
+    assert rel(dw.double(), ref_dw) < 3e-5
+    assert rel(db.double(), dy.double().sum((0, 1, 2))) < 2e-5
+    dw2, db2 = torch.empty_like(w), torch.empty_like(b)
+    ops.conv_wgrad(None, dy, dw2, db2, 1, 1, x_sti=xs, dy_sti=dys)
+    assert torch.equal(dw, dw2) and rel(db2.double(), dy.double().sum((0, 1, 2))) < 1e-5
+
+
+def test_sti_layernorm_and_attention():
+    from neosr_b200 import ops
+    rows, c = 2 * 16 * 16, 180
+    x = rnd(2, 16, 16, c, seed=1)
+    g, b = 1 + 0.1 * rnd(c, seed=2), rnd(c, seed=3, scale=0.1)
+    y_ref = F.layer_norm(x, (c,), g, b, 1e-5)
+    (yf, ys), mu, rs = ops.layernorm_fwd(x, g, b, sti_out=True)
+    assert rel(yf, y_ref) < 1e-5 and rel(ys.to_f32(), y_ref) < 2e-5
+    dy, dres = rnd(2, 16, 16, c, seed=4), rnd(2, 16, 16, c, seed=5)
+    dg, db = torch.empty_like(g), torch.empty_like(b)
+    dx, dxs = ops.layernorm_bwd(dy, x, g, mu, rs, dg, db, dres=dres, sti_out=True)
+    dx0 = ops.layernorm_bwd(dy, x, g, mu, rs, torch.empty_like(g), torch.empty_like(b), dres=dres)
+    assert torch.equal(dx, dx0) and rel(dxs.to_f32(), dx) < 2e-5
+    qkv = rnd(2, 16, 16, 3 * c, seed=6)
+    table = rnd(225, 6, seed=7, scale=0.5)
+    scale = 30 ** -0.5
+    for shift in (0, 4):
+        o = ops.window_attn_fwd(qkv, table, 6, 8, shift, scale)
+        os_ = ops.window_attn_fwd(qkv, table, 6, 8, shift, scale, sti_out=True)
+        assert rel(os_.to_f32(), o) < 2e-5
+        dout = rnd(2, 16, 16, c, seed=8)
+        dt1, dt2 = torch.empty_like(table), torch.empty_like(table)
+        dq = ops.window_attn_bwd(qkv, table, dout, dt1, 6, 8, shift, scale)
+        dqs = ops.window_attn_bwd(qkv, table, dout, dt2, 6, 8, shift, scale, sti_out=True)
+        assert rel(dqs.to_f32(), dq) < 2e-5 and torch.equal(dt1, dt2)
