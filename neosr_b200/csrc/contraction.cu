@@ -14,6 +14,12 @@ int conv_fprop_tc(const NsrConv& d, cudaStream_t st);
 bool conv_wgrad_tc_supported(const NsrWgrad& d);
 size_t conv_wgrad_workspace_tc(const NsrWgrad& d);
 int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st);
+// <= 4-channel image-side convolutions (conv_small.cu)
+bool conv_small_fprop_supported(const NsrConv& d);
+int conv_small_fprop(const NsrConv& d, cudaStream_t st);
+bool conv_small_wgrad_supported(const NsrWgrad& d);
+size_t conv_small_wgrad_workspace(const NsrWgrad& d);
+int conv_small_wgrad(const NsrWgrad& d, cudaStream_t st);
 
 static int forced_engine() {
   static int cached = -1;
@@ -195,6 +201,7 @@ extern "C" int nsr_conv_fprop(const NsrConv* d, void* stream) {
   }
   if (eng == NSR_ENGINE_AUTO && conv_fprop_tc_supported(*d)) return conv_fprop_tc(*d, st);
   NSR_CHECK_ARG(d->x && d->y && !d->y_sti, "nsr_conv_fprop: split-tile-image operands need the tcgen05 engine");
+  if (eng == NSR_ENGINE_AUTO && conv_small_fprop_supported(*d)) return conv_small_fprop(*d, st);
   return conv_fprop_simt(*d, st);
 }
 
@@ -218,7 +225,9 @@ extern "C" size_t nsr_conv_wgrad_workspace(const NsrWgrad* d) {
   if (!d) return 0;
   size_t a = conv_wgrad_workspace_simt(*d);
   size_t b = conv_wgrad_tc_supported(*d) ? conv_wgrad_workspace_tc(*d) : 0;
-  return a > b ? a : b;
+  size_t c = conv_small_wgrad_supported(*d) ? conv_small_wgrad_workspace(*d) : 0;
+  a = a > b ? a : b;
+  return a > c ? a : c;
 }
 
 extern "C" int nsr_conv_wgrad(const NsrWgrad* d, void* stream) {
@@ -230,5 +239,6 @@ extern "C" int nsr_conv_wgrad(const NsrWgrad* d, void* stream) {
     NSR_CHECK_ARG(conv_wgrad_tc_supported(*d), "nsr_conv_wgrad: shape not supported by the tcgen05 engine");
   if (wgrad_use_tc(d)) return conv_wgrad_tc(*d, st);
   NSR_CHECK_ARG(d->x && d->dy, "nsr_conv_wgrad: split-tile-image operands need the tcgen05 engine");
+  if (eng == NSR_ENGINE_AUTO && conv_small_wgrad_supported(*d)) return conv_small_wgrad(*d, st);
   return conv_wgrad_simt(*d, st);
 }

@@ -34,13 +34,14 @@ def nchw(x):
     return x.permute(0, 3, 1, 2).contiguous()
 
 
-ENGINES = ["simt", "tcgen05"]
+ENGINES = ["simt", "tcgen05", "auto"]  # auto also routes 3-channel convs to conv_small.cu
 
 
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("B,H,W,cin,cout,k", [
     (2, 16, 24, 36, 36, 3), (1, 8, 8, 3, 180, 3), (2, 16, 16, 64, 3, 3), (2, 8, 16, 180, 540, 1),
-    (1, 16, 16, 180, 180, 3), (3, 8, 8, 64, 256, 3), (2, 8, 8, 360, 180, 1), (1, 40, 24, 20, 70, 3)])
+    (1, 16, 16, 180, 180, 3), (3, 8, 8, 64, 256, 3), (2, 8, 8, 360, 180, 1), (1, 40, 24, 20, 70, 3),
+    (2, 24, 40, 3, 64, 3), (2, 24, 40, 64, 3, 3), (1, 16, 16, 128, 3, 3), (2, 16, 24, 4, 48, 3)])
 def test_conv_fprop_dgrad_wgrad(engine, B, H, W, cin, cout, k):
     from neosr_b200 import ops
     if engine == "tcgen05" and (min(cin, cout) < 16 or cin % 4 or cout % 4):
