@@ -169,9 +169,6 @@ def run_ours(args) -> None:
     from neosr_b200.models import build_model
     B = args.batch
     model = build_model(make_opt(B, world > 1, rank, world))
-    if world > 1:  # identical replicas: broadcast rank-0 initial weights (what DDP does at wrap time)
-        for p in model.net_g.parameters():
-            dist.broadcast(p.data, 0)
     pool = synth_batches(args.pool, B, seed=1024 + rank)
     dev_pool = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in pool]
     torch.cuda.synchronize()

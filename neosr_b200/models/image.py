@@ -33,6 +33,7 @@ from torch.optim.swa_utils import AveragedModel, get_ema_multi_avg_fn
 from .. import ops
 from ..archs import build_network
 from ..archs.arch_util import set_default_scale
+from ..dist import allreduce_mean_, broadcast_params_
 from ..losses import build_loss
 from ..optimizers import AdamW, adan_sf
 from ..registry import MODEL_REGISTRY
@@ -61,6 +62,8 @@ class image:
                               path.get("strict_load_g", True))
         self.dist = bool(opt.get("dist", False))
         self.world_size = int(opt.get("world_size", 1))
+        if self.dist and self.world_size > 1:
+            broadcast_params_(self.net_g.parameters())  # identical replicas, as DDP does when wrapping
         if self.is_train:
             self.init_training_settings()
 
@@ -152,7 +155,7 @@ class image:
         logs["l_g_total"] = total
         net.engine_backward(saved, dout)
         if self.dist and self.world_size > 1:
-            torch.distributed.all_reduce(ps.flat_grad, op=torch.distributed.ReduceOp.AVG)
+            allreduce_mean_(ps.flat_grad)  # the one collective of the step (DDP-style gradient averaging)
         ps.attach_grads()
         ema = None
         if self.ema > 0:
@@ -185,7 +188,7 @@ class image:
             keys = list(logs)
             vec = torch.cat([logs[k].view(1) for k in keys])
             if self.dist and self.world_size > 1:
-                torch.distributed.all_reduce(vec, op=torch.distributed.ReduceOp.AVG)
+                allreduce_mean_(vec)
             vals = vec.tolist()
             if any(v != v for v in vals):
                 raise ValueError("NaN found, aborting training. Make sure you're using a proper learning rate.")
