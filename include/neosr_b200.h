@@ -37,6 +37,7 @@ extern "C" {
 #define NSR_ACT_LRELU 2 /* slope = act_slope */
 #define NSR_ACT_GELU 3  /* exact erf GELU (torch.nn.GELU default) */
 #define NSR_ACT_PRELU 4 /* per-output-channel slope vector */
+#define NSR_ACT_MULAUX 5 /* actgrad only: aux already holds act'(pre) (saved by pre_mode = 1) */
 
 /* engine selection for the contraction kernels */
 #define NSR_ENGINE_AUTO 0
@@ -57,7 +58,7 @@ int nsr_device_supports_tcgen05(void);
  * vgg_arch.py:134 features) and their autograd dgrad (same call with the dgrad-packed
  * weight).  Epilogue, in order:
  *   v = acc + bias[co]                       (bias may be NULL)
- *   if (y_pre) y_pre[p,co] = v               (pre-activation copy, e.g. GELU input)
+ *   if (y_pre) y_pre[p,co] = pre_mode ? act'(v) : v   (saved for the backward pass)
  *   v = act(v)                               (NSR_ACT_*)
  *   if (mul_actgrad) v *= act'(aux[p,co])    (chain rule through the producer's
  *                                             activation; aux = its saved output /
@@ -91,6 +92,10 @@ typedef struct NsrConv {
    * value pre-split to bf16 hi/lo in the layout the next contraction bulk-copies. */
   const void* x_sti;
   void* y_sti;
+  int32_t pre_mode;      /* 0: y_pre = pre-activation; 1: y_pre = act'(pre-activation), so the backward
+                            epilogue is a plain multiply (actgrad = NSR_ACT_MULAUX) and the erf/exp terms
+                            are shared with the forward activation */
+  int32_t reserved;
 } NsrConv;
 
 int nsr_conv_fprop(const NsrConv* d, void* stream);

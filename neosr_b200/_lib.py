@@ -30,6 +30,7 @@ class NsrConv(C.Structure):
         ("x", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("prelu", C.c_void_p),
         ("aux", C.c_void_p), ("row_scale", C.c_void_p), ("residual", C.c_void_p),
         ("y_pre", C.c_void_p), ("y", C.c_void_p), ("x_sti", C.c_void_p), ("y_sti", C.c_void_p),
+        ("pre_mode", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -65,7 +66,7 @@ class NsrAdamW(C.Structure):
 
 
 OPT_CHUNK = 4096
-ACT = {"none": 0, "relu": 1, "lrelu": 2, "gelu": 3, "prelu": 4}
+ACT = {"none": 0, "relu": 1, "lrelu": 2, "gelu": 3, "prelu": 4, "mulaux": 5}
 ENGINE = {"auto": 0, "simt": 1, "tcgen05": 2}
 
 _i, _f, _p, _z, _l = C.c_int, C.c_float, C.c_void_p, C.c_size_t, C.c_int64

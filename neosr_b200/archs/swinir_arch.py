@@ -252,7 +252,9 @@ class swinir(nn.Module):
                 x1 = lin(pre + "attn.proj", att, residual=t, row_scale=ds[0] if ds else None)
                 ln2, mu2, rs2 = ops.layernorm_fwd(x1, ps.p(pre + "norm2.weight"), ps.p(pre + "norm2.bias"),
                                                   sti_out=sti, f32_out=not sti)
-                a, hpre = lin(pre + "mlp.fc1", ln2, act="gelu", want_pre=True, sti_out=sti, f32_out=not sti)
+                # hpre holds gelu'(fc1 pre-activation): the only thing the backward pass needs of it
+                a, hpre = lin(pre + "mlp.fc1", ln2, act="gelu", want_pre=True, pre_is_actgrad=True, sti_out=sti,
+                              f32_out=not sti)
                 x2 = lin(pre + "mlp.fc2", a, residual=x1, row_scale=ds[1] if ds else None)
                 if save:
                     S["blocks"].append((t, mu1, rs1, ln1, qkv, att, x1, mu2, rs2, ln2, hpre, a, ds))
@@ -361,7 +363,7 @@ class swinir(nn.Module):
                 shift = self.layers[li].residual_group.blocks[bi].shift_size
                 gf = split(g)[0]
                 gb = scaled(g, ds[1] if ds else None)
-                dh = bwd(pre + "mlp.fc2", a, gb, actgrad="gelu", aux=hpre, sti_out=sti, f32_out=not sti)
+                dh = bwd(pre + "mlp.fc2", a, gb, actgrad="mulaux", aux=hpre, sti_out=sti, f32_out=not sti)
                 dln2 = bwd(pre + "mlp.fc1", ln2, dh)
                 g1 = ops.layernorm_bwd(dln2, x1, ps.p(pre + "norm2.weight"), mu2, rs2, ps.g(pre + "norm2.weight"),
                                        ps.g(pre + "norm2.bias"), dres=gf, sti_out=sti)

@@ -86,6 +86,33 @@ __device__ __forceinline__ float act_grad_fast(float aux, int act, float slope) 
     default: return 1.f;
   }
 }
+// compile-time-selected versions (tcgen05 epilogue): value and derivative in one go
+template <int ACT>
+__device__ __forceinline__ void act_value_grad(float v, float slope, float& val, float& grad) {
+  if (ACT == NSR_ACT_GELU) {
+    float c, p;
+    gelu_terms(v, c, p);
+    val = v * c;
+    grad = fmaf(v, p, c);
+  } else if (ACT == NSR_ACT_RELU) {
+    val = v > 0.f ? v : 0.f;
+    grad = v > 0.f ? 1.f : 0.f;
+  } else if (ACT == NSR_ACT_LRELU || ACT == NSR_ACT_PRELU) {
+    val = v > 0.f ? v : v * slope;
+    grad = v > 0.f ? 1.f : slope;
+  } else {
+    val = v;
+    grad = 1.f;
+  }
+}
+template <int AG>
+__device__ __forceinline__ float act_grad_ct(float aux, float slope) {
+  if (AG == NSR_ACT_MULAUX) return aux;
+  if (AG == NSR_ACT_GELU) return gelu_fast_grad(aux);
+  if (AG == NSR_ACT_RELU) return aux > 0.f ? 1.f : 0.f;
+  if (AG == NSR_ACT_LRELU || AG == NSR_ACT_PRELU) return aux > 0.f ? 1.f : slope;
+  return 1.f;
+}
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   switch (act) {
     case NSR_ACT_RELU: return v > 0.f ? v : 0.f;
@@ -99,6 +126,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 // (sign is preserved for slope > 0); for GELU / PReLU aux is the PRE-activation.
 __device__ __forceinline__ float act_grad(float aux, int act, float slope) {
   switch (act) {
+    case NSR_ACT_MULAUX: return aux;
     case NSR_ACT_RELU: return aux > 0.f ? 1.f : 0.f;
     case NSR_ACT_LRELU:
     case NSR_ACT_PRELU: return aux > 0.f ? 1.f : slope;

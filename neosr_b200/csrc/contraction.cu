@@ -184,7 +184,7 @@ static int check_conv(const NsrConv* d) {
   NSR_CHECK_ARG((d->x || d->x_sti) && d->w_packed && (d->y || d->y_sti), "nsr_conv_fprop: null x / w / y");
   NSR_CHECK_ARG(!(d->actgrad) || d->aux, "nsr_conv_fprop: actgrad needs aux");
   NSR_CHECK_ARG(!(d->act == NSR_ACT_PRELU || d->actgrad == NSR_ACT_PRELU) || d->prelu, "nsr_conv_fprop: prelu slopes missing");
-  NSR_CHECK_ARG(d->act >= 0 && d->act <= NSR_ACT_PRELU && d->actgrad >= 0 && d->actgrad <= NSR_ACT_PRELU,
+  NSR_CHECK_ARG(d->act >= 0 && d->act <= NSR_ACT_PRELU && d->actgrad >= 0 && d->actgrad <= NSR_ACT_MULAUX,
                 "nsr_conv_fprop: bad activation code");
   return NSR_OK;
 }

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(FTHREADS) igemm_fprop_simt(NsrConv d, const fl
       if (n >= d.cout) continue;
       const long long o = p * d.y_ld + n;
       float v = acc[i][j] + (d.bias ? d.bias[n] : 0.f);
-      if (d.y_pre) d.y_pre[o] = v;
+      if (d.y_pre) d.y_pre[o] = d.pre_mode ? act_grad(v, d.act, d.act == NSR_ACT_PRELU ? d.prelu[n] : d.act_slope) : v;
       if (d.act) v = apply_act(v, d.act, d.act == NSR_ACT_PRELU ? d.prelu[n] : d.act_slope);
       if (d.actgrad) v *= act_grad(d.aux[o], d.actgrad, d.actgrad == NSR_ACT_PRELU ? d.prelu[n] : d.actgrad_slope);
       if (d.row_scale) v *= rs;

@@ -280,6 +280,7 @@ bool conv_fprop_tc_supported(const NsrConv& d) {
     return false;
   }
   if (d.y == nullptr && d.y_sti == nullptr) return false;
+  if (d.act != NSR_ACT_NONE && d.actgrad != NSR_ACT_NONE) return false;  // epilogue is specialised on one of them
   if (!aligned16(d.x) || !aligned16(d.y) || !aligned16(d.y_sti) || !aligned16(d.bias) || !aligned16(d.aux) || !aligned16(d.residual) ||
       !aligned16(d.y_pre) || !aligned16(d.prelu) || !aligned16(d.w_packed))
     return false;
@@ -689,15 +690,17 @@ static WgPlan wg_plan(const NsrWgrad& d) {
   g.m_tiles = (g.pc + 127) / 128;
   g.n_tiles = (g.qc + p.bn - 1) / p.bn;
   const int tiles = g.m_tiles * g.n_tiles * g.taps;
-  int want = (kNumSMs + tiles - 1) / tiles;
-  const int maxs = (int)((g.M + 1023) / 1024);
+  // Pixels per split: at most WG_MAX_ROWS_PER_SPLIT (the tensor-core accumulator truncates on every
+  // add, so its error grows with the number of sequential accumulations; the fixed-order fp32 reduce
+  // over split partials rounds to nearest), and such that tiles * splits fills whole waves of 148 CTAs.
+  const int min_splits = (int)((g.M + WG_MAX_ROWS_PER_SPLIT - 1) / WG_MAX_ROWS_PER_SPLIT);
+  const int waves = (tiles * min_splits + kNumSMs - 1) / kNumSMs;
+  int want = (waves * kNumSMs) / tiles;
+  if (want < min_splits) want = min_splits;
+  const int maxs = (int)((g.M + 255) / 256);
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
   long long rps = (g.M + want - 1) / want;
-  // The tensor-core accumulator truncates on every add, so its error grows linearly with the
-  // number of sequential accumulations (measured: ~2e-5 rel after ~850 adds).  Cap the pixels one
-  // TMEM accumulator sees; the fixed-order fp32 reduce over split partials rounds to nearest.
-  if (rps > WG_MAX_ROWS_PER_SPLIT) rps = WG_MAX_ROWS_PER_SPLIT;
   g.rows_per_split = (rps + WG_KPIX - 1) / WG_KPIX * WG_KPIX;
   g.splitk = (int)((g.M + g.rows_per_split - 1) / g.rows_per_split);
   g.num_items = tiles * g.splitk;

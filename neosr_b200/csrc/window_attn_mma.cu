@@ -202,24 +202,38 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
   }
   __syncthreads();
   const int hp = gm.D / 2;  // float2 pairs per token
-  for (int idx = t; idx < AM_N * hp; idx += AM_THREADS) {
-    const int n = idx / hp, pr = idx - n * hp;
-    const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
-    const float2 q = *reinterpret_cast<const float2*>(p);
-    const float2 k = *reinterpret_cast<const float2*>(p + gm.C);
-    const float2 v = *reinterpret_cast<const float2*>(p + 2 * gm.C);
-    uint32_t hi, lo;
-    split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
-    *reinterpret_cast<uint32_t*>(&Qh[n * AM_LD + 2 * pr]) = hi;
-    *reinterpret_cast<uint32_t*>(&Ql[n * AM_LD + 2 * pr]) = lo;
-    split_pair(k.x, k.y, hi, lo);
-    *reinterpret_cast<uint32_t*>(&Kh[n * AM_LD + 2 * pr]) = hi;
-    *reinterpret_cast<uint32_t*>(&Kl[n * AM_LD + 2 * pr]) = lo;
-    split_pair(v.x, v.y, hi, lo);
-    reinterpret_cast<uint16_t*>(Vth)[(2 * pr) * AM_LDT + n] = (uint16_t)(hi & 0xFFFF);
-    reinterpret_cast<uint16_t*>(Vth)[(2 * pr + 1) * AM_LDT + n] = (uint16_t)(hi >> 16);
-    reinterpret_cast<uint16_t*>(Vtl)[(2 * pr) * AM_LDT + n] = (uint16_t)(lo & 0xFFFF);
-    reinterpret_cast<uint16_t*>(Vtl)[(2 * pr + 1) * AM_LDT + n] = (uint16_t)(lo >> 16);
+  constexpr int LB = 4;     // loads are issued LB iterations at a time so 3*LB requests are in flight per thread
+  for (int base = t; base < AM_N * hp; base += AM_THREADS * LB) {
+    float2 q[LB], k[LB], v[LB];
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int idx = base + u * AM_THREADS;
+      if (idx < AM_N * hp) {
+        const int n = idx / hp, pr = idx - n * hp;
+        const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
+        q[u] = *reinterpret_cast<const float2*>(p);
+        k[u] = *reinterpret_cast<const float2*>(p + gm.C);
+        v[u] = *reinterpret_cast<const float2*>(p + 2 * gm.C);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int idx = base + u * AM_THREADS;
+      if (idx >= AM_N * hp) break;
+      const int n = idx / hp, pr = idx - n * hp;
+      uint32_t hi, lo;
+      split_pair(q[u].x * gm.scale, q[u].y * gm.scale, hi, lo);
+      *reinterpret_cast<uint32_t*>(&Qh[n * AM_LD + 2 * pr]) = hi;
+      *reinterpret_cast<uint32_t*>(&Ql[n * AM_LD + 2 * pr]) = lo;
+      split_pair(k[u].x, k[u].y, hi, lo);
+      *reinterpret_cast<uint32_t*>(&Kh[n * AM_LD + 2 * pr]) = hi;
+      *reinterpret_cast<uint32_t*>(&Kl[n * AM_LD + 2 * pr]) = lo;
+      split_pair(v[u].x, v[u].y, hi, lo);
+      reinterpret_cast<uint16_t*>(Vth)[(2 * pr) * AM_LDT + n] = (uint16_t)(hi & 0xFFFF);
+      reinterpret_cast<uint16_t*>(Vth)[(2 * pr + 1) * AM_LDT + n] = (uint16_t)(hi >> 16);
+      reinterpret_cast<uint16_t*>(Vtl)[(2 * pr) * AM_LDT + n] = (uint16_t)(lo & 0xFFFF);
+      reinterpret_cast<uint16_t*>(Vtl)[(2 * pr + 1) * AM_LDT + n] = (uint16_t)(lo >> 16);
+    }
   }
   __syncthreads();
   const int row0 = warp * 16;
@@ -290,29 +304,44 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
       *reinterpret_cast<uint32_t*>(&sm[rowt * AM_LD + gm.D + 2 * cpair]) = 0;
     }
     __syncthreads();
-    for (int idx = t; idx < AM_N * hp; idx += AM_THREADS) {
-      const int n = idx / hp, pr = idx - n * hp;
-      const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
-      const float2 q = *reinterpret_cast<const float2*>(p);
-      const float2 k = *reinterpret_cast<const float2*>(p + gm.C);
-      const float2 v = *reinterpret_cast<const float2*>(p + 2 * gm.C);
-      const float2 dy = *reinterpret_cast<const float2*>(dout + (size_t)tok[n] * gm.C + head * gm.D + 2 * pr);
-      uint32_t hi, lo;
-      const int o1 = n * AM_LD + 2 * pr, t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
-      split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
-      *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
-      reinterpret_cast<uint16_t*>(Qth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Qth)[t1] = (uint16_t)(hi >> 16);
-      reinterpret_cast<uint16_t*>(Qtl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Qtl)[t1] = (uint16_t)(lo >> 16);
-      split_pair(k.x, k.y, hi, lo);
-      *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
-      reinterpret_cast<uint16_t*>(Kth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Kth)[t1] = (uint16_t)(hi >> 16);
-      reinterpret_cast<uint16_t*>(Ktl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ktl)[t1] = (uint16_t)(lo >> 16);
-      split_pair(v.x, v.y, hi, lo);
-      *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
-      split_pair(dy.x, dy.y, hi, lo);
-      *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
-      reinterpret_cast<uint16_t*>(Oth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Oth)[t1] = (uint16_t)(hi >> 16);
-      reinterpret_cast<uint16_t*>(Otl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Otl)[t1] = (uint16_t)(lo >> 16);
+    constexpr int LB = 2;  // 8 independent 8-byte loads in flight per thread
+    for (int base = t; base < AM_N * hp; base += AM_THREADS * LB) {
+      float2 qv[LB], kv[LB], vv[LB], dv[LB];
+#pragma unroll
+      for (int u = 0; u < LB; ++u) {
+        const int idx = base + u * AM_THREADS;
+        if (idx < AM_N * hp) {
+          const int n = idx / hp, pr = idx - n * hp;
+          const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
+          qv[u] = *reinterpret_cast<const float2*>(p);
+          kv[u] = *reinterpret_cast<const float2*>(p + gm.C);
+          vv[u] = *reinterpret_cast<const float2*>(p + 2 * gm.C);
+          dv[u] = *reinterpret_cast<const float2*>(dout + (size_t)tok[n] * gm.C + head * gm.D + 2 * pr);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < LB; ++u) {
+        const int idx = base + u * AM_THREADS;
+        if (idx >= AM_N * hp) break;
+        const int n = idx / hp, pr = idx - n * hp;
+        const float2 q = qv[u], k = kv[u], v = vv[u], dy = dv[u];
+        uint32_t hi, lo;
+        const int o1 = n * AM_LD + 2 * pr, t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
+        split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
+        reinterpret_cast<uint16_t*>(Qth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Qth)[t1] = (uint16_t)(hi >> 16);
+        reinterpret_cast<uint16_t*>(Qtl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Qtl)[t1] = (uint16_t)(lo >> 16);
+        split_pair(k.x, k.y, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
+        reinterpret_cast<uint16_t*>(Kth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Kth)[t1] = (uint16_t)(hi >> 16);
+        reinterpret_cast<uint16_t*>(Ktl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ktl)[t1] = (uint16_t)(lo >> 16);
+        split_pair(v.x, v.y, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
+        split_pair(dy.x, dy.y, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
+        reinterpret_cast<uint16_t*>(Oth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Oth)[t1] = (uint16_t)(hi >> 16);
+        reinterpret_cast<uint16_t*>(Otl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Otl)[t1] = (uint16_t)(lo >> 16);
+      }
     }
     __syncthreads();
     // ---- phase 1: P = softmax(Qs K^T + bias + mask); dP = dO V^T; dS = P o (dP - rowsum(P o dP))

@@ -166,7 +166,7 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
                act: str = "none", act_slope: float = 0.0, actgrad: str = "none", actgrad_slope: float = 0.0,
                aux: Tensor | None = None, prelu: Tensor | None = None, row_scale: Tensor | None = None,
                residual: Tensor | None = None, want_pre: bool = False, out: Tensor | None = None,
-               engine: str = "auto", sti_out: bool = False, f32_out: bool = True):
+               engine: str = "auto", sti_out: bool = False, f32_out: bool = True, pre_is_actgrad: bool = False):
     """y = epilogue(conv(x, w)); x is [B,H,W,Cin] NHWC fp32 or an STI (1x1 only).  With dgrad=True
     the dgrad-packed filter is used and the roles of cin/cout swap (x is then dY [B,H,W,Cout]).
     sti_out / f32_out select the output formats: returns y (fp32), or the STI, or (y, sti)."""
@@ -191,7 +191,8 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
                 actgrad_slope=actgrad_slope, engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
                 x=None if x_is_sti else x.data_ptr(), w_packed=(pw.dgrad if dgrad else pw.fprop).data_ptr(),
                 bias=_p(bias), prelu=_p(prelu), aux=_p(aux), row_scale=_p(row_scale), residual=_p(residual),
-                y_pre=_p(y_pre), y=_p(y), x_sti=x.data_ptr() if x_is_sti else None, y_sti=_p(y_sti))
+                y_pre=_p(y_pre), y=_p(y), x_sti=x.data_ptr() if x_is_sti else None, y_sti=_p(y_sti),
+                pre_mode=1 if pre_is_actgrad else 0, reserved=0)
     M = B * H * W
     with _prof(("conv_dgrad" if dgrad else "conv_fprop") + ("_sti" if x_is_sti else ""), (M, cin, cout, pw.kh),
                2.0 * M * cin * cout * pw.kh * pw.kw, 4.0 * M * (cin + cout)):

@@ -85,6 +85,13 @@ def test_conv_epilogues(engine):
     assert rel(y, F.linear(x, w) * aux.grad) < 1e-4
     y = ops.conv_fprop(x, pw, None, actgrad="relu", aux=res, residual=res, engine=engine)
     assert rel(y, F.linear(x, w) * (res > 0).float() + res) < 1e-4
+    # pre_mode = 1: y_pre holds gelu'(pre) so that the backward epilogue is a plain multiply (mulaux)
+    h = lin.detach().clone().requires_grad_(True)
+    F.gelu(h).sum().backward()
+    y, dact = ops.conv_fprop(x, pw, b, act="gelu", want_pre=True, pre_is_actgrad=True, engine=engine)
+    assert rel(y, F.gelu(lin)) < 1e-4 and rel(dact, h.grad) < 1e-4
+    y = ops.conv_fprop(x, pw, None, actgrad="mulaux", aux=dact, engine=engine)
+    assert rel(y, F.linear(x, w) * h.grad) < 1e-4
 
 
 @pytest.mark.parametrize("M,K,N,k", [(131072, 180, 540, 1), (131072, 360, 180, 1), (32 * 64 * 64, 180, 180, 3),

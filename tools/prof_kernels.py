@@ -45,6 +45,44 @@ def main():
                                aux=x if name == "fc2" else None)
             else:
                 ops.conv_wgrad(x, dy, dw, db, k, k)
+    elif what.startswith("sti"):
+        # STI-operand 1x1 contractions: stifprop_qkv, stidgrad_fc2, stiwgrad_qkv ...
+        kind, name = what[3:].split("_", 1)
+        cin, cout = {"qkv": (180, 540), "proj": (180, 180), "fc1": (180, 360), "fc2": (360, 180)}[name]
+        x = rnd(B, H, W, cin, seed=1)
+        w = rnd(cout, cin, seed=2, scale=1 / math.sqrt(cin))
+        b = rnd(cout, seed=3, scale=0.1)
+        res = rnd(B, H, W, cout, seed=4)
+        dy = rnd(B, H, W, cout, seed=5)
+        pw = ops.PackedWeight(w).refresh()
+        xs, dys = ops.STI.from_f32(x), ops.STI.from_f32(dy)
+        dw, db = torch.empty_like(w), torch.empty_like(b)
+
+        def run():
+            if kind == "fprop":
+                if name == "fc1":
+                    ops.conv_fprop(xs, pw, b, act="gelu", want_pre=True, sti_out=True, f32_out=False)
+                else:
+                    ops.conv_fprop(xs, pw, b, residual=res if name in ("proj", "fc2") else None)
+            elif kind == "dgrad":
+                if name == "fc2":
+                    ops.conv_fprop(dys, pw, None, dgrad=True, actgrad="gelu", aux=x, sti_out=True, f32_out=False)
+                else:
+                    ops.conv_fprop(dys, pw, None, dgrad=True)
+            else:
+                ops.conv_wgrad(None, dy, dw, db, 1, 1, x_sti=xs, dy_sti=dys)
+    elif what.startswith("ln"):
+        x = rnd(B, H, W, C, seed=1)
+        g, bb = 1 + 0.1 * rnd(C, seed=2), rnd(C, seed=3, scale=0.1)
+        dy, dres = rnd(B, H, W, C, seed=4), rnd(B, H, W, C, seed=5)
+        _, mu, rs = ops.layernorm_fwd(x, g, bb)
+        dg, db = torch.empty_like(g), torch.empty_like(bb)
+
+        def run():
+            if what == "ln_fwd":
+                ops.layernorm_fwd(x, g, bb, sti_out=True, f32_out=False)
+            else:
+                ops.layernorm_bwd(dy, x, g, mu, rs, dg, db, dres=dres, sti_out=True)
     elif what.startswith("attn"):
         qkv = rnd(B, H, W, 3 * C, seed=1)
         table = rnd(225, 6, seed=2, scale=0.5)
@@ -53,9 +91,9 @@ def main():
 
         def run():
             if what == "attn_fwd":
-                ops.window_attn_fwd(qkv, table, 6, 8, 4, 30 ** -0.5)
+                ops.window_attn_fwd(qkv, table, 6, 8, 4, 30 ** -0.5, sti_out=True)
             else:
-                ops.window_attn_bwd(qkv, table, dout, dtable, 6, 8, 4, 30 ** -0.5)
+                ops.window_attn_bwd(qkv, table, dout, dtable, 6, 8, 4, 30 ** -0.5, sti_out=True)
     else:
         raise SystemExit(f"unknown kernel {what}")
     for _ in range(2):
