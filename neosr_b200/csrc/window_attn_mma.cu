@@ -82,6 +82,18 @@ __device__ __forceinline__ void sti_store_pair(uint8_t* sti, int kbs, long long 
   *reinterpret_cast<uint32_t*>(dst) = hi;
   *reinterpret_cast<uint32_t*>(dst + 16384) = lo;
 }
+// same, with the row part of the address (block row base, r & 7) hoisted by the caller
+__device__ __forceinline__ void sti_store_pair_row(uint8_t* rowbase, int r7, int cidx, float v0, float v1) {
+  uint32_t hi, lo;
+  split_pair(v0, v1, hi, lo);
+  const int cc = cidx & 63;
+  uint8_t* dst = rowbase + ((size_t)(cidx >> 6) << 15) + ((((cc >> 3) ^ r7) << 4) + (cc & 7) * 2);
+  *reinterpret_cast<uint32_t*>(dst) = hi;
+  *reinterpret_cast<uint32_t*>(dst + 16384) = lo;
+}
+__device__ __forceinline__ uint8_t* sti_row_base(uint8_t* sti, int kbs, long long p) {
+  return sti + ((size_t)((p >> 7) * kbs) << 15) + (size_t)(p & 127) * 128;
+}
 // zero the channel padding [cfirst, kbs*64) of this window's 64 tokens (done by the last head's CTA)
 __device__ __forceinline__ void sti_zero_padding(uint8_t* sti, int kbs, const int* tok, int cfirst, int t) {
   const int pairs = (kbs * 64 - cfirst) / 2;
@@ -111,29 +123,36 @@ __device__ __forceinline__ void qk_scores(const __nv_bfloat16* Ah, const __nv_bf
   }
 }
 
-// bias + mask + softmax on the accumulator layout (rows row0+g and row0+g+8), in place -> P
-__device__ __forceinline__ void bias_mask_softmax(const AttnGeom& gm, const float* bias_s, const int* rid, int row0,
-                                                  int g, int tid, float (&acc)[8][4]) {
-  const bool masked = gm.use_mask && gm.shift > 0;
-  const int span = 2 * gm.ws - 1;
+// bias + mask + softmax on the accumulator layout (rows row0+g and row0+g+8), in place -> P.
+// ws == 8: token j = 8*jy + jx, so column j = 8*nt + 2*tid + e has jy = nt, jx = 2*tid + e and the
+// relative-position index (iy-jy+7)*15 + (ix-jx+7) = (15*iy + ix + 112 - 2*tid) - 15*nt - e: one
+// integer add per element.  `masked` is false for windows whose 64 tokens share one region id.
+__device__ __forceinline__ void bias_mask_softmax(const float* bias_s, const int* rid, bool masked, int row0, int g,
+                                                  int tid, float (&acc)[8][4]) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int i = row0 + g + 8 * h;
-    const int iy = i / gm.ws, ix = i - iy * gm.ws;
-    const int ri = rid[i];
+    const int base = 15 * (i >> 3) + (i & 7) + 112 - 2 * tid;
     float m = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = nt * 8 + tid * 2 + e;
-        const int jy = j / gm.ws, jx = j - jy * gm.ws;
-        float v = acc[nt][2 * h + e] + bias_s[(iy - jy + gm.ws - 1) * span + (ix - jx + gm.ws - 1)];
-        if (masked && ri != rid[j]) v += -100.0f;
+        const float v = acc[nt][2 * h + e] + bias_s[base - 15 * nt - e];
         acc[nt][2 * h + e] = v;
-        m = fmaxf(m, v);
       }
     }
+    if (masked) {
+      const int ri = rid[i];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int2 rj = *reinterpret_cast<const int2*>(&rid[nt * 8 + tid * 2]);
+        if (ri != rj.x) acc[nt][2 * h] += -100.0f;
+        if (ri != rj.y) acc[nt][2 * h + 1] += -100.0f;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) m = fmaxf(m, fmaxf(acc[nt][2 * h], acc[nt][2 * h + 1]));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
     float s = 0.f;
@@ -141,7 +160,7 @@ __device__ __forceinline__ void bias_mask_softmax(const AttnGeom& gm, const floa
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float ev = expf(acc[nt][2 * h + e] - m);
+        const float ev = __expf(acc[nt][2 * h + e] - m);
         acc[nt][2 * h + e] = ev;
         s += ev;
       }
@@ -187,10 +206,16 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
   __shared__ __align__(16) __nv_bfloat16 Qh[AM_N * AM_LD], Ql[AM_N * AM_LD], Kh[AM_N * AM_LD], Kl[AM_N * AM_LD];
   __shared__ __align__(16) __nv_bfloat16 Vth[32 * AM_LDT], Vtl[32 * AM_LDT];
   __shared__ float bias_s[225];
-  __shared__ int tok[AM_N], rid[AM_N];
+  __shared__ __align__(8) int tok[AM_N], rid[AM_N];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
   const int wi = blockIdx.x, head = blockIdx.y;
-  if (t < AM_N) attn_token_map(gm, wi, t, tok[t], rid[t]);
+  int differs = 0;
+  if (t < AM_N) {
+    attn_token_map(gm, wi, t, tok[t], rid[t]);
+    int t0, r0;
+    attn_token_map(gm, wi, 0, t0, r0);
+    differs = rid[t] != r0;
+  }
   for (int i = t; i < (2 * gm.ws - 1) * (2 * gm.ws - 1); i += AM_THREADS) bias_s[i] = table[i * gm.heads + head];
   // zero the d-padding (columns D..31) once
   for (int i = t; i < AM_N * AM_LD / 2; i += AM_THREADS) {
@@ -200,7 +225,7 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
   for (int i = t; i < 32 * AM_LDT / 2; i += AM_THREADS) {
     reinterpret_cast<uint32_t*>(Vth)[i] = 0; reinterpret_cast<uint32_t*>(Vtl)[i] = 0;
   }
-  __syncthreads();
+  const bool masked = __syncthreads_or(differs) && gm.use_mask && gm.shift > 0;
   const int hp = gm.D / 2;  // float2 pairs per token
   constexpr int LB = 4;     // loads are issued LB iterations at a time so 3*LB requests are in flight per thread
   for (int base = t; base < AM_N * hp; base += AM_THREADS * LB) {
@@ -239,7 +264,7 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
   const int row0 = warp * 16;
   float acc[8][4];
   qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, acc);
-  bias_mask_softmax(gm, bias_s, rid, row0, g, tid, acc);
+  bias_mask_softmax(bias_s, rid, masked, row0, g, tid, acc);
   float o[4][4];
   acc_times(acc, Vth, Vtl, g, tid, o);
 #pragma unroll
@@ -283,7 +308,7 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
   __nv_bfloat16* Kth = Qtl + BW_TT;       __nv_bfloat16* Ktl = Kth + BW_TT;
   __nv_bfloat16* Oth = Ktl + BW_TT;       __nv_bfloat16* Otl = Oth + BW_TT;
   __shared__ float bias_s[225];
-  __shared__ int tok[AM_N], rid[AM_N];
+  __shared__ __align__(8) int tok[AM_N], rid[AM_N];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
   const int head = blockIdx.y;
   const int row0 = warp * 16;
@@ -296,58 +321,67 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
 
   for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
     __syncthreads();  // previous window's phase-2 reads are done
-    if (t < AM_N) attn_token_map(gm, wi, t, tok[t], rid[t]);
+    int differs = 0;
+    if (t < AM_N) {
+      attn_token_map(gm, wi, t, tok[t], rid[t]);
+      int t0, r0;
+      attn_token_map(gm, wi, 0, t0, r0);
+      differs = rid[t] != r0;
+    }
     // zero the k-padding (columns D..31) of the eight [token][d] tiles (phase 2 aliased over them)
     for (int i = t; i < 8 * AM_N * ((32 - gm.D) / 2); i += AM_THREADS) {
       const int per_row = (32 - gm.D) / 2;
       const int cpair = i % per_row, rowt = i / per_row;  // rowt = tile * 64 + row
       *reinterpret_cast<uint32_t*>(&sm[rowt * AM_LD + gm.D + 2 * cpair]) = 0;
     }
-    __syncthreads();
+    const bool masked = __syncthreads_or(differs) && gm.use_mask && gm.shift > 0;
     constexpr int LB = 2;  // 8 independent 8-byte loads in flight per thread
-    for (int base = t; base < AM_N * hp; base += AM_THREADS * LB) {
-      float2 qv[LB], kv[LB], vv[LB], dv[LB];
+    {
+      const int n = t >> 1, pr0 = (t & 1) * 8;     // this thread's token and first channel pair (hp <= 16)
+      const float* qrow = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D;
+      const float* drow = dout + (size_t)tok[n] * gm.C + head * gm.D;
 #pragma unroll
-      for (int u = 0; u < LB; ++u) {
-        const int idx = base + u * AM_THREADS;
-        if (idx < AM_N * hp) {
-          const int n = idx / hp, pr = idx - n * hp;
-          const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
-          qv[u] = *reinterpret_cast<const float2*>(p);
-          kv[u] = *reinterpret_cast<const float2*>(p + gm.C);
-          vv[u] = *reinterpret_cast<const float2*>(p + 2 * gm.C);
-          dv[u] = *reinterpret_cast<const float2*>(dout + (size_t)tok[n] * gm.C + head * gm.D + 2 * pr);
+      for (int b0 = 0; b0 < 8; b0 += LB) {
+        float2 qv[LB], kv[LB], vv[LB], dv[LB];
+#pragma unroll
+        for (int u = 0; u < LB; ++u) {
+          const int pr = pr0 + b0 + u;
+          if (pr < hp) {
+            qv[u] = *reinterpret_cast<const float2*>(qrow + 2 * pr);
+            kv[u] = *reinterpret_cast<const float2*>(qrow + gm.C + 2 * pr);
+            vv[u] = *reinterpret_cast<const float2*>(qrow + 2 * gm.C + 2 * pr);
+            dv[u] = *reinterpret_cast<const float2*>(drow + 2 * pr);
+          }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < LB; ++u) {
-        const int idx = base + u * AM_THREADS;
-        if (idx >= AM_N * hp) break;
-        const int n = idx / hp, pr = idx - n * hp;
-        const float2 q = qv[u], k = kv[u], v = vv[u], dy = dv[u];
-        uint32_t hi, lo;
-        const int o1 = n * AM_LD + 2 * pr, t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
-        split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
-        *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
-        reinterpret_cast<uint16_t*>(Qth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Qth)[t1] = (uint16_t)(hi >> 16);
-        reinterpret_cast<uint16_t*>(Qtl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Qtl)[t1] = (uint16_t)(lo >> 16);
-        split_pair(k.x, k.y, hi, lo);
-        *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
-        reinterpret_cast<uint16_t*>(Kth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Kth)[t1] = (uint16_t)(hi >> 16);
-        reinterpret_cast<uint16_t*>(Ktl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ktl)[t1] = (uint16_t)(lo >> 16);
-        split_pair(v.x, v.y, hi, lo);
-        *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
-        split_pair(dy.x, dy.y, hi, lo);
-        *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
-        reinterpret_cast<uint16_t*>(Oth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Oth)[t1] = (uint16_t)(hi >> 16);
-        reinterpret_cast<uint16_t*>(Otl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Otl)[t1] = (uint16_t)(lo >> 16);
+        for (int u = 0; u < LB; ++u) {
+          const int pr = pr0 + b0 + u;
+          if (pr >= hp) break;
+          const float2 q = qv[u], k = kv[u], v = vv[u], dy = dv[u];
+          uint32_t hi, lo;
+          const int o1 = n * AM_LD + 2 * pr, t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
+          split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
+          *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
+          reinterpret_cast<uint16_t*>(Qth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Qth)[t1] = (uint16_t)(hi >> 16);
+          reinterpret_cast<uint16_t*>(Qtl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Qtl)[t1] = (uint16_t)(lo >> 16);
+          split_pair(k.x, k.y, hi, lo);
+          *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
+          reinterpret_cast<uint16_t*>(Kth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Kth)[t1] = (uint16_t)(hi >> 16);
+          reinterpret_cast<uint16_t*>(Ktl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ktl)[t1] = (uint16_t)(lo >> 16);
+          split_pair(v.x, v.y, hi, lo);
+          *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
+          split_pair(dy.x, dy.y, hi, lo);
+          *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
+          reinterpret_cast<uint16_t*>(Oth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Oth)[t1] = (uint16_t)(hi >> 16);
+          reinterpret_cast<uint16_t*>(Otl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Otl)[t1] = (uint16_t)(lo >> 16);
+        }
       }
     }
     __syncthreads();
     // ---- phase 1: P = softmax(Qs K^T + bias + mask); dP = dO V^T; dS = P o (dP - rowsum(P o dP))
     float pr_[8][4], ds[8][4];
     qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, pr_);
-    bias_mask_softmax(gm, bias_s, rid, row0, g, tid, pr_);
+    bias_mask_softmax(bias_s, rid, masked, row0, g, tid, pr_);
     qk_scores(Oh, Ol, Vh, Vl, row0, g, tid, ds);  // dP[i][j] = sum_d dO[i][d] V[j][d]
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -388,16 +422,24 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
     float o[4][4];
     acc_times(ds, Kth, Ktl, g, tid, o);
     const int kbs3 = (3 * gm.C + 63) / 64;
+    uint8_t* rb[2];
+    int r7[2];
+    long long tkk[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const long long tk = tok[row0 + g + 8 * h];
+      tkk[h] = tok[row0 + g + 8 * h];
+      rb[h] = dqkv_sti ? sti_row_base(dqkv_sti, kbs3, tkk[h]) : nullptr;
+      r7[h] = (int)(tkk[h] & 7);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int c = nt * 8 + tid * 2;
         if (c < gm.D) {
           const float v0 = o[nt][2 * h] * gm.scale, v1 = o[nt][2 * h + 1] * gm.scale;
-          if (dqkv) *reinterpret_cast<float2*>(dqkv + tk * 3 * gm.C + head * gm.D + c) = make_float2(v0, v1);
-          if (dqkv_sti) sti_store_pair(dqkv_sti, kbs3, tk, head * gm.D + c, v0, v1);
+          if (dqkv) *reinterpret_cast<float2*>(dqkv + tkk[h] * 3 * gm.C + head * gm.D + c) = make_float2(v0, v1);
+          if (dqkv_sti) sti_store_pair_row(rb[h], r7[h], head * gm.D + c, v0, v1);
         }
       }
     }
@@ -426,14 +468,13 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const long long tk = tok[row0 + g + 8 * h];
         const int cbase = (which == 0 ? gm.C : 2 * gm.C) + head * gm.D;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int c = nt * 8 + tid * 2;
           if (c < gm.D) {
-            if (dqkv) *reinterpret_cast<float2*>(dqkv + tk * 3 * gm.C + cbase + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
-            if (dqkv_sti) sti_store_pair(dqkv_sti, kbs3, tk, cbase + c, o[nt][2 * h], o[nt][2 * h + 1]);
+            if (dqkv) *reinterpret_cast<float2*>(dqkv + tkk[h] * 3 * gm.C + cbase + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
+            if (dqkv_sti) sti_store_pair_row(rb[h], r7[h], cbase + c, o[nt][2 * h], o[nt][2 * h + 1]);
           }
         }
       }
