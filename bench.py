@@ -168,7 +168,9 @@ def run_ours(args) -> None:
     from neosr_b200 import ops
     from neosr_b200.models import build_model
     B = args.batch
-    model = build_model(make_opt(B, world > 1, rank, world))
+    opt = make_opt(B, world > 1, rank, world)
+    opt["cuda_graph"] = not args.no_graph
+    model = build_model(opt)
     pool = synth_batches(args.pool, B, seed=1024 + rank)
     dev_pool = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in pool]
     torch.cuda.synchronize()
@@ -178,13 +180,17 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(loop, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for i in range(steps):
             loop(i)
         e1.record()
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / steps  # host time to ENQUEUE a step
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
@@ -212,16 +218,19 @@ def run_ours(args) -> None:
     sampler.start()
     l0 = ops.LAUNCHES
     ms = timed(step_resident, args.steps)
+    host_enqueue_ms = host_ms[0]
     launches = ops.LAUNCHES - l0
     ms_e2e = timed(step_e2e, args.steps)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
-    # one extra step with per-launch CUDA events: which kernel dominates, and its roofline
+    # one extra EAGER step with per-launch CUDA events: which kernel dominates, and its roofline
+    graph_mode, model._graph_mode = model._graph_mode, False
     ops.PROFILE = []
     step_resident(0)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
+    model._graph_mode = graph_mode
     agg: dict = {}
     for name, key, flops, nbytes, a, b in prof:
         r = agg.setdefault((name, key), {"ms": 0.0, "n": 0, "flops": flops, "bytes": nbytes})
@@ -277,7 +286,8 @@ def run_ours(args) -> None:
                 "clocks": sampler.summary(),
                 "e2e": {"value": crops / (ms_e2e * 1e-3), "unit": "crops/s", "h2d_bytes_per_step": bytes_in,
                         "d2h_bytes_per_step": 4 * 3, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches,
+                "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
+                "cuda_graph": bool(graph_mode and model._graphs is not None),
                 "roofline": roof,
                 "step_roofline": {"bound": "tensor", "achieved": step_tflops, "unit": "TFLOP/s",
                                   "peak": pk["bf16_sustained"], "frac": step_tflops / pk["bf16_sustained"],
@@ -299,6 +309,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=32, help="LR crops per GPU per step (C3: 32)")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

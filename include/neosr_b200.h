@@ -277,6 +277,10 @@ typedef struct NsrAdanSF {
  * max_norm <= 0).  Gradient buffers are left holding the clipped gradient, as in the reference. */
 int nsr_adan_sf_step(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
                      const NsrAdanSF* hp, const float* sumsq, void* stream);
+/* Same, with the scalars read from DEVICE memory (`hp_dev`): the launch can then sit inside a
+ * captured CUDA graph while the host refreshes the per-step scalars with one small async copy. */
+int nsr_adan_sf_step_dev(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
+                         const NsrAdanSF* hp_dev, const float* sumsq, void* stream);
 
 typedef struct NsrAdamW {
   float beta1, one_minus_beta1, beta2, one_minus_beta2;

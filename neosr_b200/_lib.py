@@ -103,6 +103,7 @@ SIGNATURES = {
     "nsr_grad_sumsq_workspace": (_z, []),
     "nsr_grad_sumsq": (_i, [_p, _i, _l, _p, _p, _p]),
     "nsr_adan_sf_step": (_i, [_p, _i, _l, C.POINTER(NsrAdanSF), _p, _p]),
+    "nsr_adan_sf_step_dev": (_i, [_p, _i, _l, _p, _p, _p]),
     "nsr_adamw_step": (_i, [_p, _i, _l, C.POINTER(NsrAdamW), _p, _p]),
 }
 

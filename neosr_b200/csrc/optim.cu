@@ -64,8 +64,10 @@ __device__ __forceinline__ float clip_coef(const float* sumsq, float max_norm) {
 }
 
 __global__ void __launch_bounds__(OPT_THREADS) adan_sf_kernel(const NsrParamEntry* __restrict__ tab, int n_tensors,
-                                                              long long total_chunks, NsrAdanSF hp,
+                                                              long long total_chunks, NsrAdanSF hp_val,
+                                                              const NsrAdanSF* __restrict__ hp_dev,
                                                               const float* __restrict__ sumsq) {
+  const NsrAdanSF hp = hp_dev ? *hp_dev : hp_val;
   const float clip = clip_coef(sumsq, hp.max_norm);
   for (long long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
     const int ti = find_tensor(tab, n_tensors, ch);
@@ -156,8 +158,16 @@ extern "C" int nsr_adan_sf_step(const NsrParamEntry* tab, int n_tensors, int64_t
                                 const float* sumsq, void* stream) {
   NSR_CHECK_ARG(tab && n_tensors > 0 && total_chunks > 0 && hp, "nsr_adan_sf_step: bad arguments");
   adan_sf_kernel<<<opt_blocks(total_chunks), OPT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tab, n_tensors, total_chunks, *hp, sumsq);
+      tab, n_tensors, total_chunks, *hp, nullptr, sumsq);
   NSR_CHECK_LAUNCH("adan_sf_step");
+  return NSR_OK;
+}
+extern "C" int nsr_adan_sf_step_dev(const NsrParamEntry* tab, int n_tensors, int64_t total_chunks, const NsrAdanSF* hp_dev,
+                                    const float* sumsq, void* stream) {
+  NSR_CHECK_ARG(tab && n_tensors > 0 && total_chunks > 0 && hp_dev, "nsr_adan_sf_step_dev: bad arguments");
+  adan_sf_kernel<<<opt_blocks(total_chunks), OPT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tab, n_tensors, total_chunks, NsrAdanSF{}, hp_dev, sumsq);
+  NSR_CHECK_LAUNCH("adan_sf_step_dev");
   return NSR_OK;
 }
 extern "C" int nsr_adamw_step(const NsrParamEntry* tab, int n_tensors, int64_t total_chunks, const NsrAdamW* hp,

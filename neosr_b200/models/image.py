@@ -49,6 +49,7 @@ class image:
         self.is_train = opt.get("is_train", True)
         self.optimizers: list = []
         self.schedulers: list = []
+        self._graph_mode = False
         self.log_dict: dict = {}
         set_default_scale(opt.get("scale", 4), self.is_train)
 
@@ -87,6 +88,15 @@ class image:
             raise NotImplementedError("neosr_b200.image: apply_augment (augmentations.py:219-310) not built yet")
         self.n_accumulated = 0
         self._ema_updates = 0  # host mirror of net_g_ema.n_averaged (avoids a device read per step)
+        self._ema_params = None
+        # CUDA-graph replay of the step (opt-out: `cuda_graph = false` in the option file); needs a
+        # deterministic launch sequence, i.e. no DropPath draws, and the device-scalar optimizer path
+        ng = self.opt["network_g"]
+        dp = float(ng.get("drop_path_rate", 0.1)) if "swinir" in ng.get("type", "") else 0.0
+        self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0
+                            and train_opt["optim_g"].get("type") in {"adan_sf", "Adan_SF"})
+        self._graphs, self._graph_logs, self._eager_steps = None, None, 0
+        self._lq_static = self._gt_static = None
         self.scale = self.opt.get("scale", 4)
         self.patch_size = ds.get("patch_size")
         self.gradclip = train_opt.get("grad_clip", True)
@@ -130,12 +140,26 @@ class image:
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
     def feed_data(self, data: dict) -> None:  # image.py:374-391
-        self.lq = data["lq"].to(self.device, non_blocking=True)
-        if "gt" in data:
-            self.gt = data["gt"].to(self.device, non_blocking=True)
+        lq, gt = data["lq"], data.get("gt")
+        if self._graph_mode:
+            # CUDA-graph replay needs fixed input addresses: copy the batch into static device buffers
+            if self._lq_static is None or self._lq_static.shape != lq.shape or (gt is not None and self._gt_static.shape != gt.shape):
+                self._lq_static = torch.empty(lq.shape, dtype=torch.float32, device=self.device)
+                self._gt_static = torch.empty(gt.shape, dtype=torch.float32, device=self.device) if gt is not None else None
+                self._graphs = None  # shapes changed: re-capture
+                self._eager_steps = 0
+            self._lq_static.copy_(lq, non_blocking=True)
+            if gt is not None:
+                self._gt_static.copy_(gt, non_blocking=True)
+            self.lq, self.gt = self._lq_static, self._gt_static
+            return
+        self.lq = lq.to(self.device, non_blocking=True)
+        if gt is not None:
+            self.gt = gt.to(self.device, non_blocking=True)
 
-    @torch.no_grad()
-    def optimize_parameters(self, current_iter: int) -> None:  # image.py:427-662
+    def _forward_backward(self) -> OrderedDict:
+        """G fprop -> fused loss value+grad kernels -> G backward into the flat gradient buffer.
+        Returns the loss scalars as device tensors (image.py:448-531)."""
         net = self.net_g
         ps = net.param_set()
         ps.ensure_grads(self.device)
@@ -154,19 +178,75 @@ class image:
             dout = g if dout is None else ops.axpby(dout, 1.0, g, 1.0, out=dout)
         logs["l_g_total"] = total
         net.engine_backward(saved, dout)
-        if self.dist and self.world_size > 1:
-            allreduce_mean_(ps.flat_grad)  # the one collective of the step (DDP-style gradient averaging)
-        ps.attach_grads()
-        ema = None
-        if self.ema > 0:
-            ema_params = [e.detach() for e, p in zip(self.net_g_ema.module.parameters(), net.parameters())
-                          if p.requires_grad]
-            ema = (ema_params, self.ema, self._ema_updates == 0)
-        self.optimizer_g.step(clip_max_norm=1.0 if self.gradclip else None, ema=ema)
+        return logs
+
+    def _ema_arg(self):
+        if self.ema <= 0:
+            return None
+        if self._ema_params is None:
+            self._ema_params = [e.detach() for e, p in zip(self.net_g_ema.module.parameters(), self.net_g.parameters())
+                                if p.requires_grad]
+        return (self._ema_params, self.ema, self._ema_updates == 0)
+
+    @torch.no_grad()
+    def optimize_parameters(self, current_iter: int) -> None:  # image.py:427-662
+        ps = self.net_g.param_set()
+        clip = 1.0 if self.gradclip else None
+        multi = self.dist and self.world_size > 1
+        if self._graph_mode and self._graphs is None and self._eager_steps >= 2:
+            self._capture_graphs(clip)
+        if self._graph_mode and self._graphs is not None:
+            g_fb, g_opt, n_fb, n_opt = self._graphs
+            g_fb.replay()
+            if multi:
+                allreduce_mean_(ps.flat_grad)
+            self.optimizer_g.prepare(clip_max_norm=clip, ema=self._ema_arg(), to_device=True)
+            g_opt.replay()
+            self.optimizer_g.bump_versions()
+            ops._count(n_fb + n_opt)
+            logs = self._graph_logs
+        else:
+            logs = self._forward_backward()
+            if multi:
+                allreduce_mean_(ps.flat_grad)  # the one collective of the step (DDP-style gradient averaging)
+            ps.attach_grads()
+            self.optimizer_g.step(clip_max_norm=clip, ema=self._ema_arg())
+            self._eager_steps += 1
         if self.ema > 0:
             self.net_g_ema.n_averaged += 1
             self._ema_updates += 1
         self._pending_logs = logs
+
+    def _capture_graphs(self, clip) -> None:
+        """Capture the step into two CUDA graphs (forward+loss+backward | grad-norm+optimizer+EMA) so the
+        ~2000 launches of a step cost no host time; the gradient all-reduce (N > 1) and the 72-byte
+        upload of the optimizer's per-step scalars stay between/around the replays."""
+        ps = self.net_g.param_set()
+        ps.invalidate_packed()  # the weight re-pack kernels must be part of the captured step
+        torch.cuda.synchronize()
+        l0 = ops.LAUNCHES
+        g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_fb):
+            self._graph_logs = self._forward_backward()
+        n_fb = ops.LAUNCHES - l0
+        ps.attach_grads()
+        # plan (tables, device-resident scalars) without advancing the schedule twice: prepare() is
+        # re-run before every replay, the capture only needs the launch sequence and stable pointers
+        saved = [dict(step=g.get("step"), weight_sum=g["weight_sum"], lr_max=g["lr_max"]) for g in self.optimizer_g.param_groups]
+        self.optimizer_g.prepare(clip_max_norm=clip, ema=self._ema_arg(), to_device=True)
+        for g, sv in zip(self.optimizer_g.param_groups, saved):
+            g["weight_sum"], g["lr_max"] = sv["weight_sum"], sv["lr_max"]
+            if sv["step"] is None:
+                g.pop("step", None)
+            else:
+                g["step"] = sv["step"]
+        torch.cuda.synchronize()
+        l0 = ops.LAUNCHES
+        g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_opt):
+            self.optimizer_g.launch()
+        n_opt = ops.LAUNCHES - l0
+        self._graphs = (g_fb, g_opt, n_fb, n_opt)
 
     def update_learning_rate(self, current_iter: int, warmup_iter: int = -1) -> None:  # base.py:229-254
         if current_iter > 0 and self.n_accumulated == 0:

@@ -45,6 +45,9 @@ class adan_sf(Optimizer):
         super().__init__(params, defaults)
         self._tables: dict = {}
         self._sumsq = None
+        self._hp_slots: dict = {}
+        self._plan: list = []
+        self._clip = 0.0
 
     def __setstate__(self, state) -> None:
         super().__setstate__(state)
@@ -78,20 +81,16 @@ class adan_sf(Optimizer):
         t = self._tables.setdefault("norm", ParamTable())
         return t.build(rows)
 
+    # ---------------------------------------------------------------------------------------
+    # step() = prepare() (host: advance the schedule, derive the scalars exactly where the reference
+    # does, adan_sf.py:176-211/289-330) + launch() (device: grad-norm + ONE fused kernel).  In
+    # CUDA-graph mode the model calls prepare(..., to_device=True) every iteration (a 72-byte async
+    # copy) and replays a graph that contains launch().
     @torch.no_grad()
-    def step(self, closure=None, *, clip_max_norm: float | None = None, ema=None):
-        """ema = (list of EMA tensors aligned with this optimizer's params-with-grad, decay, first: bool)."""
-        loss = closure() if closure is not None else 0.0
-        L = _lib.lib()
-        sumsq_ptr = None
-        if clip_max_norm is not None and clip_max_norm > 0:
-            tab = self._all_grads_table()
-            if tab.n:
-                if self._sumsq is None or self._sumsq.device != tab.dev.device:
-                    self._sumsq = torch.zeros(1, dtype=torch.float32, device=tab.dev.device)
-                grad_sumsq(tab, self._sumsq)
-                sumsq_ptr = self._sumsq.data_ptr()
+    def prepare(self, *, clip_max_norm: float | None = None, ema=None, to_device: bool = False) -> None:
         ema_iter = iter(ema[0]) if ema is not None else None
+        self._plan = []
+        self._clip = float(clip_max_norm or 0.0)
         for gi, group in enumerate(self.param_groups):
             beta1, beta2, beta3 = group["betas"]
             group["step"] = group["step"] + 1 if "step" in group else 1
@@ -144,11 +143,59 @@ class adan_sf(Optimizer):
                            beta3=beta3, one_minus_beta3=1 - beta3, bias_correction3_sqrt=math.sqrt(bc3),
                            eps=group["eps"], decay=1 - lr * group["weight_decay"], ckp1=ckp1, step_size=step_size,
                            step_size_diff=step_size_diff, lr=lr, schedule_free=int(sf), first_step=int(step == 1),
-                           max_norm=float(clip_max_norm or 0.0),
+                           max_norm=self._clip,
                            ema_lerp=float(1.0 - ema[1]) if ema is not None else 0.0,
                            ema_first=int(bool(ema[2])) if ema is not None else 0)
-            _lib.check(L.nsr_adan_sf_step(tab.dev.data_ptr(), tab.n, tab.chunks, C.byref(hp), sumsq_ptr, _stream()),
-                       "nsr_adan_sf_step")
+            hp_dev = None
+            if to_device:
+                # ring of pinned staging buffers: the host may run several steps ahead of the GPU, so a
+                # slot is reused only after the async copy that read it has completed
+                ring = self._hp_slots.get(gi)
+                if ring is None:
+                    n = C.sizeof(NsrAdanSF)
+                    ring = self._hp_slots[gi] = {"dev": torch.zeros(n, dtype=torch.uint8, device=tab.dev.device),
+                                                 "host": [torch.zeros(n, dtype=torch.uint8).pin_memory() for _ in range(4)],
+                                                 "ev": [None] * 4, "i": 0}
+                i = ring["i"]
+                if ring["ev"][i] is not None:
+                    ring["ev"][i].synchronize()
+                C.memmove(ring["host"][i].data_ptr(), C.addressof(hp), C.sizeof(NsrAdanSF))
+                ring["dev"].copy_(ring["host"][i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                ring["ev"][i], ring["i"] = ev, (i + 1) % 4
+                hp_dev = ring["dev"]
+            self._plan.append((tab, hp, hp_dev, [r["p"] for r in rows]))
+
+    @torch.no_grad()
+    def launch(self) -> None:
+        L = _lib.lib()
+        sumsq_ptr = None
+        if self._clip > 0:
+            tab = self._all_grads_table()
+            if tab.n:
+                if self._sumsq is None or self._sumsq.device != tab.dev.device:
+                    self._sumsq = torch.zeros(1, dtype=torch.float32, device=tab.dev.device)
+                grad_sumsq(tab, self._sumsq)
+                sumsq_ptr = self._sumsq.data_ptr()
+        for tab, hp, hp_dev, params in self._plan:
+            if hp_dev is not None:
+                _lib.check(L.nsr_adan_sf_step_dev(tab.dev.data_ptr(), tab.n, tab.chunks, hp_dev.data_ptr(), sumsq_ptr,
+                                                  _stream()), "nsr_adan_sf_step_dev")
+            else:
+                _lib.check(L.nsr_adan_sf_step(tab.dev.data_ptr(), tab.n, tab.chunks, C.byref(hp), sumsq_ptr, _stream()),
+                           "nsr_adan_sf_step")
             ops_mod._count(1)
-            torch.autograd.graph.increment_version([r["p"] for r in rows])
+
+    def bump_versions(self) -> None:
+        for _, _, _, params in self._plan:
+            torch.autograd.graph.increment_version(params)
+
+    @torch.no_grad()
+    def step(self, closure=None, *, clip_max_norm: float | None = None, ema=None):
+        """ema = (list of EMA tensors aligned with this optimizer's params-with-grad, decay, first: bool)."""
+        loss = closure() if closure is not None else 0.0
+        self.prepare(clip_max_norm=clip_max_norm, ema=ema)
+        self.launch()
+        self.bump_versions()
         return loss
