@@ -318,6 +318,15 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) dacc[nt][0] = dacc[nt][1] = dacc[nt][2] = dacc[nt][3] = 0.f;
   const int hp = gm.D / 2;
+  // (token, channel pair) of this thread's <= 8 load iterations: fixed for the whole kernel, so the
+  // divisions are paid once; lanes stay on consecutive pairs of one token (coalesced 120-byte rows)
+  int nidx[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int idx = t + u * AM_THREADS;
+    const int n = idx < AM_N * hp ? idx / hp : AM_N;
+    nidx[u] = (n << 8) | (idx - n * hp < 0 ? 0 : (idx - n * hp) & 255);
+  }
 
   for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
     __syncthreads();  // previous window's phase-2 reads are done
@@ -336,45 +345,41 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
     }
     const bool masked = __syncthreads_or(differs) && gm.use_mask && gm.shift > 0;
     constexpr int LB = 2;  // 8 independent 8-byte loads in flight per thread
-    {
-      const int n = t >> 1, pr0 = (t & 1) * 8;     // this thread's token and first channel pair (hp <= 16)
-      const float* qrow = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D;
-      const float* drow = dout + (size_t)tok[n] * gm.C + head * gm.D;
 #pragma unroll
-      for (int b0 = 0; b0 < 8; b0 += LB) {
-        float2 qv[LB], kv[LB], vv[LB], dv[LB];
+    for (int b0 = 0; b0 < 8; b0 += LB) {
+      float2 qv[LB], kv[LB], vv[LB], dv[LB];
 #pragma unroll
-        for (int u = 0; u < LB; ++u) {
-          const int pr = pr0 + b0 + u;
-          if (pr < hp) {
-            qv[u] = *reinterpret_cast<const float2*>(qrow + 2 * pr);
-            kv[u] = *reinterpret_cast<const float2*>(qrow + gm.C + 2 * pr);
-            vv[u] = *reinterpret_cast<const float2*>(qrow + 2 * gm.C + 2 * pr);
-            dv[u] = *reinterpret_cast<const float2*>(drow + 2 * pr);
-          }
+      for (int u = 0; u < LB; ++u) {
+        const int n = nidx[b0 + u] >> 8, pr = nidx[b0 + u] & 255;  // consecutive lanes -> consecutive pairs of a token
+        if (n < AM_N) {
+          const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
+          qv[u] = *reinterpret_cast<const float2*>(p);
+          kv[u] = *reinterpret_cast<const float2*>(p + gm.C);
+          vv[u] = *reinterpret_cast<const float2*>(p + 2 * gm.C);
+          dv[u] = *reinterpret_cast<const float2*>(dout + (size_t)tok[n] * gm.C + head * gm.D + 2 * pr);
         }
+      }
 #pragma unroll
-        for (int u = 0; u < LB; ++u) {
-          const int pr = pr0 + b0 + u;
-          if (pr >= hp) break;
-          const float2 q = qv[u], k = kv[u], v = vv[u], dy = dv[u];
-          uint32_t hi, lo;
-          const int o1 = n * AM_LD + 2 * pr, t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
-          split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
-          *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
-          reinterpret_cast<uint16_t*>(Qth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Qth)[t1] = (uint16_t)(hi >> 16);
-          reinterpret_cast<uint16_t*>(Qtl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Qtl)[t1] = (uint16_t)(lo >> 16);
-          split_pair(k.x, k.y, hi, lo);
-          *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
-          reinterpret_cast<uint16_t*>(Kth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Kth)[t1] = (uint16_t)(hi >> 16);
-          reinterpret_cast<uint16_t*>(Ktl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ktl)[t1] = (uint16_t)(lo >> 16);
-          split_pair(v.x, v.y, hi, lo);
-          *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
-          split_pair(dy.x, dy.y, hi, lo);
-          *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
-          reinterpret_cast<uint16_t*>(Oth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Oth)[t1] = (uint16_t)(hi >> 16);
-          reinterpret_cast<uint16_t*>(Otl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Otl)[t1] = (uint16_t)(lo >> 16);
-        }
+      for (int u = 0; u < LB; ++u) {
+        const int n = nidx[b0 + u] >> 8, pr = nidx[b0 + u] & 255;
+        if (n >= AM_N) continue;
+        const float2 q = qv[u], k = kv[u], v = vv[u], dy = dv[u];
+        uint32_t hi, lo;
+        const int o1 = n * AM_LD + 2 * pr, t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
+        split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
+        reinterpret_cast<uint16_t*>(Qth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Qth)[t1] = (uint16_t)(hi >> 16);
+        reinterpret_cast<uint16_t*>(Qtl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Qtl)[t1] = (uint16_t)(lo >> 16);
+        split_pair(k.x, k.y, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
+        reinterpret_cast<uint16_t*>(Kth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Kth)[t1] = (uint16_t)(hi >> 16);
+        reinterpret_cast<uint16_t*>(Ktl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ktl)[t1] = (uint16_t)(lo >> 16);
+        split_pair(v.x, v.y, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
+        split_pair(dy.x, dy.y, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
+        reinterpret_cast<uint16_t*>(Oth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Oth)[t1] = (uint16_t)(hi >> 16);
+        reinterpret_cast<uint16_t*>(Otl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Otl)[t1] = (uint16_t)(lo >> 16);
       }
     }
     __syncthreads();
