@@ -174,6 +174,16 @@ int nsr_maxpool2_nhwc(const float* x, float* y, int batch, int h, int w, int c, 
 int nsr_maxpool2_relu_bwd_nhwc(const float* x, const float* dy, const float* dextra, float* dx,
                                int batch, int h, int w, int c, void* stream);
 
+/* nn.PReLU(C) backward on NHWC (compact_arch.py:52-70): dx = dy * (pre > 0 ? 1 : slope[c]),
+ * dslope[c] = sum_rows dy * min(pre, 0); deterministic two-pass reduction via workspace. */
+size_t nsr_prelu_bwd_workspace(int c);
+int nsr_prelu_bwd(const float* dy, const float* pre, const float* slope, float* dx, float* dslope,
+                  long long rows, int c, void* workspace, size_t workspace_bytes, void* stream);
+/* y_nchw[b,c,Y,X] = x_nhwc[b,Y,X,c] + base_nchw[b,c,Y/s,X/s]: the `out += F.interpolate(x, scale, "nearest")`
+ * skip of compact_arch.py:80-84 fused with the NHWC->NCHW output transpose (C <= 4). */
+int nsr_nhwc_to_nchw_add_nearest(const float* x, const float* base, float* y, int batch, int c, int h, int w,
+                                 int scale, void* stream);
+
 /* y = a * alpha + b * beta (b may be NULL). Gradient accumulation glue. */
 int nsr_axpby(const float* a, float alpha, const float* b, float beta, float* y, size_t n, void* stream);
 /* dx = dy * act'(aux) + (dextra ? dextra : 0) */

@@ -86,6 +86,9 @@ SIGNATURES = {
     "nsr_maxpool2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "nsr_maxpool2_relu_bwd_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "nsr_axpby": (_i, [_p, _f, _p, _f, _p, _z, _p]),
+    "nsr_prelu_bwd_workspace": (_z, [_i]),
+    "nsr_prelu_bwd": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _p, _z, _p]),
+    "nsr_nhwc_to_nchw_add_nearest": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "nsr_actgrad_mul": (_i, [_p, _p, _p, _p, _z, _i, _f, _p]),
     "nsr_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _p]),
     "nsr_sti_bytes": (_z, [C.c_longlong, _i]),

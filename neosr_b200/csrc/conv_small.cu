@@ -144,7 +144,8 @@ template <int NARROW>
 __global__ void __launch_bounds__(CS_WARPS * 32) conv_narrow2wide(const float* __restrict__ x,
                                                                  const float* __restrict__ w,
                                                                  const float* __restrict__ bias, float* __restrict__ y,
-                                                                 SmallGeom g, int act, float slope) {
+                                                                 SmallGeom g, int act, float slope,
+                                                                 const float* __restrict__ prelu, float* __restrict__ y_pre) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int taps = g.kh * g.kw;
   const int groups = (g.wide + 63) / 64;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(CS_WARPS * 32) conv_narrow2wide(const float* _
         wr[t][ci][1] = (t < taps && c1) ? w[((size_t)(c + 1) * taps + t) * NARROW + ci] : 0.f;
       }
     const float b0 = (bias && c0) ? bias[c] : 0.f, b1 = (bias && c1) ? bias[c + 1] : 0.f;
+    const float s0 = (act == NSR_ACT_PRELU && c0) ? prelu[c] : slope, s1 = (act == NSR_ACT_PRELU && c1) ? prelu[c + 1] : slope;
     for (long long p = (long long)blockIdx.x * CS_WARPS + warp; p < g.M; p += nwarps) {
       int oh, ow;
       pix_decode(p, g.H, g.W, oh, ow);
@@ -179,7 +181,11 @@ __global__ void __launch_bounds__(CS_WARPS * 32) conv_narrow2wide(const float* _
           a1 = fmaf(v, wr[t][ci][1], a1);
         }
       }
-      if (act) { a0 = apply_act(a0, act, slope); a1 = apply_act(a1, act, slope); }
+      if (y_pre) {
+        if (c0) y_pre[p * g.y_ld + c] = a0;
+        if (c1) y_pre[p * g.y_ld + c + 1] = a1;
+      }
+      if (act) { a0 = apply_act(a0, act, s0); a1 = apply_act(a1, act, s1); }
       float* yp = y + p * g.y_ld + c;
       if (c1 && (g.y_ld % 2 == 0)) *reinterpret_cast<float2*>(yp) = make_float2(a0, a1);
       else { if (c0) yp[0] = a0; if (c1) yp[1] = a1; }
@@ -261,8 +267,8 @@ constexpr int CS_WGRAD_BLOCKS = kNumSMs * 4;
 bool conv_small_fprop_supported(const NsrConv& d) {
   if (d.x == nullptr || d.y == nullptr || d.y_sti || d.x_sti) return false;
   if (d.kh * d.kw > CS_MAXTAPS) return false;
-  if (d.actgrad || d.residual || d.row_scale || d.y_pre || d.act == NSR_ACT_PRELU || d.act == NSR_ACT_GELU) return false;
-  if (d.cout <= 4 && d.cout >= 3 && d.cin % 64 == 0 && d.x_ld % 2 == 0 && d.act == NSR_ACT_NONE) return true;
+  if (d.actgrad || d.residual || d.row_scale || d.act == NSR_ACT_GELU || d.pre_mode) return false;
+  if (d.cout <= 4 && d.cout >= 3 && d.cin % 64 == 0 && d.x_ld % 2 == 0 && d.act == NSR_ACT_NONE && !d.y_pre) return true;
   if (d.cin <= 4 && d.cin >= 3 && d.cout >= 16) return true;
   return false;
 }
@@ -279,8 +285,8 @@ int conv_small_fprop(const NsrConv& d, cudaStream_t st) {
     else conv_wide2narrow<4><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g);
   } else {
     g.wide = d.cout; g.narrow = d.cin;
-    if (d.cin == 3) conv_narrow2wide<3><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g, d.act, d.act_slope);
-    else conv_narrow2wide<4><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g, d.act, d.act_slope);
+    if (d.cin == 3) conv_narrow2wide<3><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g, d.act, d.act_slope, d.prelu, d.y_pre);
+    else conv_narrow2wide<4><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g, d.act, d.act_slope, d.prelu, d.y_pre);
   }
   NSR_CHECK_LAUNCH("conv_small_fprop");
   return NSR_OK;

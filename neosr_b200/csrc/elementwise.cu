@@ -144,8 +144,97 @@ __global__ void actgrad_mul_kernel(const float* __restrict__ dy, const float* __
     dx[i] = dy[i] * act_grad(aux[i], act, slope) + (dextra ? dextra[i] : 0.f);
 }
 
+// PReLU backward on NHWC [rows, C]: dx = dy * (pre > 0 ? 1 : slope[c]); dslope[c] = sum_rows dy * min(pre, 0).
+// blockDim = (64 column quads, 4 row lanes) like the bias-gradient column sum; deterministic two-pass.
+__global__ void __launch_bounds__(256) prelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
+                                                        const float* __restrict__ slope, float* __restrict__ dx,
+                                                        float* __restrict__ partial, long long rows, int C) {
+  __shared__ float4 red[4][64];
+  const int c = (blockIdx.x * 64 + threadIdx.x) * 4;
+  const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * rows_per;
+  long long r1 = r0 + rows_per;
+  if (r1 > rows) r1 = rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    const float4 sl = *reinterpret_cast<const float4*>(slope + c);
+    for (long long r = r0 + threadIdx.y; r < r1; r += 4) {
+      const float4 g = *reinterpret_cast<const float4*>(dy + r * C + c);
+      const float4 x = *reinterpret_cast<const float4*>(pre + r * C + c);
+      float4 o;
+      o.x = g.x * (x.x > 0.f ? 1.f : sl.x); o.y = g.y * (x.y > 0.f ? 1.f : sl.y);
+      o.z = g.z * (x.z > 0.f ? 1.f : sl.z); o.w = g.w * (x.w > 0.f ? 1.f : sl.w);
+      *reinterpret_cast<float4*>(dx + r * C + c) = o;
+      acc.x += g.x * fminf(x.x, 0.f); acc.y += g.y * fminf(x.y, 0.f);
+      acc.z += g.z * fminf(x.z, 0.f); acc.w += g.w * fminf(x.w, 0.f);
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float4 s = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float4 o = red[k][threadIdx.x];
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * C + c) = s;
+  }
+}
+__global__ void prelu_bwd_final(const float* __restrict__ partial, float* __restrict__ dslope, int blocks, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * C + c];
+  dslope[c] = s;
+}
+
+// y_nchw[b,c,Y,X] = x_nhwc[b,Y,X,c] + base_nchw[b,c,Y/s,X/s]  (compact_arch.py:80-84: pixel-shuffled
+// residual + nearest-upsampled input); C <= 4.
+__global__ void nhwc_to_nchw_add_nearest(const float* __restrict__ x, const float* __restrict__ base,
+                                         float* __restrict__ y, int B, int C, int H, int W, int s) {
+  const size_t total = (size_t)B * H * W;
+  const int h0 = H / s, w0 = W / s;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W);
+    const size_t q = i / W;
+    const int Y = (int)(q % H);
+    const size_t b = q / H;
+    for (int c = 0; c < C; ++c)
+      y[((b * C + c) * H + Y) * W + X] = x[i * C + c] + base[((b * C + c) * h0 + Y / s) * w0 + X / s];
+  }
+}
+
 }  // namespace nsr
 using namespace nsr;
+
+extern "C" size_t nsr_prelu_bwd_workspace(int c) { return (size_t)kNumSMs * 4 * c * sizeof(float); }
+extern "C" int nsr_prelu_bwd(const float* dy, const float* pre, const float* slope, float* dx, float* dslope,
+                             long long rows, int c, void* workspace, size_t workspace_bytes, void* stream) {
+  NSR_CHECK_ARG(dy && pre && slope && dx && dslope && rows > 0 && c > 0 && c % 4 == 0, "nsr_prelu_bwd: bad arguments (C % 4 == 0)");
+  if (!workspace || workspace_bytes < nsr_prelu_bwd_workspace(c)) {
+    set_error("nsr_prelu_bwd: workspace too small");
+    return NSR_E_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int by = (int)((rows + 255) / 256);
+  if (by > kNumSMs * 4) by = kNumSMs * 4;
+  dim3 grid((unsigned)ceil_div(c, 256), (unsigned)by), block(64, 4);
+  prelu_bwd_kernel<<<grid, block, 0, st>>>(dy, pre, slope, dx, reinterpret_cast<float*>(workspace), rows, c);
+  NSR_CHECK_LAUNCH("prelu_bwd");
+  prelu_bwd_final<<<ceil_div(c, 128), 128, 0, st>>>(reinterpret_cast<const float*>(workspace), dslope, by, c);
+  NSR_CHECK_LAUNCH("prelu_bwd_final");
+  return NSR_OK;
+}
+extern "C" int nsr_nhwc_to_nchw_add_nearest(const float* x, const float* base, float* y, int B, int C, int H, int W,
+                                             int scale, void* stream) {
+  NSR_CHECK_ARG(x && base && y && B > 0 && C > 0 && C <= 4 && H > 0 && W > 0 && scale > 0 && H % scale == 0 && W % scale == 0,
+                "nsr_nhwc_to_nchw_add_nearest: bad arguments");
+  const size_t n = (size_t)B * H * W;
+  nhwc_to_nchw_add_nearest<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, base, y, B, C, H, W, scale);
+  NSR_CHECK_LAUNCH("nhwc_to_nchw_add_nearest");
+  return NSR_OK;
+}
 
 static int layout_affine(const float* x, float* y, int B, int C, int H, int W, const float* scale, const float* shift,
                          int to_nhwc, cudaStream_t st) {

@@ -206,9 +206,17 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const float
   for (int i = t; i < WA_N * WA_N; i += WA_THREADS) outp[i] = Acc[i];
 }
 
-// dtable[tidx, head] = sum over CTA partials and over (i,j) with rel_index(i,j) == tidx.
-__global__ void window_attn_dbias_kernel(const float* __restrict__ partial, float* __restrict__ dtable, int gx,
-                                         int heads, int ws) {
+// Bias-table gradient, two deterministic passes:
+//  (1) dS_sum[head][i][j] = sum over CTA partials (one thread per element, coalesced over j)
+//  (2) dtable[tidx, head] = sum of dS_sum over the (i, j) pairs with rel_index(i, j) == tidx
+__global__ void window_attn_dbias_sum(const float* __restrict__ partial, float* __restrict__ dssum, int gx, int heads) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // head * N*N + i*N + j
+  if (e >= heads * WA_N * WA_N) return;
+  float s = 0.f;
+  for (int b = 0; b < gx; ++b) s += partial[(size_t)b * heads * WA_N * WA_N + e];
+  dssum[e] = s;
+}
+__global__ void window_attn_dbias_kernel(const float* __restrict__ dssum, float* __restrict__ dtable, int heads, int ws) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   const int span = 2 * ws - 1;
   if (id >= span * span * heads) return;
@@ -222,7 +230,7 @@ __global__ void window_attn_dbias_kernel(const float* __restrict__ partial, floa
       const int ix = jx + dx;
       if (ix < 0 || ix >= ws) continue;
       const int i = iy * ws + ix, j = jy * ws + jx;
-      for (int b = 0; b < gx; ++b) s += partial[((size_t)b * heads + head) * WA_N * WA_N + i * WA_N + j];
+      s += dssum[(size_t)head * WA_N * WA_N + i * WA_N + j];
     }
   }
   dtable[tidx * heads + head] = s;
@@ -281,7 +289,7 @@ extern "C" int nsr_window_attn_fwd(const float* qkv, const float* bias_table, fl
 
 extern "C" size_t nsr_window_attn_bwd_workspace(int heads, int ws) {
   (void)ws;
-  return (size_t)(3 * kNumSMs + (heads > 0 ? heads : 1)) * WA_N * WA_N * sizeof(float);
+  return (size_t)(3 * kNumSMs + 2 * (heads > 0 ? heads : 1)) * WA_N * WA_N * sizeof(float);
 }
 
 extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv,
@@ -295,7 +303,7 @@ extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, co
   const int nwin = batch * g.nwh * g.nww;
   const bool mma = use_mma(c, heads, ws);
   const int gx = bwd_gx(nwin, heads, mma);
-  const size_t need = (size_t)gx * heads * WA_N * WA_N * sizeof(float);
+  const size_t need = (size_t)(gx + 1) * heads * WA_N * WA_N * sizeof(float);
   if (!workspace || workspace_bytes < need) {
     set_error("nsr_window_attn_bwd: workspace %zu < %zu", workspace_bytes, need);
     return NSR_E_WORKSPACE;
@@ -326,8 +334,11 @@ extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, co
       if (rc) return rc;
     }
   }
+  float* dssum = partial + (size_t)gx * heads * WA_N * WA_N;  // the workspace has `heads` spare tiles after the partials
+  window_attn_dbias_sum<<<ceil_div(heads * WA_N * WA_N, 256), 256, 0, st>>>(partial, dssum, gx, heads);
+  NSR_CHECK_LAUNCH("window_attn_dbias_sum");
   const int n = (2 * ws - 1) * (2 * ws - 1) * heads;
-  window_attn_dbias_kernel<<<ceil_div(n, 128), 128, 0, st>>>(partial, dbias_table, gx, heads, ws);
+  window_attn_dbias_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dssum, dbias_table, heads, ws);
   NSR_CHECK_LAUNCH("window_attn_dbias");
   return NSR_OK;
 }

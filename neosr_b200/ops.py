@@ -308,6 +308,33 @@ def axpby(a: Tensor, alpha: float, b: Tensor | None, beta: float, out: Tensor | 
     return y
 
 
+def prelu_bwd(dy: Tensor, pre: Tensor, slope: Tensor, dslope: Tensor) -> Tensor:
+    """dx = dy * prelu'(pre); dslope (overwritten) = sum dy * min(pre, 0)."""
+    _chk(dy, "dy"), _chk(pre, "pre"), _chk(slope, "slope"), _chk(dslope, "dslope")
+    c = dy.shape[-1]
+    rows = dy.numel() // c
+    dx = torch.empty_like(dy)
+    L = _lib.lib()
+    ws = scratch(L.nsr_prelu_bwd_workspace(c), dy.device)
+    with _prof("nsr_prelu_bwd", (rows, c), 0.0, 12.0 * dy.numel()):
+        check(L.nsr_prelu_bwd(dy.data_ptr(), pre.data_ptr(), slope.data_ptr(), dx.data_ptr(), dslope.data_ptr(), rows, c,
+                              ws.data_ptr(), ws.numel(), _stream()), "nsr_prelu_bwd")
+    _count(2)
+    return dx
+
+
+def nhwc_to_nchw_add_nearest(x: Tensor, base: Tensor, scale: int) -> Tensor:
+    """[B,H,W,C] NHWC + nearest-upsampled NCHW base [B,C,H/s,W/s] -> NCHW [B,C,H,W]."""
+    _chk(x, "x"), _chk(base, "base")
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    with _prof("nsr_nhwc_to_nchw_add_nearest", (x.numel(),), 0.0, 8.0 * x.numel()):
+        check(_lib.lib().nsr_nhwc_to_nchw_add_nearest(x.data_ptr(), base.data_ptr(), y.data_ptr(), B, Cc, H, W, scale,
+                                                      _stream()), "nsr_nhwc_to_nchw_add_nearest")
+    _count(1)
+    return y
+
+
 def actgrad_mul(dy: Tensor, aux: Tensor, act: str, slope: float = 0.0, dextra: Tensor | None = None) -> Tensor:
     _chk(dy, "dy"), _chk(aux, "aux"), _chk(dextra, "dextra")
     dx = torch.empty_like(dy)

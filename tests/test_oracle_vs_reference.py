@@ -94,3 +94,21 @@ def test_perceptual_and_step():
     sd = model.optimizer_g.state_dict()
     assert set(sd["state"][0]) == {"exp_avg", "exp_avg_sq", "exp_avg_diff", "z", "neg_pre_grad"}
     assert abs(sd["param_groups"][0]["weight_sum"] - tr.opt.weight_sum) < 1e-12
+
+
+def test_compact_forward_backward():
+    from oracle.compact import compact_forward, compact_param_shapes
+    ref_shim.activate(4)
+    net = ref_shim.build_network({"type": "compact", "upscale": 2, "num_conv": 4, "num_feat": 32})
+    shapes = compact_param_shapes(num_feat=32, num_conv=4, upscale=2)
+    assert {k: tuple(v.shape) for k, v in net.named_parameters()} == shapes
+    p = synth_params(shapes, seed=7)
+    net.load_state_dict(p)
+    x = torch.rand(2, 3, 16, 24, generator=torch.Generator().manual_seed(8))
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y, y_ref = compact_forward(pr, x, num_conv=4, upscale=2), net(x)
+    assert _rel(y, y_ref) < 1e-5
+    (y_ref ** 2).mean().backward()
+    g = torch.autograd.grad((y ** 2).mean(), list(pr.values()))
+    for (k, v), gi in zip(net.named_parameters(), g):
+        assert _rel(gi, v.grad) < 1e-4, k

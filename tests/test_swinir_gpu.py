@@ -125,3 +125,61 @@ def test_tiny_step3_vs_golden():
         assert rel(v.detach(), z[f"param.{k}"]) < 1e-3, k
     for k, v in model.net_g_ema.module.named_parameters():
         assert rel(v.detach(), z[f"ema.{k}"]) < 1e-3, k
+
+
+@pytest.mark.parametrize("act_type", ["prelu", "leakyrelu"])
+def test_compact_forward_backward_vs_oracle(act_type):
+    """C1 generator (SRVGGNetCompact): forward and every parameter gradient vs the oracle."""
+    from neosr_b200.archs import build_network
+    from oracle.compact import compact_forward, compact_param_shapes
+    from oracle.swinir import synth_params
+    shapes = compact_param_shapes(num_feat=64, num_conv=3, upscale=2, act_type=act_type)
+    p = synth_params(shapes, seed=7)
+    net = build_network({"type": "compact", "upscale": 2, "num_conv": 3, "act_type": act_type})
+    net.load_state_dict(p)
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(4, 3, 32, 32, generator=g)
+    gt = torch.rand(4, 3, 64, 64, generator=g)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y_ref = compact_forward(pr, x, num_conv=3, upscale=2, act_type=act_type)
+    grads = torch.autograd.grad(((y_ref - gt) ** 2).mean(), list(pr.values()))
+    y = net(x.cuda())
+    assert rel(y.detach(), y_ref.detach()) < 1e-4
+    ((y - gt.cuda()) ** 2).mean().backward()
+    for (k, v), gi in zip(net.named_parameters(), grads):
+        assert rel(v.grad, gi) < 1e-3, k
+
+
+def test_compact_c1_training_steps_vs_oracle():
+    """C1: compact x2, B=4, 32->64, L1 only, adan_sf + EMA: 4 steps of the `image` model vs the oracle trainer
+    (the last two replayed from the captured CUDA graphs)."""
+    from neosr_b200.models import build_model
+    from oracle.compact import compact_forward, compact_param_shapes
+    from oracle.make_golden import OPTIM
+    from oracle.step import OracleTrainer
+    from oracle.swinir import synth_params
+    opt = {"model_type": "image", "scale": 2, "is_train": True, "dist": False, "rank": 0, "world_size": 1,
+           "network_g": {"type": "compact", "upscale": 2}, "datasets": {"train": {"patch_size": 32}},
+           "train": {"ema": 0.999, "grad_clip": False, "optim_g": {"type": "adan_sf", **OPTIM},
+                     "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0}}, "path": {}}
+    model = build_model(opt)
+    p = synth_params(compact_param_shapes(upscale=2), seed=9)
+    model.net_g.load_state_dict(p)
+    tr = OracleTrainer(p, lambda q, x: compact_forward(q, x, upscale=2), pixel_weight=1.0, optim=OPTIM, ema=0.999,
+                       grad_clip=False)
+    g = torch.Generator().manual_seed(10)
+    for it in range(4):
+        lq, gt = torch.rand(4, 3, 32, 32, generator=g), torch.rand(4, 3, 64, 64, generator=g)
+        model.feed_data({"lq": lq, "gt": gt})
+        model.optimize_parameters(it)
+        tr.feed_data({"lq": lq, "gt": gt})
+        tr.optimize_parameters(it)
+        log = model.get_current_log()
+        for k, v in tr.get_current_log().items():
+            assert abs(log[k] - v) <= 1e-3 * max(1e-3, abs(v)), (it, k, log[k], v)
+    assert model._graphs is not None  # steps 3 and 4 ran as CUDA-graph replays
+    for k, v in model.net_g.named_parameters():
+        assert rel(v.detach(), tr.params[k].detach()) < 2e-3, k
+    for i, (k, v) in enumerate(model.net_g_ema.module.named_parameters()):
+        assert rel(v.detach(), tr.ema.avg[i]) < 2e-3, k
