@@ -92,6 +92,8 @@ typedef struct NsrConv {
    * value pre-split to bf16 hi/lo in the layout the next contraction bulk-copies. */
   const void* x_sti;
   void* y_sti;
+  int32_t res_ld;        /* leading dims of `residual` / `aux` when they differ from y_ld (0 = y_ld): lets an */
+  int32_t aux_ld;        /* epilogue read a channel slab of a wider buffer (ESRGAN dense blocks)              */
   int32_t pre_mode;      /* 0: y_pre = pre-activation; 1: y_pre = act'(pre-activation), so the backward
                             epilogue is a plain multiply (actgrad = NSR_ACT_MULAUX) and the erf/exp terms
                             are shared with the forward activation */
@@ -183,6 +185,18 @@ int nsr_prelu_bwd(const float* dy, const float* pre, const float* slope, float* 
  * skip of compact_arch.py:80-84 fused with the NHWC->NCHW output transpose (C <= 4). */
 int nsr_nhwc_to_nchw_add_nearest(const float* x, const float* base, float* y, int batch, int c, int h, int w,
                                  int scale, void* stream);
+
+/* 2-D strided glue for channel slabs [rows, cols] with independent leading dims:
+ *   axpby2d:       y = a * alpha + b * beta               (b may be NULL)
+ *   actgrad_mul2d: dx = dy * act'(aux)                    (LeakyReLU/ReLU backward on a slab slice) */
+int nsr_axpby2d(const float* a, int lda, float alpha, const float* b, int ldb, float beta, float* y, int ldy,
+                long long rows, int cols, void* stream);
+int nsr_actgrad_mul2d(const float* dy, int ld_dy, const float* aux, int ld_aux, float* dx, int ld_dx, long long rows,
+                      int cols, int act, float slope, void* stream);
+/* F.interpolate(x, scale_factor=2, mode="nearest") on NHWC (esrgan_arch.py:207-211) and its backward
+ * (sum of each 2x2 block). */
+int nsr_nearest_up2_nhwc(const float* x, float* y, int batch, int h, int w, int c, void* stream);
+int nsr_nearest_up2_bwd_nhwc(const float* dy, float* dx, int batch, int h, int w, int c, void* stream);
 
 /* y = a * alpha + b * beta (b may be NULL). Gradient accumulation glue. */
 int nsr_axpby(const float* a, float alpha, const float* b, float beta, float* y, size_t n, void* stream);

@@ -30,7 +30,7 @@ class NsrConv(C.Structure):
         ("x", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("prelu", C.c_void_p),
         ("aux", C.c_void_p), ("row_scale", C.c_void_p), ("residual", C.c_void_p),
         ("y_pre", C.c_void_p), ("y", C.c_void_p), ("x_sti", C.c_void_p), ("y_sti", C.c_void_p),
-        ("pre_mode", C.c_int32), ("reserved", C.c_int32),
+        ("res_ld", C.c_int32), ("aux_ld", C.c_int32), ("pre_mode", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -86,6 +86,10 @@ SIGNATURES = {
     "nsr_maxpool2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "nsr_maxpool2_relu_bwd_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "nsr_axpby": (_i, [_p, _f, _p, _f, _p, _z, _p]),
+    "nsr_axpby2d": (_i, [_p, _i, _f, _p, _i, _f, _p, _i, C.c_longlong, _i, _p]),
+    "nsr_actgrad_mul2d": (_i, [_p, _i, _p, _i, _p, _i, C.c_longlong, _i, _i, _f, _p]),
+    "nsr_nearest_up2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "nsr_nearest_up2_bwd_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "nsr_prelu_bwd_workspace": (_z, [_i]),
     "nsr_prelu_bwd": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _p, _z, _p]),
     "nsr_nhwc_to_nchw_add_nearest": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),

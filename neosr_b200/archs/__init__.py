@@ -7,6 +7,7 @@ from copy import deepcopy
 from ..registry import ARCH_REGISTRY
 from . import swinir_arch  # noqa: F401  (registers swinir_*)
 from . import compact_arch  # noqa: F401
+from . import esrgan_arch  # noqa: F401
 from . import vgg_arch  # noqa: F401
 
 

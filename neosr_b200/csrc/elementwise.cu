@@ -144,6 +144,51 @@ __global__ void actgrad_mul_kernel(const float* __restrict__ dy, const float* __
     dx[i] = dy[i] * act_grad(aux[i], act, slope) + (dextra ? dextra[i] : 0.f);
 }
 
+__global__ void axpby2d_kernel(const float* __restrict__ a, int lda, float alpha, const float* __restrict__ b, int ldb,
+                               float beta, float* __restrict__ y, int ldy, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    y[r * ldy + c] = a[r * lda + c] * alpha + (b ? b[r * ldb + c] * beta : 0.f);
+  }
+}
+__global__ void actgrad_mul2d_kernel(const float* __restrict__ dy, int ld_dy, const float* __restrict__ aux, int ld_aux,
+                                     float* __restrict__ dx, int ld_dx, long long rows, int cols, int act, float slope) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dx[r * ld_dx + c] = dy[r * ld_dy + c] * act_grad(aux[r * ld_aux + c], act, slope);
+  }
+}
+// nearest x2: y[b, 2h+i, 2w+j, c] = x[b, h, w, c]; backward sums the 2x2 block
+__global__ void nearest_up2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const size_t total = (size_t)B * 2 * H * 2 * W * C;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(o % C);
+    size_t q = o / C;
+    const int ow = (int)(q % (2 * W));
+    q /= 2 * W;
+    const int oh = (int)(q % (2 * H));
+    const size_t b = q / (2 * H);
+    y[o] = x[((b * H + (oh >> 1)) * W + (ow >> 1)) * C + c];
+  }
+}
+__global__ void nearest_up2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const size_t total = (size_t)B * H * W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t q = i / C;
+    const int w = (int)(q % W);
+    q /= W;
+    const int h = (int)(q % H);
+    const size_t b = q / H;
+    const float* p = dy + ((b * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c;
+    dx[i] = (p[0] + p[C]) + (p[(size_t)2 * W * C] + p[(size_t)2 * W * C + C]);
+  }
+}
+
 // PReLU backward on NHWC [rows, C]: dx = dy * (pre > 0 ? 1 : slope[c]); dslope[c] = sum_rows dy * min(pre, 0).
 // blockDim = (64 column quads, 4 row lanes) like the bias-gradient column sum; deterministic two-pass.
 __global__ void __launch_bounds__(256) prelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
@@ -208,6 +253,35 @@ __global__ void nhwc_to_nchw_add_nearest(const float* __restrict__ x, const floa
 }  // namespace nsr
 using namespace nsr;
 
+extern "C" int nsr_axpby2d(const float* a, int lda, float alpha, const float* b, int ldb, float beta, float* y, int ldy,
+                           long long rows, int cols, void* stream) {
+  NSR_CHECK_ARG(a && y && rows > 0 && cols > 0 && lda >= cols && ldy >= cols && (!b || ldb >= cols), "nsr_axpby2d: bad arguments");
+  axpby2d_kernel<<<ew_blocks((size_t)rows * cols), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, lda, alpha, b, ldb, beta, y,
+                                                                                                   ldy, rows, cols);
+  NSR_CHECK_LAUNCH("axpby2d");
+  return NSR_OK;
+}
+extern "C" int nsr_actgrad_mul2d(const float* dy, int ld_dy, const float* aux, int ld_aux, float* dx, int ld_dx,
+                                 long long rows, int cols, int act, float slope, void* stream) {
+  NSR_CHECK_ARG(dy && aux && dx && rows > 0 && cols > 0 && ld_dy >= cols && ld_aux >= cols && ld_dx >= cols,
+                "nsr_actgrad_mul2d: bad arguments");
+  actgrad_mul2d_kernel<<<ew_blocks((size_t)rows * cols), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dy, ld_dy, aux, ld_aux, dx, ld_dx, rows, cols, act, slope);
+  NSR_CHECK_LAUNCH("actgrad_mul2d");
+  return NSR_OK;
+}
+extern "C" int nsr_nearest_up2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  NSR_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0, "nsr_nearest_up2_nhwc: bad arguments");
+  nearest_up2_kernel<<<ew_blocks((size_t)B * H * W * C * 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, H, W, C);
+  NSR_CHECK_LAUNCH("nearest_up2");
+  return NSR_OK;
+}
+extern "C" int nsr_nearest_up2_bwd_nhwc(const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+  NSR_CHECK_ARG(dy && dx && B > 0 && H > 0 && W > 0 && C > 0, "nsr_nearest_up2_bwd_nhwc: bad arguments");
+  nearest_up2_bwd_kernel<<<ew_blocks((size_t)B * H * W * C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, dx, B, H, W, C);
+  NSR_CHECK_LAUNCH("nearest_up2_bwd");
+  return NSR_OK;
+}
 extern "C" size_t nsr_prelu_bwd_workspace(int c) { return (size_t)kNumSMs * 4 * c * sizeof(float); }
 extern "C" int nsr_prelu_bwd(const float* dy, const float* pre, const float* slope, float* dx, float* dslope,
                              long long rows, int c, void* workspace, size_t workspace_bytes, void* stream) {

@@ -127,12 +127,13 @@ __global__ void __launch_bounds__(FTHREADS) igemm_fprop_simt(NsrConv d, const fl
       const int n = n0 + tn * 4 + j;
       if (n >= d.cout) continue;
       const long long o = p * d.y_ld + n;
+      const long long ores = p * (d.res_ld ? d.res_ld : d.y_ld) + n, oaux = p * (d.aux_ld ? d.aux_ld : d.y_ld) + n;
       float v = acc[i][j] + (d.bias ? d.bias[n] : 0.f);
       if (d.y_pre) d.y_pre[o] = d.pre_mode ? act_grad(v, d.act, d.act == NSR_ACT_PRELU ? d.prelu[n] : d.act_slope) : v;
       if (d.act) v = apply_act(v, d.act, d.act == NSR_ACT_PRELU ? d.prelu[n] : d.act_slope);
-      if (d.actgrad) v *= act_grad(d.aux[o], d.actgrad, d.actgrad == NSR_ACT_PRELU ? d.prelu[n] : d.actgrad_slope);
+      if (d.actgrad) v *= act_grad(d.aux[oaux], d.actgrad, d.actgrad == NSR_ACT_PRELU ? d.prelu[n] : d.actgrad_slope);
       if (d.row_scale) v *= rs;
-      if (d.residual) v += d.residual[o];
+      if (d.residual) v += d.residual[ores];
       d.y[o] = v;
     }
   }

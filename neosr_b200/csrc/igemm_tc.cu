@@ -271,7 +271,7 @@ bool conv_fprop_tc_supported(const NsrConv& d) {
   static int ok_dev = -1;
   if (ok_dev < 0) ok_dev = nsr_device_supports_tcgen05();
   if (!ok_dev) return false;
-  if (d.cin % 4 || d.x_ld % 4 || d.cout % 4 || d.y_ld % 4) return false;
+  if (d.cin % 4 || d.x_ld % 4 || d.cout % 4 || d.y_ld % 4 || d.res_ld % 4 || d.aux_ld % 4) return false;
   if (d.cin < 16 || d.cout < 16) return false;  // image-side 3-channel convs stay on the SIMT engine
   if (d.x_sti != nullptr) {
     if (d.kh != 1 || d.kw != 1) return false;  // tile images carry no halo: 1x1 contractions only

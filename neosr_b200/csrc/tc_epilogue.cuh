@@ -33,9 +33,9 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
   for (int i = half * 4; i < half * 4 + 4; ++i) {
     const long long p = p0 + i * 4 + er;
     const bool ok = ncol && p < M;
-    const long long o = p * d.y_ld + n;
-    if (AG != NSR_ACT_NONE) aux4[i] = ok ? *reinterpret_cast<const float4*>(d.aux + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-    res4[i] = (ok && d.residual) ? *reinterpret_cast<const float4*>(d.residual + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long ores = p * (d.res_ld ? d.res_ld : d.y_ld) + n, oaux = p * (d.aux_ld ? d.aux_ld : d.y_ld) + n;
+    if (AG != NSR_ACT_NONE) aux4[i] = ok ? *reinterpret_cast<const float4*>(d.aux + oaux) : make_float4(0.f, 0.f, 0.f, 0.f);
+    res4[i] = (ok && d.residual) ? *reinterpret_cast<const float4*>(d.residual + ores) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
   for (int i = half * 4; i < half * 4 + 4; ++i) {

@@ -118,6 +118,36 @@ class STI:
         return y
 
 
+class Slab:
+    """A channel slice [c0, c0 + c) of a wider NHWC buffer [B,H,W,LD] (ESRGAN dense blocks read and
+    write growing channel slabs in place instead of torch.cat copies, esrgan_arch.py:109-116)."""
+
+    def __init__(self, base: Tensor, c0: int, c: int):
+        _chk(base, "slab base")
+        B, H, W, LD = base.shape
+        if c0 < 0 or c0 + c > LD or c0 % 4 or LD % 4:
+            raise ValueError("Slab: channel range must lie in the buffer and be 16-byte aligned")
+        self.base, self.c0, self.c, self.ld = base, c0, c, LD
+        self.shape = (B, H, W, c)
+        self.device = base.device
+
+    def data_ptr(self):
+        return self.base.data_ptr() + 4 * self.c0
+
+    def numel(self):
+        return self.shape[0] * self.shape[1] * self.shape[2] * self.c
+
+
+def _ptr_ld(t):
+    """(device pointer, leading dim) of a contiguous NHWC tensor or a Slab."""
+    if t is None:
+        return None, 0
+    if isinstance(t, Slab):
+        return t.data_ptr(), t.ld
+    _chk(t, "tensor")
+    return t.data_ptr(), t.shape[-1]
+
+
 def sti_enabled() -> bool:
     """Split-tile-image operands need the tcgen05 engine (sm_100) and are skipped when a test
     forces the exact-fp32 engine."""
@@ -171,27 +201,34 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
     the dgrad-packed filter is used and the roles of cin/cout swap (x is then dY [B,H,W,Cout]).
     sti_out / f32_out select the output formats: returns y (fp32), or the STI, or (y, sti)."""
     x_is_sti = isinstance(x, STI)
-    if not x_is_sti:
+    if not x_is_sti and not isinstance(x, Slab):
         _chk(x, "x")
     B, H, W, cx = x.shape
     cin, cout = (pw.cout, pw.cin) if dgrad else (pw.cin, pw.cout)
     if cx != cin:
         raise ValueError(f"conv_fprop: x has {cx} channels, weight expects {cin}")
-    for t, n in ((bias, "bias"), (aux, "aux"), (prelu, "prelu"), (row_scale, "row_scale"), (residual, "residual")):
+    for t, n in ((bias, "bias"), (prelu, "prelu"), (row_scale, "row_scale")):
         _chk(t, n)
+    x_ptr, x_ld = (None, cin) if x_is_sti else _ptr_ld(x)
+    aux_ptr, aux_ld = _ptr_ld(aux)
+    res_ptr, res_ld = _ptr_ld(residual)
     y = None
     if f32_out:
         y = out if out is not None else torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device)
+    y_ptr, y_ld = _ptr_ld(y) if y is not None else (None, cout)
+    if want_pre and isinstance(y, Slab):
+        raise ValueError("conv_fprop: y_pre shares y's leading dim; write y to a dense tensor when want_pre")
     y_sti = STI((B, H, W, cout), x.device) if sti_out else None
     if y is None and y_sti is None:
         raise ValueError("conv_fprop: no output format selected")
     y_pre = torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device) if want_pre else None
     d = NsrConv(batch=B, h=H, w=W, cin=cin, cout=cout, kh=pw.kh, kw=pw.kw, pad=pw.kh // 2,
-                x_ld=cin, y_ld=cout, act=ACT[act], act_slope=act_slope, actgrad=ACT[actgrad],
+                x_ld=x_ld, y_ld=y_ld, act=ACT[act], act_slope=act_slope, actgrad=ACT[actgrad],
                 actgrad_slope=actgrad_slope, engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
-                x=None if x_is_sti else x.data_ptr(), w_packed=(pw.dgrad if dgrad else pw.fprop).data_ptr(),
-                bias=_p(bias), prelu=_p(prelu), aux=_p(aux), row_scale=_p(row_scale), residual=_p(residual),
-                y_pre=_p(y_pre), y=_p(y), x_sti=x.data_ptr() if x_is_sti else None, y_sti=_p(y_sti),
+                x=x_ptr, w_packed=(pw.dgrad if dgrad else pw.fprop).data_ptr(),
+                bias=_p(bias), prelu=_p(prelu), aux=aux_ptr, row_scale=_p(row_scale), residual=res_ptr,
+                y_pre=_p(y_pre), y=y_ptr, x_sti=x.data_ptr() if x_is_sti else None, y_sti=_p(y_sti),
+                res_ld=res_ld if res_ld != y_ld else 0, aux_ld=aux_ld if aux_ld != y_ld else 0,
                 pre_mode=1 if pre_is_actgrad else 0, reserved=0)
     M = B * H * W
     with _prof(("conv_dgrad" if dgrad else "conv_fprop") + ("_sti" if x_is_sti else ""), (M, cin, cout, pw.kh),
@@ -206,16 +243,18 @@ def conv_wgrad(x, dy, dw: Tensor, dbias: Tensor | None, kh: int, kw: int, engine
                x_sti: STI | None = None, dy_sti: STI | None = None):
     """dw[cout,cin,kh,kw] (+ dbias) from x [B,H,W,Cin] and dy [B,H,W,Cout]; overwrites dw/dbias.
     x / dy may be None when their split tile images are given (1x1 contractions)."""
-    _chk(x, "x"), _chk(dy, "dy"), _chk(dw, "dw"), _chk(dbias, "dbias")
+    _chk(dw, "dw"), _chk(dbias, "dbias")
     xs, ds = (x if x is not None else x_sti), (dy if dy is not None else dy_sti)
     B, H, W, cin = xs.shape
     cout = ds.shape[-1]
     x, dy = (x if x is not None else xs), (dy if dy is not None else ds)
     if dy.shape[:3] != x.shape[:3] or dw.numel() != cout * cin * kh * kw:
         raise ValueError(f"conv_wgrad: shape mismatch x{tuple(x.shape)} dy{tuple(dy.shape)} dw{tuple(dw.shape)}")
-    d = NsrWgrad(batch=B, h=H, w=W, cin=cin, cout=cout, kh=kh, kw=kw, pad=kh // 2, x_ld=cin, dy_ld=cout,
+    x_ptr, x_ld = (None, cin) if isinstance(x, STI) else _ptr_ld(x)
+    dy_ptr, dy_ld = (None, cout) if isinstance(dy, STI) else _ptr_ld(dy)
+    d = NsrWgrad(batch=B, h=H, w=W, cin=cin, cout=cout, kh=kh, kw=kw, pad=kh // 2, x_ld=x_ld, dy_ld=dy_ld,
                  engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
-                 x=None if isinstance(x, STI) else x.data_ptr(), dy=None if isinstance(dy, STI) else dy.data_ptr(),
+                 x=x_ptr, dy=dy_ptr,
                  dw=dw.data_ptr(), dbias=_p(dbias), workspace=None, workspace_bytes=0,
                  x_sti=_p(x_sti), dy_sti=_p(dy_sti))
     L = _lib.lib()
@@ -306,6 +345,52 @@ def axpby(a: Tensor, alpha: float, b: Tensor | None, beta: float, out: Tensor | 
         check(_lib.lib().nsr_axpby(a.data_ptr(), alpha, _p(b), beta, y.data_ptr(), a.numel(), _stream()), "nsr_axpby")
     _count(1)
     return y
+
+
+def axpby2d(a, alpha: float, b, beta: float, out=None):
+    """out = a * alpha + b * beta over [rows, cols] views (tensors or Slabs); returns `out` (dense if not given)."""
+    B, H, W, cols = a.shape
+    rows = B * H * W
+    y = out if out is not None else torch.empty((B, H, W, cols), dtype=torch.float32, device=a.device)
+    (ap, lda), (bp, ldb), (yp, ldy) = _ptr_ld(a), _ptr_ld(b), _ptr_ld(y)
+    with _prof("nsr_axpby2d", (rows, cols), 0.0, 12.0 * rows * cols):
+        check(_lib.lib().nsr_axpby2d(ap, lda, alpha, bp, ldb, beta, yp, ldy, rows, cols, _stream()), "nsr_axpby2d")
+    _count(1)
+    return y
+
+
+def actgrad_mul2d(dy, aux, act: str, slope: float = 0.0) -> Tensor:
+    """dense dx = dy * act'(aux) for Slab / tensor views."""
+    B, H, W, cols = dy.shape
+    rows = B * H * W
+    dx = torch.empty((B, H, W, cols), dtype=torch.float32, device=dy.device)
+    (dp, ldd), (xp, lda) = _ptr_ld(dy), _ptr_ld(aux)
+    with _prof("nsr_actgrad_mul2d", (rows, cols), 0.0, 12.0 * rows * cols):
+        check(_lib.lib().nsr_actgrad_mul2d(dp, ldd, xp, lda, dx.data_ptr(), cols, rows, cols, ACT[act], slope, _stream()),
+              "nsr_actgrad_mul2d")
+    _count(1)
+    return dx
+
+
+def nearest_up2(x: Tensor) -> Tensor:
+    _chk(x, "x")
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, Cc), dtype=torch.float32, device=x.device)
+    with _prof("nsr_nearest_up2_nhwc", (x.numel(),), 0.0, 20.0 * x.numel()):
+        check(_lib.lib().nsr_nearest_up2_nhwc(x.data_ptr(), y.data_ptr(), B, H, W, Cc, _stream()), "nsr_nearest_up2_nhwc")
+    _count(1)
+    return y
+
+
+def nearest_up2_bwd(dy: Tensor) -> Tensor:
+    _chk(dy, "dy")
+    B, H2, W2, Cc = dy.shape
+    dx = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=torch.float32, device=dy.device)
+    with _prof("nsr_nearest_up2_bwd_nhwc", (dy.numel(),), 0.0, 5.0 * dy.numel()):
+        check(_lib.lib().nsr_nearest_up2_bwd_nhwc(dy.data_ptr(), dx.data_ptr(), B, H2 // 2, W2 // 2, Cc, _stream()),
+              "nsr_nearest_up2_bwd_nhwc")
+    _count(1)
+    return dx
 
 
 def prelu_bwd(dy: Tensor, pre: Tensor, slope: Tensor, dslope: Tensor) -> Tensor:

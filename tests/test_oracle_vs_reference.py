@@ -112,3 +112,22 @@ def test_compact_forward_backward():
     g = torch.autograd.grad((y ** 2).mean(), list(pr.values()))
     for (k, v), gi in zip(net.named_parameters(), g):
         assert _rel(gi, v.grad) < 1e-4, k
+
+
+@pytest.mark.parametrize("scale", [4, 2])
+def test_esrgan_forward_backward(scale):
+    from oracle.esrgan import esrgan_forward, esrgan_param_shapes
+    ref_shim.activate(4)
+    net = ref_shim.build_network({"type": "esrgan", "scale": scale, "num_block": 2, "num_feat": 32, "num_grow_ch": 16})
+    shapes = esrgan_param_shapes(scale=scale, num_feat=32, num_block=2, num_grow_ch=16)
+    assert {k: tuple(v.shape) for k, v in net.named_parameters()} == shapes
+    p = synth_params(shapes, seed=11)
+    net.load_state_dict(p)
+    x = torch.rand(2, 3, 16, 24, generator=torch.Generator().manual_seed(12))
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y, y_ref = esrgan_forward(pr, x, scale=scale, num_block=2), net(x)
+    assert _rel(y, y_ref) < 1e-5
+    (y_ref ** 2).mean().backward()
+    g = torch.autograd.grad((y ** 2).mean(), list(pr.values()))
+    for (k, v), gi in zip(net.named_parameters(), g):
+        assert _rel(gi, v.grad) < 1e-4, k

@@ -183,3 +183,29 @@ def test_compact_c1_training_steps_vs_oracle():
         assert rel(v.detach(), tr.params[k].detach()) < 2e-3, k
     for i, (k, v) in enumerate(model.net_g_ema.module.named_parameters()):
         assert rel(v.detach(), tr.ema.avg[i]) < 2e-3, k
+
+
+@pytest.mark.parametrize("scale", [4, 2])
+def test_esrgan_forward_backward_vs_oracle(scale):
+    """C2 generator (RRDBNet): slab-based dense blocks, forward and every parameter gradient vs the oracle."""
+    from neosr_b200.archs import build_network
+    from oracle.esrgan import esrgan_forward, esrgan_param_shapes
+    from oracle.swinir import synth_params
+    kw = dict(num_block=2, num_feat=64, num_grow_ch=32)
+    shapes = esrgan_param_shapes(scale=scale, **kw)
+    p = synth_params(shapes, seed=11)
+    net = build_network({"type": "esrgan", "scale": scale, **kw})
+    assert {k: tuple(v.shape) for k, v in net.named_parameters()} == shapes
+    net.load_state_dict(p)
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(2, 3, 32, 32, generator=g)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y_ref = esrgan_forward(pr, x, scale=scale, num_block=2)
+    gt = torch.rand(y_ref.shape, generator=g)
+    grads = torch.autograd.grad(((y_ref - gt) ** 2).mean(), list(pr.values()))
+    y = net(x.cuda())
+    assert rel(y.detach(), y_ref.detach()) < 1e-4
+    ((y - gt.cuda()) ** 2).mean().backward()
+    for (k, v), gi in zip(net.named_parameters(), grads):
+        assert rel(v.grad, gi) < 1e-3, k
