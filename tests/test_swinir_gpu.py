@@ -204,8 +204,18 @@ def test_esrgan_forward_backward_vs_oracle(scale):
     y_ref = esrgan_forward(pr, x, scale=scale, num_block=2)
     gt = torch.rand(y_ref.shape, generator=g)
     grads = torch.autograd.grad(((y_ref - gt) ** 2).mean(), list(pr.values()))
-    y = net(x.cuda())
-    assert rel(y.detach(), y_ref.detach()) < 1e-4
-    ((y - gt.cuda()) ** 2).mean().backward()
-    for (k, v), gi in zip(net.named_parameters(), grads):
-        assert rel(v.grad, gi) < 1e-3, k
+    # 30 stacked LeakyReLU convs: a 1e-6 perturbation flips the slope of a few near-zero pre-activations, which
+    # shows up as ~1e-3 relative on the smallest feature maps.  The exact-fp32 engine is held to 2e-4 (the
+    # slab/in-place dgrad bookkeeping is exact), the split-precision engine to 3e-3.
+    from neosr_b200 import ops
+    for engine, tol in (("simt", 2e-4), ("auto", 3e-3)):
+        ops.DEFAULT_ENGINE = engine
+        try:
+            net.zero_grad()
+            y = net(x.cuda())
+            assert rel(y.detach(), y_ref.detach()) < 1e-4
+            ((y - gt.cuda()) ** 2).mean().backward()
+        finally:
+            ops.DEFAULT_ENGINE = "auto"
+        for (k, v), gi in zip(net.named_parameters(), grads):
+            assert rel(v.grad, gi) < tol, (engine, k)
