@@ -198,6 +198,25 @@ int nsr_actgrad_mul2d(const float* dy, int ld_dy, const float* aux, int ld_aux, 
 int nsr_nearest_up2_nhwc(const float* x, float* y, int batch, int h, int w, int c, void* stream);
 int nsr_nearest_up2_bwd_nhwc(const float* dy, float* dx, int batch, int h, int w, int c, void* stream);
 
+/* ---- U-Net discriminator pieces (neosr/archs/unet_arch.py:40-67) ---- */
+/* F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) on NHWC and its backward. */
+int nsr_bilinear_up2_nhwc(const float* x, float* y, int batch, int h, int w, int c, void* stream);
+int nsr_bilinear_up2_bwd_nhwc(const float* dy, float* dx, int batch, int h, int w, int c, void* stream);
+/* nn.Conv2d(cin, cout, 4, 2, 1) == 3x3 stride-1 "same" conv over pixel_unshuffle(x, 2) with the weight
+ * w3[cout, 4*cin, 3, 3] this remap builds from w4[cout, cin, 4, 4] (unused taps are zero); inverse != 0
+ * gathers a gradient in the 3x3 layout back into the 4x4 layout. */
+int nsr_conv4x4s2_remap(const float* src, float* dst, int cout, int cin, int inverse, void* stream);
+/* torch.nn.utils.spectral_norm on W[rows = cout, cols = cin*kh*kw]: `power_iterations` updates of the
+ * u / v buffers in place (1 in training mode, 0 in eval), sigma = u^T W v, w_out = W / sigma. */
+size_t nsr_spectral_norm_workspace(int rows, int cols);
+int nsr_spectral_norm_fwd(const float* w_orig, float* u, float* v, float* w_out, float* sigma, int rows, int cols,
+                          int power_iterations, float eps, void* workspace, size_t workspace_bytes, void* stream);
+/* dL/dW_orig = (G - <G, W_sn> u v^T) / sigma with G = dL/dW_sn (u, v constants, as in torch);
+ * accumulate != 0 adds into dw_orig. */
+int nsr_spectral_norm_bwd(const float* g_wsn, const float* w_sn, const float* u, const float* v, const float* sigma,
+                          float* dw_orig, int rows, int cols, int accumulate, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* y = a * alpha + b * beta (b may be NULL). Gradient accumulation glue. */
 int nsr_axpby(const float* a, float alpha, const float* b, float beta, float* y, size_t n, void* stream);
 /* dx = dy * act'(aux) + (dextra ? dextra : 0) */

@@ -90,6 +90,12 @@ SIGNATURES = {
     "nsr_actgrad_mul2d": (_i, [_p, _i, _p, _i, _p, _i, C.c_longlong, _i, _i, _f, _p]),
     "nsr_nearest_up2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "nsr_nearest_up2_bwd_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "nsr_bilinear_up2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "nsr_bilinear_up2_bwd_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "nsr_conv4x4s2_remap": (_i, [_p, _p, _i, _i, _i, _p]),
+    "nsr_spectral_norm_workspace": (_z, [_i, _i]),
+    "nsr_spectral_norm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _z, _p]),
+    "nsr_spectral_norm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _z, _p]),
     "nsr_prelu_bwd_workspace": (_z, [_i]),
     "nsr_prelu_bwd": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _p, _z, _p]),
     "nsr_nhwc_to_nchw_add_nearest": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),

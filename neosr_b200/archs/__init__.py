@@ -8,6 +8,7 @@ from ..registry import ARCH_REGISTRY
 from . import swinir_arch  # noqa: F401  (registers swinir_*)
 from . import compact_arch  # noqa: F401
 from . import esrgan_arch  # noqa: F401
+from . import unet_arch  # noqa: F401
 from . import vgg_arch  # noqa: F401
 
 

@@ -257,6 +257,13 @@ __global__ void wgrad_n2w_final(const float* __restrict__ partial, float* __rest
 }
 
 // ---------------------------------------------------------------- host
+#define CS_NARROW_SWITCH(n, LAUNCH)                      \
+  switch (n) {                                           \
+    case 1: { constexpr int NW = 1; LAUNCH; } break;     \
+    case 2: { constexpr int NW = 2; LAUNCH; } break;     \
+    case 3: { constexpr int NW = 3; LAUNCH; } break;     \
+    default: { constexpr int NW = 4; LAUNCH; } break;    \
+  }
 static int cs_blocks(long long M) {
   long long b = (M + CS_WARPS - 1) / CS_WARPS;
   const long long cap = (long long)kNumSMs * 8;
@@ -268,8 +275,8 @@ bool conv_small_fprop_supported(const NsrConv& d) {
   if (d.x == nullptr || d.y == nullptr || d.y_sti || d.x_sti) return false;
   if (d.kh * d.kw > CS_MAXTAPS) return false;
   if (d.actgrad || d.residual || d.row_scale || d.act == NSR_ACT_GELU || d.pre_mode) return false;
-  if (d.cout <= 4 && d.cout >= 3 && d.cin % 64 == 0 && d.x_ld % 2 == 0 && d.act == NSR_ACT_NONE && !d.y_pre) return true;
-  if (d.cin <= 4 && d.cin >= 3 && d.cout >= 16) return true;
+  if (d.cout <= 4 && d.cout >= 1 && d.cin % 64 == 0 && d.x_ld % 2 == 0 && d.act == NSR_ACT_NONE && !d.y_pre) return true;
+  if (d.cin <= 4 && d.cin >= 1 && d.cout >= 16) return true;
   return false;
 }
 
@@ -281,12 +288,10 @@ int conv_small_fprop(const NsrConv& d, cudaStream_t st) {
   const float* w = reinterpret_cast<const float*>(d.w_packed);  // fp32 view W[cout][tap][cin]
   if (d.cout <= 4 && d.cin % 64 == 0) {
     g.wide = d.cin; g.narrow = d.cout;
-    if (d.cout == 3) conv_wide2narrow<3><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g);
-    else conv_wide2narrow<4><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g);
+    CS_NARROW_SWITCH(d.cout, (conv_wide2narrow<NW><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g)));
   } else {
     g.wide = d.cout; g.narrow = d.cin;
-    if (d.cin == 3) conv_narrow2wide<3><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g, d.act, d.act_slope, d.prelu, d.y_pre);
-    else conv_narrow2wide<4><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g, d.act, d.act_slope, d.prelu, d.y_pre);
+    CS_NARROW_SWITCH(d.cin, (conv_narrow2wide<NW><<<cs_blocks(g.M), CS_WARPS * 32, 0, st>>>(d.x, w, d.bias, d.y, g, d.act, d.act_slope, d.prelu, d.y_pre)));
   }
   NSR_CHECK_LAUNCH("conv_small_fprop");
   return NSR_OK;
@@ -297,8 +302,8 @@ int conv_bias_grad(const NsrWgrad& d, float* bias_partial, int bias_blocks, cuda
 bool conv_small_wgrad_supported(const NsrWgrad& d) {
   if (d.x == nullptr || d.dy == nullptr) return false;
   if (d.kh * d.kw > CS_MAXTAPS) return false;
-  if (d.cout <= 4 && d.cout >= 3 && d.cin % 64 == 0 && d.x_ld % 2 == 0) return true;
-  if (d.cin <= 4 && d.cin >= 3 && d.cout >= 16) return true;
+  if (d.cout <= 4 && d.cout >= 1 && d.cin % 64 == 0 && d.x_ld % 2 == 0) return true;
+  if (d.cin <= 4 && d.cin >= 1 && d.cout >= 16) return true;
   return false;
 }
 size_t conv_small_wgrad_workspace(const NsrWgrad& d) {
@@ -322,8 +327,7 @@ int conv_small_wgrad(const NsrWgrad& d, cudaStream_t st) {
   if (d.cout <= 4 && d.cin % 64 == 0) {
     g.wide = d.cin; g.narrow = d.cout;
     for (int grp = 0; grp < d.cin / 64; ++grp) {
-      if (d.cout == 3) wgrad_wide2narrow<3><<<blocks, CS_WG_WARPS * 32, 0, st>>>(d.x, d.dy, partial, g, grp);
-      else wgrad_wide2narrow<4><<<blocks, CS_WG_WARPS * 32, 0, st>>>(d.x, d.dy, partial, g, grp);
+      CS_NARROW_SWITCH(d.cout, (wgrad_wide2narrow<NW><<<blocks, CS_WG_WARPS * 32, 0, st>>>(d.x, d.dy, partial, g, grp)));
       NSR_CHECK_LAUNCH("wgrad_wide2narrow");
       wgrad_w2n_final<<<ceil_div(d.cout * taps * 64, 128), 128, 0, st>>>(partial, d.dw, blocks, d.cout, taps, d.cin, grp);
       NSR_CHECK_LAUNCH("wgrad_w2n_final");
@@ -331,8 +335,7 @@ int conv_small_wgrad(const NsrWgrad& d, cudaStream_t st) {
   } else {
     g.wide = d.cout; g.narrow = d.cin;
     for (int grp = 0; grp < (d.cout + 63) / 64; ++grp) {
-      if (d.cin == 3) wgrad_narrow2wide<3><<<blocks, CS_WG_WARPS * 32, 0, st>>>(d.x, d.dy, partial, g, grp);
-      else wgrad_narrow2wide<4><<<blocks, CS_WG_WARPS * 32, 0, st>>>(d.x, d.dy, partial, g, grp);
+      CS_NARROW_SWITCH(d.cin, (wgrad_narrow2wide<NW><<<blocks, CS_WG_WARPS * 32, 0, st>>>(d.x, d.dy, partial, g, grp)));
       NSR_CHECK_LAUNCH("wgrad_narrow2wide");
       wgrad_n2w_final<<<ceil_div(taps * d.cin * 64, 128), 128, 0, st>>>(partial, d.dw, blocks, d.cin, taps, d.cout, grp);
       NSR_CHECK_LAUNCH("wgrad_n2w_final");

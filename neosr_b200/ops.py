@@ -393,6 +393,68 @@ def nearest_up2_bwd(dy: Tensor) -> Tensor:
     return dx
 
 
+def bilinear_up2(x: Tensor) -> Tensor:
+    """F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) on NHWC."""
+    _chk(x, "x")
+    B, H, W, C = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
+    with _prof("nsr_bilinear_up2_nhwc", (x.numel(),), 0.0, 20.0 * x.numel()):
+        check(_lib.lib().nsr_bilinear_up2_nhwc(x.data_ptr(), y.data_ptr(), B, H, W, C, _stream()), "nsr_bilinear_up2_nhwc")
+    _count(1)
+    return y
+
+
+def bilinear_up2_bwd(dy: Tensor) -> Tensor:
+    _chk(dy, "dy")
+    B, H2, W2, C = dy.shape
+    dx = torch.empty((B, H2 // 2, W2 // 2, C), dtype=torch.float32, device=dy.device)
+    with _prof("nsr_bilinear_up2_bwd_nhwc", (dy.numel(),), 0.0, 5.0 * dy.numel()):
+        check(_lib.lib().nsr_bilinear_up2_bwd_nhwc(dy.data_ptr(), dx.data_ptr(), B, H2 // 2, W2 // 2, C, _stream()),
+              "nsr_bilinear_up2_bwd_nhwc")
+    _count(1)
+    return dx
+
+
+def conv4x4s2_remap(src: Tensor, cout: int, cin: int, inverse: bool = False, out: Tensor | None = None) -> Tensor:
+    """w4 [cout,cin,4,4] -> w3 [cout,4cin,3,3] (or the gradient gather back when inverse)."""
+    _chk(src, "src")
+    if out is None:
+        out = torch.empty((cout, cin, 4, 4) if inverse else (cout, 4 * cin, 3, 3), dtype=torch.float32, device=src.device)
+    _chk(out, "out")
+    check(_lib.lib().nsr_conv4x4s2_remap(src.data_ptr(), out.data_ptr(), cout, cin, int(inverse), _stream()),
+          "nsr_conv4x4s2_remap")
+    _count(1)
+    return out
+
+
+def spectral_norm_fwd(w_orig: Tensor, u: Tensor, v: Tensor, w_out: Tensor, sigma: Tensor, power_iterations: int = 1,
+                      eps: float = 1e-12) -> None:
+    """torch.nn.utils.spectral_norm forward; u, v updated in place when power_iterations > 0."""
+    for t, n in ((w_orig, "w_orig"), (u, "u"), (v, "v"), (w_out, "w_out"), (sigma, "sigma")):
+        _chk(t, n)
+    rows = w_orig.shape[0]
+    cols = w_orig.numel() // rows
+    L = _lib.lib()
+    ws = scratch(L.nsr_spectral_norm_workspace(rows, cols), w_orig.device)
+    check(L.nsr_spectral_norm_fwd(w_orig.data_ptr(), u.data_ptr(), v.data_ptr(), w_out.data_ptr(), sigma.data_ptr(), rows, cols,
+                                  power_iterations, eps, ws.data_ptr(), ws.numel(), _stream()), "nsr_spectral_norm_fwd")
+    _count(3 + 4 * power_iterations)
+
+
+def spectral_norm_bwd(g_wsn: Tensor, w_sn: Tensor, u: Tensor, v: Tensor, sigma: Tensor, dw_orig: Tensor,
+                      accumulate: bool = False) -> None:
+    for t, n in ((g_wsn, "g_wsn"), (w_sn, "w_sn"), (u, "u"), (v, "v"), (sigma, "sigma"), (dw_orig, "dw_orig")):
+        _chk(t, n)
+    rows = w_sn.shape[0]
+    cols = w_sn.numel() // rows
+    L = _lib.lib()
+    ws = scratch(L.nsr_spectral_norm_workspace(rows, cols), w_sn.device)
+    check(L.nsr_spectral_norm_bwd(g_wsn.data_ptr(), w_sn.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(),
+                                  dw_orig.data_ptr(), rows, cols, int(accumulate), ws.data_ptr(), ws.numel(), _stream()),
+          "nsr_spectral_norm_bwd")
+    _count(2)
+
+
 def prelu_bwd(dy: Tensor, pre: Tensor, slope: Tensor, dslope: Tensor) -> Tensor:
     """dx = dy * prelu'(pre); dslope (overwritten) = sum dy * min(pre, 0)."""
     _chk(dy, "dy"), _chk(pre, "pre"), _chk(slope, "slope"), _chk(dslope, "dslope")

