@@ -37,7 +37,23 @@ def peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
 
 
-def make_opt(batch: int, dist: bool, rank: int, world: int) -> dict:
+WORKLOADS = {
+    "c3": "C3: swinir_medium x4, 64x64->256x256 RGB, L1(1.0)+vgg19 perceptual(0.5, chc), adan_sf + EMA 0.999, "
+          "grad-clip 1.0, drop_path 0",
+    "c2": "C2: esrgan (23 RRDB) x4, 64x64->256x256 RGB, L1(1.0)+vgg19 perceptual(0.5, chc)+GAN(bce 0.1, unet "
+          "discriminator with spectral norm), adan_sf on G and D + EMA 0.999, grad-clip 1.0",
+}
+
+
+def make_opt(batch: int, dist: bool, rank: int, world: int, config: str = "c3") -> dict:
+    if config == "c2":
+        o = make_opt(batch, dist, rank, world, "c3")
+        o["name"] = "bench_c2"
+        o["network_g"] = {"type": "esrgan", "num_block": 23, "num_feat": 64, "num_grow_ch": 32}
+        o["network_d"] = {"type": "unet", "num_feat": 64}
+        o["train"]["optim_d"] = dict(o["train"]["optim_g"])
+        o["train"]["gan_opt"] = {"type": "gan_loss", "gan_type": "bce", "loss_weight": 0.1}
+        return o
     return {"name": "bench_c3", "model_type": "image", "scale": 4, "is_train": True, "dist": dist, "rank": rank,
             "world_size": world, "num_gpu": world,
             "network_g": {"type": "swinir_medium", "drop_path_rate": 0.0, "upscale": 4},
@@ -167,8 +183,8 @@ def run_ours(args) -> None:
 
     from neosr_b200 import ops
     from neosr_b200.models import build_model
-    B = args.batch
-    opt = make_opt(B, world > 1, rank, world)
+    B = args.batch if args.batch else (16 if args.config == "c2" else 32)
+    opt = make_opt(B, world > 1, rank, world, args.config)
     opt["cuda_graph"] = not args.no_graph
     model = build_model(opt)
     pool = synth_batches(args.pool, B, seed=1024 + rank)
@@ -288,7 +304,7 @@ def run_ours(args) -> None:
         except OSError:
             pass
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == "c3":
             r = cpu_oracle_run(1, 2, 1, budget_s=60.0)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         bytes_in = sum(v.numel() * 4 for v in pool[0].values())
@@ -296,8 +312,7 @@ def run_ours(args) -> None:
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded rand, 8-bit quantised; VGG19 weights "
                                                                "seeded-random: no pretrained weights offline)",
-                "config": {"workload": "C3: swinir_medium x4, 64x64->256x256 RGB, L1(1.0)+vgg19 perceptual(0.5, chc), "
-                                       "adan_sf + EMA 0.999, grad-clip 1.0, drop_path 0", "batch_per_gpu": B,
+                "config": {"workload": WORKLOADS[args.config], "batch_per_gpu": B,
                            "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": "per-step working set (activations > 40 GB at B=32) >> 126 MB L2; pool of "
                                  f"{len(pool)} distinct batches cycled"},
@@ -324,7 +339,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="LR crops per GPU per step (C3: 32)")
+    ap.add_argument("--batch", type=int, default=0, help="LR crops per GPU per step (default: C3 32, C2 16)")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2"],
+                    help="c3 = BASELINE.json's headline workload (what the driver runs); c2 = the GAN configuration")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")

@@ -54,17 +54,24 @@ class image:
         set_default_scale(opt.get("scale", 4), self.is_train)
 
         self.net_g = build_network(opt["network_g"]).to(self.device)
-        if opt.get("network_d") is not None:
-            raise NotImplementedError("neosr_b200.image: discriminator / GAN branch (image.py:516-608) not built yet")
         self.net_d = None
+        if opt.get("network_d") is not None:  # image.py:40-46
+            self.net_d = build_network(opt["network_d"]).to(self.device)
+            if not hasattr(self.net_d, "engine_backward"):
+                raise NotImplementedError("neosr_b200.image: network_d must be an engine-backed arch (unet)")
         path = opt.get("path", {}) or {}
         if path.get("pretrain_network_g"):
             self.load_network(self.net_g, path["pretrain_network_g"], path.get("param_key_g"),
                               path.get("strict_load_g", True))
+        if self.net_d is not None and path.get("pretrain_network_d"):
+            self.load_network(self.net_d, path["pretrain_network_d"], path.get("param_key_d", "params"),
+                              path.get("strict_load_d", True))
         self.dist = bool(opt.get("dist", False))
         self.world_size = int(opt.get("world_size", 1))
         if self.dist and self.world_size > 1:
             broadcast_params_(self.net_g.parameters())  # identical replicas, as DDP does when wrapping
+            if self.net_d is not None:
+                broadcast_params_([*self.net_d.parameters(), *self.net_d.buffers()])
         if self.is_train:
             self.init_training_settings()
 
@@ -93,7 +100,7 @@ class image:
         # deterministic launch sequence, i.e. no DropPath draws, and the device-scalar optimizer path
         ng = self.opt["network_g"]
         dp = float(ng.get("drop_path_rate", 0.1)) if "swinir" in ng.get("type", "") else 0.0
-        self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0
+        self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0 and self.net_d is None
                             and train_opt["optim_g"].get("type") in {"adan_sf", "Adan_SF"})
         self._graphs, self._graph_logs, self._eager_steps = None, None, 0
         self._lq_static = self._gt_static = None
@@ -112,30 +119,52 @@ class image:
 
         self.cri_pix = mk("pixel_opt")
         self.cri_perceptual = mk("perceptual_opt")
-        for k in ("mssim_opt", "consistency_opt", "dists_opt", "gan_opt", "ldl_opt", "ff_opt", "gw_opt"):
+        self.cri_gan = mk("gan_opt")
+        for k in ("mssim_opt", "consistency_opt", "dists_opt", "ldl_opt", "ff_opt", "gw_opt"):
             if train_opt.get(k):
                 raise NotImplementedError(f"neosr_b200.image: train.{k} not built yet")
         if self.cri_pix is None and self.cri_perceptual is None:
             raise ValueError("Both pixel/mssim and perceptual losses are None. Please enable at least one.")
+        optim_d = train_opt.get("optim_d")  # image.py:259-275
+        if self.net_d is None and optim_d is not None:
+            raise ValueError("Please set a discriminator in network_d or disable optim_d.")
+        if self.net_d is not None and optim_d is None:
+            raise ValueError("Please set an optimizer for the discriminator or disable network_d.")
+        if self.net_d is not None and self.cri_gan is None:
+            raise ValueError("Discriminator needs GAN to be enabled.")
+        if self.net_d is None and self.cri_gan is not None:
+            raise ValueError("GAN requires a discriminator to be set.")
         self.setup_optimizers()
         self.net_g.train()
         if self.sf_optim_g:
             self.optimizer_g.train()
+        if self.net_d is not None:
+            self.net_d.train()
+            if self.sf_optim_d:
+                self.optimizer_d.train()
 
-    def setup_optimizers(self) -> None:
-        o = dict(self.opt["train"]["optim_g"])
+    @staticmethod
+    def _make_optimizer(params, o: dict):
+        o = dict(o)
         optim_type = o.pop("type")
-        self.sf_optim_g = o.get("schedule_free", False)
-        params = [p for p in self.net_g.parameters() if p.requires_grad]
         if optim_type in {"Adan_SF", "adan_sf"}:
             if "schedule_free" not in o:
                 raise ValueError("The option 'schedule_free' must be in the config file.")
-            self.optimizer_g = adan_sf(params, **o)
-        elif optim_type in {"AdamW", "adamw"}:
-            self.optimizer_g = AdamW(params, **o)
-        else:
-            raise NotImplementedError(f"neosr_b200.image: optimizer {optim_type} not built (adan_sf, AdamW are)")
+            return adan_sf(params, **o)
+        if optim_type in {"AdamW", "adamw"}:
+            return AdamW(params, **o)
+        raise NotImplementedError(f"neosr_b200.image: optimizer {optim_type} not built (adan_sf, AdamW are)")
+
+    def setup_optimizers(self) -> None:  # image.py:340-372
+        o = self.opt["train"]["optim_g"]
+        self.sf_optim_g = o.get("schedule_free", False)
+        self.optimizer_g = self._make_optimizer([p for p in self.net_g.parameters() if p.requires_grad], o)
         self.optimizers.append(self.optimizer_g)
+        if self.net_d is not None:
+            o = self.opt["train"]["optim_d"]
+            self.sf_optim_d = o.get("schedule_free", False)
+            self.optimizer_d = self._make_optimizer(list(self.net_d.parameters()), o)
+            self.optimizers.append(self.optimizer_d)
 
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
@@ -176,9 +205,35 @@ class image:
             v, g = self.cri_perceptual.value_and_grad(out, self.gt, True, total)
             logs["l_g_percep"] = v
             dout = g if dout is None else ops.axpby(dout, 1.0, g, 1.0, out=dout)
+        if self.cri_gan is not None:
+            # generator's adversarial term (image.py:516-520): D is frozen, only d(loss)/d(output) flows back
+            pred, sd = self.net_d.engine_forward(out, save=True)
+            v, g = self.cri_gan.value_and_grad(pred, True, False, True, total)
+            logs["l_g_gan"] = v
+            g = self.net_d.engine_backward(sd, g, param_grads=False, need_dx=True)
+            del sd
+            dout = g if dout is None else ops.axpby(dout, 1.0, g, 1.0, out=dout)
         logs["l_g_total"] = total
         net.engine_backward(saved, dout)
+        del saved
+        if self.net_d is not None:
+            self._discriminator_backward(out, logs)
         return logs
+
+    def _discriminator_backward(self, out: Tensor, logs: OrderedDict) -> None:
+        """Real and fake passes of net_d (image.py:547-596); the fake pass accumulates onto the real pass's
+        gradients.  Each backward runs before the next forward (spectral-norm state is per forward)."""
+        d = self.net_d
+        pred, sd = d.engine_forward(self.gt, save=True)
+        l_real, g = self.cri_gan.value_and_grad(pred, True, True, True, None)
+        logs["l_d_real"], logs["out_d_real"] = l_real, pred.mean()
+        d.engine_backward(sd, g, param_grads=True, accumulate=False, need_dx=False)
+        del sd
+        pred, sd = d.engine_forward(out, save=True)  # `out` carries no graph: the reference's .detach()
+        l_fake, g = self.cri_gan.value_and_grad(pred, False, True, True, None)
+        logs["l_d_fake"], logs["out_d_fake"] = l_fake, pred.mean()
+        d.engine_backward(sd, g, param_grads=True, accumulate=True, need_dx=False)
+        logs["l_d_total"] = (l_real + l_fake) / 2
 
     def _ema_arg(self):
         if self.ema <= 0:
@@ -211,6 +266,12 @@ class image:
                 allreduce_mean_(ps.flat_grad)  # the one collective of the step (DDP-style gradient averaging)
             ps.attach_grads()
             self.optimizer_g.step(clip_max_norm=clip, ema=self._ema_arg())
+            if self.net_d is not None:  # image.py:598-608, 645
+                psd = self.net_d.param_set()
+                if multi:
+                    allreduce_mean_(psd.flat_grad)
+                psd.attach_grads()
+                self.optimizer_d.step(clip_max_norm=clip, ema=None)
             self._eager_steps += 1
         if self.ema > 0:
             self.net_g_ema.n_averaged += 1
@@ -311,6 +372,8 @@ class image:
             self.save_network(self.net_g_ema, "net_g", current_iter)
         else:
             self.save_network(self.net_g, "net_g", current_iter)
+        if self.net_d is not None:  # image.py:939-940
+            self.save_network(self.net_d, "net_d", current_iter)
         self.save_training_state(epoch, current_iter)
 
     def load_network(self, net, load_path, param_key: str | None = None, strict: bool = True) -> None:

@@ -99,7 +99,8 @@ def build_vgg_perceptual(seed_params: dict, loss_weight: float = 0.5, criterion:
     return mod
 
 
-def make_image_model(net_g, *, cri_pix=None, cri_perceptual=None, optim_kw=None, ema=0.999, scale=4):
+def make_image_model(net_g, *, cri_pix=None, cri_perceptual=None, optim_kw=None, ema=0.999, scale=4,
+                     net_d=None, cri_gan=None, optim_d_kw=None):
     """`object.__new__(image)` with the attributes `closure`/`optimize_parameters` read
     (image.py:73-230), so the reference's REAL step methods run on CPU."""
     activate()
@@ -134,4 +135,13 @@ def make_image_model(net_g, *, cri_pix=None, cri_perceptual=None, optim_kw=None,
     m.scale, m.aug, m.aug_prob, m.patch_size = scale, None, None, 64
     net_g.train()
     m.optimizer_g.train()
+    if net_d is not None:  # image.py:40-46, 356-372
+        dkw = dict(optim_d_kw or kw)
+        m.net_d, m.cri_gan = net_d, cri_gan
+        m.optimizer_d = adan_sf(list(net_d.parameters()), **dkw)
+        m.optimizers.append(m.optimizer_d)
+        m.sf_optim_d = dkw.get("schedule_free", True)
+        m.gradscaler_d = torch.amp.GradScaler("cuda", enabled=False)
+        net_d.train()
+        m.optimizer_d.train()
     return m

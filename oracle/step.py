@@ -1,8 +1,8 @@
 """Oracle: one `feed_data` + `optimize_parameters` iteration (TEST INFRASTRUCTURE).
 
 Restates image.closure (neosr/models/image.py:427-625) and
-image.optimize_parameters (627-662) for the generator-only configurations
-(C1: L1; C3: L1 + VGG perceptual), accumulate = 1, AMP off, no SAM/ECO.
+image.optimize_parameters (627-662) for the configurations C1 (L1), C3 (L1 + VGG perceptual) and C2 (adding the U-Net
+discriminator + BCE GAN loss, image.py:516-520, 547-608), accumulate = 1, AMP off, no SAM/ECO.
 Autograd supplies the backward pass, exactly as in the reference.
 """
 from __future__ import annotations
@@ -24,7 +24,8 @@ class OracleTrainer:
     def __init__(self, params: dict, net_fn, *, pixel_weight: float | None = 1.0,
                  percep_weight: float | None = None, vgg_params: dict | None = None,
                  layer_weights: dict | None = None, optim: dict | None = None,
-                 ema: float = 0.999, grad_clip: bool = True):
+                 ema: float = 0.999, grad_clip: bool = True, disc: tuple | None = None,
+                 gan_weight: float = 0.1, optim_d: dict | None = None):
         self.names = list(params)
         self.params = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
         self.net_fn = net_fn
@@ -35,6 +36,17 @@ class OracleTrainer:
         self.ema = EMAState([self.params[k] for k in self.names], ema) if ema and ema > 0 else None
         self.log_dict: OrderedDict = OrderedDict()
         self.last_grads: dict = {}
+        # discriminator: (params, buffers) of oracle.unet; buffers are updated in place by each forward
+        self.disc = None
+        if disc is not None:
+            dp, db = disc
+            self.d_names = list(dp)
+            self.d_params = {k: v.detach().clone().requires_grad_(True) for k, v in dp.items()}
+            self.d_buffers = {k: v.detach().clone() for k, v in db.items()}
+            self.disc = True
+            self.gan_weight = gan_weight
+            self.opt_d = AdanSFState([self.d_params[k] for k in self.d_names], **(optim_d or optim or {}))
+            self.last_grads_d: dict = {}
 
     def feed_data(self, data: dict) -> None:  # image.py:374-391 (no augmentation)
         self.lq, self.gt = data["lq"], data["gt"]
@@ -52,16 +64,37 @@ class OracleTrainer:
             l_per = L.vgg_perceptual_loss(self.vgg_params, out, self.gt, self.percep_weight, self.layer_weights)
             total = total + l_per
             log["l_g_percep"] = l_per
+        if self.disc:  # image.py:516-520 — net_d frozen (requires_grad False): gradient reaches net_g only
+            from .unet import unet_forward
+            frozen = {k: v.detach() for k, v in self.d_params.items()}
+            l_gan = L.gan_loss(unet_forward(frozen, self.d_buffers, out, True), True, False, loss_weight=self.gan_weight)
+            total = total + l_gan
+            log["l_g_gan"] = l_gan
         log["l_g_total"] = total
         plist = [self.params[k] for k in self.names]
         grads = torch.autograd.grad(total, plist, allow_unused=True)
         grads = [torch.zeros_like(p) if g is None else g.contiguous().clone() for g, p in zip(grads, plist)]
         self.grad_norm = clip_grad_norm(grads, 1.0) if self.grad_clip else None  # image.py:533-544
         self.last_grads = dict(zip(self.names, [g.clone() for g in grads]))
+        if self.disc:  # image.py:547-608
+            real = unet_forward(self.d_params, self.d_buffers, self.gt, True)
+            l_real = L.gan_loss(real, True, True)
+            fake = unet_forward(self.d_params, self.d_buffers, out.detach(), True)
+            l_fake = L.gan_loss(fake, False, True)
+            log["l_d_real"], log["out_d_real"] = l_real, real.detach().mean()
+            log["l_d_fake"], log["out_d_fake"] = l_fake, fake.detach().mean()
+            log["l_d_total"] = (l_real + l_fake) / 2
+            dlist = [self.d_params[k] for k in self.d_names]
+            dgrads = [g.contiguous().clone() for g in torch.autograd.grad(l_real + l_fake, dlist)]
+            if self.grad_clip:
+                clip_grad_norm(dgrads, 1.0)
+            self.last_grads_d = dict(zip(self.d_names, [g.clone() for g in dgrads]))
         if torch.isnan(total).any():  # image.py:611-619
             raise ValueError("NaN found, aborting training.")
         self.log_dict = OrderedDict((k, float(v.detach().mean())) for k, v in log.items())
         adan_sf_step(self.opt, grads)  # image.py:642
+        if self.disc:
+            adan_sf_step(self.opt_d, dgrads)  # image.py:645
         if self.ema is not None:  # image.py:661-662
             self.ema.update(plist)
 

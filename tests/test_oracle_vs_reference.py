@@ -165,3 +165,41 @@ def test_unet_sn_forward_backward_and_buffers():
     x = torch.rand(1, 3, 16, 16, generator=gen)
     with torch.no_grad():
         assert _rel(unet_forward(pr, bo, x, training=False), net(x)) < 1e-5
+
+
+def test_gan_step_with_unet_discriminator():
+    """C2's step shape: 3 iterations of the reference's REAL optimize_parameters with net_d = unet and
+    gan_loss(bce) vs the oracle trainer — logs, both networks' parameters, spectral-norm buffers."""
+    from oracle.unet import synth_unet
+    cfg = SwinIRConfig(**TINY)
+    p = synth_params(swinir_param_shapes(cfg), seed=4)
+    dp, db = synth_unet(num_feat=16, seed=9)
+    ref_shim.activate(4)
+    from neosr.losses.basic_loss import L1Loss
+    from neosr.losses.gan_loss import gan_loss
+    net = _ref_swinir(TINY, p)
+    net_d = ref_shim.build_network({"type": "unet", "num_feat": 16})
+    net_d.load_state_dict({**dp, **db})
+    okw = dict(lr=1e-3, betas=(0.98, 0.92, 0.987), weight_decay=0.02, schedule_free=True, warmup_steps=1600)
+    model = ref_shim.make_image_model(net, cri_pix=L1Loss(1.0), optim_kw=okw, net_d=net_d,
+                                      cri_gan=gan_loss("bce", loss_weight=0.3))
+    tr = make_swinir_trainer(p, cfg, pixel_weight=1.0, optim=okw, ema=0.999, disc=(dp, db), gan_weight=0.3)
+    g = torch.Generator().manual_seed(6)
+    for it in range(3):
+        lq, gt = torch.rand(2, 3, 16, 16, generator=g), torch.rand(2, 3, 64, 64, generator=g)
+        model.feed_data({"lq": lq, "gt": gt})
+        model.optimize_parameters(it)
+        tr.feed_data({"lq": lq, "gt": gt})
+        tr.optimize_parameters(it)
+        ref_log = model.get_current_log()
+        olog = tr.get_current_log()
+        assert set(olog) == set(ref_log), (sorted(olog), sorted(ref_log))
+        for k, v in olog.items():
+            assert abs(v - ref_log[k]) <= 1e-5 * max(1.0, abs(ref_log[k])), (it, k, v, ref_log[k])
+    ref_params = dict(net.named_parameters())
+    for k in tr.names:
+        assert _rel(tr.params[k].detach(), ref_params[k].detach()) < 1e-4, k
+    for k, v in net_d.named_parameters():
+        assert _rel(tr.d_params[k].detach(), v.detach()) < 1e-4, k
+    for k, v in net_d.named_buffers():
+        assert _rel(tr.d_buffers[k], v) < 1e-5, k

@@ -1,14 +1,22 @@
 import torch
 from neosr_b200 import ops
-def rel(a,b): return float((a-b).abs().max()/b.abs().max())
-g=torch.Generator().manual_seed(0)
-for (cin,cout,H,W) in [(64,64,32,48),(128,64,32,48),(256,128,16,24),(512,256,8,12),(1024,512,4,6),(512,256,8,12),(256,128,16,24)]:
-    w=(torch.randn(cout,cin,3,3,generator=g)*0.05).cuda()
-    pw=ops.PackedWeight(w).refresh()
-    dy=torch.randn(2,H,W,cout,generator=g).cuda(); aux=torch.randn(2,H,W,cin,generator=g).cuda()
-    x=torch.randn(2,H,W,cin,generator=g).cuda()
-    a=ops.conv_fprop(dy,pw,None,dgrad=True,engine="simt"); b=ops.conv_fprop(dy,pw,None,dgrad=True,engine="auto")
-    f1=ops.conv_fprop(x,pw,None,engine="simt",act="lrelu",act_slope=0.2); f2=ops.conv_fprop(x,pw,None,engine="auto",act="lrelu",act_slope=0.2)
-    a2,p2=ops.conv_fprop(dy,pw,None,dgrad=True,engine="simt",actgrad="lrelu",actgrad_slope=0.2,aux=aux,want_pre=True)
-    b2,q2=ops.conv_fprop(dy,pw,None,dgrad=True,engine="auto",actgrad="lrelu",actgrad_slope=0.2,aux=aux,want_pre=True)
-    print((cin,cout,H,W),"fprop",rel(f2,f1),"dgrad",rel(b,a),"dgrad+actgrad",rel(b2,a2),"pre",rel(q2,p2),flush=True)
+from neosr_b200.archs import build_network
+from oracle.unet import synth_unet, unet_forward
+nf=64; skip=False
+p,b=synth_unet(num_feat=nf,seed=31)
+net=build_network({"type":"unet","num_feat":nf,"skip_connection":skip}); net.load_state_dict({**p,**b}); net=net.cuda().train()
+gen=torch.Generator().manual_seed(32)
+xs=[torch.rand(2,3,32,48,generator=gen) for _ in range(3)]; ts=[torch.randn(2,1,32,48,generator=gen) for _ in range(3)]; x,t=xs[0],ts[0]
+res={}
+for dt in (torch.float32, torch.float64):
+    pr={k:v.clone().to(dt) for k,v in p.items()}; bo={k:v.clone().to(dt) for k,v in b.items()}
+    xo=x.clone().to(dt).requires_grad_(True)
+    yo=unet_forward(pr,bo,xo,True,skip)
+    gx,=torch.autograd.grad(((yo-t.to(dt))**2).mean(),xo)
+    res[dt]=gx.double()
+ops.DEFAULT_ENGINE="simt"
+y,S=net.engine_forward(x.cuda(),save=True)
+dy=(2.0/y.numel())*(y-t.cuda())
+dx=net.engine_backward(S,dy,param_grads=False).cpu().double()
+def r2(a,b): return float((a-b).norm()/b.norm())
+print("gpu-vs-cpu32",r2(dx,res[torch.float32]),"gpu-vs-cpu64",r2(dx,res[torch.float64]),"cpu32-vs-cpu64",r2(res[torch.float32],res[torch.float64]))
