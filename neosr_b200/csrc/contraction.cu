@@ -2,6 +2,8 @@
 // the weight packer.  Engine dispatch lives here.
 #include <stdlib.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace nsr {
@@ -17,6 +19,9 @@ int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st);
 // <= 4-channel image-side convolutions (conv_small.cu)
 bool conv_small_fprop_supported(const NsrConv& d);
 int conv_small_fprop(const NsrConv& d, cudaStream_t st);
+bool conv_wgrad_tma_supported(const NsrWgrad& d);
+size_t conv_wgrad_workspace_tma(const NsrWgrad& d);
+int conv_wgrad_tma(const NsrWgrad& d, cudaStream_t st);
 bool conv_small_wgrad_supported(const NsrWgrad& d);
 size_t conv_small_wgrad_workspace(const NsrWgrad& d);
 int conv_small_wgrad(const NsrWgrad& d, cudaStream_t st);
@@ -221,9 +226,25 @@ static bool wgrad_use_tc(const NsrWgrad* d) {
   return conv_wgrad_tc_supported(*d);
 }
 
+// TMA-staged 3x3 wgrad (igemm_wgrad_tma.cu); NSR_WGRAD_TMA=0 keeps the producer-warp kernel (A/B runs)
+static bool wgrad_use_tma(const NsrWgrad* d) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("NSR_WGRAD_TMA");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return false;
+  const bool sti = d->x_sti != nullptr && d->dy_sti != nullptr && d->kh == 1 && d->kw == 1;
+  return !sti && conv_wgrad_tma_supported(*d);
+}
+
 extern "C" size_t nsr_conv_wgrad_workspace(const NsrWgrad* d) {
   if (!d) return 0;
   size_t a = conv_wgrad_workspace_simt(*d);
+  if (wgrad_use_tma(d)) {
+    const size_t t = conv_wgrad_workspace_tma(*d);
+    a = a > t ? a : t;
+  }
   size_t b = conv_wgrad_tc_supported(*d) ? conv_wgrad_workspace_tc(*d) : 0;
   size_t c = conv_small_wgrad_supported(*d) ? conv_small_wgrad_workspace(*d) : 0;
   a = a > b ? a : b;
@@ -237,7 +258,7 @@ extern "C" int nsr_conv_wgrad(const NsrWgrad* d, void* stream) {
   int eng = d->engine == NSR_ENGINE_AUTO ? forced_engine() : d->engine;
   if (eng == NSR_ENGINE_TCGEN05)
     NSR_CHECK_ARG(conv_wgrad_tc_supported(*d), "nsr_conv_wgrad: shape not supported by the tcgen05 engine");
-  if (wgrad_use_tc(d)) return conv_wgrad_tc(*d, st);
+  if (wgrad_use_tc(d)) return wgrad_use_tma(d) ? conv_wgrad_tma(*d, st) : conv_wgrad_tc(*d, st);
   NSR_CHECK_ARG(d->x && d->dy, "nsr_conv_wgrad: split-tile-image operands need the tcgen05 engine");
   if (eng == NSR_ENGINE_AUTO && conv_small_wgrad_supported(*d)) return conv_small_wgrad(*d, st);
   return conv_wgrad_simt(*d, st);

@@ -333,3 +333,25 @@ def test_sti_layernorm_and_attention():
         dq = ops.window_attn_bwd(qkv, table, dout, dt1, 6, 8, shift, scale)
         dqs = ops.window_attn_bwd(qkv, table, dout, dt2, 6, 8, shift, scale, sti_out=True)
         assert rel(dqs.to_f32(), dq) < 2e-5 and torch.equal(dt1, dt2)
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,x_ld", [
+    (2, 16, 16, 64, 32, 192), (2, 32, 32, 160, 32, 192), (1, 64, 64, 192, 64, 192), (2, 6, 48, 96, 32, 96),
+    (1, 5, 128, 64, 64, 64), (3, 4, 16, 180, 180, 180), (2, 16, 32, 20, 72, 20), (1, 8, 64, 256, 128, 256)])
+def test_wgrad_tma_3x3(B, H, W, cin, cout, x_ld):
+    """TMA-staged 3x3 weight gradient (igemm_wgrad_tma.cu): halo tiles, OOB zero fill at the image border, slab
+    (strided) inputs, every BN / orientation; vs fp64 autograd and vs the exact-fp32 engine."""
+    from neosr_b200 import ops
+    slab = rnd(B, H, W, x_ld, seed=21)
+    x = ops.Slab(slab, 0, cin) if x_ld != cin else slab
+    xd = slab[..., :cin].contiguous()
+    dy = rnd(B, H, W, cout, seed=22)
+    wg = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+    F.conv2d(nchw(xd).double(), wg, None, 1, 1).backward(nchw(dy).double())
+    dw, db = torch.empty(cout, cin, 3, 3, device="cuda"), torch.empty(cout, device="cuda")
+    ops.conv_wgrad(x, dy, dw, db, 3, 3, engine="tcgen05")
+    assert rel(dw.double(), wg.grad) < 3e-5
+    assert rel(db.double(), dy.double().sum((0, 1, 2))) < 1e-5
+    dw2 = torch.empty_like(dw)
+    ops.conv_wgrad(x, dy, dw2, None, 3, 3, engine="tcgen05")
+    assert torch.equal(dw, dw2)

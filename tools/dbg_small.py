@@ -1,22 +1,15 @@
-import torch
+import torch, time, os
 from neosr_b200 import ops
-from neosr_b200.archs import build_network
-from oracle.unet import synth_unet, unet_forward
-nf=64; skip=False
-p,b=synth_unet(num_feat=nf,seed=31)
-net=build_network({"type":"unet","num_feat":nf,"skip_connection":skip}); net.load_state_dict({**p,**b}); net=net.cuda().train()
-gen=torch.Generator().manual_seed(32)
-xs=[torch.rand(2,3,32,48,generator=gen) for _ in range(3)]; ts=[torch.randn(2,1,32,48,generator=gen) for _ in range(3)]; x,t=xs[0],ts[0]
-res={}
-for dt in (torch.float32, torch.float64):
-    pr={k:v.clone().to(dt) for k,v in p.items()}; bo={k:v.clone().to(dt) for k,v in b.items()}
-    xo=x.clone().to(dt).requires_grad_(True)
-    yo=unet_forward(pr,bo,xo,True,skip)
-    gx,=torch.autograd.grad(((yo-t.to(dt))**2).mean(),xo)
-    res[dt]=gx.double()
-ops.DEFAULT_ENGINE="simt"
-y,S=net.engine_forward(x.cuda(),save=True)
-dy=(2.0/y.numel())*(y-t.cuda())
-dx=net.engine_backward(S,dy,param_grads=False).cpu().double()
-def r2(a,b): return float((a-b).norm()/b.norm())
-print("gpu-vs-cpu32",r2(dx,res[torch.float32]),"gpu-vs-cpu64",r2(dx,res[torch.float64]),"cpu32-vs-cpu64",r2(res[torch.float32],res[torch.float64]))
+def bench(B,H,W,cin,cout,n=20):
+    x=torch.randn(B,H,W,cin,device="cuda"); dy=torch.randn(B,H,W,cout,device="cuda")
+    dw=torch.empty(cout,cin,3,3,device="cuda")
+    for _ in range(3): ops.conv_wgrad(x,dy,dw,None,3,3)
+    torch.cuda.synchronize()
+    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): ops.conv_wgrad(x,dy,dw,None,3,3)
+    e1.record(); torch.cuda.synchronize()
+    ms=e0.elapsed_time(e1)/n
+    print(f"wgrad B{B} {H}x{W} {cin}->{cout}: {ms*1e3:8.1f} us  {2*B*H*W*cin*cout*9/ms/1e9:7.1f} TF",flush=True)
+for s in [(16,64,64,192,64),(16,64,64,160,32),(16,64,64,64,32),(32,64,64,180,180),(8,128,128,64,256),(16,256,256,64,64),(4,32,32,512,512)]:
+    bench(*s)
