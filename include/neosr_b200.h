@@ -98,7 +98,12 @@ typedef struct NsrConv {
                             epilogue is a plain multiply (actgrad = NSR_ACT_MULAUX) and the erf/exp terms
                             are shared with the forward activation */
   int32_t reserved;
+  void* workspace;       /* optional scratch of nsr_conv_fprop_workspace() bytes: lets <= 4-channel convolutions */
+  size_t workspace_bytes;/* (conv_first / conv_last, VGG conv1_1) run as im2col + one tensor-core contraction */
 } NsrConv;
+
+/* Scratch nsr_conv_fprop can use for this descriptor (0 when it needs none). */
+size_t nsr_conv_fprop_workspace(const NsrConv* desc);
 
 int nsr_conv_fprop(const NsrConv* d, void* stream);
 

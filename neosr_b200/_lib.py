@@ -31,6 +31,7 @@ class NsrConv(C.Structure):
         ("aux", C.c_void_p), ("row_scale", C.c_void_p), ("residual", C.c_void_p),
         ("y_pre", C.c_void_p), ("y", C.c_void_p), ("x_sti", C.c_void_p), ("y_sti", C.c_void_p),
         ("res_ld", C.c_int32), ("aux_ld", C.c_int32), ("pre_mode", C.c_int32), ("reserved", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -76,6 +77,7 @@ SIGNATURES = {
     "nsr_version": (_i, []),
     "nsr_device_supports_tcgen05": (_i, []),
     "nsr_conv_fprop": (_i, [C.POINTER(NsrConv), _p]),
+    "nsr_conv_fprop_workspace": (_z, [C.POINTER(NsrConv)]),
     "nsr_packed_weight_bytes": (_z, [_i, _i, _i, _i, _i]),
     "nsr_pack_weight": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nsr_conv_wgrad_workspace": (_z, [C.POINTER(NsrWgrad)]),

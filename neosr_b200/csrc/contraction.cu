@@ -19,6 +19,13 @@ int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st);
 // <= 4-channel image-side convolutions (conv_small.cu)
 bool conv_small_fprop_supported(const NsrConv& d);
 int conv_small_fprop(const NsrConv& d, cudaStream_t st);
+// <= 4-channel convs as im2col + tensor-core GEMM (conv_narrow_gemm.cu)
+bool conv_narrow_gemm_supported(const NsrConv& d);
+size_t conv_narrow_gemm_workspace(const NsrConv& d);
+int conv_narrow_gemm_fprop(const NsrConv& d, cudaStream_t st);
+bool conv_narrow_gemm_wgrad_supported(const NsrWgrad& d);
+size_t conv_narrow_gemm_wgrad_workspace(const NsrWgrad& d);
+int conv_narrow_gemm_wgrad(const NsrWgrad& d, cudaStream_t st);
 bool conv_wgrad_tma_supported(const NsrWgrad& d);
 size_t conv_wgrad_workspace_tma(const NsrWgrad& d);
 int conv_wgrad_tma(const NsrWgrad& d, cudaStream_t st);
@@ -82,6 +89,15 @@ __global__ void pack_weight_bf16(const float* __restrict__ wf32, uint8_t* __rest
     *reinterpret_cast<uint4*>(img + tile_hi + off) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(img + tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
   }
+}
+
+int launch_pack_weight_bf16(const float* wf32, uint8_t* img, const PackedGeom& g, cudaStream_t st) {
+  const size_t t2 = (size_t)g.taps * g.cblks * g.n_pad64 * 8;
+  int blocks = ceil_div(t2, 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  pack_weight_bf16<<<blocks, 256, 0, st>>>(wf32, img, g);
+  NSR_CHECK_LAUNCH("pack_weight_bf16");
+  return NSR_OK;
 }
 
 // ---- split tile image <-> fp32 (utility; producers emit STI directly on the hot path) -------
@@ -180,6 +196,16 @@ extern "C" int nsr_pack_weight(const float* w, int cout, int cin, int kh, int kw
   return NSR_OK;
 }
 
+// NSR_NARROW_GEMM=0 keeps the SIMT kernels of conv_small.cu for the <= 4-channel convolutions (A/B runs)
+static bool narrow_gemm_enabled() {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("NSR_NARROW_GEMM");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  return enabled != 0;
+}
+
 static int check_conv(const NsrConv* d) {
   NSR_CHECK_ARG(d, "nsr_conv_fprop: null descriptor");
   NSR_CHECK_ARG(d->batch > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "nsr_conv_fprop: bad geometry");
@@ -206,8 +232,16 @@ extern "C" int nsr_conv_fprop(const NsrConv* d, void* stream) {
   }
   if (eng == NSR_ENGINE_AUTO && conv_fprop_tc_supported(*d)) return conv_fprop_tc(*d, st);
   NSR_CHECK_ARG(d->x && d->y && !d->y_sti, "nsr_conv_fprop: split-tile-image operands need the tcgen05 engine");
+  if (eng == NSR_ENGINE_AUTO && narrow_gemm_enabled() && conv_narrow_gemm_supported(*d)) return conv_narrow_gemm_fprop(*d, st);
   if (eng == NSR_ENGINE_AUTO && conv_small_fprop_supported(*d)) return conv_small_fprop(*d, st);
   return conv_fprop_simt(*d, st);
+}
+
+extern "C" size_t nsr_conv_fprop_workspace(const NsrConv* d) {
+  if (!d || !narrow_gemm_enabled() || !nsr_device_supports_tcgen05()) return 0;
+  int eng = d->engine == NSR_ENGINE_AUTO ? forced_engine() : d->engine;
+  if (eng != NSR_ENGINE_AUTO) return 0;
+  return conv_narrow_gemm_workspace(*d);
 }
 
 static int check_wgrad(const NsrWgrad* d) {
@@ -248,7 +282,12 @@ extern "C" size_t nsr_conv_wgrad_workspace(const NsrWgrad* d) {
   size_t b = conv_wgrad_tc_supported(*d) ? conv_wgrad_workspace_tc(*d) : 0;
   size_t c = conv_small_wgrad_supported(*d) ? conv_small_wgrad_workspace(*d) : 0;
   a = a > b ? a : b;
-  return a > c ? a : c;
+  a = a > c ? a : c;
+  if (narrow_gemm_enabled() && conv_narrow_gemm_wgrad_supported(*d)) {
+    const size_t n = conv_narrow_gemm_wgrad_workspace(*d);
+    a = a > n ? a : n;
+  }
+  return a;
 }
 
 extern "C" int nsr_conv_wgrad(const NsrWgrad* d, void* stream) {
@@ -260,6 +299,7 @@ extern "C" int nsr_conv_wgrad(const NsrWgrad* d, void* stream) {
     NSR_CHECK_ARG(conv_wgrad_tc_supported(*d), "nsr_conv_wgrad: shape not supported by the tcgen05 engine");
   if (wgrad_use_tc(d)) return wgrad_use_tma(d) ? conv_wgrad_tma(*d, st) : conv_wgrad_tc(*d, st);
   NSR_CHECK_ARG(d->x && d->dy, "nsr_conv_wgrad: split-tile-image operands need the tcgen05 engine");
+  if (eng == NSR_ENGINE_AUTO && narrow_gemm_enabled() && conv_narrow_gemm_wgrad_supported(*d)) return conv_narrow_gemm_wgrad(*d, st);
   if (eng == NSR_ENGINE_AUTO && conv_small_wgrad_supported(*d)) return conv_small_wgrad(*d, st);
   return conv_wgrad_simt(*d, st);
 }

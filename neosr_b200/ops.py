@@ -229,7 +229,12 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
                 bias=_p(bias), prelu=_p(prelu), aux=aux_ptr, row_scale=_p(row_scale), residual=res_ptr,
                 y_pre=_p(y_pre), y=y_ptr, x_sti=x.data_ptr() if x_is_sti else None, y_sti=_p(y_sti),
                 res_ld=res_ld if res_ld != y_ld else 0, aux_ld=aux_ld if aux_ld != y_ld else 0,
-                pre_mode=1 if pre_is_actgrad else 0, reserved=0)
+                pre_mode=1 if pre_is_actgrad else 0, reserved=0, workspace=None, workspace_bytes=0)
+    if min(cin, cout) <= 4:  # image-side convs: im2col + tensor-core contraction needs scratch
+        need = _lib.lib().nsr_conv_fprop_workspace(C.byref(d))
+        if need:
+            ws = scratch(need, x.device)
+            d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     M = B * H * W
     with _prof(("conv_dgrad" if dgrad else "conv_fprop") + ("_sti" if x_is_sti else ""), (M, cin, cout, pw.kh),
                2.0 * M * cin * cout * pw.kh * pw.kw, 4.0 * M * (cin + cout)):

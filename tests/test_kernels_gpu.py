@@ -355,3 +355,32 @@ def test_wgrad_tma_3x3(B, H, W, cin, cout, x_ld):
     dw2 = torch.empty_like(dw)
     ops.conv_wgrad(x, dy, dw2, None, 3, 3, engine="tcgen05")
     assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 96, 96, 3, 64), (2, 96, 96, 64, 3), (1, 128, 160, 1, 64), (1, 128, 160, 64, 1),
+                                            (2, 96, 100, 4, 48), (3, 80, 72, 128, 3)])
+def test_narrow_conv_as_gemm(B, H, W, cin, cout):
+    """<= 4-channel convs at sizes where they run as im2col + tcgen05 contraction (conv_narrow_gemm.cu):
+    fprop with epilogue, dgrad, wgrad + bias grad, vs torch fp32 autograd and vs the exact-fp32 engine."""
+    from neosr_b200 import ops
+    x = rnd(B, cin, H, W, seed=1).requires_grad_(True)
+    w = rnd(cout, cin, 3, 3, seed=2, scale=1 / math.sqrt(cin * 9)).requires_grad_(True)
+    b = rnd(cout, seed=3, scale=0.1).requires_grad_(True)
+    y_ref = F.conv2d(x, w, b, 1, 1)
+    dy = rnd(B, cout, H, W, seed=4)
+    y_ref.backward(dy)
+    pw = ops.PackedWeight(w.detach()).refresh()
+    xh, dyh = nhwc(x.detach()), nhwc(dy)
+    y = ops.conv_fprop(xh, pw, b.detach())
+    assert rel(nchw(y), y_ref.detach()) < 2e-5
+    assert rel(y, ops.conv_fprop(xh, pw, b.detach(), engine="simt")) < 2e-5
+    if cin <= 4:  # fused epilogue of the wide side
+        y2, pre = ops.conv_fprop(xh, pw, b.detach(), act="lrelu", act_slope=0.2, want_pre=True)
+        assert rel(nchw(pre), y_ref.detach()) < 2e-5
+        assert rel(nchw(y2), F.leaky_relu(y_ref.detach(), 0.2)) < 2e-5
+    dx = ops.conv_fprop(dyh, pw, None, dgrad=True)
+    assert rel(nchw(dx), x.grad) < 2e-5
+    dw, db = torch.empty_like(w), torch.empty_like(b)
+    ops.conv_wgrad(xh, dyh, dw, db, 3, 3)
+    assert rel(dw, w.grad) < 5e-5
+    assert rel(db, b.grad) < 1e-5

@@ -1,15 +1,15 @@
-import torch, time, os
+import torch, os
 from neosr_b200 import ops
-def bench(B,H,W,cin,cout,n=20):
-    x=torch.randn(B,H,W,cin,device="cuda"); dy=torch.randn(B,H,W,cout,device="cuda")
-    dw=torch.empty(cout,cin,3,3,device="cuda")
-    for _ in range(3): ops.conv_wgrad(x,dy,dw,None,3,3)
+def t(fn,n=10):
+    for _ in range(2): fn()
     torch.cuda.synchronize()
     e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n): ops.conv_wgrad(x,dy,dw,None,3,3)
+    for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
-    ms=e0.elapsed_time(e1)/n
-    print(f"wgrad B{B} {H}x{W} {cin}->{cout}: {ms*1e3:8.1f} us  {2*B*H*W*cin*cout*9/ms/1e9:7.1f} TF",flush=True)
-for s in [(16,64,64,192,64),(16,64,64,160,32),(16,64,64,64,32),(32,64,64,180,180),(8,128,128,64,256),(16,256,256,64,64),(4,32,32,512,512)]:
-    bench(*s)
+    return e0.elapsed_time(e1)/n*1e3
+for (B,H,W,cin,cout) in [(32,256,256,3,64),(32,256,256,64,3)]:
+    x=torch.randn(B,H,W,cin,device="cuda"); dy=torch.randn(B,H,W,cout,device="cuda")
+    w=torch.randn(cout,cin,3,3,device="cuda")*0.1; b=torch.zeros(cout,device="cuda")
+    pw=ops.PackedWeight(w).refresh(); dw=torch.empty_like(w); db=torch.empty_like(b)
+    print(f"{cin}->{cout} fprop {t(lambda: ops.conv_fprop(x,pw,b)):8.1f} us  dgrad {t(lambda: ops.conv_fprop(dy,pw,None,dgrad=True)):8.1f} us  wgrad {t(lambda: ops.conv_wgrad(x,dy,dw,db,3,3)):8.1f} us  (NSR_NARROW_GEMM={os.environ.get('NSR_NARROW_GEMM','1')})")
