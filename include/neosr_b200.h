@@ -222,6 +222,25 @@ int nsr_spectral_norm_bwd(const float* g_wsn, const float* w_sn, const float* u,
                           float* dw_orig, int rows, int cols, int accumulate, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* ---- RealPLKSR pieces (neosr/archs/realplksr_arch.py) ---- */
+/* nn.Mish (DCCM, :14-23) and its derivative times dy. */
+int nsr_mish_fwd(const float* x, float* y, size_t n, void* stream);
+int nsr_mish_bwd(const float* dy, const float* x, float* dx, size_t n, void* stream);
+/* EA gate (:44-53): y = x * sigmoid(s); backward gives dx (gate path only) and ds. */
+int nsr_mul_sigmoid_fwd(const float* x, const float* s, float* y, size_t n, void* stream);
+int nsr_mul_sigmoid_bwd(const float* dy, const float* x, const float* s, float* dx, float* ds, size_t n, void* stream);
+/* y[rows, c*r] += repeat_interleave(x[rows, c], r) (:158-160), NHWC. */
+int nsr_add_repeat_interleave(float* y, const float* x, size_t rows, int c, int r, void* stream);
+/* nn.GroupNorm(groups, c) on NHWC [batch, hw, c] (+ optional residual add, PLKBlock :85-99); mean / rstd
+ * [batch*groups] are saved for the backward, which also yields dgamma / dbeta (overwritten). */
+size_t nsr_groupnorm_workspace(int batch, int c, int groups);
+int nsr_groupnorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y, float* mean,
+                      float* rstd, int batch, int hw, int c, int groups, float eps, void* workspace, size_t workspace_bytes,
+                      void* stream);
+int nsr_groupnorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx,
+                      float* dgamma, float* dbeta, int batch, int hw, int c, int groups, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* y = a * alpha + b * beta (b may be NULL). Gradient accumulation glue. */
 int nsr_axpby(const float* a, float alpha, const float* b, float beta, float* y, size_t n, void* stream);
 /* dx = dy * act'(aux) + (dextra ? dextra : 0) */

@@ -92,6 +92,14 @@ SIGNATURES = {
     "nsr_actgrad_mul2d": (_i, [_p, _i, _p, _i, _p, _i, C.c_longlong, _i, _i, _f, _p]),
     "nsr_nearest_up2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "nsr_nearest_up2_bwd_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "nsr_mish_fwd": (_i, [_p, _p, _z, _p]),
+    "nsr_mish_bwd": (_i, [_p, _p, _p, _z, _p]),
+    "nsr_mul_sigmoid_fwd": (_i, [_p, _p, _p, _z, _p]),
+    "nsr_mul_sigmoid_bwd": (_i, [_p, _p, _p, _p, _p, _z, _p]),
+    "nsr_add_repeat_interleave": (_i, [_p, _p, _z, _i, _i, _p]),
+    "nsr_groupnorm_workspace": (_z, [_i, _i, _i]),
+    "nsr_groupnorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _z, _p]),
+    "nsr_groupnorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _z, _p]),
     "nsr_bilinear_up2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "nsr_bilinear_up2_bwd_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "nsr_conv4x4s2_remap": (_i, [_p, _p, _i, _i, _i, _p]),

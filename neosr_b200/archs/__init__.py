@@ -9,6 +9,7 @@ from . import swinir_arch  # noqa: F401  (registers swinir_*)
 from . import compact_arch  # noqa: F401
 from . import esrgan_arch  # noqa: F401
 from . import unet_arch  # noqa: F401
+from . import realplksr_arch  # noqa: F401
 from . import vgg_arch  # noqa: F401
 
 

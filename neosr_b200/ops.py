@@ -398,6 +398,88 @@ def nearest_up2_bwd(dy: Tensor) -> Tensor:
     return dx
 
 
+def mish_fwd(x: Tensor) -> Tensor:
+    _chk(x, "x")
+    y = torch.empty_like(x)
+    with _prof("nsr_mish_fwd", (x.numel(),), 0.0, 8.0 * x.numel()):
+        check(_lib.lib().nsr_mish_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "nsr_mish_fwd")
+    _count(1)
+    return y
+
+
+def mish_bwd(dy: Tensor, x: Tensor) -> Tensor:
+    _chk(dy, "dy"), _chk(x, "x")
+    dx = torch.empty_like(x)
+    with _prof("nsr_mish_bwd", (x.numel(),), 0.0, 12.0 * x.numel()):
+        check(_lib.lib().nsr_mish_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "nsr_mish_bwd")
+    _count(1)
+    return dx
+
+
+def mul_sigmoid_fwd(x: Tensor, s: Tensor) -> Tensor:
+    _chk(x, "x"), _chk(s, "s")
+    y = torch.empty_like(x)
+    with _prof("nsr_mul_sigmoid_fwd", (x.numel(),), 0.0, 12.0 * x.numel()):
+        check(_lib.lib().nsr_mul_sigmoid_fwd(x.data_ptr(), s.data_ptr(), y.data_ptr(), x.numel(), _stream()),
+              "nsr_mul_sigmoid_fwd")
+    _count(1)
+    return y
+
+
+def mul_sigmoid_bwd(dy: Tensor, x: Tensor, s: Tensor):
+    _chk(dy, "dy"), _chk(x, "x"), _chk(s, "s")
+    dx, ds = torch.empty_like(x), torch.empty_like(x)
+    with _prof("nsr_mul_sigmoid_bwd", (x.numel(),), 0.0, 20.0 * x.numel()):
+        check(_lib.lib().nsr_mul_sigmoid_bwd(dy.data_ptr(), x.data_ptr(), s.data_ptr(), dx.data_ptr(), ds.data_ptr(), x.numel(),
+                                             _stream()), "nsr_mul_sigmoid_bwd")
+    _count(1)
+    return dx, ds
+
+
+def add_repeat_interleave_(y: Tensor, x: Tensor, r: int) -> Tensor:
+    """y[..., c*r + k] += x[..., c] in place (NHWC)."""
+    _chk(y, "y"), _chk(x, "x")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    check(_lib.lib().nsr_add_repeat_interleave(y.data_ptr(), x.data_ptr(), rows, c, r, _stream()), "nsr_add_repeat_interleave")
+    _count(1)
+    return y
+
+
+def groupnorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float = 1e-5, residual: Tensor | None = None):
+    """nn.GroupNorm on NHWC [B,H,W,C] (+ residual); returns (y, mean, rstd)."""
+    for t, n in ((x, "x"), (gamma, "gamma"), (beta, "beta"), (residual, "residual")):
+        _chk(t, n)
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(B * groups, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    L = _lib.lib()
+    ws = scratch(L.nsr_groupnorm_workspace(B, Cc, groups), x.device)
+    with _prof("nsr_groupnorm_fwd", (x.numel(),), 0.0, 16.0 * x.numel()):
+        check(L.nsr_groupnorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(residual), y.data_ptr(), mean.data_ptr(),
+                                  rstd.data_ptr(), B, H * W, Cc, groups, eps, ws.data_ptr(), ws.numel(), _stream()),
+              "nsr_groupnorm_fwd")
+    _count(3)
+    return y, mean, rstd
+
+
+def groupnorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dgamma: Tensor, dbeta: Tensor,
+                  groups: int) -> Tensor:
+    for t, n in ((dy, "dy"), (x, "x"), (gamma, "gamma"), (mean, "mean"), (rstd, "rstd"), (dgamma, "dgamma"), (dbeta, "dbeta")):
+        _chk(t, n)
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    L = _lib.lib()
+    ws = scratch(L.nsr_groupnorm_workspace(B, Cc, groups), x.device)
+    with _prof("nsr_groupnorm_bwd", (x.numel(),), 0.0, 24.0 * x.numel()):
+        check(L.nsr_groupnorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                                  dgamma.data_ptr(), dbeta.data_ptr(), B, H * W, Cc, groups, ws.data_ptr(), ws.numel(),
+                                  _stream()), "nsr_groupnorm_bwd")
+    _count(3)
+    return dx
+
+
 def bilinear_up2(x: Tensor) -> Tensor:
     """F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) on NHWC."""
     _chk(x, "x")

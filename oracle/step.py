@@ -13,7 +13,7 @@ import torch
 from torch import Tensor
 
 from . import losses as L
-from .optim import AdanSFState, EMAState, adan_sf_step, clip_grad_norm
+from .optim import AdamWState, AdanSFState, EMAState, adamw_step, adan_sf_step, clip_grad_norm
 from .swinir import SwinIRConfig, swinir_forward
 
 
@@ -25,14 +25,16 @@ class OracleTrainer:
                  percep_weight: float | None = None, vgg_params: dict | None = None,
                  layer_weights: dict | None = None, optim: dict | None = None,
                  ema: float = 0.999, grad_clip: bool = True, disc: tuple | None = None,
-                 gan_weight: float = 0.1, optim_d: dict | None = None):
+                 gan_weight: float = 0.1, optim_d: dict | None = None, optim_type: str = "adan_sf"):
         self.names = list(params)
         self.params = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
         self.net_fn = net_fn
         self.pixel_weight, self.percep_weight = pixel_weight, percep_weight
         self.vgg_params, self.layer_weights = vgg_params, layer_weights
         self.grad_clip = grad_clip
-        self.opt = AdanSFState([self.params[k] for k in self.names], **(optim or {}))
+        self.optim_type = optim_type  # adan_sf (templates' default) or AdamW (C5, base.py:154-155)
+        state_cls = AdamWState if optim_type == "adamw" else AdanSFState
+        self.opt = state_cls([self.params[k] for k in self.names], **(optim or {}))
         self.ema = EMAState([self.params[k] for k in self.names], ema) if ema and ema > 0 else None
         self.log_dict: OrderedDict = OrderedDict()
         self.last_grads: dict = {}
@@ -92,7 +94,7 @@ class OracleTrainer:
         if torch.isnan(total).any():  # image.py:611-619
             raise ValueError("NaN found, aborting training.")
         self.log_dict = OrderedDict((k, float(v.detach().mean())) for k, v in log.items())
-        adan_sf_step(self.opt, grads)  # image.py:642
+        (adamw_step if self.optim_type == "adamw" else adan_sf_step)(self.opt, grads)  # image.py:642
         if self.disc:
             adan_sf_step(self.opt_d, dgrads)  # image.py:645
         if self.ema is not None:  # image.py:661-662

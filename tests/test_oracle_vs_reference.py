@@ -203,3 +203,23 @@ def test_gan_step_with_unet_discriminator():
         assert _rel(tr.d_params[k].detach(), v.detach()) < 1e-4, k
     for k, v in net_d.named_buffers():
         assert _rel(tr.d_buffers[k], v) < 1e-5, k
+
+
+@pytest.mark.parametrize("use_ea,ks", [(True, 17), (False, 13)])
+def test_realplksr_forward_backward(use_ea, ks):
+    from oracle.realplksr import realplksr_forward, realplksr_param_shapes
+    ref_shim.activate(4)
+    kw = dict(dim=32, n_blocks=2, upscaling_factor=4, kernel_size=ks, use_ea=use_ea)
+    net = ref_shim.build_network({"type": "realplksr", **kw}).train()
+    shapes = realplksr_param_shapes(**kw)
+    assert {k: tuple(v.shape) for k, v in net.named_parameters()} == shapes
+    p = synth_params(shapes, seed=13)
+    net.load_state_dict(p)
+    x = torch.rand(2, 3, 20, 24, generator=torch.Generator().manual_seed(14))
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y, y_ref = realplksr_forward(pr, x, n_blocks=2, kernel_size=ks, use_ea=use_ea), net(x)
+    assert _rel(y, y_ref) < 1e-5
+    (y_ref ** 2).mean().backward()
+    g = torch.autograd.grad((y ** 2).mean(), list(pr.values()))
+    for (k, v), gi in zip(net.named_parameters(), g):
+        assert _rel(gi, v.grad) < 1e-4, k

@@ -1,0 +1,147 @@
+"""RealPLKSR (C5's generator) on the GPU, through the C ABI, against the oracle: support kernels
+(Mish, sigmoid gate, GroupNorm + skip, repeat-interleave add), the 17x17 partial large-kernel convolution on a
+channel slab, the whole network, and C5-shaped training steps (AdamW + EMA)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_mish_and_sigmoid_gate():
+    from neosr_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(3, 5, 7, 16, generator=g) * 6).requires_grad_(True)   # covers the softplus threshold
+    x.data[0, 0, 0, :4] = torch.tensor([25.0, -30.0, 20.0, 0.0])
+    dy = torch.randn(x.shape, generator=g)
+    F.mish(x).backward(dy)
+    assert rel(ops.mish_fwd(x.detach().cuda()), F.mish(x).detach()) < 1e-6
+    assert rel(ops.mish_bwd(dy.cuda(), x.detach().cuda()), x.grad) < 1e-5
+    t = torch.randn(x.shape, generator=g).requires_grad_(True)
+    s = torch.randn(x.shape, generator=g).requires_grad_(True)
+    (t * torch.sigmoid(s)).backward(dy)
+    assert rel(ops.mul_sigmoid_fwd(t.detach().cuda(), s.detach().cuda()), (t * torch.sigmoid(s)).detach()) < 1e-6
+    dt, ds = ops.mul_sigmoid_bwd(dy.cuda(), t.detach().cuda(), s.detach().cuda())
+    assert rel(dt, t.grad) < 1e-5 and rel(ds, s.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,C,G", [(2, 12, 20, 64, 4), (3, 7, 9, 32, 4), (1, 48, 48, 64, 4), (2, 5, 5, 16, 1)])
+def test_groupnorm_fwd_bwd(B, H, W, C, G):
+    from neosr_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(B, C, H, W, generator=g) * 2 + 0.5).requires_grad_(True)
+    gamma = (torch.randn(C, generator=g) * 0.5 + 1).requires_grad_(True)
+    beta = torch.randn(C, generator=g).requires_grad_(True)
+    res = torch.randn(B, C, H, W, generator=g)
+    dy = torch.randn(B, C, H, W, generator=g)
+    y_ref = F.group_norm(x, G, gamma, beta, 1e-5) + res
+    y_ref.backward(dy)
+    nh = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()  # noqa: E731
+    y, mean, rstd = ops.groupnorm_fwd(nh(x.detach()), gamma.detach().cuda(), beta.detach().cuda(), G, 1e-5, residual=nh(res))
+    assert rel(y.permute(0, 3, 1, 2), y_ref.detach()) < 1e-5
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    dx = ops.groupnorm_bwd(nh(dy), nh(x.detach()), gamma.detach().cuda(), mean, rstd, dg, db, G)
+    assert rel(dx.permute(0, 3, 1, 2), x.grad) < 1e-4
+    assert rel(dg, gamma.grad) < 1e-4 and rel(db, beta.grad) < 1e-5
+
+
+def test_repeat_interleave_add_and_large_kernel_slab_conv():
+    from neosr_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 6, 5, 3, generator=g)
+    y = torch.randn(2, 6, 5, 48, generator=g)
+    ref = y + torch.repeat_interleave(x, 16, dim=3)
+    assert torch.equal(ops.add_repeat_interleave_(y.clone().cuda(), x.cuda(), 16).cpu(), ref)
+    # 17x17 conv on the first 16 channels of a 64-channel tensor, written into another tensor's first 16 channels
+    h = torch.randn(2, 64, 24, 32, generator=g).requires_grad_(True)
+    w = (torch.randn(16, 16, 17, 17, generator=g) * 0.02).requires_grad_(True)
+    b = torch.randn(16, generator=g).requires_grad_(True)
+    y_ref = F.conv2d(h[:, :16], w, b, 1, 8)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    hn = h.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    pw = ops.PackedWeight(w.detach().cuda()).refresh()
+    for engine in ("simt", "auto"):
+        t = torch.zeros_like(hn)
+        ops.conv_fprop(ops.Slab(hn, 0, 16), pw, b.detach().cuda(), out=ops.Slab(t, 0, 16), engine=engine)
+        assert rel(t[..., :16].permute(0, 3, 1, 2), y_ref.detach()) < 2e-5, engine
+        assert float(t[..., 16:].abs().max()) == 0.0
+        dyn = dy.permute(0, 2, 3, 1).contiguous().cuda()
+        dx = ops.conv_fprop(dyn, pw, None, dgrad=True, engine=engine)
+        assert rel(dx.permute(0, 3, 1, 2), h.grad[:, :16]) < 2e-5, engine
+        dw, db = torch.empty_like(w).cuda(), torch.empty(16, device="cuda")
+        ops.conv_wgrad(ops.Slab(hn, 0, 16), dyn, dw, db, 17, 17, engine=engine)
+        assert rel(dw, w.grad) < 5e-5 and rel(db, b.grad) < 1e-5, engine
+
+
+@pytest.mark.parametrize("kw", [dict(n_blocks=2, kernel_size=17, use_ea=True), dict(n_blocks=2, kernel_size=13, use_ea=False)])
+def test_realplksr_forward_backward_vs_oracle(kw):
+    from neosr_b200 import ops
+    from neosr_b200.archs import build_network
+    from oracle.realplksr import realplksr_forward, realplksr_param_shapes
+    from oracle.swinir import synth_params
+    shapes = realplksr_param_shapes(dim=64, upscaling_factor=4, **kw)
+    p = synth_params(shapes, seed=61)
+    net = build_network({"type": "realplksr", "dim": 64, "upscaling_factor": 4, **kw})
+    assert {k: tuple(v.shape) for k, v in net.named_parameters()} == shapes
+    net.load_state_dict(p)
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(62)
+    x = torch.rand(2, 3, 24, 32, generator=g)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y_ref = realplksr_forward(pr, x, **kw)
+    gt = torch.rand(y_ref.shape, generator=g)
+    grads = torch.autograd.grad(((y_ref - gt) ** 2).mean(), list(pr.values()))
+    for engine, tol in (("simt", 2e-4), ("auto", 1e-3)):   # smooth activations (Mish, sigmoid): the north-star bound holds
+        ops.DEFAULT_ENGINE = engine
+        try:
+            net.zero_grad()
+            y = net(x.cuda())
+            assert rel(y.detach(), y_ref.detach()) < 1e-4
+            ((y - gt.cuda()) ** 2).mean().backward()
+        finally:
+            ops.DEFAULT_ENGINE = "auto"
+        for (k, v), gi in zip(net.named_parameters(), grads):
+            assert rel(v.grad, gi) < tol, (engine, k, rel(v.grad, gi))
+
+
+def test_c5_shaped_training_steps_vs_oracle():
+    """realplksr x4, L1 loss, AdamW + EMA (C5's optimizer), 3 iterations of the `image` model vs the oracle trainer."""
+    from neosr_b200.models import build_model
+    from oracle.realplksr import realplksr_forward, realplksr_param_shapes
+    from oracle.step import OracleTrainer
+    from oracle.swinir import synth_params
+    kw = dict(n_blocks=2, kernel_size=17, use_ea=True)
+    okw = dict(lr=1e-3, betas=(0.9, 0.99), weight_decay=0.01)
+    opt = {"model_type": "image", "scale": 4, "is_train": True, "dist": False, "rank": 0, "world_size": 1,
+           "network_g": {"type": "realplksr", "upscaling_factor": 4, **kw}, "datasets": {"train": {"patch_size": 24}},
+           "train": {"ema": 0.999, "optim_g": {"type": "AdamW", **okw}, "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0}},
+           "path": {}}
+    model = build_model(opt)
+    p = synth_params(realplksr_param_shapes(**kw), seed=71)
+    model.net_g.load_state_dict(p)
+    tr = OracleTrainer(p, lambda q, x: realplksr_forward(q, x, **kw), pixel_weight=1.0, optim=okw, ema=0.999,
+                       optim_type="adamw")
+    g = torch.Generator().manual_seed(72)
+    for it in range(3):
+        lq, gt = torch.rand(2, 3, 24, 24, generator=g), torch.rand(2, 3, 96, 96, generator=g)
+        model.feed_data({"lq": lq, "gt": gt})
+        model.optimize_parameters(it)
+        tr.feed_data({"lq": lq, "gt": gt})
+        tr.optimize_parameters(it)
+        log = model.get_current_log()
+        for k, v in tr.get_current_log().items():
+            assert abs(log[k] - v) <= 1e-3 * max(1e-3, abs(v)), (it, k, log[k], v)
+    # AdamW's first steps move every weight by ~lr regardless of gradient size (m / sqrt(v) ~ +-1), so weights whose
+    # gradient is near zero amplify 1e-5 gradient differences; bound the parameters loosely and the UPDATE in L2.
+    for k, v in model.net_g.named_parameters():
+        assert rel(v.detach(), tr.params[k].detach()) < 5e-3, k
+        du, dr = (v.detach().cpu() - p[k]).double(), (tr.params[k].detach() - p[k]).double()
+        assert float((du - dr).norm() / dr.norm().clamp_min(1e-30)) < 2e-2, k
+    for i, (k, v) in enumerate(model.net_g_ema.module.named_parameters()):
+        assert rel(v.detach(), tr.ema.avg[i]) < 5e-3, k
