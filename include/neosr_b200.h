@@ -361,6 +361,53 @@ typedef struct NsrAdamW {
 int nsr_adamw_step(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
                    const NsrAdamW* hp, const float* sumsq, void* stream);
 
+/* ------------------------------------------------------------------ OTF degradations --- */
+/* The on-the-fly degradation pipeline of the `otf` model (neosr/models/otf.py:92-283).  Images are
+ * NCHW fp32 planes in [0,1] (the layout feed_data receives); per-sample parameters are small DEVICE
+ * arrays of `batch` floats, so no stage synchronises the host. */
+
+/* filter2D (neosr/utils/diffjpeg.py:558-584): reflect-pad k/2, per-sample k x k correlation shared by
+ * the channels of a sample.  kernel: [kernel_batch, k, k], kernel_batch == 1 (one kernel for all) or
+ * == batch; k odd, <= 21 (any other k is the reference's "Wrong kernel size" ValueError). */
+int nsr_filter2d(const float* img, const float* kernel, float* out, int batch, int channels, int h, int w,
+                 int k, int kernel_batch, void* stream);
+/* F.interpolate(..., mode = area | bilinear | bicubic), align_corners=False, no antialias
+ * (otf.py:126,179-186,222-226,243-247).  mode: 0 area (adaptive average), 1 bilinear, 2 bicubic
+ * (A = -0.75).  coord_scale_* is the source-coordinate scale torch uses: 1/scale_factor when the call
+ * passed scale_factor (otf.py:126), in/out when it passed size. */
+int nsr_resize(const float* in, float* out, int planes, int h, int w, int oh, int ow, int mode,
+               float coord_scale_h, float coord_scale_w, void* stream);
+/* random_add_gaussian_noise_pt(clip=True, rounds=False) (neosr/data/degradations.py:569-605,665-676):
+ * out = clamp(img + N(0,1)*sigma[b]/255 mixed with ONE batch-shared [h,w] gray field for samples with
+ * gray[b] == 1, 0, 1).  z ([batch,3,h,w]) / z_gray ([h,w]): optional caller-provided standard-normal
+ * fields; NULL => drawn in-kernel (Philox4x32-10 keyed by seed, Box-Muller). */
+int nsr_gaussian_noise(const float* img, float* out, const float* sigma, const float* gray, int any_gray,
+                       const float* z, const float* z_gray, int batch, int h, int w, uint64_t seed, void* stream);
+/* random_add_poisson_noise_pt(clip=True, rounds=False) (degradations.py:738-786,851-862).  The
+ * per-sample `vals = 2^ceil(log2(#distinct 8-bit levels))` (torch.unique in a Python loop, 766-768,
+ * 777-779) comes from a 256-bin presence bitmap built on the device.  counts_color ([batch,3,h,w]) /
+ * counts_gray ([batch,1,h,w]): optional caller-provided Poisson draws for lambda = quantised image *
+ * vals; NULL => drawn in-kernel (Philox; product method below lambda 10, PTRS rejection above). */
+size_t nsr_poisson_noise_workspace(int batch);
+int nsr_poisson_noise(const float* img, float* out, const float* scale, const float* gray, int any_gray,
+                      const float* counts_color, const float* counts_gray, int batch, int h, int w,
+                      uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
+/* DiffJPEG(differentiable=False)(clamp(x,0,1), quality) (neosr/utils/diffjpeg.py:254-291,461-508,531-555; the
+ * clamp is the torch.clamp that precedes every call, otf.py:154,232,239): zero-pad to a
+ * multiple of 16, *255, RGB->YCbCr, 2x2 chroma mean, 8x8 DCT, quantise by the (transposed) tables *
+ * quality_to_factor(quality[b]) with round-half-even, dequantise, IDCT, chroma nearest x2, YCbCr->RGB,
+ * clamp, /255, crop — one CTA per 16x16 MCU.  quality: [batch] device floats (the reference converts
+ * them to factors in a per-sample Python loop with tensor compares, 542-543). */
+int nsr_jpeg(const float* img, float* out, const float* quality, int batch, int h, int w, void* stream);
+/* paired_random_crop tensor branch (neosr/data/transforms.py:38-131) for one tensor, optionally fused
+ * with the 8-bit quantisation of otf.py:251 (quantise != 0: clamp(round(x*255),0,255)/255). */
+int nsr_crop(const float* in, float* out, int planes, int h, int w, int top, int left, int ph, int pw,
+             int quantise, void* stream);
+/* Training-pair pool (otf.py:37-90) without the full-pool randperm gather: for i < b,
+ * out[i] = pool[slots[i]] (when dequeue != 0) and pool[slots[i]] = in[i].  slots: [b] int32 on device. */
+int nsr_pool_swap(float* pool, const float* in, float* out, const int32_t* slots, int b, size_t sample_elems,
+                  int dequeue, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

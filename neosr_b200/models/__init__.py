@@ -3,6 +3,7 @@ from __future__ import annotations
 
 from ..registry import MODEL_REGISTRY
 from . import image  # noqa: F401  (registers `image`)
+from . import otf  # noqa: F401  (registers `otf`)
 
 
 def build_model(opt: dict):

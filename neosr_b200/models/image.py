@@ -93,6 +93,7 @@ class image:
         aug = ds.get("augmentation")
         if aug is not None and not (len(aug) == 1 and "none" in aug):
             raise NotImplementedError("neosr_b200.image: apply_augment (augmentations.py:219-310) not built yet")
+        self.aug = None
         self.n_accumulated = 0
         self._ema_updates = 0  # host mirror of net_g_ema.n_averaged (avoids a device read per step)
         self._ema_params = None

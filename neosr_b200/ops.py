@@ -7,7 +7,9 @@ on the hot path.  Activations are NHWC ("tokens"): a tensor of shape [B, H, W, C
 from __future__ import annotations
 
 import ctypes as C
+import math
 
+import numpy as _np
 import torch
 from torch import Tensor
 
@@ -695,3 +697,120 @@ def bce_logits_loss(logits: Tensor, label: float, weight: float, loss_accum: Ten
               "nsr_bce_logits_loss")
     _count(2)
     return val, dl
+
+
+# ----------------------------------------------------------------------------- OTF degradations
+RESIZE_MODE = {"area": 0, "bilinear": 1, "bicubic": 2}
+
+
+def filter2d(img: Tensor, kernel: Tensor) -> Tensor:
+    """filter2D (diffjpeg.py:558-584): img [B,C,H,W], kernel [B or 1, k, k]."""
+    _chk(img, "img"), _chk(kernel, "kernel")
+    B, Cc, H, W = img.shape
+    k = kernel.shape[-1]
+    if k % 2 != 1 or kernel.shape[-2] != k:
+        raise ValueError("Wrong kernel size")  # the reference's message (diffjpeg.py:571-573)
+    out = torch.empty_like(img)
+    with _prof("nsr_filter2d", (B, Cc, H, W, k), 2.0 * img.numel() * k * k, 8.0 * img.numel()):
+        check(_lib.lib().nsr_filter2d(img.data_ptr(), kernel.data_ptr(), out.data_ptr(), B, Cc, H, W, k,
+                                      kernel.shape[0], _stream()), "nsr_filter2d")
+    _count(1)
+    return out
+
+
+def resize(img: Tensor, mode: str, *, scale_factor: float | None = None, size: tuple[int, int] | None = None) -> Tensor:
+    """F.interpolate(img, scale_factor=... | size=..., mode=area|bilinear|bicubic) (align_corners False, no antialias)."""
+    _chk(img, "img")
+    B, Cc, H, W = img.shape
+    if (scale_factor is None) == (size is None):
+        raise ValueError("only one of size or scale_factor should be defined")
+    if size is None:
+        oh, ow = int(math.floor(float(H) * scale_factor)), int(math.floor(float(W) * scale_factor))
+        rh = rw = float(_np.float32(1.0 / scale_factor))  # torch: (float)(1.0 / scale) when a scale_factor is given
+    else:
+        oh, ow = int(size[0]), int(size[1])
+        rh, rw = float(_np.float32(H) / _np.float32(oh)), float(_np.float32(W) / _np.float32(ow))
+    out = torch.empty((B, Cc, oh, ow), dtype=torch.float32, device=img.device)
+    with _prof("nsr_resize", (B * Cc, H, W, oh, ow, mode), 0.0, 4.0 * (img.numel() + out.numel())):
+        check(_lib.lib().nsr_resize(img.data_ptr(), out.data_ptr(), B * Cc, H, W, oh, ow, RESIZE_MODE[mode], rh, rw,
+                                    _stream()), "nsr_resize")
+    _count(1)
+    return out
+
+
+def gaussian_noise(img: Tensor, sigma: Tensor, gray: Tensor, any_gray: bool, seed: int, z: Tensor | None = None,
+                   z_gray: Tensor | None = None) -> Tensor:
+    """random_add_gaussian_noise_pt(clip=True) with per-sample sigma / gray flags already drawn."""
+    _chk(img, "img"), _chk(sigma, "sigma"), _chk(gray, "gray"), _chk(z, "z"), _chk(z_gray, "z_gray")
+    B, Cc, H, W = img.shape
+    if Cc != 3:
+        raise ValueError("gaussian_noise: RGB images expected")
+    out = torch.empty_like(img)
+    with _prof("nsr_gaussian_noise", (B, H, W), 0.0, 8.0 * img.numel()):
+        check(_lib.lib().nsr_gaussian_noise(img.data_ptr(), out.data_ptr(), sigma.data_ptr(), gray.data_ptr(),
+                                            int(any_gray), _p(z), _p(z_gray), B, H, W, seed & (2**64 - 1), _stream()),
+              "nsr_gaussian_noise")
+    _count(1)
+    return out
+
+
+def poisson_noise(img: Tensor, scale: Tensor, gray: Tensor, any_gray: bool, seed: int,
+                  counts_color: Tensor | None = None, counts_gray: Tensor | None = None) -> Tensor:
+    """random_add_poisson_noise_pt(clip=True) with per-sample scale / gray flags already drawn."""
+    _chk(img, "img"), _chk(scale, "scale"), _chk(gray, "gray"), _chk(counts_color, "counts_color")
+    _chk(counts_gray, "counts_gray")
+    B, Cc, H, W = img.shape
+    if Cc != 3:
+        raise ValueError("poisson_noise: RGB images expected")
+    out = torch.empty_like(img)
+    wsb = _lib.lib().nsr_poisson_noise_workspace(B)
+    ws = scratch(wsb, img.device)
+    with _prof("nsr_poisson_noise", (B, H, W), 0.0, 12.0 * img.numel()):
+        check(_lib.lib().nsr_poisson_noise(img.data_ptr(), out.data_ptr(), scale.data_ptr(), gray.data_ptr(),
+                                           int(any_gray), _p(counts_color), _p(counts_gray), B, H, W,
+                                           seed & (2**64 - 1), ws.data_ptr(), ws.numel(), _stream()), "nsr_poisson_noise")
+    _count(2)
+    return out
+
+
+def jpeg(img: Tensor, quality: Tensor) -> Tensor:
+    """DiffJPEG(differentiable=False)(img, quality=[B] tensor)."""
+    _chk(img, "img"), _chk(quality, "quality")
+    B, Cc, H, W = img.shape
+    if Cc != 3 or quality.numel() != B:
+        raise ValueError("jpeg: RGB images and one quality per sample expected")
+    out = torch.empty_like(img)
+    with _prof("nsr_jpeg", (B, H, W), 0.0, 8.0 * img.numel()):
+        check(_lib.lib().nsr_jpeg(img.data_ptr(), out.data_ptr(), quality.data_ptr(), B, H, W, _stream()), "nsr_jpeg")
+    _count(1)
+    return out
+
+
+def crop(img: Tensor, top: int, left: int, ph: int, pw: int, quantise: bool = False, out: Tensor | None = None) -> Tensor:
+    _chk(img, "img")
+    B, Cc, H, W = img.shape
+    if out is None:
+        out = torch.empty((B, Cc, ph, pw), dtype=torch.float32, device=img.device)
+    with _prof("nsr_crop", (B * Cc, ph, pw), 0.0, 8.0 * out.numel()):
+        check(_lib.lib().nsr_crop(img.data_ptr(), out.data_ptr(), B * Cc, H, W, top, left, ph, pw, int(quantise),
+                                  _stream()), "nsr_crop")
+    _count(1)
+    return out
+
+
+def pool_swap(pool: Tensor, new: Tensor, slots: Tensor, dequeue: bool, out: Tensor | None = None) -> Tensor | None:
+    """pool[slots[i]] <-> new[i]; returns the dequeued samples (dequeue=True) or None (enqueue only)."""
+    _chk(pool, "pool"), _chk(new, "new")
+    if not (slots.is_cuda and slots.dtype == torch.int32 and slots.is_contiguous()):
+        raise ValueError("pool_swap: slots must be a contiguous CUDA int32 tensor")
+    b = new.shape[0]
+    elems = new.numel() // b
+    if pool.numel() // pool.shape[0] != elems:
+        raise ValueError("pool_swap: sample shape mismatch")
+    if dequeue and out is None:
+        out = torch.empty_like(new)
+    with _prof("nsr_pool_swap", (b, elems), 0.0, (12.0 if dequeue else 8.0) * new.numel()):
+        check(_lib.lib().nsr_pool_swap(pool.data_ptr(), new.data_ptr(), _p(out) if dequeue else None, slots.data_ptr(),
+                                       b, elems, int(dequeue), _stream()), "nsr_pool_swap")
+    _count(1)
+    return out if dequeue else None

@@ -223,3 +223,78 @@ def test_realplksr_forward_backward(use_ea, ks):
     g = torch.autograd.grad((y ** 2).mean(), list(pr.values()))
     for (k, v), gi in zip(net.named_parameters(), g):
         assert _rel(gi, v.grad) < 1e-4, k
+
+
+# ---------------------------------------------------------------- OTF degradation pipeline
+def test_otf_stage_functions_vs_reference():
+    """oracle.otf.{filter2d, jpeg, gaussian_noise, poisson_noise} against the reference's own functions
+    (diffjpeg.py:531-584, degradations.py:569-605,738-786) on the same inputs and the same random draws."""
+    from oracle import otf as O
+    from oracle.ref_otf import structured_gt
+    ref_shim.activate(4)
+    import neosr.utils.diffjpeg as dj
+    dj.device = torch.device("cpu")
+    from neosr.data import degradations as D
+    g = torch.Generator().manual_seed(0)
+    img = structured_gt(3, 3, 50, 70)
+    k = torch.rand(3, 21, 21, generator=g)
+    k /= k.sum((1, 2), keepdim=True)
+    assert torch.equal(O.filter2d(img, k), dj.filter2D(img, k))
+    k1 = torch.rand(1, 7, 7, generator=g)
+    assert torch.equal(O.filter2d(img, k1), dj.filter2D(img, k1))
+    with pytest.raises(ValueError, match="Wrong kernel size"):
+        dj.filter2D(img, torch.rand(1, 8, 8))
+    with pytest.raises(ValueError, match="Wrong kernel size"):
+        O.filter2d(img, torch.rand(1, 8, 8))
+    q = torch.tensor([35.0, 50.0, 93.0])
+    ref = dj.DiffJPEG(differentiable=False)(img.clone(), quality=q.clone())
+    assert float((ref - O.jpeg(img, q)).abs().max()) < 1e-6
+    z, zg = torch.randn(3, 3, 50, 70, generator=g), torch.randn(50, 70, generator=g)
+    sigma, gray = torch.tensor([3.0, 10.0, 25.0]), torch.tensor([0.0, 1.0, 0.0])
+    calls, orig = [zg, z], torch.randn
+    torch.randn = lambda *a, **kw: calls.pop(0)
+    try:
+        noise = D.generate_gaussian_noise_pt(img, sigma, gray)
+    finally:
+        torch.randn = orig
+    assert torch.equal(torch.clamp(img + noise, 0, 1), O.gaussian_noise(img, sigma, gray, z, zg))
+    rec, origp = [], torch.poisson
+
+    def fakep(lam, generator=None):
+        rec.append(origp(lam, generator=g))
+        return rec[-1]
+
+    x = img * 0.7 + 0.1 * torch.rand(3, 3, 50, 70, generator=g)
+    scale = torch.tensor([0.5, 1.0, 2.0])
+    torch.poisson = fakep
+    try:
+        noise = D.generate_poisson_noise_pt(x, scale, gray)
+    finally:
+        torch.poisson = origp
+    out, _, _ = O.poisson_noise(x, scale, gray, counts_color=rec[1], counts_gray=rec[0])
+    assert torch.equal(torch.clamp(x + noise, 0, 1), out)
+
+
+def test_otf_feed_data_record_and_replay():
+    """The reference's REAL otf.feed_data on CPU (oracle/ref_otf.py), recorded, then replayed through
+    oracle.otf.degrade + Pool: bit-identical LQ/GT over iterations that fill and then cycle the pool."""
+    import random
+
+    import numpy as np
+
+    from neosr_b200.data.degradations import synth_kernels
+    from oracle import otf as O
+    from oracle import ref_otf as R
+    ds = dict(R.DEGRADATIONS, patch_size=16, batch_size=2)
+    model, pool = None, O.Pool(4)
+    for it in range(5):
+        seed = 500 + it
+        gt = R.structured_gt(seed, 2, 96, 96)
+        rng, pr = np.random.default_rng(seed), random.Random(seed)
+        ks = [synth_kernels(ds, rng, pr) for _ in range(2)]
+        k1, k2, sk = [torch.from_numpy(np.stack([k[i] for k in ks])) for i in range(3)]
+        lq_r, gt_r, plan, fields, perm, model = R.run_reference(gt, k1, k2, sk, ds, 4, seed, model=model, queue_size=4)
+        lq, gtc, _, _ = O.degrade(gt, k1, k2, sk, plan, 4, fields)
+        lq, gtc = pool.step(lq, gtc, perm)
+        assert torch.equal(lq, lq_r) and torch.equal(gtc, gt_r), it
+        assert torch.equal(torch.round(lq * 255) / 255, lq)

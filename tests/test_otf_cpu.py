@@ -1,0 +1,109 @@
+"""OTF degradation pipeline — CPU side: the oracle against the committed fixtures of the reference's REAL
+`otf.feed_data` (tests/golden/otf_feed_data.npz, made by oracle/make_golden_otf.py), the host blur-kernel
+synthesis against the reference's kernels, and the plan drawing logic."""
+import json
+import random
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from neosr_b200.data.degradations import circular_lowpass_kernel, random_mixed_kernels
+from neosr_b200.models.otf import MODES, draw_plan
+from oracle import otf as O
+from oracle.make_golden_otf import CASE, case_inputs
+from oracle.ref_otf import DEGRADATIONS
+
+G = Path(__file__).parent / "golden"
+
+
+def _plan(z, it):
+    return json.loads(bytes(z[f"{it}.plan"]).decode())
+
+
+def test_oracle_reproduces_reference_feed_data():
+    """Bit-exact: inputs and torch-RNG draws are regenerated from the seed, the host decisions come from the
+    fixture, the outputs must equal what the reference's own feed_data produced (pool included)."""
+    z = np.load(G / "otf_feed_data.npz")
+    c = CASE
+    ds = dict(DEGRADATIONS, patch_size=c["patch_size"], batch_size=c["batch"])
+    pool = O.Pool(c["queue_size"])
+    dequeued = 0
+    for it in range(c["iters"]):
+        seed = c["seed0"] + it
+        gt, k1, k2, sk = case_inputs(seed, ds, c["batch"], c["hr"])
+        gen = torch.Generator().manual_seed(seed)
+        lq, gtc, _, _ = O.degrade(gt, k1, k2, sk, _plan(z, it), c["scale"], ds=ds, gen=gen)
+        perm = None
+        if f"{it}.perm" in z:
+            perm = torch.randperm(c["queue_size"], generator=gen)  # the reference draws it right after (otf.py:70)
+            assert np.array_equal(perm.numpy(), z[f"{it}.perm"])
+            dequeued += 1
+        lq, gtc = pool.step(lq, gtc, perm)
+        assert np.array_equal(np.round(lq.numpy() * 255).astype(np.uint8), z[f"{it}.lq"]), it
+        assert np.array_equal(lq.numpy(), z[f"{it}.lq"].astype(np.float32) / np.float32(255)), it
+        assert np.array_equal(gtc.numpy(), z[f"{it}.gt"].astype(np.float32) / np.float32(255)), it
+    assert dequeued >= 4
+
+
+def test_host_decisions_match_reference_for_equal_seeds():
+    z = np.load(G / "otf_feed_data.npz")
+    c = CASE
+    ds = dict(DEGRADATIONS, patch_size=c["patch_size"], batch_size=c["batch"])
+    for it in range(c["iters"]):
+        seed = c["seed0"] + it
+        p = draw_plan(ds, c["batch"], c["hr"], c["hr"], c["scale"], np.random.default_rng(seed), random.Random(seed),
+                      np.random.default_rng(7))
+        ref = _plan(z, it)
+        for k in ("scale1", "mode1", "gauss1", "blur2", "scale2", "mode2", "gauss2", "sinc_first", "mode3", "top", "left"):
+            assert p[k] == ref[k], (it, k, p[k], ref[k])
+
+
+def test_plan_ranges():
+    ds = dict(DEGRADATIONS, patch_size=24, batch_size=8)
+    rng, pr, rd = np.random.default_rng(0), random.Random(0), np.random.default_rng(1)
+    seen_modes, gauss = set(), 0
+    for _ in range(300):
+        p = draw_plan(ds, 8, 128, 128, 4, rng, pr, rd)
+        assert p["scale1"] == 1 or 0.5 <= p["scale1"] <= 1.5
+        assert p["scale2"] == 1 or 0.3 <= p["scale2"] <= 1.5
+        assert {p["mode1"], p["mode2"], p["mode3"]} <= set(MODES)
+        seen_modes |= {p["mode1"]}
+        for i, sfx in ((1, ""), (2, "2")):
+            if p[f"gauss{i}"]:
+                gauss += 1
+                lo, hi = ds["noise_range" + sfx]
+                assert p[f"sigma{i}"].shape == (8,) and (p[f"sigma{i}"] >= lo).all() and (p[f"sigma{i}"] <= hi).all()
+            else:
+                lo, hi = ds["poisson_scale_range" + sfx]
+                assert (p[f"pscale{i}"] >= lo).all() and (p[f"pscale{i}"] <= hi).all()
+            assert set(np.unique(p[f"gray{i}"])) <= {0.0, 1.0}
+        assert (p["jpeg_q1"] >= 40).all() and (p["jpeg_q1"] <= 95).all()
+        assert (p["jpeg_q2"] >= 35).all() and (p["jpeg_q2"] <= 95).all()
+        assert 0 <= p["top"] <= 32 - 24 and 0 <= p["left"] <= 32 - 24
+    assert seen_modes == set(MODES)
+    assert 60 < gauss < 180  # gaussian_noise_prob = 0.2 on 600 draws
+
+
+def test_blur_kernels_match_reference():
+    z = np.load(G / "otf_kernels.npz")
+    ds = DEGRADATIONS
+    for seed in range(12):
+        k = 7 + 2 * (seed % 8)
+        mine = random_mixed_kernels(ds["kernel_list"], ds["kernel_prob"], k, ds["blur_sigma"], ds["blur_sigma"],
+                                    [-np.pi, np.pi], ds["betag_range"], ds["betap_range"], np.random.default_rng(seed),
+                                    random.Random(seed))
+        np.testing.assert_allclose(mine.astype(np.float32), z[f"mixed{seed}"], rtol=1e-6, atol=1e-9)
+        assert abs(mine.sum() - 1) < 1e-12
+        sinc = circular_lowpass_kernel(np.pi / 3 + 0.15 * seed, k, pad_to=21)
+        assert sinc.shape == (21, 21)
+        np.testing.assert_allclose(sinc.astype(np.float32), z[f"sinc{seed}"], rtol=1e-6, atol=1e-9)
+
+
+def test_oracle_jpeg_fp64_agrees_with_fp32():
+    """The fp64 twin of the oracle JPEG (tie-breaker for quantiser flips) agrees with fp32 except on flips."""
+    x = torch.rand(2, 3, 40, 56, generator=torch.Generator().manual_seed(0))
+    q = torch.tensor([30.0, 80.0])
+    a, b = O.jpeg(x, q), O.jpeg(x.double(), q.double()).float()
+    d = (a - b).abs()
+    assert float((d > 1e-4).float().mean()) < 2e-3
