@@ -408,6 +408,46 @@ int nsr_crop(const float* in, float* out, int planes, int h, int w, int top, int
 int nsr_pool_swap(float* pool, const float* in, float* out, const int32_t* slots, int b, size_t sample_elems,
                   int dequeue, void* stream);
 
+/* ------------------------------------------------------------------ MS-SSIM / consistency losses --- */
+/* mssim_loss (neosr/losses/ssim_loss.py:66-163) on NCHW fp32 [planes = B*C, h, w] images, built from per-scale
+ * calls so the caller owns the pyramid buffers:
+ *   for s in 0..4:  nsr_ssim_scale_fwd(x_s, y_s) -> sums[2s] = sum(cs), sums[2s+1] = sum(ssim), partials3_s;
+ *                   x_{s+1} = nsr_avgpool2(x_s, pad = size % 2)                      (ssim_loss.py:141-143)
+ *   nsr_msssim_finalize: loss = weight * (1 - prod_s mean_s^{w_s}), coef[s] = dloss/dsum_s  (device scalars)
+ *   for s in 4..0:  nsr_ssim_scale_bwd -> dx_s = coef[s]*(G(P0) + 2x G(P1) + y G(P2)) + avgpool2^T(dx_{s+1}).
+ * window: [window_size, window_size] fp32 on the device (the module's `gaussian_window` buffer, one channel);
+ * the filter is F.conv2d with zero padding window_size/2 (ssim_loss.py:57-64).  partials3: [3, planes, h, w]. */
+int nsr_avgpool2(const float* in, float* out, int planes, int h, int w, int pad_h, int pad_w, void* stream);
+size_t nsr_ssim_scale_workspace(int planes, int h, int w);
+int nsr_ssim_scale_fwd(const float* x, const float* y, const float* window, int window_size, float c1, float c2,
+                       int use_ssim, float* partials3, float* sums2, int planes, int h, int w, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int nsr_msssim_finalize(const float* sums, const float* counts, int nscales, float weight, float* coef,
+                        float* loss_value, float* loss_accum, void* stream);
+int nsr_ssim_scale_bwd(const float* partials3, const float* x, const float* y, const float* window, int window_size,
+                       const float* coef, const float* dx_coarse, int coarse_h, int coarse_w, int pad_h, int pad_w,
+                       float* dx, int planes, int h, int w, void* stream);
+/* consistency_loss (neosr/losses/consistency_loss.py:146-192), criterion "chc".  x_blur / y_blur are
+ * nsr_filter2d(nsr_clamp(x, 1/255, 1), GaussianBlur(21, 3) kernel) (reflect padding, torchvision) or the clamped
+ * images when blur is off.  fwd writes the CIE-L* planes [B,h,w], the loss and — in the workspace — the column
+ * cosine terms and the device flag of the `cosim < 1e-3` branch (186-190); bwd writes g_blur = dloss/dx_blur and
+ * d_direct = the Oklab-chroma path gradient; the caller pushes g_blur through the blur's adjoint
+ * (nsr_corr2d_zero_ext with ext = 10, flip = 1, then nsr_reflect_fold, which also adds d_direct and applies the
+ * clamp mask).  The same workspace must be passed to fwd and bwd. */
+int nsr_clamp(const float* in, float* out, size_t n, float lo, float hi, void* stream);
+int nsr_corr2d_zero_ext(const float* img, const float* kernel, float* out, int planes, int h, int w, int k, int ext,
+                        int flip, void* stream);
+size_t nsr_consistency_workspace(int batch, int h, int w);
+int nsr_consistency_fwd(const float* x, const float* y, const float* x_blur, const float* y_blur, float saturation,
+                        float brightness, int use_cosim, float weight, float* luma_x, float* luma_y,
+                        float* loss_value, float* loss_accum, int batch, int h, int w, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int nsr_consistency_bwd(const float* x, const float* y, const float* x_blur, const float* luma_x, const float* luma_y,
+                        float saturation, float weight, float* g_blur, float* d_direct, int batch, int h, int w,
+                        const void* workspace, void* stream);
+int nsr_reflect_fold(const float* dpad, const float* d_direct, const float* x, float* dx, int planes, int h, int w,
+                     int r, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,17 @@ SIGNATURES = {
     "nsr_jpeg": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "nsr_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "nsr_pool_swap": (_i, [_p, _p, _p, _p, _i, _z, _i, _p]),
+    "nsr_avgpool2": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "nsr_ssim_scale_workspace": (_z, [_i, _i, _i]),
+    "nsr_ssim_scale_fwd": (_i, [_p, _p, _p, _i, _f, _f, _i, _p, _p, _i, _i, _i, _p, _z, _p]),
+    "nsr_msssim_finalize": (_i, [_p, _p, _i, _f, _p, _p, _p, _p]),
+    "nsr_ssim_scale_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
+    "nsr_clamp": (_i, [_p, _p, _z, _f, _f, _p]),
+    "nsr_corr2d_zero_ext": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "nsr_consistency_workspace": (_z, [_i, _i, _i]),
+    "nsr_consistency_fwd": (_i, [_p, _p, _p, _p, _f, _f, _i, _f, _p, _p, _p, _p, _i, _i, _i, _p, _z, _p]),
+    "nsr_consistency_bwd": (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _p, _p]),
+    "nsr_reflect_fold": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
 }
 
 _lib = None

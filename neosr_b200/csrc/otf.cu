@@ -223,10 +223,11 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float nz = n[c] * sg / 255.0f;
-      if (any_gray) nz = nz * (1.f - g) + (ng * sg / 255.0f) * g;
+      // every product and sum rounded separately, as the reference's chain of ATen ops does (no FMA contraction)
+      float nz = __fmul_rn(n[c], sg) / 255.0f;
+      if (any_gray) nz = __fadd_rn(__fmul_rn(nz, 1.f - g), __fmul_rn(__fmul_rn(ng, sg) / 255.0f, g));
       const size_t o = ((size_t)b * 3 + c) * hw + pix;
-      out[o] = fminf(fmaxf(img[o] + nz, 0.f), 1.f);
+      out[o] = fminf(fmaxf(__fadd_rn(img[o], nz), 0.f), 1.f);
     }
   }
 }
@@ -286,17 +287,17 @@ __global__ void __launch_bounds__(256) poisson_noise_kernel(const float* __restr
     float ng = 0.f;
     if (any_gray) {
       const float q = quant8(gray_of(v[0], v[1], v[2])) / 255.0f;
-      const float cnt = counts_g ? counts_g[idx] : poisson_sample(ph, q * vg);
-      ng = cnt / vg - q;
+      const float cnt = counts_g ? counts_g[idx] : poisson_sample(ph, __fmul_rn(q, vg));
+      ng = __fsub_rn(cnt / vg, q);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const size_t o = ((size_t)b * 3 + c) * hw + pix;
       const float q = quant8(v[c]) / 255.0f;
-      const float cnt = counts_c ? counts_c[o] : poisson_sample(ph, q * vc);
-      float nz = cnt / vc - q;
-      if (any_gray) nz = nz * (1.f - g) + ng * g;
-      out[o] = fminf(fmaxf(v[c] + nz * sc, 0.f), 1.f);
+      const float cnt = counts_c ? counts_c[o] : poisson_sample(ph, __fmul_rn(q, vc));
+      float nz = __fsub_rn(cnt / vc, q);  // rounded op by op, as the reference's ATen chain (no FMA contraction)
+      if (any_gray) nz = __fadd_rn(__fmul_rn(nz, 1.f - g), __fmul_rn(ng, g));
+      out[o] = fminf(fmaxf(__fadd_rn(v[c], __fmul_rn(nz, sc)), 0.f), 1.f);
     }
   }
 }

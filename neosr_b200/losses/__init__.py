@@ -4,7 +4,7 @@ from __future__ import annotations
 from copy import deepcopy
 
 from ..registry import LOSS_REGISTRY
-from . import basic_loss, gan_loss, vgg_perceptual_loss  # noqa: F401
+from . import basic_loss, consistency_loss, gan_loss, ssim_loss, vgg_perceptual_loss  # noqa: F401
 
 
 def build_loss(opt: dict):

@@ -121,10 +121,12 @@ class image:
         self.cri_pix = mk("pixel_opt")
         self.cri_perceptual = mk("perceptual_opt")
         self.cri_gan = mk("gan_opt")
-        for k in ("mssim_opt", "consistency_opt", "dists_opt", "ldl_opt", "ff_opt", "gw_opt"):
+        self.cri_mssim = mk("mssim_opt")
+        self.cri_consistency = mk("consistency_opt")
+        for k in ("dists_opt", "ldl_opt", "ff_opt", "gw_opt"):
             if train_opt.get(k):
                 raise NotImplementedError(f"neosr_b200.image: train.{k} not built yet")
-        if self.cri_pix is None and self.cri_perceptual is None:
+        if self.cri_pix is None and self.cri_mssim is None and self.cri_perceptual is None:
             raise ValueError("Both pixel/mssim and perceptual losses are None. Please enable at least one.")
         optim_d = train_opt.get("optim_d")  # image.py:259-275
         if self.net_d is None and optim_d is not None:
@@ -202,6 +204,14 @@ class image:
             v, g = self.cri_pix.value_and_grad(out, self.gt, True, total)
             logs["l_g_pix"] = v
             dout = g
+        if self.cri_mssim is not None:  # image.py:479-482
+            v, g = self.cri_mssim.value_and_grad(out, self.gt, True, total)
+            logs["l_g_mssim"] = v
+            dout = g if dout is None else ops.axpby(dout, 1.0, g, 1.0, out=dout)
+        if self.cri_consistency is not None:  # image.py:500-503
+            v, g = self.cri_consistency.value_and_grad(out, self.gt, True, total)
+            logs["l_g_consistency"] = v
+            dout = g if dout is None else ops.axpby(dout, 1.0, g, 1.0, out=dout)
         if self.cri_perceptual is not None:
             v, g = self.cri_perceptual.value_and_grad(out, self.gt, True, total)
             logs["l_g_percep"] = v

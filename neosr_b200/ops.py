@@ -814,3 +814,136 @@ def pool_swap(pool: Tensor, new: Tensor, slots: Tensor, dequeue: bool, out: Tens
                                        b, elems, int(dequeue), _stream()), "nsr_pool_swap")
     _count(1)
     return out if dequeue else None
+
+
+# ----------------------------------------------------------------------------- MS-SSIM / consistency
+def avgpool2(x: Tensor) -> Tensor:
+    """F.avg_pool2d(x, 2, 2, padding=[s % 2 for s in x.shape[2:]]) (ssim_loss.py:141-143)."""
+    B, Cc, H, W = x.shape
+    ph, pw = H % 2, W % 2
+    out = torch.empty((B, Cc, (H + 2 * ph - 2) // 2 + 1, (W + 2 * pw - 2) // 2 + 1), dtype=torch.float32, device=x.device)
+    with _prof("nsr_avgpool2", (B * Cc, H, W), 0.0, 5.0 * x.numel()):
+        check(_lib.lib().nsr_avgpool2(x.data_ptr(), out.data_ptr(), B * Cc, H, W, ph, pw, _stream()), "nsr_avgpool2")
+    _count(1)
+    return out
+
+
+MSSSIM_SCALES = 5
+
+
+def msssim_loss(x: Tensor, y: Tensor, window: Tensor, weight: float, c1: float, c2: float,
+                loss_accum: Tensor | None = None, want_grad: bool = True):
+    """mssim_loss.forward (ssim_loss.py:112-163): returns (loss [1], dloss/dx or None)."""
+    _chk(x, "x"), _chk(y, "y"), _chk(window, "window")
+    if x.shape != y.shape or x.dim() != 4:
+        raise AssertionError(f"x: {tuple(x.shape)} and y: {tuple(y.shape)} must be the same 4-d shape")
+    L = _lib.lib()
+    wsz = window.shape[-1]
+    dev = x.device
+    xs, ys, Ps = [x], [y], []
+    sums = torch.empty(2 * MSSSIM_SCALES, dtype=torch.float32, device=dev)
+    counts = []
+    for s in range(MSSSIM_SCALES):
+        xi, yi = xs[s], ys[s]
+        B, Cc, H, W = xi.shape
+        counts.append(float(xi.numel()))
+        P = torch.empty((3, B * Cc, H, W), dtype=torch.float32, device=dev) if want_grad else None
+        ws = scratch(L.nsr_ssim_scale_workspace(B * Cc, H, W), dev)
+        with _prof("nsr_ssim_scale_fwd", (B * Cc, H, W), 10.0 * wsz * wsz * xi.numel(), (8.0 + 12.0 * want_grad) * xi.numel()):
+            check(L.nsr_ssim_scale_fwd(xi.data_ptr(), yi.data_ptr(), window.data_ptr(), wsz, c1, c2,
+                                       int(s == MSSSIM_SCALES - 1), _p(P), sums[2 * s:].data_ptr(), B * Cc, H, W,
+                                       ws.data_ptr(), ws.numel(), _stream()), "nsr_ssim_scale_fwd")
+        _count(2)
+        Ps.append(P)
+        if s < MSSSIM_SCALES - 1:
+            xs.append(avgpool2(xi))
+            ys.append(avgpool2(yi))
+    counts_t = _const_vec(tuple(counts), dev)
+    coef = torch.empty(MSSSIM_SCALES, dtype=torch.float32, device=dev)
+    val = torch.empty(1, dtype=torch.float32, device=dev)
+    check(L.nsr_msssim_finalize(sums.data_ptr(), counts_t.data_ptr(), MSSSIM_SCALES, weight, coef.data_ptr(), val.data_ptr(),
+                                _p(loss_accum), _stream()), "nsr_msssim_finalize")
+    _count(1)
+    if not want_grad:
+        return val, None
+    dx = None
+    for s in reversed(range(MSSSIM_SCALES)):
+        xi, yi = xs[s], ys[s]
+        B, Cc, H, W = xi.shape
+        d = torch.empty_like(xi)
+        ch, cw = (dx.shape[2], dx.shape[3]) if dx is not None else (0, 0)
+        with _prof("nsr_ssim_scale_bwd", (B * Cc, H, W), 6.0 * wsz * wsz * xi.numel(), 24.0 * xi.numel()):
+            check(L.nsr_ssim_scale_bwd(Ps[s].data_ptr(), xi.data_ptr(), yi.data_ptr(), window.data_ptr(), wsz,
+                                       coef[s:].data_ptr(), _p(dx), ch, cw, H % 2, W % 2, d.data_ptr(), B * Cc, H, W,
+                                       _stream()), "nsr_ssim_scale_bwd")
+        _count(1)
+        dx = d
+    return val, dx
+
+
+_CONST_VECS: dict = {}
+
+
+def _const_vec(values: tuple, device) -> Tensor:
+    """Small constant fp32 device vectors, uploaded once per (values, device)."""
+    key = (values, device.index)
+    t = _CONST_VECS.get(key)
+    if t is None:
+        t = _CONST_VECS[key] = torch.tensor(values, dtype=torch.float32, device=device)
+    return t
+
+
+def clamp(x: Tensor, lo: float, hi: float) -> Tensor:
+    _chk(x, "x")
+    out = torch.empty_like(x)
+    check(_lib.lib().nsr_clamp(x.data_ptr(), out.data_ptr(), x.numel(), lo, hi, _stream()), "nsr_clamp")
+    _count(1)
+    return out
+
+
+def consistency_loss(x: Tensor, y: Tensor, blur_kernel: Tensor | None, saturation: float, brightness: float, cosim: bool,
+                     weight: float, loss_accum: Tensor | None = None, want_grad: bool = True):
+    """consistency_loss.forward (consistency_loss.py:146-192, criterion chc): (loss [1], dloss/dx or None)."""
+    _chk(x, "x"), _chk(y, "y"), _chk(blur_kernel, "blur_kernel")
+    B, Cc, H, W = x.shape
+    if Cc != 3 or x.shape != y.shape:
+        raise ValueError(f"Input size must have a shape of (*, 3, H, W). Got {tuple(x.shape)}")
+    L, dev = _lib.lib(), x.device
+    xc, yc = clamp(x, 1 / 255, 1.0), clamp(y, 1 / 255, 1.0)
+    if blur_kernel is not None:
+        k = blur_kernel.shape[-1]
+        xb, yb = filter2d(xc, blur_kernel.view(1, k, k)), filter2d(yc, blur_kernel.view(1, k, k))
+    else:
+        xb, yb = xc, yc
+    lx = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    ly = torch.empty_like(lx)
+    val = torch.empty(1, dtype=torch.float32, device=dev)
+    wsb = L.nsr_consistency_workspace(B, H, W)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)  # own buffer: fwd -> bwd state must survive other scratch users
+    with _prof("nsr_consistency_fwd", (B, H, W), 0.0, 56.0 * B * H * W):
+        check(L.nsr_consistency_fwd(x.data_ptr(), y.data_ptr(), xb.data_ptr(), yb.data_ptr(), saturation, brightness,
+                                    int(cosim), weight, lx.data_ptr(), ly.data_ptr(), val.data_ptr(), _p(loss_accum), B, H, W,
+                                    ws.data_ptr(), ws.numel(), _stream()), "nsr_consistency_fwd")
+    _count(3)
+    if not want_grad:
+        return val, None
+    g_blur, d_direct = torch.empty_like(x), torch.empty_like(x)
+    with _prof("nsr_consistency_bwd", (B, H, W), 0.0, 68.0 * B * H * W):
+        check(L.nsr_consistency_bwd(x.data_ptr(), y.data_ptr(), xb.data_ptr(), lx.data_ptr(), ly.data_ptr(), saturation, weight,
+                                    g_blur.data_ptr(), d_direct.data_ptr(), B, H, W, ws.data_ptr(), _stream()),
+              "nsr_consistency_bwd")
+    _count(1)
+    dx = torch.empty_like(x)
+    if blur_kernel is not None:
+        r = k // 2
+        dpad = torch.empty((B, 3, H + 2 * r, W + 2 * r), dtype=torch.float32, device=dev)
+        with _prof("nsr_corr2d_zero_ext", (B * 3, H, W, k), 2.0 * k * k * dpad.numel(), 4.0 * (x.numel() + dpad.numel())):
+            check(L.nsr_corr2d_zero_ext(g_blur.data_ptr(), blur_kernel.data_ptr(), dpad.data_ptr(), B * 3, H, W, k, r, 1,
+                                        _stream()), "nsr_corr2d_zero_ext")
+        check(L.nsr_reflect_fold(dpad.data_ptr(), d_direct.data_ptr(), x.data_ptr(), dx.data_ptr(), B * 3, H, W, r, _stream()),
+              "nsr_reflect_fold")
+    else:
+        check(L.nsr_reflect_fold(g_blur.data_ptr(), d_direct.data_ptr(), x.data_ptr(), dx.data_ptr(), B * 3, H, W, 0, _stream()),
+              "nsr_reflect_fold")
+    _count(2)
+    return val, dx

@@ -107,3 +107,97 @@ def gan_loss(logits: Tensor, target_is_real: bool, is_disc: bool, gan_type: str 
     else:
         loss = F.huber_loss(logits, tgt)
     return loss if is_disc else loss * loss_weight
+
+
+# ---------------------------------------------------------------- MS-SSIM (ssim_loss.py:66-163)
+def gaussian_window(window_size: int = 11, sigma: float = 1.5) -> Tensor:
+    """GaussianFilter2D._get_gaussian_window1d/2d, ssim_loss.py:42-52 (one channel, [k,k])."""
+    x = torch.arange(-(window_size // 2), window_size // 2 + 1)
+    w = torch.exp(-0.5 * x**2 / (sigma * sigma))
+    w = (w / w.sum()).reshape(1, window_size)
+    return torch.matmul(w.t(), w)
+
+
+def msssim_loss(x: Tensor, y: Tensor, loss_weight: float = 1.0, window_size: int = 11, sigma: float = 1.5,
+                K1: float = 0.01, K2: float = 0.03, L: float = 1.0) -> Tensor:
+    """mssim_loss.forward / msssim / _ssim, ssim_loss.py:112-163."""
+    C1, C2 = (K1 * L) ** 2, (K2 * L) ** 2
+    win = gaussian_window(window_size, sigma).to(x.dtype).view(1, 1, window_size, window_size).repeat(x.shape[1], 1, 1, 1)
+    filt = lambda t: F.conv2d(t, win, stride=1, padding=window_size // 2, groups=t.shape[1])  # noqa: E731
+    comps = []
+    for i, w in enumerate((0.0448, 0.2856, 0.3001, 0.2363, 0.1333)):
+        mu_x, mu_y = filt(x), filt(y)
+        s2x, s2y, sxy = filt(x * x) - mu_x * mu_x, filt(y * y) - mu_y * mu_y, filt(x * y) - mu_x * mu_y
+        A1, A2 = 2 * mu_x * mu_y + C1, 2 * sxy + C2
+        B1, B2 = mu_x.pow(2) + mu_y.pow(2) + C1, s2x + s2y + C2
+        cs = A2 / B2
+        ssim = (A1 / B1) * cs
+        if i == 4:
+            comps.append(ssim.mean() ** w)
+        else:
+            comps.append(cs.mean() ** w)
+            pad = [s % 2 for s in x.shape[2:]]
+            x, y = F.avg_pool2d(x, 2, 2, padding=pad), F.avg_pool2d(y, 2, 2, padding=pad)
+    prod = comps[0]
+    for c in comps[1:]:
+        prod = prod * c
+    return loss_weight * (1 - prod)
+
+
+# ---------------------------------------------------------------- consistency (consistency_loss.py:14-192)
+def _lin_rgb(img: Tensor) -> Tensor:
+    return torch.where(img <= 0.04045, img / 12.92, torch.pow((img + 0.055) / 1.055, 2.4))
+
+
+def _oklab_chroma(img: Tensor) -> Tensor:
+    img = _lin_rgb(img)
+    r, g, b = img[:, 0], img[:, 1], img[:, 2]
+    l = 0.4122214708 * r + 0.5363325363 * g + 0.0514459929 * b
+    m = 0.2119034982 * r + 0.6806995451 * g + 0.1073969566 * b
+    s = 0.0883024619 * r + 0.2817188376 * g + 0.6299787005 * b
+    l_, m_, s_ = (t.sign() * t.abs().pow(1 / 3) for t in (l, m, s))
+    a = 1.9779984951 * l_ - 2.4285922050 * m_ + 0.4505937099 * s_
+    bb = 0.0259040371 * l_ + 0.7827717662 * m_ - 0.8086757660 * s_
+    return torch.stack([a, bb], dim=1)
+
+
+def _l_star(img: Tensor) -> Tensor:
+    img = _lin_rgb(img.permute(0, 2, 3, 1)) @ torch.tensor([0.2126, 0.7152, 0.0722], dtype=img.dtype)
+    img = torch.where(img <= (216 / 24389), img * (img * (24389 / 27)), img.sign() * img.abs().pow(1 / 3) * 116 - 16)
+    return torch.clamp(img / 100, 0, 1)
+
+
+def gaussian_blur_21_3(x: Tensor) -> Tensor:
+    """torchvision GaussianBlur(21, 3): reflect pad 10, separable kernel as a 2-D depthwise conv."""
+    half = 10.0
+    t = torch.linspace(-half, half, steps=21)
+    pdf = torch.exp(-0.5 * (t / 3.0).pow(2))
+    k1 = pdf / pdf.sum()
+    k2 = torch.mm(k1[:, None], k1[None, :]).to(x.dtype)
+    c = x.shape[1]
+    return F.conv2d(F.pad(x, (10, 10, 10, 10), mode="reflect"), k2.expand(c, 1, 21, 21), groups=c)
+
+
+def _chc(a: Tensor, b: Tensor) -> Tensor:  # chc_loss(loss_lambda=0, clip_min=0, clip_max=1), basic_loss.py:192-219
+    return torch.mean(torch.clamp(torch.sqrt((a - b) ** 2 + 1e-12), 0, 1))
+
+
+def consistency_loss(x: Tensor, gt: Tensor, loss_weight: float = 1.0, blur: bool = True, cosim: bool = True,
+                     saturation: float = 1.0, brightness: float = 1.0, force_cosim: bool | None = None) -> Tensor:
+    """consistency_loss.forward, consistency_loss.py:146-192 (criterion chc).  force_cosim overrides the
+    data-dependent `cosim < 1e-3` branch (tests only)."""
+    x, gt = torch.clamp(x, 1 / 255, 1), torch.clamp(gt, 1 / 255, 1)
+    if blur:
+        il = _l_star(torch.clamp(gaussian_blur_21_3(x), 0, 1))
+        tl = _l_star(torch.clamp(gaussian_blur_21_3(gt), 0, 1)) * brightness
+    else:
+        il, tl = _l_star(x), _l_star(gt) * brightness
+    ic = torch.clamp(_oklab_chroma(x) + 0.5, 0, 1)
+    tc = torch.clamp(_oklab_chroma(gt) * saturation + 0.5, 0, 1)
+    loss = _chc(il, tl) + _chc(ic, tc)
+    if cosim:
+        sim = torch.nn.CosineSimilarity(dim=1, eps=1e-20)
+        cs = 0.5 * (1 - sim(ic, tc).mean()) + 0.5 * (1 - sim(il, tl).mean())
+        if (force_cosim is None and cs < 1e-3) or force_cosim:
+            loss = loss + cs
+    return loss * loss_weight

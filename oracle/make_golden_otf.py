@@ -66,11 +66,36 @@ def kernel_cases():
         out[f"sinc{seed}"] = D.circular_lowpass_kernel(np.pi / 3 + 0.15 * seed, 7 + 2 * (seed % 8), pad_to=21).astype(np.float32)
     np.savez_compressed(OUT / "otf_kernels.npz", **out)
 
+def loss_cases():
+    """mssim_loss / consistency_loss values and input gradients from the reference modules (ssim_loss.py, consistency_loss.py)."""
+    from neosr.losses.consistency_loss import consistency_loss
+    from neosr.losses.ssim_loss import mssim_loss
+    out = {}
+    for tag, (x, gt) in loss_inputs().items():
+        x = x.clone().requires_grad_(True)
+        for name, mod in (("mssim", mssim_loss(loss_weight=1.0)), ("cons", consistency_loss(loss_weight=1.0)),
+                          ("cons_noblur", consistency_loss(blur=False, saturation=1.1, brightness=0.95, loss_weight=0.5))):
+            v = mod(x, gt)
+            g, = torch.autograd.grad(v, x)
+            out[f"{tag}.{name}.value"] = np.float32(v.item())
+            out[f"{tag}.{name}.grad"] = g.numpy().copy()
+    np.savez_compressed(OUT / "losses_ssim_consistency.npz", **out)
+
+
+def loss_inputs():
+    g = torch.Generator().manual_seed(11)
+    gt = R.structured_gt(12, 2, 48, 40)
+    far = (gt + 0.1 * torch.randn(gt.shape, generator=g)).clamp(-0.05, 1.05)
+    near = gt + 0.002 * torch.randn(gt.shape, generator=g)  # cosim < 1e-3: the cosine branch is live
+    return {"far": (far, gt), "near": (near, gt)}
+
+
 
 if __name__ == "__main__":
     assert ref_shim.available(), "needs /root/reference"
     ref_shim.activate(4)
     feed_data_cases()
     kernel_cases()
-    for f in sorted(OUT.glob("otf_*.npz")):
+    loss_cases()
+    for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

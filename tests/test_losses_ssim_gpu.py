@@ -1,0 +1,102 @@
+"""MS-SSIM and consistency loss kernels (csrc/losses_ssim.cu) through the C ABI: value and input gradient against
+the CPU oracle's autograd (oracle/losses.py, pinned to the reference modules).  Bound: 1e-3 relative
+(`north_star`); measured errors are ~1e-5."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from neosr_b200.losses import build_loss  # noqa: E402
+from oracle import losses as OL  # noqa: E402
+from oracle.make_golden_otf import loss_inputs  # noqa: E402
+from oracle.ref_otf import structured_gt  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _check(mod, fn, x, gt, vtol=1e-5, gtol=1e-3):
+    xo = x.clone().requires_grad_(True)
+    vo = fn(xo, gt)
+    go, = torch.autograd.grad(vo, xo)
+    acc = torch.zeros(1, device="cuda")
+    v, g = mod.value_and_grad(x.cuda().contiguous(), gt.cuda(), True, acc)
+    assert abs(float(v) - float(vo)) <= vtol * max(abs(float(vo)), 1e-3), (float(v), float(vo))
+    assert float(acc) == float(v)
+    assert rel(g, go) < gtol, rel(g, go)
+    v2, g2 = mod.value_and_grad(x.cuda().contiguous(), gt.cuda(), False, None)
+    assert g2 is None and float(v2) == float(v)
+    return rel(g, go)
+
+
+@pytest.mark.parametrize("shape", [(2, 96, 80), (1, 64, 64), (3, 50, 38), (2, 33, 47)])
+@pytest.mark.parametrize("weight", [1.0, 0.4])
+def test_mssim_loss(shape, weight):
+    b, h, w = shape
+    gt = structured_gt(21, b, h, w)
+    x = (gt + 0.1 * torch.randn(gt.shape, generator=torch.Generator().manual_seed(1))).clamp(-0.05, 1.05)
+    mod = build_loss({"type": "mssim_loss", "loss_weight": weight}).cuda()
+    _check(mod, lambda a, c: OL.msssim_loss(a, c, weight), x, gt)
+
+
+def test_mssim_module_surface():
+    mod = build_loss({"type": "mssim_loss"})
+    assert tuple(mod.gaussian_filter.gaussian_window.shape) == (3, 1, 11, 11)
+    assert torch.equal(mod.gaussian_filter.gaussian_window[1, 0], OL.gaussian_window())
+    with pytest.raises(ValueError, match="Window size must be odd"):
+        build_loss({"type": "mssim_loss", "window_size": 10})
+    # autograd surface (the reference's closure calls loss(pred, gt).backward())
+    gt = structured_gt(3, 1, 32, 32)
+    x = (gt * 0.9 + 0.03).cuda().requires_grad_(True)
+    mod = mod.cuda()
+    mod(x, gt.cuda()).backward()
+    xo = (gt * 0.9 + 0.03).requires_grad_(True)
+    OL.msssim_loss(xo, gt).backward()
+    assert rel(x.grad, xo.grad) < 1e-3
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(blur=False), dict(saturation=1.2, brightness=0.9, loss_weight=0.5), dict(cosim=False)])
+@pytest.mark.parametrize("shape", [(2, 96, 80), (2, 30, 44)])
+def test_consistency_loss_far(kw, shape):
+    b, h, w = shape
+    gt = structured_gt(22, b, h, w)
+    x = (gt + 0.1 * torch.randn(gt.shape, generator=torch.Generator().manual_seed(2))).clamp(-0.05, 1.05)
+    mod = build_loss({"type": "consistency_loss", **kw}).cuda()
+    okw = dict(kw)
+    lw = okw.pop("loss_weight", 1.0)
+    _check(mod, lambda a, c: OL.consistency_loss(a, c, lw, **okw), x, gt)
+
+
+@pytest.mark.parametrize("blur", [True, False])
+def test_consistency_loss_cosine_branch_live(blur):
+    """Prediction within 0.002 of GT: cosim < 1e-3, so the cosine terms enter the loss and its gradient
+    (consistency_loss.py:186-190) — decided on the device, no host sync."""
+    x, gt = loss_inputs()["near"]
+    assert float(OL.consistency_loss(x, gt, blur=blur)) != float(OL.consistency_loss(x, gt, blur=blur, force_cosim=False))
+    mod = build_loss({"type": "consistency_loss", "blur": blur}).cuda()
+    _check(mod, lambda a, c: OL.consistency_loss(a, c, 1.0, blur=blur), x, gt, gtol=2e-3)
+
+
+def test_image_model_full_loss_stack_step():
+    """`image` step with the template loss stack of the otf configs minus GAN/perceptual (mssim 1.0 + consistency 1.0
+    + L1) on compact: log keys and values vs the oracle losses on the same output."""
+    from neosr_b200.models import build_model
+    opt = {"model_type": "image", "scale": 2, "is_train": True, "dist": False, "rank": 0, "world_size": 1,
+           "network_g": {"type": "compact", "num_feat": 16, "num_conv": 2, "upscale": 2}, "datasets": {"train": {"patch_size": 24}},
+           "train": {"ema": 0.999, "optim_g": {"type": "adan_sf", "lr": 1e-3, "betas": (0.98, 0.92, 0.987), "weight_decay": 0.02,
+                                               "schedule_free": True, "warmup_steps": 100},
+                     "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0}, "mssim_opt": {"type": "mssim_loss", "loss_weight": 1.0},
+                     "consistency_opt": {"type": "consistency_loss", "loss_weight": 1.0}}, "path": {}, "cuda_graph": False}
+    model = build_model(opt)
+    gt = structured_gt(5, 2, 48, 48)
+    lq = torch.nn.functional.avg_pool2d(gt, 2)
+    model.feed_data({"lq": lq, "gt": gt})
+    model.optimize_parameters(0)
+    log = model.get_current_log()
+    out = model.output.cpu()
+    assert list(log)[:4] == ["l_g_pix", "l_g_mssim", "l_g_consistency", "l_g_total"]
+    assert abs(log["l_g_mssim"] - float(OL.msssim_loss(out, gt))) < 1e-4
+    assert abs(log["l_g_consistency"] - float(OL.consistency_loss(out, gt))) < 1e-4
+    assert abs(log["l_g_total"] - (log["l_g_pix"] + log["l_g_mssim"] + log["l_g_consistency"])) < 1e-5

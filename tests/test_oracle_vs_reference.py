@@ -298,3 +298,24 @@ def test_otf_feed_data_record_and_replay():
         lq, gtc = pool.step(lq, gtc, perm)
         assert torch.equal(lq, lq_r) and torch.equal(gtc, gt_r), it
         assert torch.equal(torch.round(lq * 255) / 255, lq)
+
+
+def test_mssim_and_consistency_vs_reference_modules():
+    """oracle.losses.{msssim_loss, consistency_loss} vs the live reference modules: value and input gradient, including
+    the case where the data-dependent cosine branch (consistency_loss.py:186-190) is active."""
+    from oracle.make_golden_otf import loss_inputs
+    ref_shim.activate(4)
+    from neosr.losses.consistency_loss import consistency_loss
+    from neosr.losses.ssim_loss import mssim_loss
+    for tag, (x, gt) in loss_inputs().items():
+        x = x.clone().requires_grad_(True)
+        cases = [(mssim_loss(loss_weight=0.7), lambda a, b: OL.msssim_loss(a, b, 0.7)),
+                 (consistency_loss(), lambda a, b: OL.consistency_loss(a, b)),
+                 (consistency_loss(blur=False, saturation=1.2, brightness=0.9, loss_weight=0.5),
+                  lambda a, b: OL.consistency_loss(a, b, 0.5, blur=False, saturation=1.2, brightness=0.9))]
+        for mod, fn in cases:
+            r, o = mod(x, gt), fn(x, gt)
+            gr, = torch.autograd.grad(r, x)
+            go, = torch.autograd.grad(o, x)
+            assert float(r.detach()) == float(o.detach()), tag
+            assert _rel(go, gr) < 1e-6, tag

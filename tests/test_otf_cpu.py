@@ -107,3 +107,22 @@ def test_oracle_jpeg_fp64_agrees_with_fp32():
     a, b = O.jpeg(x, q), O.jpeg(x.double(), q.double()).float()
     d = (a - b).abs()
     assert float((d > 1e-4).float().mean()) < 2e-3
+
+
+def test_oracle_mssim_consistency_vs_reference_fixture():
+    """oracle.losses.{msssim_loss, consistency_loss} (values + input gradients) against fixtures written from the
+    reference modules; the `near` case has the data-dependent cosine branch active (consistency_loss.py:186-190)."""
+    from oracle import losses as OL
+    from oracle.make_golden_otf import loss_inputs
+    z = np.load(G / "losses_ssim_consistency.npz")
+    for tag, (x, gt) in loss_inputs().items():
+        x = x.clone().requires_grad_(True)
+        for name, fn in (("mssim", lambda a, b: OL.msssim_loss(a, b, 1.0)), ("cons", lambda a, b: OL.consistency_loss(a, b, 1.0)),
+                         ("cons_noblur", lambda a, b: OL.consistency_loss(a, b, 0.5, blur=False, saturation=1.1, brightness=0.95))):
+            v = fn(x, gt)
+            g, = torch.autograd.grad(v, x)
+            assert abs(float(v) - float(z[f"{tag}.{name}.value"])) <= 1e-6 * abs(float(v)), (tag, name)
+            ref = torch.from_numpy(z[f"{tag}.{name}.grad"])
+            assert float((g - ref).abs().max() / ref.abs().max()) < 1e-5, (tag, name)
+    near = loss_inputs()["near"]
+    assert float(OL.consistency_loss(*near)) != float(OL.consistency_loss(*near, force_cosim=False))

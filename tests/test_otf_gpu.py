@@ -236,8 +236,9 @@ def test_feed_data_in_kernel_rng_runs_and_is_seeded():
             lq, g = m._dequeue_and_enqueue(lq, g)
             assert lq.shape == (4, 3, 24, 24) and g.shape == (4, 3, 96, 96)
             assert float(lq.min()) >= 0 and float(lq.max()) <= 1
-            assert torch.equal(torch.round(lq * 255) / 255, lq)
-            res.append((lq.cpu(), g.cpu()))
+            lq, g = lq.cpu(), g.cpu()
+            assert torch.equal(torch.round(lq * 255) / 255, lq)  # on the CPU: true division, as the kernel does
+            res.append((lq, g))
         assert m.queue_ptr == 8
         outs.append(res)
     for (a, b), (c2, d) in zip(*outs):
