@@ -448,6 +448,40 @@ int nsr_consistency_bwd(const float* x, const float* y, const float* x_blur, con
 int nsr_reflect_fold(const float* dpad, const float* d_direct, const float* x, float* dx, int planes, int h, int w,
                      int r, void* stream);
 
+/* ------------------------------------------------------------------ HAT pieces (neosr/archs/hat_arch.py) --- */
+/* Generic (cross-)window attention over qkv [tokens = batch*h*w, 3*c] (q | k | v, heads split c as in the reference's
+ * reshape):  queries = the ws x ws window, keys/values = the ows x ows window centred on it (ows == ws: HAB
+ * self-attention with cyclic shift + {0,-100} mask as index math, hat_arch.py:168-215,299-350; ows > ws: OCAB,
+ * keys/values are the zero-padded neighbourhood nn.Unfold(ows, stride ws, pad (ows-ws)/2) would materialise,
+ * 445-515 — padded keys score `bias` and carry value 0, exactly as in the reference).  bias_table:
+ * [(ws+ows-1)^2, heads]; the relative-position index is computed arithmetically (1015-1068; OCA's negative entries
+ * wrap to the end of the table as Python indexing does).  out: [tokens, c]; lse: log-sum-exp per (window, head,
+ * query) for the backward pass (nsr_xwin_attn_stat_floats floats).  head dim <= 32, (ws+ows-1) <= 39. */
+size_t nsr_xwin_attn_stat_floats(int batch, int h, int w, int heads, int ws);
+int nsr_xwin_attn_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int batch, int h, int w, int c,
+                      int heads, int ws, int ows, int shift, int use_mask, float scale, void* stream);
+size_t nsr_xwin_attn_bwd_workspace(int batch, int h, int w, int c, int heads, int ws, int ows);
+/* dqkv [tokens, 3c] and dbias_table are OVERWRITTEN; deterministic (fixed-order partial sums). */
+int nsr_xwin_attn_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
+                      float* dqkv, float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int ows,
+                      int shift, int use_mask, float scale, void* workspace, size_t workspace_bytes, void* stream);
+/* ChannelAttention (hat_arch.py:15-37) on NHWC [batch, hw, c]:
+ *   pooled = nsr_channel_mean(x, NULL, scale = 1/hw)            AdaptiveAvgPool2d(1)
+ *   gate   = sigmoid(W2 relu(W1 pooled + b1) + b2)              the two 1x1 convs (w1: [cs, c], w2: [c, cs])
+ *   y (+)= alpha * x * gate                                     `x * y`, fused with HAB's `conv_x * conv_scale` (349)
+ * backward: dgate = nsr_channel_mean(g, x, scale = alpha) (sum of g*x), nsr_channel_gate_bwd (parameter gradients
+ * overwritten, summed over the batch in order), dx = alpha * g * gate + dpooled / hw. */
+int nsr_channel_mean(const float* x, const float* mul, float* pooled, int batch, int hw, int c, float scale, void* stream);
+int nsr_channel_gate_fwd(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                         float* hidden, float* gate, int batch, int c, int cs, void* stream);
+int nsr_channel_scale_add(const float* x, const float* gate, float* y, int batch, int hw, int c, float alpha,
+                          int accumulate, void* stream);
+int nsr_channel_gate_bwd(const float* dgate, const float* gate, const float* hidden, const float* pooled, const float* w1,
+                         const float* w2, float* dpooled, float* dw1, float* db1, float* dw2, float* db2, int batch,
+                         int c, int cs, void* stream);
+int nsr_channel_scale_bwd(const float* g, const float* gate, const float* dpooled, float* dx, int batch, int hw, int c,
+                          float alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ from . import compact_arch  # noqa: F401
 from . import esrgan_arch  # noqa: F401
 from . import unet_arch  # noqa: F401
 from . import realplksr_arch  # noqa: F401
+from . import hat_arch  # noqa: F401
 from . import vgg_arch  # noqa: F401
 
 

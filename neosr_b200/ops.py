@@ -947,3 +947,90 @@ def consistency_loss(x: Tensor, y: Tensor, blur_kernel: Tensor | None, saturatio
               "nsr_reflect_fold")
     _count(2)
     return val, dx
+
+
+# ----------------------------------------------------------------------------- HAT pieces
+def xwin_attn_fwd(qkv: Tensor, table: Tensor, heads: int, ws: int, ows: int, shift: int, scale: float):
+    """qkv [B,H,W,3C] -> (out [B,H,W,C], lse).  ows == ws: HAB window self-attention; ows > ws: OCAB."""
+    _chk(qkv, "qkv"), _chk(table, "table")
+    B, H, W, c3 = qkv.shape
+    c = c3 // 3
+    L = _lib.lib()
+    out = torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty(L.nsr_xwin_attn_stat_floats(B, H, W, heads, ws), dtype=torch.float32, device=qkv.device)
+    nk = ows * ows
+    with _prof("nsr_xwin_attn_fwd", (B * H * W, c, heads, ws, ows), 4.0 * B * H * W * nk * c, 16.0 * qkv.numel() / 3):
+        check(L.nsr_xwin_attn_fwd(qkv.data_ptr(), table.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, W, c, heads, ws, ows,
+                                  shift, int(shift > 0), scale, _stream()), "nsr_xwin_attn_fwd")
+    _count(1)
+    return out, lse
+
+
+def xwin_attn_bwd(qkv: Tensor, table: Tensor, out: Tensor, dout: Tensor, lse: Tensor, dtable: Tensor, heads: int, ws: int,
+                  ows: int, shift: int, scale: float) -> Tensor:
+    _chk(qkv, "qkv"), _chk(table, "table"), _chk(out, "out"), _chk(dout, "dout"), _chk(dtable, "dtable")
+    B, H, W, c3 = qkv.shape
+    c = c3 // 3
+    L = _lib.lib()
+    dqkv = torch.empty_like(qkv)
+    ws_t = scratch(L.nsr_xwin_attn_bwd_workspace(B, H, W, c, heads, ws, ows), qkv.device)
+    nk = ows * ows
+    with _prof("nsr_xwin_attn_bwd", (B * H * W, c, heads, ws, ows), 14.0 * B * H * W * nk * c, 28.0 * qkv.numel() / 3):
+        check(L.nsr_xwin_attn_bwd(qkv.data_ptr(), table.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                  dqkv.data_ptr(), dtable.data_ptr(), B, H, W, c, heads, ws, ows, shift, int(shift > 0), scale,
+                                  ws_t.data_ptr(), ws_t.numel(), _stream()), "nsr_xwin_attn_bwd")
+    _count(4 if ows != ws else 3)
+    return dqkv
+
+
+def channel_mean(x: Tensor, mul: Tensor | None, scale: float) -> Tensor:
+    """[B,H,W,C] -> [B,C]: scale * sum over pixels of x (* mul)."""
+    _chk(x, "x"), _chk(mul, "mul")
+    B, H, W, c = x.shape
+    out = torch.empty((B, c), dtype=torch.float32, device=x.device)
+    with _prof("nsr_channel_mean", (B, H * W, c), 0.0, (8.0 if mul is not None else 4.0) * x.numel()):
+        check(_lib.lib().nsr_channel_mean(x.data_ptr(), _p(mul), out.data_ptr(), B, H * W, c, scale, _stream()), "nsr_channel_mean")
+    _count(1)
+    return out
+
+
+def channel_gate_fwd(pooled: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor):
+    B, c = pooled.shape
+    cs = w1.shape[0]
+    hidden = torch.empty((B, cs), dtype=torch.float32, device=pooled.device)
+    gate = torch.empty((B, c), dtype=torch.float32, device=pooled.device)
+    check(_lib.lib().nsr_channel_gate_fwd(pooled.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                          hidden.data_ptr(), gate.data_ptr(), B, c, cs, _stream()), "nsr_channel_gate_fwd")
+    _count(1)
+    return hidden, gate
+
+
+def channel_scale_add_(y: Tensor, x: Tensor, gate: Tensor, alpha: float, accumulate: bool = True) -> Tensor:
+    _chk(y, "y"), _chk(x, "x")
+    B, H, W, c = x.shape
+    with _prof("nsr_channel_scale_add", (x.numel(),), 0.0, 12.0 * x.numel()):
+        check(_lib.lib().nsr_channel_scale_add(x.data_ptr(), gate.data_ptr(), y.data_ptr(), B, H * W, c, alpha, int(accumulate),
+                                               _stream()), "nsr_channel_scale_add")
+    _count(1)
+    return y
+
+
+def channel_gate_bwd(dgate, gate, hidden, pooled, w1, w2, dw1, db1, dw2, db2) -> Tensor:
+    B, c = gate.shape
+    dpooled = torch.empty_like(gate)
+    check(_lib.lib().nsr_channel_gate_bwd(dgate.data_ptr(), gate.data_ptr(), hidden.data_ptr(), pooled.data_ptr(), w1.data_ptr(),
+                                          w2.data_ptr(), dpooled.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(),
+                                          db2.data_ptr(), B, c, w1.shape[0], _stream()), "nsr_channel_gate_bwd")
+    _count(1)
+    return dpooled
+
+
+def channel_scale_bwd(g: Tensor, gate: Tensor, dpooled: Tensor, alpha: float) -> Tensor:
+    _chk(g, "g")
+    B, H, W, c = g.shape
+    dx = torch.empty_like(g)
+    with _prof("nsr_channel_scale_bwd", (g.numel(),), 0.0, 8.0 * g.numel()):
+        check(_lib.lib().nsr_channel_scale_bwd(g.data_ptr(), gate.data_ptr(), dpooled.data_ptr(), dx.data_ptr(), B, H * W, c, alpha,
+                                               _stream()), "nsr_channel_scale_bwd")
+    _count(1)
+    return dx

@@ -25,11 +25,13 @@ class OracleTrainer:
                  percep_weight: float | None = None, vgg_params: dict | None = None,
                  layer_weights: dict | None = None, optim: dict | None = None,
                  ema: float = 0.999, grad_clip: bool = True, disc: tuple | None = None,
-                 gan_weight: float = 0.1, optim_d: dict | None = None, optim_type: str = "adan_sf"):
+                 gan_weight: float = 0.1, optim_d: dict | None = None, optim_type: str = "adan_sf",
+                 mssim_weight: float | None = None, consistency_weight: float | None = None):
         self.names = list(params)
         self.params = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
         self.net_fn = net_fn
         self.pixel_weight, self.percep_weight = pixel_weight, percep_weight
+        self.mssim_weight, self.consistency_weight = mssim_weight, consistency_weight
         self.vgg_params, self.layer_weights = vgg_params, layer_weights
         self.grad_clip = grad_clip
         self.optim_type = optim_type  # adan_sf (templates' default) or AdamW (C5, base.py:154-155)
@@ -62,6 +64,14 @@ class OracleTrainer:
             l_pix = L.l1_loss(out, self.gt, self.pixel_weight)
             total = total + l_pix
             log["l_g_pix"] = l_pix
+        if self.mssim_weight is not None:  # image.py:478-482
+            l_ms = L.msssim_loss(out, self.gt, self.mssim_weight)
+            total = total + l_ms
+            log["l_g_mssim"] = l_ms
+        if self.consistency_weight is not None:  # image.py:484-491 (match_lq_colors off)
+            l_co = L.consistency_loss(out, self.gt, self.consistency_weight)
+            total = total + l_co
+            log["l_g_consistency"] = l_co
         if self.percep_weight is not None:  # image.py:491-494
             l_per = L.vgg_perceptual_loss(self.vgg_params, out, self.gt, self.percep_weight, self.layer_weights)
             total = total + l_per

@@ -319,3 +319,37 @@ def test_mssim_and_consistency_vs_reference_modules():
             go, = torch.autograd.grad(o, x)
             assert float(r.detach()) == float(o.detach()), tag
             assert _rel(go, gr) < 1e-6, tag
+
+
+def test_hat_oracle_and_module_surface_vs_reference():
+    """oracle.hat.hat_forward (forward + every parameter gradient) against the live reference `hat`; and the product
+    module's state_dict: same keys, order, shapes and index buffers as the reference (checkpoints / optimizer states
+    interchange)."""
+    from neosr_b200.archs.hat_arch import hat as our_hat
+    from oracle.hat import HATConfig, hat_forward, hat_param_shapes
+    ref_shim.activate(4)
+    from neosr.archs.hat_arch import hat
+    kw = dict(img_size=64, embed_dim=36, depths=(2, 2), num_heads=(3, 3), window_size=16, compress_ratio=3, squeeze_factor=6,
+              conv_scale=0.01, overlap_ratio=0.5, mlp_ratio=2, upscale=4)
+    net = hat(drop_path_rate=0.0, upsampler="pixelshuffle", resi_connection="1conv", **kw).train()
+    cfg = HATConfig(**kw)
+    shapes = hat_param_shapes(cfg)
+    assert shapes == {k: tuple(v.shape) for k, v in net.named_parameters()}
+    p = synth_params(shapes, seed=3)
+    net.load_state_dict(p, strict=False)
+    x = torch.rand(2, 3, 32, 48, generator=torch.Generator().manual_seed(1))
+    y_ref = net(x)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y = hat_forward(pr, cfg, x)
+    assert _rel(y.detach(), y_ref.detach()) < 1e-5
+    gt = torch.rand_like(y_ref)
+    ((y_ref - gt) ** 2).mean().backward()
+    g = torch.autograd.grad(((y - gt) ** 2).mean(), list(pr.values()))
+    rg = {k: v.grad for k, v in net.named_parameters()}
+    for k, gi in zip(pr, g):
+        assert _rel(gi, rg[k]) < 2e-4, k
+    ours = our_hat(drop_path_rate=0.0, upsampler="pixelshuffle", resi_connection="1conv", **kw)
+    assert [(k, tuple(v.shape)) for k, v in ours.state_dict().items()] == [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    assert torch.equal(ours.relative_position_index_SA, net.relative_position_index_SA)
+    assert torch.equal(ours.relative_position_index_OCA, net.relative_position_index_OCA)
+    assert int(net.relative_position_index_OCA.min()) < 0  # the reference's OCA index has negative (wrapping) entries
