@@ -25,7 +25,12 @@ sys.path.insert(0, str(ROOT))
 
 # algorithmic work per LR crop for C3 (SURVEY.md §8d / BASELINE.md §3): G fwd+bwd + VGG fwd(x)+fwd(gt)+dgrad(x)
 GFLOP_PER_CROP_C3 = 321.30 + 152.88
+# C2 G 440.56 + VGG 152.88 + D 103.68 + 2*155.52; C4 (hat_l, HR 128) 446.4; C5 (realplksr, HR 192) 421.3
+GFLOP_PER_CROP = {"c3": GFLOP_PER_CROP_C3, "c2": 1008.2, "c4": 446.4, "c5": 421.3}
+DEFAULT_BATCH = {"c3": 32, "c2": 16, "c4": 8, "c5": 64}
 METRIC = "LR-crops/sec (SwinIR-M 4x, 64->256, full training step)"
+METRICS = {"c3": METRIC, "c2": "LR-crops/sec (ESRGAN 4x GAN step, 64->256)",
+           "c4": "LR-crops/sec (HAT-L 4x otf step, HR 128 -> LQ 32)", "c5": "LR-crops/sec (RealPLKSR 4x otf step, HR 192 -> LQ 48)"}
 
 
 def peaks() -> dict:
@@ -42,6 +47,10 @@ WORKLOADS = {
           "grad-clip 1.0, drop_path 0",
     "c2": "C2: esrgan (23 RRDB) x4, 64x64->256x256 RGB, L1(1.0)+vgg19 perceptual(0.5, chc)+GAN(bce 0.1, unet "
           "discriminator with spectral norm), adan_sf on G and D + EMA 0.999, grad-clip 1.0",
+    "c4": "C4: hat_l x4, `otf` model: on-the-fly degradation of 128x128 HR crops (train_hat_otf.toml [degradations]) -> "
+          "32x32 LQ, pool 176, mssim(1.0)+consistency(1.0)+vgg19 perceptual(0.5)+GAN(bce 0.3, unet), adan_sf + EMA",
+    "c5": "C5: realplksr x4, `otf` model: on-the-fly degradation of 192x192 HR crops -> 48x48 LQ, pool 128, "
+          "mssim(1.0)+consistency(1.0)+vgg19 perceptual(0.5)+GAN(bce 0.2, unet), AdamW 5e-4 + EMA 0.999",
 }
 
 
@@ -53,6 +62,26 @@ def make_opt(batch: int, dist: bool, rank: int, world: int, config: str = "c3") 
         o["network_d"] = {"type": "unet", "num_feat": 64}
         o["train"]["optim_d"] = dict(o["train"]["optim_g"])
         o["train"]["gan_opt"] = {"type": "gan_loss", "gan_type": "bce", "loss_weight": 0.1}
+        return o
+    if config in ("c4", "c5"):
+        from oracle.ref_otf import DEGRADATIONS  # a plain dict of the template's [degradations] table (no oracle code runs)
+        o = make_opt(batch, dist, rank, world, "c3")
+        ps = 32 if config == "c4" else 48
+        o.update(name=f"bench_{config}", model_type="otf", manual_seed=1024)
+        o["datasets"]["train"] = dict(DEGRADATIONS, patch_size=ps, batch_size=batch, queue_size=180)
+        o["network_d"] = {"type": "unet", "num_feat": 64}
+        tr = o["train"]
+        del tr["pixel_opt"]
+        tr["mssim_opt"] = {"type": "mssim_loss", "loss_weight": 1.0}
+        tr["consistency_opt"] = {"type": "consistency_loss", "loss_weight": 1.0}
+        tr["gan_opt"] = {"type": "gan_loss", "gan_type": "bce", "loss_weight": 0.3 if config == "c4" else 0.2}
+        if config == "c4":
+            o["network_g"] = {"type": "hat_l", "drop_path_rate": 0.0, "upscale": 4}
+            tr["optim_d"] = dict(tr["optim_g"])
+        else:
+            o["network_g"] = {"type": "realplksr", "upscaling_factor": 4}
+            tr["optim_g"] = {"type": "AdamW", "lr": 5e-4, "betas": [0.9, 0.99], "weight_decay": 0.01}
+            tr["optim_d"] = dict(tr["optim_g"])
         return o
     return {"name": "bench_c3", "model_type": "image", "scale": 4, "is_train": True, "dist": dist, "rank": rank,
             "world_size": world, "num_gpu": world,
@@ -81,6 +110,28 @@ def synth_batches(n: int, batch: int, seed: int, lq_size: int = 64, scale: int =
         lq = torch.round(lq * 255) / 255
         out.append({"lq": lq.contiguous().pin_memory() if torch.cuda.is_available() else lq,
                     "gt": gt.contiguous().pin_memory() if torch.cuda.is_available() else gt})
+    return out
+
+
+def synth_otf_batches(n: int, batch: int, seed: int, hr: int):
+    """OTF inputs: structured-free white-noise GT on 8-bit levels + the three blur kernels per sample
+    from the host synthesis (neosr_b200/data/degradations.py), numpy seed as in the templates."""
+    import random
+
+    import numpy as np
+    import torch
+
+    from neosr_b200.data.degradations import synth_kernels
+    from oracle.ref_otf import DEGRADATIONS
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    rng, pr = np.random.default_rng(seed), random.Random(seed)
+    out = []
+    for _ in range(n):
+        gt = torch.round(torch.rand(batch, 3, hr, hr, generator=g) * 255) / 255
+        ks = [synth_kernels(DEGRADATIONS, rng, pr) for _ in range(batch)]
+        d = {"gt": gt, "kernel1": torch.from_numpy(np.stack([k[0] for k in ks])),
+             "kernel2": torch.from_numpy(np.stack([k[1] for k in ks])), "sinc_kernel": torch.from_numpy(np.stack([k[2] for k in ks]))}
+        out.append({k: (v.contiguous().pin_memory() if torch.cuda.is_available() else v) for k, v in d.items()})
     return out
 
 
@@ -183,11 +234,14 @@ def run_ours(args) -> None:
 
     from neosr_b200 import ops
     from neosr_b200.models import build_model
-    B = args.batch if args.batch else (16 if args.config == "c2" else 32)
+    B = args.batch if args.batch else DEFAULT_BATCH[args.config]
     opt = make_opt(B, world > 1, rank, world, args.config)
     opt["cuda_graph"] = not args.no_graph
     model = build_model(opt)
-    pool = synth_batches(args.pool, B, seed=1024 + rank)
+    if args.config in ("c4", "c5"):
+        pool = synth_otf_batches(args.pool, B, seed=1024 + rank, hr=128 if args.config == "c4" else 192)
+    else:
+        pool = synth_batches(args.pool, B, seed=1024 + rank)
     dev_pool = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in pool]
     torch.cuda.synchronize()
 
@@ -294,7 +348,7 @@ def run_ours(args) -> None:
     if rank == 0:
         crops = B * world * args.steps
         value = crops / (ms * 1e-3)
-        step_tflops = value / world * GFLOP_PER_CROP_C3 / 1e3
+        step_tflops = value / world * GFLOP_PER_CROP[args.config] / 1e3
         out_dir = ROOT / "gpurun_out"
         try:
             out_dir.mkdir(exist_ok=True)
@@ -308,13 +362,13 @@ def run_ours(args) -> None:
             r = cpu_oracle_run(1, 2, 1, budget_s=60.0)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         bytes_in = sum(v.numel() * 4 for v in pool[0].values())
-        line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRICS[args.config], "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded rand, 8-bit quantised; VGG19 weights "
                                                                "seeded-random: no pretrained weights offline)",
                 "config": {"workload": WORKLOADS[args.config], "batch_per_gpu": B,
                            "global_batch": B * world, "parallelism": f"dp{world}",
-                           "l2": "per-step working set (activations > 40 GB at B=32) >> 126 MB L2; pool of "
+                           "l2": "per-step working set (saved activations, GBs) >> 126 MB L2; pool of "
                                  f"{len(pool)} distinct batches cycled"},
                 "clocks": sampler.summary(),
                 "e2e": {"value": crops / (ms_e2e * 1e-3), "unit": "crops/s", "h2d_bytes_per_step": bytes_in,
@@ -324,7 +378,7 @@ def run_ours(args) -> None:
                 "roofline": roof,
                 "step_roofline": {"bound": "tensor", "achieved": step_tflops, "unit": "TFLOP/s",
                                   "peak": pk["bf16_sustained"], "frac": step_tflops / pk["bf16_sustained"],
-                                  "gflop_per_crop": GFLOP_PER_CROP_C3,
+                                  "gflop_per_crop": GFLOP_PER_CROP[args.config],
                                   "note": "whole step vs sustained bf16 peak; the fp32-parity engines are exact-fp32 "
                                           "SIMT or 3xBF16-split tcgen05 (ceiling = peak/3)"},
                 "cpu_baseline": cpu, "final_loss": losses[-1] if losses else None}
@@ -340,8 +394,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="LR crops per GPU per step (default: C3 32, C2 16)")
-    ap.add_argument("--config", default="c3", choices=["c3", "c2"],
-                    help="c3 = BASELINE.json's headline workload (what the driver runs); c2 = the GAN configuration")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"],
+                    help="c3 = BASELINE.json's headline workload (what the driver runs); c2 = the GAN configuration; "
+                         "c4 / c5 = the otf configurations (hat_l / realplksr, per-GPU shapes of BASELINE.json configs[3], [4])")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")
