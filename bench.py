@@ -64,7 +64,7 @@ def make_opt(batch: int, dist: bool, rank: int, world: int, config: str = "c3") 
         o["train"]["gan_opt"] = {"type": "gan_loss", "gan_type": "bce", "loss_weight": 0.1}
         return o
     if config in ("c4", "c5"):
-        from oracle.ref_otf import DEGRADATIONS  # a plain dict of the template's [degradations] table (no oracle code runs)
+        from neosr_b200.data.degradations import TEMPLATE_DEGRADATIONS as DEGRADATIONS
         o = make_opt(batch, dist, rank, world, "c3")
         ps = 32 if config == "c4" else 48
         o.update(name=f"bench_{config}", model_type="otf", manual_seed=1024)
@@ -114,20 +114,21 @@ def synth_batches(n: int, batch: int, seed: int, lq_size: int = 64, scale: int =
 
 
 def synth_otf_batches(n: int, batch: int, seed: int, hr: int):
-    """OTF inputs: structured-free white-noise GT on 8-bit levels + the three blur kernels per sample
-    from the host synthesis (neosr_b200/data/degradations.py), numpy seed as in the templates."""
+    """OTF inputs: STRUCTURED synthetic GT on 8-bit levels (low-pass noise + edges: white noise blurs to
+    a constant and drives MS-SSIM's cs mean negative, whose fractional power is NaN in the reference too) + the three
+    blur kernels per sample from the host synthesis (neosr_b200/data/degradations.py)."""
     import random
 
     import numpy as np
     import torch
 
+    from neosr_b200.data.degradations import TEMPLATE_DEGRADATIONS as DEGRADATIONS
     from neosr_b200.data.degradations import synth_kernels
-    from oracle.ref_otf import DEGRADATIONS
-    g = torch.Generator(device="cpu").manual_seed(seed)
+    from neosr_b200.data.synthetic import structured_gt
     rng, pr = np.random.default_rng(seed), random.Random(seed)
     out = []
-    for _ in range(n):
-        gt = torch.round(torch.rand(batch, 3, hr, hr, generator=g) * 255) / 255
+    for i in range(n):
+        gt = structured_gt(seed * 1009 + i, batch, hr, hr)
         ks = [synth_kernels(DEGRADATIONS, rng, pr) for _ in range(batch)]
         d = {"gt": gt, "kernel1": torch.from_numpy(np.stack([k[0] for k in ks])),
              "kernel2": torch.from_numpy(np.stack([k[1] for k in ks])), "sinc_kernel": torch.from_numpy(np.stack([k[2] for k in ks]))}

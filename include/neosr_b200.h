@@ -408,6 +408,19 @@ int nsr_crop(const float* in, float* out, int planes, int h, int w, int top, int
 int nsr_pool_swap(float* pool, const float* in, float* out, const int32_t* slots, int b, size_t sample_elems,
                   int dequeue, void* stream);
 
+/* apply_augment pieces (neosr/data/augmentations.py:14-310), NCHW fp32.
+ * nsr_resize_aa: clamp(F.interpolate(src[perm], size/scale, mode = bilinear | bicubic, antialias=True), 0, 1) written
+ * into the window (top, left, oh, ow) of dst [batch, channels, dst_h, dst_w] (whole image when the window is the
+ * image): the up/down resizes of apply_augment (257-266, 300-308) and resizemix's paste (104-122).  perm: optional
+ * [batch] int32 device permutation of the source batch.  coord_scale_*: in/out, or 1/scale_factor.
+ * nsr_batch_mix: mode 0  dst = lam*a + lam2*other[perm[b]], lam2 = fp32(1 - lam)   (mixup, 29-31);
+ *                mode 1  dst = a, except dst[:, :, y0:y1, x0:x1] = other[perm ? perm[b] : b] (cutmix 58-59, cutblur 164). */
+int nsr_resize_aa(const float* src, float* dst, const int32_t* perm, int batch, int channels, int h, int w, int oh,
+                  int ow, int dst_h, int dst_w, int top, int left, int bicubic, float coord_scale_h,
+                  float coord_scale_w, void* stream);
+int nsr_batch_mix(const float* a, const float* other, float* dst, const int32_t* perm, int batch, int channels, int h,
+                  int w, int mode, float lam, float lam2, int y0, int y1, int x0, int x1, void* stream);
+
 /* ------------------------------------------------------------------ MS-SSIM / consistency losses --- */
 /* mssim_loss (neosr/losses/ssim_loss.py:66-163) on NCHW fp32 [planes = B*C, h, w] images, built from per-scale
  * calls so the caller owns the pyramid buffers:

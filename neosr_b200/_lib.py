@@ -136,6 +136,8 @@ SIGNATURES = {
     "nsr_jpeg": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "nsr_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "nsr_pool_swap": (_i, [_p, _p, _p, _p, _i, _z, _i, _p]),
+    "nsr_resize_aa": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "nsr_batch_mix": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _i, _i, _i, _p]),
     "nsr_avgpool2": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "nsr_ssim_scale_workspace": (_z, [_i, _i, _i]),
     "nsr_ssim_scale_fwd": (_i, [_p, _p, _p, _i, _f, _f, _i, _p, _p, _i, _i, _i, _p, _z, _p]),

@@ -518,3 +518,93 @@ extern "C" int nsr_pool_swap(float* pool, const float* in, float* out, const int
   NSR_CHECK_LAUNCH("nsr_pool_swap");
   return NSR_OK;
 }
+
+// ------------------------------------------------------------------ augmentations ----------
+// apply_augment pieces (neosr/data/augmentations.py:14-310).  F.interpolate(..., antialias=True) for bilinear /
+// bicubic (PIL-style: triangle / cubic a = -0.5 filters whose support widens with the down-scale factor; ATen
+// upsample_{bilinear,bicubic}2d_aa), as one 2-D gather kernel writing into a window of the destination, with the
+// clamp to [0,1] that follows every call site fused in.
+namespace nsr {
+__device__ __forceinline__ float aa_filter(float x, int cubic) {
+  x = fabsf(x);
+  if (!cubic) return x < 1.f ? 1.f - x : 0.f;
+  const float a = -0.5f;
+  if (x < 1.f) return ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+  if (x < 2.f) return (((x - 5.f) * x + 8.f) * x - 4.f) * a;
+  return 0.f;
+}
+struct AAAxis { int xmin, xsize; float center, invscale, total; };
+__device__ __forceinline__ AAAxis aa_axis(int o, int in, float scale, int cubic) {
+  AAAxis a;
+  const float interp = cubic ? 4.f : 2.f;
+  const float support = scale >= 1.f ? (interp * 0.5f) * scale : interp * 0.5f;
+  a.center = scale * ((float)o + 0.5f);
+  a.invscale = scale >= 1.f ? 1.f / scale : 1.f;
+  a.xmin = max(0, (int)(a.center - support + 0.5f));
+  a.xsize = min(in, (int)(a.center + support + 0.5f)) - a.xmin;
+  a.total = 0.f;
+  for (int k = 0; k < a.xsize; ++k) a.total += aa_filter(((float)(k + a.xmin) - a.center + 0.5f) * a.invscale, cubic);
+  return a;
+}
+// dst[b, c, top + oy, left + ox] = clamp(resize_aa(src[perm ? perm[b] : b, c])[oy, ox], 0, 1)
+__global__ void __launch_bounds__(256) resize_aa_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                        const int32_t* __restrict__ perm, int B, int C, int H, int W, int OH,
+                                                        int OW, int DH, int DW, int top, int left, float sh, float sw, int cubic) {
+  const size_t total = (size_t)B * C * OH * OW;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % OW), oy = (int)((idx / OW) % OH);
+    const int c = (int)((idx / ((size_t)OW * OH)) % C), b = (int)(idx / ((size_t)OW * OH * C));
+    const int sb = perm ? perm[b] : b;
+    const float* s = src + ((size_t)sb * C + c) * H * W;
+    const AAAxis ay = aa_axis(oy, H, sh, cubic), ax = aa_axis(ox, W, sw, cubic);
+    float acc = 0.f;
+    for (int i = 0; i < ay.xsize; ++i) {
+      const float wy = aa_filter(((float)(i + ay.xmin) - ay.center + 0.5f) * ay.invscale, cubic) / ay.total;
+      float row = 0.f;
+      for (int j = 0; j < ax.xsize; ++j)
+        row += s[(size_t)(ay.xmin + i) * W + ax.xmin + j] * (aa_filter(((float)(j + ax.xmin) - ax.center + 0.5f) * ax.invscale, cubic) / ax.total);
+      acc += wy * row;
+    }
+    dst[(((size_t)b * C + c) * DH + top + oy) * DW + left + ox] = fminf(fmaxf(acc, 0.f), 1.f);
+  }
+}
+// mode 0 mixup: dst = lam*a + lam2*other[perm[b]], lam2 = fp32(1-lam)  (other = the GT batch for both GT and LQ, 29-31)
+// mode 1 box copy: dst[box] = other[perm ? perm[b] : b][box]  (cutmix 58-59, cutblur 164); rest of dst = a
+__global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ a, const float* __restrict__ other,
+                                                  float* __restrict__ dst, const int32_t* __restrict__ perm, int B, size_t chw,
+                                                  int H, int W, int mode, float lam, float lam2, int y0, int y1, int x0, int x1) {
+  const size_t total = (size_t)B * chw;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / chw);
+    const size_t e = idx - (size_t)b * chw;
+    const int sb = perm ? perm[b] : b;
+    if (mode == 0) {
+      dst[idx] = __fadd_rn(__fmul_rn(lam, a[idx]), __fmul_rn(lam2, other[(size_t)sb * chw + e]));
+    } else {
+      const int x = (int)(e % W), y = (int)((e / W) % H);
+      dst[idx] = (y >= y0 && y < y1 && x >= x0 && x < x1) ? other[(size_t)sb * chw + e] : a[idx];
+    }
+  }
+}
+}  // namespace nsr
+
+extern "C" int nsr_resize_aa(const float* src, float* dst, const int32_t* perm, int batch, int channels, int h, int w, int oh,
+                             int ow, int dst_h, int dst_w, int top, int left, int bicubic, float coord_scale_h,
+                             float coord_scale_w, void* stream) {
+  NSR_CHECK_ARG(src && dst && src != dst && batch > 0 && channels > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "nsr_resize_aa: bad arguments");
+  NSR_CHECK_ARG(top >= 0 && left >= 0 && top + oh <= dst_h && left + ow <= dst_w, "nsr_resize_aa: window outside the destination");
+  resize_aa_kernel<<<grid_for((size_t)batch * channels * oh * ow), 256, 0, (cudaStream_t)stream>>>(
+      src, dst, perm, batch, channels, h, w, oh, ow, dst_h, dst_w, top, left, coord_scale_h, coord_scale_w, bicubic);
+  NSR_CHECK_LAUNCH("nsr_resize_aa");
+  return NSR_OK;
+}
+extern "C" int nsr_batch_mix(const float* a, const float* other, float* dst, const int32_t* perm, int batch, int channels, int h,
+                             int w, int mode, float lam, float lam2, int y0, int y1, int x0, int x1, void* stream) {
+  NSR_CHECK_ARG(a && other && dst && batch > 0 && channels > 0 && h > 0 && w > 0 && (mode == 0 || mode == 1), "nsr_batch_mix: bad arguments");
+  NSR_CHECK_ARG(dst != other || !perm, "nsr_batch_mix: in-place on the permuted source");
+  mix_kernel<<<grid_for((size_t)batch * channels * h * w), 256, 0, (cudaStream_t)stream>>>(a, other, dst, perm, batch,
+                                                                                         (size_t)channels * h * w, h, w, mode, lam,
+                                                                                         lam2, y0, y1, x0, x1);
+  NSR_CHECK_LAUNCH("nsr_batch_mix");
+  return NSR_OK;
+}

@@ -113,3 +113,17 @@ def synth_kernels(opt: dict, rng: np.random.Generator, pyrandom=_random):
         sinc = np.zeros((21, 21))
         sinc[10, 10] = 1.0  # pulse: no blur
     return k1.astype(np.float32), k2.astype(np.float32), sinc.astype(np.float32)
+
+
+# the [degradations] table shared by options/train_hat_otf.toml and options/train_realplksr_otf.toml
+TEMPLATE_DEGRADATIONS = dict(  # options/train_hat_otf.toml / train_realplksr_otf.toml [degradations]
+    resize_prob=[0.3, 0.4, 0.3], resize_range=[0.5, 1.5], gaussian_noise_prob=0.2, noise_range=[0, 2],
+    poisson_scale_range=[0.05, 0.25], gray_noise_prob=0.1, jpeg_range=[40, 95], second_blur_prob=0.4,
+    resize_prob2=[0.3, 0.4, 0.3], resize_range2=[0.3, 1.5], gaussian_noise_prob2=0.2, noise_range2=[0, 2],
+    poisson_scale_range2=[0.05, 0.1], gray_noise_prob2=0.1, jpeg_range2=[35, 95],
+    blur_kernel_size=7, kernel_list=["iso", "aniso", "generalized_iso", "generalized_aniso", "plateau_iso", "plateau_aniso"],
+    kernel_prob=[0.45, 0.25, 0.12, 0.03, 0.12, 0.03], sinc_prob=0.1, blur_sigma=[0.2, 3], betag_range=[0.5, 4],
+    betap_range=[1, 2], blur_kernel_size2=9,
+    kernel_list2=["iso", "aniso", "generalized_iso", "generalized_aniso", "plateau_iso", "plateau_aniso"],
+    kernel_prob2=[0.45, 0.25, 0.12, 0.03, 0.12, 0.03], sinc_prob2=0.1, blur_sigma2=[0.2, 1.5], betag_range2=[0.5, 4],
+    betap_range2=[1, 2], final_sinc_prob=0.8)

@@ -29,3 +29,16 @@ class SyntheticPairedDataset(Dataset):
     def __getitem__(self, i: int) -> dict:
         lq, gt = synth_pair(i, self.lq_size, self.scale, self.seed)
         return {"lq": lq, "gt": gt, "lq_path": f"synthetic/{i}", "gt_path": f"synthetic/{i}"}
+
+
+def structured_gt(seed: int, b: int, h: int, w: int) -> torch.Tensor:
+    """Structured synthetic GT: low-pass noise + step edges + a flat patch, on 8-bit levels,
+    so the JPEG quantiser, the Poisson level count and the clamps are all exercised."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(b, 3, h, w, generator=g)
+    x = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(x, (4, 4, 4, 4), mode="reflect"), 9, 1)
+    x = (x - x.amin((1, 2, 3), keepdim=True)) / (x.amax((1, 2, 3), keepdim=True) - x.amin((1, 2, 3), keepdim=True))
+    x[:, :, h // 3:, w // 2:] = 1.0 - x[:, :, h // 3:, w // 2:]
+    x[:, :, : h // 4, : w // 4] = 0.25
+    x = x + 0.02 * torch.rand(b, 3, h, w, generator=g)
+    return torch.round(x.clamp(0, 1) * 255) / 255

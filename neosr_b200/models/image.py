@@ -21,11 +21,13 @@ from __future__ import annotations
 
 import copy
 import os
+import random
 import time
 from collections import OrderedDict
 from pathlib import Path
 from typing import Any
 
+import numpy as np
 import torch
 from torch import Tensor
 from torch.optim.swa_utils import AveragedModel, get_ema_multi_avg_fn
@@ -33,6 +35,7 @@ from torch.optim.swa_utils import AveragedModel, get_ema_multi_avg_fn
 from .. import ops
 from ..archs import build_network
 from ..archs.arch_util import set_default_scale
+from ..data.augmentations import draw_augment_plan, run_augment_plan
 from ..dist import allreduce_mean_, broadcast_params_
 from ..losses import build_loss
 from ..optimizers import AdamW, adan_sf
@@ -90,10 +93,14 @@ class image:
         self.accum_iters = ds.get("accumulate", 1) or 1
         if self.accum_iters != 1:
             raise NotImplementedError("neosr_b200.image: accumulate != 1 (ill-defined in the reference, SURVEY.md §3.2)")
-        aug = ds.get("augmentation")
-        if aug is not None and not (len(aug) == 1 and "none" in aug):
-            raise NotImplementedError("neosr_b200.image: apply_augment (augmentations.py:219-310) not built yet")
-        self.aug = None
+        self.aug = ds.get("augmentation")  # image.py:114-115
+        self.aug_prob = ds.get("aug_prob")
+        ps = ds.get("patch_size")
+        if self.aug is not None and ps is not None and ps % 4 != 0:  # image.py:275-277
+            raise ValueError("The patch_size value must be a multiple of 4 while using augmentations.")
+        seed = int(self.opt.get("manual_seed", 1024) or 1024) + int(self.opt.get("rank", 0))
+        self._aug_rng, self._aug_pyrandom = np.random.default_rng([seed, 2]), random.Random(seed + 2)
+        self._aug_rng_dev = np.random.default_rng([seed, 3])
         self.n_accumulated = 0
         self._ema_updates = 0  # host mirror of net_g_ema.n_averaged (avoids a device read per step)
         self._ema_params = None
@@ -173,6 +180,13 @@ class image:
     @torch.no_grad()
     def feed_data(self, data: dict) -> None:  # image.py:374-391
         lq, gt = data["lq"], data.get("gt")
+        if self.is_train and self.aug is not None and gt is not None and not (len(self.aug) == 1 and "none" in self.aug):
+            # image.py:380-391: mixup / cutmix / resizemix / cutblur on the device
+            lq = lq.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            gt = gt.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            plan = draw_augment_plan(gt.size(0), gt.size(2), gt.size(3), self.scale, self.aug, self.aug_prob, self._aug_rng,
+                                     self._aug_pyrandom, self._aug_rng_dev)
+            gt, lq = run_augment_plan(gt, lq, self.scale, plan)
         if self._graph_mode:
             # CUDA-graph replay needs fixed input addresses: copy the batch into static device buffers
             if self._lq_static is None or self._lq_static.shape != lq.shape or (gt is not None and self._gt_static.shape != gt.shape):

@@ -174,6 +174,4 @@ class otf(image):
         plan = draw_plan(self._ds, gt.size(0), gt.size(2), gt.size(3), self.opt["scale"], self._rng, self._pyrandom, self._rng_dev)
         lq, gt = self.run_plan(gt, k1, k2, sk, plan)
         lq, gt = self._dequeue_and_enqueue(lq, gt)
-        if self.aug is not None and self.patch_size % 4 != 0:
-            raise ValueError("The patch_size value must be a multiple of 4 while using augmentations.")
-        super().feed_data({"lq": lq, "gt": gt})
+        super().feed_data({"lq": lq, "gt": gt})  # applies apply_augment when configured (otf.py:266-278)

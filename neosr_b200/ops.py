@@ -79,6 +79,11 @@ _scratch: dict = {}
 
 
 def scratch(nbytes: int, device) -> Tensor:
+    if torch.cuda.is_current_stream_capturing():
+        # Inside a CUDA-graph capture: memory comes from the graph's private pool and dies with the graph, and the raw
+        # handle of the capture stream is recycled by later captures - a cached buffer would dangle (illegal address on
+        # a later graph's replay).  Allocate per call; the pool reuses the block in capture order.
+        return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     s = _scratch.get(key)
     if s is None:
@@ -1034,3 +1039,38 @@ def channel_scale_bwd(g: Tensor, gate: Tensor, dpooled: Tensor, alpha: float) ->
                                                _stream()), "nsr_channel_scale_bwd")
     _count(1)
     return dx
+
+
+# ----------------------------------------------------------------------------- augmentations
+def resize_aa(src: Tensor, mode: str, *, scale_factor: float | None = None, size=None, perm: Tensor | None = None,
+              dst: Tensor | None = None, top: int = 0, left: int = 0) -> Tensor:
+    """clamp(F.interpolate(src[perm], ..., mode=bilinear|bicubic, antialias=True), 0, 1), optionally pasted into the
+    window (top, left) of `dst`."""
+    _chk(src, "src"), _chk(dst, "dst")
+    B, Cc, H, W = src.shape
+    if size is None:
+        oh, ow = int(math.floor(float(H) * scale_factor)), int(math.floor(float(W) * scale_factor))
+        rh = rw = float(_np.float32(1.0 / scale_factor))
+    else:
+        oh, ow = int(size[0]), int(size[1])
+        rh, rw = float(_np.float32(H) / _np.float32(oh)), float(_np.float32(W) / _np.float32(ow))
+    if dst is None:
+        dst = torch.empty((B, Cc, oh, ow), dtype=torch.float32, device=src.device)
+    with _prof("nsr_resize_aa", (B * Cc, H, W, oh, ow), 0.0, 4.0 * (src.numel() + B * Cc * oh * ow)):
+        check(_lib.lib().nsr_resize_aa(src.data_ptr(), dst.data_ptr(), _p(perm), B, Cc, H, W, oh, ow, dst.shape[2], dst.shape[3],
+                                       top, left, int(mode == "bicubic"), rh, rw, _stream()), "nsr_resize_aa")
+    _count(1)
+    return dst
+
+
+def batch_mix(a: Tensor, other: Tensor, perm: Tensor | None, mode: str, lam: float = 0.0, box=(0, 0, 0, 0)) -> Tensor:
+    """mode 'mixup': lam*a + (1-lam)*other[perm]; mode 'box': a with [:, :, y0:y1, x0:x1] taken from other[perm]."""
+    _chk(a, "a"), _chk(other, "other")
+    B, Cc, H, W = a.shape
+    dst = torch.empty_like(a)
+    with _prof("nsr_batch_mix", (a.numel(),), 0.0, 12.0 * a.numel()):
+        check(_lib.lib().nsr_batch_mix(a.data_ptr(), other.data_ptr(), dst.data_ptr(), _p(perm), B, Cc, H, W,
+                                       0 if mode == "mixup" else 1, lam, float(_np.float32(1.0 - lam)), *[int(v) for v in box],
+                                       _stream()), "nsr_batch_mix")
+    _count(1)
+    return dst

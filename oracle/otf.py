@@ -214,3 +214,34 @@ def degrade(gt: Tensor, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, p
     lq = lq[:, :, top:top + ps, left:left + ps]
     gt = gt[:, :, top * scale:(top + ps) * scale, left * scale:(left + ps) * scale]
     return lq.contiguous(), gt.contiguous(), plan, fields
+
+
+def apply_augment(gt: Tensor, lq: Tensor, scale: int, plan: dict):
+    """apply_augment (neosr/data/augmentations.py:219-310) with every draw given by `plan`
+    (neosr_b200.data.augmentations.draw_augment_plan): up-sample LQ (antialias), the mix operations in the
+    reference's order, down-sample (bicubic antialias)."""
+    gt, lq = gt.clone(), lq.clone()
+    if scale > 1:
+        lq = torch.clamp(F.interpolate(lq, scale_factor=scale, mode=plan["up_mode"], antialias=True), 0, 1)
+    for op in plan["ops"]:
+        perm = torch.as_tensor(np.asarray(op["perm"]), dtype=torch.long) if "perm" in op else None
+        if op["op"] == "mixup":  # augmentations.py:14-33
+            lam = op["lam"]
+            g_ = gt[perm]
+            gt, lq = lam * gt + (1 - lam) * g_, lam * lq + (1 - lam) * g_
+        elif op["op"] == "cutmix":  # 36-61
+            x1, y1, x2, y2 = op["box"]
+            g_, l_ = gt[perm], lq[perm]
+            gt[:, :, x1:x2, y1:y2] = g_[:, :, x1:x2, y1:y2]
+            lq[:, :, x1:x2, y1:y2] = l_[:, :, x1:x2, y1:y2]
+        elif op["op"] == "resizemix":  # 64-124
+            x1, y1, x2, y2 = op["box"]
+            g_, l_ = gt.clone()[perm], lq.clone()[perm]
+            gt[:, :, y1:y2, x1:x2] = torch.clamp(F.interpolate(g_, (y2 - y1, x2 - x1), mode="bicubic", antialias=True), 0, 1)
+            lq[:, :, y1:y2, x1:x2] = torch.clamp(F.interpolate(l_, (y2 - y1, x2 - x1), mode="bicubic", antialias=True), 0, 1)
+        else:  # cutblur 127-166
+            x1, y1, x2, y2 = op["box"]
+            lq[:, :, x1:x2, y1:y2] = gt[:, :, x1:x2, y1:y2]
+    if scale > 1:
+        lq = torch.clamp(F.interpolate(lq, scale_factor=1 / scale, mode="bicubic", antialias=True), 0, 1)
+    return gt, lq

@@ -14,30 +14,8 @@ import torch
 
 from oracle import ref_shim
 
-DEGRADATIONS = dict(  # options/train_hat_otf.toml / train_realplksr_otf.toml [degradations]
-    resize_prob=[0.3, 0.4, 0.3], resize_range=[0.5, 1.5], gaussian_noise_prob=0.2, noise_range=[0, 2],
-    poisson_scale_range=[0.05, 0.25], gray_noise_prob=0.1, jpeg_range=[40, 95], second_blur_prob=0.4,
-    resize_prob2=[0.3, 0.4, 0.3], resize_range2=[0.3, 1.5], gaussian_noise_prob2=0.2, noise_range2=[0, 2],
-    poisson_scale_range2=[0.05, 0.1], gray_noise_prob2=0.1, jpeg_range2=[35, 95],
-    blur_kernel_size=7, kernel_list=["iso", "aniso", "generalized_iso", "generalized_aniso", "plateau_iso", "plateau_aniso"],
-    kernel_prob=[0.45, 0.25, 0.12, 0.03, 0.12, 0.03], sinc_prob=0.1, blur_sigma=[0.2, 3], betag_range=[0.5, 4],
-    betap_range=[1, 2], blur_kernel_size2=9,
-    kernel_list2=["iso", "aniso", "generalized_iso", "generalized_aniso", "plateau_iso", "plateau_aniso"],
-    kernel_prob2=[0.45, 0.25, 0.12, 0.03, 0.12, 0.03], sinc_prob2=0.1, blur_sigma2=[0.2, 1.5], betag_range2=[0.5, 4],
-    betap_range2=[1, 2], final_sinc_prob=0.8)
-
-
-def structured_gt(seed: int, b: int, h: int, w: int) -> torch.Tensor:
-    """Structured synthetic GT: low-pass noise + step edges + a flat patch, on 8-bit levels,
-    so the JPEG quantiser, the Poisson level count and the clamps are all exercised."""
-    g = torch.Generator().manual_seed(seed)
-    x = torch.rand(b, 3, h, w, generator=g)
-    x = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(x, (4, 4, 4, 4), mode="reflect"), 9, 1)
-    x = (x - x.amin((1, 2, 3), keepdim=True)) / (x.amax((1, 2, 3), keepdim=True) - x.amin((1, 2, 3), keepdim=True))
-    x[:, :, h // 3:, w // 2:] = 1.0 - x[:, :, h // 3:, w // 2:]
-    x[:, :, : h // 4, : w // 4] = 0.25
-    x = x + 0.02 * torch.rand(b, 3, h, w, generator=g)
-    return torch.round(x.clamp(0, 1) * 255) / 255
+from neosr_b200.data.degradations import TEMPLATE_DEGRADATIONS as DEGRADATIONS  # noqa: E402
+from neosr_b200.data.synthetic import structured_gt  # noqa: E402,F401
 
 
 def make_ref_otf(ds: dict, scale: int, queue_size: int):

@@ -353,3 +353,48 @@ def test_hat_oracle_and_module_surface_vs_reference():
     assert torch.equal(ours.relative_position_index_SA, net.relative_position_index_SA)
     assert torch.equal(ours.relative_position_index_OCA, net.relative_position_index_OCA)
     assert int(net.relative_position_index_OCA.min()) < 0  # the reference's OCA index has negative (wrapping) entries
+
+
+def test_apply_augment_plan_and_oracle_vs_reference():
+    """neosr_b200.data.augmentations.draw_augment_plan draws what the reference's apply_augment draws (same python
+    `random` / numpy streams; torch.randperm results injected), and oracle.otf.apply_augment then reproduces the
+    reference's output bit for bit, over seeds that cover every operation and the multi-augmentation branch."""
+    import random
+
+    import numpy as np
+
+    from neosr_b200.data.augmentations import draw_augment_plan
+    from neosr_b200.data.synthetic import structured_gt
+    from oracle import otf as O
+    ref_shim.activate(4)
+    import neosr.data.augmentations as A
+    augs, prob = ["none", "mixup", "cutmix", "resizemix", "cutblur"], [0.5, 0.1, 0.1, 0.1, 0.5]
+    seen = set()
+    for seed in range(40):
+        gt = structured_gt(seed, 4, 64, 64)
+        lq = torch.nn.functional.avg_pool2d(gt, 4)
+        A.rng, A.random = np.random.default_rng(seed), random.Random(seed)
+        perms, o_randperm, g = [], torch.randperm, torch.Generator().manual_seed(seed)
+
+        def rp(n, **k):
+            perms.append(o_randperm(n, generator=g))
+            return perms[-1]
+
+        torch.randperm = rp
+        try:
+            gr, lr = A.apply_augment(gt.clone(), lq.clone(), scale=4, augs=augs, prob=prob)
+        finally:
+            torch.randperm = o_randperm
+
+        class Replay:
+            i = 0
+
+            def permutation(self, n):
+                self.i += 1
+                return perms[self.i - 1].numpy()
+
+        plan = draw_augment_plan(4, 64, 64, 4, augs, prob, np.random.default_rng(seed), random.Random(seed), Replay())
+        go, lo = O.apply_augment(gt, lq, 4, plan)
+        assert torch.equal(go, gr) and torch.equal(lo, lr), (seed, plan)
+        seen |= {o["op"] for o in plan["ops"]}
+    assert seen == {"mixup", "cutmix", "resizemix", "cutblur"}

@@ -243,3 +243,39 @@ def test_feed_data_in_kernel_rng_runs_and_is_seeded():
         outs.append(res)
     for (a, b), (c2, d) in zip(*outs):
         assert torch.equal(a, c2) and torch.equal(b, d)
+
+
+# ---------------------------------------------------------------- apply_augment (augmentations.py:219-310)
+@pytest.mark.parametrize("mode", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("args", [dict(scale_factor=4), dict(scale_factor=0.25), dict(size=(17, 29)), dict(size=(50, 70)), dict(scale_factor=2)])
+def test_resize_antialias(mode, args):
+    import torch.nn.functional as F
+    img = structured_gt(9, 2, 40, 56) * 1.1 - 0.05
+    ref = torch.clamp(F.interpolate(img, mode=mode, antialias=True, **args), 0, 1)
+    out = ops.resize_aa(img.to(DEV), mode, **args).cpu()
+    assert out.shape == ref.shape and float((out - ref).abs().max()) < 3e-6
+
+
+def test_apply_augment_vs_oracle():
+    """run_augment_plan on plans covering every operation and the multi branch: GT exact where no resampling is involved,
+    everything within fp32 resampling noise of the oracle (== the reference, tests/test_oracle_vs_reference.py)."""
+    from neosr_b200.data.augmentations import draw_augment_plan, run_augment_plan
+    augs, prob = ["none", "mixup", "cutmix", "resizemix", "cutblur"], [0.5, 0.1, 0.1, 0.1, 0.5]
+    seen = set()
+    for seed in range(30):
+        gt = structured_gt(seed, 4, 64, 64)
+        lq = torch.nn.functional.avg_pool2d(gt, 4)
+        plan = draw_augment_plan(4, 64, 64, 4, augs, prob, np.random.default_rng(seed), random.Random(seed), np.random.default_rng(seed + 1))
+        go, lo = O.apply_augment(gt, lq, 4, plan)
+        g, l = run_augment_plan(gt.to(DEV), lq.to(DEV), 4, plan)
+        names = {o["op"] for o in plan["ops"]}
+        seen |= names
+        if "resizemix" not in names:
+            assert torch.equal(g.cpu(), go), (seed, plan)
+        assert float((g.cpu() - go).abs().max()) < 3e-6 and float((l.cpu() - lo).abs().max()) < 5e-6, (seed, plan)
+        assert l.shape == lq.shape
+    assert seen == {"mixup", "cutmix", "resizemix", "cutblur"}
+    with pytest.raises(ValueError, match="batch >1"):
+        draw_augment_plan(1, 64, 64, 4, augs, prob, np.random.default_rng(0))
+    with pytest.raises(ValueError, match="don't match"):
+        draw_augment_plan(4, 64, 64, 4, augs, prob[:3], np.random.default_rng(0))
