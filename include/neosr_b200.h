@@ -247,6 +247,17 @@ int nsr_axpby(const float* a, float alpha, const float* b, float beta, float* y,
 int nsr_actgrad_mul(const float* dy, const float* aux, const float* dextra, float* dx, size_t n,
                     int act, float slope, void* stream);
 
+/* RealPLKSR's partial large-kernel conv (neosr/archs/realplksr_arch.py:26-41): dense k x k (odd, <= 17), 16 -> 16
+ * channels, stride 1, "same" zero padding, on a channel slab of an NHWC tensor (x_ld / y_ld / dy_ld = floats between
+ * consecutive pixels).  Exact fp32.  w_ntc: [n = 16][tap = k*k][c = 16] — the fp32 region at the start of an
+ * nsr_pack_weight() buffer (flavour 0 = fprop, flavour 1 = dgrad: rotated + transposed, so dgrad is the same call on
+ * dy).  wgrad overwrites dw [16,16,k,k] (reference layout) and dbias [16] (may be NULL); deterministic. */
+int nsr_conv_lk16_fprop(const float* x, int x_ld, const float* w_ntc, const float* bias, float* y, int y_ld, int batch,
+                        int h, int w, int k, void* stream);
+size_t nsr_conv_lk16_wgrad_workspace(int batch, int h, int w, int k);
+int nsr_conv_lk16_wgrad(const float* x, int x_ld, const float* dy, int dy_ld, float* dw, float* dbias, int batch, int h,
+                        int w, int k, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ LayerNorm ---------- */
 /* nn.LayerNorm(c, eps) over the last dim of [rows, c] (swinir_arch.py:284,297,708,960). */
 int nsr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,

@@ -17,6 +17,7 @@ from . import _lib
 from ._lib import ACT, ENGINE, NsrConv, NsrWgrad, check
 
 
+LK16_ENABLED = True   # route 16->16-channel k>=7 convs to the dedicated large-kernel kernels (tests flip it)
 DEFAULT_ENGINE = "auto"  # what engine="auto" resolves to ("auto" | "simt" | "tcgen05"); tests flip it
 LAUNCHES = 0          # kernels launched through this module (claim reported by bench.py)
 PROFILE: list | None = None  # when a list: (kernel, shape-key, flops, bytes, start_evt, end_evt) per call
@@ -217,6 +218,19 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
     for t, n in ((bias, "bias"), (prelu, "prelu"), (row_scale, "row_scale")):
         _chk(t, n)
     x_ptr, x_ld = (None, cin) if x_is_sti else _ptr_ld(x)
+    if (LK16_ENABLED and cin == 16 and cout == 16 and pw.kh == pw.kw and pw.kh >= 7 and not x_is_sti and act == "none"
+            and actgrad == "none" and aux is None and prelu is None and row_scale is None and residual is None
+            and not want_pre and not sti_out and f32_out and engine == "auto"):
+        # RealPLKSR's 16-channel large-kernel conv: dedicated exact-fp32 kernel (csrc/conv_lk.cu)
+        y = out if out is not None else torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device)
+        y_ptr, y_ld = _ptr_ld(y)
+        wbuf = pw.dgrad if dgrad else pw.fprop
+        with _prof("conv_lk16_" + ("dgrad" if dgrad else "fprop"), (B * H * W, cin, cout, pw.kh),
+                   2.0 * B * H * W * cin * cout * pw.kh * pw.kw, 4.0 * B * H * W * (cin + cout)):
+            check(_lib.lib().nsr_conv_lk16_fprop(x_ptr, x_ld, wbuf.data_ptr(), _p(bias), y_ptr, y_ld, B, H, W, pw.kh, _stream()),
+                  "nsr_conv_lk16_fprop")
+        _count(1)
+        return y
     aux_ptr, aux_ld = _ptr_ld(aux)
     res_ptr, res_ld = _ptr_ld(residual)
     y = None
@@ -264,6 +278,16 @@ def conv_wgrad(x, dy, dw: Tensor, dbias: Tensor | None, kh: int, kw: int, engine
         raise ValueError(f"conv_wgrad: shape mismatch x{tuple(x.shape)} dy{tuple(dy.shape)} dw{tuple(dw.shape)}")
     x_ptr, x_ld = (None, cin) if isinstance(x, STI) else _ptr_ld(x)
     dy_ptr, dy_ld = (None, cout) if isinstance(dy, STI) else _ptr_ld(dy)
+    if (LK16_ENABLED and cin == 16 and cout == 16 and kh == kw and kh >= 7 and engine == "auto" and x_ptr is not None
+            and dy_ptr is not None):
+        L = _lib.lib()
+        ws = scratch(L.nsr_conv_lk16_wgrad_workspace(B, H, W, kh), dw.device)
+        with _prof("conv_lk16_wgrad", (B * H * W, cin, cout, kh), 2.0 * B * H * W * cin * cout * kh * kw,
+                   4.0 * B * H * W * (cin + cout)):
+            check(L.nsr_conv_lk16_wgrad(x_ptr, x_ld, dy_ptr, dy_ld, dw.data_ptr(), _p(dbias), B, H, W, kh, ws.data_ptr(),
+                                        ws.numel(), _stream()), "nsr_conv_lk16_wgrad")
+        _count(2)
+        return
     d = NsrWgrad(batch=B, h=H, w=W, cin=cin, cout=cout, kh=kh, kw=kw, pad=kh // 2, x_ld=x_ld, dy_ld=dy_ld,
                  engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
                  x=x_ptr, dy=dy_ptr,

@@ -151,3 +151,40 @@ def test_c5_shaped_training_steps_vs_oracle():
         r = tr.ema.avg[i]  # the first EMA update copies the weights, so the same isolated flips show up here
         bad = ((v.detach().cpu() - r).abs() > 5e-3 * r.abs().max().clamp_min(1e-30)).float().mean()
         assert float(bad) < 2e-3, (k, float(bad))
+
+
+@pytest.mark.parametrize("k,hw", [(17, (19, 37)), (13, (48, 48)), (7, (16, 16)), (17, (5, 70))])
+def test_large_kernel_conv_kernels(k, hw):
+    """csrc/conv_lk.cu (the dedicated 16-channel large-kernel fprop / dgrad / wgrad) against torch on the CPU: ragged tile
+    edges, every supported kernel size class, slab leading dims, run-to-run determinism."""
+    from neosr_b200 import ops
+    g = torch.Generator().manual_seed(k)
+    h = torch.randn(2, 64, *hw, generator=g).requires_grad_(True)
+    w = (torch.randn(16, 16, k, k, generator=g) * 0.03).requires_grad_(True)
+    b = torch.randn(16, generator=g).requires_grad_(True)
+    y_ref = F.conv2d(h[:, 16:32], w, b, 1, k // 2)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    hn = h.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    pw = ops.PackedWeight(w.detach().cuda()).refresh()
+    t = torch.zeros(2, *hw, 32, device="cuda")
+    ops.conv_fprop(ops.Slab(hn, 16, 16), pw, b.detach().cuda(), out=ops.Slab(t, 16, 16))
+    assert rel(t[..., 16:].permute(0, 3, 1, 2), y_ref.detach()) < 2e-5
+    assert float(t[..., :16].abs().max()) == 0.0
+    dyn = dy.permute(0, 2, 3, 1).contiguous().cuda()
+    dx = ops.conv_fprop(dyn, pw, None, dgrad=True)
+    assert rel(dx.permute(0, 3, 1, 2), h.grad[:, 16:32]) < 2e-5
+    dw, db = torch.empty_like(w).cuda(), torch.empty(16, device="cuda")
+    ops.conv_wgrad(ops.Slab(hn, 16, 16), dyn, dw, db, k, k)
+    assert rel(dw, w.grad) < 5e-5 and rel(db, b.grad) < 1e-5
+    dw2, db2 = torch.empty_like(dw), torch.empty_like(db)
+    ops.conv_wgrad(ops.Slab(hn, 16, 16), dyn, dw2, db2, k, k)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    n0 = ops.LAUNCHES
+    ops.LK16_ENABLED = False
+    try:
+        t2 = torch.zeros_like(t)
+        ops.conv_fprop(ops.Slab(hn, 16, 16), pw, b.detach().cuda(), out=ops.Slab(t2, 16, 16), engine="simt")
+    finally:
+        ops.LK16_ENABLED = True
+    assert ops.LAUNCHES > n0 and rel(t2, t) < 2e-5
