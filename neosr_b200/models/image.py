@@ -53,6 +53,8 @@ class image:
         self.optimizers: list = []
         self.schedulers: list = []
         self._graph_mode = False
+        self.is_train_mode = False
+        self.ema = -1
         self.log_dict: dict = {}
         set_default_scale(opt.get("scale", 4), self.is_train)
 
@@ -419,5 +421,115 @@ class image:
         for i, s in enumerate(resume_state["schedulers"]):
             self.schedulers[i].load_state_dict(s)
 
-    def validation(self, dataloader, current_iter, tb_logger, save_img: bool = True) -> None:
-        raise NotImplementedError("neosr_b200.image.validation: SURVEY.md §8f.1 (next after the training step)")
+    # ------------------------------------------------------------------ validation (image.py:664-925)
+    def _infer(self, x: Tensor) -> Tensor:
+        net = self.net_g_ema if (self.is_train_mode and self.ema > 0) else self.net_g
+        return net(x.to(self.device, dtype=torch.float32).contiguous())
+
+    @torch.no_grad()
+    def test(self) -> None:
+        """EMA-weights inference on self.lq: whole image (`val.tile = -1`) or the reference's partition scheme with a
+        16-pixel overlap (image.py:664-784).  The forward is the same engine kernels in save=False mode."""
+        self.tile = (self.opt.get("val") or {}).get("tile", -1)
+        scale = self.opt["scale"]
+        self.is_train_mode = getattr(self, "optimizer_g", None) is not None
+        sf = self.is_train_mode and getattr(self, "sf_optim_g", False)
+        if sf:
+            self.optimizer_g.eval()
+        if self.is_train_mode and self.ema > 0:
+            self.net_g_ema.eval()  # also drops the packed-weight images: the fused optimizer updates EMA weights in place
+        else:
+            self.net_g.eval()
+        try:
+            if self.tile == -1:
+                self.output = self._infer(self.lq)
+            else:
+                _, C, h, w = self.lq.size()
+                nh, nw = h // self.tile + 1, w // self.tile + 1
+                pad_h = (nh - h % nh) % nh
+                pad_w = (nw - w % nw) % nw
+                img = self.lq
+                img = torch.cat([img, torch.flip(img, [2])], 2)[:, :, : h + pad_h, :]
+                img = torch.cat([img, torch.flip(img, [3])], 3)[:, :, :, : w + pad_w]
+                _, _, H, W = img.size()
+                sh, sw, shave = H // nh, W // nw, 16
+                ral, row = H // sh, W // sw
+                out = torch.zeros(1, C, H * scale, W * scale, device=self.device)
+                for i in range(ral):
+                    for j in range(row):
+                        top = slice(i * sh - (shave if i > 0 else 0), (i + 1) * sh + (shave if i < ral - 1 else 0))
+                        left = slice(j * sw - (shave if j > 0 else 0), (j + 1) * sw + (shave if j < row - 1 else 0))
+                        o = self._infer(img[..., top, left].contiguous())
+                        _top = slice(0, sh * scale) if i == 0 else slice(shave * scale, (shave + sh) * scale)
+                        _left = slice(0, sw * scale) if j == 0 else slice(shave * scale, (shave + sw) * scale)
+                        out[..., i * sh * scale:(i + 1) * sh * scale, j * sw * scale:(j + 1) * sw * scale] = o[..., _top, _left]
+                self.output = out[:, :, 0:H * scale - pad_h * scale, 0:W * scale - pad_w * scale]
+        finally:
+            self.net_g.train()
+            if sf:
+                self.optimizer_g.train()
+
+    def get_current_visuals(self) -> OrderedDict:  # image.py:925-931
+        out = OrderedDict(lq=self.lq.detach().cpu(), result=self.output.detach().cpu())
+        if getattr(self, "gt", None) is not None:
+            out["gt"] = self.gt.detach().cpu()
+        return out
+
+    def validation(self, dataloader, current_iter, tb_logger, save_img: bool = True) -> None:  # base.py:64-77
+        if self.opt.get("dist"):
+            if self.opt.get("rank", 0) == 0:  # image.py:786-790
+                self.nondist_validation(dataloader, current_iter, tb_logger, save_img)
+        else:
+            self.nondist_validation(dataloader, current_iter, tb_logger, save_img)
+
+    def nondist_validation(self, dataloader, current_iter, tb_logger, save_img: bool = True) -> None:  # image.py:792-901
+        from ._validation import calculate_metric, imwrite, tensor2img
+        was_train, self.is_train = self.is_train, False  # no augmentation / graph buffers during validation
+        graph_mode, self._graph_mode = self._graph_mode, False
+        vopt = self.opt.get("val") or {}
+        ds_opt = getattr(dataloader.dataset, "opt", {}) or {}
+        dataset_name, dataset_type = ds_opt.get("name", "val"), ds_opt.get("type", "paired")
+        with_metrics = dataset_type != "single" and vopt.get("metrics") is not None
+        if with_metrics:
+            self.metric_results = dict.fromkeys(vopt["metrics"].keys(), 0.0)
+            if not hasattr(self, "best_metric_results"):
+                self.best_metric_results = {}
+            self.best_metric_results.setdefault(dataset_name, {
+                m: {"better": c.get("better", "higher"), "val": float("-inf") if c.get("better", "higher") == "higher" else float("inf"),
+                    "iter": -1} for m, c in vopt["metrics"].items()})
+        n = 0
+        try:
+            for val_data in dataloader:
+                lq_path = val_data.get("lq_path", [f"img{n}"])
+                name = Path(lq_path[0] if isinstance(lq_path, (list, tuple)) else lq_path).stem
+                self.feed_data(val_data)
+                self.test()
+                vis = self.get_current_visuals()
+                sr = tensor2img(vis["result"])
+                data = {"img": sr}
+                if "gt" in vis:
+                    data["img2"] = tensor2img(vis["gt"])
+                    self.gt = None
+                self.lq = self.output = None
+                if vopt.get("save_img", save_img) and (self.opt.get("path") or {}).get("visualization"):
+                    root = Path(self.opt["path"]["visualization"])
+                    if self.opt.get("is_train", True):
+                        f = root / name / f"{name}_{current_iter}.png"
+                    else:
+                        f = root / dataset_name / f"{name}_{vopt.get('suffix') or self.opt.get('name', 'b200')}.png"
+                    imwrite(sr, str(f))
+                if with_metrics:
+                    for m, c in vopt["metrics"].items():
+                        self.metric_results[m] += calculate_metric(data, c)
+                n += 1
+        finally:
+            self.is_train, self._graph_mode = was_train, graph_mode
+        if with_metrics and n:
+            for m in self.metric_results:
+                self.metric_results[m] /= n
+                best = self.best_metric_results[dataset_name][m]
+                v = self.metric_results[m]
+                if (best["better"] == "higher" and v >= best["val"]) or (best["better"] != "higher" and v <= best["val"]):
+                    best["val"], best["iter"] = v, current_iter
+                if tb_logger:
+                    tb_logger.add_scalar(f"metrics/{dataset_name}/{m}", v, current_iter)
