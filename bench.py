@@ -340,6 +340,14 @@ def run_ours(args) -> None:
         ach = drec["bytes"] / (drec["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "traffic": None}
+    try:  # measured DRAM traffic per launch of the dominant kernel, from the committed ncu --set full capture
+        tr = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(dname)
+        if tr:
+            roof["traffic"] = tr["bytes_per_launch"]
+            roof["traffic_source"] = tr["source"]
+            roof["algorithmic_bytes_per_launch"] = drec["bytes"] / drec["n"]
+    except (OSError, ValueError):
+        pass
     roof.update({"kernel": dname, "avg_launch_ms": avg_ms, "launches_per_step": drec["n"],
                  "share_of_step": drec["ms"] / step_ms_prof, "peak_source": pk["source"],
                  "engine": os.environ.get("NSR_ENGINE", "auto"),

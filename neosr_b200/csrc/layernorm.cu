@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_v2(const float* _
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_v2(
+__global__ void __launch_bounds__(LN_WARPS * 32, NCH == 1 ? 4 : 2) layernorm_bwd_v2(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
     float* __restrict__ dx, uint8_t* __restrict__ dx_sti, float* __restrict__ partial, int rows, int C) {

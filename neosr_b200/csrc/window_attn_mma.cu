@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
   __shared__ float bias_s[225];
   __shared__ __align__(8) int tok[AM_N], rid[AM_N];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
-  const int wi = blockIdx.x, head = blockIdx.y;
+  // heads vary fastest over the grid: the six CTAs that read the same 64 qkv rows (120 of each row's 2160 bytes per
+  // head) run together, so the rows come from DRAM once and from L2 five times (was: 2.2x the algorithmic DRAM reads)
+  const int wi = blockIdx.x / gm.heads, head = blockIdx.x - wi * gm.heads;
   int differs = 0;
   if (t < AM_N) {
     attn_token_map(gm, wi, t, tok[t], rid[t]);
@@ -507,7 +509,7 @@ bool window_attn_mma_supported(int c, int heads, int ws) {
 int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w,
                                int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st) {
   AttnGeom g{batch, h, w, c, heads, ws, shift, use_mask, c / heads, h / ws, w / ws, scale};
-  dim3 grid(batch * g.nwh * g.nww, heads);
+  dim3 grid(batch * g.nwh * g.nww * heads);
   window_attn_fwd_mma<<<grid, AM_THREADS, 0, st>>>(qkv, table, out, reinterpret_cast<uint8_t*>(out_sti), g);
   NSR_CHECK_LAUNCH("window_attn_fwd_mma");
   return NSR_OK;
