@@ -118,14 +118,17 @@ class swinir(nn.Module):
         if patch_size != 1 or ape or flash_attn or drop_rate or attn_drop_rate or norm_layer is not nn.LayerNorm:
             raise NotImplementedError("neosr_b200.swinir: patch_size!=1 / ape / flash_attn / dropout are not "
                                       "part of the B200 hot path (reference defaults only)")
-        if upsampler not in ("pixelshuffle", "pixelshuffledirect") or resi_connection != "1conv":
-            raise NotImplementedError(f"neosr_b200.swinir: upsampler={upsampler!r}/resi={resi_connection!r} "
-                                      "not built yet (pixelshuffle[direct] + 1conv are)")
+        if upsampler not in ("pixelshuffle", "pixelshuffledirect", "nearest+conv") or resi_connection not in ("1conv", "3conv"):
+            raise NotImplementedError(f"neosr_b200.swinir: upsampler={upsampler!r}/resi={resi_connection!r} not built "
+                                      "(pixelshuffle, pixelshuffledirect, nearest+conv with 1conv / 3conv are)")
+        if upsampler == "nearest+conv" and upscale != 4:
+            raise AssertionError("only support x4 now.")  # swinir_arch.py:993
         nf = 64
         self.img_range, self.upscale, self.upsampler = img_range, upscale, upsampler
         self.embed_dim, self.window_size, self.num_heads = embed_dim, window_size, tuple(num_heads)
         self.depths, self.patch_norm, self.qk_scale = tuple(depths), patch_norm, qk_scale
         self.in_chans, self.num_feat, self.mlp_ratio = in_chans, nf, mlp_ratio
+        self.resi_connection = resi_connection
         self.mean = torch.full((1, 3, 1, 1), 0.5) if in_chans == 3 else torch.zeros(1, 1, 1, 1)
         res = (img_size, img_size)
 
@@ -153,6 +156,13 @@ class swinir(nn.Module):
                 raise ValueError(f"scale {upscale} is not supported. Supported scales: 2^n and 3.")
             self.upsample = nn.Sequential(*ups)
             self.conv_last = nn.Conv2d(nf, in_chans, 3, 1, 1)
+        elif upsampler == "nearest+conv":  # swinir_arch.py:991-1001
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, nf, 3, 1, 1), nn.LeakyReLU(inplace=True))
+            self.conv_up1 = nn.Conv2d(nf, nf, 3, 1, 1)
+            self.conv_up2 = nn.Conv2d(nf, nf, 3, 1, 1)
+            self.conv_hr = nn.Conv2d(nf, nf, 3, 1, 1)
+            self.conv_last = nn.Conv2d(nf, in_chans, 3, 1, 1)
+            self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
         else:
             self.upsample = nn.Sequential(nn.Conv2d(embed_dim, upscale ** 2 * in_chans, 3, 1, 1),
                                           nn.PixelShuffle(upscale))
@@ -225,6 +235,14 @@ class swinir(nn.Module):
         def lin(name, t, **kw):
             return ops.conv_fprop(t, ps.pw(name + ".weight"), ps.p(name + ".bias") if ps.has(name + ".bias") else None, **kw)
 
+        def resi(name, t, residual):
+            """RSTB.conv / conv_after_body: one 3x3 conv, or the 3conv bottleneck (swinir_arch.py:628-641, 962-973)."""
+            if self.resi_connection == "1conv":
+                return lin(name, t, residual=residual), None
+            a = lin(name + ".0", t, act="lrelu", act_slope=0.2)
+            b = lin(name + ".2", a, act="lrelu", act_slope=0.2)
+            return lin(name + ".4", b, residual=residual), (a, b)
+
         xin = ops.nchw_to_nhwc_affine(x, k["in_scale"], k["in_shift"])
         f0 = lin("conv_first", xin)
         if self.patch_norm:
@@ -259,14 +277,14 @@ class swinir(nn.Module):
                 if save:
                     S["blocks"].append((t, mu1, rs1, ln1, qkv, att, x1, mu2, rs2, ln2, hpre, a, ds))
                 t = x2
-            y = lin(f"layers.{li}.conv", t, residual=inp)
+            y, rs_saved = resi(f"layers.{li}.conv", t, inp)
             if save:
-                S["layers"].append(t)
+                S["layers"].append((t, rs_saved))
             t = y
         xn, mun, rsn = ops.layernorm_fwd(t, ps.p("norm.weight"), ps.p("norm.bias"))
-        body = lin("conv_after_body", xn, residual=f0)
+        body, cab_saved = resi("conv_after_body", xn, f0)
         if save:
-            S["final"] = (t, mun, rsn, xn, body)
+            S["final"] = (t, mun, rsn, xn, body, cab_saved)
         if self.upsampler == "pixelshuffle":
             u0 = lin("conv_before_upsample.0", body, act="lrelu", act_slope=0.01)
             cur, ups = u0, []
@@ -280,6 +298,16 @@ class swinir(nn.Module):
             out = lin("conv_last", cur)
             if save:
                 S["tail"] = (u0, ups, cur)
+        elif self.upsampler == "nearest+conv":  # swinir_arch.py:1056-1069
+            u0 = lin("conv_before_upsample.0", body, act="lrelu", act_slope=0.01)
+            n1 = ops.nearest_up2(u0)
+            c1 = lin("conv_up1", n1, act="lrelu", act_slope=0.2)
+            n2 = ops.nearest_up2(c1)
+            c2 = lin("conv_up2", n2, act="lrelu", act_slope=0.2)
+            c3 = lin("conv_hr", c2, act="lrelu", act_slope=0.2)
+            out = lin("conv_last", c3)
+            if save:
+                S["tail"] = (u0, n1, c1, n2, c2, c3)
         else:
             c = lin("upsample.0", body)
             out = ops.pixel_shuffle(c, self.upscale)
@@ -327,8 +355,26 @@ class swinir(nn.Module):
             gf = (gf.view(B, -1) * s.view(B, 1)).view_as(gf).contiguous()
             return (gf, ops.STI.from_f32(gf)) if sti else gf
 
+        def resi_bwd(name, x_in, g, saved, **epi):
+            if self.resi_connection == "1conv":
+                return bwd(name, x_in, g, **epi)
+            a, b = saved
+            g = bwd(name + ".4", b, g, actgrad="lrelu", actgrad_slope=0.2, aux=b)
+            g = bwd(name + ".2", a, g, actgrad="lrelu", actgrad_slope=0.2, aux=a)
+            return bwd(name + ".0", x_in, g, **epi)
+
         g = ops.nchw_to_nhwc_affine(dy.contiguous().float(), k["out_scale"], None)
-        if self.upsampler == "pixelshuffle":
+        if self.upsampler == "nearest+conv":
+            u0, n1, c1, n2, c2, c3 = S["tail"]
+            g = bwd("conv_last", c3, g, actgrad="lrelu", actgrad_slope=0.2, aux=c3)
+            g = bwd("conv_hr", c2, g, actgrad="lrelu", actgrad_slope=0.2, aux=c2)
+            g = ops.nearest_up2_bwd(bwd("conv_up2", n2, g))
+            g = ops.actgrad_mul(g, c1, "lrelu", 0.2)
+            g = ops.nearest_up2_bwd(bwd("conv_up1", n1, g))
+            g = ops.actgrad_mul(g, u0, "lrelu", 0.01)
+            t_last, mun, rsn, xn, body, cab_saved = S["final"]
+            g = bwd("conv_before_upsample.0", body, g)
+        elif self.upsampler == "pixelshuffle":
             u0, ups, last_in = S["tail"]
             g = bwd("conv_last", last_in, g)
             for i in reversed(range(len(ups))):
@@ -338,14 +384,14 @@ class swinir(nn.Module):
                     g = bwd(f"upsample.{2 * i}", src, g, actgrad="lrelu", actgrad_slope=0.01, aux=u0)
                 else:
                     g = bwd(f"upsample.{2 * i}", src, g)
-            t_last, mun, rsn, xn, body = S["final"]
+            t_last, mun, rsn, xn, body, cab_saved = S["final"]
             g = bwd("conv_before_upsample.0", body, g)
         else:
-            t_last, mun, rsn, xn, body = S["final"]
+            t_last, mun, rsn, xn, body, cab_saved = S["final"]
             g = ops.pixel_unshuffle(g, self.upscale)
             g = bwd("upsample.0", body, g)
         df0 = g  # through the `+ x` skip of conv_after_body (swinir_arch.py:1047)
-        g = bwd("conv_after_body", xn, g)
+        g = resi_bwd("conv_after_body", xn, g, cab_saved)
         g = ops.layernorm_bwd(g, t_last, ps.p("norm.weight"), mun, rsn, ps.g("norm.weight"), ps.g("norm.bias"))
         nblk = len(S["blocks"])
         bi_glob = nblk
@@ -354,7 +400,7 @@ class swinir(nn.Module):
             scale = self.qk_scale or (self.embed_dim // heads) ** -0.5
             dinp = g
             # grad w.r.t. the last block's output: fp32 for the LayerNorm backward, STI for fc2's dgrad/wgrad
-            g = bwd(f"layers.{li}.conv", S["layers"][li], g, sti_out=sti)
+            g = resi_bwd(f"layers.{li}.conv", S["layers"][li][0], g, S["layers"][li][1], sti_out=sti)
             depth = len(self.layers[li].residual_group.blocks)
             for bi in reversed(range(depth)):
                 bi_glob -= 1

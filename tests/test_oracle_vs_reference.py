@@ -398,3 +398,19 @@ def test_apply_augment_plan_and_oracle_vs_reference():
         assert torch.equal(go, gr) and torch.equal(lo, lr), (seed, plan)
         seen |= {o["op"] for o in plan["ops"]}
     assert seen == {"mixup", "cutmix", "resizemix", "cutblur"}
+
+
+def test_swinir_3conv_nearest_conv_oracle_and_keys_vs_reference():
+    """swinir_large's variants (3conv, nearest+conv): oracle forward == reference, product state_dict == reference's."""
+    from neosr_b200.archs.swinir_arch import swinir as our_swinir
+    ref_shim.activate(4)
+    from neosr.archs.swinir_arch import swinir
+    kw = dict(img_size=16, embed_dim=48, depths=(2, 2), num_heads=(4, 4), window_size=8, mlp_ratio=2.0, upsampler="nearest+conv",
+              resi_connection="3conv", upscale=4)
+    ref, ours = swinir(drop_path_rate=0.0, **kw).train(), our_swinir(drop_path_rate=0.0, **kw)
+    assert [(k, tuple(v.shape)) for k, v in ref.state_dict().items()] == [(k, tuple(v.shape)) for k, v in ours.state_dict().items()]
+    cfg = SwinIRConfig(**kw)
+    p = synth_params(swinir_param_shapes(cfg), seed=9)
+    ref.load_state_dict(p, strict=False)
+    x = torch.rand(2, 3, 16, 24, generator=torch.Generator().manual_seed(0))
+    assert _rel(swinir_forward(p, cfg, x), ref(x).detach()) < 1e-5

@@ -219,3 +219,39 @@ def test_esrgan_forward_backward_vs_oracle(scale):
             ops.DEFAULT_ENGINE = "auto"
         for (k, v), gi in zip(net.named_parameters(), grads):
             assert rel(v.grad, gi) < tol, (engine, k)
+
+
+def test_swinir_large_style_3conv_nearest_conv_vs_oracle():
+    """`swinir_large`'s building blocks (resi_connection='3conv', upsampler='nearest+conv', swinir_arch.py:628-641,
+    962-973, 991-1001, 1056-1069) on a tiny config: forward and every parameter gradient vs the oracle's autograd."""
+    from neosr_b200 import ops
+    from neosr_b200.archs.swinir_arch import swinir
+    from oracle.swinir import SwinIRConfig, swinir_forward, swinir_param_shapes, synth_params
+    kw = dict(img_size=16, embed_dim=48, depths=(2, 2), num_heads=(4, 4), window_size=8, mlp_ratio=2.0, upsampler="nearest+conv",
+              resi_connection="3conv", upscale=4)
+    cfg = SwinIRConfig(**kw)
+    p = synth_params(swinir_param_shapes(cfg), seed=9)
+    net = swinir(drop_path_rate=0.0, **kw)
+    missing = net.load_state_dict(p, strict=False)
+    assert not missing.unexpected_keys and all("relative_position_index" in k or "attn_mask" in k for k in missing.missing_keys)
+    assert {k for k, _ in net.named_parameters()} == set(p)
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(10)
+    x = torch.rand(2, 3, 16, 24, generator=g)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y_ref = swinir_forward(pr, cfg, x)
+    gt = torch.rand(y_ref.shape, generator=g)
+    grads = dict(zip(pr, torch.autograd.grad(((y_ref - gt) ** 2).mean(), list(pr.values()))))
+    for engine, tol in (("simt", 2e-4), ("auto", 3e-3)):  # LeakyReLU kinks: see tests/test_unet_gpu.py on the split engine
+        ops.DEFAULT_ENGINE = engine
+        try:
+            net.zero_grad()
+            y = net(x.cuda())
+            assert rel(y.detach(), y_ref.detach()) < 1e-4
+            ((y - gt.cuda()) ** 2).mean().backward()
+        finally:
+            ops.DEFAULT_ENGINE = "auto"
+        for k, v in net.named_parameters():
+            assert rel(v.grad, grads[k]) < tol, (engine, k, rel(v.grad, grads[k]))
+    from neosr_b200.registry import ARCH_REGISTRY
+    assert "swinir_large" in ARCH_REGISTRY
