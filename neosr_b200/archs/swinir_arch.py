@@ -361,7 +361,8 @@ class swinir(nn.Module):
             a, b = saved
             g = bwd(name + ".4", b, g, actgrad="lrelu", actgrad_slope=0.2, aux=b)
             g = bwd(name + ".2", a, g, actgrad="lrelu", actgrad_slope=0.2, aux=a)
-            return bwd(name + ".0", x_in, g, **epi)
+            g = bwd(name + ".0", x_in, g)  # dim/4 input channels: may run on the narrow / exact engine (fp32 output only)
+            return (g, ops.STI.from_f32(g)) if epi.get("sti_out") else g
 
         g = ops.nchw_to_nhwc_affine(dy.contiguous().float(), k["out_scale"], None)
         if self.upsampler == "nearest+conv":
