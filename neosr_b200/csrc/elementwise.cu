@@ -86,6 +86,86 @@ __global__ void pixel_shuffle_nhwc(const float* __restrict__ x, float* __restric
   }
 }
 
+// r == 2, Co % 4 == 0: one thread per (input pixel, 4 output channels).  The 16 input floats c*4 .. c*4+15 are the
+// (i, j) sub-pixels of output channels c .. c+3: four coalesced 16-byte loads, a 4x4 register transpose, four 16-byte
+// stores (one per sub-pixel) — no per-element div/mod, every sector fully used in both directions.
+__global__ void __launch_bounds__(256) pixel_shuffle2_nhwc_v4(const float* __restrict__ x, float* __restrict__ y, size_t npix,
+                                                              int W, int Co, int inverse) {
+  const int cg = Co >> 2;
+  const size_t total = npix * cg;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    const size_t pix = t / cg;           // b*H*W + h*W + w
+    const size_t row = pix / W;          // b*H + h
+    const int w = (int)(pix - row * W);
+    float* big = (inverse ? const_cast<float*>(x) : y);  // the [B, 2H, 2W, Co] side
+    const size_t o00 = ((row * 2) * (size_t)(2 * W) + 2 * w) * Co + 4 * g;
+    const size_t small_off = pix * (size_t)(4 * Co) + 16 * g;
+    if (!inverse) {
+      float4 a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] = *reinterpret_cast<const float4*>(x + small_off + 4 * k);  // channel c+k: (00,01,10,11)
+      *reinterpret_cast<float4*>(big + o00) = make_float4(a[0].x, a[1].x, a[2].x, a[3].x);
+      *reinterpret_cast<float4*>(big + o00 + Co) = make_float4(a[0].y, a[1].y, a[2].y, a[3].y);
+      *reinterpret_cast<float4*>(big + o00 + (size_t)2 * W * Co) = make_float4(a[0].z, a[1].z, a[2].z, a[3].z);
+      *reinterpret_cast<float4*>(big + o00 + (size_t)2 * W * Co + Co) = make_float4(a[0].w, a[1].w, a[2].w, a[3].w);
+    } else {
+      const float4 s0 = *reinterpret_cast<const float4*>(big + o00), s1 = *reinterpret_cast<const float4*>(big + o00 + Co);
+      const float4 s2 = *reinterpret_cast<const float4*>(big + o00 + (size_t)2 * W * Co);
+      const float4 s3 = *reinterpret_cast<const float4*>(big + o00 + (size_t)2 * W * Co + Co);
+      float* o = y + small_off;
+      *reinterpret_cast<float4*>(o) = make_float4(s0.x, s1.x, s2.x, s3.x);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(s0.y, s1.y, s2.y, s3.y);
+      *reinterpret_cast<float4*>(o + 8) = make_float4(s0.z, s1.z, s2.z, s3.z);
+      *reinterpret_cast<float4*>(o + 12) = make_float4(s0.w, s1.w, s2.w, s3.w);
+    }
+  }
+}
+
+// even H, W and C % 4 == 0: one thread per (OUTPUT pixel, 4 channels): the 2x2 window is read once (not once per input
+// element), the routed gradient of all four inputs is written from registers.
+__global__ void __launch_bounds__(256) maxpool2_relu_bwd_nhwc_v4(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 const float* __restrict__ dextra, float* __restrict__ dx,
+                                                                 size_t nout, int Wo, int C) {
+  const int cg = C >> 2;
+  const size_t total = nout * cg;
+  const size_t rs = (size_t)2 * Wo * C;  // input row stride
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    const size_t opix = t / cg;            // b*Ho*Wo + oh*Wo + ow
+    const size_t orow = opix / Wo;         // b*Ho + oh
+    const int ow = (int)(opix - orow * Wo);
+    const size_t i00 = (orow * 2) * rs + (size_t)(2 * ow) * C + 4 * g;
+    const size_t off[4] = {i00, i00 + C, i00 + rs, i00 + rs + C};
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(x + off[k]);
+    const float4 gy = *reinterpret_cast<const float4*>(dy + opix * C + 4 * g);
+    float out[4][4];
+    const float gyv[4] = {gy.x, gy.y, gy.z, gy.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float vv[4] = {(&v[0].x)[e], (&v[1].x)[e], (&v[2].x)[e], (&v[3].x)[e]};
+      int am = 0;
+      float best = vv[0];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (vv[k] > best) { best = vv[k]; am = k; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out[k][e] = (k == am && vv[k] > 0.f) ? gyv[e] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 o = make_float4(out[k][0], out[k][1], out[k][2], out[k][3]);
+      if (dextra) {
+        const float4 ex = *reinterpret_cast<const float4*>(dextra + off[k]);
+        o.x += ex.x; o.y += ex.y; o.z += ex.z; o.w += ex.w;
+      }
+      *reinterpret_cast<float4*>(dx + off[k]) = o;
+    }
+  }
+}
+
 __global__ void maxpool2_nhwc(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = (size_t)B * Ho * Wo * C;
@@ -338,7 +418,11 @@ extern "C" int nsr_pixel_shuffle_nhwc(const float* x, float* y, int B, int H, in
   NSR_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && Co > 0 && r > 0, "nsr_pixel_shuffle_nhwc: bad arguments");
   const size_t n = (size_t)B * H * r * W * r * Co;
   // forward: x = [B,H,W,Co*r*r] -> y = [B,H*r,W*r,Co]; inverse: x = [B,H*r,W*r,Co] -> y = [B,H,W,Co*r*r]
-  pixel_shuffle_nhwc<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, H, W, Co, r, inverse);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (r == 2 && Co % 4 == 0 && al16(x) && al16(y))
+    pixel_shuffle2_nhwc_v4<<<ew_blocks(n / 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, (size_t)B * H * W, W, Co, inverse);
+  else
+    pixel_shuffle_nhwc<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, H, W, Co, r, inverse);
   NSR_CHECK_LAUNCH("pixel_shuffle_nhwc");
   return NSR_OK;
 }
@@ -353,7 +437,12 @@ extern "C" int nsr_maxpool2_relu_bwd_nhwc(const float* x, const float* dy, const
                                            int W, int C, void* stream) {
   NSR_CHECK_ARG(x && dy && dx && B > 0 && H > 1 && W > 1 && C > 0, "nsr_maxpool2_relu_bwd_nhwc: bad arguments");
   const size_t n = (size_t)B * H * W * C;
-  maxpool2_relu_bwd_nhwc<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, dy, dextra, dx, B, H, W, C);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (H % 2 == 0 && W % 2 == 0 && C % 4 == 0 && al16(x) && al16(dy) && al16(dx) && al16(dextra))
+    maxpool2_relu_bwd_nhwc_v4<<<ew_blocks(n / 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, dy, dextra, dx, (size_t)B * (H / 2) * (W / 2), W / 2, C);
+  else
+    maxpool2_relu_bwd_nhwc<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, dy, dextra, dx, B, H, W, C);
   NSR_CHECK_LAUNCH("maxpool2_relu_bwd_nhwc");
   return NSR_OK;
 }

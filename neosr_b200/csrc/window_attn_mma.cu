@@ -39,7 +39,6 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
 // A fragment (16 rows x 16 k) from a row-major [row][k] bf16 tile
@@ -339,21 +338,6 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
       int t0, r0;
       attn_token_map(gm, wi, 0, t0, r0);
       differs = rid[t] != r0;
-    } else if (wi + (int)gridDim.x < nwin) {
-      // the other 64 threads pull the NEXT window's q/k/v/dO segments (120 B each, <= 2 lines) into L2 while this window
-      // is computed: the loads at the top of the next iteration then cost an L2 hit instead of a DRAM round trip
-      int tn, rn;
-      attn_token_map(gm, wi + gridDim.x, t - AM_N, tn, rn);
-      const char* q = reinterpret_cast<const char*>(qkv + (size_t)tn * 3 * gm.C + head * gm.D);
-      const char* o = reinterpret_cast<const char*>(dout + (size_t)tn * gm.C + head * gm.D);
-      const int last = gm.D * 4 - 4;
-#pragma unroll
-      for (int s3 = 0; s3 < 3; ++s3) {
-        prefetch_l2(q + (size_t)s3 * gm.C * 4);
-        prefetch_l2(q + (size_t)s3 * gm.C * 4 + last);
-      }
-      prefetch_l2(o);
-      prefetch_l2(o + last);
     }
     // zero the k-padding (columns D..31) of the eight [token][d] tiles (phase 2 aliased over them)
     for (int i = t; i < 8 * AM_N * ((32 - gm.D) / 2); i += AM_THREADS) {
