@@ -91,11 +91,98 @@ def loss_inputs():
 
 
 
+HAT_TINY = dict(img_size=64, embed_dim=36, depths=(2, 2), num_heads=(3, 3), window_size=16, compress_ratio=3, squeeze_factor=6,
+                conv_scale=0.01, overlap_ratio=0.5, mlp_ratio=2, upscale=4)
+
+
+def hat_case():
+    """Reference `hat` (hat_arch.py) on a tiny config: forward image, loss and a spread of parameter gradients."""
+    from neosr.archs.hat_arch import hat
+
+    from oracle.hat import HATConfig, hat_param_shapes
+    from oracle.swinir import synth_params
+    net = hat(drop_path_rate=0.0, upsampler="pixelshuffle", resi_connection="1conv", **HAT_TINY).train()
+    p = synth_params(hat_param_shapes(HATConfig(**HAT_TINY)), seed=3)
+    net.load_state_dict(p, strict=False)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(2, 3, 32, 48, generator=g)
+    y = net(x)
+    gt = torch.rand(y.shape, generator=g)
+    ((y - gt) ** 2).mean().backward()
+    out = {"y": y.detach().numpy().copy()}
+    for k, v in net.named_parameters():
+        if k.startswith(("layers.0.residual_group.blocks.1.", "layers.1.residual_group.overlap_attn.", "conv_first", "conv_last", "norm.")):
+            out["grad." + k] = v.grad.numpy().copy()
+    np.savez_compressed(OUT / "hat_tiny_fwd_bwd.npz", **out)
+
+
+def arch_cases():
+    """compact / esrgan / realplksr / unet reference modules: forward output and the gradient norm of every parameter for
+    (y**2).mean(), plus the U-Net's spectral-norm buffers after three training forwards; and the log + final parameter
+    checksums of three REAL optimize_parameters iterations with the U-Net discriminator (C2's step shape)."""
+    from oracle.compact import compact_param_shapes
+    from oracle.esrgan import esrgan_param_shapes
+    from oracle.realplksr import realplksr_param_shapes
+    from oracle.swinir import SwinIRConfig, swinir_param_shapes, synth_params
+    from oracle.unet import synth_unet
+    out = {}
+
+    def run(tag, net, p, x):
+        net.load_state_dict(p)
+        net.train()
+        y = net(x)
+        (y ** 2).mean().backward()
+        out[f"{tag}.y"] = y.detach().numpy().copy()
+        out[f"{tag}.gnorm"] = np.array([float(v.grad.double().norm()) for _, v in net.named_parameters()])
+
+    g = torch.Generator().manual_seed(8)
+    run("compact", ref_shim.build_network({"type": "compact", "upscale": 2, "num_conv": 4, "num_feat": 32}),
+        synth_params(compact_param_shapes(num_feat=32, num_conv=4, upscale=2), seed=7), torch.rand(2, 3, 16, 24, generator=g))
+    run("esrgan", ref_shim.build_network({"type": "esrgan", "scale": 4, "num_block": 2, "num_feat": 32, "num_grow_ch": 16}),
+        synth_params(esrgan_param_shapes(scale=4, num_feat=32, num_block=2, num_grow_ch=16), seed=11), torch.rand(2, 3, 16, 24, generator=g))
+    kw = dict(dim=32, n_blocks=2, upscaling_factor=4, kernel_size=17, use_ea=True)
+    run("realplksr", ref_shim.build_network({"type": "realplksr", **kw}), synth_params(realplksr_param_shapes(**kw), seed=13),
+        torch.rand(2, 3, 20, 24, generator=g))
+    net = ref_shim.build_network({"type": "unet", "num_feat": 16})
+    dp, db = synth_unet(num_feat=16, seed=21)
+    net.load_state_dict({**dp, **db})
+    net.train()
+    for it in range(3):
+        y = net(torch.rand(2, 3, 32, 40, generator=g))
+    out["unet.y3"] = y.detach().numpy().copy()
+    for k, v in net.named_buffers():
+        out[f"unet.buf.{k}"] = v.numpy().copy()
+    # GAN step (reference's real closure / optimize_parameters)
+    from neosr.archs.swinir_arch import swinir
+    from neosr.losses.basic_loss import L1Loss
+    from neosr.losses.gan_loss import gan_loss
+
+    from oracle.make_golden import OPTIM, TINY
+    p = synth_params(swinir_param_shapes(SwinIRConfig(**TINY)), seed=4)
+    netg = swinir(drop_path_rate=0.0, **TINY)
+    netg.load_state_dict(p, strict=False)
+    netd = ref_shim.build_network({"type": "unet", "num_feat": 16})
+    dp, db = synth_unet(num_feat=16, seed=9)
+    netd.load_state_dict({**dp, **db})
+    model = ref_shim.make_image_model(netg.train(), cri_pix=L1Loss(1.0), optim_kw=OPTIM, net_d=netd, cri_gan=gan_loss("bce", loss_weight=0.3))
+    gg = torch.Generator().manual_seed(6)
+    for it in range(3):
+        model.feed_data({"lq": torch.rand(2, 3, 16, 16, generator=gg), "gt": torch.rand(2, 3, 64, 64, generator=gg)})
+        model.optimize_parameters(it)
+        log = model.get_current_log()
+        out[f"gan.log{it}"] = np.frombuffer(json.dumps({k: float(v) for k, v in log.items()}).encode(), dtype=np.uint8)
+    out["gan.g_norms"] = np.array([float(v.detach().double().norm()) for _, v in netg.named_parameters()])
+    out["gan.d_norms"] = np.array([float(v.detach().double().norm()) for _, v in netd.named_parameters()])
+    np.savez_compressed(OUT / "archs_fwd.npz", **out)
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "needs /root/reference"
     ref_shim.activate(4)
     feed_data_cases()
     kernel_cases()
     loss_cases()
+    hat_case()
+    arch_cases()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -126,3 +126,78 @@ def test_oracle_mssim_consistency_vs_reference_fixture():
             assert float((g - ref).abs().max() / ref.abs().max()) < 1e-5, (tag, name)
     near = loss_inputs()["near"]
     assert float(OL.consistency_loss(*near)) != float(OL.consistency_loss(*near, force_cosim=False))
+
+
+def test_oracle_hat_vs_reference_fixture():
+    """oracle.hat.hat_forward + autograd against a fixture written from the reference `hat` module (tiny config, both HAB
+    kinds, OCAB with its wrapping index, CAB): pins the HAT oracle wherever the reference tree is absent."""
+    from oracle.hat import HATConfig, hat_forward, hat_param_shapes
+    from oracle.make_golden_otf import HAT_TINY
+    from oracle.swinir import synth_params
+    z = np.load(G / "hat_tiny_fwd_bwd.npz")
+    cfg = HATConfig(**HAT_TINY)
+    p = {k: v.requires_grad_(True) for k, v in synth_params(hat_param_shapes(cfg), seed=3).items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(2, 3, 32, 48, generator=g)
+    y = hat_forward(p, cfg, x)
+    gt = torch.rand(y.shape, generator=g)
+    ref_y = torch.from_numpy(z["y"])
+    assert float((y.detach() - ref_y).abs().max() / ref_y.abs().max()) < 1e-5
+    keys = [k[5:] for k in z.files if k.startswith("grad.")]
+    assert len(keys) > 30
+    grads = torch.autograd.grad(((y - gt) ** 2).mean(), [p[k] for k in keys])
+    for k, gi in zip(keys, grads):
+        r = torch.from_numpy(z["grad." + k])
+        assert float((gi - r).abs().max() / r.abs().max().clamp_min(1e-30)) < 2e-4, k
+
+
+def test_oracle_archs_and_gan_step_vs_reference_fixture():
+    """compact / esrgan / realplksr / unet oracles and the oracle GAN step against fixtures written from the reference
+    modules and its REAL optimize_parameters (tests/golden/archs_fwd.npz)."""
+    from oracle.compact import compact_forward, compact_param_shapes
+    from oracle.esrgan import esrgan_forward, esrgan_param_shapes
+    from oracle.make_golden import OPTIM, TINY
+    from oracle.realplksr import realplksr_forward, realplksr_param_shapes
+    from oracle.step import make_swinir_trainer
+    from oracle.swinir import SwinIRConfig, swinir_param_shapes, synth_params
+    from oracle.unet import synth_unet, unet_forward
+    z = np.load(G / "archs_fwd.npz")
+
+    def check(tag, fn, shapes, seed, x):
+        p = {k: v.requires_grad_(True) for k, v in synth_params(shapes, seed=seed).items()}
+        y = fn(p, x)
+        ref = torch.from_numpy(z[f"{tag}.y"])
+        assert float((y.detach() - ref).abs().max() / ref.abs().max()) < 1e-5, tag
+        gr = torch.autograd.grad((y ** 2).mean(), list(p.values()))
+        gn = np.array([float(t.double().norm()) for t in gr])
+        np.testing.assert_allclose(gn, z[f"{tag}.gnorm"], rtol=2e-4, atol=1e-12, err_msg=tag)
+
+    g = torch.Generator().manual_seed(8)
+    check("compact", lambda p, x: compact_forward(p, x, num_conv=4, upscale=2), compact_param_shapes(num_feat=32, num_conv=4, upscale=2),
+          7, torch.rand(2, 3, 16, 24, generator=g))
+    check("esrgan", lambda p, x: esrgan_forward(p, x, scale=4, num_block=2), esrgan_param_shapes(scale=4, num_feat=32, num_block=2, num_grow_ch=16),
+          11, torch.rand(2, 3, 16, 24, generator=g))
+    kw = dict(dim=32, n_blocks=2, upscaling_factor=4, kernel_size=17, use_ea=True)
+    check("realplksr", lambda p, x: realplksr_forward(p, x, n_blocks=2, kernel_size=17, use_ea=True), realplksr_param_shapes(**kw),
+          13, torch.rand(2, 3, 20, 24, generator=g))
+    dp, db = synth_unet(num_feat=16, seed=21)
+    bo = {k: v.clone() for k, v in db.items()}
+    for it in range(3):
+        y = unet_forward(dp, bo, torch.rand(2, 3, 32, 40, generator=g), training=True)
+    ref = torch.from_numpy(z["unet.y3"])
+    assert float((y - ref).abs().max() / ref.abs().max()) < 1e-5
+    for k, v in bo.items():
+        r = torch.from_numpy(z[f"unet.buf.{k}"])
+        assert float((v - r).abs().max() / r.abs().max().clamp_min(1e-30)) < 1e-5, k
+    p = synth_params(swinir_param_shapes(SwinIRConfig(**TINY)), seed=4)
+    dp, db = synth_unet(num_feat=16, seed=9)
+    tr = make_swinir_trainer(p, SwinIRConfig(**TINY), pixel_weight=1.0, optim=OPTIM, ema=0.999, disc=(dp, db), gan_weight=0.3)
+    gg = torch.Generator().manual_seed(6)
+    for it in range(3):
+        tr.feed_data({"lq": torch.rand(2, 3, 16, 16, generator=gg), "gt": torch.rand(2, 3, 64, 64, generator=gg)})
+        tr.optimize_parameters(it)
+        ref_log = json.loads(bytes(z[f"gan.log{it}"]).decode())
+        for k, v in tr.get_current_log().items():
+            assert abs(v - ref_log[k]) <= 1e-5 * max(1.0, abs(ref_log[k])), (it, k)
+    np.testing.assert_allclose([float(tr.params[k].detach().double().norm()) for k in tr.names], z["gan.g_norms"], rtol=1e-5)
+    np.testing.assert_allclose([float(tr.d_params[k].detach().double().norm()) for k in tr.d_names], z["gan.d_norms"], rtol=1e-5)

@@ -189,7 +189,7 @@ def _otf_model(ds, queue_size):
 def test_pipeline_replay_vs_oracle_and_reference_fixture():
     """Whole feed_data pipeline + pool over 8 iterations on the decisions the REFERENCE took (fixture) and
     the random fields the oracle drew: LQ must sit on 8-bit levels and equal the oracle's (== the
-    reference's, tests/test_otf_cpu.py) except for isolated quantiser flips; GT crops are exact."""
+    reference's, tests/test_oracle_fixtures_cpu.py) except for isolated quantiser flips; GT crops are exact."""
     z = np.load(G / "otf_feed_data.npz")
     c = CASE
     ds = dict(DEGRADATIONS, patch_size=c["patch_size"], batch_size=c["batch"])
