@@ -258,6 +258,13 @@ size_t nsr_conv_lk16_wgrad_workspace(int batch, int h, int w, int k);
 int nsr_conv_lk16_wgrad(const float* x, int x_ld, const float* dy, int dy_ld, float* dw, float* dbias, int batch, int h,
                         int w, int k, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Split tile images written by nsr_layernorm_fwd, nsr_window_attn_fwd and nsr_conv_fprop carry 1.0 in their first
+ * padding channel (channel C when C % 64 != 0; the packed weights are zero there, so no contraction over C sees it).
+ * A weight gradient taken over cin + 4 input channels of such an image (same image geometry) therefore returns the bias
+ * gradient as column cin: t = [cout, cin + 4]; this call scatters t into dw [cout, cin] and dbias [cout], replacing the
+ * separate column-sum pass over dy. */
+int nsr_wgrad_split(const float* t, float* dw, float* dbias, int cout, int cin, int cinp, void* stream);
+
 /* ------------------------------------------------------------------ LayerNorm ---------- */
 /* nn.LayerNorm(c, eps) over the last dim of [rows, c] (swinir_arch.py:284,297,708,960). */
 int nsr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,

@@ -100,6 +100,7 @@ SIGNATURES = {
     "nsr_groupnorm_workspace": (_z, [_i, _i, _i]),
     "nsr_groupnorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _z, _p]),
     "nsr_groupnorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _z, _p]),
+    "nsr_wgrad_split": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "nsr_conv_lk16_fprop": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "nsr_conv_lk16_wgrad_workspace": (_z, [_i, _i, _i, _i]),
     "nsr_conv_lk16_wgrad": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _z, _p]),

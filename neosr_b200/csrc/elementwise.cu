@@ -330,8 +330,25 @@ __global__ void nhwc_to_nchw_add_nearest(const float* __restrict__ x, const floa
   }
 }
 
+// dw[n, c] = t[n, c] (c < cin), dbias[n] = t[n, cin] for t = [cout, cinp] (a wgrad over the ones-padded tile image)
+__global__ void wgrad_split_kernel(const float* __restrict__ t, float* __restrict__ dw, float* __restrict__ dbias, int cout, int cin,
+                                   int cinp) {
+  const int total = cout * (cin + 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / (cin + 1), c = i - n * (cin + 1);
+    const float v = t[(size_t)n * cinp + c];
+    if (c < cin) dw[(size_t)n * cin + c] = v;
+    else dbias[n] = v;
+  }
+}
 }  // namespace nsr
 using namespace nsr;
+extern "C" int nsr_wgrad_split(const float* t, float* dw, float* dbias, int cout, int cin, int cinp, void* stream) {
+  NSR_CHECK_ARG(t && dw && dbias && cout > 0 && cin > 0 && cinp > cin, "nsr_wgrad_split: bad arguments");
+  wgrad_split_kernel<<<ew_blocks((size_t)cout * (cin + 1)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, dw, dbias, cout, cin, cinp);
+  NSR_CHECK_LAUNCH("nsr_wgrad_split");
+  return NSR_OK;
+}
 
 extern "C" int nsr_axpby2d(const float* a, int lda, float alpha, const float* b, int ldb, float beta, float* y, int ldy,
                            long long rows, int cols, void* stream) {

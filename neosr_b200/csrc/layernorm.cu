@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_v2(const float* _
       const int ch = lane + 32 * k, c0 = ch * 8;
       float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (c0 + e < C) ? (v[k][e] - mu) * rs * gm[k][e] + bt[k][e] : 0.f;
+      // channel C of the tile image (first padding channel) carries 1.0: a wgrad over C+4 input channels then yields the
+      // bias gradient as column C of dW for free (weights are zero-padded there, so fprop / dgrad never see it)
+      for (int e = 0; e < 8; ++e) o[e] = (c0 + e < C) ? (v[k][e] - mu) * rs * gm[k][e] + bt[k][e] : (c0 + e == C ? 1.f : 0.f);
       if (y) {
         if (c0 < C) *reinterpret_cast<float4*>(y + r * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
         if (c0 + 4 < C) *reinterpret_cast<float4*>(y + r * C + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);

@@ -41,7 +41,7 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
   for (int i = half * 4; i < half * 4 + 4; ++i) {
     const long long p = p0 + i * 4 + er;
     if (p >= M) continue;
-    float ov[4] = {0.f, 0.f, 0.f, 0.f};
+    float ov[4] = {n == d.cout ? 1.f : 0.f, 0.f, 0.f, 0.f};  // first padding channel of an STI output = 1 (bias-gradient column)
     if (ncol) {
       const long long o = p * d.y_ld + n;
       const float4 a4 = *reinterpret_cast<const float4*>(stg + (i * 4 + er) * EPI_LD + ec);

@@ -95,11 +95,12 @@ __device__ __forceinline__ uint8_t* sti_row_base(uint8_t* sti, int kbs, long lon
   return sti + ((size_t)((p >> 7) * kbs) << 15) + (size_t)(p & 127) * 128;
 }
 // zero the channel padding [cfirst, kbs*64) of this window's 64 tokens (done by the last head's CTA)
-__device__ __forceinline__ void sti_zero_padding(uint8_t* sti, int kbs, const int* tok, int cfirst, int t) {
+// ones: channel cfirst carries 1.0 (the bias-gradient column of the consumer's wgrad, see layernorm.cu)
+__device__ __forceinline__ void sti_zero_padding(uint8_t* sti, int kbs, const int* tok, int cfirst, int t, bool ones = false) {
   const int pairs = (kbs * 64 - cfirst) / 2;
   for (int i = t; i < AM_N * pairs; i += AM_THREADS) {
     const int n = i / pairs, pr = i - n * pairs;
-    sti_store_pair(sti, kbs, tok[n], cfirst + 2 * pr, 0.f, 0.f);
+    sti_store_pair(sti, kbs, tok[n], cfirst + 2 * pr, (ones && pr == 0) ? 1.f : 0.f, 0.f);
   }
 }
 
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
       }
     }
   }
-  if (out_sti && head == gm.heads - 1) sti_zero_padding(out_sti, (gm.C + 63) / 64, tok, gm.C, t);
+  if (out_sti && head == gm.heads - 1) sti_zero_padding(out_sti, (gm.C + 63) / 64, tok, gm.C, t, true);
 }
 
 // ------------------------------------------------------------------------------------ backward

@@ -17,6 +17,7 @@ from . import _lib
 from ._lib import ACT, ENGINE, NsrConv, NsrWgrad, check
 
 
+BIAS_COLUMN_ENABLED = True  # bias gradients from the ones channel of split tile images (tests flip it)
 LK16_ENABLED = True   # route 16->16-channel k>=7 convs to the dedicated large-kernel kernels (tests flip it)
 DEFAULT_ENGINE = "auto"  # what engine="auto" resolves to ("auto" | "simt" | "tcgen05"); tests flip it
 LAUNCHES = 0          # kernels launched through this module (claim reported by bench.py)
@@ -107,6 +108,7 @@ class STI:
         alloc = torch.zeros if self.rows % 128 else torch.empty
         self.buf = alloc(n, dtype=torch.uint8, device=device)
         self.device = device
+        self.ones = False  # set by producers that write 1.0 into the first padding channel (bias-gradient column)
 
     def data_ptr(self):
         return self.buf.data_ptr()
@@ -240,6 +242,8 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
     if want_pre and isinstance(y, Slab):
         raise ValueError("conv_fprop: y_pre shares y's leading dim; write y to a dense tensor when want_pre")
     y_sti = STI((B, H, W, cout), x.device) if sti_out else None
+    if y_sti is not None:
+        y_sti.ones = cout % 64 != 0
     if y is None and y_sti is None:
         raise ValueError("conv_fprop: no output format selected")
     y_pre = torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device) if want_pre else None
@@ -288,11 +292,18 @@ def conv_wgrad(x, dy, dw: Tensor, dbias: Tensor | None, kh: int, kw: int, engine
                                         ws.numel(), _stream()), "nsr_conv_lk16_wgrad")
         _count(2)
         return
-    d = NsrWgrad(batch=B, h=H, w=W, cin=cin, cout=cout, kh=kh, kw=kw, pad=kh // 2, x_ld=x_ld, dy_ld=dy_ld,
+    # bias gradient for free: the x image carries 1.0 in channel cin, so dW over cin + 4 channels has dbias as column cin
+    fused_bias = (BIAS_COLUMN_ENABLED and dbias is not None and x_sti is not None and dy_sti is not None and x_sti.ones
+                  and kh == 1 and kw == 1 and cin % 64 != 0 and cin + 4 <= (cin + 63) // 64 * 64)
+    tmp = None
+    if fused_bias:
+        tmp = torch.empty((cout, cin + 4), dtype=torch.float32, device=dw.device)
+    d = NsrWgrad(batch=B, h=H, w=W, cin=cin + 4 if fused_bias else cin, cout=cout, kh=kh, kw=kw, pad=kh // 2,
+                 x_ld=x_ld + 4 if fused_bias else x_ld, dy_ld=dy_ld,
                  engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
-                 x=x_ptr, dy=dy_ptr,
-                 dw=dw.data_ptr(), dbias=_p(dbias), workspace=None, workspace_bytes=0,
-                 x_sti=_p(x_sti), dy_sti=_p(dy_sti))
+                 x=None if fused_bias else x_ptr, dy=None if fused_bias else dy_ptr,
+                 dw=tmp.data_ptr() if fused_bias else dw.data_ptr(), dbias=None if fused_bias else _p(dbias),
+                 workspace=None, workspace_bytes=0, x_sti=_p(x_sti), dy_sti=_p(dy_sti))
     L = _lib.lib()
     need = L.nsr_conv_wgrad_workspace(C.byref(d))
     ws = scratch(need, x.device)
@@ -301,7 +312,9 @@ def conv_wgrad(x, dy, dw: Tensor, dbias: Tensor | None, kh: int, kw: int, engine
     with _prof("conv_wgrad" + ("_sti" if x_sti is not None and dy_sti is not None else ""), (M, cin, cout, kh),
                2.0 * M * cin * cout * kh * kw, 4.0 * M * (cin + cout)):
         check(L.nsr_conv_wgrad(C.byref(d), _stream()), "nsr_conv_wgrad")
-    _count(4 if dbias is not None else 2)
+        if fused_bias:
+            check(L.nsr_wgrad_split(tmp.data_ptr(), dw.data_ptr(), dbias.data_ptr(), cout, cin, cin + 4, _stream()), "nsr_wgrad_split")
+    _count(3 if fused_bias else (4 if dbias is not None else 2))
 
 
 # ----------------------------------------------------------------------------- layout
@@ -619,6 +632,8 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, sti
     rows = x.numel() // c
     y = torch.empty_like(x) if f32_out else None
     y_sti = STI(x.shape, x.device) if sti_out else None
+    if y_sti is not None:
+        y_sti.ones = c % 64 != 0
     mean = torch.empty(rows, dtype=torch.float32, device=x.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
     with _prof("nsr_layernorm_fwd", (rows, c), 0.0, 8.0 * x.numel()):
@@ -661,6 +676,8 @@ def window_attn_fwd(qkv: Tensor, table: Tensor, heads: int, ws: int, shift: int,
     c = c3 // 3
     out_sti = STI((B, H, W, c), qkv.device) if sti_out else None
     need_f32 = (not sti_out) or not _attn_mma_ok(c, heads, ws)
+    if out_sti is not None:
+        out_sti.ones = (not need_f32) and c % 64 != 0  # the tensor-core kernel writes the image itself
     out = torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device) if need_f32 else None
     with _prof("nsr_window_attn_fwd", (B * H * W, c, heads, ws), 0.0, 4.0 * (qkv.numel() + B * H * W * c)):
         check(_lib.lib().nsr_window_attn_fwd(qkv.data_ptr(), table.data_ptr(), _p(out), B, H, W, c, heads, ws, shift,
