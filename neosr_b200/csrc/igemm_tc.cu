@@ -36,17 +36,9 @@ struct TcCfg {
   static constexpr int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
   static constexpr int epi_warps = STI ? 12 : 4;
   static constexpr int epi_bytes = epi_warps * 32 * EPI_LD * 4;  // per-warp transpose tiles
-  // Narrow tiles (BN <= 128) are bound by the LATENCY of the im2col gather: with the A k-blocks staged through
-  // registers only one k-block (32 KiB) is in flight per SM (measured: 29 GB/s per SM, 10 us per 64->64 3x3 tile).
-  // There the producers gather with cp.async into raw fp32 staging buffers, several k-blocks deep, and split from
-  // shared memory; the price is fewer bf16 operand stages.
-  static constexpr int raw_stages = STI ? 0 : (BN == 64 ? 3 : (BN == 128 ? 2 : 0));
-  static constexpr int raw_bytes = raw_stages * TC_BM * 256;
-  static constexpr int budget = 227 * 1024 - 1024 - 256 - 128 - epi_bytes - raw_bytes;
+  static constexpr int budget = 227 * 1024 - 1024 - 256 - epi_bytes;
   static constexpr int stages = budget / stage_bytes > 4 ? 4 : budget / stage_bytes;
-  static constexpr int raw_offset = (stages * stage_bytes + 256 + epi_bytes + 127) / 128 * 128;
-  static constexpr int smem_bytes = stages * stage_bytes + 1024 /* align slack */ + 256 /* barriers */ + epi_bytes + 128 + raw_bytes;
-  static_assert(stages >= 2, "need at least two operand stages");
+  static constexpr int smem_bytes = stages * stage_bytes + 1024 /* align slack */ + 256 /* barriers */ + epi_bytes;
 };
 
 struct TcGeom {
@@ -136,62 +128,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) ++my_tiles;
     const int total = my_tiles * g.nk;
     float4 cur[4][2], nxt[4][2];
-    if constexpr (Cfg::raw_stages > 0) {
-      // ---- cp.async gather, raw_stages k-blocks deep; every thread reads back only what it copied itself
-      constexpr int RS = Cfg::raw_stages;
-      uint8_t* raw = smem + Cfg::raw_offset;
-      const uint32_t my_off = (uint32_t)(row0 * 256 + chunk * 32);
-      auto issue = [&](int slot) {  // gathers (l_tile, l_kb) into raw[slot] and advances the cursor
-        if (l_kb == 0) decode_rows(l_tile);
-        const int tap = l_kb / g.cblks, cblk = l_kb - tap * g.cblks;
-        const int r = tap / d.kw, sx = tap - r * d.kw;
-        const int dh = r - d.pad, dw = sx - d.pad;
-        const int c = cblk * TC_BK + chunk * 8;
-        const uint32_t dst0 = smem_u32(raw + slot * (TC_BM * 256)) + my_off;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ih = oh[i] + dh, iw = ow[i] + dw;
-          const bool ok = ih >= 0 && ih < d.h && iw >= 0 && iw < d.w;
-          const float* src = d.x + (pix[i] + (long long)dh * d.w + dw) * d.x_ld + c;
-          const uint32_t dst = dst0 + (uint32_t)i * (32 * 256);
-          const int n0 = (ok && c < d.cin) ? 16 : 0, n1 = (ok && c + 4 < d.cin) ? 16 : 0;  // src-size 0 => zero fill
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(n0 ? src : d.x), "r"(n0) : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16), "l"(n1 ? src + 4 : d.x), "r"(n1) : "memory");
-        }
-        if (++l_kb == g.nk) { l_kb = 0; l_tile += gridDim.x; }
-      };
-      for (int k = 0; k < RS; ++k) {
-        if (k < total) issue(k);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-      for (int it = 0; it < total; ++it) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(RS - 1) : "memory");
-        const uint8_t* rsrc = raw + (it % RS) * (TC_BM * 256) + my_off;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          cur[i][0] = *reinterpret_cast<const float4*>(rsrc + i * (32 * 256));
-          cur[i][1] = *reinterpret_cast<const float4*>(rsrc + i * (32 * 256) + 16);
-        }
-        if (it + RS < total) issue(it % RS);  // the slot is free again: its contents sit in registers
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* a_hi = smem + stage * Cfg::stage_bytes;
-        uint8_t* a_lo = a_hi + TC_A_BYTES;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = row0 + 32 * i;
-          uint4 hi, lo;
-          split8(cur[i][0], cur[i][1], hi, lo);
-          const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(a_hi + off) = hi;
-          *reinterpret_cast<uint4*>(a_lo + off) = lo;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&full[stage]);
-        if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
-      }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-    } else {
     if (total > 0) load(cur);
     for (int it = 0; it < total; ++it) {
       const bool more = it + 1 < total;
@@ -215,7 +151,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
 #pragma unroll
         for (int i = 0; i < 4; ++i) { cur[i][0] = nxt[i][0]; cur[i][1] = nxt[i][1]; }
       }
-    }
     }
   } else if (warp == TC_PROD_WARPS) {
     // ================================ B loader ============================================
