@@ -320,7 +320,13 @@ def run_ours(args) -> None:
             small = min(key[1], key[2]) < 16
             if small:
                 return "conv_small (3-channel image-side convs)"
-            return "igemm_wgrad_tc (tcgen05)" if "wgrad" in name else "igemm_fprop_tc (tcgen05, fprop+dgrad)"
+            if "wgrad" in name:
+                return "igemm_wgrad_tc (tcgen05)"
+            # two instantiations of the kernel template, two different kernels in the binary: <BN, STI=true> takes
+            # bulk-copied split-tile operands (the 1x1 contractions of the transformer body), <BN, STI=false> gathers the
+            # im2col tile with producer warps (3x3 convs)
+            return ("igemm_fprop_tc<STI> (tcgen05, 1x1 fprop+dgrad, bulk-copied operands)" if name.endswith("_sti")
+                    else "igemm_fprop_tc (tcgen05, 3x3 fprop+dgrad, producer warps)")
         return name
     fams: dict = {}
     for (name, key), r in agg.items():
