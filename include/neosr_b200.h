@@ -489,6 +489,10 @@ int nsr_reflect_fold(const float* dpad, const float* d_direct, const float* x, f
  * wrap to the end of the table as Python indexing does).  out: [tokens, c]; lse: log-sum-exp per (window, head,
  * query) for the backward pass (nsr_xwin_attn_stat_floats floats).  head dim <= 32, (ws+ows-1) <= 39. */
 size_t nsr_xwin_attn_stat_floats(int batch, int h, int w, int heads, int ws);
+/* Engine of the nsr_xwin_attn_* calls: 1 (default) = mma.sync tensor-core kernels (bf16 hi/lo split, 3 passes, fp32
+ * accumulate) where the shape allows (even head dim <= 32), 0 = exact-fp32 CUDA-core kernels.  Process-wide switch for
+ * cross-checks; returns the previous setting. */
+int nsr_xwin_attn_use_tensor_cores(int on);
 int nsr_xwin_attn_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int batch, int h, int w, int c,
                       int heads, int ws, int ows, int shift, int use_mask, float scale, void* stream);
 size_t nsr_xwin_attn_bwd_workspace(int batch, int h, int w, int c, int heads, int ws, int ows);

@@ -4,7 +4,7 @@
 // materialise) — and the CAB channel-attention gate (15-52).  fp32 CUDA-core kernels, flash-style: the
 // [Nq x Nk] score matrix never leaves registers; backward recomputes it from the saved log-sum-exp.
 // Everything is deterministic (fixed-order partial sums, no float atomics).
-#include "common.cuh"
+#include "xwin_geom.cuh"
 
 namespace nsr {
 
@@ -12,46 +12,6 @@ constexpr int GA_D = 32;       // max head dim
 constexpr int GA_THREADS = 128;
 constexpr int GA_CHUNK = 32;   // keys (fwd / bwd-q) or queries (bwd-kv) staged per step
 constexpr int GA_MAXTAB = 39 * 39;
-
-struct GAGeom {
-  int B, H, W, C, heads, D, ws, ows, pad, shift, use_mask, oca, nwh, nww, Nq, Nk, L, ntab;
-  float scale;
-};
-
-// query n of window wi -> token index + mask region id (shifted frame), HAB only uses shift/mask
-__device__ __forceinline__ void ga_query(const GAGeom& g, int wi, int n, int& tok, int& rid, int& iy, int& ix) {
-  const int per = g.nwh * g.nww, b = wi / per, rem = wi - b * per, wy = rem / g.nww, wx = rem - wy * g.nww;
-  iy = n / g.ws; ix = n - iy * g.ws;
-  const int hs = wy * g.ws + iy, wsx = wx * g.ws + ix;
-  int ho = hs + g.shift, wo = wsx + g.shift;  // torch.roll(x, -shift)
-  if (ho >= g.H) ho -= g.H;
-  if (wo >= g.W) wo -= g.W;
-  tok = (b * g.H + ho) * g.W + wo;
-  const int rh = hs < g.H - g.ws ? 0 : (hs < g.H - g.shift ? 1 : 2), rw = wsx < g.W - g.ws ? 0 : (wsx < g.W - g.shift ? 1 : 2);
-  rid = rh * 3 + rw;
-}
-// key n of window wi -> token index (-1: zero padding of nn.Unfold) + region id
-__device__ __forceinline__ void ga_key(const GAGeom& g, int wi, int n, int& tok, int& rid, int& jy, int& jx) {
-  const int per = g.nwh * g.nww, b = wi / per, rem = wi - b * per, wy = rem / g.nww, wx = rem - wy * g.nww;
-  jy = n / g.ows; jx = n - jy * g.ows;
-  const int hs = wy * g.ws - g.pad + jy, wsx = wx * g.ws - g.pad + jx;
-  if (hs < 0 || hs >= g.H || wsx < 0 || wsx >= g.W) { tok = -1; rid = 0; return; }
-  int ho = hs + g.shift, wo = wsx + g.shift;
-  if (ho >= g.H) ho -= g.H;
-  if (wo >= g.W) wo -= g.W;
-  tok = (b * g.H + ho) * g.W + wo;
-  const int rh = hs < g.H - g.ws ? 0 : (hs < g.H - g.shift ? 1 : 2), rw = wsx < g.W - g.ws ? 0 : (wsx < g.W - g.shift ? 1 : 2);
-  rid = rh * 3 + rw;
-}
-// relative_position_index: SA (hat_arch.py:1015-1033) / OCA (1035-1068; negative entries index the table from
-// its end, as Python indexing does in the reference)
-__device__ __forceinline__ int ga_rel(const GAGeom& g, int iy, int ix, int jy, int jx) {
-  if (!g.oca) return (iy - jy + g.ws - 1) * g.L + (ix - jx + g.ws - 1);
-  const int off = g.ws - g.ows + 1;
-  int e = (jy - iy + off) * g.L + (jx - ix + off);
-  if (e < 0) e += g.ntab;
-  return e;
-}
 
 __global__ void __launch_bounds__(GA_THREADS) ga_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ table,
                                                             float* __restrict__ out, float* __restrict__ lse, GAGeom g) {
@@ -307,6 +267,11 @@ __global__ void ga_dtab_reduce_kernel(const float* __restrict__ part, float* __r
   dtable[idx] = s;
 }
 
+// tensor-core implementations (xwin_attn_mma.cu)
+bool xwin_attn_mma_supported(const GAGeom& g);
+int xwin_fwd_mma_launch(const float* qkv, const float* table, float* out, float* lse, const GAGeom& g, cudaStream_t st);
+static int g_xwin_tc = 1;  // 1: mma.sync 3xBF16 kernels where supported; 0: exact-fp32 CUDA-core kernels (cross-check)
+
 static int ga_make(GAGeom& g, int batch, int h, int w, int c, int heads, int ws, int ows, int shift, int use_mask, float scale,
                    const char* who) {
   NSR_CHECK_ARG(batch > 0 && h > 0 && w > 0 && c > 0 && heads > 0 && c % heads == 0, "%s: bad shape", who);
@@ -432,6 +397,11 @@ static inline int grid1(size_t total) {
 }  // namespace nsr
 using namespace nsr;
 
+extern "C" int nsr_xwin_attn_use_tensor_cores(int on) {
+  const int prev = g_xwin_tc;
+  g_xwin_tc = on ? 1 : 0;
+  return prev;
+}
 extern "C" size_t nsr_xwin_attn_stat_floats(int batch, int h, int w, int heads, int ws) {
   return (size_t)batch * (h / ws) * (w / ws) * heads * ws * ws;
 }
@@ -441,6 +411,7 @@ extern "C" int nsr_xwin_attn_fwd(const float* qkv, const float* bias_table, floa
   GAGeom g;
   int rc = ga_make(g, batch, h, w, c, heads, ws, ows, shift, use_mask, scale, "nsr_xwin_attn_fwd");
   if (rc) return rc;
+  if (g_xwin_tc && xwin_attn_mma_supported(g)) return xwin_fwd_mma_launch(qkv, bias_table, out, lse, g, (cudaStream_t)stream);
   dim3 grid(batch * g.nwh * g.nww * heads, ceil_div(g.Nq, GA_THREADS));
   ga_fwd_kernel<<<grid, GA_THREADS, 0, (cudaStream_t)stream>>>(qkv, bias_table, out, lse, g);
   NSR_CHECK_LAUNCH("nsr_xwin_attn_fwd");

@@ -1,0 +1,165 @@
+// Generic (cross-)window attention on the tensor cores: HAT's HAB self-attention (16x16 windows, 256 x 256 scores per
+// head) and OCAB overlapping cross-attention (256 queries x 576 zero-padded keys), hat_arch.py:168-215, 445-515.
+// Same scheme as the 8x8-window kernels (window_attn_mma.cu): warp-level mma.sync m16n8k16, every operand split into
+// bf16 hi + lo and multiplied in three passes with fp32 accumulation; the score tile lives in registers, flash-style
+// (running max / sum per query row), and the backward pass recomputes it from the saved log-sum-exp.
+//   forward     : CTA = (window, head, 64-query tile), 4 warps x 16 rows, loop over 64-key chunks
+//   backward dQ : same tiling; dS = P o (dP - delta), dQ += dS K
+//   backward dKV: CTA = (window, head, 64-key tile), loop over 64-query chunks on the TRANSPOSED problem
+//                 (S^T = K Qs^T), dK += dS^T Qs, dV += P^T dO; the bias-table gradient is accumulated with 64-bit
+//                 fixed-point shared-memory atomics (integer adds commute: deterministic), per-CTA partials reduced in
+//                 a fixed order.
+#include "attn_mma.cuh"
+#include "xwin_geom.cuh"
+
+namespace nsr {
+
+constexpr int XM_T = 64;        // tile edge (queries / keys per step)
+constexpr int XM_THREADS = 128;
+constexpr int XM_MAXTAB = 39 * 39;
+constexpr float XM_FIX = 1099511627776.0f;  // 2^40: fixed-point scale of the bias-table gradient accumulators
+
+// rows n = 0..63 -> tokens tokv[n] (-1: zero row); D channels at column offset coff of a [tokens, ld] fp32 tensor, times mul;
+// written as bf16 hi/lo [n][AM_LD] tiles and, when Tth != nullptr, transposed [d][AM_LDT] tiles
+__device__ __forceinline__ void xm_load_tile(const float* __restrict__ base, size_t ld, int coff, const int* tokv, int D, float mul,
+                                             __nv_bfloat16* Th, __nv_bfloat16* Tl, __nv_bfloat16* Tth, __nv_bfloat16* Ttl, int t) {
+  const int hp = D >> 1;
+  for (int idx = t; idx < XM_T * hp; idx += XM_THREADS) {
+    const int n = idx / hp, pr = idx - n * hp;
+    const int tk = tokv[n];
+    float2 v = make_float2(0.f, 0.f);
+    if (tk >= 0) v = *reinterpret_cast<const float2*>(base + (size_t)tk * ld + coff + 2 * pr);
+    uint32_t hi, lo;
+    split_pair(v.x * mul, v.y * mul, hi, lo);
+    if (Th) {
+      *reinterpret_cast<uint32_t*>(&Th[n * AM_LD + 2 * pr]) = hi;
+      *reinterpret_cast<uint32_t*>(&Tl[n * AM_LD + 2 * pr]) = lo;
+    }
+    if (Tth) {
+      const int t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
+      reinterpret_cast<uint16_t*>(Tth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Tth)[t1] = (uint16_t)(hi >> 16);
+      reinterpret_cast<uint16_t*>(Ttl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ttl)[t1] = (uint16_t)(lo >> 16);
+    }
+  }
+}
+__device__ __forceinline__ void xm_zero(__nv_bfloat16* p, int n, int t) {
+  for (int i = t; i < n / 2; i += XM_THREADS) reinterpret_cast<uint32_t*>(p)[i] = 0u;
+}
+
+struct XmMeta {  // per-token metadata of a 64-token tile
+  int tok[XM_T], rid[XM_T], y[XM_T], x[XM_T];
+};
+__device__ __forceinline__ void xm_query_meta(const GAGeom& g, int wi, int q0, XmMeta& m, int t) {
+  if (t < XM_T) {
+    int tk = -1, r = -1, iy = 0, ix = 0;
+    if (q0 + t < g.Nq) ga_query(g, wi, q0 + t, tk, r, iy, ix);
+    m.tok[t] = tk; m.rid[t] = r; m.y[t] = iy; m.x[t] = ix;
+  }
+}
+__device__ __forceinline__ void xm_key_meta(const GAGeom& g, int wi, int k0, XmMeta& m, int t) {
+  if (t < XM_T) {
+    int tk = -1, r = -2, jy = 0, jx = 0;  // rid -2: beyond Nk (excluded); a zero-padded key of nn.Unfold keeps tok -1, rid 0
+    if (k0 + t < g.Nk) ga_key(g, wi, k0 + t, tk, r, jy, jx);
+    m.tok[t] = tk; m.rid[t] = r; m.y[t] = jy; m.x[t] = jx;
+  }
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(XM_THREADS) xwin_fwd_mma(const float* __restrict__ qkv, const float* __restrict__ table,
+                                                           float* __restrict__ out, float* __restrict__ lse, GAGeom gm) {
+  __shared__ __align__(16) __nv_bfloat16 Qh[XM_T * AM_LD], Ql[XM_T * AM_LD], Kh[XM_T * AM_LD], Kl[XM_T * AM_LD];
+  __shared__ __align__(16) __nv_bfloat16 Vth[32 * AM_LDT], Vtl[32 * AM_LDT];
+  __shared__ float tab[XM_MAXTAB];
+  __shared__ XmMeta qm, km;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
+  const int wi = blockIdx.x / gm.heads, head = blockIdx.x - wi * gm.heads, q0 = blockIdx.y * XM_T;
+  const int row0 = warp * 16;
+  for (int e = t; e < gm.ntab; e += XM_THREADS) tab[e] = table[(size_t)e * gm.heads + head];
+  xm_zero(Qh, XM_T * AM_LD, t); xm_zero(Ql, XM_T * AM_LD, t); xm_zero(Kh, XM_T * AM_LD, t); xm_zero(Kl, XM_T * AM_LD, t);
+  xm_zero(Vth, 32 * AM_LDT, t); xm_zero(Vtl, 32 * AM_LDT, t);
+  xm_query_meta(gm, wi, q0, qm, t);
+  __syncthreads();
+  xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm.tok, gm.D, gm.scale, Qh, Ql, nullptr, nullptr, t);
+  float o[4][4], mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  int qy[2], qx[2], qr[2];
+  for (int k0 = 0; k0 < gm.Nk; k0 += XM_T) {
+    __syncthreads();  // previous chunk consumed (first pass: Q tile / metadata written)
+    xm_key_meta(gm, wi, k0, km, t);
+    __syncthreads();
+    xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km.tok, gm.D, 1.f, Kh, Kl, nullptr, nullptr, t);
+    xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km.tok, gm.D, 1.f, nullptr, nullptr, Vth, Vtl, t);
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) { qy[h] = qm.y[row0 + g + 8 * h]; qx[h] = qm.x[row0 + g + 8 * h]; qr[h] = qm.rid[row0 + g + 8 * h]; }
+    float s[8][4];
+    qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, s);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float cm = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + tid * 2 + e;
+          const int kr = km.rid[j];
+          float v = -INFINITY;
+          if (kr != -2) {
+            v = s[nt][2 * h + e] + tab[ga_rel(gm, qy[h], qx[h], km.y[j], km.x[j])];
+            if (gm.use_mask && kr != qr[h]) v += -100.f;
+          }
+          s[nt][2 * h + e] = v;
+          cm = fmaxf(cm, v);
+        }
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+      const float mn = fmaxf(mrun[h], cm), corr = __expf(mrun[h] - mn);
+      mrun[h] = mn;
+      float ps = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float p = __expf(s[nt][2 * h + e] - mn);
+          s[nt][2 * h + e] = p;
+          ps += p;
+        }
+      lrun[h] = lrun[h] * corr + ps;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { o[nt][2 * h] *= corr; o[nt][2 * h + 1] *= corr; }
+    }
+    float oc[4][4];
+    acc_times(s, Vth, Vtl, g, tid, oc);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[nt][e] += oc[nt][e];
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float l = lrun[h];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const int i = row0 + g + 8 * h, tk = qm.tok[i];
+    if (tk < 0) continue;
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = nt * 8 + tid * 2;
+      if (c < gm.D) *reinterpret_cast<float2*>(out + (size_t)tk * gm.C + head * gm.D + c) = make_float2(o[nt][2 * h] * inv, o[nt][2 * h + 1] * inv);
+    }
+    if (tid == 0) lse[((size_t)wi * gm.heads + head) * gm.Nq + q0 + i] = mrun[h] + logf(l);
+  }
+}
+
+bool xwin_attn_mma_supported(const GAGeom& g) { return g.D % 2 == 0 && g.D <= 32 && g.C % 2 == 0 && g.ntab <= XM_MAXTAB; }
+
+int xwin_fwd_mma_launch(const float* qkv, const float* table, float* out, float* lse, const GAGeom& g, cudaStream_t st) {
+  dim3 grid(g.B * g.nwh * g.nww * g.heads, ceil_div(g.Nq, XM_T));
+  xwin_fwd_mma<<<grid, XM_THREADS, 0, st>>>(qkv, table, out, lse, g);
+  NSR_CHECK_LAUNCH("xwin_fwd_mma");
+  return NSR_OK;
+}
+
+}  // namespace nsr
