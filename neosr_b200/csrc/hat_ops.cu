@@ -270,6 +270,9 @@ __global__ void ga_dtab_reduce_kernel(const float* __restrict__ part, float* __r
 // tensor-core implementations (xwin_attn_mma.cu)
 bool xwin_attn_mma_supported(const GAGeom& g);
 int xwin_fwd_mma_launch(const float* qkv, const float* table, float* out, float* lse, const GAGeom& g, cudaStream_t st);
+int xwin_bwd_mma_launch(const float* qkv, const float* table, const float* out, const float* dout, const float* lse, float* delta,
+                        float* dqkv, float* dkv_win, float* part, const GAGeom& g, cudaStream_t st);
+constexpr int GA_KTILE_MMA = 64;  // keys per CTA of the tensor-core dK/dV kernel (more, smaller partial tables)
 static int g_xwin_tc = 1;  // 1: mma.sync 3xBF16 kernels where supported; 0: exact-fp32 CUDA-core kernels (cross-check)
 
 static int ga_make(GAGeom& g, int batch, int h, int w, int c, int heads, int ws, int ows, int shift, int use_mask, float scale,
@@ -419,7 +422,7 @@ extern "C" int nsr_xwin_attn_fwd(const float* qkv, const float* bias_table, floa
 }
 extern "C" size_t nsr_xwin_attn_bwd_workspace(int batch, int h, int w, int c, int heads, int ws, int ows) {
   const size_t nwin = (size_t)batch * (h / ws) * (w / ws);
-  const size_t ntab = (size_t)(ws + ows - 1) * (ws + ows - 1), ktiles = (size_t)ceil_div(ows * ows, GA_THREADS);
+  const size_t ntab = (size_t)(ws + ows - 1) * (ws + ows - 1), ktiles = (size_t)ceil_div(ows * ows, GA_KTILE_MMA);
   size_t fl = nwin * heads * ws * ws;              // delta
   fl += ktiles * nwin * heads * ntab;              // bias-table partials
   if (ows != ws) fl += nwin * ows * ows * 2 * c;   // per-window dk/dv
@@ -437,14 +440,20 @@ extern "C" int nsr_xwin_attn_bwd(const float* qkv, const float* bias_table, cons
     return NSR_E_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int nwin = batch * g.nwh * g.nww, ktiles = ceil_div(g.Nk, GA_THREADS);
+  const bool tc = g_xwin_tc && xwin_attn_mma_supported(g);
+  const int nwin = batch * g.nwh * g.nww, ktiles = ceil_div(g.Nk, tc ? GA_KTILE_MMA : GA_THREADS);
   float* delta = (float*)workspace;
   float* part = delta + (size_t)nwin * heads * g.Nq;
-  float* dkv_win = g.oca ? part + (size_t)ktiles * nwin * heads * g.ntab : nullptr;
-  ga_bwd_q_kernel<<<dim3(nwin * heads, ceil_div(g.Nq, GA_THREADS)), GA_THREADS, 0, st>>>(qkv, bias_table, out, dout, lse, delta, dqkv, g);
-  NSR_CHECK_LAUNCH("nsr_xwin_attn_bwd(q)");
-  ga_bwd_kv_kernel<<<dim3(nwin * heads, ktiles), GA_THREADS, 0, st>>>(qkv, bias_table, dout, lse, delta, dqkv, dkv_win, part, g);
-  NSR_CHECK_LAUNCH("nsr_xwin_attn_bwd(kv)");
+  float* dkv_win = g.oca ? part + (size_t)ceil_div(g.Nk, GA_KTILE_MMA) * nwin * heads * g.ntab : nullptr;
+  if (tc) {
+    rc = xwin_bwd_mma_launch(qkv, bias_table, out, dout, lse, delta, dqkv, dkv_win, part, g, st);
+    if (rc) return rc;
+  } else {
+    ga_bwd_q_kernel<<<dim3(nwin * heads, ceil_div(g.Nq, GA_THREADS)), GA_THREADS, 0, st>>>(qkv, bias_table, out, dout, lse, delta, dqkv, g);
+    NSR_CHECK_LAUNCH("nsr_xwin_attn_bwd(q)");
+    ga_bwd_kv_kernel<<<dim3(nwin * heads, ktiles), GA_THREADS, 0, st>>>(qkv, bias_table, dout, lse, delta, dqkv, dkv_win, part, g);
+    NSR_CHECK_LAUNCH("nsr_xwin_attn_bwd(kv)");
+  }
   if (g.oca) {
     ga_fold_kernel<<<grid1((size_t)batch * h * w * 2 * c), 256, 0, st>>>(dkv_win, dqkv, g);
     NSR_CHECK_LAUNCH("nsr_xwin_attn_bwd(fold)");

@@ -153,6 +153,226 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_fwd_mma(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------ backward: dQ
+// dynamic smem: Qh Ql Oh Ol Kh Kl Vh Vl [64][AM_LD] | Kth Ktl [32][AM_LDT] | tab | metas | delta
+constexpr size_t XQ_SMEM = (size_t)(8 * XM_T * AM_LD + 2 * 32 * AM_LDT) * sizeof(__nv_bfloat16) + XM_MAXTAB * sizeof(float) +
+                           2 * sizeof(XmMeta) + 2 * XM_T * sizeof(float);
+__global__ void __launch_bounds__(XM_THREADS) xwin_bwd_q_mma(const float* __restrict__ qkv, const float* __restrict__ table,
+                                                             const float* __restrict__ out, const float* __restrict__ dout,
+                                                             const float* __restrict__ lse, float* __restrict__ delta,
+                                                             float* __restrict__ dqkv, GAGeom gm) {
+  extern __shared__ __align__(16) uint8_t xsm[];
+  __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(xsm);
+  __nv_bfloat16 *Ql = Qh + XM_T * AM_LD, *Oh = Ql + XM_T * AM_LD, *Ol = Oh + XM_T * AM_LD, *Kh = Ol + XM_T * AM_LD;
+  __nv_bfloat16 *Kl = Kh + XM_T * AM_LD, *Vh = Kl + XM_T * AM_LD, *Vl = Vh + XM_T * AM_LD, *Kth = Vl + XM_T * AM_LD;
+  __nv_bfloat16* Ktl = Kth + 32 * AM_LDT;
+  float* tab = reinterpret_cast<float*>(Ktl + 32 * AM_LDT);
+  XmMeta* qm = reinterpret_cast<XmMeta*>(tab + XM_MAXTAB);
+  XmMeta* km = qm + 1;
+  float* lse_s = reinterpret_cast<float*>(km + 1);
+  float* del_s = lse_s + XM_T;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
+  const int wi = blockIdx.x / gm.heads, head = blockIdx.x - wi * gm.heads, q0 = blockIdx.y * XM_T;
+  const int row0 = warp * 16;
+  for (int e = t; e < gm.ntab; e += XM_THREADS) tab[e] = table[(size_t)e * gm.heads + head];
+  xm_zero(Qh, 8 * XM_T * AM_LD + 2 * 32 * AM_LDT, t);
+  xm_query_meta(gm, wi, q0, *qm, t);
+  __syncthreads();
+  if (t < XM_T) {
+    const int tk = qm->tok[t];
+    float dl = 0.f, L = 0.f;
+    if (tk >= 0) {
+      const float* op = out + (size_t)tk * gm.C + head * gm.D;
+      const float* gp = dout + (size_t)tk * gm.C + head * gm.D;
+      for (int d = 0; d < gm.D; ++d) dl = fmaf(gp[d], op[d], dl);
+      const size_t si = ((size_t)wi * gm.heads + head) * gm.Nq + q0 + t;
+      L = lse[si];
+      delta[si] = dl;
+    }
+    lse_s[t] = L;
+    del_s[t] = dl;
+  }
+  xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm->tok, gm.D, gm.scale, Qh, Ql, nullptr, nullptr, t);
+  xm_load_tile(dout, (size_t)gm.C, head * gm.D, qm->tok, gm.D, 1.f, Oh, Ol, nullptr, nullptr, t);
+  float dq[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+  for (int k0 = 0; k0 < gm.Nk; k0 += XM_T) {
+    __syncthreads();
+    xm_key_meta(gm, wi, k0, *km, t);
+    __syncthreads();
+    xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km->tok, gm.D, 1.f, Kh, Kl, Kth, Ktl, t);
+    xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km->tok, gm.D, 1.f, Vh, Vl, nullptr, nullptr, t);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+    qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, s);
+    qk_scores(Oh, Ol, Vh, Vl, row0, g, tid, dp);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = row0 + g + 8 * h;
+      const int qy = qm->y[i], qx = qm->x[i], qr = qm->rid[i];
+      const float L = lse_s[i], dl = del_s[i];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + tid * 2 + e;
+          const int kr = km->rid[j];
+          float ds = 0.f;
+          if (kr != -2) {
+            float v = s[nt][2 * h + e] + tab[ga_rel(gm, qy, qx, km->y[j], km->x[j])];
+            if (gm.use_mask && kr != qr) v += -100.f;
+            ds = __expf(v - L) * (dp[nt][2 * h + e] - dl);
+          }
+          s[nt][2 * h + e] = ds;
+        }
+    }
+    float oc[4][4];
+    acc_times(s, Kth, Ktl, g, tid, oc);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dq[nt][e] += oc[nt][e];
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int tk = qm->tok[row0 + g + 8 * h];
+    if (tk < 0) continue;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = nt * 8 + tid * 2;
+      if (c < gm.D)
+        *reinterpret_cast<float2*>(dqkv + (size_t)tk * 3 * gm.C + head * gm.D + c) = make_float2(dq[nt][2 * h] * gm.scale, dq[nt][2 * h + 1] * gm.scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward: dK, dV, bias-table gradient
+// dynamic smem: Kh Kl Vh Vl Qh Ql Oh Ol [64][AM_LD] | Qth Qtl Oth Otl [32][AM_LDT] | dtab64 | tab | metas | lse, delta
+constexpr size_t XK_SMEM = (size_t)(8 * XM_T * AM_LD + 4 * 32 * AM_LDT) * sizeof(__nv_bfloat16) + XM_MAXTAB * (sizeof(float) + 8) +
+                           2 * sizeof(XmMeta) + 2 * XM_T * sizeof(float) + 16;
+__global__ void __launch_bounds__(XM_THREADS) xwin_bwd_kv_mma(const float* __restrict__ qkv, const float* __restrict__ table,
+                                                              const float* __restrict__ dout, const float* __restrict__ lse,
+                                                              const float* __restrict__ delta, float* __restrict__ dqkv,
+                                                              float* __restrict__ dkv_win, float* __restrict__ dtab_part, GAGeom gm) {
+  extern __shared__ __align__(16) uint8_t xsm[];
+  unsigned long long* dtab64 = reinterpret_cast<unsigned long long*>(xsm);
+  __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(dtab64 + XM_MAXTAB);
+  __nv_bfloat16 *Kl = Kh + XM_T * AM_LD, *Vh = Kl + XM_T * AM_LD, *Vl = Vh + XM_T * AM_LD, *Qh = Vl + XM_T * AM_LD;
+  __nv_bfloat16 *Ql = Qh + XM_T * AM_LD, *Oh = Ql + XM_T * AM_LD, *Ol = Oh + XM_T * AM_LD, *Qth = Ol + XM_T * AM_LD;
+  __nv_bfloat16 *Qtl = Qth + 32 * AM_LDT, *Oth = Qtl + 32 * AM_LDT, *Otl = Oth + 32 * AM_LDT;
+  float* tab = reinterpret_cast<float*>(Otl + 32 * AM_LDT);
+  XmMeta* km = reinterpret_cast<XmMeta*>(tab + XM_MAXTAB);
+  XmMeta* qm = km + 1;
+  float* lse_s = reinterpret_cast<float*>(qm + 1);
+  float* del_s = lse_s + XM_T;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
+  const int wi = blockIdx.x / gm.heads, head = blockIdx.x - wi * gm.heads, k0 = blockIdx.y * XM_T;
+  const int row0 = warp * 16;
+  for (int e = t; e < gm.ntab; e += XM_THREADS) { tab[e] = table[(size_t)e * gm.heads + head]; dtab64[e] = 0ull; }
+  xm_zero(Kh, 8 * XM_T * AM_LD + 4 * 32 * AM_LDT, t);
+  xm_key_meta(gm, wi, k0, *km, t);
+  __syncthreads();
+  xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km->tok, gm.D, 1.f, Kh, Kl, nullptr, nullptr, t);
+  xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km->tok, gm.D, 1.f, Vh, Vl, nullptr, nullptr, t);
+  float dk[4][4], dv[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dk[nt][e] = 0.f; dv[nt][e] = 0.f; }
+  for (int q0 = 0; q0 < gm.Nq; q0 += XM_T) {
+    __syncthreads();
+    xm_query_meta(gm, wi, q0, *qm, t);
+    if (t < XM_T) {
+      const bool ok = q0 + t < gm.Nq;
+      const size_t si = ((size_t)wi * gm.heads + head) * gm.Nq + q0 + t;
+      lse_s[t] = ok ? lse[si] : 0.f;
+      del_s[t] = ok ? delta[si] : 0.f;
+    }
+    __syncthreads();
+    xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm->tok, gm.D, gm.scale, Qh, Ql, Qth, Qtl, t);
+    xm_load_tile(dout, (size_t)gm.C, head * gm.D, qm->tok, gm.D, 1.f, Oh, Ol, Oth, Otl, t);
+    __syncthreads();
+    float st[8][4], dpt[8][4];
+    qk_scores(Kh, Kl, Qh, Ql, row0, g, tid, st);    // S^T[j][i]  = K_j . Qs_i
+    qk_scores(Vh, Vl, Oh, Ol, row0, g, tid, dpt);   // dP^T[j][i] = V_j . dO_i
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = row0 + g + 8 * h;
+      const int ky = km->y[j], kx = km->x[j], kr = km->rid[j];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = nt * 8 + tid * 2 + e;
+          float p = 0.f, ds = 0.f;
+          if (kr != -2 && qm->tok[i] >= 0) {
+            const int ti = ga_rel(gm, qm->y[i], qm->x[i], ky, kx);
+            float v = st[nt][2 * h + e] + tab[ti];
+            if (gm.use_mask && kr != qm->rid[i]) v += -100.f;
+            p = __expf(v - lse_s[i]);
+            ds = p * (dpt[nt][2 * h + e] - del_s[i]);
+            atomicAdd(&dtab64[ti], (unsigned long long)__float2ll_rn(ds * XM_FIX));
+          }
+          st[nt][2 * h + e] = ds;
+          dpt[nt][2 * h + e] = p;
+        }
+    }
+    float oc[4][4];
+    acc_times(st, Qth, Qtl, g, tid, oc);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dk[nt][e] += oc[nt][e];
+    acc_times(dpt, Oth, Otl, g, tid, oc);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dv[nt][e] += oc[nt][e];
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = row0 + g + 8 * h;
+    if (km->rid[j] == -2) continue;
+    const int tk = km->tok[j];
+    float* o = nullptr;
+    if (dkv_win) o = dkv_win + (((size_t)wi * gm.Nk + k0 + j) * 2) * gm.C + head * gm.D;
+    else if (tk >= 0) o = dqkv + (size_t)tk * 3 * gm.C + gm.C + head * gm.D;
+    if (!o) continue;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = nt * 8 + tid * 2;
+      if (c < gm.D) {
+        *reinterpret_cast<float2*>(o + c) = make_float2(dk[nt][2 * h], dk[nt][2 * h + 1]);
+        *reinterpret_cast<float2*>(o + gm.C + c) = make_float2(dv[nt][2 * h], dv[nt][2 * h + 1]);
+      }
+    }
+  }
+  __syncthreads();
+  float* part = dtab_part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * gm.ntab;
+  for (int e = t; e < gm.ntab; e += XM_THREADS) part[e] = (float)((double)(long long)dtab64[e] * (1.0 / (double)XM_FIX));
+}
+
+int xwin_bwd_mma_launch(const float* qkv, const float* table, const float* out, const float* dout, const float* lse, float* delta,
+                        float* dqkv, float* dkv_win, float* part, const GAGeom& g, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(xwin_bwd_q_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XQ_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(xwin_bwd_kv_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XK_SMEM);
+    if (e != cudaSuccess) {
+      set_error("xwin_bwd_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return NSR_E_CUDA;
+    }
+    attr = true;
+  }
+  const int nwh = g.B * g.nwh * g.nww * g.heads;
+  xwin_bwd_q_mma<<<dim3(nwh, ceil_div(g.Nq, XM_T)), XM_THREADS, XQ_SMEM, st>>>(qkv, table, out, dout, lse, delta, dqkv, g);
+  NSR_CHECK_LAUNCH("xwin_bwd_q_mma");
+  xwin_bwd_kv_mma<<<dim3(nwh, ceil_div(g.Nk, XM_T)), XM_THREADS, XK_SMEM, st>>>(qkv, table, dout, lse, delta, dqkv, dkv_win, part, g);
+  NSR_CHECK_LAUNCH("xwin_bwd_kv_mma");
+  return NSR_OK;
+}
+
 bool xwin_attn_mma_supported(const GAGeom& g) { return g.D % 2 == 0 && g.D <= 32 && g.C % 2 == 0 && g.ntab <= XM_MAXTAB; }
 
 int xwin_fwd_mma_launch(const float* qkv, const float* table, float* out, float* lse, const GAGeom& g, cudaStream_t st) {

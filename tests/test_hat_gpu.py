@@ -27,12 +27,10 @@ class _engine:
         self.tc = tc
 
     def __enter__(self):
-        from neosr_b200 import _lib
-        self.prev = _lib.lib().nsr_xwin_attn_use_tensor_cores(self.tc)
+        self.prev, ops.XWIN_TENSOR_CORES = ops.XWIN_TENSOR_CORES, bool(self.tc)
 
     def __exit__(self, *a):
-        from neosr_b200 import _lib
-        _lib.lib().nsr_xwin_attn_use_tensor_cores(self.prev)
+        ops.XWIN_TENSOR_CORES = self.prev
 
 
 def _self_attn_ref(qkv, table, heads, ws, shift):
