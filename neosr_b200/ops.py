@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import ACT, ENGINE, NsrConv, NsrWgrad, check
 
 
-XWIN_TENSOR_CORES = True     # HAT window attention on mma.sync (False: exact-fp32 CUDA-core kernels)
+XWIN_TENSOR_CORES = 1        # HAT window attention engine mask: bit 0 forward, bit 1 backward on mma.sync; 0 = exact fp32
 BIAS_COLUMN_ENABLED = True  # bias gradients from the ones channel of split tile images (tests flip it)
 LK16_ENABLED = True   # route 16->16-channel k>=7 convs to the dedicated large-kernel kernels (tests flip it)
 DEFAULT_ENGINE = "auto"  # what engine="auto" resolves to ("auto" | "simt" | "tcgen05"); tests flip it
@@ -1003,7 +1003,7 @@ def xwin_attn_fwd(qkv: Tensor, table: Tensor, heads: int, ws: int, ows: int, shi
     B, H, W, c3 = qkv.shape
     c = c3 // 3
     L = _lib.lib()
-    L.nsr_xwin_attn_use_tensor_cores(int(XWIN_TENSOR_CORES and DEFAULT_ENGINE != "simt"))  # the exact-fp32 engines go together
+    L.nsr_xwin_attn_use_tensor_cores(0 if DEFAULT_ENGINE == "simt" else int(XWIN_TENSOR_CORES))  # the exact-fp32 engines go together
     out = torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device)
     lse = torch.empty(L.nsr_xwin_attn_stat_floats(B, H, W, heads, ws), dtype=torch.float32, device=qkv.device)
     nk = ows * ows
@@ -1020,7 +1020,7 @@ def xwin_attn_bwd(qkv: Tensor, table: Tensor, out: Tensor, dout: Tensor, lse: Te
     B, H, W, c3 = qkv.shape
     c = c3 // 3
     L = _lib.lib()
-    L.nsr_xwin_attn_use_tensor_cores(int(XWIN_TENSOR_CORES and DEFAULT_ENGINE != "simt"))
+    L.nsr_xwin_attn_use_tensor_cores(0 if DEFAULT_ENGINE == "simt" else int(XWIN_TENSOR_CORES))
     dqkv = torch.empty_like(qkv)
     ws_t = scratch(L.nsr_xwin_attn_bwd_workspace(B, H, W, c, heads, ws, ows), qkv.device)
     nk = ows * ows

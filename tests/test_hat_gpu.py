@@ -27,7 +27,7 @@ class _engine:
         self.tc = tc
 
     def __enter__(self):
-        self.prev, ops.XWIN_TENSOR_CORES = ops.XWIN_TENSOR_CORES, bool(self.tc)
+        self.prev, ops.XWIN_TENSOR_CORES = ops.XWIN_TENSOR_CORES, int(self.tc)
 
     def __exit__(self, *a):
         ops.XWIN_TENSOR_CORES = self.prev
@@ -73,9 +73,9 @@ def _oca_ref(qkv, table, heads, ws, ows):
 
 @pytest.mark.parametrize("case", [dict(B=2, H=32, W=48, c=36, heads=3, ws=16, shift=0), dict(B=2, H=32, W=48, c=36, heads=3, ws=16, shift=8),
                                   dict(B=1, H=32, W=32, c=180, heads=6, ws=16, shift=8), dict(B=1, H=16, W=24, c=24, heads=2, ws=8, shift=4)])
-@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("tc", [0, 3])
 def test_xwin_attn_self(case, tc):
-    """tc = 0: exact-fp32 CUDA-core kernels (tight bounds); tc = 1: mma.sync 3xBF16 tensor-core kernels (1e-4 class)."""
+    """tc = 0: exact-fp32 CUDA-core kernels (tight bounds); tc = 3: mma.sync 3xBF16 forward AND backward (1e-4 class)."""
     with _engine(tc):
         _xwin_self(case, 1.0 if tc == 0 else 10.0)
 
@@ -101,7 +101,7 @@ def _xwin_self(case, loosen):
 
 @pytest.mark.parametrize("case", [dict(B=2, H=32, W=48, c=36, heads=3, ws=16, ows=24), dict(B=1, H=32, W=32, c=180, heads=6, ws=16, ows=24),
                                   dict(B=2, H=16, W=16, c=24, heads=2, ws=16, ows=24), dict(B=1, H=16, W=24, c=24, heads=2, ws=8, ows=12)])
-@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("tc", [0, 3])
 def test_xwin_attn_overlapping(case, tc):
     with _engine(tc):
         _xwin_oca(case, 1.0 if tc == 0 else 10.0)
