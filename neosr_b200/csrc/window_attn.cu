@@ -239,6 +239,7 @@ __global__ void window_attn_dbias_kernel(const float* __restrict__ dssum, float*
 bool window_attn_mma_supported(int c, int heads, int ws);
 int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w,
                                int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
+int window_attn_bwd_mma_ctas();
 int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float* dout, float* dqkv, void* dqkv_sti,
                                float* partial, int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
                                float scale, cudaStream_t st);
@@ -252,7 +253,7 @@ static bool use_mma(int c, int heads, int ws) {
 }
 
 static int bwd_gx(int nwin, int heads, bool mma) {
-  int gx = ((mma ? 3 : 2) * kNumSMs) / heads;
+  int gx = ((mma ? window_attn_bwd_mma_ctas() : 2) * kNumSMs) / heads;
   if (gx < 1) gx = 1;
   return gx > nwin ? nwin : gx;
 }
@@ -289,7 +290,7 @@ extern "C" int nsr_window_attn_fwd(const float* qkv, const float* bias_table, fl
 
 extern "C" size_t nsr_window_attn_bwd_workspace(int heads, int ws) {
   (void)ws;
-  return (size_t)(3 * kNumSMs + 2 * (heads > 0 ? heads : 1)) * WA_N * WA_N * sizeof(float);
+  return (size_t)(window_attn_bwd_mma_ctas() * kNumSMs + 2 * (heads > 0 ? heads : 1)) * WA_N * WA_N * sizeof(float);
 }
 
 extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv,

@@ -68,8 +68,9 @@ __device__ __forceinline__ void sti_zero_padding(uint8_t* sti, int kbs, const in
 // ws == 8: token j = 8*jy + jx, so column j = 8*nt + 2*tid + e has jy = nt, jx = 2*tid + e and the
 // relative-position index (iy-jy+7)*15 + (ix-jx+7) = (15*iy + ix + 112 - 2*tid) - 15*nt - e: one
 // integer add per element.  `masked` is false for windows whose 64 tokens share one region id.
+template <bool STATS = false>
 __device__ __forceinline__ void bias_mask_softmax(const float* bias_s, const int* rid, bool masked, int row0, int g,
-                                                  int tid, float (&acc)[8][4]) {
+                                                  int tid, float (&acc)[8][4], float* lse = nullptr) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int i = row0 + g + 8 * h;
@@ -109,6 +110,7 @@ __device__ __forceinline__ void bias_mask_softmax(const float* bias_s, const int
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     const float inv = 1.f / s;
+    if (STATS) lse[h] = m + logf(s);  // P = exp(score - lse): what the backward's transposed pass recomputes
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       acc[nt][2 * h] *= inv;
@@ -123,8 +125,10 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
                                                                  const float* __restrict__ table,
                                                                  float* __restrict__ out, uint8_t* __restrict__ out_sti,
                                                                  AttnGeom gm) {
-  __shared__ __align__(16) __nv_bfloat16 Qh[AM_N * AM_LD], Ql[AM_N * AM_LD], Kh[AM_N * AM_LD], Kl[AM_N * AM_LD];
-  __shared__ __align__(16) __nv_bfloat16 Vth[32 * AM_LDT], Vtl[32 * AM_LDT];
+  __shared__ __align__(16) __nv_bfloat16 tiles[6 * AM_N * AM_LD];  // Q, K, V hi/lo, all [token][d]
+  __nv_bfloat16* Qh = tiles;                  __nv_bfloat16* Ql = Qh + AM_N * AM_LD;
+  __nv_bfloat16* Kh = Ql + AM_N * AM_LD;      __nv_bfloat16* Kl = Kh + AM_N * AM_LD;
+  __nv_bfloat16* Vh = Kl + AM_N * AM_LD;      __nv_bfloat16* Vl = Vh + AM_N * AM_LD;
   __shared__ float bias_s[225];
   __shared__ __align__(8) int tok[AM_N], rid[AM_N];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
@@ -139,65 +143,65 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
     differs = rid[t] != r0;
   }
   for (int i = t; i < (2 * gm.ws - 1) * (2 * gm.ws - 1); i += AM_THREADS) bias_s[i] = table[i * gm.heads + head];
-  // zero the d-padding (columns D..31) once
-  for (int i = t; i < AM_N * AM_LD / 2; i += AM_THREADS) {
-    reinterpret_cast<uint32_t*>(Qh)[i] = 0; reinterpret_cast<uint32_t*>(Ql)[i] = 0;
-    reinterpret_cast<uint32_t*>(Kh)[i] = 0; reinterpret_cast<uint32_t*>(Kl)[i] = 0;
-  }
-  for (int i = t; i < 32 * AM_LDT / 2; i += AM_THREADS) {
-    reinterpret_cast<uint32_t*>(Vth)[i] = 0; reinterpret_cast<uint32_t*>(Vtl)[i] = 0;
+  // zero the d-padding (columns D..31) of the six tiles
+  {
+    const int per_row = (32 - gm.D) / 2;
+    for (int i = t; i < 6 * AM_N * per_row; i += AM_THREADS) {
+      const int cpair = i % per_row, rowt = i / per_row;  // rowt = tile * 64 + row
+      *reinterpret_cast<uint32_t*>(&tiles[rowt * AM_LD + gm.D + 2 * cpair]) = 0;
+    }
   }
   const bool masked = __syncthreads_or(differs) && gm.use_mask && gm.shift > 0;
-  const int hp = gm.D / 2;  // float2 pairs per token
-  constexpr int LB = 4;     // loads are issued LB iterations at a time so 3*LB requests are in flight per thread
-  for (int base = t; base < AM_N * hp; base += AM_THREADS * LB) {
+  // 16 lanes per token row (D / 2 <= 16 float2 pairs, coalesced 4 D-byte rows), 8 rows per pass, 8 passes;
+  // LB passes are issued together so 3 * LB requests are in flight per thread
+  const int pr = t & 15, rbase = t >> 4;
+  const bool act = pr < gm.D / 2;
+  constexpr int LB = 4;
+#pragma unroll
+  for (int u0 = 0; u0 < 8; u0 += LB) {
     float2 q[LB], k[LB], v[LB];
 #pragma unroll
     for (int u = 0; u < LB; ++u) {
-      const int idx = base + u * AM_THREADS;
-      if (idx < AM_N * hp) {
-        const int n = idx / hp, pr = idx - n * hp;
+      const int n = rbase + 8 * (u0 + u);
+      if (act) {
         const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
         q[u] = *reinterpret_cast<const float2*>(p);
         k[u] = *reinterpret_cast<const float2*>(p + gm.C);
         v[u] = *reinterpret_cast<const float2*>(p + 2 * gm.C);
       }
     }
+    if (act) {
 #pragma unroll
-    for (int u = 0; u < LB; ++u) {
-      const int idx = base + u * AM_THREADS;
-      if (idx >= AM_N * hp) break;
-      const int n = idx / hp, pr = idx - n * hp;
-      uint32_t hi, lo;
-      split_pair(q[u].x * gm.scale, q[u].y * gm.scale, hi, lo);
-      *reinterpret_cast<uint32_t*>(&Qh[n * AM_LD + 2 * pr]) = hi;
-      *reinterpret_cast<uint32_t*>(&Ql[n * AM_LD + 2 * pr]) = lo;
-      split_pair(k[u].x, k[u].y, hi, lo);
-      *reinterpret_cast<uint32_t*>(&Kh[n * AM_LD + 2 * pr]) = hi;
-      *reinterpret_cast<uint32_t*>(&Kl[n * AM_LD + 2 * pr]) = lo;
-      split_pair(v[u].x, v[u].y, hi, lo);
-      reinterpret_cast<uint16_t*>(Vth)[(2 * pr) * AM_LDT + n] = (uint16_t)(hi & 0xFFFF);
-      reinterpret_cast<uint16_t*>(Vth)[(2 * pr + 1) * AM_LDT + n] = (uint16_t)(hi >> 16);
-      reinterpret_cast<uint16_t*>(Vtl)[(2 * pr) * AM_LDT + n] = (uint16_t)(lo & 0xFFFF);
-      reinterpret_cast<uint16_t*>(Vtl)[(2 * pr + 1) * AM_LDT + n] = (uint16_t)(lo >> 16);
+      for (int u = 0; u < LB; ++u) {
+        const int o1 = (rbase + 8 * (u0 + u)) * AM_LD + 2 * pr;
+        uint32_t hi, lo;
+        split_pair(q[u].x * gm.scale, q[u].y * gm.scale, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
+        split_pair(k[u].x, k[u].y, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
+        split_pair(v[u].x, v[u].y, hi, lo);
+        *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
+      }
     }
   }
   __syncthreads();
   const int row0 = warp * 16;
   float acc[8][4];
-  qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, acc);
+  qk_scores_ldm(Qh, Ql, Kh, Kl, row0, lane, acc);
   bias_mask_softmax(bias_s, rid, masked, row0, g, tid, acc);
   float o[4][4];
-  acc_times(acc, Vth, Vtl, g, tid, o);
+  acc_times_ldm(acc, Vh, Vl, lane, o);  // V read [token][d] through ldmatrix.trans
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int i = row0 + g + 8 * h;
+    const long long tk = tok[row0 + g + 8 * h];
+    uint8_t* rb = out_sti ? sti_row_base(out_sti, (gm.C + 63) / 64, tk) : nullptr;
+    const int r7 = (int)(tk & 7);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int c = nt * 8 + tid * 2;
       if (c < gm.D) {
-        if (out) *reinterpret_cast<float2*>(out + (size_t)tok[i] * gm.C + head * gm.D + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
-        if (out_sti) sti_store_pair(out_sti, (gm.C + 63) / 64, tok[i], head * gm.D + c, o[nt][2 * h], o[nt][2 * h + 1]);
+        if (out) *reinterpret_cast<float2*>(out + (size_t)tk * gm.C + head * gm.D + c) = make_float2(o[nt][2 * h], o[nt][2 * h + 1]);
+        if (out_sti) sti_store_pair_row(rb, r7, head * gm.D + c, o[nt][2 * h], o[nt][2 * h + 1]);
       }
     }
   }
@@ -205,53 +209,45 @@ __global__ void __launch_bounds__(AM_THREADS) window_attn_fwd_mma(const float* _
 }
 
 // ------------------------------------------------------------------------------------ backward
-// smem map (bf16 elements). Phase-1 tiles [token][d]; phase-2 tiles alias them.
-constexpr int BW_TILE = AM_N * AM_LD;      // 2560
-constexpr int BW_TT = 32 * AM_LDT;         // 2304   [d][token]
-constexpr int BW_PT = AM_N * AM_LDT;       // 4608   [token][token]
-constexpr int BW_PHASE1 = 8 * BW_TILE;     // Q,K,V,dO hi+lo = 20480 elements
-static_assert(4 * BW_PT <= BW_PHASE1, "Pt/dSt (hi+lo) must fit in the phase-1 region");
-constexpr size_t BW_SMEM = (size_t)(BW_PHASE1 + 6 * BW_TT) * sizeof(__nv_bfloat16);
+constexpr int BW_TILE = AM_N * AM_LD;      // 2560 bf16 per [token][d] tile
+constexpr int BW_PHASE1 = 8 * BW_TILE;     // Q, K, V, dO hi + lo
+// One persistent CTA iterates over windows of one head; no transposed operand copies and no P / dS exchange
+// through shared memory.  Row pass (warp = 16 queries i): P, dP, delta_i, dS -> dQ and the bias-gradient accumulators;
+// it leaves lse_i and delta_i in shared memory.  Column pass (warp = 16 keys j): recomputes the TRANSPOSED tiles
+// S^T = K Qs^T and dP^T = V dO^T on the tensor cores (2 x 48 extra MMAs, cheaper than 256 two-byte scatter stores),
+// so P^T and dS^T appear in the accumulator layout = the A operand of dV = P^T dO and dK = dS^T Qs.  The B operands
+// of dQ / dK / dV are K / Qs / dO read [token][d] through ldmatrix.trans.  Shared memory: 8 tiles (40 KB).
+constexpr size_t BW2_SMEM = (size_t)BW_PHASE1 * sizeof(__nv_bfloat16);
 
+// 3 CTAs / SM (168 registers): 4 (128 registers, 330 B of spills) and 5 (96) measured the same and 19% slower.
 __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float* __restrict__ qkv,
-                                                                 const float* __restrict__ table,
-                                                                 const float* __restrict__ dout,
-                                                                 float* __restrict__ dqkv,
-                                                                 uint8_t* __restrict__ dqkv_sti,
-                                                                 float* __restrict__ partial, AttnGeom gm, int nwin) {
+                                                                  const float* __restrict__ table,
+                                                                  const float* __restrict__ dout,
+                                                                  float* __restrict__ dqkv,
+                                                                  uint8_t* __restrict__ dqkv_sti,
+                                                                  float* __restrict__ partial, AttnGeom gm, int nwin) {
   extern __shared__ __align__(16) __nv_bfloat16 sm[];
   __nv_bfloat16* Qh = sm;                 __nv_bfloat16* Ql = Qh + BW_TILE;
   __nv_bfloat16* Kh = Ql + BW_TILE;       __nv_bfloat16* Kl = Kh + BW_TILE;
   __nv_bfloat16* Vh = Kl + BW_TILE;       __nv_bfloat16* Vl = Vh + BW_TILE;
   __nv_bfloat16* Oh = Vl + BW_TILE;       __nv_bfloat16* Ol = Oh + BW_TILE;    // dO
-  __nv_bfloat16* Pth = sm;                __nv_bfloat16* Ptl = Pth + BW_PT;    // alias phase-1 region
-  __nv_bfloat16* Sth = Ptl + BW_PT;       __nv_bfloat16* Stl = Sth + BW_PT;
-  __nv_bfloat16* Qth = sm + BW_PHASE1;    __nv_bfloat16* Qtl = Qth + BW_TT;    // [d][token]
-  __nv_bfloat16* Kth = Qtl + BW_TT;       __nv_bfloat16* Ktl = Kth + BW_TT;
-  __nv_bfloat16* Oth = Ktl + BW_TT;       __nv_bfloat16* Otl = Oth + BW_TT;
   __shared__ float bias_s[225];
   __shared__ __align__(8) int tok[AM_N], rid[AM_N];
+  __shared__ __align__(8) float lse_s[AM_N], delta_s[AM_N];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
   const int head = blockIdx.y;
   const int row0 = warp * 16;
   for (int i = t; i < (2 * gm.ws - 1) * (2 * gm.ws - 1); i += AM_THREADS) bias_s[i] = table[i * gm.heads + head];
-  for (int i = t; i < 6 * BW_TT / 2; i += AM_THREADS) reinterpret_cast<uint32_t*>(Qth)[i] = 0;  // d padding rows
+  for (int i = t; i < BW_PHASE1 / 2; i += AM_THREADS) reinterpret_cast<uint32_t*>(sm)[i] = 0;  // d padding columns stay 0
   float dacc[8][4];  // sum over this CTA's windows of dS, accumulator layout (fixed (i,j) per thread)
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) dacc[nt][0] = dacc[nt][1] = dacc[nt][2] = dacc[nt][3] = 0.f;
-  const int hp = gm.D / 2;
-  // (token, channel pair) of this thread's <= 8 load iterations: fixed for the whole kernel, so the
-  // divisions are paid once; lanes stay on consecutive pairs of one token (coalesced 120-byte rows)
-  int nidx[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int idx = t + u * AM_THREADS;
-    const int n = idx < AM_N * hp ? idx / hp : AM_N;
-    nidx[u] = (n << 8) | (idx - n * hp < 0 ? 0 : (idx - n * hp) & 255);
-  }
+  const int pr = t & 15, rbase = t >> 4;  // loads: 16 lanes per token row, 8 rows per pass (see the forward kernel)
+  const bool act = pr < gm.D / 2;
+  const int kbs3 = (3 * gm.C + 63) / 64;
 
   for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
-    __syncthreads();  // previous window's phase-2 reads are done
+    __syncthreads();  // previous window's column pass is done with the tiles, tok, rid and the row statistics
     int differs = 0;
     if (t < AM_N) {
       attn_token_map(gm, wi, t, tok[t], rid[t]);
@@ -259,143 +255,121 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
       attn_token_map(gm, wi, 0, t0, r0);
       differs = rid[t] != r0;
     }
-    // zero the k-padding (columns D..31) of the eight [token][d] tiles (phase 2 aliased over them)
-    for (int i = t; i < 8 * AM_N * ((32 - gm.D) / 2); i += AM_THREADS) {
-      const int per_row = (32 - gm.D) / 2;
-      const int cpair = i % per_row, rowt = i / per_row;  // rowt = tile * 64 + row
-      *reinterpret_cast<uint32_t*>(&sm[rowt * AM_LD + gm.D + 2 * cpair]) = 0;
-    }
     const bool masked = __syncthreads_or(differs) && gm.use_mask && gm.shift > 0;
-    constexpr int LB = 2;  // 8 independent 8-byte loads in flight per thread
+    constexpr int LB = 4;  // 16 independent 8-byte loads in flight per thread
 #pragma unroll
-    for (int b0 = 0; b0 < 8; b0 += LB) {
+    for (int u0 = 0; u0 < 8; u0 += LB) {
       float2 qv[LB], kv[LB], vv[LB], dv[LB];
 #pragma unroll
       for (int u = 0; u < LB; ++u) {
-        const int n = nidx[b0 + u] >> 8, pr = nidx[b0 + u] & 255;  // consecutive lanes -> consecutive pairs of a token
-        if (n < AM_N) {
-          const float* p = qkv + (size_t)tok[n] * 3 * gm.C + head * gm.D + 2 * pr;
+        if (act) {
+          const long long tk = tok[rbase + 8 * (u0 + u)];
+          const float* p = qkv + (size_t)tk * 3 * gm.C + head * gm.D + 2 * pr;
           qv[u] = *reinterpret_cast<const float2*>(p);
           kv[u] = *reinterpret_cast<const float2*>(p + gm.C);
           vv[u] = *reinterpret_cast<const float2*>(p + 2 * gm.C);
-          dv[u] = *reinterpret_cast<const float2*>(dout + (size_t)tok[n] * gm.C + head * gm.D + 2 * pr);
+          dv[u] = *reinterpret_cast<const float2*>(dout + (size_t)tk * gm.C + head * gm.D + 2 * pr);
         }
       }
+      if (act) {
 #pragma unroll
-      for (int u = 0; u < LB; ++u) {
-        const int n = nidx[b0 + u] >> 8, pr = nidx[b0 + u] & 255;
-        if (n >= AM_N) continue;
-        const float2 q = qv[u], k = kv[u], v = vv[u], dy = dv[u];
-        uint32_t hi, lo;
-        const int o1 = n * AM_LD + 2 * pr, t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
-        split_pair(q.x * gm.scale, q.y * gm.scale, hi, lo);
-        *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
-        reinterpret_cast<uint16_t*>(Qth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Qth)[t1] = (uint16_t)(hi >> 16);
-        reinterpret_cast<uint16_t*>(Qtl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Qtl)[t1] = (uint16_t)(lo >> 16);
-        split_pair(k.x, k.y, hi, lo);
-        *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
-        reinterpret_cast<uint16_t*>(Kth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Kth)[t1] = (uint16_t)(hi >> 16);
-        reinterpret_cast<uint16_t*>(Ktl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ktl)[t1] = (uint16_t)(lo >> 16);
-        split_pair(v.x, v.y, hi, lo);
-        *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
-        split_pair(dy.x, dy.y, hi, lo);
-        *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
-        reinterpret_cast<uint16_t*>(Oth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Oth)[t1] = (uint16_t)(hi >> 16);
-        reinterpret_cast<uint16_t*>(Otl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Otl)[t1] = (uint16_t)(lo >> 16);
+        for (int u = 0; u < LB; ++u) {
+          uint32_t hi, lo;
+          const int o1 = (rbase + 8 * (u0 + u)) * AM_LD + 2 * pr;
+          split_pair(qv[u].x * gm.scale, qv[u].y * gm.scale, hi, lo);
+          *reinterpret_cast<uint32_t*>(&Qh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ql[o1]) = lo;
+          split_pair(kv[u].x, kv[u].y, hi, lo);
+          *reinterpret_cast<uint32_t*>(&Kh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Kl[o1]) = lo;
+          split_pair(vv[u].x, vv[u].y, hi, lo);
+          *reinterpret_cast<uint32_t*>(&Vh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Vl[o1]) = lo;
+          split_pair(dv[u].x, dv[u].y, hi, lo);
+          *reinterpret_cast<uint32_t*>(&Oh[o1]) = hi; *reinterpret_cast<uint32_t*>(&Ol[o1]) = lo;
+        }
       }
     }
     __syncthreads();
-    // ---- phase 1: P = softmax(Qs K^T + bias + mask); dP = dO V^T; dS = P o (dP - rowsum(P o dP))
-    float pr_[8][4], ds[8][4];
-    qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, pr_);
-    bias_mask_softmax(bias_s, rid, masked, row0, g, tid, pr_);
-    qk_scores(Oh, Ol, Vh, Vl, row0, g, tid, ds);  // dP[i][j] = sum_d dO[i][d] V[j][d]
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float delta = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) delta += pr_[nt][2 * h] * ds[nt][2 * h] + pr_[nt][2 * h + 1] * ds[nt][2 * h + 1];
-      delta += __shfl_xor_sync(0xffffffffu, delta, 1);
-      delta += __shfl_xor_sync(0xffffffffu, delta, 2);
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float v = pr_[nt][2 * h + e] * (ds[nt][2 * h + e] - delta);
-          ds[nt][2 * h + e] = v;
-          dacc[nt][2 * h + e] += v;
-        }
-      }
-    }
-    __syncthreads();  // every warp is done reading the phase-1 tiles; they become Pt / dSt
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = row0 + g + 8 * h;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = nt * 8 + tid * 2 + e;
-          const float pv = pr_[nt][2 * h + e], sv = ds[nt][2 * h + e];
-          const __nv_bfloat16 ph = __float2bfloat16_rn(pv), sh = __float2bfloat16_rn(sv);
-          Pth[j * AM_LDT + i] = ph;
-          Ptl[j * AM_LDT + i] = __float2bfloat16_rn(pv - __bfloat162float(ph));
-          Sth[j * AM_LDT + i] = sh;
-          Stl[j * AM_LDT + i] = __float2bfloat16_rn(sv - __bfloat162float(sh));
-        }
-      }
-    }
-    // ---- phase 2a: dQ[i][d] = scale * sum_j dS[i][j] K[j][d]   (A = dS from registers, B = Kt)
-    float o[4][4];
-    acc_times(ds, Kth, Ktl, g, tid, o);
-    const int kbs3 = (3 * gm.C + 63) / 64;
     uint8_t* rb[2];
     int r7[2];
     long long tkk[2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2; ++h) {  // rows row0+g, row0+g+8: the queries of the row pass and the keys of the column pass
       tkk[h] = tok[row0 + g + 8 * h];
       rb[h] = dqkv_sti ? sti_row_base(dqkv_sti, kbs3, tkk[h]) : nullptr;
       r7[h] = (int)(tkk[h] & 7);
     }
+    float pr_[8][4], ds[8][4], o[4][4];
+    // ---- row pass: P = softmax(Qs K^T + bias + mask); dP = dO V^T; dS = P o (dP - rowsum(P o dP)); dQ = scale dS K
+    {
+      float lse[2];
+      qk_scores_ldm(Qh, Ql, Kh, Kl, row0, lane, pr_);
+      bias_mask_softmax<true>(bias_s, rid, masked, row0, g, tid, pr_, lse);
+      qk_scores_ldm(Oh, Ol, Vh, Vl, row0, lane, ds);  // dP[i][j] = sum_d dO[i][d] V[j][d]
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 2; ++h) {
+        float delta = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int c = nt * 8 + tid * 2;
-        if (c < gm.D) {
-          const float v0 = o[nt][2 * h] * gm.scale, v1 = o[nt][2 * h + 1] * gm.scale;
-          if (dqkv) *reinterpret_cast<float2*>(dqkv + tkk[h] * 3 * gm.C + head * gm.D + c) = make_float2(v0, v1);
-          if (dqkv_sti) sti_store_pair_row(rb[h], r7[h], head * gm.D + c, v0, v1);
+        for (int nt = 0; nt < 8; ++nt) delta += pr_[nt][2 * h] * ds[nt][2 * h] + pr_[nt][2 * h + 1] * ds[nt][2 * h + 1];
+        delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+        if (tid == 0) { lse_s[row0 + g + 8 * h] = lse[h]; delta_s[row0 + g + 8 * h] = delta; }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float v = pr_[nt][2 * h + e] * (ds[nt][2 * h + e] - delta);
+            ds[nt][2 * h + e] = v;
+            dacc[nt][2 * h + e] += v;
+          }
+        }
+      }
+      acc_times_ldm(ds, Kh, Kl, lane, o);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int c = nt * 8 + tid * 2;
+          if (c < gm.D) {
+            const float v0 = o[nt][2 * h] * gm.scale, v1 = o[nt][2 * h + 1] * gm.scale;
+            if (dqkv) *reinterpret_cast<float2*>(dqkv + tkk[h] * 3 * gm.C + head * gm.D + c) = make_float2(v0, v1);
+            if (dqkv_sti) sti_store_pair_row(rb[h], r7[h], head * gm.D + c, v0, v1);
+          }
         }
       }
     }
-    __syncthreads();  // Pt / dSt complete
-    // ---- phase 2b: dK[j][d] = sum_i dS[i][j] Qs[i][d];  dV[j][d] = sum_i P[i][j] dO[i][d]   (rows j = this warp's 16)
+    __syncthreads();  // lse / delta of all 64 queries are visible
+    // ---- column pass (rows = keys j, columns = queries i = 8 nt + 2 tid + e): P^T, dP^T, dS^T -> dK, dV
+    qk_scores_ldm(Kh, Kl, Qh, Ql, row0, lane, pr_);   // S^T[j][i] = sum_d K[j][d] Qs[i][d]
+    qk_scores_ldm(Vh, Vl, Oh, Ol, row0, lane, ds);    // dP^T[j][i] = sum_d V[j][d] dO[i][d]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = row0 + g + 8 * h;
+      // relative-position index of (i, j): (iy - jy + 7) * 15 + (ix - jx + 7) with iy = nt, ix = 2 tid + e
+      const int base = 15 * (7 - (j >> 3)) + 7 - (j & 7) + 2 * tid;
+      const int rj = rid[j];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 ls = *reinterpret_cast<const float2*>(&lse_s[nt * 8 + tid * 2]);
+        const float2 dl = *reinterpret_cast<const float2*>(&delta_s[nt * 8 + tid * 2]);
+        float s0 = pr_[nt][2 * h] + bias_s[base + 15 * nt], s1 = pr_[nt][2 * h + 1] + bias_s[base + 15 * nt + 1];
+        if (masked) {
+          const int2 ri = *reinterpret_cast<const int2*>(&rid[nt * 8 + tid * 2]);
+          if (ri.x != rj) s0 += -100.0f;
+          if (ri.y != rj) s1 += -100.0f;
+        }
+        const float p0 = __expf(s0 - ls.x), p1 = __expf(s1 - ls.y);
+        pr_[nt][2 * h] = p0;
+        pr_[nt][2 * h + 1] = p1;
+        ds[nt][2 * h] = p0 * (ds[nt][2 * h] - dl.x);
+        ds[nt][2 * h + 1] = p1 * (ds[nt][2 * h + 1] - dl.y);
+      }
+    }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      const __nv_bfloat16* Ah = which == 0 ? Sth : Pth;
-      const __nv_bfloat16* Al = which == 0 ? Stl : Ptl;
-      const __nv_bfloat16* Bh = which == 0 ? Qth : Oth;
-      const __nv_bfloat16* Bl = which == 0 ? Qtl : Otl;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t ah[4], al[4];
-        load_a(Ah, AM_LDT, row0, kk * 16, g, tid, ah);
-        load_a(Al, AM_LDT, row0, kk * 16, g, tid, al);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          uint32_t bh0, bh1, bl0, bl1;
-          load_b(Bh, AM_LDT, nt * 8, kk * 16, g, tid, bh0, bh1);
-          load_b(Bl, AM_LDT, nt * 8, kk * 16, g, tid, bl0, bl1);
-          mma3(o[nt], ah, al, bh0, bh1, bl0, bl1);
-        }
-      }
+      if (which == 0) acc_times_ldm(ds, Qh, Ql, lane, o);   // dK[j][d] = sum_i dS[i][j] Qs[i][d]
+      else acc_times_ldm(pr_, Oh, Ol, lane, o);             // dV[j][d] = sum_i P[i][j] dO[i][d]
+      const int cbase = (which == 0 ? gm.C : 2 * gm.C) + head * gm.D;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int cbase = (which == 0 ? gm.C : 2 * gm.C) + head * gm.D;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int c = nt * 8 + tid * 2;
@@ -421,6 +395,7 @@ __global__ void __launch_bounds__(AM_THREADS, 3) window_attn_bwd_mma(const float
 }
 
 // ------------------------------------------------------------------------------------ host
+int window_attn_bwd_mma_ctas() { return 3; }  // persistent CTAs per SM of the backward kernel (grid and workspace follow it)
 bool window_attn_mma_supported(int c, int heads, int ws) {
   const int d = c / heads;
   return ws == 8 && d <= 32 && d % 2 == 0 && (c % 2 == 0);
@@ -439,18 +414,9 @@ int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float
                                float* partial, int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
                                float scale, cudaStream_t st) {
   AttnGeom g{batch, h, w, c, heads, ws, shift, use_mask, c / heads, h / ws, w / ws, scale};
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(window_attn_bwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SMEM);
-    if (e != cudaSuccess) {
-      set_error("window_attn_bwd_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return NSR_E_CUDA;
-    }
-    attr = true;
-  }
   dim3 grid(gx, heads);
-  window_attn_bwd_mma<<<grid, AM_THREADS, BW_SMEM, st>>>(qkv, table, dout, dqkv, reinterpret_cast<uint8_t*>(dqkv_sti), partial,
-                                                         g, batch * g.nwh * g.nww);
+  window_attn_bwd_mma<<<grid, AM_THREADS, BW2_SMEM, st>>>(qkv, table, dout, dqkv, reinterpret_cast<uint8_t*>(dqkv_sti), partial,
+                                                          g, batch * g.nwh * g.nww);
   NSR_CHECK_LAUNCH("window_attn_bwd_mma");
   return NSR_OK;
 }

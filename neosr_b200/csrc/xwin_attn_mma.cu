@@ -20,26 +20,25 @@ constexpr int XM_MAXTAB = 39 * 39;
 constexpr float XM_FIX = 1099511627776.0f;  // 2^40: fixed-point scale of the bias-table gradient accumulators
 
 // rows n = 0..63 -> tokens tokv[n] (-1: zero row); D channels at column offset coff of a [tokens, ld] fp32 tensor, times mul;
-// written as bf16 hi/lo [n][AM_LD] tiles and, when Tth != nullptr, transposed [d][AM_LDT] tiles
+// written as bf16 hi/lo [n][AM_LD] tiles.  16 lanes per row (D / 2 <= 16 float2 pairs), 8 rows per pass.
 __device__ __forceinline__ void xm_load_tile(const float* __restrict__ base, size_t ld, int coff, const int* tokv, int D, float mul,
-                                             __nv_bfloat16* Th, __nv_bfloat16* Tl, __nv_bfloat16* Tth, __nv_bfloat16* Ttl, int t) {
-  const int hp = D >> 1;
-  for (int idx = t; idx < XM_T * hp; idx += XM_THREADS) {
-    const int n = idx / hp, pr = idx - n * hp;
-    const int tk = tokv[n];
-    float2 v = make_float2(0.f, 0.f);
-    if (tk >= 0) v = *reinterpret_cast<const float2*>(base + (size_t)tk * ld + coff + 2 * pr);
+                                             __nv_bfloat16* Th, __nv_bfloat16* Tl, int t) {
+  const int pr = t & 15, rbase = t >> 4;
+  if (pr >= (D >> 1)) return;
+  float2 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int tk = tokv[rbase + 8 * u];
+    v[u] = make_float2(0.f, 0.f);
+    if (tk >= 0) v[u] = *reinterpret_cast<const float2*>(base + (size_t)tk * ld + coff + 2 * pr);
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
     uint32_t hi, lo;
-    split_pair(v.x * mul, v.y * mul, hi, lo);
-    if (Th) {
-      *reinterpret_cast<uint32_t*>(&Th[n * AM_LD + 2 * pr]) = hi;
-      *reinterpret_cast<uint32_t*>(&Tl[n * AM_LD + 2 * pr]) = lo;
-    }
-    if (Tth) {
-      const int t0 = (2 * pr) * AM_LDT + n, t1 = t0 + AM_LDT;
-      reinterpret_cast<uint16_t*>(Tth)[t0] = (uint16_t)(hi & 0xFFFF); reinterpret_cast<uint16_t*>(Tth)[t1] = (uint16_t)(hi >> 16);
-      reinterpret_cast<uint16_t*>(Ttl)[t0] = (uint16_t)(lo & 0xFFFF); reinterpret_cast<uint16_t*>(Ttl)[t1] = (uint16_t)(lo >> 16);
-    }
+    split_pair(v[u].x * mul, v[u].y * mul, hi, lo);
+    const int o1 = (rbase + 8 * u) * AM_LD + 2 * pr;
+    *reinterpret_cast<uint32_t*>(&Th[o1]) = hi;
+    *reinterpret_cast<uint32_t*>(&Tl[o1]) = lo;
   }
 }
 __device__ __forceinline__ void xm_zero(__nv_bfloat16* p, int n, int t) {
@@ -68,7 +67,7 @@ __device__ __forceinline__ void xm_key_meta(const GAGeom& g, int wi, int k0, XmM
 __global__ void __launch_bounds__(XM_THREADS) xwin_fwd_mma(const float* __restrict__ qkv, const float* __restrict__ table,
                                                            float* __restrict__ out, float* __restrict__ lse, GAGeom gm) {
   __shared__ __align__(16) __nv_bfloat16 Qh[XM_T * AM_LD], Ql[XM_T * AM_LD], Kh[XM_T * AM_LD], Kl[XM_T * AM_LD];
-  __shared__ __align__(16) __nv_bfloat16 Vth[32 * AM_LDT], Vtl[32 * AM_LDT];
+  __shared__ __align__(16) __nv_bfloat16 Vh[XM_T * AM_LD], Vl[XM_T * AM_LD];
   __shared__ float tab[XM_MAXTAB];
   __shared__ XmMeta qm, km;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tid = lane & 3;
@@ -76,10 +75,10 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_fwd_mma(const float* __restri
   const int row0 = warp * 16;
   for (int e = t; e < gm.ntab; e += XM_THREADS) tab[e] = table[(size_t)e * gm.heads + head];
   xm_zero(Qh, XM_T * AM_LD, t); xm_zero(Ql, XM_T * AM_LD, t); xm_zero(Kh, XM_T * AM_LD, t); xm_zero(Kl, XM_T * AM_LD, t);
-  xm_zero(Vth, 32 * AM_LDT, t); xm_zero(Vtl, 32 * AM_LDT, t);
+  xm_zero(Vh, XM_T * AM_LD, t); xm_zero(Vl, XM_T * AM_LD, t);
   xm_query_meta(gm, wi, q0, qm, t);
   __syncthreads();
-  xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm.tok, gm.D, gm.scale, Qh, Ql, nullptr, nullptr, t);
+  xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm.tok, gm.D, gm.scale, Qh, Ql, t);
   float o[4][4], mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
@@ -88,13 +87,13 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_fwd_mma(const float* __restri
     __syncthreads();  // previous chunk consumed (first pass: Q tile / metadata written)
     xm_key_meta(gm, wi, k0, km, t);
     __syncthreads();
-    xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km.tok, gm.D, 1.f, Kh, Kl, nullptr, nullptr, t);
-    xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km.tok, gm.D, 1.f, nullptr, nullptr, Vth, Vtl, t);
+    xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km.tok, gm.D, 1.f, Kh, Kl, t);
+    xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km.tok, gm.D, 1.f, Vh, Vl, t);
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) { qy[h] = qm.y[row0 + g + 8 * h]; qx[h] = qm.x[row0 + g + 8 * h]; qr[h] = qm.rid[row0 + g + 8 * h]; }
     float s[8][4];
-    qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, s);
+    qk_scores_ldm(Qh, Ql, Kh, Kl, row0, lane, s);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float cm = -INFINITY;
@@ -130,7 +129,7 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_fwd_mma(const float* __restri
       for (int nt = 0; nt < 4; ++nt) { o[nt][2 * h] *= corr; o[nt][2 * h + 1] *= corr; }
     }
     float oc[4][4];
-    acc_times(s, Vth, Vtl, g, tid, oc);
+    acc_times_ldm(s, Vh, Vl, lane, oc);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -154,8 +153,8 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_fwd_mma(const float* __restri
 }
 
 // ------------------------------------------------------------------ backward: dQ
-// dynamic smem: Qh Ql Oh Ol Kh Kl Vh Vl [64][AM_LD] | Kth Ktl [32][AM_LDT] | tab | metas | delta
-constexpr size_t XQ_SMEM = (size_t)(8 * XM_T * AM_LD + 2 * 32 * AM_LDT) * sizeof(__nv_bfloat16) + XM_MAXTAB * sizeof(float) +
+// dynamic smem: Qh Ql Oh Ol Kh Kl Vh Vl [64][AM_LD] | tab | metas | delta
+constexpr size_t XQ_SMEM = (size_t)(8 * XM_T * AM_LD) * sizeof(__nv_bfloat16) + XM_MAXTAB * sizeof(float) +
                            2 * sizeof(XmMeta) + 2 * XM_T * sizeof(float);
 __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_q_mma(const float* __restrict__ qkv, const float* __restrict__ table,
                                                              const float* __restrict__ out, const float* __restrict__ dout,
@@ -164,9 +163,8 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_q_mma(const float* __rest
   extern __shared__ __align__(16) uint8_t xsm[];
   __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(xsm);
   __nv_bfloat16 *Ql = Qh + XM_T * AM_LD, *Oh = Ql + XM_T * AM_LD, *Ol = Oh + XM_T * AM_LD, *Kh = Ol + XM_T * AM_LD;
-  __nv_bfloat16 *Kl = Kh + XM_T * AM_LD, *Vh = Kl + XM_T * AM_LD, *Vl = Vh + XM_T * AM_LD, *Kth = Vl + XM_T * AM_LD;
-  __nv_bfloat16* Ktl = Kth + 32 * AM_LDT;
-  float* tab = reinterpret_cast<float*>(Ktl + 32 * AM_LDT);
+  __nv_bfloat16 *Kl = Kh + XM_T * AM_LD, *Vh = Kl + XM_T * AM_LD, *Vl = Vh + XM_T * AM_LD;
+  float* tab = reinterpret_cast<float*>(Vl + XM_T * AM_LD);
   XmMeta* qm = reinterpret_cast<XmMeta*>(tab + XM_MAXTAB);
   XmMeta* km = qm + 1;
   float* lse_s = reinterpret_cast<float*>(km + 1);
@@ -175,7 +173,7 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_q_mma(const float* __rest
   const int wi = blockIdx.x / gm.heads, head = blockIdx.x - wi * gm.heads, q0 = blockIdx.y * XM_T;
   const int row0 = warp * 16;
   for (int e = t; e < gm.ntab; e += XM_THREADS) tab[e] = table[(size_t)e * gm.heads + head];
-  xm_zero(Qh, 8 * XM_T * AM_LD + 2 * 32 * AM_LDT, t);
+  xm_zero(Qh, 8 * XM_T * AM_LD, t);
   xm_query_meta(gm, wi, q0, *qm, t);
   __syncthreads();
   if (t < XM_T) {
@@ -192,8 +190,8 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_q_mma(const float* __rest
     lse_s[t] = L;
     del_s[t] = dl;
   }
-  xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm->tok, gm.D, gm.scale, Qh, Ql, nullptr, nullptr, t);
-  xm_load_tile(dout, (size_t)gm.C, head * gm.D, qm->tok, gm.D, 1.f, Oh, Ol, nullptr, nullptr, t);
+  xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm->tok, gm.D, gm.scale, Qh, Ql, t);
+  xm_load_tile(dout, (size_t)gm.C, head * gm.D, qm->tok, gm.D, 1.f, Oh, Ol, t);
   float dq[4][4];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
@@ -201,12 +199,12 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_q_mma(const float* __rest
     __syncthreads();
     xm_key_meta(gm, wi, k0, *km, t);
     __syncthreads();
-    xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km->tok, gm.D, 1.f, Kh, Kl, Kth, Ktl, t);
-    xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km->tok, gm.D, 1.f, Vh, Vl, nullptr, nullptr, t);
+    xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km->tok, gm.D, 1.f, Kh, Kl, t);
+    xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km->tok, gm.D, 1.f, Vh, Vl, t);
     __syncthreads();
     float s[8][4], dp[8][4];
-    qk_scores(Qh, Ql, Kh, Kl, row0, g, tid, s);
-    qk_scores(Oh, Ol, Vh, Vl, row0, g, tid, dp);
+    qk_scores_ldm(Qh, Ql, Kh, Kl, row0, lane, s);
+    qk_scores_ldm(Oh, Ol, Vh, Vl, row0, lane, dp);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int i = row0 + g + 8 * h;
@@ -228,7 +226,7 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_q_mma(const float* __rest
         }
     }
     float oc[4][4];
-    acc_times(s, Kth, Ktl, g, tid, oc);
+    acc_times_ldm(s, Kh, Kl, lane, oc);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -248,8 +246,8 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_q_mma(const float* __rest
 }
 
 // ------------------------------------------------------------------ backward: dK, dV, bias-table gradient
-// dynamic smem: Kh Kl Vh Vl Qh Ql Oh Ol [64][AM_LD] | Qth Qtl Oth Otl [32][AM_LDT] | dtab64 | tab | metas | lse, delta
-constexpr size_t XK_SMEM = (size_t)(8 * XM_T * AM_LD + 4 * 32 * AM_LDT) * sizeof(__nv_bfloat16) + XM_MAXTAB * (sizeof(float) + 8) +
+// dynamic smem: Kh Kl Vh Vl Qh Ql Oh Ol [64][AM_LD] | dtab64 | tab | metas | lse, delta
+constexpr size_t XK_SMEM = (size_t)(8 * XM_T * AM_LD) * sizeof(__nv_bfloat16) + XM_MAXTAB * (sizeof(float) + 8) +
                            2 * sizeof(XmMeta) + 2 * XM_T * sizeof(float) + 16;
 __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_kv_mma(const float* __restrict__ qkv, const float* __restrict__ table,
                                                               const float* __restrict__ dout, const float* __restrict__ lse,
@@ -257,11 +255,10 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_kv_mma(const float* __res
                                                               float* __restrict__ dkv_win, float* __restrict__ dtab_part, GAGeom gm) {
   extern __shared__ __align__(16) uint8_t xsm[];
   unsigned long long* dtab64 = reinterpret_cast<unsigned long long*>(xsm);
-  __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(dtab64 + XM_MAXTAB);
+  __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(dtab64 + ((XM_MAXTAB + 1) & ~1));  // 16-byte aligned (ldmatrix rows)
   __nv_bfloat16 *Kl = Kh + XM_T * AM_LD, *Vh = Kl + XM_T * AM_LD, *Vl = Vh + XM_T * AM_LD, *Qh = Vl + XM_T * AM_LD;
-  __nv_bfloat16 *Ql = Qh + XM_T * AM_LD, *Oh = Ql + XM_T * AM_LD, *Ol = Oh + XM_T * AM_LD, *Qth = Ol + XM_T * AM_LD;
-  __nv_bfloat16 *Qtl = Qth + 32 * AM_LDT, *Oth = Qtl + 32 * AM_LDT, *Otl = Oth + 32 * AM_LDT;
-  float* tab = reinterpret_cast<float*>(Otl + 32 * AM_LDT);
+  __nv_bfloat16 *Ql = Qh + XM_T * AM_LD, *Oh = Ql + XM_T * AM_LD, *Ol = Oh + XM_T * AM_LD;
+  float* tab = reinterpret_cast<float*>(Ol + XM_T * AM_LD);
   XmMeta* km = reinterpret_cast<XmMeta*>(tab + XM_MAXTAB);
   XmMeta* qm = km + 1;
   float* lse_s = reinterpret_cast<float*>(qm + 1);
@@ -270,11 +267,11 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_kv_mma(const float* __res
   const int wi = blockIdx.x / gm.heads, head = blockIdx.x - wi * gm.heads, k0 = blockIdx.y * XM_T;
   const int row0 = warp * 16;
   for (int e = t; e < gm.ntab; e += XM_THREADS) { tab[e] = table[(size_t)e * gm.heads + head]; dtab64[e] = 0ull; }
-  xm_zero(Kh, 8 * XM_T * AM_LD + 4 * 32 * AM_LDT, t);
+  xm_zero(Kh, 8 * XM_T * AM_LD, t);
   xm_key_meta(gm, wi, k0, *km, t);
   __syncthreads();
-  xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km->tok, gm.D, 1.f, Kh, Kl, nullptr, nullptr, t);
-  xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km->tok, gm.D, 1.f, Vh, Vl, nullptr, nullptr, t);
+  xm_load_tile(qkv, (size_t)3 * gm.C, gm.C + head * gm.D, km->tok, gm.D, 1.f, Kh, Kl, t);
+  xm_load_tile(qkv, (size_t)3 * gm.C, 2 * gm.C + head * gm.D, km->tok, gm.D, 1.f, Vh, Vl, t);
   float dk[4][4], dv[4][4];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt)
@@ -290,12 +287,12 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_kv_mma(const float* __res
       del_s[t] = ok ? delta[si] : 0.f;
     }
     __syncthreads();
-    xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm->tok, gm.D, gm.scale, Qh, Ql, Qth, Qtl, t);
-    xm_load_tile(dout, (size_t)gm.C, head * gm.D, qm->tok, gm.D, 1.f, Oh, Ol, Oth, Otl, t);
+    xm_load_tile(qkv, (size_t)3 * gm.C, head * gm.D, qm->tok, gm.D, gm.scale, Qh, Ql, t);
+    xm_load_tile(dout, (size_t)gm.C, head * gm.D, qm->tok, gm.D, 1.f, Oh, Ol, t);
     __syncthreads();
     float st[8][4], dpt[8][4];
-    qk_scores(Kh, Kl, Qh, Ql, row0, g, tid, st);    // S^T[j][i]  = K_j . Qs_i
-    qk_scores(Vh, Vl, Oh, Ol, row0, g, tid, dpt);   // dP^T[j][i] = V_j . dO_i
+    qk_scores_ldm(Kh, Kl, Qh, Ql, row0, lane, st);    // S^T[j][i]  = K_j . Qs_i
+    qk_scores_ldm(Vh, Vl, Oh, Ol, row0, lane, dpt);   // dP^T[j][i] = V_j . dO_i
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = row0 + g + 8 * h;
@@ -319,12 +316,12 @@ __global__ void __launch_bounds__(XM_THREADS) xwin_bwd_kv_mma(const float* __res
         }
     }
     float oc[4][4];
-    acc_times(st, Qth, Qtl, g, tid, oc);
+    acc_times_ldm(st, Qh, Ql, lane, oc);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) dk[nt][e] += oc[nt][e];
-    acc_times(dpt, Oth, Otl, g, tid, oc);
+    acc_times_ldm(dpt, Oh, Ol, lane, oc);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
