@@ -490,8 +490,8 @@ int nsr_reflect_fold(const float* dpad, const float* d_direct, const float* x, f
  * query) for the backward pass (nsr_xwin_attn_stat_floats floats).  head dim <= 32, (ws+ows-1) <= 39. */
 size_t nsr_xwin_attn_stat_floats(int batch, int h, int w, int heads, int ws);
 /* Engine of the nsr_xwin_attn_* calls, a bit mask: bit 0 = forward, bit 1 = backward on the mma.sync tensor-core kernels
- * (bf16 hi/lo split, 3 passes, fp32 accumulate; even head dim <= 32), cleared = exact-fp32 CUDA-core kernels.  Default 1
- * (forward only: the faster choice per direction as measured on B200).  Process-wide switch; returns the previous mask. */
+ * (bf16 hi/lo split, 3 passes, fp32 accumulate; even head dim <= 32), cleared = exact-fp32 CUDA-core kernels.  Default 3
+ * (both directions; measured faster on B200).  Process-wide switch; returns the previous mask. */
 int nsr_xwin_attn_use_tensor_cores(int on);
 int nsr_xwin_attn_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int batch, int h, int w, int c,
                       int heads, int ws, int ows, int shift, int use_mask, float scale, void* stream);

@@ -273,7 +273,7 @@ int xwin_fwd_mma_launch(const float* qkv, const float* table, float* out, float*
 int xwin_bwd_mma_launch(const float* qkv, const float* table, const float* out, const float* dout, const float* lse, float* delta,
                         float* dqkv, float* dkv_win, float* part, const GAGeom& g, cudaStream_t st);
 constexpr int GA_KTILE_MMA = 64;  // keys per CTA of the tensor-core dK/dV kernel (more, smaller partial tables)
-static int g_xwin_tc = 1;  // bit 0: forward, bit 1: backward on the mma.sync 3xBF16 kernels; 0: exact-fp32 CUDA-core kernels
+static int g_xwin_tc = 3;  // bit 0: forward, bit 1: backward on the mma.sync 3xBF16 kernels; 0: exact-fp32 CUDA-core kernels
                            // (default 1: measured on B200 at C4 the tensor-core forward wins 9.8 vs 11.3 ms, the backward does not yet:
                            // 38.4 vs 36.0 ms - its tile loads and the fixed-point table atomics dominate, not the MMAs)
 

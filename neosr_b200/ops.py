@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import ACT, ENGINE, NsrConv, NsrWgrad, check
 
 
-XWIN_TENSOR_CORES = int(os.environ.get("NSR_XWIN_TC", "1"))  # HAT window attention engine mask: bit 0 forward, bit 1 backward on mma.sync; 0 = exact fp32
+XWIN_TENSOR_CORES = int(os.environ.get("NSR_XWIN_TC", "3"))  # HAT window attention engine mask: bit 0 forward, bit 1 backward on mma.sync; 0 = exact fp32
 BIAS_COLUMN_ENABLED = True  # bias gradients from the ones channel of split tile images (tests flip it)
 LK16_ENABLED = True   # route 16->16-channel k>=7 convs to the dedicated large-kernel kernels (tests flip it)
 DEFAULT_ENGINE = "auto"  # what engine="auto" resolves to ("auto" | "simt" | "tcgen05"); tests flip it
