@@ -17,7 +17,9 @@ __device__ __forceinline__ size_t sti_offset(long long p, int col, int kbs) {
 }
 
 // The per-row work of one chunk, specialised at compile time on (activation, activation-gradient) so the
-// 8x-unrolled loop carries no per-element switch.  Lane = (row-in-group er, 4 columns starting at ec).
+// 8x-unrolled loop carries no per-element switch.  Lane = (row-in-group er, 4 columns starting at ec); group i is row
+// p0 + 4 i + er.  p0 is a multiple of 32 (tiles start at multiples of 128 rows, warps at multiples of 32), so the 32
+// rows share one 128-row block of a split tile image and every address is a base + compile-time multiple of a stride.
 template <int ACT, int AG>
 __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, long long p0, int n, bool ncol, bool nsti,
                                          long long M, int hw, int er, int ec, int kbs_out) {
@@ -26,55 +28,73 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
   if (ncol && d.bias) b4 = __ldg(reinterpret_cast<const float4*>(d.bias + n));
   if (ncol && (ACT == NSR_ACT_PRELU)) s4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
   if (ncol && (AG == NSR_ACT_PRELU)) g4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
+  const long long pb = p0 + er, left = M - pb;
+  const int nval = left <= 0 ? 0 : (left > 28 ? 8 : (int)((left + 3) >> 2));  // groups i < nval have a row < M
+  const long long yo = pb * d.y_ld + n;
+  float* const yp = d.y ? d.y + yo : nullptr;
+  float* const prep = d.y_pre ? d.y_pre + yo : nullptr;
+  const int res_ld = d.res_ld ? d.res_ld : d.y_ld, aux_ld = d.aux_ld ? d.aux_ld : d.y_ld;
+  const float* const resp = d.residual ? d.residual + pb * res_ld + n : nullptr;
+  const float* const auxp = (AG != NSR_ACT_NONE) ? d.aux + pb * aux_ld + n : nullptr;
+  const int ystep = 4 * d.y_ld, rstep = 4 * res_ld, astep = 4 * aux_ld;
+  // split tile image: 16-byte chunk index is swizzled with (row & 7) = er + 4 (i & 1)
+  uint8_t* sp = nullptr;
+  int sw0 = 0, sw1 = 0;
+  if (nsti) {
+    const int cc = n & 63;
+    sp = reinterpret_cast<uint8_t*>(d.y_sti) + ((size_t)((pb >> 7) * kbs_out + (n >> 6)) << 15) + (size_t)(pb & 127) * 128 +
+         ((cc >> 2) & 1) * 8;
+    sw0 = ((cc >> 3) ^ er) << 4;
+    sw1 = ((cc >> 3) ^ (er + 4)) << 4;
+  }
+  const float one0 = n == d.cout ? 1.f : 0.f;  // first padding channel of an STI output = 1 (bias-gradient column)
 #pragma unroll
   for (int half = 0; half < 2; ++half) {  // two batches of 4 row-groups: 8 independent 16-byte loads in flight
-  float4 aux4[8], res4[8];
+    float4 aux4[4], res4[4];
 #pragma unroll
-  for (int i = half * 4; i < half * 4 + 4; ++i) {
-    const long long p = p0 + i * 4 + er;
-    const bool ok = ncol && p < M;
-    const long long ores = p * (d.res_ld ? d.res_ld : d.y_ld) + n, oaux = p * (d.aux_ld ? d.aux_ld : d.y_ld) + n;
-    if (AG != NSR_ACT_NONE) aux4[i] = ok ? *reinterpret_cast<const float4*>(d.aux + oaux) : make_float4(0.f, 0.f, 0.f, 0.f);
-    res4[i] = (ok && d.residual) ? *reinterpret_cast<const float4*>(d.residual + ores) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int i = half * 4; i < half * 4 + 4; ++i) {
-    const long long p = p0 + i * 4 + er;
-    if (p >= M) continue;
-    float ov[4] = {n == d.cout ? 1.f : 0.f, 0.f, 0.f, 0.f};  // first padding channel of an STI output = 1 (bias-gradient column)
-    if (ncol) {
-      const long long o = p * d.y_ld + n;
-      const float4 a4 = *reinterpret_cast<const float4*>(stg + (i * 4 + er) * EPI_LD + ec);
-      const float pre[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
-      const float sl[4] = {s4.x, s4.y, s4.z, s4.w};
-      float gr[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) act_value_grad<ACT>(pre[e], sl[e], ov[e], gr[e]);
-      if (d.y_pre) {
-        if (d.pre_mode) *reinterpret_cast<float4*>(d.y_pre + o) = make_float4(gr[0], gr[1], gr[2], gr[3]);
-        else *reinterpret_cast<float4*>(d.y_pre + o) = make_float4(pre[0], pre[1], pre[2], pre[3]);
-      }
-      if (AG != NSR_ACT_NONE) {
-        ov[0] *= act_grad_ct<AG>(aux4[i].x, g4.x); ov[1] *= act_grad_ct<AG>(aux4[i].y, g4.y);
-        ov[2] *= act_grad_ct<AG>(aux4[i].z, g4.z); ov[3] *= act_grad_ct<AG>(aux4[i].w, g4.w);
-      }
-      if (d.row_scale) {
-        const float rs = d.row_scale[p / hw];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) ov[e] *= rs;
-      }
-      if (d.residual) { ov[0] += res4[i].x; ov[1] += res4[i].y; ov[2] += res4[i].z; ov[3] += res4[i].w; }
-      if (d.y) *reinterpret_cast<float4*>(d.y + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    for (int j = 0; j < 4; ++j) {
+      const int i = half * 4 + j;
+      const bool ok = ncol && i < nval;
+      if (AG != NSR_ACT_NONE) aux4[j] = ok ? *reinterpret_cast<const float4*>(auxp + i * astep) : make_float4(0.f, 0.f, 0.f, 0.f);
+      res4[j] = (ok && resp) ? *reinterpret_cast<const float4*>(resp + i * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (nsti) {  // channels in [cout, kbs_out*64) are written as zeros (K padding of the next contraction)
-      uint2 hi, lo;
-      split2(ov[0], ov[1], hi.x, lo.x);
-      split2(ov[2], ov[3], hi.y, lo.y);
-      uint8_t* dst = reinterpret_cast<uint8_t*>(d.y_sti) + sti_offset(p, n, kbs_out);
-      *reinterpret_cast<uint2*>(dst) = hi;
-      *reinterpret_cast<uint2*>(dst + 16384) = lo;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = half * 4 + j;
+      if (i >= nval) continue;
+      float ov[4] = {one0, 0.f, 0.f, 0.f};
+      if (ncol) {
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + (i * 4 + er) * EPI_LD + ec);
+        const float pre[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
+        const float sl[4] = {s4.x, s4.y, s4.z, s4.w};
+        float gr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) act_value_grad<ACT>(pre[e], sl[e], ov[e], gr[e]);
+        if (prep) {
+          if (d.pre_mode) *reinterpret_cast<float4*>(prep + i * ystep) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+          else *reinterpret_cast<float4*>(prep + i * ystep) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+        }
+        if (AG != NSR_ACT_NONE) {
+          ov[0] *= act_grad_ct<AG>(aux4[j].x, g4.x); ov[1] *= act_grad_ct<AG>(aux4[j].y, g4.y);
+          ov[2] *= act_grad_ct<AG>(aux4[j].z, g4.z); ov[3] *= act_grad_ct<AG>(aux4[j].w, g4.w);
+        }
+        if (d.row_scale) {
+          const float rs = d.row_scale[(pb + 4 * i) / hw];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ov[e] *= rs;
+        }
+        if (resp) { ov[0] += res4[j].x; ov[1] += res4[j].y; ov[2] += res4[j].z; ov[3] += res4[j].w; }
+        if (yp) *reinterpret_cast<float4*>(yp + i * ystep) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      }
+      if (nsti) {  // channels in [cout, kbs_out*64) are written as zeros (K padding of the next contraction)
+        uint2 hi, lo;
+        split2(ov[0], ov[1], hi.x, lo.x);
+        split2(ov[2], ov[3], hi.y, lo.y);
+        uint8_t* dst = sp + i * 512 + ((i & 1) ? sw1 : sw0);
+        *reinterpret_cast<uint2*>(dst) = hi;
+        *reinterpret_cast<uint2*>(dst + 16384) = lo;
+      }
     }
-  }
   }
 }
 

@@ -172,7 +172,8 @@ def test_layernorm(rows, c):
 
 
 @pytest.mark.parametrize("B,H,W,C,heads,ws,shift", [(2, 16, 16, 36, 3, 8, 0), (2, 16, 24, 36, 3, 8, 4),
-                                                     (1, 64, 64, 180, 6, 8, 4), (1, 8, 16, 60, 6, 4, 2)])
+                                                     (1, 64, 64, 180, 6, 8, 4), (1, 8, 16, 60, 6, 4, 2),
+                                                     (1, 16, 16, 64, 2, 8, 4), (2, 8, 16, 96, 6, 8, 0)])  # head dim 32 (no padding), 16
 def test_window_attention(B, H, W, C, heads, ws, shift):
     """vs the oracle's roll + window_partition + WindowAttention core + reverse (index-exact)."""
     from neosr_b200 import ops
