@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
         const uint32_t bytes = (uint32_t)rows * 128;
         const size_t mt = (size_t)(tile / g.n_tiles);
         for (int kb = 0; kb < g.nk; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait<64>(&empty[stage], phase ^ 1);
           uint8_t* b_hi = smem + stage * Cfg::stage_bytes + 2 * TC_A_BYTES;
           uint8_t* b_lo = b_hi + Cfg::b_bytes;
           const uint8_t* src_hi = wimg + ((size_t)(kb * 2 + 0) * nblk + (n0 >> 6)) * 8192;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
         const int buf = local & 1;
         const uint32_t bphase = (local >> 1) & 1;
-        mbar_wait(&tempty[buf], bphase ^ 1);
+        mbar_wait<64>(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
         for (int kb = 0; kb < g.nk; ++kb) {

@@ -21,6 +21,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Spin on the phase parity; traps instead of hanging the GPU if a pipeline bug deadlocks.
+// BACKOFF_NS > 0: sleep between polls - for waits off the critical path (a loader waiting for a free stage, the MMA
+// issuer waiting for a drained accumulator), whose spinning would otherwise take issue slots from the epilogue warps
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -34,6 +37,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
+    if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
     if (++spins > (1u << 26)) asm volatile("trap;");
   }
 }

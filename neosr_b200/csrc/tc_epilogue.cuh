@@ -20,7 +20,9 @@ __device__ __forceinline__ size_t sti_offset(long long p, int col, int kbs) {
 // 8x-unrolled loop carries no per-element switch.  Lane = (row-in-group er, 4 columns starting at ec); group i is row
 // p0 + 4 i + er.  p0 is a multiple of 32 (tiles start at multiples of 128 rows, warps at multiples of 32), so the 32
 // rows share one 128-row block of a split tile image and every address is a base + compile-time multiple of a stride.
-template <int ACT, int AG>
+// MODE >= 0 additionally fixes which outputs exist (bit 0: y_pre, 1: y_pre holds the activation gradient, 2: residual,
+// 3: y, 4: split tile image; no row_scale), removing the warp-uniform tests from the unrolled loop; -1 reads them from d.
+template <int ACT, int AG, int MODE = -1>
 __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, long long p0, int n, bool ncol, bool nsti,
                                          long long M, int hw, int er, int ec, int kbs_out) {
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(d.act_slope, d.act_slope, d.act_slope, d.act_slope);
@@ -30,11 +32,17 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
   if (ncol && (AG == NSR_ACT_PRELU)) g4 = __ldg(reinterpret_cast<const float4*>(d.prelu + n));
   const long long pb = p0 + er, left = M - pb;
   const int nval = left <= 0 ? 0 : (left > 28 ? 8 : (int)((left + 3) >> 2));  // groups i < nval have a row < M
+  const bool has_pre = MODE >= 0 ? (MODE & 1) != 0 : d.y_pre != nullptr;
+  const bool pre_grad = MODE >= 0 ? (MODE & 2) != 0 : d.pre_mode != 0;
+  const bool has_res = MODE >= 0 ? (MODE & 4) != 0 : d.residual != nullptr;
+  const bool has_y = MODE >= 0 ? (MODE & 8) != 0 : d.y != nullptr;
+  const bool has_rs = MODE >= 0 ? false : d.row_scale != nullptr;
+  if (MODE >= 0) nsti = nsti && (MODE & 16) != 0;
   const long long yo = pb * d.y_ld + n;
-  float* const yp = d.y ? d.y + yo : nullptr;
-  float* const prep = d.y_pre ? d.y_pre + yo : nullptr;
+  float* const yp = has_y ? d.y + yo : nullptr;
+  float* const prep = has_pre ? d.y_pre + yo : nullptr;
   const int res_ld = d.res_ld ? d.res_ld : d.y_ld, aux_ld = d.aux_ld ? d.aux_ld : d.y_ld;
-  const float* const resp = d.residual ? d.residual + pb * res_ld + n : nullptr;
+  const float* const resp = has_res ? d.residual + pb * res_ld + n : nullptr;
   const float* const auxp = (AG != NSR_ACT_NONE) ? d.aux + pb * aux_ld + n : nullptr;
   const int ystep = 4 * d.y_ld, rstep = 4 * res_ld, astep = 4 * aux_ld;
   // split tile image: 16-byte chunk index is swizzled with (row & 7) = er + 4 (i & 1)
@@ -56,7 +64,7 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
       const int i = half * 4 + j;
       const bool ok = ncol && i < nval;
       if (AG != NSR_ACT_NONE) aux4[j] = ok ? *reinterpret_cast<const float4*>(auxp + i * astep) : make_float4(0.f, 0.f, 0.f, 0.f);
-      res4[j] = (ok && resp) ? *reinterpret_cast<const float4*>(resp + i * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+      res4[j] = (ok && has_res) ? *reinterpret_cast<const float4*>(resp + i * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -70,21 +78,21 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
         float gr[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) act_value_grad<ACT>(pre[e], sl[e], ov[e], gr[e]);
-        if (prep) {
-          if (d.pre_mode) *reinterpret_cast<float4*>(prep + i * ystep) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+        if (has_pre) {
+          if (pre_grad) *reinterpret_cast<float4*>(prep + i * ystep) = make_float4(gr[0], gr[1], gr[2], gr[3]);
           else *reinterpret_cast<float4*>(prep + i * ystep) = make_float4(pre[0], pre[1], pre[2], pre[3]);
         }
         if (AG != NSR_ACT_NONE) {
           ov[0] *= act_grad_ct<AG>(aux4[j].x, g4.x); ov[1] *= act_grad_ct<AG>(aux4[j].y, g4.y);
           ov[2] *= act_grad_ct<AG>(aux4[j].z, g4.z); ov[3] *= act_grad_ct<AG>(aux4[j].w, g4.w);
         }
-        if (d.row_scale) {
+        if (has_rs) {
           const float rs = d.row_scale[(pb + 4 * i) / hw];
 #pragma unroll
           for (int e = 0; e < 4; ++e) ov[e] *= rs;
         }
-        if (resp) { ov[0] += res4[j].x; ov[1] += res4[j].y; ov[2] += res4[j].z; ov[3] += res4[j].w; }
-        if (yp) *reinterpret_cast<float4*>(yp + i * ystep) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        if (has_res) { ov[0] += res4[j].x; ov[1] += res4[j].y; ov[2] += res4[j].z; ov[3] += res4[j].w; }
+        if (has_y) *reinterpret_cast<float4*>(yp + i * ystep) = make_float4(ov[0], ov[1], ov[2], ov[3]);
       }
       if (nsti) {  // channels in [cout, kbs_out*64) are written as zeros (K padding of the next contraction)
         uint2 hi, lo;
@@ -102,7 +110,7 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
 // taddr: TMEM address of (lane quarter, first column of the chunk), p0: first row of this warp,
 // nc0: first output channel of the chunk, kbs_out: 64-channel blocks of the STI output (0 if none)
 __device__ __forceinline__ void epi_chunk(const NsrConv& d, float* stg, uint32_t taddr, long long p0, int nc0,
-                                          long long M, int hw, int lane, int kbs_out) {
+                                          long long M_rows, int hw, int lane, int kbs_out) {
   const int er = lane >> 3, ec = (lane & 7) * 4;
   float v[32];
   tmem_ld_32x32(taddr, v);
@@ -115,8 +123,25 @@ __device__ __forceinline__ void epi_chunk(const NsrConv& d, float* stg, uint32_t
   const bool ncol = n < d.cout;
   const bool nsti = d.y_sti != nullptr && n < kbs_out * 64;
   if (!ncol && !nsti) return;
+  // the output combinations of the SwinIR / VGG hot path get loops without warp-uniform tests
+  const int mode = d.row_scale ? -1
+                               : (d.y_pre ? 1 : 0) | (d.y_pre && d.pre_mode ? 2 : 0) | (d.residual ? 4 : 0) | (d.y ? 8 : 0) |
+                                     (d.y_sti ? 16 : 0);
+#define NSR_EPI_HOT(A, G, M)                                                         \
+  if (d.act == (A) && d.actgrad == (G) && mode == (M)) {                             \
+    epi_rows<A, G, M>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out);       \
+    return;                                                                          \
+  }
+  NSR_EPI_HOT(NSR_ACT_GELU, NSR_ACT_NONE, 19)    // fc1: gelu'(pre) + STI of gelu(pre)
+  NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_MULAUX, 16)  // fc2 dgrad: dy * gelu' -> STI
+  NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_NONE, 12)    // proj / fc2 / RSTB conv: + residual -> fp32
+  NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_NONE, 8)     // qkv, plain dgrads -> fp32
+  NSR_EPI_HOT(NSR_ACT_RELU, NSR_ACT_NONE, 8)     // VGG conv + ReLU
+  NSR_EPI_HOT(NSR_ACT_RELU, NSR_ACT_NONE, 9)     // VGG tapped layers: pre-activation kept
+  NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_RELU, 8)     // VGG dgrad chain
+#undef NSR_EPI_HOT
 #define NSR_EPI_CASE(A, G) \
-  case (A) * 8 + (G): epi_rows<A, G>(d, stg, p0, n, ncol, nsti, M, hw, er, ec, kbs_out); break;
+  case (A) * 8 + (G): epi_rows<A, G>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out); break;
   switch (d.act * 8 + d.actgrad) {  // warp-uniform
     NSR_EPI_CASE(NSR_ACT_NONE, NSR_ACT_NONE)
     NSR_EPI_CASE(NSR_ACT_GELU, NSR_ACT_NONE)
