@@ -130,6 +130,9 @@ int nsr_sti_to_f32(const void* sti, long long rows, int c, float* y, int ld, voi
 size_t nsr_packed_weight_bytes(int cout, int cin, int kh, int kw, int flavour);
 int nsr_pack_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int flavour,
                     void* packed, void* stream);
+/* Both flavours in ONE launch (packed_dgrad may be NULL): what the engine calls per parameter after every optimizer step. */
+int nsr_pack_weight_pair(const float* w_oihw, int cout, int cin, int kh, int kw, void* packed_fprop,
+                         void* packed_dgrad, void* stream);
 
 /*
  * Weight gradient of the same contraction (autograd of nn.Linear / nn.Conv2d weights):

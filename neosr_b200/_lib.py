@@ -80,6 +80,7 @@ SIGNATURES = {
     "nsr_conv_fprop_workspace": (_z, [C.POINTER(NsrConv)]),
     "nsr_packed_weight_bytes": (_z, [_i, _i, _i, _i, _i]),
     "nsr_pack_weight": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "nsr_pack_weight_pair": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "nsr_conv_wgrad_workspace": (_z, [C.POINTER(NsrWgrad)]),
     "nsr_conv_wgrad": (_i, [C.POINTER(NsrWgrad), _p]),
     "nsr_nchw_to_nhwc_affine": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),

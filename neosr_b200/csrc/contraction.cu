@@ -46,28 +46,35 @@ static int forced_engine() {
 
 // ---- weight packing ---------------------------------------------------------------------
 // fp32 region: W[n][tap][c]; flavour 0: n=co, c=ci, tap=(r,s); flavour 1: n=ci, c=co, tap flipped.
-__global__ void pack_weight_f32(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int kh,
-                                int kw, int flavour) {
-  const int taps = kh * kw;
+__device__ __forceinline__ float packed_src(const float* __restrict__ w, int n, int tap, int c, int cin, int taps, int flavour) {
+  const int co = flavour == 0 ? n : c, ci = flavour == 0 ? c : n;
+  const int src_tap = flavour == 0 ? tap : taps - 1 - tap;  // 180-degree rotation
+  return w[((size_t)co * cin + ci) * taps + src_tap];
+}
+__device__ __forceinline__ void pack_f32_range(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int taps,
+                                               int flavour, size_t first, size_t step) {
   const int N = flavour == 0 ? cout : cin, C = flavour == 0 ? cin : cout;
   const size_t total = (size_t)N * taps * C;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t i = first; i < total; i += step) {
     const int c = (int)(i % C);
     const size_t r = i / C;
-    const int tap = (int)(r % taps);
-    const int n = (int)(r / taps);
-    const int co = flavour == 0 ? n : c, ci = flavour == 0 ? c : n;
-    const int src_tap = flavour == 0 ? tap : taps - 1 - tap;  // 180-degree rotation
-    out[i] = w[((size_t)co * cin + ci) * taps + src_tap];
+    out[i] = packed_src(w, (int)(r / taps), (int)(r % taps), c, cin, taps, flavour);
   }
+}
+__global__ void pack_weight_f32(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int kh,
+                                int kw, int flavour) {
+  pack_f32_range(w, out, cout, cin, kh * kw, flavour, blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
 
 // bf16 hi/lo tile images (see common.cuh PackedGeom and igemm_tc.cu): for k-block kb=(tap,cblk),
 // half h, 64-row block j: 8 KiB tile, row r = 128 B, 16-byte chunk ch stored at ch ^ (r & 7).
-__global__ void pack_weight_bf16(const float* __restrict__ wf32, uint8_t* __restrict__ img, PackedGeom g) {
+// SRC_RAW: read the parameter tensor itself (OIHW) instead of the fp32 region (used by the one-launch packer)
+template <bool SRC_RAW>
+__device__ __forceinline__ void pack_bf16_range(const float* __restrict__ src, uint8_t* __restrict__ img, const PackedGeom& g,
+                                                int cin, int flavour, size_t first, size_t step) {
   const int nblk = g.n_pad64 / 64;
   const size_t total = (size_t)g.taps * g.cblks * g.n_pad64 * 8;  // one thread per (kb, n, chunk)
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t i = first; i < total; i += step) {
     const int ch = (int)(i & 7);
     size_t r = i >> 3;
     const int n = (int)(r % g.n_pad64);
@@ -78,7 +85,7 @@ __global__ void pack_weight_bf16(const float* __restrict__ wf32, uint8_t* __rest
     for (int e = 0; e < 8; ++e) {
       const int c = cblk * 64 + ch * 8 + e;
       float v = 0.f;
-      if (n < g.n && c < g.c) v = wf32[((size_t)n * g.taps + tap) * g.c + c];
+      if (n < g.n && c < g.c) v = SRC_RAW ? packed_src(src, n, tap, c, cin, g.taps, flavour) : src[((size_t)n * g.taps + tap) * g.c + c];
       hi[e] = __float2bfloat16_rn(v);
       lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
     }
@@ -88,6 +95,20 @@ __global__ void pack_weight_bf16(const float* __restrict__ wf32, uint8_t* __rest
     const size_t off = (size_t)row * 128 + (size_t)((ch ^ (row & 7)) * 16);
     *reinterpret_cast<uint4*>(img + tile_hi + off) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(img + tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+__global__ void pack_weight_bf16(const float* __restrict__ wf32, uint8_t* __restrict__ img, PackedGeom g) {
+  pack_bf16_range<false>(wf32, img, g, 0, 0, blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+// one launch per parameter: fp32 region + bf16 tile images of the fprop packing and (p1 != nullptr) the dgrad packing
+__global__ void pack_weight_all(const float* __restrict__ w, uint8_t* __restrict__ p0, uint8_t* __restrict__ p1, PackedGeom g0,
+                                PackedGeom g1, int cout, int cin) {
+  const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  pack_f32_range(w, reinterpret_cast<float*>(p0), cout, cin, g0.taps, 0, first, step);
+  pack_bf16_range<true>(w, p0 + g0.f32_bytes, g0, cin, 0, first, step);
+  if (p1) {
+    pack_f32_range(w, reinterpret_cast<float*>(p1), cout, cin, g1.taps, 1, first, step);
+    pack_bf16_range<true>(w, p1 + g1.f32_bytes, g1, cin, 1, first, step);
   }
 }
 
@@ -193,6 +214,24 @@ extern "C" int nsr_pack_weight(const float* w, int cout, int cin, int kh, int kw
   pack_weight_bf16<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(packed),
                                           reinterpret_cast<uint8_t*>(packed) + g.f32_bytes, g);
   NSR_CHECK_LAUNCH("pack_weight_bf16");
+  return NSR_OK;
+}
+
+extern "C" int nsr_pack_weight_pair(const float* w, int cout, int cin, int kh, int kw, void* packed_fprop, void* packed_dgrad,
+                                    void* stream) {
+  NSR_CHECK_ARG(w && packed_fprop && cout > 0 && cin > 0 && kh > 0 && kw > 0, "nsr_pack_weight_pair: bad arguments");
+  NSR_CHECK_ARG((reinterpret_cast<uintptr_t>(packed_fprop) & 255) == 0 && (reinterpret_cast<uintptr_t>(packed_dgrad) & 255) == 0,
+                "nsr_pack_weight_pair: packed buffers must be 256-byte aligned");
+  const PackedGeom g0 = packed_geom(cout, cin, kh, kw, 0), g1 = packed_geom(cout, cin, kh, kw, 1);
+  size_t work = (size_t)g0.taps * g0.cblks * g0.n_pad64 * 8;
+  const size_t w1 = (size_t)g1.taps * g1.cblks * g1.n_pad64 * 8, wf = (size_t)cout * cin * kh * kw;
+  if (packed_dgrad && w1 > work) work = w1;
+  if (wf > work) work = wf;
+  int blocks = ceil_div(work, 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  pack_weight_all<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, reinterpret_cast<uint8_t*>(packed_fprop), reinterpret_cast<uint8_t*>(packed_dgrad), g0, g1, cout, cin);
+  NSR_CHECK_LAUNCH("pack_weight_all");
   return NSR_OK;
 }
 

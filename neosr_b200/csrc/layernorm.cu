@@ -79,14 +79,25 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
   }
 }
 
-__global__ void layernorm_bwd_final(const float* __restrict__ partial, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int blocks, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * C) return;
+// column sums of the [blocks, 2C] partials: one CTA per 32 columns, 32 row groups of coalesced 128-byte loads, then a
+// fixed-order reduction over the groups (deterministic; a single thread per column walking all rows took 30 us)
+__global__ void __launch_bounds__(1024) layernorm_bwd_final(const float* __restrict__ partial, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int blocks, int C) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * 2 * C + c];
-  if (c < C) { if (dgamma) dgamma[c] = s; }
-  else if (dbeta) dbeta[c - C] = s;
+  if (c < 2 * C)
+    for (int b = ty; b < blocks; b += 32) s += partial[(size_t)b * 2 * C + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][tx];
+    if (c < C) { if (dgamma) dgamma[c] = t; }
+    else if (dbeta) dbeta[c - C] = t;
+  }
 }
 
 // ---- v2: 16-byte-chunk-per-lane kernels (C % 4 == 0, C <= 768) with optional split-tile-image output.
@@ -309,7 +320,7 @@ extern "C" int nsr_layernorm_bwd(const float* dy, const float* x, const float* g
     layernorm_bwd_kernel<<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, partial, rows, c);
   }
   NSR_CHECK_LAUNCH("layernorm_bwd");
-  layernorm_bwd_final<<<ceil_div(2 * c, 128), 128, 0, st>>>(partial, dgamma, dbeta, blocks, c);
+  layernorm_bwd_final<<<ceil_div(2 * c, 32), 1024, 0, st>>>(partial, dgamma, dbeta, blocks, c);
   NSR_CHECK_LAUNCH("layernorm_bwd_final");
   return NSR_OK;
 }

@@ -194,12 +194,9 @@ class PackedWeight:
         _chk(w, "weight")
         L = _lib.lib()
         st = _stream()
-        check(L.nsr_pack_weight(w.data_ptr(), self.cout, self.cin, self.kh, self.kw, 0, self.fprop.data_ptr(), st),
-              "nsr_pack_weight")
-        if self.dgrad is not None:
-            check(L.nsr_pack_weight(w.data_ptr(), self.cout, self.cin, self.kh, self.kw, 1, self.dgrad.data_ptr(), st),
-                  "nsr_pack_weight")
-        _count(4 if self.dgrad is not None else 2)
+        check(L.nsr_pack_weight_pair(w.data_ptr(), self.cout, self.cin, self.kh, self.kw, self.fprop.data_ptr(),
+                                     _p(self.dgrad), st), "nsr_pack_weight_pair")
+        _count(1)
         self._version = ver
         return self
 

@@ -61,7 +61,7 @@ def main():
         def run():
             if kind == "fprop":
                 if name == "fc1":
-                    ops.conv_fprop(xs, pw, b, act="gelu", want_pre=True, sti_out=True, f32_out=False)
+                    ops.conv_fprop(xs, pw, b, act="gelu", want_pre=True, pre_is_actgrad=True, sti_out=True, f32_out=False)
                 else:
                     ops.conv_fprop(xs, pw, b, residual=res if name in ("proj", "fc2") else None)
             elif kind == "dgrad":
