@@ -17,6 +17,9 @@ bool conv_wgrad_tc_supported(const NsrWgrad& d);
 size_t conv_wgrad_workspace_tc(const NsrWgrad& d);
 int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st);
 // <= 4-channel image-side convolutions (conv_small.cu)
+// direct 3x3 kernels for <= 4-channel sides at image resolution (conv_direct.cu)
+bool conv_direct_fprop_supported(const NsrConv& d);
+int conv_direct_fprop(const NsrConv& d, cudaStream_t st);
 bool conv_small_fprop_supported(const NsrConv& d);
 int conv_small_fprop(const NsrConv& d, cudaStream_t st);
 // <= 4-channel convs as im2col + tensor-core GEMM (conv_narrow_gemm.cu)
@@ -236,6 +239,15 @@ extern "C" int nsr_pack_weight_pair(const float* w, int cout, int cin, int kh, i
 }
 
 // NSR_NARROW_GEMM=0 keeps the SIMT kernels of conv_small.cu for the <= 4-channel convolutions (A/B runs)
+// NSR_CONV_DIRECT=0 routes the <= 4-channel 3x3 convolutions back through im2col + tcgen05 (A/B runs)
+static bool conv_direct_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("NSR_CONV_DIRECT");
+    on = !(e && e[0] == '0');
+  }
+  return on != 0;
+}
 static bool narrow_gemm_enabled() {
   static int enabled = -1;
   if (enabled < 0) {
@@ -271,6 +283,7 @@ extern "C" int nsr_conv_fprop(const NsrConv* d, void* stream) {
   }
   if (eng == NSR_ENGINE_AUTO && conv_fprop_tc_supported(*d)) return conv_fprop_tc(*d, st);
   NSR_CHECK_ARG(d->x && d->y && !d->y_sti, "nsr_conv_fprop: split-tile-image operands need the tcgen05 engine");
+  if (eng == NSR_ENGINE_AUTO && conv_direct_enabled() && conv_direct_fprop_supported(*d)) return conv_direct_fprop(*d, st);
   if (eng == NSR_ENGINE_AUTO && narrow_gemm_enabled() && conv_narrow_gemm_supported(*d)) return conv_narrow_gemm_fprop(*d, st);
   if (eng == NSR_ENGINE_AUTO && conv_small_fprop_supported(*d)) return conv_small_fprop(*d, st);
   return conv_fprop_simt(*d, st);
