@@ -86,41 +86,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
     const int row0 = t >> 3;          // rows row0 + 32*i, i = 0..3
     int stage = 0;
     uint32_t phase = 0;
-    // load-side cursor
-    int l_tile = blockIdx.x, l_kb = 0;
-    int oh[4], ow[4];
-    long long pix[4];
+    // load-side cursor (tile, filter row, filter column, channel block): k-block kb = (r * kw + s) * cblks + cblk is
+    // walked with counters, and everything that depends only on the tile row - the pixel's base address and which filter
+    // rows / columns land inside the image - is computed once per tile, so a k-block costs one offset, four bit tests and
+    // eight loads per thread (the gather used to spend more instructions on divisions, bounds and 64-bit addresses than on
+    // the fp32 -> hi/lo conversion: profiles/r01_v_ncu_vgg_conv1_2.txt)
+    int l_tile = blockIdx.x, l_kb = 0, l_r = 0, l_s = 0, l_cblk = 0;
+    const float* rowp[4];
+    uint32_t rmask[4], cmask[4];  // bit r / bit s: input row oh + r - pad / column ow + s - pad exists (kh, kw <= 32)
+    const bool small_m = g.M < (1LL << 31);
     auto decode_rows = [&](int tile) {
       const long long m0 = (long long)(tile / g.n_tiles) * TC_BM;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const long long p = m0 + row0 + 32 * i;
+        rmask[i] = cmask[i] = 0u;
+        rowp[i] = d.x;
         if (p < g.M) {
-          const long long b = p / hw;
-          const int rem = (int)(p - b * hw);
-          oh[i] = rem / d.w;
-          ow[i] = rem - oh[i] * d.w;
-          pix[i] = p;
-        } else {
-          oh[i] = -100000;  // every tap lands out of bounds -> zero rows
-          ow[i] = 0;
-          pix[i] = 0;
+          const int rem = small_m ? (int)((unsigned)p % (unsigned)hw) : (int)(p % hw);
+          const int oh = rem / d.w, ow = rem - oh * d.w;
+          for (int r = 0; r < d.kh; ++r) rmask[i] |= (unsigned)(oh + r - d.pad >= 0 && oh + r - d.pad < d.h) << r;
+          for (int sx = 0; sx < d.kw; ++sx) cmask[i] |= (unsigned)(ow + sx - d.pad >= 0 && ow + sx - d.pad < d.w) << sx;
+          rowp[i] = d.x + p * d.x_ld + chunk * 8;
         }
       }
     };
     auto load = [&](float4 (&f)[4][2]) {  // loads (l_tile, l_kb) and advances the cursor
-      if (l_kb == 0) decode_rows(l_tile);
-      const int tap = l_kb / g.cblks, cblk = l_kb - tap * g.cblks;
-      const int r = tap / d.kw, s = tap - r * d.kw;
-      const int dh = r - d.pad, dw = s - d.pad;
-      const int c = cblk * TC_BK + chunk * 8;
+      if (l_kb == 0) {
+        decode_rows(l_tile);
+        l_r = l_s = l_cblk = 0;
+      }
+      const int c = l_cblk * TC_BK + chunk * 8;
+      const bool c0 = c < d.cin, c1 = c + 4 < d.cin;
+      const long long off = ((long long)(l_r - d.pad) * d.w + (l_s - d.pad)) * d.x_ld + l_cblk * TC_BK;  // same for the four rows
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int ih = oh[i] + dh, iw = ow[i] + dw;
-        const bool ok = ih >= 0 && ih < d.h && iw >= 0 && iw < d.w;
-        const float* src = d.x + (pix[i] + (long long)dh * d.w + dw) * d.x_ld + c;
-        f[i][0] = (ok && c < d.cin) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        f[i][1] = (ok && c + 4 < d.cin) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = ((rmask[i] >> l_r) & (cmask[i] >> l_s) & 1u) != 0;
+        const float* src = rowp[i] + off;
+        f[i][0] = (ok && c0) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        f[i][1] = (ok && c1) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (++l_cblk == g.cblks) {
+        l_cblk = 0;
+        if (++l_s == d.kw) { l_s = 0; ++l_r; }
       }
       if (++l_kb == g.nk) { l_kb = 0; l_tile += gridDim.x; }
     };
@@ -273,6 +281,7 @@ bool conv_fprop_tc_supported(const NsrConv& d) {
   if (!ok_dev) return false;
   if (d.cin % 4 || d.x_ld % 4 || d.cout % 4 || d.y_ld % 4 || d.res_ld % 4 || d.aux_ld % 4) return false;
   if (d.cin < 16 || d.cout < 16) return false;  // image-side 3-channel convs stay on the SIMT engine
+  if (d.kh > 32 || d.kw > 32) return false;     // the gather keeps per-row validity masks of the filter rows / columns
   if (d.x_sti != nullptr) {
     if (d.kh != 1 || d.kw != 1) return false;  // tile images carry no halo: 1x1 contractions only
     if (!aligned16(d.x_sti)) return false;

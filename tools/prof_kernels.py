@@ -45,6 +45,15 @@ def main():
                                aux=x if name == "fc2" else None)
             else:
                 ops.conv_wgrad(x, dy, dw, db, k, k)
+    elif what == "vgg_conv1_2":
+        # the largest 3x3 producer-warp contraction of C3: 64 -> 64 channels at 32 x 256 x 256 pixels, ReLU epilogue
+        x = rnd(32, 256, 256, 64, seed=1)
+        w = rnd(64, 64, 3, 3, seed=2, scale=1 / math.sqrt(576))
+        b = rnd(64, seed=3, scale=0.1)
+        pw = ops.PackedWeight(w).refresh()
+
+        def run():
+            ops.conv_fprop(x, pw, b, act="relu")
     elif what.startswith("sti"):
         # STI-operand 1x1 contractions: stifprop_qkv, stidgrad_fc2, stiwgrad_qkv ...
         kind, name = what[3:].split("_", 1)
