@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
       const uint32_t bphase = (local >> 1) & 1;
       const long long p0 = (long long)(tile / g.n_tiles) * TC_BM + q * 32;   // first row of this warp
       const int n0 = (tile % g.n_tiles) * BN;
-      mbar_wait(&tfull[buf], bphase);
+      mbar_wait<STI ? 32 : 128>(&tfull[buf], bphase);  // idle epilogue warps must not spin against the producers
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = slot * 32; c0 < BN; c0 += 32 * NSLOT) {
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_wgrad_tc(NsrWgrad d, WgGe
       decode(item, mt, nt, tap, split);
       const int buf = local & 1;
       const uint32_t bphase = (local >> 1) & 1;
-      mbar_wait(&tfull[buf], bphase);
+      mbar_wait<128>(&tfull[buf], bphase);  // long K loops: sleep instead of spinning
       tc_fence_after();
       float* out = partial + (size_t)split * per_split;
       const int m = mt * 128 + q * 32 + lane;  // P-channel of this thread's accumulator row

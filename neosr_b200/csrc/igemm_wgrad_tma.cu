@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) igemm_wgrad_tma(const __grid_co
       decode(item, mt, nt, r, split);
       const int buf = local & 1;
       const uint32_t bphase = (local >> 1) & 1;
-      mbar_wait(&tfull[buf], bphase);
+      mbar_wait<128>(&tfull[buf], bphase);
       tc_fence_after();
       float* out = partial + (size_t)split * per_split;
       const int m = mt * 128 + q * 32 + lane;  // P-channel of this thread's accumulator row
