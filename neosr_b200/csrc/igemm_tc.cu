@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
     for (int it = 0; it < total; ++it) {
       const bool more = it + 1 < total;
       if (more) load(nxt);
-      mbar_wait(&empty[stage], phase ^ 1);
+      mbar_wait<64>(&empty[stage], phase ^ 1);  // MMA-bound layers: eight waiting producer warps sleep, not spin
       uint8_t* a_hi = smem + stage * Cfg::stage_bytes;
       uint8_t* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_wgrad_tc(NsrWgrad d, WgGe
     for (long long it = 0; it < total; ++it) {
       const bool more = it + 1 < total;
       if (more) load(nxt);
-      if (s_grp == 0) mbar_wait(&empty[stage], phase ^ 1);
+      if (s_grp == 0) mbar_wait<64>(&empty[stage], phase ^ 1);
       uint8_t* st_base = smem + stage * Cfg::stage_bytes;
 #pragma unroll
       for (int u = 0; u < G; ++u) {
