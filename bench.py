@@ -213,8 +213,8 @@ def run_reference(args) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "crops/s", "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3 swinir_medium x4 64->256 L1+perceptual adan_sf+EMA (CPU oracle port, "
-                                   "bounded sample)", "batch_per_step": b},
+            "config": {"workload": WORKLOADS["c3"], "batch_per_step": b,
+                       "arm": "CPU oracle port of the same step, bounded sample (see cpu_baseline.sample)"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
