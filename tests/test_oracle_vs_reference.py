@@ -414,3 +414,37 @@ def test_swinir_3conv_nearest_conv_oracle_and_keys_vs_reference():
     ref.load_state_dict(p, strict=False)
     x = torch.rand(2, 3, 16, 24, generator=torch.Generator().manual_seed(0))
     assert _rel(swinir_forward(p, cfg, x), ref(x).detach()) < 1e-5
+
+
+def test_validation_host_helpers_vs_reference():
+    """tensor2img / calculate_psnr of the standalone fallback (neosr_b200/models/_validation.py) against the reference's
+    own (`utils/img_util.py:60-129`, `metrics/calculate.py:16-66`), incl. the clamp, grayscale and crop-border paths."""
+    import importlib
+    import sys
+
+    import numpy as np
+
+    ref_shim.activate(4)
+    from neosr.metrics.calculate import calculate_psnr as ref_psnr
+    from neosr.utils import tensor2img as ref_t2i
+
+    # the fallbacks, not the delegating wrappers: import the module without `neosr` shadowing its own functions
+    V = importlib.import_module("neosr_b200.models._validation")
+    g = torch.Generator().manual_seed(11)
+    a = torch.rand(1, 3, 40, 56, generator=g) * 1.2 - 0.1  # values outside [0, 1] exercise the clamp
+    b = (a + 0.05 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    ia, ib = V.tensor2img(a), V.tensor2img(b)
+    ra, rb = ref_t2i(a), ref_t2i(b)
+    assert ia.dtype == np.uint8 and ia.shape == ra.shape and np.array_equal(ia, ra) and np.array_equal(ib, rb)
+    gray = torch.rand(1, 1, 24, 24, generator=g)
+    assert np.array_equal(V.tensor2img(gray), ref_t2i(gray))
+    # (test_y_channel=True is not compared live: the reference's to_y_channel raises under numpy 2.x, whose dtype objects
+    #  are not members of the {np.float32, np.float16} set it tests - utils/color_util.py:177-186)
+    for kw in (dict(crop_border=4, test_y_channel=False), dict(crop_border=0, test_y_channel=False),
+               dict(crop_border=7, test_y_channel=False)):
+        ours, ref = V.calculate_psnr(ia, ib, **kw), float(ref_psnr(ra, rb, **kw))
+        assert abs(ours - ref) <= 1e-4 * abs(ref), (kw, ours, ref)
+    y = V.calculate_psnr(ia, ib, crop_border=4, test_y_channel=True)
+    assert np.isfinite(y) and y > V.calculate_psnr(ia, ib, crop_border=4) - 10.0
+    assert V.calculate_psnr(ia, ia) == float("inf")
+    assert "neosr_b200.models._validation" in sys.modules
