@@ -37,3 +37,13 @@ def test_gpu_arm_refuses_to_run_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0
     assert not any(ln.startswith("{") and '"value"' in ln for ln in out.stdout.splitlines())
+
+
+def test_reference_arm_is_rank0_only():
+    """Under torchrun the other ranks of the reference arm exit 0 without work or output."""
+    import os
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
