@@ -4,8 +4,8 @@ optimize_parameters) of SwinIR-medium x4, 64->256 RGB crops, L1 + VGG19-perceptu
 adan_sf + EMA, batch 32 per GPU (BASELINE.json configs[2], "C3").
 
     python bench.py --gpus N --steps K --warmup W            # our arm (B200 kernels, C ABI)
-    python bench.py --impl reference --gpus N ...             # reference arm: the oracle's CPU
-                                                              # restatement of the same step
+    python bench.py --impl reference --gpus N ...             # reference arm: the reference's own step
+                                                              # (baseline/_ref) on the host CPU cores
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
@@ -50,7 +50,8 @@ WORKLOADS = {
     "c4": "C4: hat_l x4, `otf` model: on-the-fly degradation of 128x128 HR crops (train_hat_otf.toml [degradations]) -> "
           "32x32 LQ, pool 176, mssim(1.0)+consistency(1.0)+vgg19 perceptual(0.5)+GAN(bce 0.3, unet), adan_sf + EMA",
     "c5": "C5: realplksr x4, `otf` model: on-the-fly degradation of 192x192 HR crops -> 48x48 LQ, pool 128, "
-          "mssim(1.0)+consistency(1.0)+vgg19 perceptual(0.5)+GAN(bce 0.2, unet), AdamW 5e-4 + EMA 0.999",
+          "mssim(1.0)+consistency(1.0)+vgg19 perceptual(0.5)+GAN(bce 0.2, unet), AdamW lr 1e-4 (template: 5e-4; see make_opt) "
+          "+ EMA 0.999, drop_path 0",
 }
 
 
@@ -169,8 +170,86 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------- reference arm
+def _reference_available() -> bool:
+    from oracle import ref_shim
+    return ref_shim.available()
+
+
+def _reference_model(device: str, tf32: bool = False):
+    """The UNMODIFIED reference (baseline/_ref, or /root/reference in the build container): its own `swinir_medium`,
+    `L1Loss`, `vgg_perceptual_loss` (seeded-random VGG19: no pretrained weights offline, as on our arm), `adan_sf` and
+    EMA, driven through its REAL `image.feed_data` / `image.optimize_parameters` (neosr/models/image.py:374-391,
+    427-662) on an `object.__new__(image)` instance (the constructors hard-wire cuda + DDP)."""
+    import torch
+
+    from oracle import ref_shim
+    ref_shim.activate(4)
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    if tf32:  # what `fast_matmul = true` does (train.py:168-173)
+        torch.set_float32_matmul_precision("medium")
+    else:
+        torch.set_float32_matmul_precision("highest")
+    torch.manual_seed(0)
+    net = ref_shim.build_network({"type": "swinir_medium", "drop_path_rate": 0.0})
+    from neosr.losses.basic_loss import L1Loss
+    percep = ref_shim.build_vgg_perceptual(None, loss_weight=0.5, criterion="chc")
+    return ref_shim.make_image_model(net, cri_pix=L1Loss(loss_weight=1.0), cri_perceptual=percep, ema=0.999, scale=4,
+                                     optim_kw=dict(lr=1e-3, betas=(0.98, 0.92, 0.987), weight_decay=0.02,
+                                                   schedule_free=True, warmup_steps=1600), device=device)
+
+
+def reference_cpu_run(batch: int, steps: int, warmup: int, pool: int = 4) -> dict:
+    """The reference's own CPU step on all host threads, bounded sample = `batch` crops per step (crops/s is
+    batch-normalised; BASELINE.md section 4 / SURVEY.md section 8d: B = 4)."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = _reference_model("cpu")
+    data = synth_batches(pool, batch, seed=1024)
+    for i in range(warmup):
+        m.feed_data(data[i % pool])
+        m.optimize_parameters(i + 1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        m.feed_data(data[i % pool])
+        m.optimize_parameters(warmup + i + 1)
+    mean = (time.perf_counter() - t0) / steps
+    return {"value": batch / mean, "unit": "crops/s", "cores": cores, "kind": "reference",
+            "sample": f"{steps} timed + {warmup} warm-up step(s) of the reference's real image.feed_data + "
+                      f"image.optimize_parameters (swinir_medium, L1 + vgg19 perceptual, adan_sf + EMA) at batch {batch} "
+                      f"(crops/s is batch-normalised), torch CPU fp32, {cores} threads", "ms_per_step": mean * 1e3,
+            "steps": steps, "loss": float(m.log_dict.get("l_g_total", float("nan")))}
+
+
+def reference_cuda_run(batch: int, steps: int, warmup: int, tf32: bool, pool: int = 4) -> dict:
+    """Informational: the reference's eager CUDA step on the same B200 (what a user of the reference sees today),
+    fp32 (TF32 off) or with `fast_matmul` (TF32 on).  Device-timed with CUDA events, inputs fed from pinned memory."""
+    import torch
+    m = _reference_model("cuda", tf32=tf32)
+    data = synth_batches(pool, batch, seed=1024)
+    for i in range(warmup):
+        m.feed_data(data[i % pool])
+        m.optimize_parameters(i + 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        m.feed_data(data[i % pool])
+        m.optimize_parameters(warmup + i + 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": batch / (ms * 1e-3), "unit": "crops/s", "ms_per_step": ms, "batch": batch, "steps": steps,
+           "warmup": warmup, "tf32": tf32, "loss": float(m.log_dict.get("l_g_total", float("nan"))),
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_oracle_run(batch: int, steps: int, warmup: int, budget_s: float) -> dict:
-    """Time the oracle's CPU restatement of the same step (bounded sample of the workload)."""
+    """Fallback when no reference tree is reachable: the oracle's CPU restatement of the same step."""
     import torch
 
     from oracle import losses as OL
@@ -204,20 +283,40 @@ def cpu_oracle_run(batch: int, steps: int, warmup: int, budget_s: float) -> dict
             "steps": len(times)}
 
 
+def cpu_baseline_run(batch: int, steps: int, warmup: int, budget_s: float) -> dict:
+    if _reference_available():
+        return reference_cpu_run(batch, steps, warmup)
+    return cpu_oracle_run(1, steps, warmup, budget_s)
+
+
 def run_reference(args) -> None:
+    """`--impl reference`: the reference's own CPU implementation of the step on the box's host cores (rank 0 only),
+    same metric / unit / workload string as our arm; plus, when a GPU is visible, the reference's eager CUDA step
+    at the full batch (fp32 and fast_matmul/TF32) as informational keys."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    b = 1
-    r = cpu_oracle_run(b, max(1, min(args.steps, 6)), min(args.warmup, 1), budget_s=150.0)
+    b = args.batch or 4
+    r = cpu_baseline_run(b, args.steps, args.warmup, budget_s=240.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "crops/s", "n_gpus": args.gpus,
-            "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS["c3"], "batch_per_step": b,
-                       "arm": "CPU oracle port of the same step, bounded sample (see cpu_baseline.sample)"},
+                       "arm": "the reference's own CPU step (neosr image.optimize_parameters), bounded sample (see "
+                              "cpu_baseline.sample)" if r["kind"] == "reference" else
+                              "CPU oracle port of the same step (no reference tree reachable)"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if r["kind"] == "reference" and not args.no_ref_cuda:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+                for key, tf32 in (("ref_cuda_fp32", False), ("ref_cuda_tf32", True)):
+                    line[key] = reference_cuda_run(DEFAULT_BATCH["c3"], min(args.steps, 8), min(args.warmup, 3), tf32)
+        except Exception as e:  # informational leg: never lose the line
+            line["ref_cuda_error"] = f"{type(e).__name__}: {e}"[:300]
     print(json.dumps(line), flush=True)
 
 
@@ -241,10 +340,11 @@ def run_ours(args) -> None:
     opt = make_opt(B, world > 1, rank, world, args.config)
     opt["cuda_graph"] = not args.no_graph
     model = build_model(opt)
+    n_pool = args.pool or (64 if args.config == "c3" else 8)
     if args.config in ("c4", "c5"):
-        pool = synth_otf_batches(args.pool, B, seed=1024 + rank, hr=128 if args.config == "c4" else 192)
+        pool = synth_otf_batches(n_pool, B, seed=1024 + rank, hr=128 if args.config == "c4" else 192)
     else:
-        pool = synth_batches(args.pool, B, seed=1024 + rank)
+        pool = synth_batches(n_pool, B, seed=1024 + rank)
     dev_pool = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in pool]
     torch.cuda.synchronize()
 
@@ -386,7 +486,7 @@ def run_ours(args) -> None:
             pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.config == "c3":
-            r = cpu_oracle_run(1, 2, 1, budget_s=60.0)
+            r = cpu_baseline_run(4, 3, 1, budget_s=60.0)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         bytes_in = sum(v.numel() * 4 for v in pool[0].values())
         line = {"metric": METRICS[args.config], "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
@@ -424,8 +524,9 @@ def main() -> None:
     ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"],
                     help="c3 = BASELINE.json's headline workload (what the driver runs); c2 = the GAN configuration; "
                          "c4 / c5 = the otf configurations (hat_l / realplksr, per-GPU shapes of BASELINE.json configs[3], [4])")
-    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled")
+    ap.add_argument("--pool", type=int, default=0, help="distinct synthetic batches cycled (default: 64 for c3 as SURVEY.md section 8d states, 8 for the others)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="reference arm: skip the informational eager-CUDA legs")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -492,17 +492,16 @@ int nsr_reflect_fold(const float* dpad, const float* d_direct, const float* x, f
  * wrap to the end of the table as Python indexing does).  out: [tokens, c]; lse: log-sum-exp per (window, head,
  * query) for the backward pass (nsr_xwin_attn_stat_floats floats).  head dim <= 32, (ws+ows-1) <= 39. */
 size_t nsr_xwin_attn_stat_floats(int batch, int h, int w, int heads, int ws);
-/* Engine of the nsr_xwin_attn_* calls, a bit mask: bit 0 = forward, bit 1 = backward on the mma.sync tensor-core kernels
- * (bf16 hi/lo split, 3 passes, fp32 accumulate; even head dim <= 32), cleared = exact-fp32 CUDA-core kernels.  Default 3
- * (both directions; measured faster on B200).  Process-wide switch; returns the previous mask. */
-int nsr_xwin_attn_use_tensor_cores(int on);
+/* engine (per call; the library keeps no mutable state): NSR_ENGINE_AUTO = the mma.sync tensor-core kernels (bf16 hi/lo
+ * split, 3 passes, fp32 accumulate) when the shape allows (even head dim <= 32), NSR_ENGINE_SIMT = the exact-fp32
+ * CUDA-core kernels. */
 int nsr_xwin_attn_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int batch, int h, int w, int c,
-                      int heads, int ws, int ows, int shift, int use_mask, float scale, void* stream);
+                      int heads, int ws, int ows, int shift, int use_mask, float scale, int engine, void* stream);
 size_t nsr_xwin_attn_bwd_workspace(int batch, int h, int w, int c, int heads, int ws, int ows);
 /* dqkv [tokens, 3c] and dbias_table are OVERWRITTEN; deterministic (fixed-order partial sums). */
 int nsr_xwin_attn_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
                       float* dqkv, float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int ows,
-                      int shift, int use_mask, float scale, void* workspace, size_t workspace_bytes, void* stream);
+                      int shift, int use_mask, float scale, int engine, void* workspace, size_t workspace_bytes, void* stream);
 /* ChannelAttention (hat_arch.py:15-37) on NHWC [batch, hw, c]:
  *   pooled = nsr_channel_mean(x, NULL, scale = 1/hw)            AdaptiveAvgPool2d(1)
  *   gate   = sigmoid(W2 relu(W1 pooled + b1) + b2)              the two 1x1 convs (w1: [cs, c], w2: [c, cs])

@@ -155,10 +155,9 @@ SIGNATURES = {
     "nsr_consistency_bwd": (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _p, _p]),
     "nsr_reflect_fold": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "nsr_xwin_attn_stat_floats": (_z, [_i, _i, _i, _i, _i]),
-    "nsr_xwin_attn_use_tensor_cores": (_i, [_i]),
-    "nsr_xwin_attn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "nsr_xwin_attn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "nsr_xwin_attn_bwd_workspace": (_z, [_i, _i, _i, _i, _i, _i, _i]),
-    "nsr_xwin_attn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _z, _p]),
+    "nsr_xwin_attn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _z, _p]),
     "nsr_channel_mean": (_i, [_p, _p, _p, _i, _i, _i, _f, _p]),
     "nsr_channel_gate_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nsr_channel_scale_add": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p]),

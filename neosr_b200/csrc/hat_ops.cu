@@ -273,7 +273,6 @@ int xwin_fwd_mma_launch(const float* qkv, const float* table, float* out, float*
 int xwin_bwd_mma_launch(const float* qkv, const float* table, const float* out, const float* dout, const float* lse, float* delta,
                         float* dqkv, float* dkv_win, float* part, const GAGeom& g, cudaStream_t st);
 constexpr int GA_KTILE_MMA = 64;  // keys per CTA of the tensor-core dK/dV kernel (more, smaller partial tables)
-static int g_xwin_tc = 3;  // bit 0: forward, bit 1: backward on the mma.sync 3xBF16 kernels; 0: exact-fp32 CUDA-core kernels
                            // (default 1: measured on B200 at C4 the tensor-core forward wins 9.8 vs 11.3 ms, the backward does not yet:
                            // 38.4 vs 36.0 ms - its tile loads and the fixed-point table atomics dominate, not the MMAs)
 
@@ -402,21 +401,17 @@ static inline int grid1(size_t total) {
 }  // namespace nsr
 using namespace nsr;
 
-extern "C" int nsr_xwin_attn_use_tensor_cores(int on) {
-  const int prev = g_xwin_tc;
-  g_xwin_tc = on & 3;
-  return prev;
-}
 extern "C" size_t nsr_xwin_attn_stat_floats(int batch, int h, int w, int heads, int ws) {
   return (size_t)batch * (h / ws) * (w / ws) * heads * ws * ws;
 }
 extern "C" int nsr_xwin_attn_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int batch, int h, int w, int c,
-                                 int heads, int ws, int ows, int shift, int use_mask, float scale, void* stream) {
+                                 int heads, int ws, int ows, int shift, int use_mask, float scale, int engine, void* stream) {
   NSR_CHECK_ARG(qkv && bias_table && out && lse, "nsr_xwin_attn_fwd: null pointer");
+  NSR_CHECK_ARG(engine == NSR_ENGINE_AUTO || engine == NSR_ENGINE_SIMT, "nsr_xwin_attn_fwd: engine must be NSR_ENGINE_AUTO or NSR_ENGINE_SIMT");
   GAGeom g;
   int rc = ga_make(g, batch, h, w, c, heads, ws, ows, shift, use_mask, scale, "nsr_xwin_attn_fwd");
   if (rc) return rc;
-  if ((g_xwin_tc & 1) && xwin_attn_mma_supported(g)) return xwin_fwd_mma_launch(qkv, bias_table, out, lse, g, (cudaStream_t)stream);
+  if (engine != NSR_ENGINE_SIMT && xwin_attn_mma_supported(g)) return xwin_fwd_mma_launch(qkv, bias_table, out, lse, g, (cudaStream_t)stream);
   dim3 grid(batch * g.nwh * g.nww * heads, ceil_div(g.Nq, GA_THREADS));
   ga_fwd_kernel<<<grid, GA_THREADS, 0, (cudaStream_t)stream>>>(qkv, bias_table, out, lse, g);
   NSR_CHECK_LAUNCH("nsr_xwin_attn_fwd");
@@ -432,8 +427,9 @@ extern "C" size_t nsr_xwin_attn_bwd_workspace(int batch, int h, int w, int c, in
 }
 extern "C" int nsr_xwin_attn_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
                                  float* dqkv, float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int ows,
-                                 int shift, int use_mask, float scale, void* workspace, size_t workspace_bytes, void* stream) {
+                                 int shift, int use_mask, float scale, int engine, void* workspace, size_t workspace_bytes, void* stream) {
   NSR_CHECK_ARG(qkv && bias_table && out && dout && lse && dqkv && dbias_table, "nsr_xwin_attn_bwd: null pointer");
+  NSR_CHECK_ARG(engine == NSR_ENGINE_AUTO || engine == NSR_ENGINE_SIMT, "nsr_xwin_attn_bwd: engine must be NSR_ENGINE_AUTO or NSR_ENGINE_SIMT");
   GAGeom g;
   int rc = ga_make(g, batch, h, w, c, heads, ws, ows, shift, use_mask, scale, "nsr_xwin_attn_bwd");
   if (rc) return rc;
@@ -442,7 +438,7 @@ extern "C" int nsr_xwin_attn_bwd(const float* qkv, const float* bias_table, cons
     return NSR_E_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc = (g_xwin_tc & 2) && xwin_attn_mma_supported(g);
+  const bool tc = engine != NSR_ENGINE_SIMT && xwin_attn_mma_supported(g);
   const int nwin = batch * g.nwh * g.nww, ktiles = ceil_div(g.Nk, tc ? GA_KTILE_MMA : GA_THREADS);
   float* delta = (float*)workspace;
   float* part = delta + (size_t)nwin * heads * g.Nq;

@@ -108,8 +108,8 @@ class image:
         self._ema_params = None
         # CUDA-graph replay of the step (opt-out: `cuda_graph = false` in the option file); needs a
         # deterministic launch sequence, i.e. no DropPath draws, and the device-scalar optimizer path
-        ng = self.opt["network_g"]
-        dp = float(ng.get("drop_path_rate", 0.1)) if "swinir" in ng.get("type", "") else 0.0
+        # (read from the built network, not from the option text: hat_* defaults to drop_path_rate 0.1 too)
+        dp = max((float(getattr(m, "drop_prob", 0.0) or 0.0) for m in self.net_g.modules()), default=0.0)
         self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0 and self.net_d is None
                             and train_opt["optim_g"].get("type") in {"adan_sf", "Adan_SF"})
         self._graphs, self._graph_logs, self._eager_steps = None, None, 0
@@ -147,6 +147,7 @@ class image:
         if self.net_d is None and self.cri_gan is not None:
             raise ValueError("GAN requires a discriminator to be set.")
         self.setup_optimizers()
+        self.setup_schedulers()
         self.net_g.train()
         if self.sf_optim_g:
             self.optimizer_g.train()
@@ -177,6 +178,23 @@ class image:
             self.sf_optim_d = o.get("schedule_free", False)
             self.optimizer_d = self._make_optimizer(list(self.net_d.parameters()), o)
             self.optimizers.append(self.optimizer_d)
+
+    def setup_schedulers(self) -> None:  # base.py:174-198
+        """`[train.scheduler]`: MultiStepLR / CosineAnnealing over every optimizer, as the reference builds them (they
+        also give each param group its `initial_lr`, which the linear warm-up reads).  Unknown types are an error."""
+        so = self.opt["train"].get("scheduler")
+        if so is None:
+            return
+        so = dict(so)
+        kind = so.pop("type")
+        if kind in {"MultiStepLR", "multisteplr"}:
+            cls = torch.optim.lr_scheduler.MultiStepLR
+        elif kind in {"CosineAnnealing", "cosineannealing"}:
+            cls = torch.optim.lr_scheduler.CosineAnnealingLR
+        else:
+            raise NotImplementedError(f"Scheduler {kind} is not implemented yet.")
+        for o in self.optimizers:
+            self.schedulers.append(cls(o, **so))
 
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
@@ -341,9 +359,11 @@ class image:
             for s in self.schedulers:
                 s.step()
         if current_iter < warmup_iter:
+            # linear warm-up from the lr the scheduler recorded (base.py:203-252: `_get_init_lr` reads
+            # param_group["initial_lr"], which exists only when [train.scheduler] is set - same KeyError here)
             for opt in self.optimizers:
                 for g in opt.param_groups:
-                    g["lr"] = g.get("initial_lr", g["lr"]) / warmup_iter * current_iter
+                    g["lr"] = g["initial_lr"] / warmup_iter * current_iter
 
     def get_current_learning_rate(self):
         return [g["lr"] for g in self.optimizers[0].param_groups]

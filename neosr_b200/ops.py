@@ -1002,13 +1002,13 @@ def xwin_attn_fwd(qkv: Tensor, table: Tensor, heads: int, ws: int, ows: int, shi
     B, H, W, c3 = qkv.shape
     c = c3 // 3
     L = _lib.lib()
-    L.nsr_xwin_attn_use_tensor_cores(0 if DEFAULT_ENGINE == "simt" else int(XWIN_TENSOR_CORES))  # the exact-fp32 engines go together
+    eng = _lib.ENGINE["simt" if (DEFAULT_ENGINE == "simt" or not XWIN_TENSOR_CORES & 1) else "auto"]  # the exact-fp32 engines go together
     out = torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device)
     lse = torch.empty(L.nsr_xwin_attn_stat_floats(B, H, W, heads, ws), dtype=torch.float32, device=qkv.device)
     nk = ows * ows
     with _prof("nsr_xwin_attn_fwd", (B * H * W, c, heads, ws, ows), 4.0 * B * H * W * nk * c, 16.0 * qkv.numel() / 3):
         check(L.nsr_xwin_attn_fwd(qkv.data_ptr(), table.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, W, c, heads, ws, ows,
-                                  shift, int(shift > 0), scale, _stream()), "nsr_xwin_attn_fwd")
+                                  shift, int(shift > 0), scale, eng, _stream()), "nsr_xwin_attn_fwd")
     _count(1)
     return out, lse
 
@@ -1019,14 +1019,14 @@ def xwin_attn_bwd(qkv: Tensor, table: Tensor, out: Tensor, dout: Tensor, lse: Te
     B, H, W, c3 = qkv.shape
     c = c3 // 3
     L = _lib.lib()
-    L.nsr_xwin_attn_use_tensor_cores(0 if DEFAULT_ENGINE == "simt" else int(XWIN_TENSOR_CORES))
+    eng = _lib.ENGINE["simt" if (DEFAULT_ENGINE == "simt" or not XWIN_TENSOR_CORES & 2) else "auto"]
     dqkv = torch.empty_like(qkv)
     ws_t = scratch(L.nsr_xwin_attn_bwd_workspace(B, H, W, c, heads, ws, ows), qkv.device)
     nk = ows * ows
     with _prof("nsr_xwin_attn_bwd", (B * H * W, c, heads, ws, ows), 14.0 * B * H * W * nk * c, 28.0 * qkv.numel() / 3):
         check(L.nsr_xwin_attn_bwd(qkv.data_ptr(), table.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                   dqkv.data_ptr(), dtable.data_ptr(), B, H, W, c, heads, ws, ows, shift, int(shift > 0), scale,
-                                  ws_t.data_ptr(), ws_t.numel(), _stream()), "nsr_xwin_attn_bwd")
+                                  eng, ws_t.data_ptr(), ws_t.numel(), _stream()), "nsr_xwin_attn_bwd")
     _count(4 if ows != ws else 3)
     return dqkv
 

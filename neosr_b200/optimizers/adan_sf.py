@@ -47,6 +47,7 @@ class adan_sf(Optimizer):
         self._sumsq = None
         self._hp_slots: dict = {}
         self._plan: list = []
+        self._fresh: list = []
         self._clip = 0.0
 
     def __setstate__(self, state) -> None:
@@ -90,6 +91,7 @@ class adan_sf(Optimizer):
     def prepare(self, *, clip_max_norm: float | None = None, ema=None, to_device: bool = False) -> None:
         ema_iter = iter(ema[0]) if ema is not None else None
         self._plan = []
+        self._fresh = []
         self._clip = float(clip_max_norm or 0.0)
         for gi, group in enumerate(self.param_groups):
             beta1, beta2, beta3 = group["betas"]
@@ -126,6 +128,11 @@ class adan_sf(Optimizer):
                     st["z"] = torch.clone(p, memory_format=torch.contiguous_format).detach()
                 if "neg_pre_grad" not in st:
                     st["neg_pre_grad"] = torch.empty_like(p, memory_format=torch.contiguous_format)
+                    if step != 1:
+                        # a parameter that first meets a gradient after step 1, or a resumed state without the key: the
+                        # reference starts from -(clipped grad) (adan_sf.py:213-214); launch() fills it once the clip
+                        # coefficient is known (the kernel only initialises it on the group's first step)
+                        self._fresh.append((st["neg_pre_grad"], p.grad))
                 rows.append({"p": p.detach(), "g": p.grad, "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"],
                              "exp_avg_diff": st["exp_avg_diff"], "z": st["z"], "neg_pre_grad": st["neg_pre_grad"],
                              "ema": next(ema_iter) if ema_iter is not None else None})
@@ -178,6 +185,13 @@ class adan_sf(Optimizer):
                     self._sumsq = torch.zeros(1, dtype=torch.float32, device=tab.dev.device)
                 grad_sumsq(tab, self._sumsq)
                 sumsq_ptr = self._sumsq.data_ptr()
+        if self._fresh:  # rare, off the hot path: same coefficient the kernel derives from the squared norm
+            coef = 1.0
+            if sumsq_ptr is not None:
+                coef = torch.clamp(self._clip / (self._sumsq.sqrt() + 1e-6), max=1.0)
+            for npg, g in self._fresh:
+                npg.copy_(-(g * coef))
+            self._fresh = []
         for tab, hp, hp_dev, params in self._plan:
             if hp_dev is not None:
                 _lib.check(L.nsr_adan_sf_step_dev(tab.dev.data_ptr(), tab.n, tab.chunks, hp_dev.data_ptr(), sumsq_ptr,

@@ -17,7 +17,19 @@ import tempfile
 import types
 from pathlib import Path
 
-REF_ROOT = Path(os.environ.get("NEOSR_REFERENCE", "/root/reference"))
+def _find_ref_root() -> Path:
+    """$NEOSR_REFERENCE, else the read-only mount of the build container, else the staged copy that travels to the
+    GPU box (baseline/_ref, written by baseline/install_ref.py; git-ignored)."""
+    env = os.environ.get("NEOSR_REFERENCE")
+    if env:
+        return Path(env)
+    mount = Path("/root/reference")
+    if (mount / "neosr" / "archs" / "swinir_arch.py").exists():
+        return mount
+    return Path(__file__).resolve().parent.parent / "baseline" / "_ref"
+
+
+REF_ROOT = _find_ref_root()
 
 _TOML = """
 name = "shim"
@@ -56,7 +68,10 @@ def activate(scale: int = 4):
     if str(REF_ROOT) not in sys.path:
         sys.path.insert(0, str(REF_ROOT))
     for m in ("pywt", "lmdb"):
-        sys.modules.setdefault(m, types.ModuleType(m))
+        try:
+            __import__(m)
+        except ImportError:
+            sys.modules.setdefault(m, types.ModuleType(m))
     _state["scale"] = scale
 
 
@@ -66,8 +81,8 @@ def build_network(opt: dict):
     return bn(dict(opt))
 
 
-def build_vgg_perceptual(seed_params: dict, loss_weight: float = 0.5, criterion: str = "chc"):
-    """Reference vgg_perceptual_loss with OUR seeded VGG19 weights injected."""
+def build_vgg_perceptual(seed_params: dict | None, loss_weight: float = 0.5, criterion: str = "chc"):
+    """Reference vgg_perceptual_loss with OUR seeded VGG19 weights injected (None: torchvision's random init)."""
     activate()
     import torch  # noqa: PLC0415
     import torchvision.models.vgg as tvvgg  # noqa: PLC0415
@@ -93,14 +108,14 @@ def build_vgg_perceptual(seed_params: dict, loss_weight: float = 0.5, criterion:
         torch.tensor = orig_tensor
         vgg_arch.vgg.vgg19 = orig_vgg19
     sd = mod.vgg.state_dict()
-    for k, v in seed_params.items():
+    for k, v in (seed_params or {}).items():
         assert k in sd and tuple(sd[k].shape) == tuple(v.shape), k
         sd[k].copy_(v)
     return mod
 
 
 def make_image_model(net_g, *, cri_pix=None, cri_perceptual=None, optim_kw=None, ema=0.999, scale=4,
-                     net_d=None, cri_gan=None, optim_d_kw=None):
+                     net_d=None, cri_gan=None, optim_d_kw=None, device="cpu"):
     """`object.__new__(image)` with the attributes `closure`/`optimize_parameters` read
     (image.py:73-230), so the reference's REAL step methods run on CPU."""
     activate()
@@ -113,8 +128,13 @@ def make_image_model(net_g, *, cri_pix=None, cri_perceptual=None, optim_kw=None,
     m = object.__new__(image)
     m.opt = {"dist": False, "rank": 0, "world_size": 1, "scale": scale, "num_gpu": 1,
              "datasets": {"train": {}}, "train": {}, "path": {}}
-    m.device = torch.device("cpu")
+    m.device = torch.device(device)
     m.is_train = True
+    net_g = net_g.to(m.device)
+    cri_pix = cri_pix.to(m.device) if cri_pix is not None else None
+    cri_perceptual = cri_perceptual.to(m.device) if cri_perceptual is not None else None
+    net_d = net_d.to(m.device) if net_d is not None else None
+    cri_gan = cri_gan.to(m.device) if cri_gan is not None else None
     m.net_g, m.net_d = net_g, None
     m.optimizers, m.schedulers = [], []
     kw = dict(optim_kw or {})
