@@ -226,8 +226,17 @@ def reference_cuda_run(batch: int, steps: int, warmup: int, tf32: bool, pool: in
     """Informational: the reference's eager CUDA step on the same B200 (what a user of the reference sees today),
     fp32 (TF32 off) or with `fast_matmul` (TF32 on).  Device-timed with CUDA events, inputs fed from pinned memory."""
     import torch
-    m = _reference_model("cuda", tf32=tf32)
     data = synth_batches(pool, batch, seed=1024)
+    torch.set_default_device("cuda")  # what the reference's entry point does before it builds anything (train.py:165)
+    try:
+        return _reference_cuda_steps(data, batch, steps, warmup, tf32, pool)
+    finally:
+        torch.set_default_device("cpu")
+
+
+def _reference_cuda_steps(data, batch: int, steps: int, warmup: int, tf32: bool, pool: int) -> dict:
+    import torch
+    m = _reference_model("cuda", tf32=tf32)
     for i in range(warmup):
         m.feed_data(data[i % pool])
         m.optimize_parameters(i + 1)
@@ -316,7 +325,9 @@ def run_reference(args) -> None:
                 for key, tf32 in (("ref_cuda_fp32", False), ("ref_cuda_tf32", True)):
                     line[key] = reference_cuda_run(DEFAULT_BATCH["c3"], min(args.steps, 8), min(args.warmup, 3), tf32)
         except Exception as e:  # informational leg: never lose the line
-            line["ref_cuda_error"] = f"{type(e).__name__}: {e}"[:300]
+            import traceback
+            line["ref_cuda_error"] = (f"{type(e).__name__}: {e}"[:300] + " | " +
+                                      " <- ".join(f"{f.name}:{f.lineno}" for f in traceback.extract_tb(e.__traceback__)[-6:]))
     print(json.dumps(line), flush=True)
 
 

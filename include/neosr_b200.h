@@ -97,7 +97,10 @@ typedef struct NsrConv {
   int32_t pre_mode;      /* 0: y_pre = pre-activation; 1: y_pre = act'(pre-activation), so the backward
                             epilogue is a plain multiply (actgrad = NSR_ACT_MULAUX) and the erf/exp terms
                             are shared with the forward activation */
-  int32_t reserved;
+  int32_t sti_win;       /* 0: y_sti rows in token (image) order.  ws | shift << 16: WINDOW-ORDERED image - token (b, y, x)
+                            is stored at row ((b*H/ws + wy)*W/ws + wx)*ws*ws + iy*ws + ix, (wy,iy) = divmod((y - shift) mod H,
+                            ws), (wx,ix) likewise: torch.roll(-shift) + window_partition (swinir_arch.py:41-57,356-366) folded
+                            into the producing contraction's store, so nsr_window_attn_wsti_* bulk-copy whole windows */
   void* workspace;       /* optional scratch of nsr_conv_fprop_workspace() bytes: lets <= 4-channel convolutions */
   size_t workspace_bytes;/* (conv_first / conv_last, VGG conv1_1) run as im2col + one tensor-core contraction */
 } NsrConv;

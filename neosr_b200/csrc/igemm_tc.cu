@@ -239,12 +239,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
       const uint32_t bphase = (local >> 1) & 1;
       const long long p0 = (long long)(tile / g.n_tiles) * TC_BM + q * 32;   // first row of this warp
       const int n0 = (tile % g.n_tiles) * BN;
+      int wrow_lane = 0;  // window-ordered STI output: where tile row p0 + lane goes (computed while the MMAs run)
+      if (d.sti_win && p0 + lane < g.M) wrow_lane = sti_win_row(d, p0 + lane, hw);
       mbar_wait<STI ? 32 : 128>(&tfull[buf], bphase);  // idle epilogue warps must not spin against the producers
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = slot * 32; c0 < BN; c0 += 32 * NSLOT) {
         if (n0 + c0 >= ncols) break;  // warp-uniform
-        epi_chunk(d, stg, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, p0, n0 + c0, g.M, hw, lane, kbs_out);
+        epi_chunk(d, stg, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, p0, n0 + c0, g.M, hw, lane, kbs_out, wrow_lane);
       }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
@@ -289,6 +291,10 @@ bool conv_fprop_tc_supported(const NsrConv& d) {
     return false;
   }
   if (d.y == nullptr && d.y_sti == nullptr) return false;
+  if (d.sti_win) {  // window-ordered STI output: whole windows only
+    const int ws = d.sti_win & 0xFFFF, shift = d.sti_win >> 16;
+    if (d.y_sti == nullptr || ws <= 0 || d.h % ws || d.w % ws || shift < 0 || shift >= ws) return false;
+  }
   if (d.act != NSR_ACT_NONE && d.actgrad != NSR_ACT_NONE) return false;  // epilogue is specialised on one of them
   if (!aligned16(d.x) || !aligned16(d.y) || !aligned16(d.y_sti) || !aligned16(d.bias) || !aligned16(d.aux) || !aligned16(d.residual) ||
       !aligned16(d.y_pre) || !aligned16(d.prelu) || !aligned16(d.w_packed))

@@ -16,6 +16,21 @@ __device__ __forceinline__ size_t sti_offset(long long p, int col, int kbs) {
   return ((size_t)(mt * kbs + kb) << 15) + (size_t)(r * 128 + (((cc >> 3) ^ (r & 7)) << 4) + ((cc >> 2) & 1) * 8);
 }
 
+// Window-ordered split tile images (d.sti_win = ws | shift << 16, see NsrConv): token row p = (b, y, x) of the image is
+// stored at row  p' = ((b * H/ws + wy) * W/ws + wx) * ws^2 + iy * ws + ix  with (ys, xs) = ((y - shift) mod H, (x - shift)
+// mod W) the coordinates after torch.roll(-shift), (wy, iy) = divmod(ys, ws), (wx, ix) = divmod(xs, ws): the rows of one
+// attention window are contiguous, in the order window_partition (swinir_arch.py:41-57) flattens them.
+__device__ __forceinline__ int sti_win_row(const NsrConv& d, long long p, int hw) {
+  const int ws = d.sti_win & 0xFFFF, shift = d.sti_win >> 16;
+  const int b = (int)(p / hw), rem = (int)(p - (long long)b * hw);
+  const int y = rem / d.w, x = rem - y * d.w;
+  int ys = y - shift, xs = x - shift;
+  if (ys < 0) ys += d.h;
+  if (xs < 0) xs += d.w;
+  const int wy = ys / ws, iy = ys - wy * ws, wx = xs / ws, ix = xs - wx * ws;
+  return ((b * (d.h / ws) + wy) * (d.w / ws) + wx) * (ws * ws) + iy * ws + ix;
+}
+
 // The per-row work of one chunk, specialised at compile time on (activation, activation-gradient) so the
 // 8x-unrolled loop carries no per-element switch.  Lane = (row-in-group er, 4 columns starting at ec); group i is row
 // p0 + 4 i + er.  p0 is a multiple of 32 (tiles start at multiples of 128 rows, warps at multiples of 32), so the 32
@@ -24,7 +39,7 @@ __device__ __forceinline__ size_t sti_offset(long long p, int col, int kbs) {
 // 3: y, 4: split tile image; no row_scale), removing the warp-uniform tests from the unrolled loop; -1 reads them from d.
 template <int ACT, int AG, int MODE = -1>
 __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, long long p0, int n, bool ncol, bool nsti,
-                                         long long M, int hw, int er, int ec, int kbs_out) {
+                                         long long M, int hw, int er, int ec, int kbs_out, const int (&wrow)[8]) {
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(d.act_slope, d.act_slope, d.act_slope, d.act_slope);
   float4 g4 = make_float4(d.actgrad_slope, d.actgrad_slope, d.actgrad_slope, d.actgrad_slope);
   if (ncol && d.bias) b4 = __ldg(reinterpret_cast<const float4*>(d.bias + n));
@@ -48,12 +63,18 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
   // split tile image: 16-byte chunk index is swizzled with (row & 7) = er + 4 (i & 1)
   uint8_t* sp = nullptr;
   int sw0 = 0, sw1 = 0;
+  const bool win = d.sti_win != 0;  // window-ordered image: every row has its own block / swizzle phase (wrow[i])
   if (nsti) {
     const int cc = n & 63;
-    sp = reinterpret_cast<uint8_t*>(d.y_sti) + ((size_t)((pb >> 7) * kbs_out + (n >> 6)) << 15) + (size_t)(pb & 127) * 128 +
-         ((cc >> 2) & 1) * 8;
-    sw0 = ((cc >> 3) ^ er) << 4;
-    sw1 = ((cc >> 3) ^ (er + 4)) << 4;
+    if (win) {
+      sp = reinterpret_cast<uint8_t*>(d.y_sti) + ((size_t)(n >> 6) << 15) + ((cc >> 2) & 1) * 8;
+      sw0 = cc >> 3;
+    } else {
+      sp = reinterpret_cast<uint8_t*>(d.y_sti) + ((size_t)((pb >> 7) * kbs_out + (n >> 6)) << 15) + (size_t)(pb & 127) * 128 +
+           ((cc >> 2) & 1) * 8;
+      sw0 = ((cc >> 3) ^ er) << 4;
+      sw1 = ((cc >> 3) ^ (er + 4)) << 4;
+    }
   }
   const float one0 = n == d.cout ? 1.f : 0.f;  // first padding channel of an STI output = 1 (bias-gradient column)
 #pragma unroll
@@ -98,7 +119,13 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
         uint2 hi, lo;
         split2(ov[0], ov[1], hi.x, lo.x);
         split2(ov[2], ov[3], hi.y, lo.y);
-        uint8_t* dst = sp + i * 512 + ((i & 1) ? sw1 : sw0);
+        uint8_t* dst;
+        if (win) {
+          const int pr = wrow[i];
+          dst = sp + ((size_t)((pr >> 7) * kbs_out) << 15) + (pr & 127) * 128 + ((sw0 ^ (pr & 7)) << 4);
+        } else {
+          dst = sp + i * 512 + ((i & 1) ? sw1 : sw0);
+        }
         *reinterpret_cast<uint2*>(dst) = hi;
         *reinterpret_cast<uint2*>(dst + 16384) = lo;
       }
@@ -109,9 +136,15 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
 // d: contraction descriptor (epilogue fields), stg: this warp's [32][EPI_LD] fp32 tile,
 // taddr: TMEM address of (lane quarter, first column of the chunk), p0: first row of this warp,
 // nc0: first output channel of the chunk, kbs_out: 64-channel blocks of the STI output (0 if none)
+// wrow_lane: window-order row of tile row p0 + lane (sti_win_row; unused unless d.sti_win)
 __device__ __forceinline__ void epi_chunk(const NsrConv& d, float* stg, uint32_t taddr, long long p0, int nc0,
-                                          long long M_rows, int hw, int lane, int kbs_out) {
+                                          long long M_rows, int hw, int lane, int kbs_out, int wrow_lane = 0) {
   const int er = lane >> 3, ec = (lane & 7) * 4;
+  int wrow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (d.sti_win) {  // warp-uniform; before any per-lane exit
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wrow[i] = __shfl_sync(0xffffffffu, wrow_lane, er + 4 * i);
+  }
   float v[32];
   tmem_ld_32x32(taddr, v);
   __syncwarp();
@@ -129,19 +162,20 @@ __device__ __forceinline__ void epi_chunk(const NsrConv& d, float* stg, uint32_t
                                      (d.y_sti ? 16 : 0);
 #define NSR_EPI_HOT(A, G, M)                                                         \
   if (d.act == (A) && d.actgrad == (G) && mode == (M)) {                             \
-    epi_rows<A, G, M>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out);       \
+    epi_rows<A, G, M>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out, wrow); \
     return;                                                                          \
   }
   NSR_EPI_HOT(NSR_ACT_GELU, NSR_ACT_NONE, 19)    // fc1: gelu'(pre) + STI of gelu(pre)
   NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_MULAUX, 16)  // fc2 dgrad: dy * gelu' -> STI
   NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_NONE, 12)    // proj / fc2 / RSTB conv: + residual -> fp32
   NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_NONE, 8)     // qkv, plain dgrads -> fp32
+  NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_NONE, 16)    // qkv / proj dgrad -> (window-ordered) STI for the attention kernels
   NSR_EPI_HOT(NSR_ACT_RELU, NSR_ACT_NONE, 8)     // VGG conv + ReLU
   NSR_EPI_HOT(NSR_ACT_RELU, NSR_ACT_NONE, 9)     // VGG tapped layers: pre-activation kept
   NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_RELU, 8)     // VGG dgrad chain
 #undef NSR_EPI_HOT
 #define NSR_EPI_CASE(A, G) \
-  case (A) * 8 + (G): epi_rows<A, G>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out); break;
+  case (A) * 8 + (G): epi_rows<A, G>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out, wrow); break;
   switch (d.act * 8 + d.actgrad) {  // warp-uniform
     NSR_EPI_CASE(NSR_ACT_NONE, NSR_ACT_NONE)
     NSR_EPI_CASE(NSR_ACT_GELU, NSR_ACT_NONE)

@@ -42,7 +42,28 @@ from ..optimizers import AdamW, adan_sf
 from ..registry import MODEL_REGISTRY
 
 
+def host_default_device(cls):
+    """The reference's entry point sets `torch.set_default_device("cuda")` for the whole process (train.py:165); this
+    package is written against torch's normal default (host tensors unless a device is named: CPU generators, pinned
+    staging buffers, option scalars).  Every method the training loop can reach therefore runs with the default device
+    pinned back to the CPU; device tensors are always created with an explicit `device=`."""
+    import functools
+
+    def wrap(fn):
+        @functools.wraps(fn)
+        def inner(*a, **kw):
+            with torch.device("cpu"):
+                return fn(*a, **kw)
+        return inner
+
+    for name, attr in list(vars(cls).items()):
+        if callable(attr) and not isinstance(attr, (staticmethod, classmethod, type)) and (name == "__init__" or not name.startswith("__")):
+            setattr(cls, name, wrap(attr))
+    return cls
+
+
 @MODEL_REGISTRY.register()
+@host_default_device
 class image:
     def __init__(self, opt: dict[str, Any]) -> None:
         self.opt = opt

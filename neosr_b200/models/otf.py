@@ -19,7 +19,7 @@ from torch import Tensor
 
 from .. import ops
 from ..registry import MODEL_REGISTRY
-from .image import image
+from .image import host_default_device, image
 
 MODES = ("area", "bilinear", "bicubic")
 
@@ -75,6 +75,7 @@ def draw_plan(ds: dict, batch: int, ori_h: int, ori_w: int, scale: int, rng: np.
 
 
 @MODEL_REGISTRY.register()
+@host_default_device
 class otf(image):
     """On The Fly degradations, based on the RealESRGAN pipeline (neosr/models/otf.py:23-35)."""
 

@@ -116,3 +116,36 @@ class OracleTrainer:
 
 def make_swinir_trainer(params: dict, cfg: SwinIRConfig, **kw) -> OracleTrainer:
     return OracleTrainer(params, lambda p, x: swinir_forward(p, cfg, x), **kw)
+
+
+def displacement_report(p0: dict, ours: dict, ref32: dict, ref64: dict, noise_tol: float = 1e-2) -> dict:
+    """Compare parameter displacements after k training steps (TEST INFRASTRUCTURE).
+
+    adan's update is lr * m / sqrt(v): an element whose gradient is at round-off level (e.g. the key bias of an attention
+    layer, whose true gradient is zero because softmax ignores a constant shift) still moves by ~lr per step, in a
+    direction decided by noise - in the reference as much as anywhere.  Such elements are identified with the reference
+    itself: where its fp32 and fp64 runs (`ref32`, `ref64`: name -> tensor) disagree by more than `noise_tol` of the step,
+    fp32 round-off decides the step and the element says nothing about an implementation.  On the rest, the displacement
+    of `ours` is compared with the fp32 reference's.
+
+    Returns {"worst": (rel-L2 error on the mask, name), "coverage": min fraction of elements kept, "cos": cosine between
+    the two displacement vectors over ALL elements, "per_tensor": {name: (err, coverage)}}."""
+    per, worst, cov_min = {}, (0.0, ""), 1.0
+    dot = na = nb = 0.0
+    for k, init in p0.items():
+        if k not in ours or not init.is_floating_point():
+            continue
+        i64 = init.double()
+        d32, d64 = ref32[k].detach().double() - i64, ref64[k].detach().double() - i64
+        do = ours[k].detach().double().cpu() - i64
+        mask = (d32 - d64).abs() <= noise_tol * d64.abs()
+        cov = float(mask.double().mean())
+        err = float(((do - d32) * mask).norm() / (d32 * mask).norm().clamp_min(1e-300))
+        per[k] = (err, cov)
+        if err > worst[0]:
+            worst = (err, k)
+        cov_min = min(cov_min, cov)
+        dot += float((do * d32).sum())
+        na += float((do * do).sum())
+        nb += float((d32 * d32).sum())
+    return {"worst": worst, "coverage": cov_min, "cos": dot / max((na * nb) ** 0.5, 1e-300), "per_tensor": per}
