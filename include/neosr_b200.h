@@ -304,6 +304,29 @@ int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* 
                         int shift, int use_mask, float scale, void* workspace,
                         size_t workspace_bytes, void* dqkv_sti, void* stream);
 
+/*
+ * The same attention core on WINDOW-ORDERED operands (the default path of the SwinIR engine on sm_100):
+ *   qkv_wsti : split tile image [batch*h*w rows in window order, 3*G channels], G = nsr_window_attn_wsti_channels(heads)
+ *              = heads*32 rounded up to 64: q | k | v groups, every head padded from c/heads to 32 channels (padding = 0).
+ *              Produced by nsr_conv_fprop with NsrConv.sti_win = ws | shift << 16 from head-padded qkv weights
+ *              (nsr_gather2d): roll + window_partition + the q/k/v reshape (swinir_arch.py:353-364,172-183) cost nothing,
+ *              and a window's 64 tokens x a head pair of q, k or v is one contiguous 8 KiB run per bf16 half, fetched
+ *              with cp.async.bulk (no fp32 gather, no in-kernel bf16 split).
+ *   dout_wsti: the proj Linear's input gradient in the same row order, [rows, G] (heads padded to 32), produced by the
+ *              proj dgrad contraction with sti_win set and head-padded weights.
+ *   out / out_sti, dqkv / dqkv_sti, dbias_table: as nsr_window_attn_fwd / _bwd (natural token order, c and 3*c channels).
+ * Needs ws == 8 and an even head dim <= 32; workspace as nsr_window_attn_bwd_workspace.
+ */
+int nsr_window_attn_wsti_channels(int heads);
+int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti, int batch, int h, int w,
+                             int c, int heads, int ws, int shift, int use_mask, float scale, void* stream);
+int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_table, const void* dout_wsti, float* dqkv, void* dqkv_sti,
+                             float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
+                             float scale, void* workspace, size_t workspace_bytes, void* stream);
+/* dst[r][c] = src[row_map[r]][col_map[c]]; NULL map = identity, negative entry = 0 (head-padded weight / bias copies). */
+int nsr_gather2d(const float* src, int src_ld, const int* row_map, const int* col_map, float* dst, int rows, int cols,
+                 void* stream);
+
 /* ------------------------------------------------------------------ losses ------------- */
 /* All loss kernels ADD weight*loss into *loss_accum (device scalar) and write d(loss)/d(pred)
  * (already multiplied by weight and upstream 1.0) into dpred; reductions are two-pass and

@@ -341,6 +341,17 @@ __global__ void wgrad_split_kernel(const float* __restrict__ t, float* __restric
     else dbias[n] = v;
   }
 }
+// dst[r][c] = src[row_map[r]][col_map[c]] (a NULL map is the identity, a negative entry yields 0): head-padded copies of
+// the qkv / proj weights and biases for the window-ordered attention operands
+__global__ void gather2d_kernel(const float* __restrict__ src, int src_ld, const int* __restrict__ row_map,
+                                const int* __restrict__ col_map, float* __restrict__ dst, int rows, int cols) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+    const int sr = row_map ? row_map[r] : r, sc = col_map ? col_map[c] : c;
+    dst[i] = (sr < 0 || sc < 0) ? 0.f : src[(size_t)sr * src_ld + sc];
+  }
+}
 }  // namespace nsr
 using namespace nsr;
 extern "C" int nsr_wgrad_split(const float* t, float* dw, float* dbias, int cout, int cin, int cinp, void* stream) {
@@ -461,6 +472,14 @@ extern "C" int nsr_maxpool2_relu_bwd_nhwc(const float* x, const float* dy, const
   else
     maxpool2_relu_bwd_nhwc<<<ew_blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, dy, dextra, dx, B, H, W, C);
   NSR_CHECK_LAUNCH("maxpool2_relu_bwd_nhwc");
+  return NSR_OK;
+}
+extern "C" int nsr_gather2d(const float* src, int src_ld, const int* row_map, const int* col_map, float* dst, int rows,
+                            int cols, void* stream) {
+  NSR_CHECK_ARG(src && dst && rows > 0 && cols > 0 && src_ld > 0, "nsr_gather2d: bad arguments");
+  gather2d_kernel<<<ew_blocks((size_t)rows * cols), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_ld, row_map, col_map,
+                                                                                                  dst, rows, cols);
+  NSR_CHECK_LAUNCH("gather2d");
   return NSR_OK;
 }
 extern "C" int nsr_axpby(const float* a, float alpha, const float* b, float beta, float* y, size_t n, void* stream) {

@@ -46,7 +46,7 @@ struct TcGeom {
   long long M;
 };
 
-template <int BN, bool STI>
+template <int BN, bool STI, bool WIN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeom g, const uint8_t* __restrict__ wimg) {
   using Cfg = TcCfg<BN, STI>;
   extern __shared__ uint8_t smem_raw[];
@@ -240,13 +240,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
       const long long p0 = (long long)(tile / g.n_tiles) * TC_BM + q * 32;   // first row of this warp
       const int n0 = (tile % g.n_tiles) * BN;
       int wrow_lane = 0;  // window-ordered STI output: where tile row p0 + lane goes (computed while the MMAs run)
-      if (d.sti_win && p0 + lane < g.M) wrow_lane = sti_win_row(d, p0 + lane, hw);
+      if (WIN && p0 + lane < g.M) wrow_lane = sti_win_row(d, p0 + lane, hw);
       mbar_wait<STI ? 32 : 128>(&tfull[buf], bphase);  // idle epilogue warps must not spin against the producers
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = slot * 32; c0 < BN; c0 += 32 * NSLOT) {
         if (n0 + c0 >= ncols) break;  // warp-uniform
-        epi_chunk(d, stg, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, p0, n0 + c0, g.M, hw, lane, kbs_out, wrow_lane);
+        epi_chunk<WIN>(d, stg, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, p0, n0 + c0, g.M, hw, lane, kbs_out, wrow_lane);
       }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
@@ -293,7 +293,7 @@ bool conv_fprop_tc_supported(const NsrConv& d) {
   if (d.y == nullptr && d.y_sti == nullptr) return false;
   if (d.sti_win) {  // window-ordered STI output: whole windows only
     const int ws = d.sti_win & 0xFFFF, shift = d.sti_win >> 16;
-    if (d.y_sti == nullptr || ws <= 0 || d.h % ws || d.w % ws || shift < 0 || shift >= ws) return false;
+    if (d.y_sti == nullptr || d.x_sti == nullptr || ws <= 0 || d.h % ws || d.w % ws || shift < 0 || shift >= ws) return false;
   }
   if (d.act != NSR_ACT_NONE && d.actgrad != NSR_ACT_NONE) return false;  // epilogue is specialised on one of them
   if (!aligned16(d.x) || !aligned16(d.y) || !aligned16(d.y_sti) || !aligned16(d.bias) || !aligned16(d.aux) || !aligned16(d.residual) ||
@@ -302,12 +302,12 @@ bool conv_fprop_tc_supported(const NsrConv& d) {
   return true;
 }
 
-template <int BN, bool STI>
+template <int BN, bool STI, bool WIN = false>
 static int launch_fprop_tc(const NsrConv& d, cudaStream_t st) {
   using Cfg = TcCfg<BN, STI>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_tc<BN, STI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_tc<BN, STI, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes);
     if (e != cudaSuccess) {
       set_error("igemm_fprop_tc<%d>: cudaFuncSetAttribute(%d): %s", BN, Cfg::smem_bytes, cudaGetErrorString(e));
       return NSR_E_CUDA;
@@ -326,7 +326,7 @@ static int launch_fprop_tc(const NsrConv& d, cudaStream_t st) {
   g.n_pad64 = pg.n_pad64;
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + pg.f32_bytes;
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  igemm_fprop_tc<BN, STI><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, g, wimg);
+  igemm_fprop_tc<BN, STI, WIN><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, g, wimg);
   NSR_CHECK_LAUNCH("igemm_fprop_tc");
   return NSR_OK;
 }
@@ -335,6 +335,13 @@ int conv_fprop_tc(const NsrConv& d, cudaStream_t st) {
   if (d.x_sti != nullptr) {
     int bn = pick_bn(d.cout);
     if (bn == 256) bn = 128;  // the 12-warp epilogue staging leaves no room for BN=256 stages
+    if (d.sti_win) {  // window-ordered STI output (qkv fprop / proj dgrad feeding nsr_window_attn_wsti_*)
+      switch (bn) {
+        case 64: return launch_fprop_tc<64, true, true>(d, st);
+        case 128: return launch_fprop_tc<128, true, true>(d, st);
+        default: return launch_fprop_tc<192, true, true>(d, st);
+      }
+    }
     switch (bn) {
       case 64: return launch_fprop_tc<64, true>(d, st);
       case 128: return launch_fprop_tc<128, true>(d, st);

@@ -37,7 +37,7 @@ __device__ __forceinline__ int sti_win_row(const NsrConv& d, long long p, int hw
 // rows share one 128-row block of a split tile image and every address is a base + compile-time multiple of a stride.
 // MODE >= 0 additionally fixes which outputs exist (bit 0: y_pre, 1: y_pre holds the activation gradient, 2: residual,
 // 3: y, 4: split tile image; no row_scale), removing the warp-uniform tests from the unrolled loop; -1 reads them from d.
-template <int ACT, int AG, int MODE = -1>
+template <int ACT, int AG, int MODE = -1, bool WIN = false>
 __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, long long p0, int n, bool ncol, bool nsti,
                                          long long M, int hw, int er, int ec, int kbs_out, const int (&wrow)[8]) {
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(d.act_slope, d.act_slope, d.act_slope, d.act_slope);
@@ -63,7 +63,7 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
   // split tile image: 16-byte chunk index is swizzled with (row & 7) = er + 4 (i & 1)
   uint8_t* sp = nullptr;
   int sw0 = 0, sw1 = 0;
-  const bool win = d.sti_win != 0;  // window-ordered image: every row has its own block / swizzle phase (wrow[i])
+  constexpr bool win = WIN;  // window-ordered image: every row has its own block / swizzle phase (wrow[i])
   if (nsti) {
     const int cc = n & 63;
     if (win) {
@@ -136,12 +136,13 @@ __device__ __forceinline__ void epi_rows(const NsrConv& d, const float* stg, lon
 // d: contraction descriptor (epilogue fields), stg: this warp's [32][EPI_LD] fp32 tile,
 // taddr: TMEM address of (lane quarter, first column of the chunk), p0: first row of this warp,
 // nc0: first output channel of the chunk, kbs_out: 64-channel blocks of the STI output (0 if none)
-// wrow_lane: window-order row of tile row p0 + lane (sti_win_row; unused unless d.sti_win)
+// wrow_lane: window-order row of tile row p0 + lane (sti_win_row; WIN = the kernel instantiation for d.sti_win != 0)
+template <bool WIN = false>
 __device__ __forceinline__ void epi_chunk(const NsrConv& d, float* stg, uint32_t taddr, long long p0, int nc0,
                                           long long M_rows, int hw, int lane, int kbs_out, int wrow_lane = 0) {
   const int er = lane >> 3, ec = (lane & 7) * 4;
   int wrow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (d.sti_win) {  // warp-uniform; before any per-lane exit
+  if (WIN) {  // before any per-lane exit
 #pragma unroll
     for (int i = 0; i < 8; ++i) wrow[i] = __shfl_sync(0xffffffffu, wrow_lane, er + 4 * i);
   }
@@ -162,7 +163,7 @@ __device__ __forceinline__ void epi_chunk(const NsrConv& d, float* stg, uint32_t
                                      (d.y_sti ? 16 : 0);
 #define NSR_EPI_HOT(A, G, M)                                                         \
   if (d.act == (A) && d.actgrad == (G) && mode == (M)) {                             \
-    epi_rows<A, G, M>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out, wrow); \
+    epi_rows<A, G, M, WIN>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out, wrow); \
     return;                                                                          \
   }
   NSR_EPI_HOT(NSR_ACT_GELU, NSR_ACT_NONE, 19)    // fc1: gelu'(pre) + STI of gelu(pre)
@@ -175,7 +176,7 @@ __device__ __forceinline__ void epi_chunk(const NsrConv& d, float* stg, uint32_t
   NSR_EPI_HOT(NSR_ACT_NONE, NSR_ACT_RELU, 8)     // VGG dgrad chain
 #undef NSR_EPI_HOT
 #define NSR_EPI_CASE(A, G) \
-  case (A) * 8 + (G): epi_rows<A, G>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out, wrow); break;
+  case (A) * 8 + (G): epi_rows<A, G, -1, WIN>(d, stg, p0, n, ncol, nsti, M_rows, hw, er, ec, kbs_out, wrow); break;
   switch (d.act * 8 + d.actgrad) {  // warp-uniform
     NSR_EPI_CASE(NSR_ACT_NONE, NSR_ACT_NONE)
     NSR_EPI_CASE(NSR_ACT_GELU, NSR_ACT_NONE)

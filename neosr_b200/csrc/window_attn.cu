@@ -243,6 +243,11 @@ int window_attn_bwd_mma_ctas();
 int window_attn_bwd_mma_launch(const float* qkv, const float* table, const float* dout, float* dqkv, void* dqkv_sti,
                                float* partial, int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
                                float scale, cudaStream_t st);
+int window_attn_wsti_fwd_launch(const void* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w,
+                                int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
+int window_attn_wsti_bwd_launch(const void* qkv, const float* table, const void* dout, float* dqkv, void* dqkv_sti,
+                                float* partial, int gx, int batch, int h, int w, int c, int heads, int ws, int shift,
+                                int use_mask, float scale, cudaStream_t st);
 static bool use_mma(int c, int heads, int ws) {
   static int simt_forced = -1;
   if (simt_forced < 0) {
@@ -336,6 +341,61 @@ extern "C" int nsr_window_attn_bwd(const float* qkv, const float* bias_table, co
     }
   }
   float* dssum = partial + (size_t)gx * heads * WA_N * WA_N;  // the workspace has `heads` spare tiles after the partials
+  window_attn_dbias_sum<<<ceil_div(heads * WA_N * WA_N, 256), 256, 0, st>>>(partial, dssum, gx, heads);
+  NSR_CHECK_LAUNCH("window_attn_dbias_sum");
+  const int n = (2 * ws - 1) * (2 * ws - 1) * heads;
+  window_attn_dbias_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dssum, dbias_table, heads, ws);
+  NSR_CHECK_LAUNCH("window_attn_dbias");
+  return NSR_OK;
+}
+
+// ---- window-ordered operands (see window_attn_mma.cu) -------------------------------------------------------------
+extern "C" int nsr_window_attn_wsti_channels(int heads) { return (heads * 32 + 63) / 64 * 64; }
+
+static int wsti_check(WinGeom& g, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask, float scale,
+                      const char* who) {
+  int rc = make_geom(g, batch, h, w, c, heads, ws, shift, use_mask, scale, who);
+  if (rc) return rc;
+  NSR_CHECK_ARG(window_attn_mma_supported(c, heads, ws) && nsr_device_supports_tcgen05(),
+                "%s: needs window 8, an even head dim <= 32 and an sm_100 device (bulk-copied operands)", who);
+  return NSR_OK;
+}
+
+extern "C" int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti, int batch,
+                                        int h, int w, int c, int heads, int ws, int shift, int use_mask, float scale,
+                                        void* stream) {
+  NSR_CHECK_ARG(qkv_wsti && bias_table && (out || out_sti), "nsr_window_attn_wsti_fwd: null pointer");
+  NSR_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv_wsti) & 15) == 0, "nsr_window_attn_wsti_fwd: image must be 16-byte aligned");
+  WinGeom g;
+  int rc = wsti_check(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_wsti_fwd");
+  if (rc) return rc;
+  return window_attn_wsti_fwd_launch(qkv_wsti, bias_table, out, out_sti, batch, h, w, c, heads, ws, shift, use_mask, scale,
+                                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_table, const void* dout_wsti, float* dqkv,
+                                        void* dqkv_sti, float* dbias_table, int batch, int h, int w, int c, int heads, int ws,
+                                        int shift, int use_mask, float scale, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  NSR_CHECK_ARG(qkv_wsti && bias_table && dout_wsti && (dqkv || dqkv_sti) && dbias_table, "nsr_window_attn_wsti_bwd: null pointer");
+  NSR_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv_wsti) | reinterpret_cast<uintptr_t>(dout_wsti)) & 15) == 0,
+                "nsr_window_attn_wsti_bwd: images must be 16-byte aligned");
+  WinGeom g;
+  int rc = wsti_check(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_wsti_bwd");
+  if (rc) return rc;
+  const int nwin = batch * g.nwh * g.nww;
+  const int gx = bwd_gx(nwin, heads, true);
+  const size_t need = (size_t)(gx + 1) * heads * WA_N * WA_N * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_error("nsr_window_attn_wsti_bwd: workspace %zu < %zu", workspace_bytes, need);
+    return NSR_E_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* partial = reinterpret_cast<float*>(workspace);
+  rc = window_attn_wsti_bwd_launch(qkv_wsti, bias_table, dout_wsti, dqkv, dqkv_sti, partial, gx, batch, h, w, c, heads, ws,
+                                   shift, use_mask, scale, st);
+  if (rc) return rc;
+  float* dssum = partial + (size_t)gx * heads * WA_N * WA_N;
   window_attn_dbias_sum<<<ceil_div(heads * WA_N * WA_N, 256), 256, 0, st>>>(partial, dssum, gx, heads);
   NSR_CHECK_LAUNCH("window_attn_dbias_sum");
   const int n = (2 * ws - 1) * (2 * ws - 1) * heads;

@@ -128,10 +128,12 @@ def displacement_report(p0: dict, ours: dict, ref32: dict, ref64: dict, noise_to
     fp32 round-off decides the step and the element says nothing about an implementation.  On the rest, the displacement
     of `ours` is compared with the fp32 reference's.
 
-    Returns {"worst": (rel-L2 error on the mask, name), "coverage": min fraction of elements kept, "cos": cosine between
-    the two displacement vectors over ALL elements, "per_tensor": {name: (err, coverage)}}."""
+    Returns {"worst": (rel-L2 error on the mask, name), "coverage": min over tensors of the fraction of elements kept,
+    "coverage_all": fraction of ALL elements kept, "cos": cosine between the two displacement vectors over ALL elements
+    (masked or not), "per_tensor": {name: (err, coverage)}}."""
     per, worst, cov_min = {}, (0.0, ""), 1.0
     dot = na = nb = 0.0
+    kept = total = 0
     for k, init in p0.items():
         if k not in ours or not init.is_floating_point():
             continue
@@ -140,6 +142,8 @@ def displacement_report(p0: dict, ours: dict, ref32: dict, ref64: dict, noise_to
         do = ours[k].detach().double().cpu() - i64
         mask = (d32 - d64).abs() <= noise_tol * d64.abs()
         cov = float(mask.double().mean())
+        kept += int(mask.sum())
+        total += mask.numel()
         err = float(((do - d32) * mask).norm() / (d32 * mask).norm().clamp_min(1e-300))
         per[k] = (err, cov)
         if err > worst[0]:
@@ -148,4 +152,4 @@ def displacement_report(p0: dict, ours: dict, ref32: dict, ref64: dict, noise_to
         dot += float((do * d32).sum())
         na += float((do * do).sum())
         nb += float((d32 * d32).sum())
-    return {"worst": worst, "coverage": cov_min, "cos": dot / max((na * nb) ** 0.5, 1e-300), "per_tensor": per}
+    return {"worst": worst, "coverage": cov_min, "coverage_all": kept / max(total, 1), "cos": dot / max((na * nb) ** 0.5, 1e-300), "per_tensor": per}
