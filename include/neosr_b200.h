@@ -43,6 +43,7 @@ extern "C" {
 #define NSR_ENGINE_AUTO 0
 #define NSR_ENGINE_SIMT 1    /* exact-fp32 CUDA-core implicit GEMM */
 #define NSR_ENGINE_TCGEN05 2 /* tcgen05 (UMMA) 3xBF16-split, fp32 accumulate in TMEM */
+#define NSR_ENGINE_MMA_SYNC 3 /* nsr_window_attn_wsti_*: the warp-level mma.sync kernels instead of tcgen05 (A/B runs) */
 
 const char* nsr_last_error(void);
 int nsr_version(void);
@@ -316,10 +317,13 @@ int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* 
  *              proj dgrad contraction with sti_win set and head-padded weights.
  *   out / out_sti, dqkv / dqkv_sti, dbias_table: as nsr_window_attn_fwd / _bwd (natural token order, c and 3*c channels).
  * Needs ws == 8 and an even head dim <= 32; workspace as nsr_window_attn_bwd_workspace.
+ * engine: NSR_ENGINE_AUTO / NSR_ENGINE_TCGEN05 = Q K^T and P V as tcgen05.mma with TMEM accumulators (window_attn_tc.cu: one
+ * work item = a window pair x a head pair = three 32 KiB operand blocks, softmax by one thread per query row);
+ * NSR_ENGINE_MMA_SYNC = the warp-level mma.sync kernels on the same operands.
  */
 int nsr_window_attn_wsti_channels(int heads);
 int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti, int batch, int h, int w,
-                             int c, int heads, int ws, int shift, int use_mask, float scale, void* stream);
+                             int c, int heads, int ws, int shift, int use_mask, float scale, int engine, void* stream);
 int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_table, const void* dout_wsti, float* dqkv, void* dqkv_sti,
                              float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
                              float scale, void* workspace, size_t workspace_bytes, void* stream);

@@ -68,7 +68,7 @@ class NsrAdamW(C.Structure):
 
 OPT_CHUNK = 4096
 ACT = {"none": 0, "relu": 1, "lrelu": 2, "gelu": 3, "prelu": 4, "mulaux": 5}
-ENGINE = {"auto": 0, "simt": 1, "tcgen05": 2}
+ENGINE = {"auto": 0, "simt": 1, "tcgen05": 2, "mma_sync": 3}
 
 _i, _f, _p, _z, _l = C.c_int, C.c_float, C.c_void_p, C.c_size_t, C.c_int64
 # name -> (restype, argtypes): every symbol include/neosr_b200.h declares.
@@ -124,7 +124,7 @@ SIGNATURES = {
     "nsr_window_attn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p]),
     "nsr_window_attn_bwd_workspace": (_z, [_i, _i]),
     "nsr_window_attn_wsti_channels": (_i, [_i]),
-    "nsr_window_attn_wsti_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "nsr_window_attn_wsti_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "nsr_window_attn_wsti_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _z, _p]),
     "nsr_gather2d": (_i, [_p, _i, _p, _p, _p, _i, _i, _p]),
     "nsr_window_attn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _z, _p, _p]),

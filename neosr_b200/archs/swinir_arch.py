@@ -231,6 +231,9 @@ class swinir(nn.Module):
         S: dict = {"shape": (B, H, W)} if save else None
         drops = self._drop_scales(B, x.device)
         sti = ops.sti_enabled()  # GEMM operands as split tile images (bulk-copied, no conversion warps)
+        # attention operands in window order with heads padded to 32 channels: written that way by the qkv
+        # contraction's epilogue and fetched by the attention kernels with bulk copies (NSR_WSTI=0: A/B switch)
+        wsti = sti and ops.WSTI_ENABLED and all(ops.wsti_supported(self.embed_dim, h, ws) for h in self.num_heads)
 
         def lin(name, t, **kw):
             return ops.conv_fprop(t, ps.pw(name + ".weight"), ps.p(name + ".bias") if ps.has(name + ".bias") else None, **kw)
@@ -264,9 +267,16 @@ class swinir(nn.Module):
                 bi_glob += 1
                 ln1, mu1, rs1 = ops.layernorm_fwd(t, ps.p(pre + "norm1.weight"), ps.p(pre + "norm1.bias"),
                                                   sti_out=sti, f32_out=not sti)
-                qkv = lin(pre + "attn.qkv", ln1)
-                att = ops.window_attn_fwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), heads, ws,
-                                          blk.shift_size, scale, sti_out=sti)
+                if wsti:
+                    qw = ps.pw_mapped(pre + "attn.qkv.weight", "qkv_rows", pre + "attn.qkv.bias",
+                                      row_map=ops.head_pad_map(self.embed_dim, heads, 3), need_dgrad=False)
+                    qkv = ops.conv_fprop(ln1, qw, qw.bias_padded, sti_out=True, f32_out=False, sti_win=(ws, blk.shift_size))
+                    att = ops.window_attn_fwd_wsti(qkv, ps.p(pre + "attn.relative_position_bias_table"), self.embed_dim,
+                                                   heads, ws, blk.shift_size, scale)
+                else:
+                    qkv = lin(pre + "attn.qkv", ln1)
+                    att = ops.window_attn_fwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), heads, ws,
+                                              blk.shift_size, scale, sti_out=sti)
                 x1 = lin(pre + "attn.proj", att, residual=t, row_scale=ds[0] if ds else None)
                 ln2, mu2, rs2 = ops.layernorm_fwd(x1, ps.p(pre + "norm2.weight"), ps.p(pre + "norm2.bias"),
                                                   sti_out=sti, f32_out=not sti)
@@ -416,10 +426,19 @@ class swinir(nn.Module):
                                        ps.g(pre + "norm2.bias"), dres=gf, sti_out=sti)
                 g1f = split(g1)[0]
                 gb = scaled(g1, ds[0] if ds else None)
-                datt = bwd(pre + "attn.proj", att, gb)
-                dqkv = ops.window_attn_bwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
-                                           ps.g(pre + "attn.relative_position_bias_table"), heads, ws, shift, scale,
-                                           sti_out=sti)
+                if isinstance(qkv, ops.STI):  # window-ordered operands (see engine_forward)
+                    bwd(pre + "attn.proj", att, gb, need_dx=False)
+                    pwm = ps.pw_mapped(pre + "attn.proj.weight", "proj_cols", None,
+                                       col_map=ops.head_pad_map(self.embed_dim, heads, 1))
+                    datt = ops.conv_fprop(split(gb)[1], pwm, None, dgrad=True, sti_out=True, f32_out=False, sti_win=(ws, shift))
+                    dqkv = ops.window_attn_bwd_wsti(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
+                                                    ps.g(pre + "attn.relative_position_bias_table"), self.embed_dim, heads,
+                                                    ws, shift, scale)
+                else:
+                    datt = bwd(pre + "attn.proj", att, gb)
+                    dqkv = ops.window_attn_bwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
+                                               ps.g(pre + "attn.relative_position_bias_table"), heads, ws, shift, scale,
+                                               sti_out=sti)
                 dln1 = bwd(pre + "attn.qkv", ln1, dqkv)
                 g = ops.layernorm_bwd(dln1, t0, ps.p(pre + "norm1.weight"), mu1, rs1, ps.g(pre + "norm1.weight"),
                                       ps.g(pre + "norm1.bias"), dres=g1f, sti_out=sti and bi > 0)

@@ -248,6 +248,9 @@ int window_attn_wsti_fwd_launch(const void* qkv, const float* table, float* out,
 int window_attn_wsti_bwd_launch(const void* qkv, const float* table, const void* dout, float* dqkv, void* dqkv_sti,
                                 float* partial, int gx, int batch, int h, int w, int c, int heads, int ws, int shift,
                                 int use_mask, float scale, cudaStream_t st);
+bool window_attn_tc_supported(int c, int heads, int ws);
+int window_attn_tc_fwd_launch(const void* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w, int c,
+                              int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
 static bool use_mma(int c, int heads, int ws) {
   static int simt_forced = -1;
   if (simt_forced < 0) {
@@ -363,12 +366,18 @@ static int wsti_check(WinGeom& g, int batch, int h, int w, int c, int heads, int
 
 extern "C" int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti, int batch,
                                         int h, int w, int c, int heads, int ws, int shift, int use_mask, float scale,
-                                        void* stream) {
+                                        int engine, void* stream) {
   NSR_CHECK_ARG(qkv_wsti && bias_table && (out || out_sti), "nsr_window_attn_wsti_fwd: null pointer");
+  NSR_CHECK_ARG(engine == NSR_ENGINE_AUTO || engine == NSR_ENGINE_TCGEN05 || engine == NSR_ENGINE_MMA_SYNC,
+                "nsr_window_attn_wsti_fwd: engine must be NSR_ENGINE_AUTO, _TCGEN05 or _MMA_SYNC");
   NSR_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv_wsti) & 15) == 0, "nsr_window_attn_wsti_fwd: image must be 16-byte aligned");
   WinGeom g;
   int rc = wsti_check(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_wsti_fwd");
   if (rc) return rc;
+  if (engine != NSR_ENGINE_MMA_SYNC && window_attn_tc_supported(c, heads, ws))
+    return window_attn_tc_fwd_launch(qkv_wsti, bias_table, out, out_sti, batch, h, w, c, heads, ws, shift, use_mask, scale,
+                                     reinterpret_cast<cudaStream_t>(stream));
+  NSR_CHECK_ARG(engine != NSR_ENGINE_TCGEN05, "nsr_window_attn_wsti_fwd: shape not supported by the tcgen05 kernel");
   return window_attn_wsti_fwd_launch(qkv_wsti, bias_table, out, out_sti, batch, h, w, c, heads, ws, shift, use_mask, scale,
                                      reinterpret_cast<cudaStream_t>(stream));
 }

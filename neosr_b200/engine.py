@@ -37,6 +37,16 @@ class ParamSet:
             pk = self._packed[name] = ops.PackedWeight(w, need_dgrad=need_dgrad)
         return pk.refresh()
 
+    def pw_mapped(self, name: str, key: str, bias_name: str | None, row_map=None, col_map=None,
+                  need_dgrad: bool = True) -> ops.MappedPackedWeight:
+        """A re-indexed (head-padded) packed copy of Linear weight `name`; `key` distinguishes several views."""
+        w = self.p(name)
+        pk = self._packed.get((name, key))
+        if pk is None or pk.weight.data_ptr() != w.data_ptr():
+            pk = self._packed[(name, key)] = ops.MappedPackedWeight(
+                w, self.p(bias_name) if bias_name is not None and self.has(bias_name) else None, row_map, col_map, need_dgrad)
+        return pk.refresh()
+
     def invalidate_packed(self) -> None:
         """Force a re-pack on next use (weights changed behind autograd's back, e.g. the
         schedule-free optimizer's `p.data.lerp_` in train()/eval(), adan_sf.py:112-136)."""

@@ -6,6 +6,7 @@ on the hot path.  Activations are NHWC ("tokens"): a tensor of shape [B, H, W, C
 """
 from __future__ import annotations
 
+import functools
 import os
 
 import ctypes as C
@@ -19,6 +20,8 @@ from . import _lib
 from ._lib import ACT, ENGINE, NsrConv, NsrWgrad, check
 
 
+WSTI_ATTN_ENGINE = os.environ.get("NSR_WSTI_ATTN", "auto")  # auto / tcgen05 / mma_sync kernels behind nsr_window_attn_wsti_*
+WSTI_ENABLED = os.environ.get("NSR_WSTI", "1") != "0"  # window-ordered attention operands for SwinIR (A/B switch)
 XWIN_TENSOR_CORES = int(os.environ.get("NSR_XWIN_TC", "3"))  # HAT window attention engine mask: bit 0 forward, bit 1 backward on mma.sync; 0 = exact fp32
 BIAS_COLUMN_ENABLED = True  # bias gradients from the ones channel of split tile images (tests flip it)
 LK16_ENABLED = True   # route 16->16-channel k>=7 convs to the dedicated large-kernel kernels (tests flip it)
@@ -201,15 +204,74 @@ class PackedWeight:
         return self
 
 
+class MappedPackedWeight(PackedWeight):
+    """Packed copy of a Linear weight [cout, cin] whose output rows and / or input columns are re-indexed through int
+    maps (-1 = a zero row / column), plus the matching padded bias.  Used for the head-padded qkv (rows) and proj
+    (columns) weights behind the window-ordered attention operands: re-gathered (`nsr_gather2d`) and re-packed whenever
+    the parameter's version changes, like any PackedWeight."""
+
+    def __init__(self, weight: Tensor, bias: Tensor | None, row_map=None, col_map=None, need_dgrad: bool = True):
+        dev = weight.device
+        rows = len(row_map) if row_map is not None else weight.shape[0]
+        cols = len(col_map) if col_map is not None else weight.shape[1]
+        self.src, self.src_bias = weight, bias
+        self.row_map = torch.tensor(row_map, dtype=torch.int32, device=dev) if row_map is not None else None
+        self.col_map = torch.tensor(col_map, dtype=torch.int32, device=dev) if col_map is not None else None
+        self.padded = torch.zeros((rows, cols), dtype=torch.float32, device=dev)
+        self.bias_padded = torch.zeros(rows, dtype=torch.float32, device=dev) if bias is not None else None
+        super().__init__(self.padded, need_dgrad=need_dgrad)
+        self.weight = weight  # identity of the source parameter (ParamSet.pw compares data pointers)
+
+    def refresh(self, force: bool = False) -> "MappedPackedWeight":
+        w, b = self.src, self.src_bias
+        ver = (w.data_ptr(), w._version, None if b is None else b._version)
+        if not force and ver == self._version:
+            return self
+        _chk(w, "weight")
+        L = _lib.lib()
+        st = _stream()
+        check(L.nsr_gather2d(w.data_ptr(), w.shape[1], _p(self.row_map), _p(self.col_map), self.padded.data_ptr(),
+                             self.padded.shape[0], self.padded.shape[1], st), "nsr_gather2d")
+        if b is not None:
+            check(L.nsr_gather2d(b.data_ptr(), b.shape[0], None, _p(self.row_map), self.bias_padded.data_ptr(), 1,
+                                 self.bias_padded.shape[0], st), "nsr_gather2d")
+        check(L.nsr_pack_weight_pair(self.padded.data_ptr(), self.cout, self.cin, 1, 1, self.fprop.data_ptr(),
+                                     _p(self.dgrad), st), "nsr_pack_weight_pair")
+        _count(2 if b is None else 3)
+        self._version = ver
+        return self
+
+
+@functools.lru_cache(maxsize=64)
+def head_pad_map(c: int, heads: int, groups: int) -> tuple:
+    """Channel map of the window-ordered attention operands: `groups` blocks (q | k | v, or 1) of G =
+    nsr_window_attn_wsti_channels(heads) channels, head h of a group at [h*32, h*32 + c/heads), the rest -1 (zero)."""
+    G = _lib.lib().nsr_window_attn_wsti_channels(heads)
+    d = c // heads
+    m = [-1] * (groups * G)
+    for s in range(groups):
+        for h in range(heads):
+            for i in range(d):
+                m[s * G + h * 32 + i] = s * c + h * d + i
+    return tuple(m)
+
+
+def wsti_supported(c: int, heads: int, ws: int) -> bool:
+    """Window-ordered attention operands: tcgen05 engine + the mma attention kernels' shape limits."""
+    return sti_enabled() and _attn_mma_ok(c, heads, ws)
+
+
 # ----------------------------------------------------------------------------- contraction
 def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad: bool = False,
                act: str = "none", act_slope: float = 0.0, actgrad: str = "none", actgrad_slope: float = 0.0,
                aux: Tensor | None = None, prelu: Tensor | None = None, row_scale: Tensor | None = None,
                residual: Tensor | None = None, want_pre: bool = False, out: Tensor | None = None,
-               engine: str = "auto", sti_out: bool = False, f32_out: bool = True, pre_is_actgrad: bool = False):
+               engine: str = "auto", sti_out: bool = False, f32_out: bool = True, pre_is_actgrad: bool = False,
+               sti_win: tuple | None = None):
     """y = epilogue(conv(x, w)); x is [B,H,W,Cin] NHWC fp32 or an STI (1x1 only).  With dgrad=True
     the dgrad-packed filter is used and the roles of cin/cout swap (x is then dY [B,H,W,Cout]).
-    sti_out / f32_out select the output formats: returns y (fp32), or the STI, or (y, sti)."""
+    sti_out / f32_out select the output formats: returns y (fp32), or the STI, or (y, sti).
+    sti_win = (ws, shift): the STI's rows are written in window order (NsrConv.sti_win)."""
     x_is_sti = isinstance(x, STI)
     if not x_is_sti and not isinstance(x, Slab):
         _chk(x, "x")
@@ -254,7 +316,8 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
                 bias=_p(bias), prelu=_p(prelu), aux=aux_ptr, row_scale=_p(row_scale), residual=res_ptr,
                 y_pre=_p(y_pre), y=y_ptr, x_sti=x.data_ptr() if x_is_sti else None, y_sti=_p(y_sti),
                 res_ld=res_ld if res_ld != y_ld else 0, aux_ld=aux_ld if aux_ld != y_ld else 0,
-                pre_mode=1 if pre_is_actgrad else 0, reserved=0, workspace=None, workspace_bytes=0)
+                pre_mode=1 if pre_is_actgrad else 0, sti_win=(sti_win[0] | (sti_win[1] << 16)) if sti_win else 0,
+                workspace=None, workspace_bytes=0)
     if min(cin, cout) <= 4:  # image-side convs: im2col + tensor-core contraction needs scratch
         need = _lib.lib().nsr_conv_fprop_workspace(C.byref(d))
         if need:
@@ -701,6 +764,41 @@ def window_attn_bwd(qkv: Tensor, table: Tensor, dout: Tensor, dtable: Tensor, he
                                     B, H, W, c, heads, ws, shift, 1 if shift > 0 else 0, scale, wsb.data_ptr(), wsb.numel(),
                                     _p(dqkv_sti), _stream()), "nsr_window_attn_bwd")
     _count(2)
+    return dqkv_sti if sti_out else dqkv
+
+
+def window_attn_fwd_wsti(qkv: STI, table: Tensor, c: int, heads: int, ws: int, shift: int, scale: float,
+                         sti_out: bool = True, engine: str | None = None):
+    """qkv: window-ordered, head-padded STI [B,H,W,3G] (conv_fprop(..., sti_win=(ws, shift)) with head-padded weights)
+    -> attention output in natural token order, [B,H,W,c] as an STI (sti_out) or fp32."""
+    _chk(table, "table")
+    B, H, W, g3 = qkv.shape
+    out_sti = STI((B, H, W, c), qkv.device) if sti_out else None
+    if out_sti is not None:
+        out_sti.ones = c % 64 != 0
+    out = None if sti_out else torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device)
+    with _prof("nsr_window_attn_wsti_fwd", (B * H * W, c, heads, ws), 0.0, 4.0 * B * H * W * (g3 + c)):
+        check(_lib.lib().nsr_window_attn_wsti_fwd(qkv.data_ptr(), table.data_ptr(), _p(out), _p(out_sti), B, H, W, c, heads, ws,
+                                                  shift, 1 if shift > 0 else 0, scale, ENGINE[engine or WSTI_ATTN_ENGINE],
+                                                  _stream()), "nsr_window_attn_wsti_fwd")
+    _count(1)
+    return out_sti if sti_out else out
+
+
+def window_attn_bwd_wsti(qkv: STI, table: Tensor, dout: STI, dtable: Tensor, c: int, heads: int, ws: int, shift: int,
+                         scale: float, sti_out: bool = True):
+    """dqkv [B,H,W,3c] in natural token order (STI or fp32) from the window-ordered qkv / dout images; dtable overwritten."""
+    _chk(table, "table"), _chk(dtable, "dtable")
+    B, H, W, g3 = qkv.shape
+    dqkv_sti = STI((B, H, W, 3 * c), qkv.device) if sti_out else None
+    dqkv = None if sti_out else torch.empty((B, H, W, 3 * c), dtype=torch.float32, device=qkv.device)
+    L = _lib.lib()
+    wsb = scratch(L.nsr_window_attn_bwd_workspace(heads, ws), qkv.device)
+    with _prof("nsr_window_attn_wsti_bwd", (B * H * W, c, heads, ws), 0.0, 4.0 * B * H * W * (g3 + g3 // 3 + 3 * c)):
+        check(L.nsr_window_attn_wsti_bwd(qkv.data_ptr(), table.data_ptr(), dout.data_ptr(), _p(dqkv), _p(dqkv_sti),
+                                         dtable.data_ptr(), B, H, W, c, heads, ws, shift, 1 if shift > 0 else 0, scale,
+                                         wsb.data_ptr(), wsb.numel(), _stream()), "nsr_window_attn_wsti_bwd")
+    _count(3)
     return dqkv_sti if sti_out else dqkv
 
 
