@@ -320,10 +320,14 @@ int nsr_window_attn_bwd(const float* qkv, const float* bias_table, const float* 
  * engine: NSR_ENGINE_AUTO / NSR_ENGINE_TCGEN05 = Q K^T and P V as tcgen05.mma with TMEM accumulators (window_attn_tc.cu: one
  * work item = a window pair x a head pair = three 32 KiB operand blocks, softmax by one thread per query row);
  * NSR_ENGINE_MMA_SYNC = the warp-level mma.sync kernels on the same operands.
+ * out_padded (tcgen05 kernel): out_sti is [tokens, G] with every head padded to 32 channels like the operands, so a thread
+ * stores whole 16-byte chunks; channel c/heads of head 0 (a padding slot when c/heads < 32) carries 1.0 - the bias-gradient
+ * column of the proj contraction, which then runs on head-padded weights (K = G).
  */
 int nsr_window_attn_wsti_channels(int heads);
-int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti, int batch, int h, int w,
-                             int c, int heads, int ws, int shift, int use_mask, float scale, int engine, void* stream);
+int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti, int out_padded, int batch,
+                             int h, int w, int c, int heads, int ws, int shift, int use_mask, float scale, int engine,
+                             void* stream);
 int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_table, const void* dout_wsti, float* dqkv, void* dqkv_sti,
                              float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
                              float scale, void* workspace, size_t workspace_bytes, void* stream);

@@ -234,6 +234,7 @@ class swinir(nn.Module):
         # attention operands in window order with heads padded to 32 channels: written that way by the qkv
         # contraction's epilogue and fetched by the attention kernels with bulk copies (NSR_WSTI=0: A/B switch)
         wsti = sti and ops.WSTI_ENABLED and all(ops.wsti_supported(self.embed_dim, h, ws) for h in self.num_heads)
+        wsti_pad = wsti and ops.WSTI_ATTN_ENGINE != "mma_sync"  # tcgen05 attention writes a head-padded output image
 
         def lin(name, t, **kw):
             return ops.conv_fprop(t, ps.pw(name + ".weight"), ps.p(name + ".bias") if ps.has(name + ".bias") else None, **kw)
@@ -272,12 +273,17 @@ class swinir(nn.Module):
                                       row_map=ops.head_pad_map(self.embed_dim, heads, 3), need_dgrad=False)
                     qkv = ops.conv_fprop(ln1, qw, qw.bias_padded, sti_out=True, f32_out=False, sti_win=(ws, blk.shift_size))
                     att = ops.window_attn_fwd_wsti(qkv, ps.p(pre + "attn.relative_position_bias_table"), self.embed_dim,
-                                                   heads, ws, blk.shift_size, scale)
+                                                   heads, ws, blk.shift_size, scale, padded_out=wsti_pad)
                 else:
                     qkv = lin(pre + "attn.qkv", ln1)
                     att = ops.window_attn_fwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), heads, ws,
                                               blk.shift_size, scale, sti_out=sti)
-                x1 = lin(pre + "attn.proj", att, residual=t, row_scale=ds[0] if ds else None)
+                if wsti and wsti_pad:  # head-padded attention output: proj contracts over G channels (zero weight columns)
+                    pwm = ps.pw_mapped(pre + "attn.proj.weight", "proj_cols", None,
+                                       col_map=ops.head_pad_map(self.embed_dim, heads, 1))
+                    x1 = ops.conv_fprop(att, pwm, ps.p(pre + "attn.proj.bias"), residual=t, row_scale=ds[0] if ds else None)
+                else:
+                    x1 = lin(pre + "attn.proj", att, residual=t, row_scale=ds[0] if ds else None)
                 ln2, mu2, rs2 = ops.layernorm_fwd(x1, ps.p(pre + "norm2.weight"), ps.p(pre + "norm2.bias"),
                                                   sti_out=sti, f32_out=not sti)
                 # hpre holds gelu'(fc1 pre-activation): the only thing the backward pass needs of it
@@ -427,9 +433,13 @@ class swinir(nn.Module):
                 g1f = split(g1)[0]
                 gb = scaled(g1, ds[0] if ds else None)
                 if isinstance(qkv, ops.STI):  # window-ordered operands (see engine_forward)
-                    bwd(pre + "attn.proj", att, gb, need_dx=False)
                     pwm = ps.pw_mapped(pre + "attn.proj.weight", "proj_cols", None,
                                        col_map=ops.head_pad_map(self.embed_dim, heads, 1))
+                    if att.shape[-1] != self.embed_dim:  # head-padded attention output
+                        ops.conv_wgrad_mapped(att, split(gb)[1], ps.g(pre + "attn.proj.weight"), ps.g(pre + "attn.proj.bias"),
+                                              pwm.col_map, att.ones_col)
+                    else:
+                        bwd(pre + "attn.proj", att, gb, need_dx=False)
                     datt = ops.conv_fprop(split(gb)[1], pwm, None, dgrad=True, sti_out=True, f32_out=False, sti_win=(ws, shift))
                     dqkv = ops.window_attn_bwd_wsti(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
                                                     ps.g(pre + "attn.relative_position_bias_table"), self.embed_dim, heads,

@@ -249,8 +249,8 @@ int window_attn_wsti_bwd_launch(const void* qkv, const float* table, const void*
                                 float* partial, int gx, int batch, int h, int w, int c, int heads, int ws, int shift,
                                 int use_mask, float scale, cudaStream_t st);
 bool window_attn_tc_supported(int c, int heads, int ws);
-int window_attn_tc_fwd_launch(const void* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w, int c,
-                              int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
+int window_attn_tc_fwd_launch(const void* qkv, const float* table, float* out, void* out_sti, int out_padded, int batch, int h,
+                              int w, int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
 static bool use_mma(int c, int heads, int ws) {
   static int simt_forced = -1;
   if (simt_forced < 0) {
@@ -364,9 +364,9 @@ static int wsti_check(WinGeom& g, int batch, int h, int w, int c, int heads, int
   return NSR_OK;
 }
 
-extern "C" int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti, int batch,
-                                        int h, int w, int c, int heads, int ws, int shift, int use_mask, float scale,
-                                        int engine, void* stream) {
+extern "C" int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti,
+                                        int out_padded, int batch, int h, int w, int c, int heads, int ws, int shift,
+                                        int use_mask, float scale, int engine, void* stream) {
   NSR_CHECK_ARG(qkv_wsti && bias_table && (out || out_sti), "nsr_window_attn_wsti_fwd: null pointer");
   NSR_CHECK_ARG(engine == NSR_ENGINE_AUTO || engine == NSR_ENGINE_TCGEN05 || engine == NSR_ENGINE_MMA_SYNC,
                 "nsr_window_attn_wsti_fwd: engine must be NSR_ENGINE_AUTO, _TCGEN05 or _MMA_SYNC");
@@ -375,9 +375,10 @@ extern "C" int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_
   int rc = wsti_check(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_wsti_fwd");
   if (rc) return rc;
   if (engine != NSR_ENGINE_MMA_SYNC && window_attn_tc_supported(c, heads, ws))
-    return window_attn_tc_fwd_launch(qkv_wsti, bias_table, out, out_sti, batch, h, w, c, heads, ws, shift, use_mask, scale,
-                                     reinterpret_cast<cudaStream_t>(stream));
+    return window_attn_tc_fwd_launch(qkv_wsti, bias_table, out, out_sti, out_padded, batch, h, w, c, heads, ws, shift, use_mask,
+                                     scale, reinterpret_cast<cudaStream_t>(stream));
   NSR_CHECK_ARG(engine != NSR_ENGINE_TCGEN05, "nsr_window_attn_wsti_fwd: shape not supported by the tcgen05 kernel");
+  NSR_CHECK_ARG(!out_padded, "nsr_window_attn_wsti_fwd: the head-padded output image is written by the tcgen05 kernel only");
   return window_attn_wsti_fwd_launch(qkv_wsti, bias_table, out, out_sti, batch, h, w, c, heads, ws, shift, use_mask, scale,
                                      reinterpret_cast<cudaStream_t>(stream));
 }

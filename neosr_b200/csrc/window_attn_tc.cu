@@ -28,16 +28,19 @@
 namespace nsr {
 using namespace tc;
 
-constexpr int AT_THREADS = 320;
+constexpr int AT_THREADS = 576;                   // loader + MMA issuer + 16 softmax warps
 constexpr int AT_BLK = 32768;                      // one STI block: hi image 16 KiB + lo image 16 KiB
-constexpr int AT_SMEM_Q = 0, AT_SMEM_K = AT_BLK, AT_SMEM_V = 2 * AT_BLK, AT_SMEM_P = 3 * AT_BLK;  // P: 2 heads x 32 KiB
-constexpr int AT_SMEM_BAR = 5 * AT_BLK;
+constexpr int AT_SLOTS = 4;                        // operand slots: Q, K, V (even items), V (odd items)
+constexpr int AT_SMEM_P = AT_SLOTS * AT_BLK;       // P tiles: 2 heads x 32 KiB
+constexpr int AT_SMEM_BAR = (AT_SLOTS + 2) * AT_BLK;
+constexpr int AT_SMEM_XCH = AT_SMEM_BAR + 256;     // float2 [2 parities][2 heads][128 rows][2 halves] = 8 KiB
 constexpr int AT_MAX_HEADS = 8;
-constexpr size_t AT_FWD_SMEM = 5 * AT_BLK + 256 + 1024;  // + barriers + alignment slack
+constexpr size_t AT_FWD_SMEM = (AT_SLOTS + 2) * AT_BLK + 256 + 8192 + 1024;  // + barriers + exchange + alignment slack
 
 struct AtGeom {
   int B, H, W, C, heads, ws, shift, use_mask, D, nwh, nww, G, nwin;
   float scale;
+  int pad_out;  // out_sti is [tokens, G]: heads padded to 32 channels (whole 16-byte chunks per thread), 1.0 in channel D
 };
 
 // token index and shift-mask region id of row n (0..63) of window wi (same map as attn_token_map)
@@ -61,7 +64,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 }
 
 struct AtBars {
-  uint64_t qk_full, qk_empty, v_full, v_empty;
+  uint64_t full[AT_SLOTS], empty[AT_SLOTS];
   uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2];
   uint32_t tmem_slot;
 };
@@ -79,17 +82,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) window_attn_tc_fwd_kernel(const
   const int n_wp = (gm.nwin + 1) >> 1, n_hp = (gm.heads + 1) >> 1, kbs = 3 * gm.G / 64;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars->qk_full, 1);
-    mbar_init(&bars->qk_empty, 1);
-    mbar_init(&bars->v_full, 1);
-    mbar_init(&bars->v_empty, 1);
+    for (int i = 0; i < AT_SLOTS; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+    }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&bars->s_full[h], 1);
-      mbar_init(&bars->s_empty[h], 128);
-      mbar_init(&bars->p_full[h], 128);
+      mbar_init(&bars->s_empty[h], 256);
+      mbar_init(&bars->p_full[h], 256);
       mbar_init(&bars->p_empty[h], 1);
       mbar_init(&bars->o_full[h], 1);
-      mbar_init(&bars->o_empty[h], 128);
+      mbar_init(&bars->o_empty[h], 256);
     }
     fence_mbar_init();
   }
@@ -104,19 +107,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) window_attn_tc_fwd_kernel(const
 
   if (warp == 0) {
     // ================================ loader =============================================
+    // Four 32 KiB operand slots: Q and K of the next item (released as soon as its two S products retire, which the MMA
+    // thread issues one item ahead) and a double-buffered V (held until both P V products of its item retire).  Every
+    // block therefore has a whole item's duration to arrive.  (A single V slot - and, worse, a plain ring in consumption
+    // order - exposes the load latency once per item: the kernel then ran at ~5.5 us per item instead of ~1,
+    // profiles/r02_g_ncu_attn_tc_fwd.txt, r02_i.)
     if (lane == 0) {
-      uint32_t ph = 0;
+      int item = 0;
       for (int wp = blockIdx.x; wp < n_wp; wp += gridDim.x) {
         const uint8_t* row = qkv + ((size_t)wp * kbs << 15);
-        for (int hp = 0; hp < n_hp; ++hp) {
-          mbar_wait<64>(&bars->qk_empty, ph ^ 1);
-          mbar_arrive_expect_tx(&bars->qk_full, 2 * AT_BLK);
-          bulk_g2s(smem + AT_SMEM_Q, row + ((size_t)hp << 15), AT_BLK, &bars->qk_full);
-          bulk_g2s(smem + AT_SMEM_K, row + ((size_t)(gm.G / 64 + hp) << 15), AT_BLK, &bars->qk_full);
-          mbar_wait<64>(&bars->v_empty, ph ^ 1);
-          mbar_arrive_expect_tx(&bars->v_full, AT_BLK);
-          bulk_g2s(smem + AT_SMEM_V, row + ((size_t)(2 * gm.G / 64 + hp) << 15), AT_BLK, &bars->v_full);
-          ph ^= 1;
+        for (int hp = 0; hp < n_hp; ++hp, ++item) {
+          const uint32_t par = item & 1, par2 = (item >> 1) & 1;
+          mbar_wait<32>(&bars->empty[0], par ^ 1);
+          mbar_arrive_expect_tx(&bars->full[0], AT_BLK);
+          bulk_g2s(smem, row + ((size_t)hp << 15), AT_BLK, &bars->full[0]);
+          mbar_wait<32>(&bars->empty[1], par ^ 1);
+          mbar_arrive_expect_tx(&bars->full[1], AT_BLK);
+          bulk_g2s(smem + AT_BLK, row + ((size_t)(gm.G / 64 + hp) << 15), AT_BLK, &bars->full[1]);
+          const int vs = 2 + (item & 1);
+          mbar_wait<32>(&bars->empty[vs], par2 ^ 1);
+          mbar_arrive_expect_tx(&bars->full[vs], AT_BLK);
+          bulk_g2s(smem + vs * AT_BLK, row + ((size_t)(2 * gm.G / 64 + hp) << 15), AT_BLK, &bars->full[vs]);
         }
       }
     }
@@ -125,15 +136,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) window_attn_tc_fwd_kernel(const
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);  // S: A, B K-major, N = 128
       constexpr uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);   // O: A K-major (P), B MN-major (V), N = 64
-      const uint32_t sq = smem_u32(smem + AT_SMEM_Q), sk = smem_u32(smem + AT_SMEM_K), sv = smem_u32(smem + AT_SMEM_V);
+      const uint32_t s0 = smem_u32(smem);
       int my_items = 0;
       for (int wp = blockIdx.x; wp < n_wp; wp += gridDim.x) my_items += n_hp;
-      uint32_t ph_s = 0, ph_o = 0;             // parity of the item whose S / P V is being issued (Q K / V stages)
       uint32_t ph_sh[2] = {0, 0}, ph_oh[2] = {0, 0};  // per head: a head beyond `heads` (odd head count) skips its items
       auto head_valid = [&](int item, int h) { return (item % n_hp) * 2 + h < gm.heads; };
       auto issue_s = [&](int item) {
-        mbar_wait(&bars->qk_full, ph_s);
+        mbar_wait(&bars->full[0], item & 1);
+        mbar_wait(&bars->full[1], item & 1);
         tc_fence_after();
+        const uint32_t sq = s0, sk = s0 + AT_BLK;
         for (int h = 0; h < 2; ++h) {
           if (!head_valid(item, h)) continue;
           mbar_wait(&bars->s_empty[h], ph_sh[h] ^ 1);
@@ -150,14 +162,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) window_attn_tc_fwd_kernel(const
           for (int k = 0; k < 2; ++k) umma_bf16(d, a_lo + 2 * k, b_hi + 2 * k, idesc_s, 1);
           umma_commit(&bars->s_full[h]);
         }
-        umma_commit(&bars->qk_empty);  // Q, K smem free once these MMAs retire
-        ph_s ^= 1;
+        umma_commit(&bars->empty[0]);  // Q, K slots free once these MMAs retire
+        umma_commit(&bars->empty[1]);
       };
       if (my_items > 0) issue_s(0);
       for (int item = 0; item < my_items; ++item) {
         if (item + 1 < my_items) issue_s(item + 1);
-        mbar_wait(&bars->v_full, ph_o);
+        const int vs = 2 + (item & 1);
+        mbar_wait(&bars->full[vs], (item >> 1) & 1);
         tc_fence_after();
+        const uint32_t sv = s0 + vs * AT_BLK;
         for (int h = 0; h < 2; ++h) {
           if (!head_valid(item, h)) continue;
           mbar_wait(&bars->p_full[h], ph_oh[h]);
@@ -181,19 +195,24 @@ __global__ void __launch_bounds__(AT_THREADS, 1) window_attn_tc_fwd_kernel(const
           umma_commit(&bars->o_full[h]);
           umma_commit(&bars->p_empty[h]);
         }
-        umma_commit(&bars->v_empty);
-        ph_o ^= 1;
+        umma_commit(&bars->empty[vs]);
       }
     }
   } else {
     // ================================ softmax + epilogue ==================================
-    const int h = (warp - 2) >> 2;          // head A / B of the pair
+    // 16 warps: (head A / B) x (column half 0 / 1) x (TMEM lane quarter).  Two threads share a query row, each owns 32 of
+    // its 64 scores; they merge (max, sum) once per item through shared memory (the flash-attention rescale), so a warp
+    // scheduler has four softmax warps to interleave instead of two.
+    const int cw = warp - 2;
+    const int h = (cw >> 2) & 1;            // head A / B of the pair
+    const int half = cw >> 3;               // which 32 of the row's 64 keys (and which 16 of its 32 output channels)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;            // row of the 128-row item = TMEM lane
     const int win = r >> 6, i = r & 63;     // window of the pair, token within the window
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int base_i = 15 * (i >> 3) + (i & 7) + 112;
+    const int base_i = 15 * (i >> 3) + (i & 7) + 112 - 60 * half;  // keys j = 32 half + jj: 15 (j >> 3) + (j & 7) = 60 half + ...
     const float scale_l2 = gm.scale * 1.4426950408889634f;
+    float2* xch = reinterpret_cast<float2*>(smem + AT_SMEM_XCH);   // [parity][head][row][half] (max, sum) of a half row
     uint32_t ph = 0;
     // epilogue state of the previous item
     bool pend = false;
@@ -202,24 +221,56 @@ __global__ void __launch_bounds__(AT_THREADS, 1) window_attn_tc_fwd_kernel(const
     auto epilogue = [&](uint32_t phase) {
       mbar_wait(&bars->o_full[h], phase);
       tc_fence_after();
-      float o[32];
-      tmem_ld_32x32(lane_addr + 256 + h * 128 + win * 64 + h * 32, o);
+      float o[16];
+      tmem_ld_32x16(lane_addr + 256 + h * 128 + win * 64 + h * 32 + half * 16, o);
       tc_fence_before();
       mbar_arrive(&bars->o_empty[h]);
       if (!pend_valid) return;
       const int kbs_o = (gm.C + 63) / 64;
       const long long tk = pend_tok;
+      const int c0 = half * 16;  // first of this thread's 16 channels within the head
       if (out) {
-        float* dst = out + (size_t)tk * gm.C + pend_head * gm.D;
-        for (int c = 0; c < gm.D; c += 2) *reinterpret_cast<float2*>(dst + c) = make_float2(o[c], o[c + 1]);
+        float* dst = out + (size_t)tk * gm.C + pend_head * gm.D + c0;
+#pragma unroll
+        for (int c = 0; c < 16; c += 2)
+          if (c0 + c < gm.D) *reinterpret_cast<float2*>(dst + c) = make_float2(o[c], o[c + 1]);
       }
-      if (out_sti) {
+      if (out_sti && gm.pad_out) {
+        // head-padded image [tokens, G]: this thread's 16 channels are two whole 16-byte chunks of the token's row in
+        // block `head / 2`; channel D of head 0 carries 1.0 (bias-gradient column of proj's wgrad), other padding is 0
+        if (pend_head == 0) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c0 + c == gm.D) o[c] = 1.f;
+        }
+        uint8_t* rb = out_sti + ((size_t)((tk >> 7) * (gm.G / 64) + (pend_head >> 1)) << 15) + (size_t)(tk & 127) * 128;
+        const int r7 = (int)(tk & 7);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint4 hi, lo;
+          split_pair(o[8 * j], o[8 * j + 1], hi.x, lo.x);
+          split_pair(o[8 * j + 2], o[8 * j + 3], hi.y, lo.y);
+          split_pair(o[8 * j + 4], o[8 * j + 5], hi.z, lo.z);
+          split_pair(o[8 * j + 6], o[8 * j + 7], hi.w, lo.w);
+          const int off = ((h * 4 + half * 2 + j) ^ r7) << 4;
+          *reinterpret_cast<uint4*>(rb + off) = hi;
+          *reinterpret_cast<uint4*>(rb + 16384 + off) = lo;
+        }
+        if (pend_last && (gm.heads & 1)) {  // odd head count: the second half of the last block is padding
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int off = ((4 + half * 2 + j) ^ r7) << 4;
+            *reinterpret_cast<uint4*>(rb + off) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(rb + 16384 + off) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      } else if (out_sti) {
         uint8_t* rb = out_sti + ((size_t)((tk >> 7) * kbs_o) << 15) + (size_t)(tk & 127) * 128;
         const int r7 = (int)(tk & 7);
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          if (c < gm.D) {
-            const int cidx = pend_head * gm.D + c, cc = cidx & 63;
+        for (int c = 0; c < 16; c += 2) {
+          if (c0 + c < gm.D) {
+            const int cidx = pend_head * gm.D + c0 + c, cc = cidx & 63;
             uint32_t hi, lo;
             split_pair(o[c], o[c + 1], hi, lo);
             uint8_t* dst = rb + ((size_t)(cidx >> 6) << 15) + ((((cc >> 3) ^ r7) << 4) + (cc & 7) * 2);
@@ -227,7 +278,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) window_attn_tc_fwd_kernel(const
             *reinterpret_cast<uint32_t*>(dst + 16384) = lo;
           }
         }
-        if (pend_last) {  // channel padding [C, kbs*64): 1.0 in channel C (bias-gradient column of proj's wgrad), zeros after
+        if (pend_last && half == 1) {  // channel padding [C, kbs*64): 1.0 in channel C (bias-gradient column), zeros after
           for (int cidx = gm.C; cidx < kbs_o * 64; cidx += 2) {
             const int cc = cidx & 63;
             uint32_t hi, lo;
@@ -244,60 +295,61 @@ __global__ void __launch_bounds__(AT_THREADS, 1) window_attn_tc_fwd_kernel(const
       const bool row_valid = wi < gm.nwin;
       int tok = 0, rid = 0;
       if (row_valid) at_token_map(gm, wi, i, tok, rid);
-      named_bar_sync(1, 256);  // every softmax thread is done with the previous pair's region ids
-      if (h == 0) rid_s[r] = rid;
-      named_bar_sync(1, 256);
-      bool masked = false;  // does any key of this row's window lie in another shift-mask region?
+      named_bar_sync(1, 512);  // every softmax thread is done with the previous pair's region ids
+      if (h == 0 && half == 0) rid_s[r] = rid;
+      named_bar_sync(1, 512);
+      bool masked = false;  // does any of this thread's keys lie in another shift-mask region than its query?
       if (gm.use_mask && gm.shift > 0) {
-        for (int j = 0; j < 64; ++j) masked |= rid_s[win * 64 + j] != rid;
+        for (int j = 0; j < 32; ++j) masked |= rid_s[win * 64 + half * 32 + j] != rid;
       }
       for (int hp = 0; hp < n_hp; ++hp) {
         const int head = hp * 2 + h;
         if (head < gm.heads) {
-          // ---- scores of this item
+          // ---- this thread's 32 scores of the item
           mbar_wait(&bars->s_full[h], ph);
           tc_fence_after();
-          float s[64];
-          {
-            float a[32], b[32];
-            tmem_ld_32x32(lane_addr + h * 128 + win * 64, a);
-            tmem_ld_32x32(lane_addr + h * 128 + win * 64 + 32, b);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { s[j] = a[j]; s[32 + j] = b[j]; }
-          }
+          float s[32];
+          tmem_ld_32x32(lane_addr + h * 128 + win * 64 + half * 32, s);
           tc_fence_before();
           mbar_arrive(&bars->s_empty[h]);
           const float* bt = bias_s + head * 225 + base_i;
-          float m = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            s[j] = fmaf(s[j], scale_l2, bt[-(15 * (j >> 3) + (j & 7))]);
-          }
+          for (int j = 0; j < 32; ++j) s[j] = fmaf(s[j], scale_l2, bt[-(15 * (j >> 3) + (j & 7))]);
           if (masked) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (rid_s[win * 64 + j] != rid) s[j] += -100.0f * 1.4426950408889634f;
+            for (int j = 0; j < 32; ++j)
+              if (rid_s[win * 64 + half * 32 + j] != rid) s[j] += -100.0f * 1.4426950408889634f;
           }
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four chains: the adds / maxes are 4 cycles deep
 #pragma unroll
-          for (int j = 0; j < 64; ++j) m = fmaxf(m, s[j]);
-          float sum = 0.f;
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+          const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            s[j] = exp2f(s[j] - m);
-            sum += s[j];
+          for (int j = 0; j < 32; ++j) {
+            s[j] = ex2_approx(s[j] - m);
+            l4[j & 3] += s[j];
           }
-          const float inv = 1.f / sum;
+          const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+          // merge with the other half of the row: P = e * 2^(m - M) / (l 2^(m - M) + l' 2^(m' - M)), M = max(m, m')
+          float2* xs = xch + (((ph & 1) * 2 + h) * 128 + r) * 2;
+          xs[half] = make_float2(m, l);
+          named_bar_sync(2 + h, 256);
+          const float2 ot = xs[half ^ 1];
+          const float M = fmaxf(m, ot.x);
+          const float f = ex2_approx(m - M);
+          const float inv = f / fmaf(l, f, ot.y * ex2_approx(ot.x - M));
           // ---- P -> the K-major A tile of P V (previous item's P V must have retired)
           mbar_wait(&bars->p_empty[h], ph ^ 1);
           uint8_t* prow = smem + AT_SMEM_P + h * AT_BLK + r * 128;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < 4; ++c) {
             uint4 hi, lo;
             split_pair(s[8 * c] * inv, s[8 * c + 1] * inv, hi.x, lo.x);
             split_pair(s[8 * c + 2] * inv, s[8 * c + 3] * inv, hi.y, lo.y);
             split_pair(s[8 * c + 4] * inv, s[8 * c + 5] * inv, hi.z, lo.z);
             split_pair(s[8 * c + 6] * inv, s[8 * c + 7] * inv, hi.w, lo.w);
-            const int off = (c ^ (r & 7)) << 4;
+            const int off = ((half * 4 + c) ^ (r & 7)) << 4;
             *reinterpret_cast<uint4*>(prow + off) = hi;
             *reinterpret_cast<uint4*>(prow + 16384 + off) = lo;
           }
@@ -330,8 +382,8 @@ bool window_attn_tc_supported(int c, int heads, int ws) {
   return ws == 8 && d <= 32 && d % 2 == 0 && heads <= AT_MAX_HEADS && nsr_device_supports_tcgen05();
 }
 
-int window_attn_tc_fwd_launch(const void* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w, int c,
-                              int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st) {
+int window_attn_tc_fwd_launch(const void* qkv, const float* table, float* out, void* out_sti, int out_padded, int batch, int h,
+                              int w, int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(window_attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_FWD_SMEM);
@@ -342,7 +394,7 @@ int window_attn_tc_fwd_launch(const void* qkv, const float* table, float* out, v
     attr = true;
   }
   AtGeom g{batch, h, w, c, heads, ws, shift, use_mask, c / heads, h / ws, w / ws, (heads * 32 + 63) / 64 * 64,
-           batch * (h / ws) * (w / ws), scale};
+           batch * (h / ws) * (w / ws), scale, out_padded};
   const int n_wp = (g.nwin + 1) / 2;
   const int grid = n_wp < kNumSMs ? n_wp : kNumSMs;
   window_attn_tc_fwd_kernel<<<grid, AT_THREADS, AT_FWD_SMEM, st>>>(reinterpret_cast<const uint8_t*>(qkv), table, out,

@@ -380,6 +380,58 @@ def conv_wgrad(x, dy, dw: Tensor, dbias: Tensor | None, kh: int, kw: int, engine
     _count(3 if fused_bias else (4 if dbias is not None else 2))
 
 
+def conv_wgrad_mapped(x_sti: STI, dy_sti: STI, dw: Tensor, dbias: Tensor | None, col_map: Tensor, ones_col: int | None):
+    """Weight gradient of a Linear whose INPUT image is head-padded (x_sti: [.., G] channels, `col_map[k]` = the real
+    input channel of padded channel k or -1): dW over the padded channels on the tcgen05 wgrad kernel, then un-padded
+    into dw [cout, cin]; dbias = the column of the channel that carries 1.0 (`ones_col`)."""
+    _chk(dw, "dw"), _chk(dbias, "dbias")
+    B, H, W, G = x_sti.shape
+    cout, cin = dw.shape[0], dw.shape[1]
+    tmp = torch.empty((cout, G), dtype=torch.float32, device=dw.device)
+    d = NsrWgrad(batch=B, h=H, w=W, cin=G, cout=cout, kh=1, kw=1, pad=0, x_ld=G, dy_ld=cout, engine=ENGINE["auto"], x=None,
+                 dy=None, dw=tmp.data_ptr(), dbias=None, workspace=None, workspace_bytes=0, x_sti=x_sti.data_ptr(),
+                 dy_sti=dy_sti.data_ptr())
+    L = _lib.lib()
+    ws = scratch(L.nsr_conv_wgrad_workspace(C.byref(d)), dw.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    M = B * H * W
+    with _prof("conv_wgrad_sti", (M, G, cout, 1), 2.0 * M * G * cout, 4.0 * M * (G + cout)):
+        check(L.nsr_conv_wgrad(C.byref(d), _stream()), "nsr_conv_wgrad")
+        inv = _inverse_map(col_map, cin)
+        check(L.nsr_gather2d(tmp.data_ptr(), G, None, inv.data_ptr(), dw.data_ptr(), cout, cin, _stream()), "nsr_gather2d")
+        if dbias is not None:
+            if ones_col is None:
+                raise ValueError("conv_wgrad_mapped: the image carries no ones column for the bias gradient")
+            oc = _const_i32((ones_col,), dw.device)
+            check(L.nsr_gather2d(tmp.data_ptr(), G, None, oc.data_ptr(), dbias.data_ptr(), cout, 1, _stream()), "nsr_gather2d")
+    _count(4 if dbias is not None else 3)
+
+
+_I32_CACHE: dict = {}
+
+
+def _const_i32(vals: tuple, device) -> Tensor:
+    key = (vals, str(device))
+    t = _I32_CACHE.get(key)
+    if t is None:
+        t = _I32_CACHE[key] = torch.tensor(vals, dtype=torch.int32, device=device)
+    return t
+
+
+def _inverse_map(col_map: Tensor, n: int) -> Tensor:
+    """padded index of every real channel (col_map: padded -> real or -1), cached per map tensor."""
+    key = ("inv", col_map.data_ptr(), n)
+    t = _I32_CACHE.get(key)
+    if t is None:
+        m = col_map.tolist()
+        inv = [0] * n
+        for k, c in enumerate(m):
+            if c >= 0:
+                inv[c] = k
+        t = _I32_CACHE[key] = torch.tensor(inv, dtype=torch.int32, device=col_map.device)
+    return t
+
+
 # ----------------------------------------------------------------------------- layout
 def nchw_to_nhwc_affine(x: Tensor, scale: Tensor | None, shift: Tensor | None) -> Tensor:
     _chk(x, "x")
@@ -768,25 +820,27 @@ def window_attn_bwd(qkv: Tensor, table: Tensor, dout: Tensor, dtable: Tensor, he
 
 
 def window_attn_fwd_wsti(qkv: STI, table: Tensor, c: int, heads: int, ws: int, shift: int, scale: float,
-                         sti_out: bool = True, engine: str | None = None):
+                         sti_out: bool = True, engine: str | None = None, padded_out: bool = False):
     """qkv: window-ordered, head-padded STI [B,H,W,3G] (conv_fprop(..., sti_win=(ws, shift)) with head-padded weights)
-    -> attention output in natural token order, [B,H,W,c] as an STI (sti_out) or fp32."""
+    -> attention output in natural token order, [B,H,W,c] as an STI (sti_out) or fp32.  padded_out: the STI is
+    [B,H,W,G] with heads padded to 32 channels (tcgen05 kernel; `ones_col` = the channel that carries 1.0, or None)."""
     _chk(table, "table")
     B, H, W, g3 = qkv.shape
-    out_sti = STI((B, H, W, c), qkv.device) if sti_out else None
+    out_sti = STI((B, H, W, g3 // 3 if padded_out else c), qkv.device) if sti_out else None
     if out_sti is not None:
-        out_sti.ones = c % 64 != 0
+        out_sti.ones = (not padded_out) and c % 64 != 0
+        out_sti.ones_col = (c // heads if c // heads < 32 else None) if padded_out else None
     out = None if sti_out else torch.empty((B, H, W, c), dtype=torch.float32, device=qkv.device)
     with _prof("nsr_window_attn_wsti_fwd", (B * H * W, c, heads, ws), 0.0, 4.0 * B * H * W * (g3 + c)):
-        check(_lib.lib().nsr_window_attn_wsti_fwd(qkv.data_ptr(), table.data_ptr(), _p(out), _p(out_sti), B, H, W, c, heads, ws,
-                                                  shift, 1 if shift > 0 else 0, scale, ENGINE[engine or WSTI_ATTN_ENGINE],
-                                                  _stream()), "nsr_window_attn_wsti_fwd")
+        check(_lib.lib().nsr_window_attn_wsti_fwd(qkv.data_ptr(), table.data_ptr(), _p(out), _p(out_sti), int(padded_out), B, H,
+                                                  W, c, heads, ws, shift, 1 if shift > 0 else 0, scale,
+                                                  ENGINE[engine or WSTI_ATTN_ENGINE], _stream()), "nsr_window_attn_wsti_fwd")
     _count(1)
     return out_sti if sti_out else out
 
 
 def window_attn_bwd_wsti(qkv: STI, table: Tensor, dout: STI, dtable: Tensor, c: int, heads: int, ws: int, shift: int,
-                         scale: float, sti_out: bool = True):
+                         scale: float, sti_out: bool = True, engine: str | None = None):
     """dqkv [B,H,W,3c] in natural token order (STI or fp32) from the window-ordered qkv / dout images; dtable overwritten."""
     _chk(table, "table"), _chk(dtable, "dtable")
     B, H, W, g3 = qkv.shape

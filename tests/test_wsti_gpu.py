@@ -76,6 +76,27 @@ def test_wsti_attention_forward_backward(case, engine):
 
     assert rel(att_w, att) < 1e-4
     assert rel(att_s.to_f32(), att) < 1e-4
+    if engine == "tcgen05":  # head-padded output image: heads at 32-channel slots, 1.0 in head 0's first padding slot
+        att_p = ops.window_attn_fwd_wsti(qkv_w, table, C, heads, ws, shift, scale, sti_out=True, engine=engine, padded_out=True)
+        assert att_p.shape == (B, H, W, G) and att_p.ones_col == C // heads
+        full = att_p.to_f32()
+        m = torch.tensor(ops.head_pad_map(C, heads, 1), device="cuda")
+        assert rel(full[..., m >= 0], att) < 1e-4
+        pad = full[..., m < 0]
+        assert torch.equal(pad[..., 0], torch.ones_like(pad[..., 0])) and float(pad[..., 1:].abs().max()) == 0.0
+        # proj on the padded image: fprop over G channels with zero weight columns, wgrad un-padded, dbias from the ones column
+        wp = (torch.randn(C, C, generator=torch.Generator().manual_seed(13)) * C ** -0.5).cuda()
+        bp = torch.randn(C, generator=torch.Generator().manual_seed(14)).cuda()
+        pwm = ops.MappedPackedWeight(wp, None, col_map=ops.head_pad_map(C, heads, 1)).refresh()
+        y_pad = ops.conv_fprop(att_p, pwm, bp)
+        y_ref = ops.conv_fprop(att_s, ops.PackedWeight(wp).refresh(), bp)
+        assert rel(y_pad, y_ref) < 2e-5
+        gsti = ops.STI.from_f32(dout)
+        dw, db = torch.zeros_like(wp), torch.zeros_like(bp)
+        ops.conv_wgrad_mapped(att_p, gsti, dw, db, pwm.col_map, att_p.ones_col)
+        dw_ref, db_ref = torch.zeros_like(wp), torch.zeros_like(bp)
+        ops.conv_wgrad(None, None, dw_ref, db_ref, 1, 1, x_sti=att_s, dy_sti=gsti)
+        assert rel(dw, dw_ref) < 2e-5 and rel(db, db_ref) < 2e-5
     if C % 64:  # first padding channel of the image = 1.0 (bias-gradient column of proj's wgrad), the rest 0
         kb = (C + 63) // 64 * 64
         raw = torch.empty(B, H, W, kb, device="cuda")
