@@ -328,9 +328,12 @@ int nsr_window_attn_wsti_channels(int heads);
 int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, float* out, void* out_sti, int out_padded, int batch,
                              int h, int w, int c, int heads, int ws, int shift, int use_mask, float scale, int engine,
                              void* stream);
+/* dqkv_padded (tcgen05 kernel): dqkv_sti is [tokens, 3G] in token order with heads padded to 32 channels (q | k | v groups of
+ * G), stored 16 bytes at a time; the qkv dgrad / wgrad contractions then run on the head-padded weights.  The workspace
+ * must hold (max(nsr_window_attn_bwd_workspace)) bytes as for nsr_window_attn_bwd. */
 int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_table, const void* dout_wsti, float* dqkv, void* dqkv_sti,
-                             float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask,
-                             float scale, void* workspace, size_t workspace_bytes, void* stream);
+                             int dqkv_padded, float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int shift,
+                             int use_mask, float scale, int engine, void* workspace, size_t workspace_bytes, void* stream);
 /* dst[r][c] = src[row_map[r]][col_map[c]]; NULL map = identity, negative entry = 0 (head-padded weight / bias copies). */
 int nsr_gather2d(const float* src, int src_ld, const int* row_map, const int* col_map, float* dst, int rows, int cols,
                  void* stream);

@@ -125,7 +125,7 @@ SIGNATURES = {
     "nsr_window_attn_bwd_workspace": (_z, [_i, _i]),
     "nsr_window_attn_wsti_channels": (_i, [_i]),
     "nsr_window_attn_wsti_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
-    "nsr_window_attn_wsti_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _z, _p]),
+    "nsr_window_attn_wsti_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _z, _p]),
     "nsr_gather2d": (_i, [_p, _i, _p, _p, _p, _i, _i, _p]),
     "nsr_window_attn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _z, _p, _p]),
     "nsr_loss_workspace": (_z, []),

@@ -270,7 +270,7 @@ class swinir(nn.Module):
                                                   sti_out=sti, f32_out=not sti)
                 if wsti:
                     qw = ps.pw_mapped(pre + "attn.qkv.weight", "qkv_rows", pre + "attn.qkv.bias",
-                                      row_map=ops.head_pad_map(self.embed_dim, heads, 3), need_dgrad=False)
+                                      row_map=ops.head_pad_map(self.embed_dim, heads, 3))
                     qkv = ops.conv_fprop(ln1, qw, qw.bias_padded, sti_out=True, f32_out=False, sti_win=(ws, blk.shift_size))
                     att = ops.window_attn_fwd_wsti(qkv, ps.p(pre + "attn.relative_position_bias_table"), self.embed_dim,
                                                    heads, ws, blk.shift_size, scale, padded_out=wsti_pad)
@@ -441,15 +441,24 @@ class swinir(nn.Module):
                     else:
                         bwd(pre + "attn.proj", att, gb, need_dx=False)
                     datt = ops.conv_fprop(split(gb)[1], pwm, None, dgrad=True, sti_out=True, f32_out=False, sti_win=(ws, shift))
+                    pad = att.shape[-1] != self.embed_dim  # tcgen05 attention kernels: head-padded images throughout
                     dqkv = ops.window_attn_bwd_wsti(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
                                                     ps.g(pre + "attn.relative_position_bias_table"), self.embed_dim, heads,
-                                                    ws, shift, scale)
+                                                    ws, shift, scale, padded_out=pad)
+                    if pad:  # qkv wgrad / dgrad on the head-padded dqkv image
+                        qw = ps.pw_mapped(pre + "attn.qkv.weight", "qkv_rows", pre + "attn.qkv.bias",
+                                          row_map=ops.head_pad_map(self.embed_dim, heads, 3))
+                        ops.conv_wgrad_mapped_rows(split(ln1)[1], dqkv, ps.g(pre + "attn.qkv.weight"),
+                                                   ps.g(pre + "attn.qkv.bias") if ps.has(pre + "attn.qkv.bias") else None,
+                                                   qw.row_map)
+                        dln1 = ops.conv_fprop(dqkv, qw, None, dgrad=True)
                 else:
                     datt = bwd(pre + "attn.proj", att, gb)
                     dqkv = ops.window_attn_bwd(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
                                                ps.g(pre + "attn.relative_position_bias_table"), heads, ws, shift, scale,
                                                sti_out=sti)
-                dln1 = bwd(pre + "attn.qkv", ln1, dqkv)
+                if not (isinstance(qkv, ops.STI) and att.shape[-1] != self.embed_dim):
+                    dln1 = bwd(pre + "attn.qkv", ln1, dqkv)
                 g = ops.layernorm_bwd(dln1, t0, ps.p(pre + "norm1.weight"), mu1, rs1, ps.g(pre + "norm1.weight"),
                                       ps.g(pre + "norm1.bias"), dres=g1f, sti_out=sti and bi > 0)
             g = ops.axpby(split(g)[0], 1.0, dinp, 1.0)

@@ -251,6 +251,10 @@ int window_attn_wsti_bwd_launch(const void* qkv, const float* table, const void*
 bool window_attn_tc_supported(int c, int heads, int ws);
 int window_attn_tc_fwd_launch(const void* qkv, const float* table, float* out, void* out_sti, int out_padded, int batch, int h,
                               int w, int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
+int window_attn_tc_bwd_gx(int heads);
+int window_attn_tc_bwd_launch(const void* qkv, const float* table, const void* dout, float* dqkv, void* dqkv_sti, float* partial,
+                              int gx, int batch, int h, int w, int c, int heads, int ws, int shift, int use_mask, float scale,
+                              cudaStream_t st);
 static bool use_mma(int c, int heads, int ws) {
   static int simt_forced = -1;
   if (simt_forced < 0) {
@@ -384,17 +388,25 @@ extern "C" int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_
 }
 
 extern "C" int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_table, const void* dout_wsti, float* dqkv,
-                                        void* dqkv_sti, float* dbias_table, int batch, int h, int w, int c, int heads, int ws,
-                                        int shift, int use_mask, float scale, void* workspace, size_t workspace_bytes,
-                                        void* stream) {
+                                        void* dqkv_sti, int dqkv_padded, float* dbias_table, int batch, int h, int w, int c,
+                                        int heads, int ws, int shift, int use_mask, float scale, int engine, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
   NSR_CHECK_ARG(qkv_wsti && bias_table && dout_wsti && (dqkv || dqkv_sti) && dbias_table, "nsr_window_attn_wsti_bwd: null pointer");
+  NSR_CHECK_ARG(engine == NSR_ENGINE_AUTO || engine == NSR_ENGINE_TCGEN05 || engine == NSR_ENGINE_MMA_SYNC,
+                "nsr_window_attn_wsti_bwd: engine must be NSR_ENGINE_AUTO, _TCGEN05 or _MMA_SYNC");
   NSR_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv_wsti) | reinterpret_cast<uintptr_t>(dout_wsti)) & 15) == 0,
                 "nsr_window_attn_wsti_bwd: images must be 16-byte aligned");
   WinGeom g;
   int rc = wsti_check(g, batch, h, w, c, heads, ws, shift, use_mask, scale, "nsr_window_attn_wsti_bwd");
   if (rc) return rc;
   const int nwin = batch * g.nwh * g.nww;
-  const int gx = bwd_gx(nwin, heads, true);
+  // tcgen05 kernel: needs the head-padded dqkv image (16-byte stores); the mma.sync kernel writes the compact one
+  const bool tc_ok = window_attn_tc_supported(c, heads, ws) && (dqkv_sti == nullptr || dqkv_padded);
+  const bool use_tc = engine != NSR_ENGINE_MMA_SYNC && tc_ok;
+  NSR_CHECK_ARG(use_tc || engine != NSR_ENGINE_TCGEN05,
+                "nsr_window_attn_wsti_bwd: the tcgen05 kernel needs a supported shape and dqkv_padded = 1");
+  NSR_CHECK_ARG(use_tc || !dqkv_padded, "nsr_window_attn_wsti_bwd: the head-padded dqkv image is written by the tcgen05 kernel only");
+  const int gx = use_tc ? window_attn_tc_bwd_gx(heads) : bwd_gx(nwin, heads, true);
   const size_t need = (size_t)(gx + 1) * heads * WA_N * WA_N * sizeof(float);
   if (!workspace || workspace_bytes < need) {
     set_error("nsr_window_attn_wsti_bwd: workspace %zu < %zu", workspace_bytes, need);
@@ -402,8 +414,12 @@ extern "C" int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* partial = reinterpret_cast<float*>(workspace);
-  rc = window_attn_wsti_bwd_launch(qkv_wsti, bias_table, dout_wsti, dqkv, dqkv_sti, partial, gx, batch, h, w, c, heads, ws,
-                                   shift, use_mask, scale, st);
+  if (use_tc)
+    rc = window_attn_tc_bwd_launch(qkv_wsti, bias_table, dout_wsti, dqkv, dqkv_sti, partial, gx, batch, h, w, c, heads, ws, shift,
+                                   use_mask, scale, st);
+  else
+    rc = window_attn_wsti_bwd_launch(qkv_wsti, bias_table, dout_wsti, dqkv, dqkv_sti, partial, gx, batch, h, w, c, heads, ws,
+                                     shift, use_mask, scale, st);
   if (rc) return rc;
   float* dssum = partial + (size_t)gx * heads * WA_N * WA_N;
   window_attn_dbias_sum<<<ceil_div(heads * WA_N * WA_N, 256), 256, 0, st>>>(partial, dssum, gx, heads);

@@ -22,46 +22,17 @@
 //   warps 2-5  head A, 6-9 head B: softmax of item i, then the epilogue (O -> split tile image in token order) of
 //                            item i-1, whose P V ran meanwhile
 // TMEM: S_A, S_B (2 x 128 columns) + O_A, O_B (2 x (D1 | D2) = 2 x 128) = 512 columns.
-#include "attn_mma.cuh"
-#include "tc_common.cuh"
+#include "attn_tc.cuh"
 
 namespace nsr {
 using namespace tc;
 
 constexpr int AT_THREADS = 576;                   // loader + MMA issuer + 16 softmax warps
-constexpr int AT_BLK = 32768;                      // one STI block: hi image 16 KiB + lo image 16 KiB
 constexpr int AT_SLOTS = 4;                        // operand slots: Q, K, V (even items), V (odd items)
 constexpr int AT_SMEM_P = AT_SLOTS * AT_BLK;       // P tiles: 2 heads x 32 KiB
 constexpr int AT_SMEM_BAR = (AT_SLOTS + 2) * AT_BLK;
 constexpr int AT_SMEM_XCH = AT_SMEM_BAR + 256;     // float2 [2 parities][2 heads][128 rows][2 halves] = 8 KiB
-constexpr int AT_MAX_HEADS = 8;
 constexpr size_t AT_FWD_SMEM = (AT_SLOTS + 2) * AT_BLK + 256 + 8192 + 1024;  // + barriers + exchange + alignment slack
-
-struct AtGeom {
-  int B, H, W, C, heads, ws, shift, use_mask, D, nwh, nww, G, nwin;
-  float scale;
-  int pad_out;  // out_sti is [tokens, G]: heads padded to 32 channels (whole 16-byte chunks per thread), 1.0 in channel D
-};
-
-// token index and shift-mask region id of row n (0..63) of window wi (same map as attn_token_map)
-__device__ __forceinline__ void at_token_map(const AtGeom& g, int wi, int n, int& tok, int& rid) {
-  const int per = g.nwh * g.nww;
-  const int b = wi / per, rem = wi - b * per;
-  const int wy = rem / g.nww, wx = rem - wy * g.nww;
-  const int iy = n >> 3, ix = n & 7;
-  const int hs = wy * 8 + iy, wsx = wx * 8 + ix;
-  int ho = hs + g.shift, wo = wsx + g.shift;
-  if (ho >= g.H) ho -= g.H;
-  if (wo >= g.W) wo -= g.W;
-  tok = (b * g.H + ho) * g.W + wo;
-  const int rh = hs < g.H - 8 ? 0 : (hs < g.H - g.shift ? 1 : 2);
-  const int rw = wsx < g.W - 8 ? 0 : (wsx < g.W - g.shift ? 1 : 2);
-  rid = rh * 3 + rw;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 struct AtBars {
   uint64_t full[AT_SLOTS], empty[AT_SLOTS];

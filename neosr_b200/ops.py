@@ -407,6 +407,37 @@ def conv_wgrad_mapped(x_sti: STI, dy_sti: STI, dw: Tensor, dbias: Tensor | None,
     _count(4 if dbias is not None else 3)
 
 
+def conv_wgrad_mapped_rows(x_sti: STI, dy_sti: STI, dw: Tensor, dbias: Tensor | None, row_map: Tensor):
+    """Weight gradient of a Linear whose OUTPUT-gradient image is head-padded (dy_sti: [.., Gout] channels, `row_map[n']` =
+    the real output channel of padded channel n' or -1): dW over the padded rows on the tcgen05 wgrad kernel (bias gradient
+    from the ones column of x_sti), then the real rows are gathered into dw [cout, cin] / dbias [cout]."""
+    _chk(dw, "dw"), _chk(dbias, "dbias")
+    B, H, W, cin = x_sti.shape
+    gout = dy_sti.shape[-1]
+    cout = dw.shape[0]
+    fused = dbias is not None and x_sti.ones and cin % 64 != 0 and cin + 4 <= (cin + 63) // 64 * 64
+    if dbias is not None and not fused:
+        raise ValueError("conv_wgrad_mapped_rows: the input image carries no ones column for the bias gradient")
+    cw = cin + 4 if fused else cin
+    tmp = torch.empty((gout, cw), dtype=torch.float32, device=dw.device)
+    d = NsrWgrad(batch=B, h=H, w=W, cin=cw, cout=gout, kh=1, kw=1, pad=0, x_ld=cw, dy_ld=gout, engine=ENGINE["auto"], x=None,
+                 dy=None, dw=tmp.data_ptr(), dbias=None, workspace=None, workspace_bytes=0, x_sti=x_sti.data_ptr(),
+                 dy_sti=dy_sti.data_ptr())
+    L = _lib.lib()
+    ws = scratch(L.nsr_conv_wgrad_workspace(C.byref(d)), dw.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    M = B * H * W
+    with _prof("conv_wgrad_sti", (M, cin, gout, 1), 2.0 * M * cin * gout, 4.0 * M * (cin + gout)):
+        check(L.nsr_conv_wgrad(C.byref(d), _stream()), "nsr_conv_wgrad")
+        inv = _inverse_map(row_map, cout)
+        check(L.nsr_gather2d(tmp.data_ptr(), cw, inv.data_ptr(), None, dw.data_ptr(), cout, cin, _stream()), "nsr_gather2d")
+        if dbias is not None:
+            oc = _const_i32((cin,), dw.device)
+            check(L.nsr_gather2d(tmp.data_ptr(), cw, inv.data_ptr(), oc.data_ptr(), dbias.data_ptr(), cout, 1, _stream()),
+                  "nsr_gather2d")
+    _count(4 if dbias is not None else 3)
+
+
 _I32_CACHE: dict = {}
 
 
@@ -840,18 +871,20 @@ def window_attn_fwd_wsti(qkv: STI, table: Tensor, c: int, heads: int, ws: int, s
 
 
 def window_attn_bwd_wsti(qkv: STI, table: Tensor, dout: STI, dtable: Tensor, c: int, heads: int, ws: int, shift: int,
-                         scale: float, sti_out: bool = True, engine: str | None = None):
-    """dqkv [B,H,W,3c] in natural token order (STI or fp32) from the window-ordered qkv / dout images; dtable overwritten."""
+                         scale: float, sti_out: bool = True, engine: str | None = None, padded_out: bool = False):
+    """dqkv in natural token order from the window-ordered qkv / dout images; dtable overwritten.  STI [B,H,W,3c]
+    (or [B,H,W,3G] head-padded when padded_out: tcgen05 kernel) or fp32 [B,H,W,3c]."""
     _chk(table, "table"), _chk(dtable, "dtable")
     B, H, W, g3 = qkv.shape
-    dqkv_sti = STI((B, H, W, 3 * c), qkv.device) if sti_out else None
+    dqkv_sti = STI((B, H, W, g3 if padded_out else 3 * c), qkv.device) if sti_out else None
     dqkv = None if sti_out else torch.empty((B, H, W, 3 * c), dtype=torch.float32, device=qkv.device)
     L = _lib.lib()
     wsb = scratch(L.nsr_window_attn_bwd_workspace(heads, ws), qkv.device)
     with _prof("nsr_window_attn_wsti_bwd", (B * H * W, c, heads, ws), 0.0, 4.0 * B * H * W * (g3 + g3 // 3 + 3 * c)):
         check(L.nsr_window_attn_wsti_bwd(qkv.data_ptr(), table.data_ptr(), dout.data_ptr(), _p(dqkv), _p(dqkv_sti),
-                                         dtable.data_ptr(), B, H, W, c, heads, ws, shift, 1 if shift > 0 else 0, scale,
-                                         wsb.data_ptr(), wsb.numel(), _stream()), "nsr_window_attn_wsti_bwd")
+                                         int(padded_out and sti_out), dtable.data_ptr(), B, H, W, c, heads, ws, shift,
+                                         1 if shift > 0 else 0, scale, ENGINE[engine or WSTI_ATTN_ENGINE], wsb.data_ptr(),
+                                         wsb.numel(), _stream()), "nsr_window_attn_wsti_bwd")
     _count(3)
     return dqkv_sti if sti_out else dqkv
 

@@ -71,8 +71,28 @@ def test_wsti_attention_forward_backward(case, engine):
     dout_w = ops.conv_fprop(ops.STI.from_f32(dout), pw, None, dgrad=True, sti_out=True, f32_out=False, sti_win=(ws, shift))
     assert dout_w.shape == (B, H, W, G)
     dtab_w = torch.zeros_like(table)
-    dqkv_w = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, dtab_w, C, heads, ws, shift, scale, sti_out=False)
-    dqkv_s = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, torch.zeros_like(table), C, heads, ws, shift, scale, sti_out=True)
+    dqkv_w = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, dtab_w, C, heads, ws, shift, scale, sti_out=False, engine=engine)
+    if engine == "tcgen05":  # head-padded dqkv image [.., 3G]: real channels at the padded slots, zeros elsewhere
+        dq_p = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, torch.zeros_like(table), C, heads, ws, shift, scale, sti_out=True,
+                                        engine=engine, padded_out=True)
+        assert dq_p.shape == (B, H, W, 3 * G)
+        full = dq_p.to_f32()
+        m3 = torch.tensor(ops.head_pad_map(C, heads, 3), device="cuda")
+        assert float(full[..., m3 < 0].abs().max()) == 0.0
+        dqkv_s_f32 = full[..., m3 >= 0]
+        # the qkv contraction's gradients from the padded image: wgrad (+ bias from ln1's ones column) and dgrad
+        dwq = torch.zeros_like(wq)  # (bias gradient: needs LayerNorm's ones column in x; covered by the whole-network tests)
+        ops.conv_wgrad_mapped_rows(xs, dq_p, dwq, None, qw.row_map)
+        qw2 = ops.MappedPackedWeight(wq, bq, row_map=ops.head_pad_map(C, heads, 3)).refresh()
+        dx_p = ops.conv_fprop(dq_p, qw2, None, dgrad=True)
+        dq_c = ops.STI.from_f32(dqkv_s_f32.contiguous())
+        dwr = torch.zeros_like(wq)
+        ops.conv_wgrad(None, None, dwr, None, 1, 1, x_sti=xs, dy_sti=dq_c)
+        dx_r = ops.conv_fprop(dq_c, ops.PackedWeight(wq).refresh(), None, dgrad=True)
+        assert rel(dwq, dwr) < 2e-5 and rel(dx_p, dx_r) < 2e-5
+    else:
+        dqkv_s_f32 = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, torch.zeros_like(table), C, heads, ws, shift, scale,
+                                              sti_out=True, engine=engine).to_f32()
 
     assert rel(att_w, att) < 1e-4
     assert rel(att_s.to_f32(), att) < 1e-4
@@ -104,7 +124,7 @@ def test_wsti_attention_forward_backward(case, engine):
         _lib.check(_lib.lib().nsr_sti_to_f32(att_s.data_ptr(), B * H * W, kb, raw.data_ptr(), kb, ops._stream()), "sti_to_f32")
         assert torch.equal(raw[..., C], torch.ones_like(raw[..., C])) and float(raw[..., C + 1:].abs().max()) == 0.0
     assert rel(dqkv_w, dqkv) < 2e-4
-    assert rel(dqkv_s.to_f32(), dqkv) < 2e-4
+    assert rel(dqkv_s_f32, dqkv) < 2e-4
     assert rel(dtab_w, dtab) < 2e-4
     # and against the PyTorch restatement in fp64
     q64 = (x.double().cpu().view(-1, C) @ wq.double().cpu().t() + bq.double().cpu()).view(B, H, W, 3 * C).requires_grad_(True)
@@ -116,7 +136,7 @@ def test_wsti_attention_forward_backward(case, engine):
     assert rel(dtab_w, gt) < 2e-4
     # run-to-run determinism (fixed-order reductions)
     dtab_2 = torch.zeros_like(table)
-    dqkv_2 = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, dtab_2, C, heads, ws, shift, scale, sti_out=False)
+    dqkv_2 = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, dtab_2, C, heads, ws, shift, scale, sti_out=False, engine=engine)
     assert torch.equal(dqkv_2, dqkv_w) and torch.equal(dtab_2, dtab_w)
 
 

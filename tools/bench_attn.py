@@ -35,7 +35,7 @@ def main():
     cases = {
         "fwd_tc": lambda: ops.window_attn_fwd_wsti(qkv, table, C, heads, ws, a.shift, scale, engine="tcgen05", padded_out=True),
         "fwd_mma": lambda: ops.window_attn_fwd_wsti(qkv, table, C, heads, ws, a.shift, scale, engine="mma_sync"),
-        "bwd_tc": lambda: ops.window_attn_bwd_wsti(qkv, table, dsti, dtab, C, heads, ws, a.shift, scale, engine="tcgen05"),
+        "bwd_tc": lambda: ops.window_attn_bwd_wsti(qkv, table, dsti, dtab, C, heads, ws, a.shift, scale, engine="tcgen05", padded_out=True),
         "bwd_mma": lambda: ops.window_attn_bwd_wsti(qkv, table, dsti, dtab, C, heads, ws, a.shift, scale, engine="mma_sync"),
     }
     tokens = B * H * W
