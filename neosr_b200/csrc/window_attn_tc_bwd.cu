@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) window_attn_tc_bwd_kernel(const
   AbBars* bars = reinterpret_cast<AbBars*>(smem + AB_SMEM_BAR);
   __shared__ float bias_s[2 * 225];
   __shared__ int rid_s[128];
+  __shared__ int tok_s[128];  // token of row (window, x) of the current pair, -1 beyond the last window
+  __shared__ int mask_s[4];   // per 32-row quarter: its rows lie in more than one shift-mask region
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_wp = (gm.nwin + 1) >> 1, n_hp = (gm.heads + 1) >> 1;
   const int hp = blockIdx.x % n_hp, b = blockIdx.x / n_hp;  // this CTA's head pair and its slot among the gx CTAs of the pair
@@ -165,17 +167,24 @@ __global__ void __launch_bounds__(AB_THREADS, 1) window_attn_tc_bwd_kernel(const
     uint8_t* trow = smem + AB_SMEM_T + win * AT_BLK + (h * 64 + qi) * 128;  // this thread's row of T[window][(head, query)]
     uint32_t par = 0;
     for (int wp = b; wp < n_wp; wp += gx, par ^= 1) {
-      int tok = 0, rid = 0, e_tok = 0, e_rid = 0;
-      const bool e_valid = wp * 2 + h < gm.nwin;            // epilogue: this thread stores rows of window h of the pair
-      if (wp * 2 + win < gm.nwin) at_token_map(gm, wp * 2 + win, qi, tok, rid);
-      if (e_valid) at_token_map(gm, wp * 2 + h, qi, e_tok, e_rid);
-      named_bar_sync(1, 512);  // every thread is done with the previous pair's region ids
-      if (h == 0 && half == 0) rid_s[r] = rid;
-      named_bar_sync(1, 512);
-      bool masked = false;
-      if (gm.use_mask && gm.shift > 0) {
-        for (int j = 0; j < 32; ++j) masked |= rid_s[win * 64 + half * 32 + j] != rid;
+      // token index / shift-mask region of the pair's 128 rows: one thread per row computes them (integer divisions),
+      // everybody reads them from shared memory; a window is "masked" if its 64 tokens do not share one region
+      const bool e_valid = wp * 2 + h < gm.nwin;  // epilogue: this thread stores rows of window h of the pair
+      named_bar_sync(1, 512);  // every thread is done with the previous pair's tokens / region ids
+      if (h == 0 && half == 0) {
+        int tok = -1, rid0 = 0;
+        if (wp * 2 + win < gm.nwin) at_token_map(gm, wp * 2 + win, qi, tok, rid0);
+        rid_s[r] = rid0;
+        tok_s[r] = tok;
+        const unsigned differs = __ballot_sync(0xffffffffu, rid0 != __shfl_sync(0xffffffffu, rid0, 0));
+        if (lane == 0) mask_s[q] = differs != 0;  // per 32-row quarter; quarters of a window are combined below
       }
+      named_bar_sync(1, 512);
+      const int rid = rid_s[r];
+      const int e_tok = tok_s[h * 64 + qi];
+      bool masked = false;
+      if (gm.use_mask && gm.shift > 0)
+        masked = mask_s[win * 2] || mask_s[win * 2 + 1] || rid_s[win * 64] != rid_s[win * 64 + 32];
       // ---- phase 1 results -> P, delta
       mbar_wait(&bars->s_full, par);
       tc_fence_after();
@@ -270,44 +279,67 @@ __global__ void __launch_bounds__(AB_THREADS, 1) window_attn_tc_bwd_kernel(const
         fence_proxy_async_smem();
       }
       mbar_arrive(&bars->ds_full);
-      // ---- epilogue: lane r = (head-in-pair `win`, token x = qi) of window `h`; this thread's 16 channels of dQ, dK, dV
+      // ---- epilogue: lane r = (head-in-pair `win`, token x = qi) of window `h`; this thread's 16 channels of dQ, dK, dV.
+      // The values go through shared memory (the tile region is idle now) so that the global stores are whole 128-byte
+      // rows of the image: 4 rows per warp instruction instead of 32 scattered 16-byte pieces (the direct stores were 27 %
+      // of the kernel, profiles/r02_m_ncu_attn_tc_bwd.txt).
       mbar_wait(&bars->out_full, par);
       tc_fence_after();
       {
-        const long long tk = e_tok;
-        const int c0 = half * 16, r7 = (int)(tk & 7);
-#pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3) {  // dQ, dK, dV, one at a time (16 live values instead of 48)
+        uint8_t* stage = smem + AB_SMEM_T;  // 2 buffers x [128 token rows (window, x)][hi 128 B | lo 128 B], chunks swizzled by x
+        const int c0 = half * 16;
+        auto stage_out = [&](int s3, int buf) {
           float o[16];
           tmem_ld_32x16(lane_addr + (s3 == 0 ? 128 : (s3 == 1 ? 256 : 0)) + h * 64 + win * 32 + half * 16, o);
-          if (!e_valid) continue;
           const float sc = s3 == 2 ? 1.f : gm.scale;
-          if (dqkv && e_head_ok) {
-            float* dst = dqkv + (size_t)tk * 3 * gm.C + s3 * gm.C + e_head * gm.D + c0;
+          if (dqkv && e_tok >= 0 && e_head_ok) {  // fp32 output (tests)
+            float* dst = dqkv + (size_t)e_tok * 3 * gm.C + s3 * gm.C + e_head * gm.D + c0;
 #pragma unroll
             for (int c = 0; c < 16; c += 2)
               if (c0 + c < gm.D) *reinterpret_cast<float2*>(dst + c) = make_float2(o[c] * sc, o[c + 1] * sc);
           }
-          if (dqkv_sti) {
-            uint8_t* rb = dqkv_sti + ((size_t)((tk >> 7) * kbs + s3 * kbs_o + hp) << 15) + (size_t)(tk & 127) * 128;
+          uint8_t* srow = stage + buf * AT_BLK + (h * 64 + qi) * 256;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-              if (e_head_ok) {  // a head beyond `heads` (odd head count) is padding: zeros
-                split_pair(o[8 * j] * sc, o[8 * j + 1] * sc, hi.x, lo.x);
-                split_pair(o[8 * j + 2] * sc, o[8 * j + 3] * sc, hi.y, lo.y);
-                split_pair(o[8 * j + 4] * sc, o[8 * j + 5] * sc, hi.z, lo.z);
-                split_pair(o[8 * j + 6] * sc, o[8 * j + 7] * sc, hi.w, lo.w);
-              }
-              const int off = ((win * 4 + half * 2 + j) ^ r7) << 4;
-              *reinterpret_cast<uint4*>(rb + off) = hi;
-              *reinterpret_cast<uint4*>(rb + 16384 + off) = lo;
+          for (int j = 0; j < 2; ++j) {
+            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+            if (e_head_ok) {  // a head beyond `heads` (odd head count) is padding: zeros
+              split_pair(o[8 * j] * sc, o[8 * j + 1] * sc, hi.x, lo.x);
+              split_pair(o[8 * j + 2] * sc, o[8 * j + 3] * sc, hi.y, lo.y);
+              split_pair(o[8 * j + 4] * sc, o[8 * j + 5] * sc, hi.z, lo.z);
+              split_pair(o[8 * j + 6] * sc, o[8 * j + 7] * sc, hi.w, lo.w);
             }
+            const int off = ((win * 4 + half * 2 + j) ^ (qi & 7)) << 4;
+            *reinterpret_cast<uint4*>(srow + off) = hi;
+            *reinterpret_cast<uint4*>(srow + 128 + off) = lo;
           }
-        }
+        };
+        auto copy_out = [&](int s3, int buf) {
+          if (!dqkv_sti) return;
+          const int t = threadIdx.x - 64;  // 0..511
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int idx = it * 512 + t, row = idx >> 4, slot = idx & 15, c = slot & 7;
+            const int tk = tok_s[row];
+            if (tk < 0) continue;
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + buf * AT_BLK + row * 256 + (slot >> 3) * 128 + ((c ^ (row & 7)) << 4));
+            uint8_t* dst = dqkv_sti + ((size_t)((tk >> 7) * kbs + s3 * kbs_o + hp) << 15) + (slot >> 3) * 16384 +
+                           (size_t)(tk & 127) * 128 + ((c ^ (tk & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = v;
+          }
+        };
+        stage_out(0, 0);
+        stage_out(1, 1);
+        named_bar_sync(1, 512);
+        copy_out(0, 0);
+        copy_out(1, 1);
+        named_bar_sync(1, 512);
+        stage_out(2, 0);
+        tc_fence_before();
+        mbar_arrive(&bars->out_empty);
+        named_bar_sync(1, 512);
+        copy_out(2, 0);
+        named_bar_sync(1, 512);  // the tile region is free again for the next item's P
       }
-      tc_fence_before();
-      mbar_arrive(&bars->out_empty);
     }
     // ---- bias-table gradient partial of this CTA: sum the two windows' accumulators, [b][head][i][j]
     named_bar_sync(1, 512);  // all tiles consumed: the tile region is free as scratch
