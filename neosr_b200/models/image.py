@@ -131,8 +131,10 @@ class image:
         # deterministic launch sequence, i.e. no DropPath draws, and the device-scalar optimizer path
         # (read from the built network, not from the option text: hat_* defaults to drop_path_rate 0.1 too)
         dp = max((float(getattr(m, "drop_prob", 0.0) or 0.0) for m in self.net_g.modules()), default=0.0)
-        self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0 and self.net_d is None
-                            and train_opt["optim_g"].get("type") in {"adan_sf", "Adan_SF"})
+        sf_types = {"adan_sf", "Adan_SF"}  # the fused optimizer with device-resident per-step scalars
+        self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0
+                            and train_opt["optim_g"].get("type") in sf_types
+                            and (self.net_d is None or (train_opt.get("optim_d") or {}).get("type") in sf_types))
         self._graphs, self._graph_logs, self._eager_steps = None, None, 0
         self._lq_static = self._gt_static = None
         self.scale = self.opt.get("scale", 4)
@@ -317,13 +319,21 @@ class image:
         if self._graph_mode and self._graphs is None and self._eager_steps >= 2:
             self._capture_graphs(clip)
         if self._graph_mode and self._graphs is not None:
+            # graph 1: G forward, losses, G backward [, D real / fake forward + backward] | gradient all-reduce(s) |
+            # graph 2: grad-norm + fused optimizer + EMA of G [, of D]
             g_fb, g_opt, n_fb, n_opt = self._graphs
             g_fb.replay()
             if multi:
                 allreduce_mean_(ps.flat_grad)
+                if self.net_d is not None:
+                    allreduce_mean_(self.net_d.param_set().flat_grad)
             self.optimizer_g.prepare(clip_max_norm=clip, ema=self._ema_arg(), to_device=True)
+            if self.net_d is not None:
+                self.optimizer_d.prepare(clip_max_norm=clip, ema=None, to_device=True)
             g_opt.replay()
             self.optimizer_g.bump_versions()
+            if self.net_d is not None:
+                self.optimizer_d.bump_versions()
             ops._count(n_fb + n_opt)
             logs = self._graph_logs
         else:
@@ -350,6 +360,8 @@ class image:
         upload of the optimizer's per-step scalars stay between/around the replays."""
         ps = self.net_g.param_set()
         ps.invalidate_packed()  # the weight re-pack kernels must be part of the captured step
+        if self.net_d is not None:
+            self.net_d.param_set().invalidate_packed()
         torch.cuda.synchronize()
         l0 = ops.LAUNCHES
         g_fb = torch.cuda.CUDAGraph()
@@ -359,19 +371,25 @@ class image:
         ps.attach_grads()
         # plan (tables, device-resident scalars) without advancing the schedule twice: prepare() is
         # re-run before every replay, the capture only needs the launch sequence and stable pointers
-        saved = [dict(step=g.get("step"), weight_sum=g["weight_sum"], lr_max=g["lr_max"]) for g in self.optimizer_g.param_groups]
-        self.optimizer_g.prepare(clip_max_norm=clip, ema=self._ema_arg(), to_device=True)
-        for g, sv in zip(self.optimizer_g.param_groups, saved):
-            g["weight_sum"], g["lr_max"] = sv["weight_sum"], sv["lr_max"]
-            if sv["step"] is None:
-                g.pop("step", None)
-            else:
-                g["step"] = sv["step"]
+        opts = [(self.optimizer_g, self._ema_arg())]
+        if self.net_d is not None:
+            self.net_d.param_set().attach_grads()
+            opts.append((self.optimizer_d, None))
+        for o, ema in opts:
+            saved = [dict(step=g.get("step"), weight_sum=g["weight_sum"], lr_max=g["lr_max"]) for g in o.param_groups]
+            o.prepare(clip_max_norm=clip, ema=ema, to_device=True)
+            for g, sv in zip(o.param_groups, saved):
+                g["weight_sum"], g["lr_max"] = sv["weight_sum"], sv["lr_max"]
+                if sv["step"] is None:
+                    g.pop("step", None)
+                else:
+                    g["step"] = sv["step"]
         torch.cuda.synchronize()
         l0 = ops.LAUNCHES
         g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_opt):
-            self.optimizer_g.launch()
+            for o, _ in opts:
+                o.launch()
         n_opt = ops.LAUNCHES - l0
         self._graphs = (g_fb, g_opt, n_fb, n_opt)
 

@@ -219,3 +219,54 @@ def test_c2_gan_training_steps_vs_oracle():
         assert rel(v, tr.d_buffers[k]) < 1e-3, k
     for i, (k, v) in enumerate(model.net_g_ema.module.named_parameters()):
         assert rel2(v.detach(), tr.ema.avg[i]) < 2e-3, k
+
+
+def test_c2_gan_step_replays_from_cuda_graphs():
+    """The GAN step (G forward / losses / backward + D real / fake passes | both fused optimizers) captured into two CUDA
+    graphs after two eager iterations: iterations 3..6 replay, and every loss of every iteration still tracks the oracle
+    (spectral-norm buffers, both adan_sf states and the EMA advance inside the replayed graphs)."""
+    from neosr_b200.models import build_model
+    from oracle import losses as OL
+    from oracle.esrgan import esrgan_forward, esrgan_param_shapes
+    from oracle.make_golden import OPTIM
+    from oracle.step import OracleTrainer
+    from oracle.swinir import synth_params
+    from oracle.unet import synth_unet
+    gkw = dict(num_block=1, num_feat=64, num_grow_ch=32)
+    opt = {"model_type": "image", "scale": 4, "is_train": True, "dist": False, "rank": 0, "world_size": 1, "cuda_graph": True,
+           "network_g": {"type": "esrgan", **gkw}, "network_d": {"type": "unet", "num_feat": 16},
+           "datasets": {"train": {"patch_size": 16}},
+           "train": {"ema": 0.999, "optim_g": {"type": "adan_sf", **OPTIM}, "optim_d": {"type": "adan_sf", **OPTIM},
+                     "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0},
+                     "perceptual_opt": {"type": "vgg_perceptual_loss", "loss_weight": 0.5, "criterion": "chc",
+                                        "allow_random_init": True},
+                     "gan_opt": {"type": "gan_loss", "gan_type": "bce", "loss_weight": 0.3}},
+           "path": {}}
+    model = build_model(opt)
+    assert model._graph_mode
+    p = synth_params(esrgan_param_shapes(scale=4, **gkw), seed=51)
+    vgg_p = synth_params(OL.vgg19_conv_shapes(), seed=5)
+    dp, db = synth_unet(num_feat=16, seed=52)
+    model.net_g.load_state_dict(p)
+    model.net_d.load_state_dict({**dp, **db})
+    model.cri_perceptual.vgg.load_state_dict(vgg_p, strict=False)
+    tr = OracleTrainer(p, lambda q, x: esrgan_forward(q, x, scale=4, num_block=1), pixel_weight=1.0, percep_weight=0.5,
+                       vgg_params=vgg_p, optim=OPTIM, ema=0.999, disc=(dp, db), gan_weight=0.3)
+    g = torch.Generator().manual_seed(53)
+    for it in range(6):
+        lq, gt = torch.rand(2, 3, 16, 16, generator=g), torch.rand(2, 3, 64, 64, generator=g)
+        model.feed_data({"lq": lq, "gt": gt})
+        model.optimize_parameters(it)
+        tr.feed_data({"lq": lq, "gt": gt})
+        tr.optimize_parameters(it)
+        log, olog = model.get_current_log(), tr.get_current_log()
+        assert set(log) == set(olog), (sorted(log), sorted(olog))
+        for k, v in olog.items():
+            assert abs(log[k] - v) <= 2e-3 * max(1e-2, abs(v)), (it, k, log[k], v)
+    assert model._graphs is not None, "the GAN step was meant to replay from CUDA graphs"
+    for k, v in model.net_d.named_buffers():
+        assert rel(v, tr.d_buffers[k]) < 1e-3, k
+    for k, v in model.net_g.named_parameters():
+        assert rel2(v.detach(), tr.params[k].detach()) < 2e-3, k
+    for k, v in model.net_d.named_parameters():
+        assert rel2(v.detach(), tr.d_params[k].detach()) < 2e-3, k
