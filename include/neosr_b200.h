@@ -418,6 +418,9 @@ typedef struct NsrAdamW {
 /* torch.optim.AdamW (base.py:154-155) with the same clip + EMA fusion; uses exp_avg/exp_avg_sq. */
 int nsr_adamw_step(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
                    const NsrAdamW* hp, const float* sumsq, void* stream);
+/* Scalars from DEVICE memory, for launches inside a captured CUDA graph (see nsr_adan_sf_step_dev). */
+int nsr_adamw_step_dev(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
+                       const NsrAdamW* hp_dev, const float* sumsq, void* stream);
 
 /* ------------------------------------------------------------------ OTF degradations --- */
 /* The on-the-fly degradation pipeline of the `otf` model (neosr/models/otf.py:92-283).  Images are

@@ -109,8 +109,10 @@ __global__ void __launch_bounds__(OPT_THREADS) adan_sf_kernel(const NsrParamEntr
 }
 
 __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const NsrParamEntry* __restrict__ tab, int n_tensors,
-                                                            long long total_chunks, NsrAdamW hp,
+                                                            long long total_chunks, NsrAdamW hp_val,
+                                                            const NsrAdamW* __restrict__ hp_dev,
                                                             const float* __restrict__ sumsq) {
+  const NsrAdamW hp = hp_dev ? *hp_dev : hp_val;
   const float clip = clip_coef(sumsq, hp.max_norm);
   for (long long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
     const int ti = find_tensor(tab, n_tensors, ch);
@@ -174,7 +176,15 @@ extern "C" int nsr_adamw_step(const NsrParamEntry* tab, int n_tensors, int64_t t
                               const float* sumsq, void* stream) {
   NSR_CHECK_ARG(tab && n_tensors > 0 && total_chunks > 0 && hp, "nsr_adamw_step: bad arguments");
   adamw_kernel<<<opt_blocks(total_chunks), OPT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tab, n_tensors, total_chunks, *hp, sumsq);
+      tab, n_tensors, total_chunks, *hp, nullptr, sumsq);
   NSR_CHECK_LAUNCH("adamw_step");
+  return NSR_OK;
+}
+extern "C" int nsr_adamw_step_dev(const NsrParamEntry* tab, int n_tensors, int64_t total_chunks, const NsrAdamW* hp_dev,
+                                  const float* sumsq, void* stream) {
+  NSR_CHECK_ARG(tab && n_tensors > 0 && total_chunks > 0 && hp_dev, "nsr_adamw_step_dev: bad arguments");
+  adamw_kernel<<<opt_blocks(total_chunks), OPT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tab, n_tensors, total_chunks, NsrAdamW{}, hp_dev, sumsq);
+  NSR_CHECK_LAUNCH("adamw_step_dev");
   return NSR_OK;
 }

@@ -131,7 +131,7 @@ class image:
         # deterministic launch sequence, i.e. no DropPath draws, and the device-scalar optimizer path
         # (read from the built network, not from the option text: hat_* defaults to drop_path_rate 0.1 too)
         dp = max((float(getattr(m, "drop_prob", 0.0) or 0.0) for m in self.net_g.modules()), default=0.0)
-        sf_types = {"adan_sf", "Adan_SF"}  # the fused optimizer with device-resident per-step scalars
+        sf_types = {"adan_sf", "Adan_SF", "AdamW", "adamw"}  # fused optimizers with device-resident per-step scalars
         self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0
                             and train_opt["optim_g"].get("type") in sf_types
                             and (self.net_d is None or (train_opt.get("optim_d") or {}).get("type") in sf_types))
@@ -376,6 +376,11 @@ class image:
             self.net_d.param_set().attach_grads()
             opts.append((self.optimizer_d, None))
         for o, ema in opts:
+            if isinstance(o, AdamW):  # torch-style per-parameter `step` tensors: rewind the one this planning pass adds
+                o.prepare(clip_max_norm=clip, ema=ema, to_device=True)
+                for st in o.state.values():
+                    st["step"] -= 1
+                continue
             saved = [dict(step=g.get("step"), weight_sum=g["weight_sum"], lr_max=g["lr_max"]) for g in o.param_groups]
             o.prepare(clip_max_norm=clip, ema=ema, to_device=True)
             for g, sv in zip(o.param_groups, saved):

@@ -25,19 +25,17 @@ class AdamW(Optimizer):
                                   "amsgrad": False})
         self._tables: dict = {}
         self._sumsq = None
+        self._hp_slots: dict = {}
+        self._plan: list = []
+        self._clip = 0.0
 
+    # step() = prepare() (host: advance `step`, derive the bias corrections) + launch() (device: grad-norm + ONE fused
+    # kernel) + bump_versions(); in CUDA-graph mode the model calls prepare(to_device=True) every iteration (one small
+    # async copy per group) and replays a graph that contains launch() - the same split as adan_sf.
     @torch.no_grad()
-    def step(self, closure=None, *, clip_max_norm: float | None = None, ema=None):
-        loss = closure() if closure is not None else None
-        L = _lib.lib()
-        sumsq_ptr = None
-        if clip_max_norm is not None and clip_max_norm > 0:
-            rows = [{"p": p.detach(), "g": p.grad} for g in self.param_groups for p in g["params"] if p.grad is not None]
-            tab = self._tables.setdefault("norm", ParamTable()).build(rows)
-            if self._sumsq is None:
-                self._sumsq = torch.zeros(1, dtype=torch.float32, device=tab.dev.device)
-            grad_sumsq(tab, self._sumsq)
-            sumsq_ptr = self._sumsq.data_ptr()
+    def prepare(self, *, clip_max_norm: float | None = None, ema=None, to_device: bool = False) -> None:
+        self._plan = []
+        self._clip = float(clip_max_norm or 0.0)
         ema_iter = iter(ema[0]) if ema is not None else None
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
@@ -51,7 +49,8 @@ class AdamW(Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1
-                step = int(st["step"].item())
+                if step is None:
+                    step = int(st["step"].item())  # host tensor: no device sync
                 rows.append({"p": p.detach(), "g": p.grad, "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"],
                              "ema": next(ema_iter) if ema_iter is not None else None})
             if not rows:
@@ -60,11 +59,56 @@ class AdamW(Optimizer):
             bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
             hp = NsrAdamW(beta1=b1, one_minus_beta1=1 - b1, beta2=b2, one_minus_beta2=1 - b2, eps=group["eps"],
                           decay=1 - group["lr"] * group["weight_decay"], step_size=group["lr"] / bc1,
-                          bias_correction2_sqrt=math.sqrt(bc2), max_norm=float(clip_max_norm or 0.0),
+                          bias_correction2_sqrt=math.sqrt(bc2), max_norm=self._clip,
                           ema_lerp=float(1.0 - ema[1]) if ema is not None else 0.0,
                           ema_first=int(bool(ema[2])) if ema is not None else 0)
-            _lib.check(L.nsr_adamw_step(tab.dev.data_ptr(), tab.n, tab.chunks, C.byref(hp), sumsq_ptr, _stream()),
-                       "nsr_adamw_step")
+            hp_dev = None
+            if to_device:  # ring of pinned staging buffers, as in adan_sf.prepare
+                ring = self._hp_slots.get(gi)
+                if ring is None:
+                    n = C.sizeof(NsrAdamW)
+                    ring = self._hp_slots[gi] = {"dev": torch.zeros(n, dtype=torch.uint8, device=tab.dev.device),
+                                                 "host": [torch.zeros(n, dtype=torch.uint8).pin_memory() for _ in range(4)],
+                                                 "ev": [None] * 4, "i": 0}
+                i = ring["i"]
+                if ring["ev"][i] is not None:
+                    ring["ev"][i].synchronize()
+                C.memmove(ring["host"][i].data_ptr(), C.addressof(hp), C.sizeof(NsrAdamW))
+                ring["dev"].copy_(ring["host"][i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                ring["ev"][i], ring["i"] = ev, (i + 1) % 4
+                hp_dev = ring["dev"]
+            self._plan.append((tab, hp, hp_dev, [r["p"] for r in rows]))
+
+    @torch.no_grad()
+    def launch(self) -> None:
+        L = _lib.lib()
+        sumsq_ptr = None
+        if self._clip > 0:
+            rows = [{"p": p.detach(), "g": p.grad} for g in self.param_groups for p in g["params"] if p.grad is not None]
+            tab = self._tables.setdefault("norm", ParamTable()).build(rows)
+            if self._sumsq is None:
+                self._sumsq = torch.zeros(1, dtype=torch.float32, device=tab.dev.device)
+            grad_sumsq(tab, self._sumsq)
+            sumsq_ptr = self._sumsq.data_ptr()
+        for tab, hp, hp_dev, _ in self._plan:
+            if hp_dev is not None:
+                _lib.check(L.nsr_adamw_step_dev(tab.dev.data_ptr(), tab.n, tab.chunks, hp_dev.data_ptr(), sumsq_ptr, _stream()),
+                           "nsr_adamw_step_dev")
+            else:
+                _lib.check(L.nsr_adamw_step(tab.dev.data_ptr(), tab.n, tab.chunks, C.byref(hp), sumsq_ptr, _stream()),
+                           "nsr_adamw_step")
             ops_mod._count(1)
-            torch.autograd.graph.increment_version([r["p"] for r in rows])
+
+    def bump_versions(self) -> None:
+        for _, _, _, params in self._plan:
+            torch.autograd.graph.increment_version(params)
+
+    @torch.no_grad()
+    def step(self, closure=None, *, clip_max_norm: float | None = None, ema=None):
+        loss = closure() if closure is not None else None
+        self.prepare(clip_max_norm=clip_max_norm, ema=ema)
+        self.launch()
+        self.bump_versions()
         return loss

@@ -111,7 +111,8 @@ def test_realplksr_forward_backward_vs_oracle(kw):
 
 
 def test_c5_shaped_training_steps_vs_oracle():
-    """realplksr x4, L1 loss, AdamW + EMA (C5's optimizer), 3 iterations of the `image` model vs the oracle trainer."""
+    """realplksr x4, L1 loss, AdamW + EMA (C5's optimizer), 5 iterations of the `image` model vs the oracle trainer
+    (iterations 3..5 replay from the captured CUDA graphs: AdamW's per-step scalars are read from device memory)."""
     from neosr_b200.models import build_model
     from oracle.realplksr import realplksr_forward, realplksr_param_shapes
     from oracle.step import OracleTrainer
@@ -128,7 +129,7 @@ def test_c5_shaped_training_steps_vs_oracle():
     tr = OracleTrainer(p, lambda q, x: realplksr_forward(q, x, **kw), pixel_weight=1.0, optim=okw, ema=0.999,
                        optim_type="adamw")
     g = torch.Generator().manual_seed(72)
-    for it in range(3):
+    for it in range(5):
         lq, gt = torch.rand(2, 3, 24, 24, generator=g), torch.rand(2, 3, 96, 96, generator=g)
         model.feed_data({"lq": lq, "gt": gt})
         model.optimize_parameters(it)
@@ -137,6 +138,7 @@ def test_c5_shaped_training_steps_vs_oracle():
         log = model.get_current_log()
         for k, v in tr.get_current_log().items():
             assert abs(log[k] - v) <= 1e-3 * max(1e-3, abs(v)), (it, k, log[k], v)
+    assert model._graphs is not None, "the AdamW step was meant to replay from CUDA graphs"
     # AdamW's first steps move every weight by ~lr regardless of gradient size (m / sqrt(v) ~ +-1), so weights whose
     # gradient is near zero amplify 1e-5 gradient differences; bound the parameters loosely and the UPDATE in L2.
     # Measured on B200: a handful of 17x17-conv weights whose L1-loss gradient is ~0 take the opposite sign in m/sqrt(v)
