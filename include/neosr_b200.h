@@ -138,6 +138,26 @@ int nsr_pack_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int 
 int nsr_pack_weight_pair(const float* w_oihw, int cout, int cin, int kh, int kw, void* packed_fprop,
                          void* packed_dgrad, void* stream);
 
+/* Every weight of a network in ONE launch (what the engines call after an optimizer step).  Entry = one Conv2d / Linear
+ * weight, optionally re-indexed through int maps (padded output row / input column -> source index, -1 = zero: the
+ * head-padded qkv / proj copies behind nsr_window_attn_wsti_*), packed into the fprop and / or dgrad flavour; bias_out
+ * (optional) receives the row-mapped bias.  `cout, cin` are the PACKED (padded) sizes, `src_cin` the source tensor's input
+ * channel count.  block_base: first CUDA block of the entry, a running sum of nsr_pack_entry_blocks(cout, cin, kh, kw). */
+typedef struct NsrPackEntry {
+  const float* w;
+  const float* bias;
+  void* packed_fprop;
+  void* packed_dgrad;
+  float* bias_out;
+  const int32_t* row_map;
+  const int32_t* col_map;
+  int32_t cout, cin, kh, kw;
+  int32_t src_cin, reserved;
+  int64_t block_base;
+} NsrPackEntry;
+int64_t nsr_pack_entry_blocks(int cout, int cin, int kh, int kw);
+int nsr_pack_weights_multi(const NsrPackEntry* table_dev, int n_entries, int64_t total_blocks, void* stream);
+
 /*
  * Weight gradient of the same contraction (autograd of nn.Linear / nn.Conv2d weights):
  *   dw[co, ci, r, s] = sum_p dy[p, co] * x[p shifted by (r-pad, s-pad), ci]      (OIHW out)

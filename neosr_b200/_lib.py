@@ -46,6 +46,11 @@ class NsrWgrad(C.Structure):
     ]
 
 
+class NsrPackEntry(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w", "bias", "packed_fprop", "packed_dgrad", "bias_out", "row_map", "col_map")] + \
+               [(n, C.c_int32) for n in ("cout", "cin", "kh", "kw", "src_cin", "reserved")] + [("block_base", C.c_int64)]
+
+
 class NsrParamEntry(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("p", "g", "exp_avg", "exp_avg_sq", "exp_avg_diff", "z", "neg_pre_grad", "ema")] + \
@@ -81,6 +86,8 @@ SIGNATURES = {
     "nsr_packed_weight_bytes": (_z, [_i, _i, _i, _i, _i]),
     "nsr_pack_weight": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nsr_pack_weight_pair": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "nsr_pack_entry_blocks": (_l, [_i, _i, _i, _i]),
+    "nsr_pack_weights_multi": (_i, [_p, _i, _l, _p]),
     "nsr_conv_wgrad_workspace": (_z, [C.POINTER(NsrWgrad)]),
     "nsr_conv_wgrad": (_i, [C.POINTER(NsrWgrad), _p]),
     "nsr_nchw_to_nhwc_affine": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),

@@ -63,6 +63,7 @@ class compact(nn.Module):
             raise RuntimeError("neosr_b200.compact runs on CUDA (sm_100a) only; there is no CPU path")
         x = x.contiguous().float()
         ps = self.param_set()
+        ps.pack_all()  # one launch re-packs every weight image after an optimizer step
         t = ops.nchw_to_nhwc_affine(x, None, None)
         S = []
         for k in range(self.num_conv + 1):

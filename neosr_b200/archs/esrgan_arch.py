@@ -80,6 +80,7 @@ class esrgan(nn.Module):
             raise RuntimeError("neosr_b200.esrgan runs on CUDA (sm_100a) only; there is no CPU path")
         x = x.contiguous().float()
         ps = self.param_set()
+        ps.pack_all()  # one launch re-packs every weight image after an optimizer step
         nf, gc = self.nf, self.gc
         ld = nf + 4 * gc
         xin = ops.nchw_to_nhwc_affine(x, None, None)

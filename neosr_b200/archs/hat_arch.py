@@ -214,6 +214,7 @@ class hat(nn.Module):
         if H % ws or W % ws:
             raise ValueError(f"input {H}x{W} must be a multiple of window_size {ws}")
         ps, k = self.param_set(), self._consts(x.device)
+        ps.pack_all()  # one launch re-packs every weight image after an optimizer step
         S: dict = {"shape": (B, H, W), "layers": []} if save else None
 
         def lin(name, t, **kw):

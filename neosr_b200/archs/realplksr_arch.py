@@ -87,6 +87,7 @@ class realplksr(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("neosr_b200.realplksr runs on CUDA (sm_100a) only; there is no CPU path")
         ps = self.param_set()
+        ps.pack_all()  # one launch re-packs every weight image after an optimizer step
         dim, pdim = self.dim, self.pdim
 
         def conv(name, src, **kw):

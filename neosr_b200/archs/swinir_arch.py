@@ -227,6 +227,7 @@ class swinir(nn.Module):
         if H % ws or W % ws:
             raise ValueError(f"input {H}x{W} must be a multiple of window_size {ws}")
         ps = self.param_set()
+        ps.pack_all()  # every weight image whose parameter moved (i.e. all, after an optimizer step), in one launch
         k = self._consts(x.device)
         S: dict = {"shape": (B, H, W)} if save else None
         drops = self._drop_scales(B, x.device)

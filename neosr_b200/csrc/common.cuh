@@ -30,7 +30,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
-static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+__host__ __device__ static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 constexpr int kNumSMs = 148;  // B200
 
@@ -166,7 +166,7 @@ struct PackedGeom {
   size_t f32_bytes;      // fp32 region (1024-aligned)
   size_t bf16_bytes;     // hi/lo tile images
 };
-static inline PackedGeom packed_geom(int cout, int cin, int kh, int kw, int flavour) {
+__host__ __device__ static inline PackedGeom packed_geom(int cout, int cin, int kh, int kw, int flavour) {
   PackedGeom g;
   g.n = flavour == 0 ? cout : cin;
   g.c = flavour == 0 ? cin : cout;

@@ -115,6 +115,69 @@ __global__ void pack_weight_all(const float* __restrict__ w, uint8_t* __restrict
   }
 }
 
+// ---- every weight of a network in ONE launch ------------------------------------------------------------------------
+// Re-packing after an optimizer step used to be one launch per parameter (+ two gathers for every head-padded copy):
+// ~400 launches of ~5 us each per SwinIR-medium step (profiles/r02_r_ncu_kernels_c3.md).  Here a device table lists
+// (source, maps, destinations, geometry) per entry and the CTAs are dealt out over the entries.
+__device__ __forceinline__ float pack_entry_src(const NsrPackEntry& e, int n, int tap, int c, int taps, int flavour) {
+  int co = flavour == 0 ? n : c, ci = flavour == 0 ? c : n;
+  const int src_tap = flavour == 0 ? tap : taps - 1 - tap;
+  if (e.row_map) co = e.row_map[co];
+  if (e.col_map) ci = e.col_map[ci];
+  if (co < 0 || ci < 0) return 0.f;
+  return e.w[((size_t)co * e.src_cin + ci) * taps + src_tap];
+}
+__device__ __forceinline__ void pack_entry_flavour(const NsrPackEntry& e, uint8_t* __restrict__ dst, const PackedGeom& g, int flavour,
+                                                   size_t first, size_t step) {
+  float* f32 = reinterpret_cast<float*>(dst);
+  const size_t total_f = (size_t)g.n * g.taps * g.c;
+  for (size_t i = first; i < total_f; i += step) {
+    const int c = (int)(i % g.c);
+    const size_t r = i / g.c;
+    f32[i] = pack_entry_src(e, (int)(r / g.taps), (int)(r % g.taps), c, g.taps, flavour);
+  }
+  uint8_t* img = dst + g.f32_bytes;
+  const int nblk = g.n_pad64 / 64;
+  const size_t total = (size_t)g.taps * g.cblks * g.n_pad64 * 8;
+  for (size_t i = first; i < total; i += step) {
+    const int ch = (int)(i & 7);
+    const size_t r = i >> 3;
+    const int n = (int)(r % g.n_pad64);
+    const int kb = (int)(r / g.n_pad64);
+    const int tap = kb / g.cblks, cblk = kb - tap * g.cblks;
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cblk * 64 + ch * 8 + k;
+      const float v = (n < g.n && c < g.c) ? pack_entry_src(e, n, tap, c, g.taps, flavour) : 0.f;
+      hi[k] = __float2bfloat16_rn(v);
+      lo[k] = __float2bfloat16_rn(v - __bfloat162float(hi[k]));
+    }
+    const int j = n >> 6, row = n & 63;
+    const size_t off = (size_t)row * 128 + (size_t)((ch ^ (row & 7)) * 16);
+    *reinterpret_cast<uint4*>(img + ((size_t)(kb * 2 + 0) * nblk + j) * 8192 + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(img + ((size_t)(kb * 2 + 1) * nblk + j) * 8192 + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+__global__ void __launch_bounds__(256) pack_weights_multi(const NsrPackEntry* __restrict__ tab, int n_entries) {
+  int lo_i = 0, hi_i = n_entries - 1;  // last entry with block_base <= blockIdx.x
+  while (lo_i < hi_i) {
+    const int mid = (lo_i + hi_i + 1) >> 1;
+    if (tab[mid].block_base <= (long long)blockIdx.x) lo_i = mid; else hi_i = mid - 1;
+  }
+  const NsrPackEntry e = tab[lo_i];
+  const long long nblocks = (lo_i + 1 < n_entries ? tab[lo_i + 1].block_base : (long long)gridDim.x) - e.block_base;
+  const size_t first = (size_t)(blockIdx.x - e.block_base) * 256 + threadIdx.x, step = (size_t)nblocks * 256;
+  const PackedGeom g0 = packed_geom(e.cout, e.cin, e.kh, e.kw, 0), g1 = packed_geom(e.cout, e.cin, e.kh, e.kw, 1);
+  if (e.packed_fprop) pack_entry_flavour(e, reinterpret_cast<uint8_t*>(e.packed_fprop), g0, 0, first, step);
+  if (e.packed_dgrad) pack_entry_flavour(e, reinterpret_cast<uint8_t*>(e.packed_dgrad), g1, 1, first, step);
+  if (e.bias_out)
+    for (size_t i = first; i < (size_t)e.cout; i += step) {
+      const int src = e.row_map ? e.row_map[i] : (int)i;
+      e.bias_out[i] = src < 0 ? 0.f : e.bias[src];
+    }
+}
+
 int launch_pack_weight_bf16(const float* wf32, uint8_t* img, const PackedGeom& g, cudaStream_t st) {
   const size_t t2 = (size_t)g.taps * g.cblks * g.n_pad64 * 8;
   int blocks = ceil_div(t2, 256);
@@ -235,6 +298,22 @@ extern "C" int nsr_pack_weight_pair(const float* w, int cout, int cin, int kh, i
   pack_weight_all<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       w, reinterpret_cast<uint8_t*>(packed_fprop), reinterpret_cast<uint8_t*>(packed_dgrad), g0, g1, cout, cin);
   NSR_CHECK_LAUNCH("pack_weight_all");
+  return NSR_OK;
+}
+
+extern "C" int64_t nsr_pack_entry_blocks(int cout, int cin, int kh, int kw) {
+  const PackedGeom g0 = packed_geom(cout, cin, kh, kw, 0), g1 = packed_geom(cout, cin, kh, kw, 1);
+  size_t work = (size_t)g0.taps * g0.cblks * g0.n_pad64 * 8;
+  const size_t w1 = (size_t)g1.taps * g1.cblks * g1.n_pad64 * 8, wf = (size_t)cout * cin * kh * kw;
+  if (w1 > work) work = w1;
+  if (wf > work) work = wf;
+  int64_t blocks = (int64_t)((work + 2047) / 2048);  // ~8 items per thread
+  return blocks < 1 ? 1 : blocks;
+}
+extern "C" int nsr_pack_weights_multi(const NsrPackEntry* table_dev, int n_entries, int64_t total_blocks, void* stream) {
+  NSR_CHECK_ARG(table_dev && n_entries > 0 && total_blocks > 0 && total_blocks < (1ll << 31), "nsr_pack_weights_multi: bad arguments");
+  pack_weights_multi<<<(unsigned)total_blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table_dev, n_entries);
+  NSR_CHECK_LAUNCH("pack_weights_multi");
   return NSR_OK;
 }
 

@@ -19,6 +19,7 @@ class ParamSet:
         self.names = [n for n, _ in module.named_parameters()]
         self._params = dict(module.named_parameters())
         self._packed: dict = {}
+        self._pack_tables: dict = {}
         self.flat_grad: Tensor | None = None
         self._grads: dict = {}
         self.device = None
@@ -46,6 +47,16 @@ class ParamSet:
             pk = self._packed[(name, key)] = ops.MappedPackedWeight(
                 w, self.p(bias_name) if bias_name is not None and self.has(bias_name) else None, row_map, col_map, need_dgrad)
         return pk.refresh()
+
+    def pack_all(self) -> None:
+        """Re-pack EVERY packed weight whose parameter changed in ONE launch (`nsr_pack_weights_multi`).  The engines call
+        this at the top of a training forward: after an optimizer step all versions have moved, and packing lazily at
+        first use cost one launch per parameter (+ gathers for the head-padded copies) - ~400 five-microsecond launches per
+        SwinIR-medium step.  Weights first met later (first iteration) still pack lazily in pw() / pw_mapped()."""
+        stale = [pk for pk in self._packed.values() if pk.stale()]
+        if len(stale) < 2:
+            return  # nothing to batch; the lazy path handles it
+        ops.pack_weights_multi(stale, self._pack_tables)
 
     def invalidate_packed(self) -> None:
         """Force a re-pack on next use (weights changed behind autograd's back, e.g. the

@@ -188,6 +188,19 @@ class PackedWeight:
                                  dtype=torch.uint8, device=dev) if need_dgrad else None
         self._version = None
 
+    def version_key(self):
+        w = self.weight
+        return (w.data_ptr(), w._version)
+
+    def stale(self) -> bool:
+        return self.version_key() != self._version
+
+    def pack_entry(self) -> dict:
+        """Fields of this weight's NsrPackEntry (nsr_pack_weights_multi)."""
+        w = self.weight
+        return dict(w=w.data_ptr(), bias=None, packed_fprop=self.fprop.data_ptr(), packed_dgrad=_p(self.dgrad), bias_out=None,
+                    row_map=None, col_map=None, cout=self.cout, cin=self.cin, kh=self.kh, kw=self.kw, src_cin=self.cin)
+
     def refresh(self, force: bool = False) -> "PackedWeight":
         """Re-pack if the parameter changed since the last pack (tracked by tensor version)."""
         w = self.weight
@@ -222,9 +235,19 @@ class MappedPackedWeight(PackedWeight):
         super().__init__(self.padded, need_dgrad=need_dgrad)
         self.weight = weight  # identity of the source parameter (ParamSet.pw compares data pointers)
 
+    def version_key(self):
+        w, b = self.src, self.src_bias
+        return (w.data_ptr(), w._version, None if b is None else b._version)
+
+    def pack_entry(self) -> dict:
+        w, b = self.src, self.src_bias
+        return dict(w=w.data_ptr(), bias=_p(b), packed_fprop=self.fprop.data_ptr(), packed_dgrad=_p(self.dgrad),
+                    bias_out=_p(self.bias_padded), row_map=_p(self.row_map), col_map=_p(self.col_map), cout=self.cout,
+                    cin=self.cin, kh=1, kw=1, src_cin=w.shape[1])
+
     def refresh(self, force: bool = False) -> "MappedPackedWeight":
         w, b = self.src, self.src_bias
-        ver = (w.data_ptr(), w._version, None if b is None else b._version)
+        ver = self.version_key()
         if not force and ver == self._version:
             return self
         _chk(w, "weight")
@@ -240,6 +263,32 @@ class MappedPackedWeight(PackedWeight):
         _count(2 if b is None else 3)
         self._version = ver
         return self
+
+
+def pack_weights_multi(pks: list, cache: dict) -> None:
+    """One launch for a list of PackedWeight / MappedPackedWeight objects (engine.ParamSet.pack_all); the device table is
+    cached per set of objects (their buffers never move)."""
+    key = tuple(id(pk) for pk in pks)
+    ent = cache.get(key)
+    L = _lib.lib()
+    if ent is None:
+        arr = (_lib.NsrPackEntry * len(pks))()
+        base = 0
+        for i, pk in enumerate(pks):
+            _chk(pk.weight, "weight")
+            for k, v in pk.pack_entry().items():
+                setattr(arr[i], k, v)
+            arr[i].block_base = base
+            base += L.nsr_pack_entry_blocks(pk.cout, pk.cin, pk.kh, pk.kw)
+        dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(pks[0].weight.device)
+        ent = cache[key] = (dev, len(pks), base)
+        if len(cache) > 8:  # stale object sets (re-built ParamSets)
+            cache.pop(next(iter(cache)))
+    dev, n, blocks = ent
+    check(L.nsr_pack_weights_multi(dev.data_ptr(), n, blocks, _stream()), "nsr_pack_weights_multi")
+    _count(1)
+    for pk in pks:
+        pk._version = pk.version_key()
 
 
 @functools.lru_cache(maxsize=64)
