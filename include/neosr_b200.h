@@ -442,6 +442,15 @@ int nsr_adamw_step(const NsrParamEntry* table_dev, int n_tensors, int64_t total_
 int nsr_adamw_step_dev(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks,
                        const NsrAdamW* hp_dev, const float* sumsq, void* stream);
 
+/* F-SAM (Friendly Sharpness-Aware Minimization, neosr/optimizers/fsam.py:36-80) on the multi-tensor table; entry fields:
+ * p, g, exp_avg = fsam's `momentum`, z = fsam's `old_p`.  first_step: g -= sigma * momentum (skipped when `first`),
+ * momentum = lmbda * momentum + (1 - lmbda) * g_before (or = g when `first`), norm = || (|p| if adaptive) * g ||_2 (left in
+ * *sumsq as its square), old_p = p, p += (p^2 if adaptive) * g * rho / (norm + 1e-12).  restore: p = old_p (second_step;
+ * the base optimizer then steps with the gradients taken at the perturbed point).  workspace >= nsr_grad_sumsq_workspace(). */
+int nsr_fsam_first_step(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks, float rho, float sigma,
+                        float lmbda, int adaptive, int first, float* sumsq, void* workspace, void* stream);
+int nsr_fsam_restore(const NsrParamEntry* table_dev, int n_tensors, int64_t total_chunks, void* stream);
+
 /* ------------------------------------------------------------------ OTF degradations --- */
 /* The on-the-fly degradation pipeline of the `otf` model (neosr/models/otf.py:92-283).  Images are
  * NCHW fp32 planes in [0,1] (the layout feed_data receives); per-sample parameters are small DEVICE

@@ -145,6 +145,8 @@ SIGNATURES = {
     "nsr_adan_sf_step_dev": (_i, [_p, _i, _l, _p, _p, _p]),
     "nsr_adamw_step": (_i, [_p, _i, _l, C.POINTER(NsrAdamW), _p, _p]),
     "nsr_adamw_step_dev": (_i, [_p, _i, _l, _p, _p, _p]),
+    "nsr_fsam_first_step": (_i, [_p, _i, _l, _f, _f, _f, _i, _i, _p, _p, _p]),
+    "nsr_fsam_restore": (_i, [_p, _i, _l, _p]),
     "nsr_filter2d": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "nsr_resize": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     "nsr_gaussian_noise": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, C.c_uint64, _p]),

@@ -137,6 +137,76 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const NsrParamEntry*
   }
 }
 
+// ---- F-SAM (neosr/optimizers/fsam.py:36-80) on the same multi-tensor table: p, g, exp_avg = momentum, z = old_p ----------
+// first_step part 1: g <- g - sigma * momentum (not on the first call), momentum <- lmbda * momentum + (1 - lmbda) * g_orig
+// (first call: momentum <- g), and the partial sums of ((|p| or 1) * g)^2 for the perturbation norm
+__global__ void __launch_bounds__(OPT_THREADS) fsam_grad_kernel(const NsrParamEntry* __restrict__ tab, int n_tensors,
+                                                                long long total_chunks, float sigma, float lmbda, int first,
+                                                                int adaptive, float* __restrict__ partial) {
+  __shared__ float red[OPT_THREADS / 32];
+  float s = 0.f;
+  for (long long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+    const int ti = find_tensor(tab, n_tensors, ch);
+    const NsrParamEntry e = tab[ti];
+    const long long off = (ch - e.chunk_base) * NSR_OPT_CHUNK;
+    long long end = off + NSR_OPT_CHUNK;
+    if (end > e.n) end = e.n;
+    for (long long i = off + threadIdx.x; i < end; i += OPT_THREADS) {
+      const float g0 = e.g[i];
+      float g = g0;
+      if (first) {
+        e.exp_avg[i] = g0;
+      } else {
+        const float m = e.exp_avg[i];
+        g = g0 - m * sigma;
+        e.exp_avg[i] = m * lmbda + g0 * (1.f - lmbda);
+        e.g[i] = g;
+      }
+      const float w = adaptive ? fabsf(e.p[i]) * g : g;
+      s = fmaf(w, w, s);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < OPT_THREADS / 32; ++i) t += red[i];
+    partial[blockIdx.x] = t;
+  }
+}
+// first_step part 2: old_p <- p;  p <- p + (p^2 or 1) * g * rho / (norm + 1e-12)      (climb to "w + e(w)")
+__global__ void __launch_bounds__(OPT_THREADS) fsam_climb_kernel(const NsrParamEntry* __restrict__ tab, int n_tensors,
+                                                                 long long total_chunks, float rho, int adaptive,
+                                                                 const float* __restrict__ sumsq) {
+  const float scale = rho / (sqrtf(*sumsq) + 1e-12f);
+  for (long long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+    const int ti = find_tensor(tab, n_tensors, ch);
+    const NsrParamEntry e = tab[ti];
+    const long long off = (ch - e.chunk_base) * NSR_OPT_CHUNK;
+    long long end = off + NSR_OPT_CHUNK;
+    if (end > e.n) end = e.n;
+    for (long long i = off + threadIdx.x; i < end; i += OPT_THREADS) {
+      const float p = e.p[i];
+      e.z[i] = p;
+      e.p[i] = p + (adaptive ? p * p : 1.f) * e.g[i] * scale;
+    }
+  }
+}
+// second_step: p <- old_p
+__global__ void __launch_bounds__(OPT_THREADS) fsam_restore_kernel(const NsrParamEntry* __restrict__ tab, int n_tensors,
+                                                                   long long total_chunks) {
+  for (long long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+    const int ti = find_tensor(tab, n_tensors, ch);
+    const NsrParamEntry e = tab[ti];
+    const long long off = (ch - e.chunk_base) * NSR_OPT_CHUNK;
+    long long end = off + NSR_OPT_CHUNK;
+    if (end > e.n) end = e.n;
+    for (long long i = off + threadIdx.x; i < end; i += OPT_THREADS) e.p[i] = e.z[i];
+  }
+}
+
 static int opt_blocks(long long chunks) {
   long long cap = (long long)kNumSMs * 8;
   return (int)(chunks < cap ? (chunks > 0 ? chunks : 1) : cap);
@@ -186,5 +256,27 @@ extern "C" int nsr_adamw_step_dev(const NsrParamEntry* tab, int n_tensors, int64
   adamw_kernel<<<opt_blocks(total_chunks), OPT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       tab, n_tensors, total_chunks, NsrAdamW{}, hp_dev, sumsq);
   NSR_CHECK_LAUNCH("adamw_step_dev");
+  return NSR_OK;
+}
+
+extern "C" int nsr_fsam_first_step(const NsrParamEntry* tab, int n_tensors, int64_t total_chunks, float rho, float sigma,
+                                   float lmbda, int adaptive, int first, float* sumsq, void* workspace, void* stream) {
+  NSR_CHECK_ARG(tab && n_tensors > 0 && total_chunks > 0 && sumsq && workspace, "nsr_fsam_first_step: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = total_chunks < SUMSQ_BLOCKS ? (int)total_chunks : SUMSQ_BLOCKS;
+  fsam_grad_kernel<<<blocks, OPT_THREADS, 0, st>>>(tab, n_tensors, total_chunks, sigma, lmbda, first, adaptive,
+                                                   reinterpret_cast<float*>(workspace));
+  NSR_CHECK_LAUNCH("fsam_grad");
+  sumsq_final<<<1, OPT_THREADS, 0, st>>>(reinterpret_cast<const float*>(workspace), blocks, sumsq);
+  NSR_CHECK_LAUNCH("sumsq_final");
+  fsam_climb_kernel<<<opt_blocks(total_chunks), OPT_THREADS, 0, st>>>(tab, n_tensors, total_chunks, rho, adaptive, sumsq);
+  NSR_CHECK_LAUNCH("fsam_climb");
+  return NSR_OK;
+}
+extern "C" int nsr_fsam_restore(const NsrParamEntry* tab, int n_tensors, int64_t total_chunks, void* stream) {
+  NSR_CHECK_ARG(tab && n_tensors > 0 && total_chunks > 0, "nsr_fsam_restore: bad arguments");
+  fsam_restore_kernel<<<opt_blocks(total_chunks), OPT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tab, n_tensors,
+                                                                                                          total_chunks);
+  NSR_CHECK_LAUNCH("fsam_restore");
   return NSR_OK;
 }

@@ -38,7 +38,7 @@ from ..archs.arch_util import set_default_scale
 from ..data.augmentations import draw_augment_plan, run_augment_plan
 from ..dist import allreduce_mean_, broadcast_params_
 from ..losses import build_loss
-from ..optimizers import AdamW, adan_sf
+from ..optimizers import AdamW, adan_sf, fsam
 from ..registry import MODEL_REGISTRY
 
 
@@ -107,9 +107,22 @@ class image:
         self.ema = train_opt.get("ema", -1)
         if self.ema > 0:
             self.net_g_ema = AveragedModel(self.net_g, multi_avg_fn=get_ema_multi_avg_fn(self.ema), device=self.device)
-        for k in ("sam", "eco", "wavelet_guided", "match_lq_colors"):
+        for k in ("wavelet_guided", "match_lq_colors"):
             if train_opt.get(k):
                 raise NotImplementedError(f"neosr_b200.image: train.{k} is outside the built hot path (SURVEY.md §8f.4)")
+        # opt-in step variants (image.py:90-91, 136-146): F-SAM double closure and ECO centroid targets
+        self.sam = train_opt.get("sam", None)
+        self.sam_init = train_opt.get("sam_init", -1)
+        if self.sam is not None and self.sam not in {"FSAM", "fsam"}:
+            raise NotImplementedError(f"SAM type {self.sam} not supported yet.")
+        if self.sam is not None and self.opt.get("network_d") is not None:
+            raise NotImplementedError("neosr_b200.image: F-SAM together with a discriminator is not built (the reference's second "
+                                      "closure accumulates the discriminator gradients of both passes)")
+        self.eco = bool(train_opt.get("eco", False))
+        self.eco_schedule = train_opt.get("eco_schedule", "sigmoid")
+        self.eco_iters = train_opt.get("eco_iters", 80000)
+        self.eco_init = train_opt.get("eco_init", 15000)
+        self.pretrain = (self.opt.get("path") or {}).get("pretrain_network_g")
         if self.opt.get("use_amp", False):
             raise NotImplementedError("neosr_b200.image: AMP is opt-in in the reference and not built (fp32 path)")
         ds = self.opt.get("datasets", {}).get("train", {})
@@ -132,7 +145,7 @@ class image:
         # (read from the built network, not from the option text: hat_* defaults to drop_path_rate 0.1 too)
         dp = max((float(getattr(m, "drop_prob", 0.0) or 0.0) for m in self.net_g.modules()), default=0.0)
         sf_types = {"adan_sf", "Adan_SF", "AdamW", "adamw"}  # fused optimizers with device-resident per-step scalars
-        self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0
+        self._graph_mode = (bool(self.opt.get("cuda_graph", True)) and dp == 0.0 and self.sam is None and not self.eco
                             and train_opt["optim_g"].get("type") in sf_types
                             and (self.net_d is None or (train_opt.get("optim_d") or {}).get("type") in sf_types))
         self._graphs, self._graph_logs, self._eager_steps = None, None, 0
@@ -194,8 +207,16 @@ class image:
     def setup_optimizers(self) -> None:  # image.py:340-372
         o = self.opt["train"]["optim_g"]
         self.sf_optim_g = o.get("schedule_free", False)
-        self.optimizer_g = self._make_optimizer([p for p in self.net_g.parameters() if p.requires_grad], o)
+        g_params = [p for p in self.net_g.parameters() if p.requires_grad]
+        self.optimizer_g = self._make_optimizer(g_params, o)
         self.optimizers.append(self.optimizer_g)
+        if getattr(self, "sam", None) is not None:  # image.py:309-330: F-SAM around a second instance of the base optimizer
+            kw = dict(o)
+            t = kw.pop("type")
+            base = adan_sf if t in {"Adan_SF", "adan_sf"} else (AdamW if t in {"AdamW", "adamw"} else None)
+            if base is None:
+                raise NotImplementedError(f"SAM not supported by optimizer {t} yet.")
+            self.sam_optimizer_g = fsam(g_params, base, rho=0.5, sigma=1, lmbda=0.9, adaptive=True, **kw)
         if self.net_d is not None:
             o = self.opt["train"]["optim_d"]
             self.sf_optim_d = o.get("schedule_free", False)
@@ -246,13 +267,29 @@ class image:
         if gt is not None:
             self.gt = gt.to(self.device, non_blocking=True)
 
-    def _forward_backward(self) -> OrderedDict:
+    def _eco_input(self, current_iter: int) -> Tensor:
+        """eco_strategy (image.py:393-425): the network input is the LQ centroid (1-a) down(G(lq)) + a lq and the target
+        the GT centroid (1-a) G(lq) + a gt (self.gt is overwritten for the rest of the step, as in the reference)."""
+        import math
+        if self.eco_schedule == "sigmoid":
+            a = 1 / (1 + math.exp(-1 * (10 * (current_iter / self.eco_iters - 0.25))))
+        else:
+            a = min(current_iter / self.eco_iters, 1.0)
+        net_output, _ = self.net_g.engine_forward(self.lq, save=False)
+        self.gt = ops.axpby(net_output, 1.0 - a, self.gt, a)
+        lq_scaled = ops.resize_aa(net_output, "bicubic", scale_factor=1 / self.scale)  # clamps to [0, 1]
+        return ops.axpby(lq_scaled, 1.0 - a, self.lq, a)
+
+    def _forward_backward(self, current_iter: int = 0) -> OrderedDict:
         """G fprop -> fused loss value+grad kernels -> G backward into the flat gradient buffer.
         Returns the loss scalars as device tensors (image.py:448-531)."""
         net = self.net_g
         ps = net.param_set()
         ps.ensure_grads(self.device)
-        out, saved = net.engine_forward(self.lq, save=True)
+        lq = self.lq
+        if self.eco and current_iter <= self.eco_iters and not (current_iter < self.eco_init and self.pretrain is None):
+            lq = self._eco_input(current_iter)
+        out, saved = net.engine_forward(lq, save=True)
         self.output = out
         total = torch.zeros(1, dtype=torch.float32, device=self.device)
         logs = OrderedDict()
@@ -336,8 +373,22 @@ class image:
                 self.optimizer_d.bump_versions()
             ops._count(n_fb + n_opt)
             logs = self._graph_logs
+        elif self.sam is not None and current_iter >= self.sam_init:
+            # fsam.step (fsam.py:82-95): gradients at w -> climb to w + e(w) -> gradients there -> back to w, base optimizer
+            # step.  No generator clip under SAM (image.py:533-537).
+            self._forward_backward(current_iter)
+            if multi:
+                allreduce_mean_(ps.flat_grad)
+            ps.attach_grads()
+            self.sam_optimizer_g.first_step()
+            logs = self._forward_backward(current_iter)
+            if multi:
+                allreduce_mean_(ps.flat_grad)
+            ps.attach_grads()
+            self.sam_optimizer_g.second_step(clip_max_norm=None, ema=self._ema_arg())
+            self._eager_steps += 1
         else:
-            logs = self._forward_backward()
+            logs = self._forward_backward(current_iter)
             if multi:
                 allreduce_mean_(ps.flat_grad)  # the one collective of the step (DDP-style gradient averaging)
             ps.attach_grads()

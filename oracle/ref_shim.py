@@ -115,7 +115,7 @@ def build_vgg_perceptual(seed_params: dict | None, loss_weight: float = 0.5, cri
 
 
 def make_image_model(net_g, *, cri_pix=None, cri_perceptual=None, optim_kw=None, ema=0.999, scale=4,
-                     net_d=None, cri_gan=None, optim_d_kw=None, device="cpu"):
+                     net_d=None, cri_gan=None, optim_d_kw=None, device="cpu", eco=None, sam_init=None):
     """`object.__new__(image)` with the attributes `closure`/`optimize_parameters` read
     (image.py:73-230), so the reference's REAL step methods run on CPU."""
     activate()
@@ -153,6 +153,18 @@ def make_image_model(net_g, *, cri_pix=None, cri_perceptual=None, optim_kw=None,
     for n in ("cri_mssim", "cri_consistency", "cri_dists", "cri_gan", "cri_ldl", "cri_ff", "cri_gw"):
         setattr(m, n, None)
     m.scale, m.aug, m.aug_prob, m.patch_size = scale, None, None, 64
+    if eco:  # image.py:136-146
+        m.eco, m.eco_schedule = True, eco.get("schedule", "sigmoid")
+        m.eco_iters, m.eco_init, m.pretrain = eco.get("iters", 80000), eco.get("init", 15000), eco.get("pretrain")
+    if sam_init is not None:  # image.py:90-91, 322-330
+        from neosr.optimizers import fsam  # noqa: PLC0415
+        m.sam, m.sam_init = "fsam", sam_init
+        m.sam_optimizer_g = fsam([p for p in net_g.parameters() if p.requires_grad], adan_sf, rho=0.5, sigma=1, lmbda=0.9,
+                                 adaptive=True, **kw)
+        # the reference steps `sam_optimizer_g.base_optimizer` under SAM and `optimizer_g` before sam_init: two separate
+        # adan_sf states over the same parameters (image.py:309-330); the oracle keeps ONE, so start SAM at iteration 0
+        m.optimizer_g = m.sam_optimizer_g.base_optimizer
+        m.optimizers = [m.optimizer_g]
     net_g.train()
     m.optimizer_g.train()
     if net_d is not None:  # image.py:40-46, 356-372

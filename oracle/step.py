@@ -26,7 +26,8 @@ class OracleTrainer:
                  layer_weights: dict | None = None, optim: dict | None = None,
                  ema: float = 0.999, grad_clip: bool = True, disc: tuple | None = None,
                  gan_weight: float = 0.1, optim_d: dict | None = None, optim_type: str = "adan_sf",
-                 mssim_weight: float | None = None, consistency_weight: float | None = None):
+                 mssim_weight: float | None = None, consistency_weight: float | None = None,
+                 eco: dict | None = None, sam: dict | None = None, scale: int = 4):
         self.names = list(params)
         self.params = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
         self.net_fn = net_fn
@@ -40,6 +41,10 @@ class OracleTrainer:
         self.ema = EMAState([self.params[k] for k in self.names], ema) if ema and ema > 0 else None
         self.log_dict: OrderedDict = OrderedDict()
         self.last_grads: dict = {}
+        # opt-in step variants: ECO (image.py:393-425; keys iters, init, schedule, pretrain) and F-SAM
+        # (optimizers/fsam.py; keys init = sam_init; rho 0.5, sigma 1, lmbda 0.9, adaptive as image.py:322-330 builds it)
+        self.eco, self.sam, self.scale = eco, sam, scale
+        self.sam_momentum: dict = {}
         # discriminator: (params, buffers) of oracle.unet; buffers are updated in place by each forward
         self.disc = None
         if disc is not None:
@@ -55,8 +60,70 @@ class OracleTrainer:
     def feed_data(self, data: dict) -> None:  # image.py:374-391 (no augmentation)
         self.lq, self.gt = data["lq"], data["gt"]
 
+    def _generator_output(self, current_iter: int):
+        """image.closure 445-455 + eco_strategy 393-425: plain forward, or the ECO centroid pair (overwrites self.gt)."""
+        e = self.eco
+        if not e or current_iter > e.get("iters", 80000) or (current_iter < e.get("init", 15000) and not e.get("pretrain")):
+            return self.net_fn(self.params, self.lq)
+        import math
+
+        import torch.nn.functional as F
+        with torch.no_grad():
+            if e.get("schedule", "sigmoid") == "sigmoid":
+                a = 1 / (1 + math.exp(-1 * (10 * (current_iter / e.get("iters", 80000) - 0.25))))
+            else:
+                a = min(current_iter / e.get("iters", 80000), 1.0)
+            net_output = self.net_fn(self.params, self.lq)
+            self.gt = ((1 - a) * net_output) + (a * self.gt)
+            lq_scaled = torch.clamp(F.interpolate(net_output, scale_factor=1 / self.scale, mode="bicubic", antialias=True), 0, 1)
+            inp = ((1 - a) * lq_scaled) + (a * self.lq)
+        return self.net_fn(self.params, inp)
+
     def optimize_parameters(self, current_iter: int = 0) -> None:
-        out = self.net_fn(self.params, self.lq)
+        s = self.sam
+        if s and current_iter >= s.get("init", -1):
+            # fsam.step (fsam.py:82-95): closure at w -> first_step (climb to w + e(w)) -> closure -> second_step (back to w,
+            # base optimizer steps with the gradients taken at w + e(w)); the EMA follows the final weights
+            if self.disc:
+                raise NotImplementedError("oracle: F-SAM with a discriminator")
+            grads = self._closure(current_iter)
+            plist = [self.params[k] for k in self.names]
+            sigma, lmbda, rho = s.get("sigma", 1.0), s.get("lmbda", 0.9), s.get("rho", 0.5)
+            for k, p, g in zip(self.names, plist, grads):  # fsam.py:37-49
+                grad = g.clone()
+                if k not in self.sam_momentum:
+                    self.sam_momentum[k] = grad
+                else:
+                    g -= self.sam_momentum[k] * sigma
+                    self.sam_momentum[k] = self.sam_momentum[k] * lmbda + grad * (1 - lmbda)
+            adaptive = s.get("adaptive", True)
+            norm = torch.norm(torch.stack([((p.detach().abs() if adaptive else 1.0) * g).norm(p=2)
+                                           for p, g in zip(plist, grads)]), p=2)  # fsam.py:97-110
+            sc = rho / (norm + 1e-12)
+            old = [p.detach().clone() for p in plist]
+            with torch.no_grad():
+                for p, g in zip(plist, grads):  # fsam.py:51-65
+                    p.add_((torch.pow(p, 2) if adaptive else 1.0) * g * sc)
+            grads = self._closure(current_iter)
+            with torch.no_grad():
+                for p, o in zip(plist, old):
+                    p.copy_(o)
+            (adamw_step if self.optim_type == "adamw" else adan_sf_step)(self.opt, grads)
+            if self.ema is not None:
+                self.ema.update(plist)
+            return
+        grads = self._closure(current_iter)
+        plist = [self.params[k] for k in self.names]
+        (adamw_step if self.optim_type == "adamw" else adan_sf_step)(self.opt, grads)  # image.py:642
+        if self.disc:
+            adan_sf_step(self.opt_d, self._dgrads)  # image.py:645
+        if self.ema is not None:  # image.py:661-662
+            self.ema.update(plist)
+
+    def _closure(self, current_iter: int = 0) -> list:
+        """image.closure (427-625): forward, loss stack, backward, clip; discriminator passes.  Returns the clipped
+        generator gradients."""
+        out = self._generator_output(current_iter)
         self.output = out
         total = torch.zeros(1)
         log = OrderedDict()
@@ -86,7 +153,8 @@ class OracleTrainer:
         plist = [self.params[k] for k in self.names]
         grads = torch.autograd.grad(total, plist, allow_unused=True)
         grads = [torch.zeros_like(p) if g is None else g.contiguous().clone() for g, p in zip(grads, plist)]
-        self.grad_norm = clip_grad_norm(grads, 1.0) if self.grad_clip else None  # image.py:533-544
+        sam_on = bool(self.sam) and current_iter >= self.sam.get("init", -1)  # no generator clip under SAM (image.py:533-537)
+        self.grad_norm = clip_grad_norm(grads, 1.0) if (self.grad_clip and not sam_on) else None  # image.py:533-544
         self.last_grads = dict(zip(self.names, [g.clone() for g in grads]))
         if self.disc:  # image.py:547-608
             real = unet_forward(self.d_params, self.d_buffers, self.gt, True)
@@ -101,14 +169,11 @@ class OracleTrainer:
             if self.grad_clip:
                 clip_grad_norm(dgrads, 1.0)
             self.last_grads_d = dict(zip(self.d_names, [g.clone() for g in dgrads]))
+            self._dgrads = dgrads
         if torch.isnan(total).any():  # image.py:611-619
             raise ValueError("NaN found, aborting training.")
         self.log_dict = OrderedDict((k, float(v.detach().mean())) for k, v in log.items())
-        (adamw_step if self.optim_type == "adamw" else adan_sf_step)(self.opt, grads)  # image.py:642
-        if self.disc:
-            adan_sf_step(self.opt_d, dgrads)  # image.py:645
-        if self.ema is not None:  # image.py:661-662
-            self.ema.update(plist)
+        return grads
 
     def get_current_log(self):
         return self.log_dict

@@ -448,3 +448,34 @@ def test_validation_host_helpers_vs_reference():
     assert np.isfinite(y) and y > V.calculate_psnr(ia, ib, crop_border=4) - 10.0
     assert V.calculate_psnr(ia, ia) == float("inf")
     assert "neosr_b200.models._validation" in sys.modules
+
+
+def test_eco_and_fsam_step_variants_vs_reference():
+    """Opt-in step variants: the oracle's ECO centroid step and F-SAM double closure against the
+    reference's REAL closure / optimize_parameters (image.py:393-425, 627-662; optimizers/fsam.py)."""
+    ref_shim.activate(4)
+    from neosr.losses.basic_loss import L1Loss
+    from oracle.make_golden import TINY
+    from oracle.step import make_swinir_trainer
+    cfg = SwinIRConfig(**TINY)
+    okw = dict(lr=1e-3, betas=(0.98, 0.92, 0.987), weight_decay=0.02, schedule_free=True, warmup_steps=0)
+    for variant in ("eco", "fsam"):
+        p = synth_params(swinir_param_shapes(cfg), seed=21)
+        net = _ref_swinir(TINY, p)
+        eco = dict(iters=8, init=2, schedule="sigmoid", pretrain=None) if variant == "eco" else None
+        model = ref_shim.make_image_model(net, cri_pix=L1Loss(1.0), optim_kw=okw, eco=eco, sam_init=0 if variant == "fsam" else None)
+        tr = make_swinir_trainer(p, cfg, pixel_weight=1.0, optim=okw, ema=0.999, eco=eco,
+                                 sam=dict(init=0) if variant == "fsam" else None, scale=4)
+        g = torch.Generator().manual_seed(22)
+        for it in range(1, 5):
+            lq, gt = torch.rand(2, 3, 16, 16, generator=g), torch.rand(2, 3, 64, 64, generator=g)
+            model.feed_data({"lq": lq, "gt": gt})
+            model.optimize_parameters(it)
+            tr.feed_data({"lq": lq, "gt": gt})
+            tr.optimize_parameters(it)
+            ref_log = model.get_current_log()
+            for k, v in tr.get_current_log().items():
+                assert abs(v - ref_log[k]) <= 1e-5 * max(1.0, abs(ref_log[k])), (variant, it, k, v, ref_log[k])
+        ref_params = dict(net.named_parameters())
+        for k in tr.names:
+            assert _rel(tr.params[k].detach(), ref_params[k].detach()) < 1e-4, (variant, k)

@@ -377,3 +377,56 @@ def test_two_rank_nccl_step_equals_single_process_big_batch(graph, tmp_path):
     assert r["median_dp_rel2"] < 1e-2 and r["cos"] > 0.995, r
     for k, v in r["log_single"].items():
         assert abs(r["log_ddp"][k] - v) <= 2e-3 * max(1e-3, abs(v)), (k, r["log_ddp"][k], v)
+
+
+# ------------------------------------------------------------------------------------------ opt-in step variants (f4)
+@pytest.mark.parametrize("variant", ["eco", "fsam"])
+def test_eco_and_fsam_steps_vs_oracle(variant):
+    """`train.eco` (image.py:393-425: centroid targets from a no-grad forward + antialiased bicubic downsample) and
+    `train.sam = "fsam"` (optimizers/fsam.py: double closure around the fused base optimizer): every loss of six
+    iterations and the parameter displacement against the oracle, which tests/test_oracle_vs_reference.py pins to the
+    reference's real closure for both variants."""
+    from neosr_b200.archs.swinir_arch import swinir
+    from neosr_b200.models import build_model
+    from neosr_b200.registry import ARCH_REGISTRY
+    from oracle.make_golden import TINY
+    from oracle.step import displacement_report, make_swinir_trainer
+    from oracle.swinir import SwinIRConfig, swinir_param_shapes, synth_params
+    if "swinir" not in ARCH_REGISTRY:
+        ARCH_REGISTRY.register(swinir)
+    optim = dict(lr=1e-3, betas=(0.98, 0.92, 0.987), weight_decay=0.02, schedule_free=True, warmup_steps=0)
+    train = {"ema": 0.999, "optim_g": {"type": "adan_sf", **optim}, "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0}}
+    eco = dict(iters=8, init=2, schedule="sigmoid", pretrain=None) if variant == "eco" else None
+    if variant == "eco":
+        train.update(eco=True, eco_iters=8, eco_init=2, eco_schedule="sigmoid")
+    else:
+        train.update(sam="fsam", sam_init=0)
+    opt = {"model_type": "image", "scale": 4, "is_train": True, "dist": False, "rank": 0, "world_size": 1,
+           "network_g": {"type": "swinir", "drop_path_rate": 0.0, **TINY}, "datasets": {"train": {"patch_size": 16}},
+           "train": train, "path": {}}
+    model = build_model(opt)
+    assert not model._graph_mode  # the variants change launch arguments / weights between the passes of a step
+    cfg = SwinIRConfig(**TINY)
+    p0 = synth_params(swinir_param_shapes(cfg), seed=21)
+    model.net_g.load_state_dict(p0, strict=False)
+    kw = dict(pixel_weight=1.0, optim=optim, ema=0.999, eco=eco, sam=dict(init=0) if variant == "fsam" else None, scale=4)
+    tr = make_swinir_trainer(p0, cfg, **kw)
+    tr64 = make_swinir_trainer({k: v.double() for k, v in p0.items()}, cfg, **kw)
+    g = torch.Generator().manual_seed(22)
+    for it in range(1, 7):
+        lq, gt = torch.rand(2, 3, 16, 16, generator=g), torch.rand(2, 3, 64, 64, generator=g)
+        model.feed_data({"lq": lq, "gt": gt})
+        model.optimize_parameters(it)
+        tr.feed_data({"lq": lq, "gt": gt})
+        tr.optimize_parameters(it)
+        tr64.feed_data({"lq": lq.double(), "gt": gt.double()})
+        tr64.optimize_parameters(it)
+        log, ref = model.get_current_log(), tr.get_current_log()
+        for k, v in ref.items():
+            assert abs(log[k] - v) <= 1e-3 * max(1e-3, abs(v)), (variant, it, k, log[k], v)
+    r = displacement_report(p0, dict(model.net_g.named_parameters()), tr.params, tr64.params)
+    print(f"{variant}: displacement worst {r['worst']} coverage {r['coverage_all']:.2f} cos {r['cos']:.5f}")
+    assert r["worst"][0] < 5e-2 and r["coverage_all"] > 0.5 and r["cos"] > 0.999, (r["worst"], r["coverage_all"], r["cos"])
+    if variant == "fsam":  # state names of the reference's fsam (fsam.py:41-58)
+        st = model.sam_optimizer_g.state[next(iter(model.net_g.parameters()))]
+        assert {"momentum", "old_p"} <= set(st)
