@@ -184,6 +184,28 @@ typedef struct NsrWgrad {
 size_t nsr_conv_wgrad_workspace(const NsrWgrad* d);
 int nsr_conv_wgrad(const NsrWgrad* d, void* stream);
 
+/* Deferred reduction of 1x1 weight gradients (split-tile-image operands, tcgen05 engine): nsr_conv_wgrad_partial leaves
+ * the split-K partials [splitk][cout][cin] of the descriptor's (possibly head-padded, bias-column-extended) problem in
+ * d->workspace (>= nsr_conv_wgrad_partial_workspace bytes, owned by the caller until the finalize) and reports splitk;
+ * d->dw / d->dbias are ignored.  nsr_wgrad_finalize_multi then reduces ANY number of such work spaces in one launch, in a
+ * fixed order, straight into the parameter gradients:
+ *   dw[co][ci] = sum_k partial[k][row_map[co]][col_map[ci]]     dbias[co] = sum_k partial[k][row_map[co]][bias_col]
+ * (NULL map = identity; p_rows x p_cols = the padded problem; block_base = running sum of nsr_reduce_entry_blocks). */
+size_t nsr_conv_wgrad_partial_workspace(const NsrWgrad* d);
+int nsr_conv_wgrad_partial(const NsrWgrad* d, int* splitk, void* stream);
+typedef struct NsrReduceEntry {
+  const float* partial;
+  float* dw;
+  float* dbias;            /* NULL: no bias gradient */
+  const int32_t* row_map;  /* [cout] -> row of the padded problem */
+  const int32_t* col_map;  /* [cin]  -> column of the padded problem */
+  int32_t splitk, p_rows, p_cols;
+  int32_t cout, cin, bias_col;
+  int64_t block_base;
+} NsrReduceEntry;
+int64_t nsr_reduce_entry_blocks(int cout, int cin);
+int nsr_wgrad_finalize_multi(const NsrReduceEntry* table_dev, int n_entries, int64_t total_blocks, void* stream);
+
 /* ------------------------------------------------------------------ layout / elementwise */
 /* y_nhwc[b,h,w,c] = x_nchw[b,c,h,w] * scale[c] + shift[c]
  * Replaces `(x - self.mean) * self.img_range` (swinir_arch.py:1041-1042) and the VGG input

@@ -51,6 +51,11 @@ class NsrPackEntry(C.Structure):
                [(n, C.c_int32) for n in ("cout", "cin", "kh", "kw", "src_cin", "reserved")] + [("block_base", C.c_int64)]
 
 
+class NsrReduceEntry(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("partial", "dw", "dbias", "row_map", "col_map")] + \
+               [(n, C.c_int32) for n in ("splitk", "p_rows", "p_cols", "cout", "cin", "bias_col")] + [("block_base", C.c_int64)]
+
+
 class NsrParamEntry(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("p", "g", "exp_avg", "exp_avg_sq", "exp_avg_diff", "z", "neg_pre_grad", "ema")] + \
@@ -90,6 +95,10 @@ SIGNATURES = {
     "nsr_pack_weights_multi": (_i, [_p, _i, _l, _p]),
     "nsr_conv_wgrad_workspace": (_z, [C.POINTER(NsrWgrad)]),
     "nsr_conv_wgrad": (_i, [C.POINTER(NsrWgrad), _p]),
+    "nsr_conv_wgrad_partial_workspace": (_z, [C.POINTER(NsrWgrad)]),
+    "nsr_conv_wgrad_partial": (_i, [C.POINTER(NsrWgrad), C.POINTER(C.c_int), _p]),
+    "nsr_reduce_entry_blocks": (_l, [_i, _i]),
+    "nsr_wgrad_finalize_multi": (_i, [_p, _i, _l, _p]),
     "nsr_nchw_to_nhwc_affine": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "nsr_nhwc_to_nchw_affine": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "nsr_pixel_shuffle_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),

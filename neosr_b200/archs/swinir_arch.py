@@ -341,6 +341,7 @@ class swinir(nn.Module):
         ws = self.window_size
 
         sti = ops.sti_enabled() and bool(S["blocks"]) and isinstance(S["blocks"][0][3], ops.STI)
+        defer = sti and ops.DEFER_WGRAD
 
         def split(v):  # (fp32, STI) pair or a single tensor -> (fp32 | None, STI | None)
             if isinstance(v, tuple):
@@ -356,9 +357,13 @@ class swinir(nn.Module):
             xf, xs = split(x_in)
             gf, gs = split(g)
             use_sti = kh == 1 and xs is not None and gs is not None
-            ops.conv_wgrad(None if use_sti else xf, gf if (gf is not None and (has_b or not use_sti)) else None,
-                           ps.g(name + ".weight"), ps.g(name + ".bias") if has_b else None, kh, kh,
-                           x_sti=xs if use_sti else None, dy_sti=gs if use_sti else None)
+            if use_sti and defer and (not has_b or (xs.ones and xs.shape[-1] % 64 != 0)):
+                # split-K partials now, ONE reduction launch for all 1x1 weight gradients at the end of this pass
+                ps.deferred.add(name, xs, gs, ps.g(name + ".weight").view(w.shape[0], -1), ps.g(name + ".bias") if has_b else None)
+            else:
+                ops.conv_wgrad(None if use_sti else xf, gf if (gf is not None and (has_b or not use_sti)) else None,
+                               ps.g(name + ".weight"), ps.g(name + ".bias") if has_b else None, kh, kh,
+                               x_sti=xs if use_sti else None, dy_sti=gs if use_sti else None)
             if need_dx:
                 src = gs if (kh == 1 and gs is not None) else gf
                 return ops.conv_fprop(src, ps.pw(name + ".weight"), None, dgrad=True, **epi)
@@ -436,7 +441,10 @@ class swinir(nn.Module):
                 if isinstance(qkv, ops.STI):  # window-ordered operands (see engine_forward)
                     pwm = ps.pw_mapped(pre + "attn.proj.weight", "proj_cols", None,
                                        col_map=ops.head_pad_map(self.embed_dim, heads, 1))
-                    if att.shape[-1] != self.embed_dim:  # head-padded attention output
+                    if att.shape[-1] != self.embed_dim and defer:  # head-padded attention output
+                        ps.deferred.add(pre + "attn.proj", att, split(gb)[1], ps.g(pre + "attn.proj.weight"),
+                                        ps.g(pre + "attn.proj.bias"), col_map=pwm.col_map, bias_col=att.ones_col)
+                    elif att.shape[-1] != self.embed_dim:
                         ops.conv_wgrad_mapped(att, split(gb)[1], ps.g(pre + "attn.proj.weight"), ps.g(pre + "attn.proj.bias"),
                                               pwm.col_map, att.ones_col)
                     else:
@@ -449,9 +457,12 @@ class swinir(nn.Module):
                     if pad:  # qkv wgrad / dgrad on the head-padded dqkv image
                         qw = ps.pw_mapped(pre + "attn.qkv.weight", "qkv_rows", pre + "attn.qkv.bias",
                                           row_map=ops.head_pad_map(self.embed_dim, heads, 3))
-                        ops.conv_wgrad_mapped_rows(split(ln1)[1], dqkv, ps.g(pre + "attn.qkv.weight"),
-                                                   ps.g(pre + "attn.qkv.bias") if ps.has(pre + "attn.qkv.bias") else None,
-                                                   qw.row_map)
+                        qb = ps.g(pre + "attn.qkv.bias") if ps.has(pre + "attn.qkv.bias") else None
+                        if defer:
+                            ps.deferred.add(pre + "attn.qkv", split(ln1)[1], dqkv, ps.g(pre + "attn.qkv.weight"), qb,
+                                            row_map=qw.row_map)
+                        else:
+                            ops.conv_wgrad_mapped_rows(split(ln1)[1], dqkv, ps.g(pre + "attn.qkv.weight"), qb, qw.row_map)
                         dln1 = ops.conv_fprop(dqkv, qw, None, dgrad=True)
                 else:
                     datt = bwd(pre + "attn.proj", att, gb)
@@ -470,6 +481,7 @@ class swinir(nn.Module):
         else:
             g = ops.axpby(g, 1.0, df0, 1.0)
         bwd("conv_first", S["xin"], g, need_dx=False)
+        ps.deferred.finalize()
 
     # ------------------------------------------------------------------ nn.Module surface
     def train(self, mode: bool = True):

@@ -16,6 +16,8 @@ int conv_fprop_tc(const NsrConv& d, cudaStream_t st);
 bool conv_wgrad_tc_supported(const NsrWgrad& d);
 size_t conv_wgrad_workspace_tc(const NsrWgrad& d);
 int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st);
+int conv_wgrad_tc_partial(const NsrWgrad& d, int* splitk, cudaStream_t st);
+size_t conv_wgrad_tc_partial_bytes(const NsrWgrad& d);
 // <= 4-channel image-side convolutions (conv_small.cu)
 // direct 3x3 kernels for <= 4-channel sides at image resolution (conv_direct.cu)
 bool conv_direct_fprop_supported(const NsrConv& d);
@@ -298,6 +300,56 @@ extern "C" int nsr_pack_weight_pair(const float* w, int cout, int cin, int kh, i
   pack_weight_all<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       w, reinterpret_cast<uint8_t*>(packed_fprop), reinterpret_cast<uint8_t*>(packed_dgrad), g0, g1, cout, cin);
   NSR_CHECK_LAUNCH("pack_weight_all");
+  return NSR_OK;
+}
+
+// ---- deferred, batched split-K reduction of the 1x1 weight gradients ------------------------------------------------
+// Every STI wgrad used to be followed by its own reduce launch, a bias-column split and (head-padded operands) two
+// un-padding gathers: ~360 launches of 3-13 us per SwinIR-medium step.  The partials now stay in per-layer buffers
+// until the end of the backward pass, where ONE launch reduces all of them (fixed order: deterministic) straight
+// into dW / dbias, un-padding rows and columns and taking the bias-gradient column on the way.
+__global__ void __launch_bounds__(256) wgrad_finalize_multi(const NsrReduceEntry* __restrict__ tab, int n_entries) {
+  int lo_i = 0, hi_i = n_entries - 1;
+  while (lo_i < hi_i) {
+    const int mid = (lo_i + hi_i + 1) >> 1;
+    if (tab[mid].block_base <= (long long)blockIdx.x) lo_i = mid; else hi_i = mid - 1;
+  }
+  const NsrReduceEntry e = tab[lo_i];
+  const long long nblocks = (lo_i + 1 < n_entries ? tab[lo_i + 1].block_base : (long long)gridDim.x) - e.block_base;
+  const size_t first = (size_t)(blockIdx.x - e.block_base) * 256 + threadIdx.x, step = (size_t)nblocks * 256;
+  const size_t per_split = (size_t)e.p_rows * e.p_cols;
+  const int cols1 = e.cin + (e.dbias ? 1 : 0);  // column cin of the work space = the bias gradient
+  const size_t n = (size_t)e.cout * cols1;
+  for (size_t i = first; i < n; i += step) {
+    const int co = (int)(i / cols1), c = (int)(i - (size_t)co * cols1);
+    const int pr = e.row_map ? e.row_map[co] : co;
+    const int pc = c == e.cin ? e.bias_col : (e.col_map ? e.col_map[c] : c);
+    const float* src = e.partial + (size_t)pr * e.p_cols + pc;
+    float s = 0.f;
+    for (int k = 0; k < e.splitk; ++k) s += src[(size_t)k * per_split];
+    if (c == e.cin) e.dbias[co] = s; else e.dw[(size_t)co * e.cin + c] = s;
+  }
+}
+
+extern "C" size_t nsr_conv_wgrad_partial_workspace(const NsrWgrad* d) {
+  if (!d || !conv_wgrad_tc_supported(*d)) return 0;
+  return conv_wgrad_tc_partial_bytes(*d);
+}
+extern "C" int nsr_conv_wgrad_partial(const NsrWgrad* d, int* splitk, void* stream) {
+  NSR_CHECK_ARG(d && splitk, "nsr_conv_wgrad_partial: null descriptor / splitk");
+  NSR_CHECK_ARG(d->batch > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "nsr_conv_wgrad_partial: bad geometry");
+  NSR_CHECK_ARG(d->x_sti && d->dy_sti && d->kh == 1 && d->kw == 1 && conv_wgrad_tc_supported(*d),
+                "nsr_conv_wgrad_partial: 1x1 contractions on split-tile-image operands (tcgen05 engine) only");
+  return conv_wgrad_tc_partial(*d, splitk, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int64_t nsr_reduce_entry_blocks(int cout, int cin) {
+  const int64_t b = ((int64_t)cout * (cin + 1) + 1023) / 1024;  // ~4 outputs per thread
+  return b < 1 ? 1 : b;
+}
+extern "C" int nsr_wgrad_finalize_multi(const NsrReduceEntry* table_dev, int n_entries, int64_t total_blocks, void* stream) {
+  NSR_CHECK_ARG(table_dev && n_entries > 0 && total_blocks > 0 && total_blocks < (1ll << 31), "nsr_wgrad_finalize_multi: bad arguments");
+  wgrad_finalize_multi<<<(unsigned)total_blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table_dev, n_entries);
+  NSR_CHECK_LAUNCH("wgrad_finalize_multi");
   return NSR_OK;
 }
 

@@ -767,6 +767,25 @@ static int launch_wgrad_tc(const NsrWgrad& d, const WgPlan& p, float* partial, c
   return NSR_OK;
 }
 
+// split-K partials only (the caller reduces them later: nsr_wgrad_finalize_multi); returns the number of splits
+int conv_wgrad_tc_partial(const NsrWgrad& d, int* splitk, cudaStream_t st) {
+  WgPlan p = wg_plan(d);
+  const size_t need = p.dw_partial_floats * sizeof(float);
+  if (d.workspace_bytes < need || d.workspace == nullptr) {
+    set_error("nsr_conv_wgrad_partial: workspace %zu < %zu", d.workspace_bytes, need);
+    return NSR_E_WORKSPACE;
+  }
+  float* partial = reinterpret_cast<float*>(d.workspace);
+  *splitk = p.g.splitk;
+  switch (p.bn) {
+    case 64: return launch_wgrad_tc<64, true>(d, p, partial, st);
+    case 128: return launch_wgrad_tc<128, true>(d, p, partial, st);
+    case 192: return launch_wgrad_tc<192, true>(d, p, partial, st);
+    default: return launch_wgrad_tc<256, true>(d, p, partial, st);
+  }
+}
+size_t conv_wgrad_tc_partial_bytes(const NsrWgrad& d) { return wg_plan(d).dw_partial_floats * sizeof(float); }
+
 int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st) {
   WgPlan p = wg_plan(d);
   const size_t need = (p.dw_partial_floats + p.bias_partial_floats) * sizeof(float);

@@ -20,6 +20,7 @@ class ParamSet:
         self._params = dict(module.named_parameters())
         self._packed: dict = {}
         self._pack_tables: dict = {}
+        self.deferred = ops.DeferredWgrads()  # 1x1 weight gradients reduced in one launch at the end of a backward pass
         self.flat_grad: Tensor | None = None
         self._grads: dict = {}
         self.device = None

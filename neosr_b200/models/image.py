@@ -107,9 +107,10 @@ class image:
         self.ema = train_opt.get("ema", -1)
         if self.ema > 0:
             self.net_g_ema = AveragedModel(self.net_g, multi_avg_fn=get_ema_multi_avg_fn(self.ema), device=self.device)
-        for k in ("wavelet_guided", "match_lq_colors"):
-            if train_opt.get(k):
-                raise NotImplementedError(f"neosr_b200.image: train.{k} is outside the built hot path (SURVEY.md §8f.4)")
+        if train_opt.get("wavelet_guided"):
+            raise NotImplementedError("neosr_b200.image: train.wavelet_guided is outside the built hot path (SURVEY.md §8f.4; "
+                                      "the reference's wavelet transform needs PyWavelets)")
+        self.match_lq_colors = bool(train_opt.get("match_lq_colors", False))  # image.py:130, 451-463, 484-485
         # opt-in step variants (image.py:90-91, 136-146): F-SAM double closure and ECO centroid targets
         self.sam = train_opt.get("sam", None)
         self.sam_init = train_opt.get("sam_init", -1)
@@ -302,8 +303,11 @@ class image:
             v, g = self.cri_mssim.value_and_grad(out, self.gt, True, total)
             logs["l_g_mssim"] = v
             dout = g if dout is None else ops.axpby(dout, 1.0, g, 1.0, out=dout)
-        if self.cri_consistency is not None:  # image.py:500-503
-            v, g = self.cri_consistency.value_and_grad(out, self.gt, True, total)
+        if self.cri_consistency is not None:  # image.py:484-489
+            tgt = self.gt
+            if self.match_lq_colors:  # colours / luma are matched to the up-sampled LQ instead of the GT (451-463)
+                tgt = ops.clamp(ops.resize_aa(self.lq, "bicubic", scale_factor=self.scale), 1.0 / 255.0, 1.0)
+            v, g = self.cri_consistency.value_and_grad(out, tgt, True, total)
             logs["l_g_consistency"] = v
             dout = g if dout is None else ops.axpby(dout, 1.0, g, 1.0, out=dout)
         if self.cri_perceptual is not None:

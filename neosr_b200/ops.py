@@ -487,6 +487,76 @@ def conv_wgrad_mapped_rows(x_sti: STI, dy_sti: STI, dw: Tensor, dbias: Tensor | 
     _count(4 if dbias is not None else 3)
 
 
+class DeferredWgrads:
+    """1x1 weight gradients whose split-K partials are reduced LATER, all together (`nsr_wgrad_finalize_multi`): `add`
+    runs only the tcgen05 contraction into a per-layer buffer, `finalize` (end of the backward pass) is one launch that
+    writes every dW / dbias, un-padding head-padded rows / columns and splitting off the bias-gradient column."""
+
+    def __init__(self):
+        self.jobs: list = []
+        self.buffers: dict = {}
+        self.tables: dict = {}
+
+    def add(self, key, x_sti: STI, dy_sti: STI, dw: Tensor, dbias: Tensor | None, *, row_map: Tensor | None = None,
+            col_map: Tensor | None = None, bias_col: int | None = None) -> None:
+        """row_map / col_map: padded -> real channel maps (-1 = padding) of dy_sti's / x_sti's channels, or None."""
+        _chk(dw, "dw"), _chk(dbias, "dbias")
+        B, H, W, cx = x_sti.shape
+        gout = dy_sti.shape[-1]
+        cout, cin = dw.shape[0], dw.shape[1]
+        cw = cx
+        if dbias is not None and bias_col is None:  # LayerNorm-style image: 1.0 in the first padding channel
+            if not (x_sti.ones and cx % 64 != 0 and cx + 4 <= (cx + 63) // 64 * 64):
+                raise ValueError("DeferredWgrads: the input image carries no ones column for the bias gradient")
+            cw, bias_col = cx + 4, cx
+        d = NsrWgrad(batch=B, h=H, w=W, cin=cw, cout=gout, kh=1, kw=1, pad=0, x_ld=cw, dy_ld=gout, engine=ENGINE["auto"],
+                     x=None, dy=None, dw=None, dbias=None, workspace=None, workspace_bytes=0, x_sti=x_sti.data_ptr(),
+                     dy_sti=dy_sti.data_ptr())
+        L = _lib.lib()
+        need = L.nsr_conv_wgrad_partial_workspace(C.byref(d))
+        if need == 0:
+            raise RuntimeError("DeferredWgrads: shape not supported by the tcgen05 wgrad kernel")
+        buf = self.buffers.get(key)
+        if buf is None or buf.numel() < need:
+            buf = self.buffers[key] = torch.empty(need, dtype=torch.uint8, device=dw.device)
+        d.workspace, d.workspace_bytes = buf.data_ptr(), buf.numel()
+        splitk = C.c_int(0)
+        M = B * H * W
+        with _prof("conv_wgrad_sti", (M, cx, gout, 1), 2.0 * M * cx * gout, 4.0 * M * (cx + gout)):
+            check(L.nsr_conv_wgrad_partial(C.byref(d), C.byref(splitk), _stream()), "nsr_conv_wgrad_partial")
+        _count(1)
+        self.jobs.append(dict(partial=buf.data_ptr(), dw=dw.data_ptr(), dbias=_p(dbias),
+                              row_map=None if row_map is None else _inverse_map(row_map, cout).data_ptr(),
+                              col_map=None if col_map is None else _inverse_map(col_map, cin).data_ptr(),
+                              splitk=splitk.value, p_rows=gout, p_cols=cw, cout=cout, cin=cin,
+                              bias_col=-1 if bias_col is None else bias_col))
+
+    def finalize(self) -> None:
+        if not self.jobs:
+            return
+        jobs, self.jobs = self.jobs, []
+        key = tuple(tuple(j.values()) for j in jobs)
+        ent = self.tables.get(key)
+        L = _lib.lib()
+        if ent is None:
+            arr = (_lib.NsrReduceEntry * len(jobs))()
+            base = 0
+            for i, j in enumerate(jobs):
+                for k, v in j.items():
+                    setattr(arr[i], k, v)
+                arr[i].block_base = base
+                base += L.nsr_reduce_entry_blocks(j["cout"], j["cin"])
+            dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(torch.device("cuda", torch.cuda.current_device()))
+            ent = self.tables[key] = (dev, len(jobs), base)
+            if len(self.tables) > 4:
+                self.tables.pop(next(iter(self.tables)))
+        dev, n, blocks = ent
+        with _prof("nsr_wgrad_finalize_multi", (n,), 0.0, 0.0):
+            check(L.nsr_wgrad_finalize_multi(dev.data_ptr(), n, blocks, _stream()), "nsr_wgrad_finalize_multi")
+        _count(1)
+
+
+DEFER_WGRAD = os.environ.get("NSR_DEFER_WGRAD", "1") != "0"  # A/B switch for the deferred, batched wgrad reduction
 _I32_CACHE: dict = {}
 
 

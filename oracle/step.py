@@ -27,7 +27,7 @@ class OracleTrainer:
                  ema: float = 0.999, grad_clip: bool = True, disc: tuple | None = None,
                  gan_weight: float = 0.1, optim_d: dict | None = None, optim_type: str = "adan_sf",
                  mssim_weight: float | None = None, consistency_weight: float | None = None,
-                 eco: dict | None = None, sam: dict | None = None, scale: int = 4):
+                 eco: dict | None = None, sam: dict | None = None, scale: int = 4, match_lq_colors: bool = False):
         self.names = list(params)
         self.params = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
         self.net_fn = net_fn
@@ -44,6 +44,7 @@ class OracleTrainer:
         # opt-in step variants: ECO (image.py:393-425; keys iters, init, schedule, pretrain) and F-SAM
         # (optimizers/fsam.py; keys init = sam_init; rho 0.5, sigma 1, lmbda 0.9, adaptive as image.py:322-330 builds it)
         self.eco, self.sam, self.scale = eco, sam, scale
+        self.match_lq_colors = match_lq_colors  # image.py:451-463, 484-485
         self.sam_momentum: dict = {}
         # discriminator: (params, buffers) of oracle.unet; buffers are updated in place by each forward
         self.disc = None
@@ -135,8 +136,12 @@ class OracleTrainer:
             l_ms = L.msssim_loss(out, self.gt, self.mssim_weight)
             total = total + l_ms
             log["l_g_mssim"] = l_ms
-        if self.consistency_weight is not None:  # image.py:484-491 (match_lq_colors off)
-            l_co = L.consistency_loss(out, self.gt, self.consistency_weight)
+        if self.consistency_weight is not None:  # image.py:484-491
+            tgt = self.gt
+            if self.match_lq_colors:
+                import torch.nn.functional as F
+                tgt = torch.clamp(F.interpolate(self.lq, scale_factor=self.scale, mode="bicubic", antialias=True), 1 / 255, 1)
+            l_co = L.consistency_loss(out, tgt, self.consistency_weight)
             total = total + l_co
             log["l_g_consistency"] = l_co
         if self.percep_weight is not None:  # image.py:491-494

@@ -430,3 +430,36 @@ def test_eco_and_fsam_steps_vs_oracle(variant):
     if variant == "fsam":  # state names of the reference's fsam (fsam.py:41-58)
         st = model.sam_optimizer_g.state[next(iter(model.net_g.parameters()))]
         assert {"momentum", "old_p"} <= set(st)
+
+
+def test_match_lq_colors_step_vs_oracle():
+    """`train.match_lq_colors` (image.py:451-463, 484-485): the consistency loss targets the antialiased-bicubic up-sampled
+    LQ (clamped to [1/255, 1]) instead of the GT; three iterations (the third replays from CUDA graphs) vs the oracle."""
+    from neosr_b200.models import build_model
+    from oracle.compact import compact_forward, compact_param_shapes
+    from oracle.step import OracleTrainer
+    from oracle.swinir import synth_params
+    from neosr_b200.data.synthetic import structured_gt
+    optim = dict(lr=1e-3, betas=(0.98, 0.92, 0.987), weight_decay=0.02, schedule_free=True, warmup_steps=1600)
+    kw = dict(num_feat=32, num_conv=4, upscale=4)
+    opt = {"model_type": "image", "scale": 4, "is_train": True, "dist": False, "rank": 0, "world_size": 1,
+           "network_g": {"type": "compact", **kw}, "datasets": {"train": {"patch_size": 24}},
+           "train": {"ema": 0.999, "match_lq_colors": True, "optim_g": {"type": "adan_sf", **optim},
+                     "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0},
+                     "consistency_opt": {"type": "consistency_loss", "loss_weight": 1.0}}, "path": {}}
+    model = build_model(opt)
+    p = synth_params(compact_param_shapes(**kw), seed=31)
+    model.net_g.load_state_dict(p)
+    tr = OracleTrainer(p, lambda q, x: compact_forward(q, x, num_conv=4, upscale=4), pixel_weight=1.0, consistency_weight=1.0,
+                       optim=optim, ema=0.999, match_lq_colors=True, scale=4)
+    for it in range(3):
+        gt = structured_gt(40 + it, 2, 96, 96)
+        lq = torch.nn.functional.interpolate(gt, scale_factor=0.25, mode="bicubic", antialias=True).clamp(0, 1)
+        model.feed_data({"lq": lq, "gt": gt})
+        model.optimize_parameters(it + 1)
+        tr.feed_data({"lq": lq, "gt": gt})
+        tr.optimize_parameters(it + 1)
+        log, ref = model.get_current_log(), tr.get_current_log()
+        assert set(log) == set(ref)
+        for k, v in ref.items():
+            assert abs(log[k] - v) <= 1e-3 * max(1e-3, abs(v)), (it, k, log[k], v)
