@@ -8,6 +8,21 @@ from oracle import ref_shim
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="no reference tree (/root/reference or baseline/_ref)")
 
 
+@pytest.fixture(autouse=True)
+def _restore_reference_registries():
+    """The override is process-wide; the other CPU tests use the reference's registries as the ORACLE, so put every
+    entry back after each test here."""
+    ref_shim.activate()
+    import neosr_b200.plugin as plugin
+    plugin._force_reference_scans()
+    from neosr.utils.registry import ARCH_REGISTRY, LOSS_REGISTRY, MODEL_REGISTRY
+    saved = [(r, dict(r._obj_map)) for r in (ARCH_REGISTRY, LOSS_REGISTRY, MODEL_REGISTRY)]
+    yield
+    for r, m in saved:
+        r._obj_map.clear()
+        r._obj_map.update(m)
+
+
 def test_install_into_neosr_overrides_the_reference_registries():
     ref_shim.activate()
     import neosr_b200
