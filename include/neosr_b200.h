@@ -102,6 +102,12 @@ typedef struct NsrConv {
                             is stored at row ((b*H/ws + wy)*W/ws + wx)*ws*ws + iy*ws + ix, (wy,iy) = divmod((y - shift) mod H,
                             ws), (wx,ix) likewise: torch.roll(-shift) + window_partition (swinir_arch.py:41-57,356-366) folded
                             into the producing contraction's store, so nsr_window_attn_wsti_* bulk-copy whole windows */
+  int32_t aux_mode;      /* 0: aux is fp32.  2: aux is the 16-bit activation-gradient code below (actgrad = NSR_ACT_MULAUX).
+                            pre_mode = 2 likewise makes y_pre a uint16 buffer [pixels, y_ld] of codes
+                              code = rint((act'(pre) + 0.25) * 40000)      act' = code / 40000 - 0.25
+                            (|error| <= 1.25e-5 for GELU', whose range is [-0.13, 1.13]): the fc1 -> fc2-dgrad hand-over of a
+                            Swin MLP (swinir_arch.py:27-37) at half the bytes.  tcgen05 engine, split-tile-image output only:
+                            {act = GELU, y_pre, y_sti} and {actgrad = MULAUX, aux, y_sti}, no y / residual / row_scale */
   void* workspace;       /* optional scratch of nsr_conv_fprop_workspace() bytes: lets <= 4-channel convolutions */
   size_t workspace_bytes;/* (conv_first / conv_last, VGG conv1_1) run as im2col + one tensor-core contraction */
 } NsrConv;

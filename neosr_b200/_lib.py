@@ -31,6 +31,7 @@ class NsrConv(C.Structure):
         ("aux", C.c_void_p), ("row_scale", C.c_void_p), ("residual", C.c_void_p),
         ("y_pre", C.c_void_p), ("y", C.c_void_p), ("x_sti", C.c_void_p), ("y_sti", C.c_void_p),
         ("res_ld", C.c_int32), ("aux_ld", C.c_int32), ("pre_mode", C.c_int32), ("sti_win", C.c_int32),
+        ("aux_mode", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 

@@ -289,7 +289,7 @@ class swinir(nn.Module):
                                                   sti_out=sti, f32_out=not sti)
                 # hpre holds gelu'(fc1 pre-activation): the only thing the backward pass needs of it
                 a, hpre = lin(pre + "mlp.fc1", ln2, act="gelu", want_pre=True, pre_is_actgrad=True, sti_out=sti,
-                              f32_out=not sti)
+                              f32_out=not sti, pre_u16=sti and ops.AGC_U16)
                 x2 = lin(pre + "mlp.fc2", a, residual=x1, row_scale=ds[1] if ds else None)
                 if save:
                     S["blocks"].append((t, mu1, rs1, ln1, qkv, att, x1, mu2, rs2, ln2, hpre, a, ds))

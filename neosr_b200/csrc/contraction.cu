@@ -414,6 +414,7 @@ extern "C" int nsr_conv_fprop(const NsrConv* d, void* stream) {
   }
   if (eng == NSR_ENGINE_AUTO && conv_fprop_tc_supported(*d)) return conv_fprop_tc(*d, st);
   NSR_CHECK_ARG(d->x && d->y && !d->y_sti, "nsr_conv_fprop: split-tile-image operands need the tcgen05 engine");
+  NSR_CHECK_ARG(d->pre_mode != 2 && d->aux_mode == 0, "nsr_conv_fprop: 16-bit activation-gradient codes need the tcgen05 engine");
   if (eng == NSR_ENGINE_AUTO && conv_direct_enabled() && conv_direct_fprop_supported(*d)) return conv_direct_fprop(*d, st);
   if (eng == NSR_ENGINE_AUTO && narrow_gemm_enabled() && conv_narrow_gemm_supported(*d)) return conv_narrow_gemm_fprop(*d, st);
   if (eng == NSR_ENGINE_AUTO && conv_small_fprop_supported(*d)) return conv_small_fprop(*d, st);

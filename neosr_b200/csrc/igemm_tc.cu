@@ -17,7 +17,10 @@
 //   warps 10-13 epilogue   : tcgen05.ld TMEM -> registers, bias/activation/act-grad/row-scale/
 //                            residual, fp32 stores.  TMEM is double-buffered (2 x BN columns) so
 //                            the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cstdlib>
+#include <cstring>
 #include "tc_epilogue.cuh"
+#include "wgrad_geom.cuh"
 
 namespace nsr {
 using namespace tc;
@@ -241,6 +244,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
       const int n0 = (tile % g.n_tiles) * BN;
       int wrow_lane = 0;  // window-ordered STI output: where tile row p0 + lane goes (computed while the MMAs run)
       if (WIN && p0 + lane < g.M) wrow_lane = sti_win_row(d, p0 + lane, hw);
+      // The rows the epilogue will add (residual) or multiply by (aux) were last touched several kernels ago: pull this
+      // warp's pieces of them into L2 while the tile's MMAs run, so the loads inside the row loop see L2 latency, not
+      // HBM's (profiles/r02_x_ncu_stifprop_proj.txt: 56 % of the proj kernel's stall samples were the first FADD on them)
+      if (STI && (d.residual != nullptr || d.aux != nullptr) && p0 + lane < g.M) {
+        const long long pr = p0 + lane;
+        for (int c0 = slot * 32; c0 < BN; c0 += 32 * NSLOT) {
+          const int n = n0 + c0;
+          if (n >= d.cout) break;
+          if (d.residual) {
+            const char* a = reinterpret_cast<const char*>(d.residual + pr * (d.res_ld ? d.res_ld : d.y_ld) + n);
+            prefetch_l2(a);
+            prefetch_l2(a + 112);
+          }
+          if (d.aux) {
+            const long long e = pr * (d.aux_ld ? d.aux_ld : d.y_ld) + n;
+            const char* a = d.aux_mode == 2 ? reinterpret_cast<const char*>(reinterpret_cast<const uint16_t*>(d.aux) + e)
+                                            : reinterpret_cast<const char*>(d.aux + e);
+            prefetch_l2(a);
+            if (d.aux_mode != 2) prefetch_l2(a + 112);
+          }
+        }
+      }
       mbar_wait<STI ? 32 : 128>(&tfull[buf], bphase);  // idle epilogue warps must not spin against the producers
       tc_fence_after();
 #pragma unroll 1
@@ -296,6 +321,12 @@ bool conv_fprop_tc_supported(const NsrConv& d) {
     if (d.y_sti == nullptr || d.x_sti == nullptr || ws <= 0 || d.h % ws || d.w % ws || shift < 0 || shift >= ws) return false;
   }
   if (d.act != NSR_ACT_NONE && d.actgrad != NSR_ACT_NONE) return false;  // epilogue is specialised on one of them
+  if (d.pre_mode == 2 || d.aux_mode == 2) {  // 16-bit activation-gradient codes: exactly the two MLP hand-over epilogues
+    const bool plain = d.y_sti != nullptr && d.y == nullptr && d.residual == nullptr && d.row_scale == nullptr;
+    const bool fwd = d.pre_mode == 2 && d.aux_mode == 0 && d.act == NSR_ACT_GELU && d.actgrad == NSR_ACT_NONE && d.y_pre != nullptr;
+    const bool bwd = d.aux_mode == 2 && d.pre_mode == 0 && d.act == NSR_ACT_NONE && d.actgrad == NSR_ACT_MULAUX && d.y_pre == nullptr;
+    if (!plain || !(fwd || bwd)) return false;
+  }
   if (!aligned16(d.x) || !aligned16(d.y) || !aligned16(d.y_sti) || !aligned16(d.bias) || !aligned16(d.aux) || !aligned16(d.residual) ||
       !aligned16(d.y_pre) || !aligned16(d.prelu) || !aligned16(d.w_packed))
     return false;
@@ -375,18 +406,6 @@ struct WgCfg {
   static constexpr int stage_bytes = 2 * p_bytes + 2 * q_bytes;
   static constexpr int stages = (200 * 1024) / stage_bytes > 4 ? 4 : (200 * 1024) / stage_bytes;
   static constexpr int smem_bytes = stages * stage_bytes + 1024 + 256;
-};
-
-struct WgGeom {
-  int swap;            // 0: P = dy (rows = cout), Q = x (cols = cin); 1: P = x, Q = dy
-  int pc, qc;          // channel counts of P and Q
-  int p_ld, q_ld;
-  int m_tiles, n_tiles, taps, splitk, num_items;
-  long long M, rows_per_split;
-  const float* p_ptr;
-  const float* q_ptr;
-  const void* p_sti;
-  const void* q_sti;
 };
 
 int launch_wgrad_reduce(const float* partial, float* dw, int splitk, int cout, int taps, int cin, cudaStream_t st);
@@ -688,6 +707,22 @@ static int wg_pick_bn(int qc, int& cost) {
   return best;
 }
 
+static bool wg_is_sti(const NsrWgrad& d) { return d.x_sti != nullptr && d.dy_sti != nullptr && d.kh == 1 && d.kw == 1; }
+// process-wide tuning switches, read once (A/B measurements; the defaults are the measured best)
+static int wg_sti_knob(const char* name, int dflt) {
+  static const char* names[3] = {"NSR_WG_STI2", "NSR_WG_KPIX", "NSR_WG_PAIR"};
+  static int cached[3] = {-1, -1, -1};
+  for (int i = 0; i < 3; ++i)
+    if (name == names[i] || strcmp(name, names[i]) == 0) {
+      if (cached[i] < 0) {
+        const char* v = getenv(name);
+        cached[i] = v && *v ? atoi(v) : dflt;
+      }
+      return cached[i];
+    }
+  return dflt;
+}
+
 static WgPlan wg_plan(const NsrWgrad& d) {
   WgPlan p;
   WgGeom& g = p.g;
@@ -711,7 +746,19 @@ static WgPlan wg_plan(const NsrWgrad& d) {
   g.q_sti = g.swap ? d.dy_sti : d.x_sti;
   g.m_tiles = (g.pc + 127) / 128;
   g.n_tiles = (g.qc + p.bn - 1) / p.bn;
-  const int tiles = g.m_tiles * g.n_tiles * g.taps;
+  // split-tile-image operands run on igemm_wgrad_sti (short k-blocks, deep ring, optionally two row tiles per item)
+  g.mt = 1;
+  g.kpix = WG_KPIX;
+  if (wg_is_sti(d) && wg_sti_knob("NSR_WG_STI2", 1)) {
+    g.kpix = wg_sti_knob("NSR_WG_KPIX", 32) == 64 ? 64 : 32;
+    // two row tiles per item pay once P is wide (qkv: 576 rows, 122 -> 110 us); for 2 - 3 row tiles the longer items
+    // and the doubled partials cost more than the saved Q traffic (measured, tools/bench_wgrad.py).  NSR_WG_PAIR: 0 never, 2 always
+    const int pair = wg_sti_knob("NSR_WG_PAIR", 1);
+    g.mt = (pair == 2 && g.m_tiles >= 2) || (pair == 1 && g.m_tiles >= 4) ? 2 : 1;
+    if (g.mt == 2 && g.kpix == 64 && p.bn == 256) g.kpix = 32;  // that stage would not fit twice
+  }
+  g.m_groups = (g.m_tiles + g.mt - 1) / g.mt;
+  const int tiles = g.m_groups * g.n_tiles * g.taps;
   // Pixels per split: at most WG_MAX_ROWS_PER_SPLIT (the tensor-core accumulator truncates on every
   // add, so its error grows with the number of sequential accumulations; the fixed-order fp32 reduce
   // over split partials rounds to nearest), and such that tiles * splits fills whole waves of 148 CTAs.
@@ -767,6 +814,16 @@ static int launch_wgrad_tc(const NsrWgrad& d, const WgPlan& p, float* partial, c
   return NSR_OK;
 }
 
+static int launch_wgrad_sti_any(const NsrWgrad& d, const WgPlan& p, float* partial, cudaStream_t st) {
+  if (wg_sti_knob("NSR_WG_STI2", 1)) return launch_wgrad_sti(d, p.g, p.bn, partial, st);
+  switch (p.bn) {
+    case 64: return launch_wgrad_tc<64, true>(d, p, partial, st);
+    case 128: return launch_wgrad_tc<128, true>(d, p, partial, st);
+    case 192: return launch_wgrad_tc<192, true>(d, p, partial, st);
+    default: return launch_wgrad_tc<256, true>(d, p, partial, st);
+  }
+}
+
 // split-K partials only (the caller reduces them later: nsr_wgrad_finalize_multi); returns the number of splits
 int conv_wgrad_tc_partial(const NsrWgrad& d, int* splitk, cudaStream_t st) {
   WgPlan p = wg_plan(d);
@@ -777,12 +834,7 @@ int conv_wgrad_tc_partial(const NsrWgrad& d, int* splitk, cudaStream_t st) {
   }
   float* partial = reinterpret_cast<float*>(d.workspace);
   *splitk = p.g.splitk;
-  switch (p.bn) {
-    case 64: return launch_wgrad_tc<64, true>(d, p, partial, st);
-    case 128: return launch_wgrad_tc<128, true>(d, p, partial, st);
-    case 192: return launch_wgrad_tc<192, true>(d, p, partial, st);
-    default: return launch_wgrad_tc<256, true>(d, p, partial, st);
-  }
+  return launch_wgrad_sti_any(d, p, partial, st);
 }
 size_t conv_wgrad_tc_partial_bytes(const NsrWgrad& d) { return wg_plan(d).dw_partial_floats * sizeof(float); }
 
@@ -797,12 +849,7 @@ int conv_wgrad_tc(const NsrWgrad& d, cudaStream_t st) {
   int rc;
   const bool sti = d.x_sti != nullptr && d.dy_sti != nullptr && d.kh == 1 && d.kw == 1;
   if (sti) {
-    switch (p.bn) {
-      case 64: rc = launch_wgrad_tc<64, true>(d, p, partial, st); break;
-      case 128: rc = launch_wgrad_tc<128, true>(d, p, partial, st); break;
-      case 192: rc = launch_wgrad_tc<192, true>(d, p, partial, st); break;
-      default: rc = launch_wgrad_tc<256, true>(d, p, partial, st); break;
-    }
+    rc = launch_wgrad_sti_any(d, p, partial, st);
   } else {
     switch (p.bn) {
       case 64: rc = launch_wgrad_tc<64, false>(d, p, partial, st); break;

@@ -305,6 +305,10 @@ def head_pad_map(c: int, heads: int, groups: int) -> tuple:
     return tuple(m)
 
 
+# fc1 hands gelu'(pre) to fc2's dgrad as 16-bit codes (NsrConv.aux_mode) on the split-tile-image path; NSR_AGC_U16=0: fp32
+AGC_U16 = os.environ.get("NSR_AGC_U16", "1") != "0"
+
+
 def wsti_supported(c: int, heads: int, ws: int) -> bool:
     """Window-ordered attention operands: tcgen05 engine + the mma attention kernels' shape limits."""
     return sti_enabled() and _attn_mma_ok(c, heads, ws)
@@ -316,11 +320,13 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
                aux: Tensor | None = None, prelu: Tensor | None = None, row_scale: Tensor | None = None,
                residual: Tensor | None = None, want_pre: bool = False, out: Tensor | None = None,
                engine: str = "auto", sti_out: bool = False, f32_out: bool = True, pre_is_actgrad: bool = False,
-               sti_win: tuple | None = None):
+               sti_win: tuple | None = None, pre_u16: bool = False):
     """y = epilogue(conv(x, w)); x is [B,H,W,Cin] NHWC fp32 or an STI (1x1 only).  With dgrad=True
     the dgrad-packed filter is used and the roles of cin/cout swap (x is then dY [B,H,W,Cout]).
     sti_out / f32_out select the output formats: returns y (fp32), or the STI, or (y, sti).
-    sti_win = (ws, shift): the STI's rows are written in window order (NsrConv.sti_win)."""
+    sti_win = (ws, shift): the STI's rows are written in window order (NsrConv.sti_win).
+    pre_u16 (with pre_is_actgrad, STI-only output): y_pre is returned as int16 activation-gradient codes (NsrConv.aux_mode);
+    an int16 `aux` is read as such codes."""
     x_is_sti = isinstance(x, STI)
     if not x_is_sti and not isinstance(x, Slab):
         _chk(x, "x")
@@ -344,7 +350,12 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
                   "nsr_conv_lk16_fprop")
         _count(1)
         return y
-    aux_ptr, aux_ld = _ptr_ld(aux)
+    if aux is not None and not isinstance(aux, Slab) and aux.dtype == torch.int16:  # activation-gradient codes
+        if not (aux.is_cuda and aux.is_contiguous()):
+            raise ValueError("aux: expected a contiguous CUDA int16 tensor of activation-gradient codes")
+        aux_ptr, aux_ld = aux.data_ptr(), aux.shape[-1]
+    else:
+        aux_ptr, aux_ld = _ptr_ld(aux)
     res_ptr, res_ld = _ptr_ld(residual)
     y = None
     if f32_out:
@@ -357,7 +368,10 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
         y_sti.ones = cout % 64 != 0
     if y is None and y_sti is None:
         raise ValueError("conv_fprop: no output format selected")
-    y_pre = torch.empty((B, H, W, cout), dtype=torch.float32, device=x.device) if want_pre else None
+    if pre_u16 and not (want_pre and pre_is_actgrad and sti_out and not f32_out):
+        raise ValueError("conv_fprop: pre_u16 needs want_pre, pre_is_actgrad and a split-tile-image-only output")
+    y_pre = torch.empty((B, H, W, cout), dtype=torch.int16 if pre_u16 else torch.float32, device=x.device) if want_pre else None
+    aux_u16 = aux is not None and not isinstance(aux, Slab) and aux.dtype == torch.int16
     d = NsrConv(batch=B, h=H, w=W, cin=cin, cout=cout, kh=pw.kh, kw=pw.kw, pad=pw.kh // 2,
                 x_ld=x_ld, y_ld=y_ld, act=ACT[act], act_slope=act_slope, actgrad=ACT[actgrad],
                 actgrad_slope=actgrad_slope, engine=ENGINE[DEFAULT_ENGINE if engine == "auto" else engine],
@@ -365,7 +379,8 @@ def conv_fprop(x: Tensor, pw: PackedWeight, bias: Tensor | None = None, *, dgrad
                 bias=_p(bias), prelu=_p(prelu), aux=aux_ptr, row_scale=_p(row_scale), residual=res_ptr,
                 y_pre=_p(y_pre), y=y_ptr, x_sti=x.data_ptr() if x_is_sti else None, y_sti=_p(y_sti),
                 res_ld=res_ld if res_ld != y_ld else 0, aux_ld=aux_ld if aux_ld != y_ld else 0,
-                pre_mode=1 if pre_is_actgrad else 0, sti_win=(sti_win[0] | (sti_win[1] << 16)) if sti_win else 0,
+                pre_mode=(2 if pre_u16 else 1) if pre_is_actgrad else 0, aux_mode=2 if aux_u16 else 0,
+                sti_win=(sti_win[0] | (sti_win[1] << 16)) if sti_win else 0,
                 workspace=None, workspace_bytes=0)
     if min(cin, cout) <= 4:  # image-side convs: im2col + tensor-core contraction needs scratch
         need = _lib.lib().nsr_conv_fprop_workspace(C.byref(d))
