@@ -196,7 +196,10 @@ def displacement_report(p0: dict, ours: dict, ref32: dict, ref64: dict, noise_to
     direction decided by noise - in the reference as much as anywhere.  Such elements are identified with the reference
     itself: where its fp32 and fp64 runs (`ref32`, `ref64`: name -> tensor) disagree by more than `noise_tol` of the step,
     fp32 round-off decides the step and the element says nothing about an implementation.  On the rest, the displacement
-    of `ours` is compared with the fp32 reference's.
+    of `ours` is compared with the fp32 reference's.  The key third of every `*.attn.qkv.bias` is excluded outright: its
+    gradient is identically zero, so the fp32-vs-fp64 test only catches those of its elements where the oracle's own noise
+    happened to disagree - the others would be scored on a coin toss (seen: 8 % on one qkv.bias under F-SAM after a change
+    that only re-ordered fp32 sums).
 
     Returns {"worst": (rel-L2 error on the mask, name), "coverage": min over tensors of the fraction of elements kept,
     "coverage_all": fraction of ALL elements kept, "cos": cosine between the two displacement vectors over ALL elements
@@ -211,6 +214,9 @@ def displacement_report(p0: dict, ours: dict, ref32: dict, ref64: dict, noise_to
         d32, d64 = ref32[k].detach().double() - i64, ref64[k].detach().double() - i64
         do = ours[k].detach().double().cpu() - i64
         mask = (d32 - d64).abs() <= noise_tol * d64.abs()
+        if k.endswith("attn.qkv.bias") and mask.dim() == 1 and mask.numel() % 3 == 0:
+            c = mask.numel() // 3
+            mask[c:2 * c] = False  # key bias: d softmax / d(constant shift of the scores) = 0
         cov = float(mask.double().mean())
         kept += int(mask.sum())
         total += mask.numel()
