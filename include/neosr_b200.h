@@ -332,6 +332,13 @@ int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
                       const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
                       int rows, int c, void* workspace, size_t workspace_bytes, void* dx_sti, void* stream);
 
+/* Same, with two more options for the Swin blocks' split-tile-image path: the residual-branch gradient may arrive as a
+ * split tile image (dres_sti; hi + lo bf16 ~ 2^-17 relative; alternative to dres), and dx may be NULL when dx_sti is given -
+ * inside a residual group the gradient of the token stream then lives in ONE format instead of fp32 + tile image. */
+int nsr_layernorm_bwd2(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       const float* dres, const void* dres_sti, float* dx, float* dgamma, float* dbeta, int rows, int c,
+                       void* workspace, size_t workspace_bytes, void* dx_sti, void* stream);
+
 /* ------------------------------------------------------------------ window attention --- */
 /*
  * Fused (shifted-)window multi-head self-attention core on token-major qkv:

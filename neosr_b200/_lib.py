@@ -138,6 +138,7 @@ SIGNATURES = {
     "nsr_sti_to_f32": (_i, [_p, C.c_longlong, _i, _p, _i, _p]),
     "nsr_layernorm_bwd_workspace": (_z, [_i]),
     "nsr_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _z, _p, _p]),
+    "nsr_layernorm_bwd2": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _z, _p, _p]),
     "nsr_window_attn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p]),
     "nsr_window_attn_bwd_workspace": (_z, [_i, _i]),
     "nsr_window_attn_wsti_channels": (_i, [_i]),

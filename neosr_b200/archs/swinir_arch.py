@@ -430,13 +430,16 @@ class swinir(nn.Module):
                 pre = f"layers.{li}.residual_group.blocks.{bi}."
                 t0, mu1, rs1, ln1, qkv, att, x1, mu2, rs2, ln2, hpre, a, ds = S["blocks"][bi_glob]
                 shift = self.layers[li].residual_group.blocks[bi].shift_size
-                gf = split(g)[0]
+                # inside a residual group the token-stream gradient lives as a tile image only (ops.LN_STI_RES): the
+                # LayerNorm backward of the block above reads its residual term from the image and writes no fp32 copy
+                gf = split(g)[0] if split(g)[0] is not None else split(g)[1]
                 gb = scaled(g, ds[1] if ds else None)
                 dh = bwd(pre + "mlp.fc2", a, gb, actgrad="mulaux", aux=hpre, sti_out=sti, f32_out=not sti)
                 dln2 = bwd(pre + "mlp.fc1", ln2, dh)
+                lean = sti and ops.LN_STI_RES and ds is None
                 g1 = ops.layernorm_bwd(dln2, x1, ps.p(pre + "norm2.weight"), mu2, rs2, ps.g(pre + "norm2.weight"),
-                                       ps.g(pre + "norm2.bias"), dres=gf, sti_out=sti)
-                g1f = split(g1)[0]
+                                       ps.g(pre + "norm2.bias"), dres=gf, sti_out=sti, f32_out=not lean)
+                g1f = split(g1)[0] if split(g1)[0] is not None else split(g1)[1]
                 gb = scaled(g1, ds[0] if ds else None)
                 if isinstance(qkv, ops.STI):  # window-ordered operands (see engine_forward)
                     pwm = ps.pw_mapped(pre + "attn.proj.weight", "proj_cols", None,
@@ -472,7 +475,8 @@ class swinir(nn.Module):
                 if not (isinstance(qkv, ops.STI) and att.shape[-1] != self.embed_dim):
                     dln1 = bwd(pre + "attn.qkv", ln1, dqkv)
                 g = ops.layernorm_bwd(dln1, t0, ps.p(pre + "norm1.weight"), mu1, rs1, ps.g(pre + "norm1.weight"),
-                                      ps.g(pre + "norm1.bias"), dres=g1f, sti_out=sti and bi > 0)
+                                      ps.g(pre + "norm1.bias"), dres=g1f, sti_out=sti and bi > 0,
+                                      f32_out=not (lean and bi > 0 and (S["blocks"][bi_glob - 1][-1] is None)))
             g = ops.axpby(split(g)[0], 1.0, dinp, 1.0)
         if self.patch_norm:
             mu, rs = S["pe"]

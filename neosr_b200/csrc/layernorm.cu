@@ -261,11 +261,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 4) layernorm_fwd_v3(const float
   }
 }
 
-template <int NCH>
+// DSTI: the residual-branch gradient `dres` arrives as a split tile image (hi + lo bf16, ~2^-17 relative) instead of fp32,
+// so the producing LayerNorm backward of the block above does not have to write an fp32 copy next to its tile image.
+template <int NCH, bool DSTI = false>
 __global__ void __launch_bounds__(LN_WARPS * 32, NCH == 1 ? 4 : 2) layernorm_bwd_v2(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
-    float* __restrict__ dx, uint8_t* __restrict__ dx_sti, float* __restrict__ partial, int rows, int C) {
+    float* __restrict__ dx, uint8_t* __restrict__ dx_sti, float* __restrict__ partial, int rows, int C,
+    const uint8_t* __restrict__ dres_sti = nullptr) {
   extern __shared__ float sm[];  // [LN_WARPS][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kbs = (C + 63) / 64;
@@ -314,7 +317,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NCH == 1 ? 4 : 2) layernorm_bwd
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = (c0 + e < C) ? rs * (g[k][e] * gm[k][e] - s1 - xh[k][e] * s2) : 0.f;
-      if (dres) {
+      if (DSTI) {
+        if (c0 < C) {
+          const int rr = (int)(r & 127), kb = ch >> 3, cc = ch & 7;
+          const uint8_t* src = dres_sti + ((size_t)((r >> 7) * kbs + kb) << 15) + rr * 128 + ((cc ^ (rr & 7)) << 4);
+          const uint4 hi = *reinterpret_cast<const uint4*>(src), lo = *reinterpret_cast<const uint4*>(src + 16384);
+          const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {  // channels >= C of the image hold the ones column / zero padding: not part of dres
+            if (c0 + 2 * e < C) o[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            if (c0 + 2 * e + 1 < C) o[2 * e + 1] += __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
+          }
+        }
+      } else if (dres) {
         if (c0 < C) {
           const float4 ra = *reinterpret_cast<const float4*>(dres + r * C + c0);
           o[0] += ra.x; o[1] += ra.y; o[2] += ra.z; o[3] += ra.w;
@@ -406,10 +421,11 @@ extern "C" int nsr_layernorm_fwd(const float* x, const float* gamma, const float
   return NSR_OK;
 }
 extern "C" size_t nsr_layernorm_bwd_workspace(int c) { return (size_t)LN_MAX_BLOCKS * 2 * c * sizeof(float); }
-extern "C" int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
-                                 const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta, int rows,
-                                 int c, void* workspace, size_t workspace_bytes, void* dx_sti, void* stream) {
+extern "C" int nsr_layernorm_bwd2(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                                  const float* dres, const void* dres_sti, float* dx, float* dgamma, float* dbeta, int rows,
+                                  int c, void* workspace, size_t workspace_bytes, void* dx_sti, void* stream) {
   NSR_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_sti) && rows > 0 && c > 0, "nsr_layernorm_bwd: bad arguments");
+  NSR_CHECK_ARG(!(dres && dres_sti), "nsr_layernorm_bwd: dres and dres_sti are alternatives");
   NSR_CHECK_ARG(c <= 704, "nsr_layernorm_bwd: C > 704 not supported");
   if (!workspace || workspace_bytes < nsr_layernorm_bwd_workspace(c)) {
     set_error("nsr_layernorm_bwd: workspace too small");
@@ -419,17 +435,28 @@ extern "C" int nsr_layernorm_bwd(const float* dy, const float* x, const float* g
   const int blocks = ln_blocks(rows);
   const size_t smem = (size_t)LN_WARPS * 2 * c * sizeof(float);
   float* partial = reinterpret_cast<float*>(workspace);
-  if (ln_v2_ok(x, dy, dres, dx, c) && (reinterpret_cast<uintptr_t>(dx_sti) & 15) == 0) {
+  const uint8_t* rsti = reinterpret_cast<const uint8_t*>(dres_sti);
+  if (ln_v2_ok(x, dy, dres, dx, c) && (reinterpret_cast<uintptr_t>(dx_sti) & 15) == 0 && (reinterpret_cast<uintptr_t>(dres_sti) & 15) == 0) {
     uint8_t* sti = reinterpret_cast<uint8_t*>(dx_sti);
-    if (c <= 256) layernorm_bwd_v2<1><<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, sti, partial, rows, c);
-    else if (c <= 512) layernorm_bwd_v2<2><<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, sti, partial, rows, c);
-    else layernorm_bwd_v2<3><<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, sti, partial, rows, c);
+#define NSR_LN_BWD(NCH)                                                                                                          \
+  if (rsti) layernorm_bwd_v2<NCH, true><<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, nullptr, dx, sti, partial, rows, c, rsti); \
+  else layernorm_bwd_v2<NCH, false><<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, sti, partial, rows, c)
+    if (c <= 256) { NSR_LN_BWD(1); }
+    else if (c <= 512) { NSR_LN_BWD(2); }
+    else { NSR_LN_BWD(3); }
+#undef NSR_LN_BWD
   } else {
-    NSR_CHECK_ARG(dx && !dx_sti, "nsr_layernorm_bwd: split-tile-image output needs C % 4 == 0 and 16-byte alignment");
+    NSR_CHECK_ARG(dx && !dx_sti && !dres_sti, "nsr_layernorm_bwd: split-tile-image operands need C % 4 == 0 and 16-byte alignment");
     layernorm_bwd_kernel<<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, partial, rows, c);
   }
   NSR_CHECK_LAUNCH("layernorm_bwd");
   layernorm_bwd_final<<<ceil_div(2 * c, 32), 1024, 0, st>>>(partial, dgamma, dbeta, blocks, c);
   NSR_CHECK_LAUNCH("layernorm_bwd_final");
   return NSR_OK;
+}
+extern "C" int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                                 const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta, int rows,
+                                 int c, void* workspace, size_t workspace_bytes, void* dx_sti, void* stream) {
+  return nsr_layernorm_bwd2(dy, x, gamma, mean, rstd, dres, nullptr, dx, dgamma, dbeta, rows, c, workspace, workspace_bytes,
+                            dx_sti, stream);
 }

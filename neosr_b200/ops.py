@@ -307,6 +307,8 @@ def head_pad_map(c: int, heads: int, groups: int) -> tuple:
 
 # fc1 hands gelu'(pre) to fc2's dgrad as 16-bit codes (NsrConv.aux_mode) on the split-tile-image path; NSR_AGC_U16=0: fp32
 AGC_U16 = os.environ.get("NSR_AGC_U16", "1") != "0"
+# the LayerNorm backward kernels of a Swin block pass the token-stream gradient on as a tile image only; NSR_LN_STI_RES=0: fp32 + image
+LN_STI_RES = os.environ.get("NSR_LN_STI_RES", "1") != "0"
 
 
 def wsti_supported(c: int, heads: int, ws: int) -> bool:
@@ -924,23 +926,30 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, sti
 
 
 def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dgamma: Tensor, dbeta: Tensor,
-                  dres: Tensor | None = None, sti_out: bool = False):
-    """dx (fp32) [, dx as STI when sti_out]."""
+                  dres: "Tensor | STI | None" = None, sti_out: bool = False, f32_out: bool = True):
+    """dx = LN'(dy) + dres as fp32, as an STI, or (fp32, STI) per f32_out / sti_out; dres may be fp32 or an STI."""
     for t, n in ((dy, "dy"), (x, "x"), (gamma, "gamma"), (mean, "mean"), (rstd, "rstd"), (dgamma, "dgamma"),
-                 (dbeta, "dbeta"), (dres, "dres")):
+                 (dbeta, "dbeta")):
         _chk(t, n)
+    res_sti = dres if isinstance(dres, STI) else None
+    res_f32 = None if res_sti is not None else dres
+    _chk(res_f32, "dres")
+    if not (f32_out or sti_out):
+        raise ValueError("layernorm_bwd: no output format selected")
+    if res_sti is not None and res_sti.shape != tuple(x.shape):
+        raise ValueError(f"layernorm_bwd: dres image {res_sti.shape} vs x {tuple(x.shape)}")
     c = x.shape[-1]
     rows = x.numel() // c
-    dx = torch.empty_like(x)
+    dx = torch.empty_like(x) if f32_out else None
     dx_sti = STI(x.shape, x.device) if sti_out else None
     L = _lib.lib()
     ws = scratch(L.nsr_layernorm_bwd_workspace(c), x.device)
     with _prof("nsr_layernorm_bwd", (rows, c), 0.0, (16.0 if dres is not None else 12.0) * x.numel()):
-        check(L.nsr_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(dres),
-                                  dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, c, ws.data_ptr(), ws.numel(),
-                                  _p(dx_sti), _stream()), "nsr_layernorm_bwd")
+        check(L.nsr_layernorm_bwd2(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(res_f32),
+                                   _p(res_sti), _p(dx), dgamma.data_ptr(), dbeta.data_ptr(), rows, c, ws.data_ptr(), ws.numel(),
+                                   _p(dx_sti), _stream()), "nsr_layernorm_bwd")
     _count(2)
-    return (dx, dx_sti) if sti_out else dx
+    return dx if dx_sti is None else (dx_sti if dx is None else (dx, dx_sti))
 
 
 # ----------------------------------------------------------------------------- attention

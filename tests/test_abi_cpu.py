@@ -34,7 +34,8 @@ def test_struct_layouts_match_header_sizes():
     """ctypes mirrors of the ABI structs: pointer-sized fields, no implicit padding surprises."""
     from neosr_b200._lib import NsrAdanSF, NsrConv, NsrParamEntry, NsrWgrad
     assert ctypes.sizeof(NsrParamEntry) == 8 * 8 + 16
-    assert ctypes.sizeof(NsrConv) == 15 * 4 + 4 + 11 * 8 + 16 + 16   # 15 ints/floats, pad to 8, 11 pointers, 4 ints, ws ptr + size
+    # 15 ints/floats, pad to 8, 11 pointers, 5 ints (res_ld, aux_ld, pre_mode, sti_win, aux_mode) padded to 8, ws ptr + size
+    assert ctypes.sizeof(NsrConv) == 15 * 4 + 4 + 11 * 8 + 24 + 16
     assert ctypes.sizeof(NsrWgrad) == 11 * 4 + 4 + 5 * 8 + 8 + 2 * 8
     assert ctypes.sizeof(NsrAdanSF) == 18 * 4
 
