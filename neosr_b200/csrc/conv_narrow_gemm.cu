@@ -272,8 +272,7 @@ int conv_narrow_gemm_wgrad(const NsrWgrad& d, cudaStream_t st) {
   narrow_dw_scatter<<<ceil_div(d.cout * d.cin * taps, 256), 256, 0, st>>>(gmat, d.dw, d.cout, d.cin, taps, e.cin, n2w ? 0 : 1);
   NSR_CHECK_LAUNCH("narrow_dw_scatter");
   if (!n2w && d.dbias) {
-    int bias_blocks = (int)((M + 1023) / 1024);
-    if (bias_blocks > kNumSMs * 4) bias_blocks = kNumSMs * 4;
+    int bias_blocks = bias_grad_blocks(M);
     return conv_bias_grad(d, bias_partial, bias_blocks, st);
   }
   return NSR_OK;

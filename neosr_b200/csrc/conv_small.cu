@@ -343,8 +343,7 @@ int conv_small_wgrad(const NsrWgrad& d, cudaStream_t st) {
   }
   if (d.dbias) {
     float* bias_partial = partial + (size_t)CS_WGRAD_BLOCKS * (d.cout <= 4 ? d.cout : d.cin) * CS_MAXTAPS * 64;
-    int bias_blocks = (int)((g.M + 1023) / 1024);
-    if (bias_blocks > kNumSMs * 4) bias_blocks = kNumSMs * 4;
+    int bias_blocks = bias_grad_blocks(g.M);
     return conv_bias_grad(d, bias_partial, bias_blocks, st);
   }
   return NSR_OK;

@@ -173,8 +173,7 @@ static WgradPlan wgrad_plan(const NsrWgrad& d) {
   p.rows_per_split = (rps + WBK - 1) / WBK * WBK;
   p.splitk = (int)((M + p.rows_per_split - 1) / p.rows_per_split);
   p.dw_partial_floats = (size_t)p.splitk * d.cout * p.taps * d.cin;
-  p.bias_blocks = (int)((M + 1023) / 1024);
-  if (p.bias_blocks > kNumSMs * 4) p.bias_blocks = kNumSMs * 4;
+  p.bias_blocks = bias_grad_blocks(M);
   p.bias_partial_floats = (size_t)p.bias_blocks * d.cout;
   return p;
 }

@@ -774,8 +774,7 @@ static WgPlan wg_plan(const NsrWgrad& d) {
   g.splitk = (int)((g.M + g.rows_per_split - 1) / g.rows_per_split);
   g.num_items = tiles * g.splitk;
   p.dw_partial_floats = (size_t)g.splitk * d.cout * g.taps * d.cin;
-  p.bias_blocks = (int)((g.M + 1023) / 1024);
-  if (p.bias_blocks > kNumSMs * 4) p.bias_blocks = kNumSMs * 4;
+  p.bias_blocks = bias_grad_blocks(g.M);
   p.bias_partial_floats = (size_t)p.bias_blocks * d.cout;
   return p;
 }

