@@ -44,6 +44,9 @@ extern "C" {
 #define NSR_ENGINE_SIMT 1    /* exact-fp32 CUDA-core implicit GEMM */
 #define NSR_ENGINE_TCGEN05 2 /* tcgen05 (UMMA) 3xBF16-split, fp32 accumulate in TMEM */
 #define NSR_ENGINE_MMA_SYNC 3 /* nsr_window_attn_wsti_*: the warp-level mma.sync kernels instead of tcgen05 (A/B runs) */
+#define NSR_ENGINE_BF16 4     /* nsr_conv_fprop / nsr_conv_wgrad(_partial): routed like NSR_ENGINE_AUTO, but the tcgen05 kernels
+                                 issue ONE bf16 pass (hi x hi, fp32 accumulate) and fetch no lo halves - the mixed-precision mode
+                                 behind `use_amp` + `bfloat16` (neosr/models/image.py:117-127); everything stored stays fp32 */
 
 const char* nsr_last_error(void);
 int nsr_version(void);

@@ -79,7 +79,7 @@ class NsrAdamW(C.Structure):
 
 OPT_CHUNK = 4096
 ACT = {"none": 0, "relu": 1, "lrelu": 2, "gelu": 3, "prelu": 4, "mulaux": 5}
-ENGINE = {"auto": 0, "simt": 1, "tcgen05": 2, "mma_sync": 3}
+ENGINE = {"auto": 0, "simt": 1, "tcgen05": 2, "mma_sync": 3, "bf16": 4}
 
 _i, _f, _p, _z, _l = C.c_int, C.c_float, C.c_void_p, C.c_size_t, C.c_int64
 # name -> (restype, argtypes): every symbol include/neosr_b200.h declares.

@@ -32,6 +32,9 @@ void set_error(const char* fmt, ...);
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 __host__ __device__ static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// NSR_ENGINE_BF16 = NSR_ENGINE_AUTO routing with single-pass tensor-core products
+static inline int mma_passes(int engine) { return engine == NSR_ENGINE_BF16 ? 1 : 3; }
+static inline int route_engine(int engine) { return engine == NSR_ENGINE_BF16 ? NSR_ENGINE_AUTO : engine; }
 constexpr int kNumSMs = 148;  // B200
 // row blocks of the bias-gradient column sums (colsum_partial): 256 rows each, at most four waves.  (1024 rows per block
 // left a 32768-pixel problem - HAT at B = 8 - with 32 CTAs: 31 us per launch, 11 % of that step.)

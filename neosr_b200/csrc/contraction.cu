@@ -406,7 +406,7 @@ extern "C" int nsr_conv_fprop(const NsrConv* d, void* stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int eng = d->engine;
+  int eng = route_engine(d->engine);  // NSR_ENGINE_BF16 routes like AUTO; the tcgen05 launchers read d->engine for the pass count
   if (eng == NSR_ENGINE_AUTO) eng = forced_engine();
   if (eng == NSR_ENGINE_TCGEN05) {
     NSR_CHECK_ARG(conv_fprop_tc_supported(*d), "nsr_conv_fprop: shape not supported by the tcgen05 engine");
@@ -423,7 +423,7 @@ extern "C" int nsr_conv_fprop(const NsrConv* d, void* stream) {
 
 extern "C" size_t nsr_conv_fprop_workspace(const NsrConv* d) {
   if (!d || !narrow_gemm_enabled() || !nsr_device_supports_tcgen05()) return 0;
-  int eng = d->engine == NSR_ENGINE_AUTO ? forced_engine() : d->engine;
+  int eng = route_engine(d->engine) == NSR_ENGINE_AUTO ? forced_engine() : d->engine;
   if (eng != NSR_ENGINE_AUTO) return 0;
   return conv_narrow_gemm_workspace(*d);
 }
@@ -438,7 +438,7 @@ static int check_wgrad(const NsrWgrad* d) {
 }
 
 static bool wgrad_use_tc(const NsrWgrad* d) {
-  int eng = d->engine;
+  int eng = route_engine(d->engine);
   if (eng == NSR_ENGINE_AUTO) eng = forced_engine();
   if (eng == NSR_ENGINE_SIMT) return false;
   return conv_wgrad_tc_supported(*d);
@@ -478,7 +478,7 @@ extern "C" int nsr_conv_wgrad(const NsrWgrad* d, void* stream) {
   int rc = check_wgrad(d);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int eng = d->engine == NSR_ENGINE_AUTO ? forced_engine() : d->engine;
+  int eng = route_engine(d->engine) == NSR_ENGINE_AUTO ? forced_engine() : d->engine;
   if (eng == NSR_ENGINE_TCGEN05)
     NSR_CHECK_ARG(conv_wgrad_tc_supported(*d), "nsr_conv_wgrad: shape not supported by the tcgen05 engine");
   if (wgrad_use_tc(d)) return wgrad_use_tma(d) ? conv_wgrad_tma(*d, st) : conv_wgrad_tc(*d, st);

@@ -46,6 +46,7 @@ struct TcCfg {
 
 struct TcGeom {
   int n_tiles, m_tiles, num_tiles, cblks, nk, n_pad64;
+  int passes;  // 3: hi*hi + hi*lo + lo*hi;  1: hi*hi only (NSR_ENGINE_BF16: the lo halves are not even fetched)
   long long M;
 };
 
@@ -181,12 +182,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
           uint8_t* b_lo = b_hi + Cfg::b_bytes;
           const uint8_t* src_hi = wimg + ((size_t)(kb * 2 + 0) * nblk + (n0 >> 6)) * 8192;
           const uint8_t* src_lo = wimg + ((size_t)(kb * 2 + 1) * nblk + (n0 >> 6)) * 8192;
-          mbar_arrive_expect_tx(&full[stage], 2 * bytes + (STI ? 2 * TC_A_BYTES : 0));
+          const uint32_t halves = g.passes == 3 ? 2u : 1u;
+          mbar_arrive_expect_tx(&full[stage], halves * bytes + (STI ? halves * TC_A_BYTES : 0));
           if (STI)  // A tile = one 32 KiB block (hi image + lo image) of the split tile image
             bulk_g2s(smem + stage * Cfg::stage_bytes,
-                     reinterpret_cast<const uint8_t*>(d.x_sti) + ((mt * g.nk + kb) << 15), 2 * TC_A_BYTES, &full[stage]);
+                     reinterpret_cast<const uint8_t*>(d.x_sti) + ((mt * g.nk + kb) << 15), halves * TC_A_BYTES, &full[stage]);
           bulk_g2s(b_hi, src_hi, bytes, &full[stage]);
-          bulk_g2s(b_lo, src_lo, bytes, &full[stage]);
+          if (halves == 2) bulk_g2s(b_lo, src_lo, bytes, &full[stage]);
           if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -215,10 +217,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc(NsrConv d, TcGeo
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (2 x 16 B units) per K=16 step
             umma_bf16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+          if (g.passes == 3) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+            for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+            for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+          }
           umma_commit(&empty[stage]);  // smem stage reusable once these MMAs retire
           if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
         }
@@ -355,6 +359,7 @@ static int launch_fprop_tc(const NsrConv& d, cudaStream_t st) {
   g.cblks = pg.cblks;
   g.nk = pg.taps * pg.cblks;
   g.n_pad64 = pg.n_pad64;
+  g.passes = mma_passes(d.engine);
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + pg.f32_bytes;
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
   igemm_fprop_tc<BN, STI, WIN><<<grid, TC_THREADS, Cfg::smem_bytes, st>>>(d, g, wimg);
@@ -478,16 +483,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_wgrad_tc(NsrWgrad d, WgGe
           const uint32_t roff = (uint32_t)(pk & 127) * 128;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sb = smem + stage * Cfg::stage_bytes;
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)(np + nq) * 2 * (WG_KPIX * 128));
+          const bool lo = g.passes == 3;
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(np + nq) * (lo ? 2 : 1) * (WG_KPIX * 128));
           for (int j = 0; j < np; ++j) {
             const uint8_t* src = psti + ((pm * kbp + (size_t)(mt * 2 + j)) << 15) + roff;
             bulk_g2s(sb + j * (WG_KPIX * 128), src, WG_KPIX * 128, &full[stage]);
-            bulk_g2s(sb + Cfg::p_bytes + j * (WG_KPIX * 128), src + 16384, WG_KPIX * 128, &full[stage]);
+            if (lo) bulk_g2s(sb + Cfg::p_bytes + j * (WG_KPIX * 128), src + 16384, WG_KPIX * 128, &full[stage]);
           }
           for (int j = 0; j < nq; ++j) {
             const uint8_t* src = qsti + ((pm * kbq + (size_t)(nt * (BN / 64) + j)) << 15) + roff;
             bulk_g2s(sb + 2 * Cfg::p_bytes + j * (WG_KPIX * 128), src, WG_KPIX * 128, &full[stage]);
-            bulk_g2s(sb + 2 * Cfg::p_bytes + Cfg::q_bytes + j * (WG_KPIX * 128), src + 16384, WG_KPIX * 128, &full[stage]);
+            if (lo) bulk_g2s(sb + 2 * Cfg::p_bytes + Cfg::q_bytes + j * (WG_KPIX * 128), src + 16384, WG_KPIX * 128, &full[stage]);
           }
           if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
         }
@@ -636,10 +642,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_wgrad_tc(NsrWgrad d, WgGe
           // K = 16 pixels per MMA = two 8-row swizzle atoms = 2048 B = 128 x 16 B units
 #pragma unroll
           for (int k = 0; k < WG_KPIX / 16; ++k) umma_bf16(tmem_d, p_hi + 128 * k, q_hi + 128 * k, idesc, (kb | k) != 0);
+          if (g.passes == 3) {
 #pragma unroll
-          for (int k = 0; k < WG_KPIX / 16; ++k) umma_bf16(tmem_d, p_hi + 128 * k, q_lo + 128 * k, idesc, 1);
+            for (int k = 0; k < WG_KPIX / 16; ++k) umma_bf16(tmem_d, p_hi + 128 * k, q_lo + 128 * k, idesc, 1);
 #pragma unroll
-          for (int k = 0; k < WG_KPIX / 16; ++k) umma_bf16(tmem_d, p_lo + 128 * k, q_hi + 128 * k, idesc, 1);
+            for (int k = 0; k < WG_KPIX / 16; ++k) umma_bf16(tmem_d, p_lo + 128 * k, q_hi + 128 * k, idesc, 1);
+          }
           umma_commit(&empty[stage]);
           if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
         }
@@ -757,6 +765,7 @@ static WgPlan wg_plan(const NsrWgrad& d) {
     g.mt = (pair == 2 && g.m_tiles >= 2) || (pair == 1 && g.m_tiles >= 4) ? 2 : 1;
     if (g.mt == 2 && g.kpix == 64 && p.bn == 256) g.kpix = 32;  // that stage would not fit twice
   }
+  g.passes = mma_passes(d.engine);
   g.m_groups = (g.m_tiles + g.mt - 1) / g.mt;
   const int tiles = g.m_groups * g.n_tiles * g.taps;
   // Pixels per split: at most WG_MAX_ROWS_PER_SPLIT (the tensor-core accumulator truncates on every

@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) igemm_wgrad_sti(NsrWgrad d, WgG
         np = np > 2 * MT ? 2 * MT : np;
         int nq = kbq - nt * (BN / 64);
         nq = nq > BN / 64 ? BN / 64 : nq;
-        const uint32_t tx = (uint32_t)(np + nq) * 2 * Cfg::panel;
+        const bool lo = g.passes == 3;
+        const uint32_t tx = (uint32_t)(np + nq) * (lo ? 2 : 1) * Cfg::panel;
         for (int kb = 0; kb < nkb; ++kb) {
           const long long pk = p_begin + (long long)kb * KPIX;
           const size_t pm = (size_t)(pk >> 7);
@@ -99,12 +100,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) igemm_wgrad_sti(NsrWgrad d, WgG
           for (int j = 0; j < nq; ++j) {
             const uint8_t* src = qsti + ((pm * kbq + (size_t)(nt * (BN / 64) + j)) << 15) + roff;
             bulk_g2s(sb + 2 * Cfg::p_bytes + j * Cfg::panel, src, Cfg::panel, &full[stage]);
-            bulk_g2s(sb + 2 * Cfg::p_bytes + Cfg::q_bytes + j * Cfg::panel, src + 16384, Cfg::panel, &full[stage]);
+            if (lo) bulk_g2s(sb + 2 * Cfg::p_bytes + Cfg::q_bytes + j * Cfg::panel, src + 16384, Cfg::panel, &full[stage]);
           }
           for (int j = 0; j < np; ++j) {
             const uint8_t* src = psti + ((pm * kbp + (size_t)(mg * 2 * MT + j)) << 15) + roff;
             bulk_g2s(sb + j * Cfg::panel, src, Cfg::panel, &full[stage]);
-            bulk_g2s(sb + Cfg::p_bytes + j * Cfg::panel, src + 16384, Cfg::panel, &full[stage]);
+            if (lo) bulk_g2s(sb + Cfg::p_bytes + j * Cfg::panel, src + 16384, Cfg::panel, &full[stage]);
           }
           if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
         }
@@ -145,10 +146,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) igemm_wgrad_sti(NsrWgrad d, WgG
             // K = 16 pixels per MMA = two 8-row swizzle atoms = 2048 B = 128 x 16 B units
 #pragma unroll
             for (int k = 0; k < KPIX / 16; ++k) umma_bf16(tmem_d, p_hi + 128 * k, q_hi + 128 * k, idesc, (kb | k) != 0);
+            if (g.passes == 3) {
 #pragma unroll
-            for (int k = 0; k < KPIX / 16; ++k) umma_bf16(tmem_d, p_hi + 128 * k, q_lo + 128 * k, idesc, 1);
+              for (int k = 0; k < KPIX / 16; ++k) umma_bf16(tmem_d, p_hi + 128 * k, q_lo + 128 * k, idesc, 1);
 #pragma unroll
-            for (int k = 0; k < KPIX / 16; ++k) umma_bf16(tmem_d, p_lo + 128 * k, q_hi + 128 * k, idesc, 1);
+              for (int k = 0; k < KPIX / 16; ++k) umma_bf16(tmem_d, p_lo + 128 * k, q_hi + 128 * k, idesc, 1);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }

@@ -48,6 +48,7 @@ struct WtGeom {
   int m_tiles, n_tiles, kh, kw, pad, splitk, num_items;
   int W, H, B, bw, bh, kpix, wblocks, hblocks;
   int nblocks, blocks_per_split;
+  int passes;           // 3: hi*hi + hi*lo + lo*hi;  1: hi*hi only (NSR_ENGINE_BF16: the lo planes are not fetched)
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
@@ -135,8 +136,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) igemm_wgrad_tma(const __grid_co
           const int w0 = wb * g.bw, h0 = hb * g.bh;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sb = smem + stage * Cfg::stage_bytes;
-          mbar_arrive_expect_tx(&full[stage], 2u * ((uint32_t)np * p_box + (uint32_t)nq * q_box));
-          for (int plane = 0; plane < 2; ++plane) {
+          const int planes = g.passes == 3 ? 2 : 1;
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)planes * ((uint32_t)np * p_box + (uint32_t)nq * q_box));
+          for (int plane = 0; plane < planes; ++plane) {
             for (int j = 0; j < np; ++j)
               tma_load_5d(sb + plane * Cfg::p_bytes + j * WT_P_PANEL, &tm_p, &full[stage], mt * 128 + j * 64, w0, h0, b, plane);
             for (int j = 0; j < nq; ++j)
@@ -186,12 +188,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) igemm_wgrad_tma(const __grid_co
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (i < nk) umma_bf16(tmem_d, p_hi + poff[i], q_hi + qoff[i], idesc, first | (uint32_t)i);
+          if (g.passes == 3) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < nk) umma_bf16(tmem_d, p_hi + poff[i], q_lo + qoff[i], idesc, 1);
+            for (int i = 0; i < 4; ++i)
+              if (i < nk) umma_bf16(tmem_d, p_hi + poff[i], q_lo + qoff[i], idesc, 1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < nk) umma_bf16(tmem_d, p_lo + poff[i], q_hi + qoff[i], idesc, 1);
+            for (int i = 0; i < 4; ++i)
+              if (i < nk) umma_bf16(tmem_d, p_lo + poff[i], q_hi + qoff[i], idesc, 1);
+          }
           umma_commit(&empty[stage]);
           if (++stage == Cfg::stages) { stage = 0; phase ^= 1; }
         }
@@ -323,6 +327,7 @@ static WtPlan wt_plan(const NsrWgrad& d) {
   g.wblocks = d.w / g.bw;
   g.hblocks = d.h / g.bh;
   g.nblocks = d.batch * g.hblocks * g.wblocks;
+  g.passes = mma_passes(d.engine);
   // orientation: P tiles are 128 channels, Q tiles 64; every (P tile, Q tile) pair costs the same
   const int units_a = ((d.cout + 127) / 128) * ((d.cin + 63) / 64);   // P = dy, Q = x
   const int units_b = ((d.cin + 127) / 128) * ((d.cout + 63) / 64);   // P = x,  Q = dy

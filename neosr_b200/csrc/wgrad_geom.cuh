@@ -13,6 +13,7 @@ struct WgGeom {
   int mt;              // 128-row tiles of P per work item (1, or 2 on the STI kernel: Q is loaded once for both)
   int m_groups;        // ceil(m_tiles / mt)
   int kpix;            // pixels per k-block
+  int passes;          // 3: hi*hi + hi*lo + lo*hi;  1: hi*hi only (NSR_ENGINE_BF16)
   long long M, rows_per_split;
   const float* p_ptr;
   const float* q_ptr;

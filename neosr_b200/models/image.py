@@ -124,8 +124,15 @@ class image:
         self.eco_iters = train_opt.get("eco_iters", 80000)
         self.eco_init = train_opt.get("eco_init", 15000)
         self.pretrain = (self.opt.get("path") or {}).get("pretrain_network_g")
-        if self.opt.get("use_amp", False):
-            raise NotImplementedError("neosr_b200.image: AMP is opt-in in the reference and not built (fp32 path)")
+        # image.py:117-127: `use_amp` (+ `bfloat16`).  Here mixed precision = every tcgen05 contraction issues ONE bf16 pass
+        # (fp32 accumulate, fp32 storage; NSR_ENGINE_BF16) instead of the three of the fp32-parity split: no autocast
+        # copies and no GradScaler - bf16 has fp32's range, and gradients are formed and stored in fp32 - so the
+        # reference's scaler state is not mirrored.  float16 autocast is not built.
+        self.use_amp = self.opt.get("use_amp", False) is True
+        if self.use_amp:
+            if self.opt.get("bfloat16", False) is not True:
+                raise NotImplementedError("neosr_b200.image: use_amp needs bfloat16 = true (float16 autocast is not built)")
+            ops.DEFAULT_ENGINE = "bf16"  # process-wide, like torch.autocast in the reference's closure
         ds = self.opt.get("datasets", {}).get("train", {})
         self.accum_iters = ds.get("accumulate", 1) or 1
         if self.accum_iters != 1:

@@ -25,7 +25,14 @@ WSTI_ENABLED = os.environ.get("NSR_WSTI", "1") != "0"  # window-ordered attentio
 XWIN_TENSOR_CORES = int(os.environ.get("NSR_XWIN_TC", "3"))  # HAT window attention engine mask: bit 0 forward, bit 1 backward on mma.sync; 0 = exact fp32
 BIAS_COLUMN_ENABLED = True  # bias gradients from the ones channel of split tile images (tests flip it)
 LK16_ENABLED = True   # route 16->16-channel k>=7 convs to the dedicated large-kernel kernels (tests flip it)
-DEFAULT_ENGINE = "auto"  # what engine="auto" resolves to ("auto" | "simt" | "tcgen05"); tests flip it
+# what engine="auto" resolves to ("auto" | "simt" | "tcgen05" | "bf16"); tests flip it.  "bf16" = the mixed-precision mode of
+# `use_amp` + `bfloat16`: routed like "auto", the tcgen05 contractions issue one bf16 pass instead of three (NSR_ENGINE_BF16)
+DEFAULT_ENGINE = "auto"
+
+
+def _contraction_engine() -> int:
+    """Engine code of the wgrad helpers that always take the tcgen05 path (split-tile-image operands)."""
+    return ENGINE["bf16" if DEFAULT_ENGINE == "bf16" else "auto"]
 LAUNCHES = 0          # kernels launched through this module (claim reported by bench.py)
 PROFILE: list | None = None  # when a list: (kernel, shape-key, flops, bytes, start_evt, end_evt) per call
 
@@ -454,7 +461,7 @@ def conv_wgrad_mapped(x_sti: STI, dy_sti: STI, dw: Tensor, dbias: Tensor | None,
     B, H, W, G = x_sti.shape
     cout, cin = dw.shape[0], dw.shape[1]
     tmp = torch.empty((cout, G), dtype=torch.float32, device=dw.device)
-    d = NsrWgrad(batch=B, h=H, w=W, cin=G, cout=cout, kh=1, kw=1, pad=0, x_ld=G, dy_ld=cout, engine=ENGINE["auto"], x=None,
+    d = NsrWgrad(batch=B, h=H, w=W, cin=G, cout=cout, kh=1, kw=1, pad=0, x_ld=G, dy_ld=cout, engine=_contraction_engine(), x=None,
                  dy=None, dw=tmp.data_ptr(), dbias=None, workspace=None, workspace_bytes=0, x_sti=x_sti.data_ptr(),
                  dy_sti=dy_sti.data_ptr())
     L = _lib.lib()
@@ -486,7 +493,7 @@ def conv_wgrad_mapped_rows(x_sti: STI, dy_sti: STI, dw: Tensor, dbias: Tensor | 
         raise ValueError("conv_wgrad_mapped_rows: the input image carries no ones column for the bias gradient")
     cw = cin + 4 if fused else cin
     tmp = torch.empty((gout, cw), dtype=torch.float32, device=dw.device)
-    d = NsrWgrad(batch=B, h=H, w=W, cin=cw, cout=gout, kh=1, kw=1, pad=0, x_ld=cw, dy_ld=gout, engine=ENGINE["auto"], x=None,
+    d = NsrWgrad(batch=B, h=H, w=W, cin=cw, cout=gout, kh=1, kw=1, pad=0, x_ld=cw, dy_ld=gout, engine=_contraction_engine(), x=None,
                  dy=None, dw=tmp.data_ptr(), dbias=None, workspace=None, workspace_bytes=0, x_sti=x_sti.data_ptr(),
                  dy_sti=dy_sti.data_ptr())
     L = _lib.lib()
@@ -526,7 +533,7 @@ class DeferredWgrads:
             if not (x_sti.ones and cx % 64 != 0 and cx + 4 <= (cx + 63) // 64 * 64):
                 raise ValueError("DeferredWgrads: the input image carries no ones column for the bias gradient")
             cw, bias_col = cx + 4, cx
-        d = NsrWgrad(batch=B, h=H, w=W, cin=cw, cout=gout, kh=1, kw=1, pad=0, x_ld=cw, dy_ld=gout, engine=ENGINE["auto"],
+        d = NsrWgrad(batch=B, h=H, w=W, cin=cw, cout=gout, kh=1, kw=1, pad=0, x_ld=cw, dy_ld=gout, engine=_contraction_engine(),
                      x=None, dy=None, dw=None, dbias=None, workspace=None, workspace_bytes=0, x_sti=x_sti.data_ptr(),
                      dy_sti=dy_sti.data_ptr())
         L = _lib.lib()

@@ -385,3 +385,45 @@ def test_narrow_conv_as_gemm(B, H, W, cin, cout):
     ops.conv_wgrad(xh, dyh, dw, db, 3, 3)
     assert rel(dw, w.grad) < 5e-5
     assert rel(db, b.grad) < 1e-5
+
+
+def test_bf16_single_pass_engine_contractions():
+    """NSR_ENGINE_BF16 (`use_amp` + `bfloat16`): the same kernels with ONE bf16 pass - results within bf16 round-off of the
+    fp64 product (a few 1e-3) and clearly NOT the three-pass result (which sits at 1e-5), on every tcgen05 contraction path:
+    split-tile-image fprop / dgrad / wgrad, fp32-operand 3x3 fprop, TMA-staged 3x3 wgrad."""
+    from neosr_b200 import ops
+    B, H, W, cin, cout = 2, 32, 64, 180, 360
+    x, dy = rnd(B, H, W, cin, seed=1), rnd(B, H, W, cout, seed=5)
+    w, b = rnd(cout, cin, seed=2, scale=1 / math.sqrt(cin)), rnd(cout, seed=3, scale=0.1)
+    pw = ops.PackedWeight(w).refresh()
+    xs, dys = ops.STI.from_f32(x), ops.STI.from_f32(dy)
+    lin = F.linear(x.double(), w.double(), b.double())
+    ref_dw = dy.double().reshape(-1, cout).t() @ x.double().reshape(-1, cin)
+    w3 = rnd(64, 64, 3, 3, seed=7, scale=1 / math.sqrt(576))
+    pw3 = ops.PackedWeight(w3).refresh()
+    x3, dy3 = rnd(2, 32, 32, 64, seed=8), rnd(2, 32, 32, 64, seed=9)
+    conv3 = nhwc(F.conv2d(nchw(x3).double(), w3.double(), padding=1))
+    xr = nchw(x3).double()
+    wr = w3.double().requires_grad_(True)
+    F.conv2d(xr, wr, padding=1).backward(nchw(dy3).double())
+    errs = {}
+    for engine in ("auto", "bf16"):
+        ops.DEFAULT_ENGINE = engine
+        try:
+            e = {}
+            e["sti fprop"] = rel(ops.conv_fprop(xs, pw, b).double(), lin)
+            e["sti dgrad"] = rel(ops.conv_fprop(dys, pw, None, dgrad=True).double(), dy.double() @ w.double())
+            dw = torch.empty_like(w)
+            ops.conv_wgrad(None, None, dw, None, 1, 1, x_sti=xs, dy_sti=dys)
+            e["sti wgrad"] = rel(dw.double(), ref_dw)
+            e["3x3 fprop"] = rel(ops.conv_fprop(x3, pw3, None).double(), conv3)
+            dw3 = torch.empty_like(w3)
+            ops.conv_wgrad(x3, dy3, dw3, None, 3, 3)
+            e["3x3 wgrad"] = rel(dw3.double(), wr.grad)
+            errs[engine] = e
+        finally:
+            ops.DEFAULT_ENGINE = "auto"
+    print(errs)
+    for k in errs["auto"]:
+        assert errs["auto"][k] < 5e-5, (k, errs["auto"][k])
+        assert 2e-4 < errs["bf16"][k] < 2e-2, (k, errs["bf16"][k])

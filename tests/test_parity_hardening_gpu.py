@@ -432,6 +432,56 @@ def test_eco_and_fsam_steps_vs_oracle(variant):
         assert {"momentum", "old_p"} <= set(st)
 
 
+def test_use_amp_bfloat16_steps_track_the_fp32_oracle():
+    """`use_amp = true`, `bfloat16 = true` (image.py:117-127, 437-440): here = one bf16 tensor-core pass per contraction, fp32
+    accumulate and storage.  Four iterations of the tiny SwinIR: every loss within 2 % of the fp32 oracle's (bf16 round-off is
+    4e-3 per product term), the parameter displacement points the same way, and the step differs from the fp32-parity
+    step (the switch is live).  float16 autocast is rejected."""
+    from neosr_b200 import ops
+    from neosr_b200.archs.swinir_arch import swinir
+    from neosr_b200.models import build_model
+    from neosr_b200.registry import ARCH_REGISTRY
+    from oracle.make_golden import TINY
+    from oracle.step import displacement_report, make_swinir_trainer
+    from oracle.swinir import SwinIRConfig, swinir_param_shapes, synth_params
+    if "swinir" not in ARCH_REGISTRY:
+        ARCH_REGISTRY.register(swinir)
+    optim = dict(lr=1e-3, betas=(0.98, 0.92, 0.987), weight_decay=0.02, schedule_free=True, warmup_steps=0)
+    train = {"ema": 0.999, "optim_g": {"type": "adan_sf", **optim}, "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0}}
+    opt = {"model_type": "image", "scale": 4, "is_train": True, "dist": False, "rank": 0, "world_size": 1, "cuda_graph": False,
+           "network_g": {"type": "swinir", "drop_path_rate": 0.0, **TINY}, "datasets": {"train": {"patch_size": 16}},
+           "train": train, "path": {}}
+    with pytest.raises(NotImplementedError):
+        build_model({**opt, "use_amp": True})
+    cfg = SwinIRConfig(**TINY)
+    p0 = synth_params(swinir_param_shapes(cfg), seed=21)
+    kw = dict(pixel_weight=1.0, optim=optim, ema=0.999, scale=4)
+    tr = make_swinir_trainer(p0, cfg, **kw)
+    tr64 = make_swinir_trainer({k: v.double() for k, v in p0.items()}, cfg, **kw)
+    try:
+        model = build_model({**opt, "use_amp": True, "bfloat16": True})
+        assert ops.DEFAULT_ENGINE == "bf16"
+        model.net_g.load_state_dict(p0, strict=False)
+        g = torch.Generator().manual_seed(22)
+        worst = 0.0
+        for it in range(1, 5):
+            lq, gt = torch.rand(2, 3, 16, 16, generator=g), torch.rand(2, 3, 64, 64, generator=g)
+            model.feed_data({"lq": lq, "gt": gt})
+            model.optimize_parameters(it)
+            for t in (tr, tr64):
+                t.feed_data({"lq": lq.to(next(iter(t.params.values())).dtype), "gt": gt.to(next(iter(t.params.values())).dtype)})
+                t.optimize_parameters(it)
+            log, ref = model.get_current_log(), tr.get_current_log()
+            for k, v in ref.items():
+                worst = max(worst, abs(log[k] - v) / max(1e-3, abs(v)))
+                assert abs(log[k] - v) <= 2e-2 * max(1e-3, abs(v)), (it, k, log[k], v)
+        r = displacement_report(p0, dict(model.net_g.named_parameters()), tr.params, tr64.params)
+        print(f"amp: worst loss deviation {worst:.2e}, displacement cos {r['cos']:.4f}")
+        assert r["cos"] > 0.9 and worst > 1e-6  # same direction; and not bit-for-bit the fp32-parity path
+    finally:
+        ops.DEFAULT_ENGINE = "auto"
+
+
 def test_match_lq_colors_step_vs_oracle():
     """`train.match_lq_colors` (image.py:451-463, 484-485): the consistency loss targets the antialiased-bicubic up-sampled
     LQ (clamped to [1/255, 1]) instead of the GT; three iterations (the third replays from CUDA graphs) vs the oracle."""
