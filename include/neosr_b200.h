@@ -338,6 +338,11 @@ int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
 /* Same, with two more options for the Swin blocks' split-tile-image path: the residual-branch gradient may arrive as a
  * split tile image (dres_sti; hi + lo bf16 ~ 2^-17 relative; alternative to dres), and dx may be NULL when dx_sti is given -
  * inside a residual group the gradient of the token stream then lives in ONE format instead of fp32 + tile image. */
+/* dgamma = dbeta = NULL defers the parameter gradients: `workspace` (caller-owned until then) keeps the per-block partial sums
+ * [nsr_layernorm_bwd_blocks(rows)][2][c] (dgamma row, dbeta row), which nsr_wgrad_finalize_multi reduces as two entries
+ * {splitk = blocks, p_rows = 2, p_cols = c, cout = 1, cin = c, row_map = {0} | {1}} - one launch for every LayerNorm of a
+ * network instead of one 10 us reduction per layer. */
+int nsr_layernorm_bwd_blocks(int rows);
 int nsr_layernorm_bwd2(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        const float* dres, const void* dres_sti, float* dx, float* dgamma, float* dbeta, int rows, int c,
                        void* workspace, size_t workspace_bytes, void* dx_sti, void* stream);
@@ -392,6 +397,17 @@ int nsr_window_attn_wsti_fwd(const void* qkv_wsti, const float* bias_table, floa
 int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_table, const void* dout_wsti, float* dqkv, void* dqkv_sti,
                              int dqkv_padded, float* dbias_table, int batch, int h, int w, int c, int heads, int ws, int shift,
                              int use_mask, float scale, int engine, void* workspace, size_t workspace_bytes, void* stream);
+/* Deferred bias-table gradients: with dbias_table = NULL nsr_window_attn_wsti_bwd leaves the per-CTA partial sums of dS in
+ * `workspace` ([gx + 1][heads][64][64] floats, caller-owned until the reduction; gx = nsr_window_attn_wsti_bwd_gx(...) with the
+ * same arguments), and nsr_window_attn_dbias_multi reduces the work spaces of ANY number of layers with two launches
+ * (fixed order: deterministic) - instead of two ~9 us launches per layer. */
+typedef struct NsrAttnBiasEntry {
+  float* partial;      /* the layer's work space */
+  float* dbias_table;  /* [(2 ws - 1)^2, heads], overwritten */
+  int32_t gx, heads, ws, reserved;
+} NsrAttnBiasEntry;
+int nsr_window_attn_wsti_bwd_gx(int batch, int h, int w, int c, int heads, int ws, int dqkv_padded, int engine);
+int nsr_window_attn_dbias_multi(const NsrAttnBiasEntry* table_dev, int n_entries, int max_heads, int max_ws, void* stream);
 /* dst[r][c] = src[row_map[r]][col_map[c]]; NULL map = identity, negative entry = 0 (head-padded weight / bias copies). */
 int nsr_gather2d(const float* src, int src_ld, const int* row_map, const int* col_map, float* dst, int rows, int cols,
                  void* stream);

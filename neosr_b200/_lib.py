@@ -57,6 +57,11 @@ class NsrReduceEntry(C.Structure):
                [(n, C.c_int32) for n in ("splitk", "p_rows", "p_cols", "cout", "cin", "bias_col")] + [("block_base", C.c_int64)]
 
 
+class NsrAttnBiasEntry(C.Structure):
+    _fields_ = [("partial", C.c_void_p), ("dbias_table", C.c_void_p)] + \
+               [(n, C.c_int32) for n in ("gx", "heads", "ws", "reserved")]
+
+
 class NsrParamEntry(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("p", "g", "exp_avg", "exp_avg_sq", "exp_avg_diff", "z", "neg_pre_grad", "ema")] + \
@@ -138,12 +143,15 @@ SIGNATURES = {
     "nsr_sti_to_f32": (_i, [_p, C.c_longlong, _i, _p, _i, _p]),
     "nsr_layernorm_bwd_workspace": (_z, [_i]),
     "nsr_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _z, _p, _p]),
+    "nsr_layernorm_bwd_blocks": (_i, [_i]),
     "nsr_layernorm_bwd2": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _z, _p, _p]),
     "nsr_window_attn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p]),
     "nsr_window_attn_bwd_workspace": (_z, [_i, _i]),
     "nsr_window_attn_wsti_channels": (_i, [_i]),
     "nsr_window_attn_wsti_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "nsr_window_attn_wsti_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _z, _p]),
+    "nsr_window_attn_wsti_bwd_gx": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "nsr_window_attn_dbias_multi": (_i, [_p, _i, _i, _i, _p]),
     "nsr_gather2d": (_i, [_p, _i, _p, _p, _p, _i, _i, _p]),
     "nsr_window_attn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _z, _p, _p]),
     "nsr_loss_workspace": (_z, []),

@@ -342,6 +342,7 @@ class swinir(nn.Module):
 
         sti = ops.sti_enabled() and bool(S["blocks"]) and isinstance(S["blocks"][0][3], ops.STI)
         defer = sti and ops.DEFER_WGRAD
+        ln_def = dict(deferred=ps.deferred) if defer else {}  # LayerNorm dgamma / dbeta join the batched final reduction
 
         def split(v):  # (fp32, STI) pair or a single tensor -> (fp32 | None, STI | None)
             if isinstance(v, tuple):
@@ -415,7 +416,7 @@ class swinir(nn.Module):
             g = bwd("upsample.0", body, g)
         df0 = g  # through the `+ x` skip of conv_after_body (swinir_arch.py:1047)
         g = resi_bwd("conv_after_body", xn, g, cab_saved)
-        g = ops.layernorm_bwd(g, t_last, ps.p("norm.weight"), mun, rsn, ps.g("norm.weight"), ps.g("norm.bias"))
+        g = ops.layernorm_bwd(g, t_last, ps.p("norm.weight"), mun, rsn, ps.g("norm.weight"), ps.g("norm.bias"), key="norm", **ln_def)
         nblk = len(S["blocks"])
         bi_glob = nblk
         for li in reversed(range(len(self.layers))):
@@ -438,7 +439,7 @@ class swinir(nn.Module):
                 dln2 = bwd(pre + "mlp.fc1", ln2, dh)
                 lean = sti and ops.LN_STI_RES and ds is None
                 g1 = ops.layernorm_bwd(dln2, x1, ps.p(pre + "norm2.weight"), mu2, rs2, ps.g(pre + "norm2.weight"),
-                                       ps.g(pre + "norm2.bias"), dres=gf, sti_out=sti, f32_out=not lean)
+                                       ps.g(pre + "norm2.bias"), dres=gf, sti_out=sti, f32_out=not lean, key=pre + "norm2", **ln_def)
                 g1f = split(g1)[0] if split(g1)[0] is not None else split(g1)[1]
                 gb = scaled(g1, ds[0] if ds else None)
                 if isinstance(qkv, ops.STI):  # window-ordered operands (see engine_forward)
@@ -456,7 +457,7 @@ class swinir(nn.Module):
                     pad = att.shape[-1] != self.embed_dim  # tcgen05 attention kernels: head-padded images throughout
                     dqkv = ops.window_attn_bwd_wsti(qkv, ps.p(pre + "attn.relative_position_bias_table"), datt,
                                                     ps.g(pre + "attn.relative_position_bias_table"), self.embed_dim, heads,
-                                                    ws, shift, scale, padded_out=pad)
+                                                    ws, shift, scale, padded_out=pad, key=pre + "attn.bias_table", **ln_def)
                     if pad:  # qkv wgrad / dgrad on the head-padded dqkv image
                         qw = ps.pw_mapped(pre + "attn.qkv.weight", "qkv_rows", pre + "attn.qkv.bias",
                                           row_map=ops.head_pad_map(self.embed_dim, heads, 3))
@@ -476,12 +477,14 @@ class swinir(nn.Module):
                     dln1 = bwd(pre + "attn.qkv", ln1, dqkv)
                 g = ops.layernorm_bwd(dln1, t0, ps.p(pre + "norm1.weight"), mu1, rs1, ps.g(pre + "norm1.weight"),
                                       ps.g(pre + "norm1.bias"), dres=g1f, sti_out=sti and bi > 0,
-                                      f32_out=not (lean and bi > 0 and (S["blocks"][bi_glob - 1][-1] is None)))
+                                      f32_out=not (lean and bi > 0 and (S["blocks"][bi_glob - 1][-1] is None)),
+                                      key=pre + "norm1", **ln_def)
             g = ops.axpby(split(g)[0], 1.0, dinp, 1.0)
         if self.patch_norm:
             mu, rs = S["pe"]
             g = ops.layernorm_bwd(g, S["f0"], ps.p("patch_embed.norm.weight"), mu, rs,
-                                  ps.g("patch_embed.norm.weight"), ps.g("patch_embed.norm.bias"), dres=df0)
+                                  ps.g("patch_embed.norm.weight"), ps.g("patch_embed.norm.bias"), dres=df0,
+                                  key="patch_embed.norm", **ln_def)
         else:
             g = ops.axpby(g, 1.0, df0, 1.0)
         bwd("conv_first", S["xin"], g, need_dx=False)

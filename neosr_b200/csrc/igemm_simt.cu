@@ -350,12 +350,23 @@ __global__ void __launch_bounds__(256) colsum_sti_partial(const uint8_t* __restr
   }
 }
 
-__global__ void colsum_final(const float* __restrict__ partial, float* __restrict__ out, int blocks, int cout) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cout) return;
+// one CTA per 32 columns: 32 row groups of coalesced 128-byte loads, then a fixed-order reduction over the groups
+// (a thread per column walking all <= 592 partial rows took 32 us per call at 2 M pixels)
+__global__ void __launch_bounds__(1024) colsum_final(const float* __restrict__ partial, float* __restrict__ out, int blocks, int cout) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * cout + c];
-  out[c] = s;
+  if (c < cout)
+    for (int b = ty; b < blocks; b += 32) s += partial[(size_t)b * cout + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cout) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][tx];
+    out[c] = t;
+  }
 }
 
 int launch_wgrad_reduce(const float* partial, float* dw, int splitk, int cout, int taps, int cin, cudaStream_t st) {
@@ -385,7 +396,7 @@ int conv_bias_grad(const NsrWgrad& d, float* bias_partial, int bias_blocks, cuda
     colsum_partial<<<grid, block, 0, st>>>(d.dy, bias_partial, M, d.cout, d.dy_ld, vec);
     NSR_CHECK_LAUNCH("colsum_partial");
   }
-  colsum_final<<<ceil_div(d.cout, 128), 128, 0, st>>>(bias_partial, d.dbias, bias_blocks, d.cout);
+  colsum_final<<<ceil_div(d.cout, 32), 1024, 0, st>>>(bias_partial, d.dbias, bias_blocks, d.cout);
   NSR_CHECK_LAUNCH("colsum_final");
   return NSR_OK;
 }

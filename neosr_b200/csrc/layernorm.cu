@@ -450,10 +450,15 @@ extern "C" int nsr_layernorm_bwd2(const float* dy, const float* x, const float* 
     layernorm_bwd_kernel<<<blocks, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, partial, rows, c);
   }
   NSR_CHECK_LAUNCH("layernorm_bwd");
+  // dgamma == dbeta == NULL: the caller keeps the per-block partials [nsr_layernorm_bwd_blocks(rows)][2][c] in `workspace`
+  // and reduces them later together with other layers' (nsr_wgrad_finalize_multi: p_rows = 2, p_cols = c)
+  if (dgamma == nullptr && dbeta == nullptr) return NSR_OK;
+  NSR_CHECK_ARG(dgamma && dbeta, "nsr_layernorm_bwd: dgamma and dbeta go together");
   layernorm_bwd_final<<<ceil_div(2 * c, 32), 1024, 0, st>>>(partial, dgamma, dbeta, blocks, c);
   NSR_CHECK_LAUNCH("layernorm_bwd_final");
   return NSR_OK;
 }
+extern "C" int nsr_layernorm_bwd_blocks(int rows) { return ln_blocks(rows); }
 extern "C" int nsr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
                                  const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta, int rows,
                                  int c, void* workspace, size_t workspace_bytes, void* dx_sti, void* stream) {

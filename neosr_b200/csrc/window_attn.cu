@@ -236,6 +236,37 @@ __global__ void window_attn_dbias_kernel(const float* __restrict__ dssum, float*
   dtable[tidx * heads + head] = s;
 }
 
+// The same two steps for MANY layers in one launch each (blockIdx.y = layer): nsr_window_attn_dbias_multi
+__global__ void window_attn_dbias_sum_multi(const NsrAttnBiasEntry* __restrict__ tab) {
+  const NsrAttnBiasEntry e = tab[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // head * N*N + i*N + j
+  const int n = e.heads * WA_N * WA_N;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < e.gx; ++b) s += e.partial[(size_t)b * n + i];
+  e.partial[(size_t)e.gx * n + i] = s;  // the dssum slot behind the partials
+}
+__global__ void window_attn_dbias_multi(const NsrAttnBiasEntry* __restrict__ tab) {
+  const NsrAttnBiasEntry e = tab[blockIdx.y];
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int span = 2 * e.ws - 1;
+  if (id >= span * span * e.heads) return;
+  const float* dssum = e.partial + (size_t)e.gx * e.heads * WA_N * WA_N;
+  const int head = id % e.heads, tidx = id / e.heads;
+  const int dy = tidx / span - (e.ws - 1), dx = tidx % span - (e.ws - 1);
+  float s = 0.f;
+  for (int jy = 0; jy < e.ws; ++jy) {
+    const int iy = jy + dy;
+    if (iy < 0 || iy >= e.ws) continue;
+    for (int jx = 0; jx < e.ws; ++jx) {
+      const int ix = jx + dx;
+      if (ix < 0 || ix >= e.ws) continue;
+      s += dssum[(size_t)head * WA_N * WA_N + (iy * e.ws + ix) * WA_N + jy * e.ws + jx];
+    }
+  }
+  e.dbias_table[tidx * e.heads + head] = s;
+}
+
 bool window_attn_mma_supported(int c, int heads, int ws);
 int window_attn_fwd_mma_launch(const float* qkv, const float* table, float* out, void* out_sti, int batch, int h, int w,
                                int c, int heads, int ws, int shift, int use_mask, float scale, cudaStream_t st);
@@ -391,7 +422,7 @@ extern "C" int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_
                                         void* dqkv_sti, int dqkv_padded, float* dbias_table, int batch, int h, int w, int c,
                                         int heads, int ws, int shift, int use_mask, float scale, int engine, void* workspace,
                                         size_t workspace_bytes, void* stream) {
-  NSR_CHECK_ARG(qkv_wsti && bias_table && dout_wsti && (dqkv || dqkv_sti) && dbias_table, "nsr_window_attn_wsti_bwd: null pointer");
+  NSR_CHECK_ARG(qkv_wsti && bias_table && dout_wsti && (dqkv || dqkv_sti), "nsr_window_attn_wsti_bwd: null pointer");
   NSR_CHECK_ARG(engine == NSR_ENGINE_AUTO || engine == NSR_ENGINE_TCGEN05 || engine == NSR_ENGINE_MMA_SYNC,
                 "nsr_window_attn_wsti_bwd: engine must be NSR_ENGINE_AUTO, _TCGEN05 or _MMA_SYNC");
   NSR_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv_wsti) | reinterpret_cast<uintptr_t>(dout_wsti)) & 15) == 0,
@@ -421,11 +452,32 @@ extern "C" int nsr_window_attn_wsti_bwd(const void* qkv_wsti, const float* bias_
     rc = window_attn_wsti_bwd_launch(qkv_wsti, bias_table, dout_wsti, dqkv, dqkv_sti, partial, gx, batch, h, w, c, heads, ws,
                                      shift, use_mask, scale, st);
   if (rc) return rc;
+  // dbias_table == NULL: the caller keeps `workspace` ([gx + 1][heads][64][64]: per-CTA partials of dS, one scratch slot)
+  // and reduces it later together with the other layers' (nsr_window_attn_dbias_multi, gx = nsr_window_attn_wsti_bwd_gx)
+  if (dbias_table == nullptr) return NSR_OK;
   float* dssum = partial + (size_t)gx * heads * WA_N * WA_N;
   window_attn_dbias_sum<<<ceil_div(heads * WA_N * WA_N, 256), 256, 0, st>>>(partial, dssum, gx, heads);
   NSR_CHECK_LAUNCH("window_attn_dbias_sum");
   const int n = (2 * ws - 1) * (2 * ws - 1) * heads;
   window_attn_dbias_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dssum, dbias_table, heads, ws);
   NSR_CHECK_LAUNCH("window_attn_dbias");
+  return NSR_OK;
+}
+
+extern "C" int nsr_window_attn_wsti_bwd_gx(int batch, int h, int w, int c, int heads, int ws, int dqkv_padded, int engine) {
+  if (ws <= 0 || h % ws || w % ws) return 0;
+  const int nwin = batch * (h / ws) * (w / ws);
+  const bool use_tc = engine != NSR_ENGINE_MMA_SYNC && window_attn_tc_supported(c, heads, ws) && dqkv_padded;
+  return use_tc ? window_attn_tc_bwd_gx(heads) : bwd_gx(nwin, heads, true);
+}
+extern "C" int nsr_window_attn_dbias_multi(const NsrAttnBiasEntry* table_dev, int n_entries, int max_heads, int max_ws, void* stream) {
+  NSR_CHECK_ARG(table_dev && n_entries > 0 && n_entries <= 65535 && max_heads > 0 && max_ws > 0 && max_ws * max_ws <= WA_N,
+                "nsr_window_attn_dbias_multi: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  window_attn_dbias_sum_multi<<<dim3(ceil_div(max_heads * WA_N * WA_N, 256), n_entries), 256, 0, st>>>(table_dev);
+  NSR_CHECK_LAUNCH("window_attn_dbias_sum_multi");
+  const int n = (2 * max_ws - 1) * (2 * max_ws - 1) * max_heads;
+  window_attn_dbias_multi<<<dim3(ceil_div(n, 128), n_entries), 128, 0, st>>>(table_dev);
+  NSR_CHECK_LAUNCH("window_attn_dbias_multi");
   return NSR_OK;
 }

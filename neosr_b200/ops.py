@@ -518,6 +518,7 @@ class DeferredWgrads:
 
     def __init__(self):
         self.jobs: list = []
+        self.attn_jobs: list = []  # window-attention bias-table gradients (nsr_window_attn_dbias_multi)
         self.buffers: dict = {}
         self.tables: dict = {}
 
@@ -555,7 +556,27 @@ class DeferredWgrads:
                               splitk=splitk.value, p_rows=gout, p_cols=cw, cout=cout, cin=cin,
                               bias_col=-1 if bias_col is None else bias_col))
 
+    def _finalize_attn(self) -> None:
+        jobs, self.attn_jobs = self.attn_jobs, []
+        key = ("attn",) + tuple(tuple(j.values()) for j in jobs)
+        ent = self.tables.get(key)
+        if ent is None:
+            arr = (_lib.NsrAttnBiasEntry * len(jobs))()
+            for i, j in enumerate(jobs):
+                for k, v in j.items():
+                    setattr(arr[i], k, v)
+            dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(torch.device("cuda", torch.cuda.current_device()))
+            ent = self.tables[key] = (dev, len(jobs), max(j["heads"] for j in jobs), max(j["ws"] for j in jobs))
+            if len(self.tables) > 8:
+                self.tables.pop(next(iter(self.tables)))
+        dev, n, mh, mw = ent
+        with _prof("nsr_window_attn_dbias_multi", (n,), 0.0, 0.0):
+            check(_lib.lib().nsr_window_attn_dbias_multi(dev.data_ptr(), n, mh, mw, _stream()), "nsr_window_attn_dbias_multi")
+        _count(2)
+
     def finalize(self) -> None:
+        if self.attn_jobs:
+            self._finalize_attn()
         if not self.jobs:
             return
         jobs, self.jobs = self.jobs, []
@@ -572,7 +593,7 @@ class DeferredWgrads:
                 base += L.nsr_reduce_entry_blocks(j["cout"], j["cin"])
             dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(torch.device("cuda", torch.cuda.current_device()))
             ent = self.tables[key] = (dev, len(jobs), base)
-            if len(self.tables) > 4:
+            if len(self.tables) > 8:
                 self.tables.pop(next(iter(self.tables)))
         dev, n, blocks = ent
         with _prof("nsr_wgrad_finalize_multi", (n,), 0.0, 0.0):
@@ -933,8 +954,10 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, sti
 
 
 def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dgamma: Tensor, dbeta: Tensor,
-                  dres: "Tensor | STI | None" = None, sti_out: bool = False, f32_out: bool = True):
-    """dx = LN'(dy) + dres as fp32, as an STI, or (fp32, STI) per f32_out / sti_out; dres may be fp32 or an STI."""
+                  dres: "Tensor | STI | None" = None, sti_out: bool = False, f32_out: bool = True,
+                  deferred: "DeferredWgrads | None" = None, key=None):
+    """dx = LN'(dy) + dres as fp32, as an STI, or (fp32, STI) per f32_out / sti_out; dres may be fp32 or an STI.
+    deferred (+ key): dgamma / dbeta are written by `deferred.finalize()` together with the weight gradients."""
     for t, n in ((dy, "dy"), (x, "x"), (gamma, "gamma"), (mean, "mean"), (rstd, "rstd"), (dgamma, "dgamma"),
                  (dbeta, "dbeta")):
         _chk(t, n)
@@ -950,12 +973,27 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
     dx = torch.empty_like(x) if f32_out else None
     dx_sti = STI(x.shape, x.device) if sti_out else None
     L = _lib.lib()
-    ws = scratch(L.nsr_layernorm_bwd_workspace(c), x.device)
+    need = L.nsr_layernorm_bwd_workspace(c)
+    if deferred is not None:
+        ws = deferred.buffers.get(key)
+        if ws is None or ws.numel() < need:
+            ws = deferred.buffers[key] = torch.empty(need, dtype=torch.uint8, device=x.device)
+    else:
+        ws = scratch(need, x.device)
     with _prof("nsr_layernorm_bwd", (rows, c), 0.0, (16.0 if dres is not None else 12.0) * x.numel()):
         check(L.nsr_layernorm_bwd2(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(res_f32),
-                                   _p(res_sti), _p(dx), dgamma.data_ptr(), dbeta.data_ptr(), rows, c, ws.data_ptr(), ws.numel(),
+                                   _p(res_sti), _p(dx), None if deferred is not None else dgamma.data_ptr(),
+                                   None if deferred is not None else dbeta.data_ptr(), rows, c, ws.data_ptr(), ws.numel(),
                                    _p(dx_sti), _stream()), "nsr_layernorm_bwd")
-    _count(2)
+    if deferred is not None:
+        blocks = L.nsr_layernorm_bwd_blocks(rows)
+        for row, out in ((0, dgamma), (1, dbeta)):
+            deferred.jobs.append(dict(partial=ws.data_ptr(), dw=out.data_ptr(), dbias=None,
+                                      row_map=_const_i32((row,), x.device).data_ptr(), col_map=None, splitk=blocks, p_rows=2,
+                                      p_cols=c, cout=1, cin=c, bias_col=-1))
+        _count(1)
+    else:
+        _count(2)
     return dx if dx_sti is None else (dx_sti if dx is None else (dx, dx_sti))
 
 
@@ -1021,21 +1059,37 @@ def window_attn_fwd_wsti(qkv: STI, table: Tensor, c: int, heads: int, ws: int, s
 
 
 def window_attn_bwd_wsti(qkv: STI, table: Tensor, dout: STI, dtable: Tensor, c: int, heads: int, ws: int, shift: int,
-                         scale: float, sti_out: bool = True, engine: str | None = None, padded_out: bool = False):
+                         scale: float, sti_out: bool = True, engine: str | None = None, padded_out: bool = False,
+                         deferred: "DeferredWgrads | None" = None, key=None):
     """dqkv in natural token order from the window-ordered qkv / dout images; dtable overwritten.  STI [B,H,W,3c]
-    (or [B,H,W,3G] head-padded when padded_out: tcgen05 kernel) or fp32 [B,H,W,3c]."""
+    (or [B,H,W,3G] head-padded when padded_out: tcgen05 kernel) or fp32 [B,H,W,3c].
+    deferred (+ key): dtable is written by `deferred.finalize()`, for all layers at once."""
     _chk(table, "table"), _chk(dtable, "dtable")
     B, H, W, g3 = qkv.shape
     dqkv_sti = STI((B, H, W, g3 if padded_out else 3 * c), qkv.device) if sti_out else None
     dqkv = None if sti_out else torch.empty((B, H, W, 3 * c), dtype=torch.float32, device=qkv.device)
     L = _lib.lib()
-    wsb = scratch(L.nsr_window_attn_bwd_workspace(heads, ws), qkv.device)
+    need = L.nsr_window_attn_bwd_workspace(heads, ws)
+    eng = ENGINE[engine or WSTI_ATTN_ENGINE]
+    if deferred is not None:
+        wsb = deferred.buffers.get(key)
+        if wsb is None or wsb.numel() < need:
+            wsb = deferred.buffers[key] = torch.empty(need, dtype=torch.uint8, device=qkv.device)
+    else:
+        wsb = scratch(need, qkv.device)
     with _prof("nsr_window_attn_wsti_bwd", (B * H * W, c, heads, ws), 0.0, 4.0 * B * H * W * (g3 + g3 // 3 + 3 * c)):
         check(L.nsr_window_attn_wsti_bwd(qkv.data_ptr(), table.data_ptr(), dout.data_ptr(), _p(dqkv), _p(dqkv_sti),
-                                         int(padded_out and sti_out), dtable.data_ptr(), B, H, W, c, heads, ws, shift,
-                                         1 if shift > 0 else 0, scale, ENGINE[engine or WSTI_ATTN_ENGINE], wsb.data_ptr(),
-                                         wsb.numel(), _stream()), "nsr_window_attn_wsti_bwd")
-    _count(3)
+                                         int(padded_out and sti_out), None if deferred is not None else dtable.data_ptr(), B, H, W,
+                                         c, heads, ws, shift, 1 if shift > 0 else 0, scale, eng, wsb.data_ptr(), wsb.numel(),
+                                         _stream()), "nsr_window_attn_wsti_bwd")
+    if deferred is not None:
+        gx = L.nsr_window_attn_wsti_bwd_gx(B, H, W, c, heads, ws, int(padded_out and sti_out), eng)
+        if gx <= 0 or (gx + 1) * heads * 4096 * 4 > wsb.numel():
+            raise RuntimeError("window_attn_bwd_wsti: inconsistent deferred work space")
+        deferred.attn_jobs.append(dict(partial=wsb.data_ptr(), dbias_table=dtable.data_ptr(), gx=gx, heads=heads, ws=ws, reserved=0))
+        _count(1)
+    else:
+        _count(3)
     return dqkv_sti if sti_out else dqkv
 
 
