@@ -160,3 +160,48 @@ def test_window_ordered_sti_row_and_channel_layout():
     assert torch.equal(win.reshape(-1, win.shape[-1]), want.reshape(-1, want.shape[-1]))
     m = torch.tensor(ops.head_pad_map(C, heads, 3))
     assert torch.equal(tok[..., m < 0], torch.zeros_like(tok[..., m < 0]))  # head padding is exactly zero
+
+
+def test_deferred_reductions_match_the_immediate_ones():
+    """LayerNorm dgamma / dbeta and the attention bias-table gradient reduced LATER, batched over layers
+    (`DeferredWgrads.finalize`: nsr_wgrad_finalize_multi + nsr_window_attn_dbias_multi), against the per-layer reductions of
+    the same partial sums; two layers of different size in one batch."""
+    from neosr_b200 import ops
+    ws = 8
+    g = torch.Generator().manual_seed(5)
+    deferred = ops.DeferredWgrads()
+    want = []
+    for li, (B, H, W, C, heads, shift) in enumerate([(2, 16, 24, 36, 3, 4), (1, 32, 32, 180, 6, 0)]):
+        if not ops.wsti_supported(C, heads, ws):
+            pytest.skip("needs the tcgen05 engine")
+        scale = (C // heads) ** -0.5
+        x = (torch.randn(B, H, W, C, generator=g) * 1.5 + 0.2).cuda()
+        gm, bt = (torch.randn(C, generator=g) * 0.2 + 1).cuda(), (torch.randn(C, generator=g) * 0.1).cuda()
+        dy, dres = torch.randn(B, H, W, C, generator=g).cuda(), torch.randn(B, H, W, C, generator=g).cuda()
+        _, mu, rs = ops.layernorm_fwd(x, gm, bt)
+        dg0, db0 = torch.empty_like(gm), torch.empty_like(bt)
+        dx0 = ops.layernorm_bwd(dy, x, gm, mu, rs, dg0, db0, dres=dres)
+        dg1, db1 = torch.full_like(gm, float("nan")), torch.full_like(bt, float("nan"))
+        dx1 = ops.layernorm_bwd(dy, x, gm, mu, rs, dg1, db1, dres=dres, deferred=deferred, key=f"ln{li}")
+        assert torch.equal(dx0, dx1)
+        # attention: window-ordered operands as in test_wsti_attention_forward_backward
+        wq = (torch.randn(3 * C, C, generator=g) * C ** -0.5).cuda()
+        bq = (torch.randn(3 * C, generator=g) * 0.1).cuda()
+        table = (torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5).cuda()
+        dout = torch.randn(B, H, W, C, generator=g).cuda()
+        qw = ops.MappedPackedWeight(wq, bq, row_map=ops.head_pad_map(C, heads, 3), need_dgrad=False).refresh()
+        qkv_w = ops.conv_fprop(ops.STI.from_f32(x), qw, qw.bias_padded, sti_out=True, f32_out=False, sti_win=(ws, shift))
+        pw = ops.MappedPackedWeight(torch.eye(C, device="cuda"), None, col_map=ops.head_pad_map(C, heads, 1)).refresh()
+        dout_w = ops.conv_fprop(ops.STI.from_f32(dout), pw, None, dgrad=True, sti_out=True, f32_out=False, sti_win=(ws, shift))
+        dt0 = torch.zeros_like(table)
+        dq0 = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, dt0, C, heads, ws, shift, scale, sti_out=True, padded_out=True)
+        dt1 = torch.full_like(table, float("nan"))
+        dq1 = ops.window_attn_bwd_wsti(qkv_w, table, dout_w, dt1, C, heads, ws, shift, scale, sti_out=True, padded_out=True,
+                                       deferred=deferred, key=f"attn{li}")
+        assert torch.equal(dq0.to_f32(), dq1.to_f32())
+        want.append((dg0, db0, dt0, dg1, db1, dt1))
+    assert all(bool(torch.isnan(t).all()) for w in want for t in w[3:])  # nothing written before the batched reduction
+    deferred.finalize()
+    for dg0, db0, dt0, dg1, db1, dt1 in want:
+        assert rel(dg1, dg0) < 1e-5 and rel(db1, db0) < 1e-5  # same partial sums, different (fixed) summation order
+        assert torch.equal(dt1, dt0)  # same two-step reduction, batched
