@@ -133,6 +133,8 @@ class image:
             if self.opt.get("bfloat16", False) is not True:
                 raise NotImplementedError("neosr_b200.image: use_amp needs bfloat16 = true (float16 autocast is not built)")
             ops.DEFAULT_ENGINE = "bf16"  # process-wide, like torch.autocast in the reference's closure
+        elif ops.DEFAULT_ENGINE == "bf16":
+            ops.DEFAULT_ENGINE = "auto"  # a model without use_amp built after one with it gets the fp32-parity engine back
         ds = self.opt.get("datasets", {}).get("train", {})
         self.accum_iters = ds.get("accumulate", 1) or 1
         if self.accum_iters != 1:
